@@ -1,0 +1,194 @@
+/*
+ * udape.h — C-ABI of the B200-native (sm_100a) hot path of the mean-teacher + AdaIN
+ * domain-adaptive pose trainer (reference: VisionLearningGroup/UDA_PoseEstimation).
+ *
+ * The reference has no FFI of its own: its "operator API" is a set of Python callables
+ * (SURVEY.md §8b).  Every entry point below replaces one of those callables and cites
+ * it as  <file>:<lines>  relative to the reference tree.  The Python package
+ * uda_poseestimation_b200 binds these symbols with ctypes and re-exports the reference
+ * names/signatures; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions (all entry points):
+ *   - plain C types only; device pointers are raw `void*` owned by the caller;
+ *   - the library never allocates, frees or retains device memory and keeps no global
+ *     mutable state except a thread-local last-error string;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream) of the calling thread's current device, asynchronously, with no
+ *     host synchronisation — every call is CUDA-graph capturable;
+ *   - tensors are dense, row-major NCHW ("planes" = N*C or B*K leading items, each a
+ *     contiguous H*W plane);
+ *   - return 0 on success, a negative UDAPE_ERR_* for argument errors, a positive
+ *     cudaError_t for launch failures; udape_last_error() returns the message.
+ *   - there is NO CPU fallback: without a CUDA device the calls fail with a cudaError_t.
+ */
+#ifndef UDAPE_H_
+#define UDAPE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UDAPE_VERSION 100 /* major*10000 + minor*100 + patch */
+
+#if defined(__GNUC__)
+#define UDAPE_API __attribute__((visibility("default")))
+#else
+#define UDAPE_API
+#endif
+
+/* element type codes */
+enum {
+    UDAPE_F32 = 0,
+    UDAPE_F16 = 1,
+    UDAPE_BF16 = 2,
+    UDAPE_U8 = 3 /* bool / uint8 masks */
+};
+
+/* error codes (negative); positive return values are cudaError_t */
+enum {
+    UDAPE_OK = 0,
+    UDAPE_ERR_NULL = -1,   /* required pointer is NULL */
+    UDAPE_ERR_DTYPE = -2,  /* unsupported element type code */
+    UDAPE_ERR_SHAPE = -3,  /* non-positive / inconsistent extent */
+    UDAPE_ERR_ALIGN = -4,  /* pointer not aligned to its element size */
+    UDAPE_ERR_ARG = -5     /* scalar argument out of range */
+};
+
+/* ---- library ------------------------------------------------------------------- */
+UDAPE_API int udape_version(void);
+/* "udape-b200 <ver> sm_100a cuda <ver>" */
+UDAPE_API const char* udape_build_info(void);
+/* copies the calling thread's last error message (NUL-terminated) into buf; returns its length */
+UDAPE_API int udape_last_error(char* buf, size_t buf_bytes);
+
+/* ---- a1: calc_mean_std — adain/function.py:3-11, lib/models/Style_net.py:4-12 ------
+ * mean[p] = mean(feat[p,:]); std[p] = sqrt(var_unbiased(feat[p,:]) + eps), p < planes.
+ * mean/std are written in `dtype` (the reference returns feat's dtype).  hw == 1 gives
+ * std = NaN exactly as torch's unbiased var does. */
+UDAPE_API int udape_mean_std(const void* feat, int dtype, int64_t planes, int64_t hw, float eps,
+                   void* mean, void* std, void* stream);
+
+/* ---- a2+a3: adaptive_instance_normalization (+ alpha mix) ---------------------------
+ * adain/function.py:14-22, lib/models/Style_net.py:21-29 and :167-168.
+ * out[p,i] = alpha * ((c[p,i]-mean_c[p])/std_c[p]*std_s[p]+mean_s[p]) + (1-alpha)*c[p,i]
+ * content has hw_c elements per plane, style hw_s (only N,C must agree, function.py:15).
+ * alpha = 1 reproduces plain AdaIN.  If alpha_dev != NULL the scalar is read from that
+ * device address instead (so a captured CUDA graph can change alpha between replays). */
+UDAPE_API int udape_adain_mix(const void* content, const void* style, int dtype, int64_t planes,
+                    int64_t hw_c, int64_t hw_s, float eps, float alpha,
+                    const float* alpha_dev, void* out, void* stream);
+
+/* ---- a7 + a11 + a6: heatmap decode — lib/keypoint_detection.py:9-37 (get_max_preds),
+ * utils.py:54-75 (get_max_preds_torch), train_human.py:376-383 (conf / pred_position /
+ * conf_table), utils.py:77-109 (rectify).
+ * Per plane p (= b*K+k) of hm[planes,h,w]: flat argmax with first-index tie-break and
+ * NaN-is-maximum (numpy/torch semantics).  Every output pointer is optional (NULL = skip):
+ *   idx[p]            int32 flat argmax
+ *   preds[p,2]        float32 (x,y) = (idx % w, idx / w), zeroed when max <= 0 (or NaN)
+ *   maxvals[p]        max in hm's dtype;  maxvals_f32[p] the same value as float32
+ *   position[p,2]     int64 (x,y), never masked (train_human.py:380-381)
+ *   conf_table[p]     uint8, max >= occlude_thresh (train_human.py:383)
+ *   rectified[planes,h,w]  in hm's dtype: zeros + the (6*sigma+1)^2 unit-peak Gaussian
+ *                     pasted at (preds.x, preds.y) with rectify's clipping rules. */
+UDAPE_API int udape_decode(const void* hm, int dtype, int64_t planes, int64_t h, int64_t w,
+                 int32_t* idx, float* preds, void* maxvals, float* maxvals_f32,
+                 int64_t* position, float occlude_thresh, uint8_t* conf_table,
+                 double sigma, void* rectified, void* stream);
+
+/* ---- a11: consistency mask — train_human.py:427-430 ----------------------------------
+ * thresh = kth smallest (1-based kth, NaN sorts last: torch.kthvalue) of activates[n];
+ * tea_mask_out[i] = (tea_mask_in[i] * activates[i]) > thresh   (tea_mask_in NULL = ones).
+ * thresh_out (device float, optional) receives the threshold; no host sync. */
+UDAPE_API int udape_mask_select(const float* activates, int64_t n, int64_t kth,
+                      const float* tea_mask_in, float* thresh_out, uint8_t* tea_mask_out,
+                      void* stream);
+
+/* ---- a8: PCK counts — lib/keypoint_detection.py:40-94 (calc_dists, dist_acc, accuracy)
+ * Decodes output[B,K,h,w] and target[B,K,h,w] (dtypes may differ), then per (b,k):
+ * valid iff target (x>1 and y>1); hit iff ||pred/norm - target/norm||_2 < thr evaluated
+ * in float64 with norm = (h/10, w/10) applied to (x, y) as the reference does (:79).
+ * hits[K], valid[K] (int32) are zeroed by the call and accumulated with integer atomics,
+ * so results are order-independent.  pred[B,K,2] (float32, optional) = decoded output
+ * coordinates (accuracy()'s 4th return value); tgt[B,K,2] optional likewise. */
+UDAPE_API int udape_pck_counts(const void* output, int out_dtype, const void* target, int tgt_dtype,
+                     int64_t batch, int64_t joints, int64_t h, int64_t w, double thr,
+                     float* pred, float* tgt, int32_t* hits, int32_t* valid, void* stream);
+
+/* ---- a9: JointsMSELoss — lib/models/loss.py:11-49 ------------------------------------
+ * fwd: plane_loss[p] = weight[p] * 0.5 * mean_i (o[p,i]-t[p,i])^2   (reduction='none');
+ *      *loss_mean = mean_p plane_loss[p]                             (reduction='mean').
+ * weight (optional, [planes]) may be f32/f16/bf16.  plane_loss is required (it doubles as
+ * the deterministic reduction scratch); loss_mean optional; ticket = 4 zero-able bytes of
+ * scratch (the call zeroes it).
+ * bwd: grad_in[p,i] = c[p] * weight[p] * (o-t), c[p] = grad_out[0]/(planes*hw) for 'mean'
+ * (grad_per_plane=0) or grad_out[p]/hw for 'none' (grad_per_plane=1); grad_out is a device
+ * float pointer; grad_in is written in out_dtype. */
+UDAPE_API int udape_joints_mse_fwd(const void* output, int out_dtype, const void* target, int tgt_dtype,
+                         const void* weight, int w_dtype, int64_t planes, int64_t hw,
+                         float* plane_loss, float* loss_mean, uint32_t* ticket, void* stream);
+UDAPE_API int udape_joints_mse_bwd(const void* output, int out_dtype, const void* target, int tgt_dtype,
+                         const void* weight, int w_dtype, int64_t planes, int64_t hw,
+                         const float* grad_out, int grad_per_plane, void* grad_in,
+                         void* stream);
+
+/* ---- a10: ConsLoss — lib/models/loss.py:119-132 --------------------------------------
+ * diff = (stu - tea) * tea_mask[b,k];  loss_map[b,i] = mean_k diff^2;
+ * loss = mean over (b,i) (only where valid_mask[b,i] != 0 when valid_mask is given).
+ * tea_mask optional [B*K] u8 or f32; valid_mask optional [B*hw] u8.
+ * plane_partial[B*K] (float scratch), valid_count (int32 scratch, written when valid_mask
+ * is given), ticket (4 bytes scratch) are caller-owned.  bwd writes
+ * grad_stu = 2*g*diff*mask/(K*Nvalid) (0 where invalid) in stu_dtype. */
+UDAPE_API int udape_cons_fwd(const void* stu, int stu_dtype, const void* tea, int tea_dtype,
+                   const void* tea_mask, int mask_dtype, const uint8_t* valid_mask,
+                   int64_t batch, int64_t joints, int64_t hw, float* plane_partial,
+                   int32_t* valid_count, float* loss, uint32_t* ticket, void* stream);
+UDAPE_API int udape_cons_bwd(const void* stu, int stu_dtype, const void* tea, int tea_dtype,
+                   const void* tea_mask, int mask_dtype, const uint8_t* valid_mask,
+                   int64_t batch, int64_t joints, int64_t hw, const float* grad_out,
+                   const int32_t* valid_count, void* grad_stu, void* stream);
+
+/* ---- a4: generate_target (batched) — lib/datasets/util.py:12-70 ----------------------
+ * joints[planes,2] float64 image pixels, vis[planes] float32.  mu = trunc(j/stride+0.5)
+ * in float64, stride = image/heatmap; out of bounds -> weight 0; window pasted iff
+ * weight > 0.5.  target[planes,hm_h,hm_w] float32 (fully written), weight[planes] f32. */
+UDAPE_API int udape_gauss_target(const double* joints, const float* vis, int64_t planes, int64_t hm_w,
+                       int64_t hm_h, double sigma, double image_w, double image_h,
+                       float* target, float* weight, void* stream);
+
+/* ---- a5: draw_labelmap_ori (batched) — lib/datasets/util.py:326-363 ------------------
+ * pts[planes,2] int32 (already truncated as pt.to(int32)).  A window touching the border
+ * is rejected (vis_out=0, plane untouched/zero).  kind 0 = Gaussian, 1 = Cauchy, evaluated
+ * in float64 and stored as float32.  zero_fill != 0: write the whole plane (zeros +
+ * window); zero_fill == 0: overwrite only the window inside the existing img (in place). */
+UDAPE_API int udape_labelmap(const int32_t* pts, int64_t planes, int64_t h, int64_t w, double sigma,
+                   int kind, int zero_fill, float* img, int32_t* vis_out, void* stream);
+
+/* ---- a12/a13: EMA teacher update — utils.py:9-25 (OldWeightEMA), lib/models/ema.py ----
+ * A chunk is a contiguous run of one parameter tensor.  udape_ema_plan (host-only helper,
+ * no CUDA) splits n_tensors tensors of elem_bytes-sized elements into chunks of
+ * <= chunk_elems elements and writes them to out[capacity]; returns the number of chunks
+ * (the number required if capacity is too small / out is NULL), negative on error.  The caller copies the table to device
+ * memory once and passes it to udape_ema_multi every step.
+ * mode 0: dst = dst*a + src*b with three roundings (mul, mul, add — bit-identical to the
+ *         reference's  p.mul_(alpha); p.add_(src*(1-alpha))  in fp32);
+ * mode 1: dst = src (ModelEMA buffer copy, ema.py:31-36). `numel` counts elements of
+ *         `dtype` (use UDAPE_U8 with byte counts to copy buffers of any type). */
+typedef struct udape_ema_chunk {
+    void* dst;
+    const void* src;
+    int64_t numel;
+} udape_ema_chunk;
+
+UDAPE_API int64_t udape_ema_plan(void* const* dst, const void* const* src, const int64_t* numel,
+                       int64_t n_tensors, int64_t elem_bytes, int64_t chunk_elems,
+                       udape_ema_chunk* out, int64_t capacity);
+UDAPE_API int udape_ema_multi(const udape_ema_chunk* chunks_dev, int64_t n_chunks, int64_t chunk_elems,
+                    float a, float b, int dtype, int mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UDAPE_H_ */

@@ -1,0 +1,300 @@
+"""Generates tests/golden/*.npz by running the REAL reference functions (imported by file
+path from /root/reference, see oracle/ref_loader.py) on small seeded inputs.
+
+Run in the build container only (the reference tree does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The fixtures store inputs AND the reference's outputs, so they are self-contained:
+``tests/test_oracle_golden.py`` replays them against ``oracle/reference_port.py`` on the CPU
+and ``tests/test_gpu_golden.py`` replays them against the CUDA operators on the GPU box.
+The two inline trainer fragments that are not functions (train_human.py:376-383 and
+:427-430) are executed here verbatim as expressions.
+"""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+
+from oracle import ref_loader  # noqa: E402
+from uda_poseestimation_b200 import synthetic  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+
+
+def save(name, **arrays):
+    clean = {}
+    for k, v in arrays.items():
+        if torch.is_tensor(v):
+            v = v.detach().cpu().numpy()
+        clean[k] = np.asarray(v)
+    np.savez_compressed(OUT / f"{name}.npz", **clean)
+    size = (OUT / f"{name}.npz").stat().st_size
+    print(f"{name}.npz  {size / 1024:.1f} KiB  keys={sorted(clean)}")
+
+
+def golden_adain():
+    fn = ref_loader.load("function")
+    sn = ref_loader.load("style_net")
+    out = {}
+    cases = {"a": (2, 8, 32, 32, 32, 32), "b": (2, 3, 5, 7, 5, 7), "c": (1, 4, 16, 16, 8, 8), "d": (2, 2, 33, 31, 17, 3)}
+    for tag, (n, c, hc, wc, hs, ws) in cases.items():
+        g = torch.Generator().manual_seed(100 + ord(tag))
+        content = torch.relu(torch.randn(n, c, hc, wc, generator=g) + 0.2)
+        style = torch.relu(torch.randn(n, c, hs, ws, generator=g) * 2 + 0.5)
+        mean, std = fn.calc_mean_std(content)
+        out[f"{tag}_content"], out[f"{tag}_style"] = content, style
+        out[f"{tag}_mean"], out[f"{tag}_std"] = mean, std
+        t = fn.adaptive_instance_normalization(content, style)
+        assert torch.equal(t, sn.adain(content, style))
+        out[f"{tag}_adain"] = t
+        for alpha in (0.0, 0.37, 1.0):
+            # Style_net.py:167-168
+            t2 = sn.adain(content, style)
+            t2 = alpha * t2 + (1 - alpha) * content
+            out[f"{tag}_mix_{alpha}"] = t2
+    save("adain", **out)
+
+
+def golden_decode():
+    kd = ref_loader.load("keypoint_detection")
+    ut = ref_loader.load("utils")
+    out = {}
+    hm = synthetic.heatmaps(2, 4, seed=11, peak=(0.2, 1.1))
+    adv = synthetic.adversarial_heatmaps(k=3, h=16, w=16, seed=5)
+    odd = synthetic.heatmaps(2, 3, seed=12, h=9, w=13)
+    for tag, t in (("hm", hm), ("adv", adv), ("odd", odd)):
+        for dt_name, dt in (("f32", torch.float32), ("f16", torch.float16)):
+            x = t.to(dt)
+            preds, maxvals = kd.get_max_preds(x.numpy())
+            out[f"{tag}_{dt_name}_in"] = x.numpy()
+            out[f"{tag}_{dt_name}_preds"] = preds
+            out[f"{tag}_{dt_name}_maxvals"] = maxvals
+            if dt == torch.float32:
+                p2, m2 = ut.get_max_preds_torch(x)
+                out[f"{tag}_{dt_name}_preds_torch"] = p2
+                out[f"{tag}_{dt_name}_maxvals_torch"] = m2
+            flat = x.float().view(x.shape[0], x.shape[1], -1)
+            out[f"{tag}_{dt_name}_idx"] = torch.argmax(flat, 2).to(torch.int32)
+    save("decode", **out)
+
+
+def golden_accuracy():
+    kd = ref_loader.load("keypoint_detection")
+    du = ref_loader.load("dataset_util")
+    out = {}
+    b, k = 6, 5
+    joints, vis = synthetic.keypoints(b, k, seed=21)
+    target = np.stack([du.generate_target(joints[i], vis[i], (64, 64), 2, (256, 256))[0] for i in range(b)])
+    # predictions: the label shifted by a few pixels + noise, so that hits and misses both occur
+    g = torch.Generator().manual_seed(22)
+    shift = torch.randint(-4, 5, (b, k, 2), generator=g)
+    pred = torch.zeros(b, k, 64, 64)
+    tt = torch.from_numpy(target)
+    for i in range(b):
+        for j in range(k):
+            pred[i, j] = torch.roll(tt[i, j], shifts=(int(shift[i, j, 1]), int(shift[i, j, 0])), dims=(0, 1))
+    pred = pred + 0.02 * torch.randn(b, k, 64, 64, generator=g)
+    for tag, o in (("f32", pred.numpy()), ("f16", pred.half().numpy())):
+        acc, avg_acc, cnt, p = kd.accuracy(o, target)
+        out[f"{tag}_output"] = o
+        out[f"{tag}_acc"] = acc
+        out[f"{tag}_avg_acc"] = np.float64(avg_acc)
+        out[f"{tag}_cnt"] = np.int64(cnt)
+        out[f"{tag}_pred"] = p
+        # integer counts behind the ratios
+        tp, _ = kd.get_max_preds(target)
+        norm = np.ones((b, 2)) * np.array([64, 64]) / 10
+        d = kd.calc_dists(p, tp, norm)
+        out[f"{tag}_dists"] = d
+        out[f"{tag}_hits"] = ((d != -1) & (d < 0.5)).sum(1).astype(np.int32)
+        out[f"{tag}_valid"] = (d != -1).sum(1).astype(np.int32)
+    out["target"] = target
+    # adversarial: non-square, other threshold
+    o2 = synthetic.heatmaps(3, 4, seed=23, h=48, w=32).numpy()
+    t2 = synthetic.heatmaps(3, 4, seed=24, h=48, w=32, noise=0.0).numpy()
+    acc, avg_acc, cnt, p = kd.accuracy(o2, t2, thr=1.5)
+    out.update(ns_output=o2, ns_target=t2, ns_acc=acc, ns_avg_acc=np.float64(avg_acc), ns_cnt=np.int64(cnt), ns_pred=p)
+    save("accuracy", **out)
+
+
+def golden_losses():
+    ls = ref_loader.load("loss")
+    out = {}
+    b, k = 3, 4
+    g = torch.Generator().manual_seed(31)
+    output = synthetic.heatmaps(b, k, seed=32, h=32, w=32)
+    target = synthetic.heatmaps(b, k, seed=33, h=32, w=32, noise=0.0)
+    weight = (torch.rand(b, k, 1, generator=g) > 0.3).float()
+    weight[0, 0, 0] = 0.4
+    out.update(output=output, target=target, weight=weight)
+    for red in ("mean", "none"):
+        for wtag, w in (("w", weight), ("now", None)):
+            o = output.clone().requires_grad_(True)
+            loss = ls.JointsMSELoss(reduction=red)(o, target, w)
+            upstream = torch.full_like(loss, 1.0) if red == "mean" else torch.rand(loss.shape, generator=g)
+            loss.backward(upstream)
+            out[f"mse_{red}_{wtag}_loss"] = loss
+            out[f"mse_{red}_{wtag}_upstream"] = upstream
+            out[f"mse_{red}_{wtag}_grad"] = o.grad
+    tea = synthetic.heatmaps(b, k, seed=34, h=32, w=32, noise=0.0)
+    tea_mask = torch.rand(b, k, generator=g) > 0.4
+    valid_mask = torch.rand(b, 32, 32, generator=g) > 0.5
+    out.update(tea=tea, tea_mask=tea_mask, valid_mask=valid_mask)
+    for tag, kw in (("plain", {}), ("tm", dict(tea_mask=tea_mask)), ("vm", dict(valid_mask=valid_mask)),
+                    ("tmvm", dict(tea_mask=tea_mask, valid_mask=valid_mask))):
+        s = output.clone().requires_grad_(True)
+        loss = ls.ConsLoss()(s, tea, **kw)
+        loss.backward(torch.tensor(2.5))
+        out[f"cons_{tag}_loss"] = loss
+        out[f"cons_{tag}_grad"] = s.grad
+    save("losses", **out)
+
+
+def golden_masks():
+    out = {}
+    hm = synthetic.heatmaps(4, 6, seed=41, peak=(0.3, 1.2))
+    hm[0, 0] = -hm[0, 0].abs() - 0.1  # an all-negative plane
+    out["hm"] = hm
+    occlude_thresh, mask_ratio = 0.9, 0.5
+    y_t_tea_recon = hm
+    # ---- train_human.py:376-383 (verbatim) ----
+    b, k, h, w = y_t_tea_recon.size()
+    conf = y_t_tea_recon.amax(dim=(2, 3))
+    pred_position = y_t_tea_recon.view(b, k, -1).argmax(-1)
+    pred_position = torch.stack([pred_position % w, pred_position // w], -1).cpu().numpy()
+    conf_table = conf >= occlude_thresh
+    # ---- train_human.py:360,372 then :427,429-430 (verbatim) ----
+    tea_mask = torch.ones(y_t_tea_recon.shape[:2])
+    activates = y_t_tea_recon.amax(dim=(2, 3))
+    mask_thresh = torch.kthvalue(activates.view(-1), int(mask_ratio * activates.numel()))[0].item()
+    tea_mask = tea_mask * activates > mask_thresh
+    out.update(conf=conf, pred_position=pred_position, conf_table=conf_table, activates=activates,
+               mask_thresh=np.float32(mask_thresh), tea_mask=tea_mask, occlude_thresh=np.float32(occlude_thresh),
+               mask_ratio=np.float64(mask_ratio))
+    # ties at the threshold: quantised activations
+    q = (hm * 4).round() / 4
+    act = q.amax(dim=(2, 3))
+    for r in (0.25, 0.5, 0.9):
+        th = torch.kthvalue(act.view(-1), int(r * act.numel()))[0].item()
+        out[f"q_thresh_{r}"] = np.float32(th)
+        out[f"q_mask_{r}"] = torch.ones_like(act) * act > th
+    out["q_hm"] = q
+    save("masks", **out)
+
+
+def golden_rectify():
+    ut = ref_loader.load("utils")
+    out = {}
+    hm = synthetic.heatmaps(2, 4, seed=51, peak=(0.3, 1.2))
+    adv = synthetic.adversarial_heatmaps(k=2, h=32, w=32, seed=6)
+    out.update(hm=hm, adv=adv)
+    for sig_tag, sigma in (("2", 2), ("1.0", 1.0), ("1.5", 1.5)):
+        out[f"hm_rect_{sig_tag}"] = ut.rectify(hm, sigma)
+        out[f"adv_rect_{sig_tag}"] = ut.rectify(adv, sigma)
+    save("rectify", **out)
+
+
+def golden_targets():
+    du = ref_loader.load("dataset_util")
+    out = {}
+    joints, vis = synthetic.keypoints(3, 8, seed=61)
+    # corner cases: exactly on borders, negative fractions (int() truncates toward zero), weight 0.4
+    joints[0, 0] = [-2.1, 10.0]
+    joints[0, 1] = [255.9, 255.9]
+    joints[0, 2] = [0.0, 0.0]
+    joints[0, 3] = [254.0, 1.9]
+    joints[0, 4] = [-1.9, -1.9]
+    vis[0, 5, 0] = 0.4
+    vis[0, 6, 0] = 0.6
+    out.update(joints=joints, vis=vis)
+    for tag, hs, sigma in (("64_s2", (64, 64), 2), ("64_s1", (64, 64), 1.0), ("8_s2", (8, 8), 2), ("48x32_s1", (48, 32), 1)):
+        tg, wt = zip(*[du.generate_target(joints[i], vis[i], hs, sigma, (256, 256)) for i in range(joints.shape[0])])
+        out[f"target_{tag}"] = np.stack(tg)
+        out[f"weight_{tag}"] = np.stack(wt)
+    # draw_labelmap_ori (animal variant)
+    pts = torch.tensor([[10.7, 20.2], [2.0, 2.0], [3.0, 3.0], [60.0, 60.0], [61.0, 30.0], [30.0, 59.9], [31.5, 0.0],
+                        [-4.0, 5.0], [33.0, 47.0]])
+    out["lm_pts"] = pts
+    for tag, sigma, kind in (("g1", 1.0, "Gaussian"), ("g2", 2, "Gaussian"), ("c1", 1.0, "Cauchy")):
+        imgs, viss = [], []
+        for p in pts:
+            im, v = du.draw_labelmap_ori(torch.zeros(64, 64), p, sigma, type=kind)
+            imgs.append(im.numpy())
+            viss.append(v)
+        out[f"lm_img_{tag}"] = np.stack(imgs)
+        out[f"lm_vis_{tag}"] = np.array(viss, dtype=np.int32)
+    # drawing into a non-zero canvas
+    canvas = torch.full((64, 64), 0.25)
+    im, v = du.draw_labelmap_ori(canvas, torch.tensor([20.0, 30.0]), 1.0)
+    out["lm_canvas"] = im.numpy()
+    save("targets", **out)
+
+
+def golden_ema():
+    ut = ref_loader.load("utils")
+    em = ref_loader.load("ema")
+    out = {}
+
+    def make(seed):
+        torch.manual_seed(seed)
+        return torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.BatchNorm2d(8), torch.nn.Conv2d(8, 5, 1),
+                                   torch.nn.Linear(7, 3))
+
+    teacher, student = make(1), make(2)
+    out["student0"] = np.concatenate([p.detach().numpy().ravel() for p in student.parameters()])
+    out["teacher0"] = np.concatenate([p.detach().numpy().ravel() for p in teacher.parameters()])
+    opt = ut.OldWeightEMA(teacher, student, alpha=0.999)
+    out["teacher_init"] = np.concatenate([p.detach().numpy().ravel() for p in teacher.parameters()])
+    g = torch.Generator().manual_seed(3)
+    deltas = []
+    for step in range(3):
+        d = [torch.randn(p.shape, generator=g) * 0.05 for p in student.parameters()]
+        with torch.no_grad():
+            for p, dd in zip(student.parameters(), d):
+                p.add_(dd)
+        deltas.append(np.concatenate([x.numpy().ravel() for x in d]))
+        opt.step()
+        out[f"teacher_step{step}"] = np.concatenate([p.detach().numpy().ravel() for p in teacher.parameters()])
+    out["deltas"] = np.stack(deltas)
+    # ModelEMA (its __init__ calls .cuda(); make that a no-op in this GPU-less container)
+    orig_cuda = torch.nn.Module.cuda
+    torch.nn.Module.cuda = lambda self, device=None: self
+    try:
+        model = make(4)
+        mema = em.ModelEMA(model, decay=0.99)
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(torch.randn(p.shape, generator=g) * 0.05)
+            model[1].running_mean.add_(1.0)
+            model[1].num_batches_tracked.add_(3)
+        out["mema_model"] = np.concatenate([p.detach().numpy().ravel() for p in model.parameters()])
+        out["mema_before"] = np.concatenate([p.detach().numpy().ravel() for p in mema.ema.parameters()])
+        mema.update(model)
+        out["mema_after"] = np.concatenate([p.detach().numpy().ravel() for p in mema.ema.parameters()])
+        out["mema_buffers_after"] = np.concatenate([b.detach().double().numpy().ravel() for b in mema.ema.buffers()])
+        mema.momentum_update(model, 0.9)
+        out["mema_after_momentum"] = np.concatenate([p.detach().numpy().ravel() for p in mema.ema.parameters()])
+    finally:
+        torch.nn.Module.cuda = orig_cuda
+    save("ema", **out)
+
+
+def main():
+    if not ref_loader.available():
+        raise SystemExit(f"reference tree not found at {ref_loader.REFERENCE_ROOT}")
+    torch.manual_seed(0)
+    np.random.seed(0)
+    for fn in (golden_adain, golden_decode, golden_accuracy, golden_losses, golden_masks, golden_rectify,
+               golden_targets, golden_ema):
+        fn()
+
+
+if __name__ == "__main__":
+    main()

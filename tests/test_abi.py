@@ -1,0 +1,131 @@
+"""C-ABI checks that need no GPU: the shared library builds/loads, exports every symbol that
+include/udape.h declares, the ctypes prototype table covers exactly those symbols, argument
+errors come back as negative codes with a message (no exception/abort across the ABI), and the
+host-only chunk planner works.  No compute call is made here."""
+import ctypes
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+import torch
+
+from uda_poseestimation_b200 import _lib
+
+ROOT = Path(__file__).resolve().parents[1]
+HEADER = ROOT / "include" / "udape.h"
+
+
+def declared_symbols():
+    text = HEADER.read_text()
+    return sorted(set(re.findall(r"UDAPE_API\s+[\w\s\*]+?\b(udape_\w+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_entry_points():
+    syms = declared_symbols()
+    for must in ["udape_mean_std", "udape_adain_mix", "udape_decode", "udape_mask_select", "udape_pck_counts",
+                 "udape_joints_mse_fwd", "udape_joints_mse_bwd", "udape_cons_fwd", "udape_cons_bwd",
+                 "udape_gauss_target", "udape_labelmap", "udape_ema_plan", "udape_ema_multi",
+                 "udape_version", "udape_last_error", "udape_build_info"]:
+        assert must in syms, f"{must} missing from include/udape.h"
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"libudape_b200.so does not export {name}"
+    assert sorted(_lib.PROTOTYPES) == declared_symbols(), "ctypes prototype table out of sync with udape.h"
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.library_path()], capture_output=True, text=True)
+    if out.returncode == 0:
+        exported = {l.split()[-1] for l in out.stdout.splitlines() if " T " in l}
+        assert set(declared_symbols()) <= exported
+
+
+def test_version_and_build_info():
+    lib = _lib.load()
+    assert lib.udape_version() == 100
+    info = lib.udape_build_info().decode()
+    assert "sm_100a" in info and "udape-b200" in info
+
+
+def test_header_is_plain_c(tmp_path):
+    """the boundary must be consumable from C (no C++/torch types in the signatures)"""
+    src = tmp_path / "t.c"
+    src.write_text('#include "udape.h"\nint main(void){ udape_ema_chunk c; c.numel = 0; return (int)c.numel + (UDAPE_F32); }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), "-c", str(src), "-o",
+                        str(tmp_path / "t.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_sass_is_sm100a_only():
+    r = subprocess.run(["cuobjdump", "--list-elf", _lib.library_path()], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_\d+a?", r.stdout))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_argument_errors_are_negative_codes():
+    lib = _lib.load()
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.addressof(buf)
+    # NULL tensor
+    assert lib.udape_mean_std(None, _lib.F32, 4, 16, 1e-5, p, p, None) == -1
+    assert "NULL" in _lib.last_error()
+    # bad dtype
+    assert lib.udape_mean_std(p, 9, 4, 16, 1e-5, p, p, None) == -2
+    # bad shape
+    assert lib.udape_adain_mix(p, p, _lib.F32, 0, 16, 16, 1e-5, 1.0, None, p, None) == -3
+    # alpha outside [0,1] (Style_net.py:164)
+    assert lib.udape_adain_mix(p, p, _lib.F32, 1, 16, 16, 1e-5, 1.5, None, p, None) == -5
+    # misaligned pointer
+    assert lib.udape_mean_std(p + 2, _lib.F32, 1, 4, 1e-5, p, p, None) == -4
+    # kthvalue rank outside [1, n]
+    assert lib.udape_mask_select(p, 10, 0, None, p, p, None) == -5
+    assert lib.udape_mask_select(p, 10, 11, None, p, p, None) == -5
+    assert lib.udape_decode(None, _lib.F32, 1, 4, 4, None, None, None, None, None, 0.0, None, 1.0, None, None) == -1
+    assert lib.udape_labelmap(p, 1, 8, 8, 1.0, 7, 1, p, None, None) == -5
+    with pytest.raises(ValueError):
+        _lib.check(-3, "x")
+    with pytest.raises(_lib.UdapeError):
+        _lib.check(700, "x")
+
+
+def test_ema_plan_host_only():
+    lib = _lib.load()
+    numel = [18, 4096, 4097, 10000, 0, 5]
+    n_t = len(numel)
+    base = 0x10000
+    dst = (ctypes.c_void_p * n_t)(*[base + 0x100000 * i for i in range(n_t)])
+    src = (ctypes.c_void_p * n_t)(*[base + 0x100000 * i + 0x80000 for i in range(n_t)])
+    ne = (ctypes.c_int64 * n_t)(*numel)
+    need = lib.udape_ema_plan(dst, src, ne, n_t, 4, 4096, None, 0)
+    assert need == 1 + 1 + 2 + 3 + 0 + 1
+    table = (_lib.EmaChunk * need)()
+    assert lib.udape_ema_plan(dst, src, ne, n_t, 4, 4096, table, need) == need
+    got = [(c.dst, c.src, c.numel) for c in table]
+    assert got[0] == (base, base + 0x80000, 18)
+    assert got[2] == (base + 0x200000, base + 0x280000, 4096)
+    assert got[3] == (base + 0x200000 + 4096 * 4, base + 0x280000 + 4096 * 4, 1)
+    assert sum(c[2] for c in got) == sum(numel)
+    assert got[-1][2] == 5
+    # errors: chunk size must keep 16-byte alignment; NULL tables
+    assert lib.udape_ema_plan(dst, src, ne, n_t, 4, 1000, None, 0) < 0
+    assert lib.udape_ema_plan(None, src, ne, n_t, 4, 4096, None, 0) < 0
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    import uda_poseestimation_b200 as U
+    x = torch.randn(2, 3, 8, 8)
+    for call in (lambda: U.calc_mean_std(x), lambda: U.adain(x, x), lambda: U.JointsMSELoss()(x, x),
+                 lambda: U.ConsLoss()(x, x), lambda: U.rectify(x, 2), lambda: U.get_max_preds_torch(x),
+                 lambda: U.confidence_mask(x, 0.9), lambda: U.consistency_mask(x[:, :, 0, 0], 0.5)):
+        with pytest.raises(RuntimeError, match="CUDA-only|no CUDA device"):
+            call()
+
+
+def test_product_package_does_not_import_the_oracle():
+    """the oracle is test infrastructure: nothing under the package may reference it"""
+    for f in (ROOT / "uda_poseestimation_b200").rglob("*.py"):
+        text = f.read_text()
+        assert "reference_port" not in text and "from oracle" not in text and "import oracle" not in text, f

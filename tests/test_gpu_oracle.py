@@ -1,0 +1,319 @@
+"""GPU parity against the CPU oracle on seeded synthetic inputs at the BASELINE.json config
+sizes (C1 hand 32x21, C2/C3 human 32x16, C4 animal 64x18 sigma=1.0, C5 microbench 256x21),
+plus size-independent properties at full size.  All calls go through the C-ABI.
+"""
+import numpy as np
+import pytest
+import torch
+
+import uda_poseestimation_b200 as U
+from conftest import assert_close_scaled
+from oracle import reference_port as R
+from uda_poseestimation_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+
+# ---------------------------------------------------------------- AdaIN ---------------------------
+@pytest.mark.parametrize("n", [4, 32])
+def test_adain_fp32_vs_oracle(dev, n):
+    c, s = S.vgg_features(n, seed=1234)
+    alpha = float(np.random.RandomState(1234).uniform(0, 1))
+    ref = R.adain_mix(c, s, alpha)
+    out = U.adain_mix(c.to(dev), s.to(dev), alpha)
+    assert_close_scaled(out, ref, 1e-5, "adain_mix fp32")
+    m_ref, s_ref = R.calc_mean_std(c)
+    m, sd = U.calc_mean_std(c.to(dev))
+    assert_close_scaled(m, m_ref, 1e-5, "mean")
+    assert_close_scaled(sd, s_ref, 1e-5, "std")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_adain_16bit_vs_oracle(dev, dtype):
+    c, s = S.vgg_features(4, seed=99)
+    c16, s16 = c.to(dtype), s.to(dtype)
+    ref = R.adain_mix(c16.float(), s16.float(), 0.6)  # fp32 math on the same quantised inputs
+    out = U.adain_mix(c16.to(dev), s16.to(dev), 0.6)
+    assert out.dtype == dtype
+    assert_close_scaled(out.float(), ref, 1e-2, f"adain {dtype}")
+    m, sd = U.calc_mean_std(c16.to(dev))
+    m_ref, s_ref = R.calc_mean_std(c16.float())
+    assert_close_scaled(m.float(), m_ref, 1e-2, "mean")
+    assert_close_scaled(sd.float(), s_ref, 1e-2, "std")
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 1, 1), (1, 2, 7, 9), (2, 5, 64, 64), (1, 2, 100, 100), (1, 1, 256, 256),
+                                   (3, 4, 8, 8), (2, 2, 16, 24)])
+def test_adain_shapes(dev, shape):
+    """tails, non-vectorisable planes, planes larger than a warp's registers, hw == 1 (NaN std)."""
+    g = torch.Generator().manual_seed(5)
+    c = torch.randn(*shape, generator=g)
+    s = torch.randn(shape[0], shape[1], 11, 5, generator=g) * 3 + 1
+    assert_close_scaled(U.adain_mix(c.to(dev), s.to(dev), 0.25), R.adain_mix(c, s, 0.25), 1e-5, f"adain {shape}")
+    m, sd = U.calc_mean_std(c.to(dev))
+    m_ref, s_ref = R.calc_mean_std(c)
+    assert_close_scaled(m, m_ref, 1e-5, "mean")
+    assert_close_scaled(sd, s_ref, 1e-5, "std")
+
+
+def test_adain_properties_full_size(dev):
+    """N=32 (67 MB per tensor): the output planes carry the style statistics; alpha=0 is the
+    identity; alpha mixing is affine in alpha."""
+    c, s = S.vgg_features(32, seed=7)
+    c, s = c.to(dev), s.to(dev)
+    t = U.adaptive_instance_normalization(c, s)
+    m_t, s_t = U.calc_mean_std(t)
+    m_s, s_s = U.calc_mean_std(s)
+    # near-constant content planes: std(out)/std(style) = sqrt(var_c/(var_c+eps)) is visibly < 1
+    const = U.calc_mean_std(c)[1].flatten() < 0.3
+    assert_close_scaled(m_t.flatten()[~const], m_s.flatten()[~const], 1e-4, "mean(adain) == mean(style)")
+    assert_close_scaled(s_t.flatten()[~const], s_s.flatten()[~const], 1e-3, "std(adain) == std(style)")
+    assert torch.equal(U.adain_mix(c, s, 0.0), c)
+    half = U.adain_mix(c, s, 0.5)
+    assert_close_scaled(half, 0.5 * (t + c), 1e-5, "affine in alpha")
+
+
+# ---------------------------------------------------------------- decode / PCK ---------------------
+@pytest.mark.parametrize("cfg", ["C1", "C4", "C5"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_decode_vs_oracle(dev, cfg, dtype):
+    b, k = S.CONFIGS[cfg]["batch"], S.CONFIGS[cfg]["joints"]
+    hm = S.heatmaps(b, k, seed=1234).to(dtype)  # fp16 makes ties common
+    preds_ref, max_ref = R.get_max_preds(hm.numpy())
+    preds, maxvals = U.get_max_preds(hm.to(dev))
+    np.testing.assert_array_equal(preds.cpu().numpy(), preds_ref)
+    np.testing.assert_array_equal(maxvals.cpu().numpy(), max_ref)
+    idx_ref = np.argmax(hm.numpy().reshape(b, k, -1), 2)
+    np.testing.assert_array_equal(U.decode(hm.to(dev), want_idx=True)["idx"].cpu().numpy(), idx_ref)
+
+
+def test_decode_bf16_and_adversarial(dev):
+    adv = S.adversarial_heatmaps(k=4)
+    for dtype in (torch.float32, torch.float16, torch.bfloat16):
+        x = adv.to(dtype)
+        ref_idx = torch.argmax(x.float().view(10, 4, -1), 2)
+        ref_max = torch.amax(x.view(10, 4, -1), 2)
+        r = U.decode(x.to(dev), want_idx=True, want_maxvals=True, want_preds=True)
+        assert torch.equal(r["idx"].cpu().long(), ref_idx)
+        np.testing.assert_array_equal(r["maxvals"].float().cpu().numpy()[..., 0], ref_max.float().numpy())
+        p_ref, _ = R.get_max_preds_torch(x.float())
+        assert torch.equal(r["preds"].cpu(), p_ref)
+
+
+@pytest.mark.parametrize("cfg", ["C1", "C5"])
+def test_accuracy_vs_oracle(dev, cfg):
+    b, k = S.CONFIGS[cfg]["batch"], S.CONFIGS[cfg]["joints"]
+    joints, vis = S.keypoints(b, k, seed=4321)
+    target, _ = U.generate_target_batched(joints, vis, (64, 64), 2, (256, 256), device=dev)
+    g = torch.Generator().manual_seed(1)
+    pred = torch.roll(target.cpu(), shifts=(2, -3), dims=(2, 3)) + 0.02 * torch.randn(b, k, 64, 64, generator=g)
+    for dtype in (torch.float32, torch.float16):  # train() feeds fp16 y_s, validate() fp32
+        o = pred.to(dtype)
+        acc_ref, avg_ref, cnt_ref, pred_ref = R.accuracy(o.numpy(), target.cpu().numpy())
+        acc, avg, cnt, p = U.accuracy(o.to(dev), target)
+        np.testing.assert_array_equal(acc, acc_ref)
+        assert avg == avg_ref and cnt == cnt_ref
+        np.testing.assert_array_equal(p, pred_ref)
+        hits_ref, valid_ref, _ = R.pck_counts(o.numpy(), target.cpu().numpy())
+        hits, valid, _ = U.pck_counts(o.to(dev), target)
+        np.testing.assert_array_equal(hits.cpu().numpy(), hits_ref)
+        np.testing.assert_array_equal(valid.cpu().numpy(), valid_ref)
+
+
+def test_accuracy_adversarial(dev):
+    adv = S.adversarial_heatmaps(k=4)
+    other = torch.roll(adv, 1, dims=0)
+    acc_ref, avg_ref, cnt_ref, pred_ref = R.accuracy(adv.numpy(), other.numpy())
+    acc, avg, cnt, p = U.accuracy(adv.to(dev), other.to(dev))
+    np.testing.assert_array_equal(acc, acc_ref)
+    assert avg == avg_ref and cnt == cnt_ref
+    np.testing.assert_array_equal(p, pred_ref)
+    # no valid joint at all -> acc == -1 everywhere, avg 0, cnt 0
+    z = torch.zeros(2, 3, 64, 64)
+    acc, avg, cnt, _ = U.accuracy(z.to(dev), z.to(dev))
+    assert (acc == -1).all() and avg == 0 and cnt == 0
+
+
+# ---------------------------------------------------------------- losses ----------------------------
+@pytest.mark.parametrize("cfg", ["C1", "C2", "C4"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_losses_vs_oracle(dev, cfg, dtype):
+    b, k = S.CONFIGS[cfg]["batch"], S.CONFIGS[cfg]["joints"]
+    rtol = 1e-5 if dtype == torch.float32 else 1e-2
+    y_s = S.heatmaps(b, k, seed=10).to(dtype)
+    label = S.heatmaps(b, k, seed=11, noise=0.0)
+    weight = (torch.rand(b, k, 1, generator=torch.Generator().manual_seed(12)) > 0.1).float()
+    scale = 65536.0  # GradScaler's initial scale (train_human.py:324,436)
+    # oracle: autocast runs mse_loss / pow in fp32 on the (quantised) student output
+    o_ref = y_s.float().requires_grad_(True)
+    l_ref = R.joints_mse_loss(o_ref, label, weight)
+    (l_ref * scale).backward()
+    o = y_s.to(dev).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.float16 if dtype != torch.bfloat16 else torch.bfloat16,
+                        enabled=dtype != torch.float32):
+        l = U.JointsMSELoss()(o, label.to(dev), weight.to(dev))
+    assert l.dtype == torch.float32
+    (l * scale).backward()
+    assert o.grad.dtype == dtype
+    assert_close_scaled(l.detach(), l_ref.detach(), 1e-5, "mse loss")  # fp32 accumulation either way
+    assert_close_scaled(o.grad.float(), o_ref.grad, rtol, "mse grad")
+    # ConsLoss against a rectified teacher with the k-th value mask
+    tea = R.rectify(S.heatmaps(b, k, seed=13, peak=(0.3, 1.2)), S.CONFIGS[cfg]["sigma"])
+    tea_mask = torch.rand(b, k, generator=torch.Generator().manual_seed(14)) > 0.5
+    s_ref = y_s.float().requires_grad_(True)
+    c_ref = R.cons_loss(s_ref, tea, tea_mask=tea_mask)
+    (c_ref * scale).backward()
+    s = y_s.to(dev).requires_grad_(True)
+    c = U.ConsLoss()(s, tea.to(dev), tea_mask=tea_mask.to(dev))
+    (c * scale).backward()
+    assert_close_scaled(c.detach().float(), c_ref.detach(), 1e-5, "cons loss")
+    assert_close_scaled(s.grad.float(), s_ref.grad, rtol, "cons grad")
+
+
+def test_loss_odd_shapes_and_reduction_none(dev):
+    g = torch.Generator().manual_seed(3)
+    for shape in [(2, 3, 5, 7), (1, 1, 1, 1), (3, 2, 9, 13), (2, 2, 8, 8)]:
+        o = torch.randn(*shape, generator=g)
+        t = torch.randn(*shape, generator=g)
+        w = torch.rand(shape[0], shape[1], 1, generator=g)
+        for red in ("mean", "none"):
+            o1 = o.clone().requires_grad_(True)
+            l1 = R.joints_mse_loss(o1, t, w, red)
+            up = torch.rand(l1.shape, generator=g)
+            l1.backward(up)
+            o2 = o.to(dev).requires_grad_(True)
+            l2 = U.JointsMSELoss(reduction=red)(o2, t.to(dev), w.to(dev))
+            l2.backward(up.to(dev))
+            assert_close_scaled(l2.detach(), l1.detach(), 1e-5, f"mse {red} {shape}")
+            assert_close_scaled(o2.grad, o1.grad, 1e-5, f"mse grad {red} {shape}")
+        vm = torch.rand(shape[0], shape[2], shape[3], generator=g) > 0.3
+        tm = torch.rand(shape[0], shape[1], generator=g)  # float mask
+        s1 = o.clone().requires_grad_(True)
+        c1 = R.cons_loss(s1, t, valid_mask=vm, tea_mask=tm)
+        c1.backward()
+        s2 = o.to(dev).requires_grad_(True)
+        c2 = U.ConsLoss()(s2, t.to(dev), valid_mask=vm.to(dev), tea_mask=tm.to(dev))
+        c2.backward()
+        assert_close_scaled(c2.detach(), c1.detach(), 1e-5, f"cons {shape}")
+        assert_close_scaled(s2.grad, s1.grad, 1e-5, f"cons grad {shape}")
+
+
+# ---------------------------------------------------------------- masks / rectify --------------------
+@pytest.mark.parametrize("cfg", ["C1", "C4"])
+def test_teacher_targets_vs_oracle(dev, cfg):
+    b, k, sigma = S.CONFIGS[cfg]["batch"], S.CONFIGS[cfg]["joints"], S.CONFIGS[cfg]["sigma"]
+    hm = S.heatmaps(b, k, seed=77, peak=(0.3, 1.2))
+    conf_ref, pos_ref, table_ref = R.confidence_mask(hm, 0.9)
+    mask_ref, thresh_ref, act_ref = R.consistency_mask(hm, 0.5)
+    rect_ref = R.rectify(hm, sigma)
+    t = U.teacher_targets(hm.to(dev), sigma, 0.5, occlude_thresh=0.9)
+    assert torch.equal(t["conf"].cpu(), conf_ref) and torch.equal(t["position"].cpu(), pos_ref)
+    assert torch.equal(t["conf_table"].cpu(), table_ref)
+    assert torch.equal(t["tea_mask"].cpu(), mask_ref)
+    assert t["mask_thresh"].item() == np.float32(thresh_ref)
+    rect = t["rectified"].cpu()
+    assert torch.equal(rect != 0, rect_ref != 0) and torch.equal(rect == 1, rect_ref == 1)
+    assert_close_scaled(rect, rect_ref, 1e-5, "rectified")
+    assert_close_scaled(U.rectify(hm.to(dev), sigma), rect_ref, 1e-5, "rectify()")
+
+
+def test_mask_select_all_ranks(dev):
+    """every k of kthvalue on data with ties, NaN and infinities (bit-exact)"""
+    g = torch.Generator().manual_seed(8)
+    act = (torch.randn(97, generator=g) * 2).round() / 2
+    act[5] = float("inf")
+    act[6] = float("-inf")
+    act[7] = -0.0
+    for kth in range(1, 98):
+        ratio = (kth + 0.5) / 97
+        assert int(ratio * 97) == kth
+        th_ref = torch.kthvalue(act, kth)[0]
+        mask, th = U.consistency_mask(act.to(dev), ratio)
+        assert th.cpu() == th_ref
+        assert torch.equal(mask.cpu(), act > th_ref)
+    with pytest.raises(IndexError):
+        U.consistency_mask(act.to(dev), 0.0)
+    # NaN sorts last (torch.kthvalue): the top rank is NaN and nothing is > NaN
+    act[9] = float("nan")
+    mask, th = U.consistency_mask(act.to(dev), 1.0)
+    assert torch.isnan(th).item() and torch.isnan(torch.kthvalue(act, 97)[0]).item() and not mask.any()
+    mask, th = U.consistency_mask(act.to(dev), 96.5 / 97)
+    assert th.cpu() == torch.kthvalue(act, 96)[0] and torch.equal(mask.cpu(), act > th.cpu())
+
+
+# ---------------------------------------------------------------- target writers ----------------------
+@pytest.mark.parametrize("cfg", ["C1", "C4"])
+def test_generate_target_vs_oracle(dev, cfg):
+    b, k, sigma = S.CONFIGS[cfg]["batch"], S.CONFIGS[cfg]["joints"], S.CONFIGS[cfg]["sigma"]
+    joints, vis = S.keypoints(b, k, seed=31)
+    ref = [R.generate_target(joints[i], vis[i], (64, 64), sigma, (256, 256)) for i in range(b)]
+    ref_t, ref_w = np.stack([r[0] for r in ref]), np.stack([r[1] for r in ref])
+    t, w = U.generate_target_batched(joints, vis, (64, 64), sigma, (256, 256), device=dev)
+    np.testing.assert_array_equal(w.cpu().numpy(), ref_w)
+    np.testing.assert_array_equal(t.cpu().numpy() != 0, ref_t != 0)
+    assert_close_scaled(t, ref_t, 1e-5, "generate_target")
+    # animal variant
+    pts = torch.from_numpy(joints / 4.0).float()
+    imgs, viss = [], []
+    for i in range(min(b, 8)):
+        for j in range(k):
+            im, v = R.draw_labelmap_ori(torch.zeros(64, 64), pts[i, j], sigma)
+            imgs.append(im.numpy())
+            viss.append(v)
+    img, v = U.draw_labelmap_batched(pts[:8], 64, 64, sigma)
+    np.testing.assert_array_equal(v.cpu().numpy().ravel(), np.array(viss))
+    assert_close_scaled(img.reshape(-1, 64, 64), np.stack(imgs), 1e-6, "draw_labelmap")
+
+
+# ---------------------------------------------------------------- EMA -----------------------------------
+def test_ema_pose_resnet101_bit_exact(dev):
+    """The full 323-tensor / 52 992 853-parameter PoseResNet-101 census (K=21), 2 steps."""
+    shapes = S.pose_resnet_param_shapes(21)
+    student_cpu = S.parameter_list(shapes, seed=1)
+    teacher_cpu = S.parameter_list(shapes, seed=2)
+
+    class Bag(torch.nn.Module):
+        def __init__(self, tensors):
+            super().__init__()
+            self.ps = torch.nn.ParameterList([torch.nn.Parameter(t.clone()) for t in tensors])
+
+    student, teacher = Bag(student_cpu).to(dev), Bag(teacher_cpu).to(dev)
+    opt = U.OldWeightEMA(teacher, student, alpha=0.999)
+    R.ema_init(teacher_cpu, student_cpu)
+    for step in range(2):
+        for t in student_cpu:
+            t.mul_(1.01).add_(0.001 * (step + 1))
+        with torch.no_grad():
+            for p in student.parameters():
+                p.mul_(1.01).add_(0.001 * (step + 1))
+        opt.step()
+        R.ema_step(teacher_cpu, student_cpu, 0.999)
+    for p, ref in zip(teacher.parameters(), teacher_cpu):
+        assert torch.equal(p.detach().cpu(), ref)
+
+
+def test_ema_16bit_and_stale_plan(dev):
+    torch.manual_seed(0)
+    for dtype in (torch.bfloat16, torch.float16):
+        a = torch.nn.Linear(33, 17).to(dev, dtype)
+        b_ = torch.nn.Linear(33, 17).to(dev, dtype)
+        ref_t = [p.detach().float().cpu().clone() for p in b_.parameters()]
+        opt = U.OldWeightEMA(a, b_, alpha=0.9)
+        with torch.no_grad():
+            for p in b_.parameters():
+                p.add_(1.0)
+        src = [p.detach().float().cpu() for p in b_.parameters()]
+        opt.step()
+        for p, t0, s in zip(a.parameters(), ref_t, src):
+            expect = (t0 * 0.9 + s * (1.0 - 0.9)).to(dtype)
+            assert_close_scaled(p.detach().float(), expect.float(), 1e-2, f"ema {dtype}")
+    # re-pointing a parameter's storage is detected and the plan is rebuilt
+    a = torch.nn.Linear(8, 8).to(dev)
+    b_ = torch.nn.Linear(8, 8).to(dev)
+    opt = U.OldWeightEMA(a, b_, alpha=0.5)
+    opt.step()
+    with torch.no_grad():
+        b_.weight.data = torch.full_like(b_.weight, 3.0)
+    before = a.weight.detach().clone()
+    opt.step()
+    assert torch.equal(a.weight.detach(), before * 0.5 + 3.0 * 0.5)

@@ -1,0 +1,160 @@
+"""Pins the CPU oracle (oracle/reference_port.py) against the golden fixtures that were
+produced by the REAL reference functions (tests/golden/make_golden.py).  The oracle calls the
+same torch/numpy primitives in the same order as the reference, so equality is exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_port as R
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_adain(golden, tag):
+    g = golden("adain")
+    c, s = T(g[f"{tag}_content"]), T(g[f"{tag}_style"])
+    mean, std = R.calc_mean_std(c)
+    assert torch.equal(mean, T(g[f"{tag}_mean"]))
+    assert torch.equal(std, T(g[f"{tag}_std"]))
+    assert torch.equal(R.adaptive_instance_normalization(c, s), T(g[f"{tag}_adain"]))
+    for alpha in (0.0, 0.37, 1.0):
+        assert torch.equal(R.adain_mix(c, s, alpha), T(g[f"{tag}_mix_{alpha}"]))
+
+
+@pytest.mark.parametrize("tag", ["hm", "adv", "odd"])
+@pytest.mark.parametrize("dt", ["f32", "f16"])
+def test_get_max_preds(golden, tag, dt):
+    g = golden("decode")
+    x = g[f"{tag}_{dt}_in"]
+    preds, maxvals = R.get_max_preds(x)
+    np.testing.assert_array_equal(preds, g[f"{tag}_{dt}_preds"])
+    np.testing.assert_array_equal(maxvals, g[f"{tag}_{dt}_maxvals"])  # NaN == NaN positionally
+    assert preds.dtype == np.float32 and maxvals.dtype == x.dtype
+    if dt == "f32":
+        p2, m2 = R.get_max_preds_torch(T(x))
+        np.testing.assert_array_equal(p2.numpy(), g[f"{tag}_{dt}_preds_torch"])
+        np.testing.assert_array_equal(m2.numpy(), g[f"{tag}_{dt}_maxvals_torch"])
+
+
+@pytest.mark.parametrize("dt", ["f32", "f16"])
+def test_accuracy(golden, dt):
+    g = golden("accuracy")
+    acc, avg_acc, cnt, pred = R.accuracy(g[f"{dt}_output"], g["target"])
+    np.testing.assert_array_equal(acc, g[f"{dt}_acc"])
+    assert avg_acc == float(g[f"{dt}_avg_acc"]) and cnt == int(g[f"{dt}_cnt"])
+    np.testing.assert_array_equal(pred, g[f"{dt}_pred"])
+    hits, valid, _ = R.pck_counts(g[f"{dt}_output"], g["target"])
+    np.testing.assert_array_equal(hits, g[f"{dt}_hits"])
+    np.testing.assert_array_equal(valid, g[f"{dt}_valid"])
+
+
+def test_accuracy_nonsquare_thr(golden):
+    g = golden("accuracy")
+    acc, avg_acc, cnt, pred = R.accuracy(g["ns_output"], g["ns_target"], thr=1.5)
+    np.testing.assert_array_equal(acc, g["ns_acc"])
+    assert avg_acc == float(g["ns_avg_acc"]) and cnt == int(g["ns_cnt"])
+    np.testing.assert_array_equal(pred, g["ns_pred"])
+
+
+@pytest.mark.parametrize("red", ["mean", "none"])
+@pytest.mark.parametrize("wtag", ["w", "now"])
+def test_joints_mse(golden, red, wtag):
+    g = golden("losses")
+    o = T(g["output"]).clone().requires_grad_(True)
+    w = T(g["weight"]) if wtag == "w" else None
+    loss = R.joints_mse_loss(o, T(g["target"]), w, red)
+    assert torch.equal(loss.detach(), T(g[f"mse_{red}_{wtag}_loss"]))
+    loss.backward(T(g[f"mse_{red}_{wtag}_upstream"]))
+    assert torch.equal(o.grad, T(g[f"mse_{red}_{wtag}_grad"]))
+
+
+@pytest.mark.parametrize("tag", ["plain", "tm", "vm", "tmvm"])
+def test_cons_loss(golden, tag):
+    g = golden("losses")
+    s = T(g["output"]).clone().requires_grad_(True)
+    kw = {}
+    if "tm" in tag:
+        kw["tea_mask"] = T(g["tea_mask"])
+    if "vm" in tag:
+        kw["valid_mask"] = T(g["valid_mask"])
+    loss = R.cons_loss(s, T(g["tea"]), **kw)
+    assert torch.equal(loss.detach(), T(g[f"cons_{tag}_loss"]))
+    loss.backward(torch.tensor(2.5))
+    assert torch.equal(s.grad, T(g[f"cons_{tag}_grad"]))
+
+
+def test_masks(golden):
+    g = golden("masks")
+    hm = T(g["hm"])
+    conf, pos, table = R.confidence_mask(hm, float(g["occlude_thresh"]))
+    assert torch.equal(conf, T(g["conf"]))
+    np.testing.assert_array_equal(pos.numpy(), g["pred_position"])
+    assert torch.equal(table, T(g["conf_table"]))
+    mask, thresh, act = R.consistency_mask(hm, float(g["mask_ratio"]))
+    assert torch.equal(mask, T(g["tea_mask"])) and np.float32(thresh) == g["mask_thresh"]
+    assert torch.equal(act, T(g["activates"]))
+    for r in (0.25, 0.5, 0.9):
+        mask, thresh, _ = R.consistency_mask(T(g["q_hm"]), r)
+        assert torch.equal(mask, T(g[f"q_mask_{r}"])) and np.float32(thresh) == g[f"q_thresh_{r}"]
+
+
+@pytest.mark.parametrize("which", ["hm", "adv"])
+@pytest.mark.parametrize("sig", [("2", 2), ("1.0", 1.0), ("1.5", 1.5)])
+def test_rectify(golden, which, sig):
+    g = golden("rectify")
+    out = R.rectify(T(g[which]), sig[1])
+    assert torch.equal(out, T(g[f"{which}_rect_{sig[0]}"]))
+
+
+@pytest.mark.parametrize("case", [("64_s2", (64, 64), 2), ("64_s1", (64, 64), 1.0), ("8_s2", (8, 8), 2),
+                                  ("48x32_s1", (48, 32), 1)])
+def test_generate_target(golden, case):
+    g = golden("targets")
+    tag, hs, sigma = case
+    for i in range(g["joints"].shape[0]):
+        t, w = R.generate_target(g["joints"][i], g["vis"][i], hs, sigma, (256, 256))
+        np.testing.assert_array_equal(t, g[f"target_{tag}"][i])
+        np.testing.assert_array_equal(w, g[f"weight_{tag}"][i])
+
+
+@pytest.mark.parametrize("case", [("g1", 1.0, "Gaussian"), ("g2", 2, "Gaussian"), ("c1", 1.0, "Cauchy")])
+def test_draw_labelmap(golden, case, capsys):
+    g = golden("targets")
+    tag, sigma, kind = case
+    for i, p in enumerate(T(g["lm_pts"])):
+        img, vis = R.draw_labelmap_ori(torch.zeros(64, 64), p, sigma, type=kind)
+        np.testing.assert_array_equal(img.numpy(), g[f"lm_img_{tag}"][i])
+        assert vis == int(g[f"lm_vis_{tag}"][i])
+    img, vis = R.draw_labelmap_ori(torch.full((64, 64), 0.25), torch.tensor([20.0, 30.0]), 1.0)
+    np.testing.assert_array_equal(img.numpy(), g["lm_canvas"])
+
+
+def _split_like(flat, params):
+    out, off = [], 0
+    for p in params:
+        out.append(T(flat[off:off + p.numel()]).view(p.shape).clone())
+        off += p.numel()
+    return out
+
+
+def test_ema(golden):
+    g = golden("ema")
+    shapes = [(8, 3, 3, 3), (8,), (8,), (8,), (5, 8, 1, 1), (5,), (3, 7), (3,)]
+    protos = [torch.empty(s) for s in shapes]
+    student = _split_like(g["student0"], protos)
+    teacher = _split_like(g["teacher0"], protos)
+    R.ema_init(teacher, student)
+    np.testing.assert_array_equal(np.concatenate([t.numpy().ravel() for t in teacher]), g["teacher_init"])
+    for step in range(3):
+        for s, d in zip(student, _split_like(g["deltas"][step], protos)):
+            s.add_(d)
+        R.ema_step(teacher, student, 0.999)
+        np.testing.assert_array_equal(np.concatenate([t.numpy().ravel() for t in teacher]),
+                                      g[f"teacher_step{step}"])
+    ema = _split_like(g["mema_before"], protos)
+    model = _split_like(g["mema_model"], protos)
+    R.model_ema_update(ema, model, 0.99)
+    np.testing.assert_array_equal(np.concatenate([t.numpy().ravel() for t in ema]), g["mema_after"])

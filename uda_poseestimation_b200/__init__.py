@@ -1,0 +1,40 @@
+"""uda_poseestimation_b200 — B200-native (sm_100a) hot path of the mean-teacher + AdaIN
+domain-adaptive pose trainer, behind the reference's own Python operator names.
+
+Every operator is a hand-written CUDA kernel in ``csrc/`` reached through the C-ABI of
+``include/udape.h`` (``libudape_b200.so``, loaded with ctypes).  There is no Triton, no
+torch.compile, no CPU fallback: CPU tensors raise, and a missing shared library raises at
+first use.
+
+Reference name → module here
+    adain/function.py, lib/models/Style_net.py : calc_mean_std, adaptive_instance_normalization, adain
+                                                 (+ adain_mix = Style_net.py:167-168)
+    lib/keypoint_detection.py                  : get_max_preds, calc_dists, dist_acc, accuracy
+    utils.py                                   : get_max_preds_torch, rectify, OldWeightEMA
+    lib/models/loss.py                         : JointsMSELoss, ConsLoss
+    lib/models/ema.py                          : ModelEMA
+    lib/datasets/util.py                       : generate_target, draw_labelmap_ori
+    train_human.py:376-383,427-430 (inline)    : confidence_mask, consistency_mask, teacher_targets
+"""
+from ._lib import UdapeError, library_path, load as load_library
+from .adain import adain, adain_mix, adaptive_instance_normalization, calc_mean_std
+from .ema import ModelEMA, MultiTensorPlan, OldWeightEMA
+from .heatmap import (draw_labelmap_batched, draw_labelmap_ori, generate_target, generate_target_batched,
+                      rectify)
+from .keypoint_detection import (accuracy, accuracy_from_counts, calc_dists, decode, dist_acc, get_max_preds,
+                                 get_max_preds_torch, pck_counts)
+from .loss import ConsLoss, JointsMSELoss, cons_loss, joints_mse_loss
+from .mask import confidence_mask, consistency_mask, teacher_targets
+
+__version__ = "0.1.0"
+
+__all__ = [
+    "UdapeError", "library_path", "load_library",
+    "calc_mean_std", "adaptive_instance_normalization", "adain", "adain_mix",
+    "get_max_preds", "get_max_preds_torch", "calc_dists", "dist_acc", "accuracy", "pck_counts",
+    "accuracy_from_counts", "decode",
+    "JointsMSELoss", "ConsLoss", "joints_mse_loss", "cons_loss",
+    "generate_target", "generate_target_batched", "draw_labelmap_ori", "draw_labelmap_batched", "rectify",
+    "confidence_mask", "consistency_mask", "teacher_targets",
+    "OldWeightEMA", "ModelEMA", "MultiTensorPlan",
+]

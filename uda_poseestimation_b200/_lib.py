@@ -1,0 +1,194 @@
+"""ctypes binding of ``libudape_b200.so`` (the C-ABI declared in ``include/udape.h``).
+
+There is no CPU fallback and no alternative backend: if the shared library is missing it
+is rebuilt with nvcc when possible, otherwise importing any operator raises.  Every
+wrapper passes raw ``data_ptr()``s plus the caller's *current* CUDA stream; ctypes drops
+the GIL for the duration of the call, so ``nn.DataParallel``-style multi-threaded callers
+are safe (the library keeps no global state besides a thread-local error string).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
+
+import torch
+
+from . import build as _build
+
+# dtype codes of include/udape.h
+F32, F16, BF16, U8 = 0, 1, 2, 3
+_DTYPE_CODE = {
+    torch.float32: F32,
+    torch.float16: F16,
+    torch.bfloat16: BF16,
+    torch.uint8: U8,
+    torch.bool: U8,
+}
+
+ERR_NAMES = {-1: "NULL pointer", -2: "unsupported dtype", -3: "bad shape", -4: "misaligned pointer",
+             -5: "argument out of range"}
+
+
+class UdapeError(RuntimeError):
+    """Raised for any non-zero status returned by the C-ABI."""
+
+
+class EmaChunk(ctypes.Structure):
+    _fields_ = [("dst", c_void_p), ("src", c_void_p), ("numel", c_int64)]
+
+
+# name -> (restype, argtypes); must list every UDAPE_API symbol of include/udape.h
+PROTOTYPES = {
+    "udape_version": (c_int, []),
+    "udape_build_info": (c_char_p, []),
+    "udape_last_error": (c_int, [c_char_p, c_size_t]),
+    "udape_mean_std": (c_int, [c_void_p, c_int, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p]),
+    "udape_adain_mix": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_float, c_float,
+                                c_void_p, c_void_p, c_void_p]),
+    "udape_decode": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_float, c_void_p, c_double, c_void_p, c_void_p]),
+    "udape_mask_select": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "udape_pck_counts": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64,
+                                 c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "udape_joints_mse_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_int64,
+                                     c_void_p, c_void_p, c_void_p, c_void_p]),
+    "udape_joints_mse_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_int64,
+                                     c_void_p, c_int, c_void_p, c_void_p]),
+    "udape_cons_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64,
+                               c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "udape_cons_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64,
+                               c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "udape_gauss_target": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_double, c_double,
+                                   c_double, c_void_p, c_void_p, c_void_p]),
+    "udape_labelmap": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_double, c_int, c_int, c_void_p,
+                               c_void_p, c_void_p]),
+    "udape_ema_plan": (c_int64, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_int64, c_int64,
+                                 c_int64, POINTER(EmaChunk), c_int64]),
+    "udape_ema_multi": (c_int, [c_void_p, c_int64, c_int64, c_float, c_float, c_int, c_int, c_void_p]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def library_path() -> str:
+    return str(_build.lib_path())
+
+
+def load(rebuild: bool = True) -> ctypes.CDLL:
+    """Load (building first if stale and nvcc is available) and type the shared library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.lib_path()
+        if rebuild and os.environ.get("UDAPE_NO_BUILD") != "1":
+            try:
+                if _build.needs_build():
+                    _build.build()
+            except Exception as exc:  # no nvcc on this box: use the shipped .so if any
+                if not path.exists():
+                    raise ImportError(
+                        f"libudape_b200.so is missing and could not be built: {exc}\n"
+                        "There is no CPU/PyTorch fallback; run `python -m uda_poseestimation_b200.build`."
+                    ) from exc
+        if not path.exists():
+            raise ImportError(f"{path} not found; run `python -m uda_poseestimation_b200.build`")
+        lib = ctypes.CDLL(str(path))
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)  # AttributeError if the .so does not export the symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    buf = ctypes.create_string_buffer(512)
+    load().udape_last_error(buf, 512)
+    return buf.value.decode("utf-8", "replace")
+
+
+def check(status: int, what: str) -> None:
+    if status == 0:
+        return
+    msg = last_error()
+    if status < 0:
+        raise ValueError(f"{what}: {ERR_NAMES.get(status, status)}: {msg}")
+    raise UdapeError(f"{what}: CUDA error {status}: {msg}")
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPE_CODE[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype} (expected float32/float16/bfloat16)") from None
+
+
+def float_code(t: torch.Tensor) -> int:
+    c = dtype_code(t)
+    if c == U8:
+        raise TypeError(f"unsupported dtype {t.dtype} (expected float32/float16/bfloat16)")
+    return c
+
+
+def require_cuda(*tensors: torch.Tensor) -> torch.device:
+    """All tensors must live on the same CUDA device (there is no CPU path)."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(
+                "uda_poseestimation_b200 operators are CUDA-only (sm_100a); got a tensor on "
+                f"{t.device}. There is no CPU fallback — use the reference implementation for CPU tensors."
+            )
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {dev} vs {t.device}")
+    return dev
+
+
+def ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+class on_device:
+    """Make ``dev`` the current CUDA device for the duration of a launch (cheap no-op when
+    it already is, which is the common case)."""
+
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, dev: torch.device):
+        self.idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        self.prev = -1
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+def no_autograd(name: str, *tensors: torch.Tensor) -> None:
+    """Forward-only operators fail loudly instead of silently detaching the graph."""
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise NotImplementedError(
+            f"{name}: the CUDA operator is forward-only (the trainers call it under torch.no_grad(), "
+            "train_human.py:347); wrap the call in torch.no_grad() or detach the inputs"
+        )

@@ -1,0 +1,93 @@
+"""AdaIN channel statistics and re-normalisation — drop-in for the reference's
+``adain/function.py`` (``calc_mean_std`` :3-11, ``adaptive_instance_normalization`` :14-22)
+and the identical copies in ``lib/models/Style_net.py`` (:4-12, ``adain`` :21-29) plus the
+s2t/t2s alpha mixing line ``t = alpha * t + (1 - alpha) * content_feat`` (:167-168).
+
+Each call is ONE hand-written sm_100a kernel launch (``csrc/adain.cu``) instead of the
+reference's ~19 eager passes.  CUDA tensors only; fp32 / fp16 / bf16.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+__all__ = ["calc_mean_std", "adaptive_instance_normalization", "adain", "adain_mix"]
+
+
+def _planes(feat: torch.Tensor, name: str):
+    if feat.dim() != 4:  # function.py:6 `assert (len(size) == 4)`
+        raise AssertionError(f"{name}: expected a 4-D NCHW tensor, got {tuple(feat.shape)}")
+    n, c, h, w = feat.shape
+    return n, c, h * w
+
+
+def calc_mean_std(feat: torch.Tensor, eps: float = 1e-5):
+    """Per-(n,c) mean and ``sqrt(unbiased var + eps)`` over H*W → two ``[N,C,1,1]`` tensors.
+
+    Same signature and return convention as ``adain/function.py:3-11``.
+    """
+    n, c, hw = _planes(feat, "calc_mean_std")
+    dev = _lib.require_cuda(feat)
+    _lib.no_autograd("calc_mean_std", feat)
+    feat = feat.contiguous()
+    code = _lib.float_code(feat)
+    out = torch.empty((2, n, c, 1, 1), dtype=feat.dtype, device=dev)
+    if n * c > 0:
+        with _lib.on_device(dev):
+            st = _lib.load().udape_mean_std(feat.data_ptr(), code, n * c, hw, float(eps),
+                                            out[0].data_ptr(), out[1].data_ptr(), _lib.stream_ptr(dev))
+        _lib.check(st, "calc_mean_std")
+    return out[0], out[1]
+
+
+def adain_mix(content_feat: torch.Tensor, style_feat: torch.Tensor, alpha=1.0, eps: float = 1e-5,
+              out: torch.Tensor | None = None) -> torch.Tensor:
+    """Fused ``alpha * adain(content, style) + (1 - alpha) * content`` (Style_net.py:167-168).
+
+    ``alpha`` is a Python float in [0, 1] (asserted like Style_net.py:164) or a 0-dim / 1-element
+    float32 CUDA tensor, in which case the kernel reads it from device memory so that a
+    captured CUDA graph can be replayed with a new alpha every step.
+    """
+    if content_feat.shape[:2] != style_feat.shape[:2]:  # function.py:15
+        raise AssertionError(
+            f"adain: content {tuple(content_feat.shape)} and style {tuple(style_feat.shape)} "
+            "must agree in N and C")
+    n, c, hw_c = _planes(content_feat, "adain")
+    _, _, hw_s = _planes(style_feat, "adain")
+    dev = _lib.require_cuda(content_feat, style_feat)
+    _lib.no_autograd("adain", content_feat, style_feat)
+    if content_feat.dtype != style_feat.dtype:
+        raise TypeError(f"adain: dtype mismatch {content_feat.dtype} vs {style_feat.dtype}")
+    content_feat = content_feat.contiguous()
+    style_feat = style_feat.contiguous()
+    code = _lib.float_code(content_feat)
+    alpha_dev = None
+    alpha_host = 1.0
+    if isinstance(alpha, torch.Tensor):
+        if not (alpha.is_cuda and alpha.dtype == torch.float32 and alpha.numel() == 1):
+            raise TypeError("adain_mix: a tensor alpha must be a 1-element float32 CUDA tensor")
+        alpha_dev = alpha.data_ptr()
+    else:
+        alpha_host = float(alpha)
+        assert 0 <= alpha_host <= 1  # Style_net.py:164
+    if out is None:
+        out = torch.empty_like(content_feat)
+    elif out.shape != content_feat.shape or out.dtype != content_feat.dtype or not out.is_contiguous():
+        raise ValueError("adain_mix: `out` must be a contiguous tensor shaped and typed like content_feat")
+    if n * c > 0:
+        with _lib.on_device(dev):
+            st = _lib.load().udape_adain_mix(content_feat.data_ptr(), style_feat.data_ptr(), code, n * c,
+                                             hw_c, hw_s, float(eps), alpha_host, alpha_dev,
+                                             out.data_ptr(), _lib.stream_ptr(dev))
+        _lib.check(st, "adain")
+    return out
+
+
+def adaptive_instance_normalization(content_feat: torch.Tensor, style_feat: torch.Tensor) -> torch.Tensor:
+    """``(content - mean_c) / std_c * std_s + mean_s`` per (n,c) plane (function.py:14-22)."""
+    return adain_mix(content_feat, style_feat, 1.0)
+
+
+# lib/models/Style_net.py:21 names the same function `adain`
+adain = adaptive_instance_normalization

@@ -1,0 +1,356 @@
+// adain.cu — per-(n,c) channel statistics and fused AdaIN (+ s2t/t2s alpha mix).
+//
+// Replaces adain/function.py:3-22 and lib/models/Style_net.py:4-29,167-168 of the
+// reference.  The eager reference makes ~19 passes over the feature tensors
+// (SURVEY.md §2.1); here one launch reads content and style once and writes the
+// result once: algorithmic bytes = planes*(hw_c+hw_s)*E read + planes*hw_c*E write.
+//
+// Two code paths:
+//   * warp-per-plane (planes of <= 256 16-byte vectors, i.e. the 32x32 relu4_1
+//     planes of the trainers): each lane issues all of its 128-bit loads for BOTH
+//     planes up front (up to 16 outstanding per lane), keeps the plane in registers,
+//     and does an exact two-pass mean / sum((x-mean)^2) with warp shuffles.  No shared
+//     memory, no block barrier.
+//   * block-per-plane (any plane size / alignment): three sweeps over the plane, the
+//     2nd and 3rd served by L1/L2 (a plane is at most a few hundred KB), so DRAM still
+//     sees one read.
+#include "common.cuh"
+
+namespace udape {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kCtaThreads = 256;
+
+// ------------------------------------------------------------------------------------
+// warp-per-plane register path
+// ------------------------------------------------------------------------------------
+template <typename T, int J>
+__device__ __forceinline__ void warp_load_plane(const T* plane, int nvec, int lane, uint4 (&v)[J]) {
+    const uint4* p = reinterpret_cast<const uint4*>(plane);
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int i = lane + 32 * j;
+        v[j] = (i < nvec) ? ldg_stream(p + i) : make_uint4(0, 0, 0, 0);
+    }
+}
+
+// exact two-pass statistics of a register-resident plane
+template <typename T, int J>
+__device__ __forceinline__ void warp_plane_stats(const uint4 (&v)[J], int nvec, int hw, int lane,
+                                                 float eps, float& mean, float& stdv) {
+    constexpr int EPV = Vec16<T>::EPV;
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        if (lane + 32 * j < nvec) {
+            float f[EPV];
+            unpack16<T>(v[j], f);
+            float t = 0.0f;
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) t += f[e];
+            s += t;
+        }
+    }
+    s = warp_sum(s);
+    mean = s / static_cast<float>(hw);
+    float m2 = 0.0f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        if (lane + 32 * j < nvec) {
+            float f[EPV];
+            unpack16<T>(v[j], f);
+            float t = 0.0f;
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) {
+                const float d = f[e] - mean;
+                t = fmaf(d, d, t);
+            }
+            m2 += t;
+        }
+    }
+    m2 = warp_sum(m2);
+    // unbiased variance (torch .var default); hw == 1 -> 0/0 = NaN like the reference
+    const float var = m2 / static_cast<float>(hw - 1);
+    stdv = sqrtf(var + eps);
+}
+
+template <typename T, int J>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+mean_std_warp_kernel(const T* __restrict__ feat, T* __restrict__ mean_out, T* __restrict__ std_out,
+                     int64_t planes, int nvec, int hw, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t plane = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (plane >= planes) return;
+    uint4 v[J];
+    warp_load_plane<T, J>(feat + plane * hw, nvec, lane, v);
+    float mean, stdv;
+    warp_plane_stats<T, J>(v, nvec, hw, lane, eps, mean, stdv);
+    if (lane == 0) {
+        mean_out[plane] = from_f32<T>(mean);
+        std_out[plane] = from_f32<T>(stdv);
+    }
+}
+
+template <typename T, int J>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2)
+adain_warp_kernel(const T* __restrict__ content, const T* __restrict__ style, T* __restrict__ out,
+                  int64_t planes, int nvec_c, int nvec_s, int hw_c, int hw_s, float eps,
+                  float alpha, const float* __restrict__ alpha_dev, int mix) {
+    constexpr int EPV = Vec16<T>::EPV;
+    const int lane = threadIdx.x & 31;
+    const int64_t plane = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (plane >= planes) return;
+
+    // issue every load of both planes before the first use
+    uint4 cv[J], sv[J];
+    warp_load_plane<T, J>(content + plane * hw_c, nvec_c, lane, cv);
+    warp_load_plane<T, J>(style + plane * hw_s, nvec_s, lane, sv);
+    const float a = alpha_dev ? __ldg(alpha_dev) : alpha;
+
+    float mean_s, std_s, mean_c, std_c;
+    warp_plane_stats<T, J>(sv, nvec_s, hw_s, lane, eps, mean_s, std_s);
+    warp_plane_stats<T, J>(cv, nvec_c, hw_c, lane, eps, mean_c, std_c);
+
+    const float inv_c = 1.0f / std_c;
+    const float one_minus_a = 1.0f - a;
+    uint4* o4 = reinterpret_cast<uint4*>(out + plane * hw_c);
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int i = lane + 32 * j;
+        if (i < nvec_c) {
+            float f[EPV];
+            unpack16<T>(cv[j], f);
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) {
+                const float n = (f[e] - mean_c) * inv_c;
+                const float t = fmaf(n, std_s, mean_s);
+                f[e] = mix ? fmaf(a, t, one_minus_a * f[e]) : t;
+            }
+            stg_stream(o4 + i, pack16<T>(f));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// block-per-plane generic path
+// ------------------------------------------------------------------------------------
+template <typename T, bool VEC>
+__device__ __forceinline__ float cta_plane_sum(const T* p, int64_t hw) {
+    float s = 0.0f;
+    if (VEC) {
+        constexpr int EPV = Vec16<T>::EPV;
+        const int64_t nvec = hw / EPV;
+        const uint4* p4 = reinterpret_cast<const uint4*>(p);
+        for (int64_t i = threadIdx.x; i < nvec; i += kCtaThreads) {
+            float f[EPV];
+            unpack16<T>(ldg_cached(p4 + i), f);
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) s += f[e];
+        }
+    } else {
+        for (int64_t i = threadIdx.x; i < hw; i += kCtaThreads) s += to_f32<T>(p[i]);
+    }
+    return s;
+}
+template <typename T, bool VEC>
+__device__ __forceinline__ float cta_plane_m2(const T* p, int64_t hw, float mean) {
+    float s = 0.0f;
+    if (VEC) {
+        constexpr int EPV = Vec16<T>::EPV;
+        const int64_t nvec = hw / EPV;
+        const uint4* p4 = reinterpret_cast<const uint4*>(p);
+        for (int64_t i = threadIdx.x; i < nvec; i += kCtaThreads) {
+            float f[EPV];
+            unpack16<T>(ldg_cached(p4 + i), f);
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) {
+                const float d = f[e] - mean;
+                s = fmaf(d, d, s);
+            }
+        }
+    } else {
+        for (int64_t i = threadIdx.x; i < hw; i += kCtaThreads) {
+            const float d = to_f32<T>(p[i]) - mean;
+            s = fmaf(d, d, s);
+        }
+    }
+    return s;
+}
+
+template <typename T, bool VEC>
+__device__ __forceinline__ void cta_plane_stats(const T* p, int64_t hw, float eps, float* red,
+                                                float& mean, float& stdv) {
+    const float s = block_sum<kCtaThreads>(cta_plane_sum<T, VEC>(p, hw), red);
+    mean = s / static_cast<float>(hw);
+    const float m2 = block_sum<kCtaThreads>(cta_plane_m2<T, VEC>(p, hw, mean), red);
+    stdv = sqrtf(m2 / static_cast<float>(hw - 1) + eps);
+}
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kCtaThreads)
+mean_std_cta_kernel(const T* __restrict__ feat, T* __restrict__ mean_out, T* __restrict__ std_out,
+                    int64_t hw, float eps) {
+    __shared__ float red[32];
+    const int64_t plane = blockIdx.x;
+    float mean, stdv;
+    cta_plane_stats<T, VEC>(feat + plane * hw, hw, eps, red, mean, stdv);
+    if (threadIdx.x == 0) {
+        mean_out[plane] = from_f32<T>(mean);
+        std_out[plane] = from_f32<T>(stdv);
+    }
+}
+
+template <typename T, bool VEC_C, bool VEC_S>
+__global__ void __launch_bounds__(kCtaThreads)
+adain_cta_kernel(const T* __restrict__ content, const T* __restrict__ style, T* __restrict__ out,
+                 int64_t hw_c, int64_t hw_s, float eps, float alpha,
+                 const float* __restrict__ alpha_dev, int mix) {
+    __shared__ float red[32];
+    const int64_t plane = blockIdx.x;
+    const T* c = content + plane * hw_c;
+    const T* s = style + plane * hw_s;
+    T* o = out + plane * hw_c;
+    float mean_s, std_s, mean_c, std_c;
+    cta_plane_stats<T, VEC_S>(s, hw_s, eps, red, mean_s, std_s);
+    cta_plane_stats<T, VEC_C>(c, hw_c, eps, red, mean_c, std_c);
+    const float a = alpha_dev ? __ldg(alpha_dev) : alpha;
+    const float inv_c = 1.0f / std_c;
+    const float one_minus_a = 1.0f - a;
+    if (VEC_C) {
+        constexpr int EPV = Vec16<T>::EPV;
+        const int64_t nvec = hw_c / EPV;
+        const uint4* c4 = reinterpret_cast<const uint4*>(c);
+        uint4* o4 = reinterpret_cast<uint4*>(o);
+        for (int64_t i = threadIdx.x; i < nvec; i += kCtaThreads) {
+            float f[EPV];
+            unpack16<T>(ldg_cached(c4 + i), f);
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) {
+                const float n = (f[e] - mean_c) * inv_c;
+                const float t = fmaf(n, std_s, mean_s);
+                f[e] = mix ? fmaf(a, t, one_minus_a * f[e]) : t;
+            }
+            stg_stream(o4 + i, pack16<T>(f));
+        }
+    } else {
+        for (int64_t i = threadIdx.x; i < hw_c; i += kCtaThreads) {
+            const float x = to_f32<T>(c[i]);
+            const float n = (x - mean_c) * inv_c;
+            const float t = fmaf(n, std_s, mean_s);
+            o[i] = from_f32<T>(mix ? fmaf(a, t, one_minus_a * x) : t);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------
+template <typename T>
+static bool plane_vectorizable(const void* base, int64_t hw) {
+    return aligned16(base) && (hw % Vec16<T>::EPV) == 0;
+}
+static int pick_j(int64_t nvec) {  // vectors per lane needed to hold a plane in one warp
+    if (nvec <= 32) return 1;
+    if (nvec <= 64) return 2;
+    if (nvec <= 128) return 4;
+    if (nvec <= 256) return 8;
+    return 0;
+}
+
+template <typename T>
+static int launch_mean_std(const void* feat, int64_t planes, int64_t hw, float eps, void* mean,
+                           void* stdv, cudaStream_t st) {
+    const T* f = static_cast<const T*>(feat);
+    T* m = static_cast<T*>(mean);
+    T* s = static_cast<T*>(stdv);
+    const bool vec = plane_vectorizable<T>(feat, hw);
+    const int j = vec ? pick_j(hw / Vec16<T>::EPV) : 0;
+    if (j) {
+        const unsigned grid = static_cast<unsigned>((planes + kWarpsPerBlock - 1) / kWarpsPerBlock);
+        const int nvec = static_cast<int>(hw / Vec16<T>::EPV);
+        const int ihw = static_cast<int>(hw);
+        switch (j) {
+            case 1: mean_std_warp_kernel<T, 1><<<grid, kWarpsPerBlock * 32, 0, st>>>(f, m, s, planes, nvec, ihw, eps); break;
+            case 2: mean_std_warp_kernel<T, 2><<<grid, kWarpsPerBlock * 32, 0, st>>>(f, m, s, planes, nvec, ihw, eps); break;
+            case 4: mean_std_warp_kernel<T, 4><<<grid, kWarpsPerBlock * 32, 0, st>>>(f, m, s, planes, nvec, ihw, eps); break;
+            default: mean_std_warp_kernel<T, 8><<<grid, kWarpsPerBlock * 32, 0, st>>>(f, m, s, planes, nvec, ihw, eps); break;
+        }
+    } else if (vec) {
+        mean_std_cta_kernel<T, true><<<static_cast<unsigned>(planes), kCtaThreads, 0, st>>>(f, m, s, hw, eps);
+    } else {
+        mean_std_cta_kernel<T, false><<<static_cast<unsigned>(planes), kCtaThreads, 0, st>>>(f, m, s, hw, eps);
+    }
+    return check_launch("udape_mean_std");
+}
+
+template <typename T>
+static int launch_adain(const void* content, const void* style, int64_t planes, int64_t hw_c,
+                        int64_t hw_s, float eps, float alpha, const float* alpha_dev, int mix,
+                        void* out, cudaStream_t st) {
+    const T* c = static_cast<const T*>(content);
+    const T* s = static_cast<const T*>(style);
+    T* o = static_cast<T*>(out);
+    const bool vec_c = plane_vectorizable<T>(content, hw_c) && aligned16(out);
+    const bool vec_s = plane_vectorizable<T>(style, hw_s);
+    int j = 0;
+    if (vec_c && vec_s) {
+        const int64_t nv = (hw_c > hw_s ? hw_c : hw_s) / Vec16<T>::EPV;
+        j = pick_j(nv);
+    }
+    if (j) {
+        const unsigned grid = static_cast<unsigned>((planes + kWarpsPerBlock - 1) / kWarpsPerBlock);
+        const int nvc = static_cast<int>(hw_c / Vec16<T>::EPV), nvs = static_cast<int>(hw_s / Vec16<T>::EPV);
+        const int ihc = static_cast<int>(hw_c), ihs = static_cast<int>(hw_s);
+        switch (j) {
+            case 1: adain_warp_kernel<T, 1><<<grid, kWarpsPerBlock * 32, 0, st>>>(c, s, o, planes, nvc, nvs, ihc, ihs, eps, alpha, alpha_dev, mix); break;
+            case 2: adain_warp_kernel<T, 2><<<grid, kWarpsPerBlock * 32, 0, st>>>(c, s, o, planes, nvc, nvs, ihc, ihs, eps, alpha, alpha_dev, mix); break;
+            case 4: adain_warp_kernel<T, 4><<<grid, kWarpsPerBlock * 32, 0, st>>>(c, s, o, planes, nvc, nvs, ihc, ihs, eps, alpha, alpha_dev, mix); break;
+            default: adain_warp_kernel<T, 8><<<grid, kWarpsPerBlock * 32, 0, st>>>(c, s, o, planes, nvc, nvs, ihc, ihs, eps, alpha, alpha_dev, mix); break;
+        }
+    } else {
+        const unsigned grid = static_cast<unsigned>(planes);
+        if (vec_c && vec_s) adain_cta_kernel<T, true, true><<<grid, kCtaThreads, 0, st>>>(c, s, o, hw_c, hw_s, eps, alpha, alpha_dev, mix);
+        else if (vec_c) adain_cta_kernel<T, true, false><<<grid, kCtaThreads, 0, st>>>(c, s, o, hw_c, hw_s, eps, alpha, alpha_dev, mix);
+        else if (vec_s) adain_cta_kernel<T, false, true><<<grid, kCtaThreads, 0, st>>>(c, s, o, hw_c, hw_s, eps, alpha, alpha_dev, mix);
+        else adain_cta_kernel<T, false, false><<<grid, kCtaThreads, 0, st>>>(c, s, o, hw_c, hw_s, eps, alpha, alpha_dev, mix);
+    }
+    return check_launch("udape_adain_mix");
+}
+
+}  // namespace udape
+
+using namespace udape;
+
+extern "C" int udape_mean_std(const void* feat, int dtype, int64_t planes, int64_t hw, float eps,
+                              void* mean, void* std, void* stream) {
+    UDAPE_REQUIRE(feat && mean && std, UDAPE_ERR_NULL, "udape_mean_std: NULL pointer");
+    UDAPE_REQUIRE(planes > 0 && hw > 0 && planes < (1ll << 31) && hw < (1ll << 31), UDAPE_ERR_SHAPE,
+                  "udape_mean_std: bad extents planes=%lld hw=%lld", (long long)planes, (long long)hw);
+    const int es = dtype_size(dtype);
+    UDAPE_REQUIRE(es == 2 || es == 4, UDAPE_ERR_DTYPE, "udape_mean_std: unsupported dtype code %d", dtype);
+    UDAPE_REQUIRE(aligned_to(feat, es) && aligned_to(mean, es) && aligned_to(std, es), UDAPE_ERR_ALIGN,
+                  "udape_mean_std: pointer not aligned to element size");
+    UDAPE_DISPATCH_FLOAT(dtype, T, return launch_mean_std<T>(feat, planes, hw, eps, mean, std, as_stream(stream)));
+    return UDAPE_OK;
+}
+
+extern "C" int udape_adain_mix(const void* content, const void* style, int dtype, int64_t planes,
+                               int64_t hw_c, int64_t hw_s, float eps, float alpha,
+                               const float* alpha_dev, void* out, void* stream) {
+    UDAPE_REQUIRE(content && style && out, UDAPE_ERR_NULL, "udape_adain_mix: NULL pointer");
+    UDAPE_REQUIRE(planes > 0 && hw_c > 0 && hw_s > 0 && planes < (1ll << 31) && hw_c < (1ll << 31) &&
+                      hw_s < (1ll << 31),
+                  UDAPE_ERR_SHAPE, "udape_adain_mix: bad extents planes=%lld hw_c=%lld hw_s=%lld",
+                  (long long)planes, (long long)hw_c, (long long)hw_s);
+    const int es = dtype_size(dtype);
+    UDAPE_REQUIRE(es == 2 || es == 4, UDAPE_ERR_DTYPE, "udape_adain_mix: unsupported dtype code %d", dtype);
+    UDAPE_REQUIRE(aligned_to(content, es) && aligned_to(style, es) && aligned_to(out, es), UDAPE_ERR_ALIGN,
+                  "udape_adain_mix: pointer not aligned to element size");
+    if (!alpha_dev) {
+        // Style_net.py:164 asserts 0 <= alpha <= 1
+        UDAPE_REQUIRE(alpha >= 0.0f && alpha <= 1.0f, UDAPE_ERR_ARG, "udape_adain_mix: alpha %g outside [0,1]", (double)alpha);
+    }
+    const int mix = (alpha_dev != nullptr) || (alpha != 1.0f);
+    UDAPE_DISPATCH_FLOAT(dtype, T, return launch_adain<T>(content, style, planes, hw_c, hw_s, eps, alpha, alpha_dev, mix, out, as_stream(stream)));
+    return UDAPE_OK;
+}

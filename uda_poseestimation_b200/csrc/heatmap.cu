@@ -1,0 +1,185 @@
+// heatmap.cu — batched Gaussian target-heatmap writers.
+//
+// Replaces lib/datasets/util.py:12-70 (generate_target, human/hand datasets) and
+// :326-363 (draw_labelmap_ori, animal datasets) of the reference, which run per sample
+// and per joint in numpy inside DataLoader workers.  Here one launch writes a whole
+// [planes, H, W] float32 batch: pure write bandwidth (planes*H*W*4 bytes), 128-bit
+// streaming stores, one CTA per plane.  Integer placement follows the reference's
+// conventions exactly (float64 truncation toward zero, out-of-bounds -> weight 0,
+// `v > 0.5` gate, border-touching windows rejected by the animal variant).
+#include <cmath>
+
+#include "common.cuh"
+
+namespace udape {
+
+constexpr int kHmThreads = 256;
+
+struct TargetWindow {
+    double tmp;   // sigma*3                         (util.py:33)
+    int n;        // len(arange(0, 2*tmp+1, 1))      (util.py:51-52)
+    float x0;     // (2*tmp+1) // 2                  (util.py:54)
+    float denom;  // 2*sigma**2 as float32           (util.py:56)
+};
+
+// Python int(x): truncation toward zero; huge/NaN values are pushed out of bounds
+__device__ __forceinline__ int trunc_to_int(double v) {
+    if (!(v > -1.0e9 && v < 1.0e9)) return v < 0.0 ? -1000000000 : 1000000000;
+    return static_cast<int>(v);
+}
+
+__global__ void __launch_bounds__(kHmThreads)
+gauss_target_kernel(const double* __restrict__ joints, const float* __restrict__ vis, int hm_w,
+                    int hm_h, double stride_x, double stride_y, TargetWindow tw,
+                    float* __restrict__ target, float* __restrict__ weight) {
+    __shared__ int s_geom[6];  // ul_x, ul_y, x0i, x1i, y0i, y1i
+    const int64_t plane = blockIdx.x;
+    if (threadIdx.x == 0) {
+        // util.py:38-39  mu = int(joint / feat_stride + 0.5)   (float64)
+        const int mu_x = trunc_to_int(joints[2 * plane] / stride_x + 0.5);
+        const int mu_y = trunc_to_int(joints[2 * plane + 1] / stride_y + 0.5);
+        const int ul_x = trunc_to_int(mu_x - tw.tmp), ul_y = trunc_to_int(mu_y - tw.tmp);
+        const int br_x = trunc_to_int(mu_x + tw.tmp + 1), br_y = trunc_to_int(mu_y + tw.tmp + 1);
+        float wgt = vis[plane];
+        const bool oob = mu_x >= hm_w || mu_y >= hm_h || mu_x < 0 || mu_y < 0;  // util.py:43-47
+        if (oob) wgt = 0.0f;
+        weight[plane] = wgt;
+        const bool paste = !oob && wgt > 0.5f;  // util.py:65-66
+        s_geom[0] = ul_x;
+        s_geom[1] = ul_y;
+        s_geom[2] = paste ? max(0, ul_x) : 0;
+        s_geom[3] = paste ? min(br_x, hm_w) : 0;
+        s_geom[4] = paste ? max(0, ul_y) : 0;
+        s_geom[5] = paste ? min(br_y, hm_h) : 0;
+    }
+    __syncthreads();
+    const int ul_x = s_geom[0], ul_y = s_geom[1];
+    const int x0i = s_geom[2], x1i = s_geom[3], y0i = s_geom[4], y1i = s_geom[5];
+    const int hw = hm_w * hm_h;
+    float* t = target + plane * static_cast<int64_t>(hw);
+    auto value = [&](int x, int y) -> float {
+        if (x < x0i || x >= x1i || y < y0i || y >= y1i) return 0.0f;
+        const int gx = x - ul_x, gy = y - ul_y;
+        if (gx >= tw.n || gy >= tw.n) return 0.0f;
+        const float dx = static_cast<float>(gx) - tw.x0, dy = static_cast<float>(gy) - tw.x0;
+        return expf(-((dx * dx + dy * dy) / tw.denom));  // float32 like np.exp on float32
+    };
+    if ((hw & 3) == 0 && aligned16(target)) {
+        uint4* t4 = reinterpret_cast<uint4*>(t);
+        for (int i = threadIdx.x; i < (hw >> 2); i += kHmThreads) {
+            const int flat = i << 2;
+            int y = flat / hm_w, x = flat - y * hm_w;
+            float f[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                f[e] = value(x, y);
+                if (++x == hm_w) { x = 0; ++y; }
+            }
+            stg_stream(t4 + i, pack16<float>(f));
+        }
+    } else {
+        for (int i = threadIdx.x; i < hw; i += kHmThreads) {
+            const int y = i / hm_w, x = i - y * hm_w;
+            t[i] = value(x, y);
+        }
+    }
+}
+
+struct LabelWindow {
+    float tmp;     // 3*sigma in float32 (int32 tensor - python float -> float32, util.py:333-334)
+    int n;         // len(arange(0, 6*sigma+1, 1))
+    double x0;     // (6*sigma+1) // 2
+    double sigma;
+    int kind;      // 0 Gaussian, 1 Cauchy
+};
+
+__global__ void __launch_bounds__(kHmThreads)
+labelmap_kernel(const int32_t* __restrict__ pts, int h, int w, LabelWindow lw, int zero_fill,
+                float* __restrict__ img, int32_t* __restrict__ vis_out) {
+    const int64_t plane = blockIdx.x;
+    const int px = pts[2 * plane], py = pts[2 * plane + 1];
+    // util.py:333-334: int(pt - 3*sigma), int(pt + 3*sigma + 1) evaluated in float32
+    const int ul_x = static_cast<int>(static_cast<float>(px) - lw.tmp);
+    const int ul_y = static_cast<int>(static_cast<float>(py) - lw.tmp);
+    const int br_x = static_cast<int>(static_cast<float>(px) + lw.tmp + 1.0f);
+    const int br_y = static_cast<int>(static_cast<float>(py) + lw.tmp + 1.0f);
+    // util.py:337-340: reject any window that touches the border
+    const bool reject = br_x >= w || br_y >= h || ul_x < 0 || ul_y < 0;
+    if (threadIdx.x == 0 && vis_out) vis_out[plane] = reject ? 0 : 1;
+    const int x0i = reject ? 0 : max(0, ul_x), x1i = reject ? 0 : min(br_x, w);
+    const int y0i = reject ? 0 : max(0, ul_y), y1i = reject ? 0 : min(br_y, h);
+    const int hw = h * w;
+    float* t = img + plane * static_cast<int64_t>(hw);
+    auto value = [&](int x, int y) -> float {
+        const double dx = static_cast<double>(x - ul_x) - lw.x0, dy = static_cast<double>(y - ul_y) - lw.x0;
+        const double d2 = dx * dx + dy * dy;
+        const double s2 = lw.sigma * lw.sigma;
+        // float64 like numpy, rounded to float32 on store (util.py:349-352,362)
+        const double g = lw.kind == 0 ? exp(-d2 / (2.0 * s2)) : lw.sigma / pow(d2 + s2, 1.5);
+        return static_cast<float>(g);
+    };
+    auto inside = [&](int x, int y) -> bool {
+        return x >= x0i && x < x1i && y >= y0i && y < y1i && (x - ul_x) < lw.n && (y - ul_y) < lw.n;
+    };
+    if (zero_fill) {
+        for (int i = threadIdx.x; i < hw; i += kHmThreads) {
+            const int y = i / w, x = i - y * w;
+            t[i] = inside(x, y) ? value(x, y) : 0.0f;
+        }
+    } else if (!reject) {
+        const int ww = x1i - x0i, wh = y1i - y0i;
+        for (int i = threadIdx.x; i < ww * wh; i += kHmThreads) {
+            const int y = y0i + i / ww, x = x0i + i % ww;
+            if (inside(x, y)) t[y * w + x] = value(x, y);
+        }
+    }
+}
+
+}  // namespace udape
+
+using namespace udape;
+
+extern "C" int udape_gauss_target(const double* joints, const float* vis, int64_t planes, int64_t hm_w,
+                                  int64_t hm_h, double sigma, double image_w, double image_h,
+                                  float* target, float* weight, void* stream) {
+    UDAPE_REQUIRE(joints && vis && target && weight, UDAPE_ERR_NULL, "udape_gauss_target: NULL pointer");
+    UDAPE_REQUIRE(planes > 0 && hm_w > 0 && hm_h > 0 && planes < (1ll << 31) && hm_w * hm_h < (1ll << 31),
+                  UDAPE_ERR_SHAPE, "udape_gauss_target: bad extents planes=%lld w=%lld h=%lld",
+                  (long long)planes, (long long)hm_w, (long long)hm_h);
+    UDAPE_REQUIRE(sigma > 0.0 && sigma < 1e4 && image_w > 0.0 && image_h > 0.0, UDAPE_ERR_ARG,
+                  "udape_gauss_target: sigma/image size out of range");
+    UDAPE_REQUIRE(aligned_to(joints, 8) && aligned_to(vis, 4) && aligned_to(target, 4) && aligned_to(weight, 4),
+                  UDAPE_ERR_ALIGN, "udape_gauss_target: misaligned pointer");
+    TargetWindow tw;
+    tw.tmp = sigma * 3.0;
+    const double size = 2.0 * tw.tmp + 1.0;
+    tw.n = static_cast<int>(std::ceil(size));
+    tw.x0 = static_cast<float>(std::floor(size / 2.0));
+    tw.denom = static_cast<float>(2.0 * sigma * sigma);
+    // util.py:37: feat_stride = image_size / heatmap_size (float64)
+    const double stride_x = image_w / static_cast<double>(hm_w), stride_y = image_h / static_cast<double>(hm_h);
+    gauss_target_kernel<<<static_cast<unsigned>(planes), kHmThreads, 0, as_stream(stream)>>>(
+        joints, vis, static_cast<int>(hm_w), static_cast<int>(hm_h), stride_x, stride_y, tw, target, weight);
+    return check_launch("udape_gauss_target");
+}
+
+extern "C" int udape_labelmap(const int32_t* pts, int64_t planes, int64_t h, int64_t w, double sigma,
+                              int kind, int zero_fill, float* img, int32_t* vis_out, void* stream) {
+    UDAPE_REQUIRE(pts && img, UDAPE_ERR_NULL, "udape_labelmap: NULL pointer");
+    UDAPE_REQUIRE(planes > 0 && h > 0 && w > 0 && planes < (1ll << 31) && h * w < (1ll << 31), UDAPE_ERR_SHAPE,
+                  "udape_labelmap: bad extents planes=%lld h=%lld w=%lld", (long long)planes, (long long)h, (long long)w);
+    UDAPE_REQUIRE(sigma > 0.0 && sigma < 1e4, UDAPE_ERR_ARG, "udape_labelmap: sigma %g out of range", sigma);
+    UDAPE_REQUIRE(kind == 0 || kind == 1, UDAPE_ERR_ARG, "udape_labelmap: kind must be 0 (Gaussian) or 1 (Cauchy)");
+    UDAPE_REQUIRE(aligned_to(pts, 4) && aligned_to(img, 4) && (!vis_out || aligned_to(vis_out, 4)), UDAPE_ERR_ALIGN,
+                  "udape_labelmap: misaligned pointer");
+    LabelWindow lw;
+    lw.tmp = static_cast<float>(3.0 * sigma);
+    const double size = 6.0 * sigma + 1.0;
+    lw.n = static_cast<int>(std::ceil(size));
+    lw.x0 = std::floor(size / 2.0);
+    lw.sigma = sigma;
+    lw.kind = kind;
+    labelmap_kernel<<<static_cast<unsigned>(planes), kHmThreads, 0, as_stream(stream)>>>(
+        pts, static_cast<int>(h), static_cast<int>(w), lw, zero_fill, img, vis_out);
+    return check_launch("udape_labelmap");
+}

@@ -1,0 +1,402 @@
+// loss.cu — masked JointsMSELoss and teacher-student ConsLoss, forward and backward.
+//
+// Replaces lib/models/loss.py:11-49 (JointsMSELoss) and :119-132 (ConsLoss) of the
+// reference, whose eager form makes ~8 passes forward plus autograd's backward
+// (SURVEY.md §2.1).  Here: forward = one read of each operand, backward = one read of
+// each operand + one write of the gradient, mixed dtypes (fp16/bf16 student output
+// under autocast against an fp32 label / rectified teacher) loaded as 128-bit vectors
+// and accumulated in fp32.
+//
+// Reductions are deterministic: every CTA reduces its plane with a fixed shuffle/smem
+// tree and writes one partial; the last CTA to finish (ticket counter) sums the
+// partials in a fixed order.  No floating-point atomics anywhere.
+#include "common.cuh"
+
+namespace udape {
+
+constexpr int kLossThreads = 256;
+constexpr int kLossUnroll = 4;  // independent vector groups in flight per thread
+
+template <typename T> __device__ __forceinline__ float load_scalar(const void* p, int64_t i) {
+    return to_f32<T>(static_cast<const T*>(p)[i]);
+}
+// per-plane weight / mask in one of {f32,f16,bf16,u8}; NULL = 1
+__device__ __forceinline__ float load_plane_scalar(const void* p, int dtype, int64_t i) {
+    if (p == nullptr) return 1.0f;
+    switch (dtype) {
+        case UDAPE_F32: return static_cast<const float*>(p)[i];
+        case UDAPE_F16: return __half2float(static_cast<const __half*>(p)[i]);
+        case UDAPE_BF16: return __bfloat162float(static_cast<const __nv_bfloat16*>(p)[i]);
+        default: return static_cast<const uint8_t*>(p)[i] ? 1.0f : 0.0f;
+    }
+}
+
+// G-byte slice of the u8 validity mask owned by one thread (G in {4, 8})
+template <int G> struct MaskBytes {
+    uint32_t w[G / 4];
+    __device__ __forceinline__ void load(const uint8_t* p) {
+        if constexpr (G == 4) w[0] = *reinterpret_cast<const uint32_t*>(p);
+        else { const uint2 t = *reinterpret_cast<const uint2*>(p); w[0] = t.x; w[1] = t.y; }
+    }
+    __device__ __forceinline__ bool on(int e) const { return (w[e >> 2] >> (8 * (e & 3))) & 0xffu; }
+};
+
+// sum over the plane of  vm[i] * (a[i]-b[i])^2   (vm = optional u8 validity mask)
+template <typename TA, typename TB, bool VEC>
+__device__ __forceinline__ float thread_sq_diff(const TA* __restrict__ a, const TB* __restrict__ b,
+                                                const uint8_t* __restrict__ vm, int hw) {
+    float acc = 0.0f;
+    if (VEC) {
+        constexpr int G = PairGroup<TA, TB>::G;
+        const int ngrp = hw / G;
+        for (int base = 0; base < ngrp; base += kLossUnroll * kLossThreads) {
+            Pack<TA, G> ga[kLossUnroll];
+            Pack<TB, G> gb[kLossUnroll];
+            MaskBytes<G> m[kLossUnroll];
+#pragma unroll
+            for (int u = 0; u < kLossUnroll; ++u) {
+                const int g = base + u * kLossThreads + threadIdx.x;
+                if (g < ngrp) {
+                    ga[u].load(a + G * g);
+                    gb[u].load(b + G * g);
+                    if (vm) m[u].load(vm + G * g);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kLossUnroll; ++u) {
+                const int g = base + u * kLossThreads + threadIdx.x;
+                if (g < ngrp) {
+                    float fa[G], fb[G];
+                    ga[u].get(fa);
+                    gb[u].get(fb);
+                    float t = 0.0f;
+#pragma unroll
+                    for (int e = 0; e < G; ++e) {
+                        const float d = fa[e] - fb[e];
+                        const float sq = d * d;
+                        t += (vm == nullptr || m[u].on(e)) ? sq : 0.0f;
+                    }
+                    acc += t;
+                }
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < hw; i += kLossThreads) {
+            const float d = to_f32<TA>(a[i]) - to_f32<TB>(b[i]);
+            acc += (vm == nullptr || vm[i]) ? d * d : 0.0f;
+        }
+    }
+    return acc;
+}
+
+// Last-CTA-done final reduction: returns true in every thread of the last CTA.
+__device__ __forceinline__ bool last_block_done(uint32_t* ticket, unsigned total) {
+    __shared__ bool is_last;
+    __threadfence();  // publish this CTA's partial before taking a ticket
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(ticket, 1u);
+        is_last = (t == total - 1);
+    }
+    __syncthreads();
+    if (is_last) __threadfence();
+    return is_last;
+}
+// fixed-order sum of n floats by one CTA
+__device__ __forceinline__ float cta_sum_array(const volatile float* v, int64_t n, float* red) {
+    float s = 0.0f;
+    for (int64_t i = threadIdx.x; i < n; i += kLossThreads) s += v[i];
+    return block_sum<kLossThreads>(s, red);
+}
+
+// ---- JointsMSELoss ------------------------------------------------------------------------
+template <typename TO, typename TT, bool VEC>
+__global__ void __launch_bounds__(kLossThreads)
+joints_mse_fwd_kernel(const TO* __restrict__ output, const TT* __restrict__ target,
+                      const void* __restrict__ weight, int w_dtype, int hw,
+                      float* __restrict__ plane_loss, float* __restrict__ loss_mean,
+                      uint32_t* __restrict__ ticket) {
+    __shared__ float red[32];
+    const int64_t plane = blockIdx.x;
+    const float acc = block_sum<kLossThreads>(
+        thread_sq_diff<TO, TT, VEC>(output + plane * hw, target + plane * hw, nullptr, hw), red);
+    if (threadIdx.x == 0) {
+        // loss.py:43-45: mse(none) * 0.5 * weight, then mean over the plane (:49)
+        const float wgt = load_plane_scalar(weight, w_dtype, plane);
+        plane_loss[plane] = 0.5f * wgt * (acc / static_cast<float>(hw));
+    }
+    if (loss_mean == nullptr) return;
+    if (last_block_done(ticket, gridDim.x)) {
+        const float s = cta_sum_array(plane_loss, gridDim.x, red);
+        if (threadIdx.x == 0) *loss_mean = s / static_cast<float>(gridDim.x);
+    }
+}
+
+template <typename TO, typename TT, bool VEC>
+__global__ void __launch_bounds__(kLossThreads)
+joints_mse_bwd_kernel(const TO* __restrict__ output, const TT* __restrict__ target,
+                      const void* __restrict__ weight, int w_dtype, int hw,
+                      const float* __restrict__ grad_out, int grad_per_plane, float inv_count,
+                      TO* __restrict__ grad_in) {
+    const int64_t plane = blockIdx.x;
+    const float g = grad_per_plane ? grad_out[plane] : grad_out[0];
+    // d/do [0.5*w*(o-t)^2] * g / count
+    const float coef = g * load_plane_scalar(weight, w_dtype, plane) * inv_count;
+    const TO* o = output + plane * hw;
+    const TT* t = target + plane * hw;
+    TO* gi = grad_in + plane * hw;
+    if (VEC) {
+        constexpr int G = PairGroup<TO, TT>::G;
+        const int ngrp = hw / G;
+        for (int base = 0; base < ngrp; base += kLossUnroll * kLossThreads) {
+            Pack<TO, G> go[kLossUnroll];
+            Pack<TT, G> gt[kLossUnroll];
+#pragma unroll
+            for (int u = 0; u < kLossUnroll; ++u) {
+                const int gidx = base + u * kLossThreads + threadIdx.x;
+                if (gidx < ngrp) { go[u].load(o + G * gidx); gt[u].load(t + G * gidx); }
+            }
+#pragma unroll
+            for (int u = 0; u < kLossUnroll; ++u) {
+                const int gidx = base + u * kLossThreads + threadIdx.x;
+                if (gidx < ngrp) {
+                    float fo[G], ft[G];
+                    go[u].get(fo);
+                    gt[u].get(ft);
+#pragma unroll
+                    for (int e = 0; e < G; ++e) fo[e] = coef * (fo[e] - ft[e]);
+                    Pack<TO, G>::store(gi + G * gidx, fo);
+                }
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < hw; i += kLossThreads)
+            gi[i] = from_f32<TO>(coef * (to_f32<TO>(o[i]) - to_f32<TT>(t[i])));
+    }
+}
+
+// ---- ConsLoss -----------------------------------------------------------------------------
+// count of valid (b,i) positions; only launched when a valid_mask is supplied
+__global__ void __launch_bounds__(kLossThreads)
+count_valid_kernel(const uint8_t* __restrict__ vm, int64_t n, int32_t* __restrict__ count) {
+    int c = 0;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kLossThreads + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * kLossThreads)
+        c += vm[i] ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);  // integer: order-independent
+}
+
+template <typename TS, typename TT, bool VEC>
+__global__ void __launch_bounds__(kLossThreads)
+cons_fwd_kernel(const TS* __restrict__ stu, const TT* __restrict__ tea,
+                const void* __restrict__ tea_mask, int mask_dtype,
+                const uint8_t* __restrict__ valid_mask, int joints, int hw,
+                float* __restrict__ plane_partial, const int32_t* __restrict__ valid_count,
+                float* __restrict__ loss, uint32_t* __restrict__ ticket) {
+    __shared__ float red[32];
+    const int64_t plane = blockIdx.x;
+    const int64_t b = plane / joints;
+    const float m = load_plane_scalar(tea_mask, mask_dtype, plane);
+    const uint8_t* vm = valid_mask ? valid_mask + b * hw : nullptr;
+    const float acc = block_sum<kLossThreads>(
+        thread_sq_diff<TS, TT, VEC>(stu + plane * hw, tea + plane * hw, vm, hw), red);
+    // (diff*m)^2 = m^2 * diff^2  (loss.py:125-128)
+    if (threadIdx.x == 0) plane_partial[plane] = m * m * acc;
+    if (last_block_done(ticket, gridDim.x)) {
+        const float s = cta_sum_array(plane_partial, gridDim.x, red);
+        if (threadIdx.x == 0) {
+            // mean over k (loss.py:128) then mean over the kept (b,i) positions (:132)
+            const float npos = valid_mask ? static_cast<float>(*valid_count)
+                                          : static_cast<float>(gridDim.x / joints) * static_cast<float>(hw);
+            *loss = s / static_cast<float>(joints) / npos;
+        }
+    }
+}
+
+template <typename TS, typename TT, bool VEC>
+__global__ void __launch_bounds__(kLossThreads)
+cons_bwd_kernel(const TS* __restrict__ stu, const TT* __restrict__ tea,
+                const void* __restrict__ tea_mask, int mask_dtype,
+                const uint8_t* __restrict__ valid_mask, int joints, int hw, int64_t batch,
+                const float* __restrict__ grad_out, const int32_t* __restrict__ valid_count,
+                TS* __restrict__ grad_stu) {
+    const int64_t plane = blockIdx.x;
+    const int64_t b = plane / joints;
+    const float m = load_plane_scalar(tea_mask, mask_dtype, plane);
+    const float npos = valid_mask ? static_cast<float>(*valid_count)
+                                  : static_cast<float>(batch) * static_cast<float>(hw);
+    const float coef = 2.0f * grad_out[0] * m * m / (static_cast<float>(joints) * npos);
+    const uint8_t* vm = valid_mask ? valid_mask + b * hw : nullptr;
+    const TS* s = stu + plane * hw;
+    const TT* t = tea + plane * hw;
+    TS* gs = grad_stu + plane * hw;
+    if (VEC) {
+        constexpr int G = PairGroup<TS, TT>::G;
+        const int ngrp = hw / G;
+        for (int base = 0; base < ngrp; base += kLossUnroll * kLossThreads) {
+            Pack<TS, G> g1[kLossUnroll];
+            Pack<TT, G> g2[kLossUnroll];
+            MaskBytes<G> mk[kLossUnroll];
+#pragma unroll
+            for (int u = 0; u < kLossUnroll; ++u) {
+                const int gidx = base + u * kLossThreads + threadIdx.x;
+                if (gidx < ngrp) {
+                    g1[u].load(s + G * gidx);
+                    g2[u].load(t + G * gidx);
+                    if (vm) mk[u].load(vm + G * gidx);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kLossUnroll; ++u) {
+                const int gidx = base + u * kLossThreads + threadIdx.x;
+                if (gidx < ngrp) {
+                    float fs[G], ft[G];
+                    g1[u].get(fs);
+                    g2[u].get(ft);
+#pragma unroll
+                    for (int e = 0; e < G; ++e) {
+                        const float gval = coef * (fs[e] - ft[e]);
+                        fs[e] = (vm == nullptr || mk[u].on(e)) ? gval : 0.0f;
+                    }
+                    Pack<TS, G>::store(gs + G * gidx, fs);
+                }
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < hw; i += kLossThreads) {
+            const float gval = coef * (to_f32<TS>(s[i]) - to_f32<TT>(t[i]));
+            gs[i] = from_f32<TS>((vm == nullptr || vm[i]) ? gval : 0.0f);
+        }
+    }
+}
+
+template <typename TA, typename TB>
+static bool pair_vectorizable(const void* a, const void* b, const void* c, const void* vm, int64_t hw) {
+    // every plane must start on a 16-byte boundary of the wide operand and hold a whole
+    // number of 8-element groups (covers G = 4 and G = 8)
+    return (hw % 8) == 0 && aligned16(a) && aligned16(b) && (c == nullptr || aligned16(c)) &&
+           (vm == nullptr || aligned_to(vm, 8));
+}
+
+static bool plane_scalar_dtype_ok(int d) { return d == UDAPE_F32 || d == UDAPE_F16 || d == UDAPE_BF16 || d == UDAPE_U8; }
+
+}  // namespace udape
+
+using namespace udape;
+
+#define UDAPE_LOSS_COMMON_CHECKS(NAME, A, AD, B, BD, PLANES, HW)                                          \
+    UDAPE_REQUIRE((A) && (B), UDAPE_ERR_NULL, NAME ": NULL tensor pointer");                              \
+    UDAPE_REQUIRE((PLANES) > 0 && (HW) > 0 && (PLANES) < (1ll << 31) && (HW) < (1ll << 31), UDAPE_ERR_SHAPE, \
+                  NAME ": bad extents planes=%lld hw=%lld", (long long)(PLANES), (long long)(HW));        \
+    UDAPE_REQUIRE((dtype_size(AD) == 2 || dtype_size(AD) == 4) && (dtype_size(BD) == 2 || dtype_size(BD) == 4), \
+                  UDAPE_ERR_DTYPE, NAME ": unsupported dtype codes %d/%d", (int)(AD), (int)(BD));         \
+    UDAPE_REQUIRE(aligned_to((A), dtype_size(AD)) && aligned_to((B), dtype_size(BD)), UDAPE_ERR_ALIGN,    \
+                  NAME ": misaligned tensor pointer")
+
+extern "C" int udape_joints_mse_fwd(const void* output, int out_dtype, const void* target, int tgt_dtype,
+                                    const void* weight, int w_dtype, int64_t planes, int64_t hw,
+                                    float* plane_loss, float* loss_mean, uint32_t* ticket, void* stream) {
+    UDAPE_LOSS_COMMON_CHECKS("udape_joints_mse_fwd", output, out_dtype, target, tgt_dtype, planes, hw);
+    UDAPE_REQUIRE(plane_loss, UDAPE_ERR_NULL, "udape_joints_mse_fwd: plane_loss is NULL");
+    UDAPE_REQUIRE(!loss_mean || ticket, UDAPE_ERR_NULL, "udape_joints_mse_fwd: ticket scratch is NULL");
+    UDAPE_REQUIRE(!weight || plane_scalar_dtype_ok(w_dtype), UDAPE_ERR_DTYPE, "udape_joints_mse_fwd: bad weight dtype %d", w_dtype);
+    cudaStream_t st = as_stream(stream);
+    if (loss_mean) {
+        cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st);
+        if (e != cudaSuccess) return fail(static_cast<int>(e), "udape_joints_mse_fwd: memset: %s", cudaGetErrorString(e));
+    }
+    const unsigned grid = static_cast<unsigned>(planes);
+    const int ihw = static_cast<int>(hw);
+    UDAPE_DISPATCH_FLOAT(out_dtype, TO, UDAPE_DISPATCH_FLOAT(tgt_dtype, TT, {
+        const TO* o = static_cast<const TO*>(output);
+        const TT* t = static_cast<const TT*>(target);
+        if (pair_vectorizable<TO, TT>(output, target, nullptr, nullptr, hw))
+            joints_mse_fwd_kernel<TO, TT, true><<<grid, kLossThreads, 0, st>>>(o, t, weight, w_dtype, ihw, plane_loss, loss_mean, ticket);
+        else
+            joints_mse_fwd_kernel<TO, TT, false><<<grid, kLossThreads, 0, st>>>(o, t, weight, w_dtype, ihw, plane_loss, loss_mean, ticket);
+    }));
+    return check_launch("udape_joints_mse_fwd");
+}
+
+extern "C" int udape_joints_mse_bwd(const void* output, int out_dtype, const void* target, int tgt_dtype,
+                                    const void* weight, int w_dtype, int64_t planes, int64_t hw,
+                                    const float* grad_out, int grad_per_plane, void* grad_in, void* stream) {
+    UDAPE_LOSS_COMMON_CHECKS("udape_joints_mse_bwd", output, out_dtype, target, tgt_dtype, planes, hw);
+    UDAPE_REQUIRE(grad_out && grad_in, UDAPE_ERR_NULL, "udape_joints_mse_bwd: NULL gradient pointer");
+    UDAPE_REQUIRE(!weight || plane_scalar_dtype_ok(w_dtype), UDAPE_ERR_DTYPE, "udape_joints_mse_bwd: bad weight dtype %d", w_dtype);
+    cudaStream_t st = as_stream(stream);
+    const unsigned grid = static_cast<unsigned>(planes);
+    const int ihw = static_cast<int>(hw);
+    // 'mean': g / (planes*hw); 'none': g[p] / hw
+    const float inv_count = grad_per_plane ? 1.0f / static_cast<float>(hw)
+                                           : 1.0f / (static_cast<float>(planes) * static_cast<float>(hw));
+    UDAPE_DISPATCH_FLOAT(out_dtype, TO, UDAPE_DISPATCH_FLOAT(tgt_dtype, TT, {
+        const TO* o = static_cast<const TO*>(output);
+        const TT* t = static_cast<const TT*>(target);
+        TO* gi = static_cast<TO*>(grad_in);
+        if (pair_vectorizable<TO, TT>(output, target, grad_in, nullptr, hw))
+            joints_mse_bwd_kernel<TO, TT, true><<<grid, kLossThreads, 0, st>>>(o, t, weight, w_dtype, ihw, grad_out, grad_per_plane, inv_count, gi);
+        else
+            joints_mse_bwd_kernel<TO, TT, false><<<grid, kLossThreads, 0, st>>>(o, t, weight, w_dtype, ihw, grad_out, grad_per_plane, inv_count, gi);
+    }));
+    return check_launch("udape_joints_mse_bwd");
+}
+
+extern "C" int udape_cons_fwd(const void* stu, int stu_dtype, const void* tea, int tea_dtype,
+                              const void* tea_mask, int mask_dtype, const uint8_t* valid_mask,
+                              int64_t batch, int64_t joints, int64_t hw, float* plane_partial,
+                              int32_t* valid_count, float* loss, uint32_t* ticket, void* stream) {
+    const int64_t planes = batch * joints;
+    UDAPE_REQUIRE(batch > 0 && joints > 0, UDAPE_ERR_SHAPE, "udape_cons_fwd: bad extents B=%lld K=%lld", (long long)batch, (long long)joints);
+    UDAPE_LOSS_COMMON_CHECKS("udape_cons_fwd", stu, stu_dtype, tea, tea_dtype, planes, hw);
+    UDAPE_REQUIRE(plane_partial && loss && ticket, UDAPE_ERR_NULL, "udape_cons_fwd: NULL scratch/output pointer");
+    UDAPE_REQUIRE(!valid_mask || valid_count, UDAPE_ERR_NULL, "udape_cons_fwd: valid_count is NULL");
+    UDAPE_REQUIRE(!tea_mask || plane_scalar_dtype_ok(mask_dtype), UDAPE_ERR_DTYPE, "udape_cons_fwd: bad mask dtype %d", mask_dtype);
+    cudaStream_t st = as_stream(stream);
+    cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st);
+    if (e == cudaSuccess && valid_mask) e = cudaMemsetAsync(valid_count, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "udape_cons_fwd: memset: %s", cudaGetErrorString(e));
+    if (valid_mask) {
+        const int64_t n = batch * hw;
+        const unsigned g = static_cast<unsigned>((n + kLossThreads * 8 - 1) / (kLossThreads * 8));
+        count_valid_kernel<<<g ? g : 1, kLossThreads, 0, st>>>(valid_mask, n, valid_count);
+    }
+    const unsigned grid = static_cast<unsigned>(planes);
+    const int ihw = static_cast<int>(hw), ij = static_cast<int>(joints);
+    UDAPE_DISPATCH_FLOAT(stu_dtype, TS, UDAPE_DISPATCH_FLOAT(tea_dtype, TT, {
+        const TS* s = static_cast<const TS*>(stu);
+        const TT* t = static_cast<const TT*>(tea);
+        if (pair_vectorizable<TS, TT>(stu, tea, nullptr, valid_mask, hw))
+            cons_fwd_kernel<TS, TT, true><<<grid, kLossThreads, 0, st>>>(s, t, tea_mask, mask_dtype, valid_mask, ij, ihw, plane_partial, valid_count, loss, ticket);
+        else
+            cons_fwd_kernel<TS, TT, false><<<grid, kLossThreads, 0, st>>>(s, t, tea_mask, mask_dtype, valid_mask, ij, ihw, plane_partial, valid_count, loss, ticket);
+    }));
+    return check_launch("udape_cons_fwd");
+}
+
+extern "C" int udape_cons_bwd(const void* stu, int stu_dtype, const void* tea, int tea_dtype,
+                              const void* tea_mask, int mask_dtype, const uint8_t* valid_mask,
+                              int64_t batch, int64_t joints, int64_t hw, const float* grad_out,
+                              const int32_t* valid_count, void* grad_stu, void* stream) {
+    const int64_t planes = batch * joints;
+    UDAPE_REQUIRE(batch > 0 && joints > 0, UDAPE_ERR_SHAPE, "udape_cons_bwd: bad extents B=%lld K=%lld", (long long)batch, (long long)joints);
+    UDAPE_LOSS_COMMON_CHECKS("udape_cons_bwd", stu, stu_dtype, tea, tea_dtype, planes, hw);
+    UDAPE_REQUIRE(grad_out && grad_stu, UDAPE_ERR_NULL, "udape_cons_bwd: NULL gradient pointer");
+    UDAPE_REQUIRE(!valid_mask || valid_count, UDAPE_ERR_NULL, "udape_cons_bwd: valid_count is NULL");
+    UDAPE_REQUIRE(!tea_mask || plane_scalar_dtype_ok(mask_dtype), UDAPE_ERR_DTYPE, "udape_cons_bwd: bad mask dtype %d", mask_dtype);
+    cudaStream_t st = as_stream(stream);
+    const unsigned grid = static_cast<unsigned>(planes);
+    const int ihw = static_cast<int>(hw), ij = static_cast<int>(joints);
+    UDAPE_DISPATCH_FLOAT(stu_dtype, TS, UDAPE_DISPATCH_FLOAT(tea_dtype, TT, {
+        const TS* s = static_cast<const TS*>(stu);
+        const TT* t = static_cast<const TT*>(tea);
+        TS* gs = static_cast<TS*>(grad_stu);
+        if (pair_vectorizable<TS, TT>(stu, tea, grad_stu, valid_mask, hw))
+            cons_bwd_kernel<TS, TT, true><<<grid, kLossThreads, 0, st>>>(s, t, tea_mask, mask_dtype, valid_mask, ij, ihw, batch, grad_out, valid_count, gs);
+        else
+            cons_bwd_kernel<TS, TT, false><<<grid, kLossThreads, 0, st>>>(s, t, tea_mask, mask_dtype, valid_mask, ij, ihw, batch, grad_out, valid_count, gs);
+    }));
+    return check_launch("udape_cons_bwd");
+}

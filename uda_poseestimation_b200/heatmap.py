@@ -1,0 +1,125 @@
+"""Gaussian heatmap writers — drop-in for ``lib/datasets/util.py`` ``generate_target``
+(:12-70) and ``draw_labelmap_ori`` (:326-363), and ``utils.py`` ``rectify`` (:77-109).
+
+The reference runs these per sample / per joint in numpy inside DataLoader workers
+(``rendered_hand_pose_mt.py:99-147``) or, for ``rectify``, in a B×K Python loop with four
+host syncs per joint.  The batched functions here write a whole ``[B,K,H,W]`` tensor with
+one CUDA launch; the single-sample functions keep the reference signatures on top of them.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .keypoint_detection import decode
+
+__all__ = ["generate_target", "generate_target_batched", "draw_labelmap_ori", "draw_labelmap_batched",
+           "rectify"]
+
+
+def _default_device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("uda_poseestimation_b200: no CUDA device; this package has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def generate_target_batched(joints, joints_vis, heatmap_size, sigma, image_size, device=None):
+    """Batched ``generate_target``: ``joints[...,K,2]`` (image pixels), ``joints_vis[...,K,1]``
+    → ``(target[...,K,H,W] float32, target_weight[...,K,1] float32)`` on the GPU.
+
+    ``heatmap_size`` and ``image_size`` are ``(W, H)`` as in the reference.  Placement is
+    evaluated in float64 (``mu = int(joint / stride + 0.5)``, util.py:38-39), so pass float64
+    keypoints when they come from numpy.
+    """
+    if isinstance(joints, np.ndarray):
+        joints = torch.from_numpy(np.ascontiguousarray(joints, dtype=np.float64))
+    if isinstance(joints_vis, np.ndarray):
+        joints_vis = torch.from_numpy(np.ascontiguousarray(joints_vis, dtype=np.float32))
+    if device is None:
+        device = joints.device if joints.is_cuda else _default_device()
+    device = torch.device(device)
+    lead = tuple(joints.shape[:-1])
+    if joints.shape[-1] != 2:
+        raise ValueError(f"generate_target: joints must end in 2 coordinates, got {tuple(joints.shape)}")
+    planes = int(np.prod(lead)) if lead else 1
+    if joints_vis.numel() != planes and joints_vis.shape[:len(lead)] != lead:
+        raise ValueError("generate_target: joints_vis must have one entry per joint")
+    j = joints.detach().to(device=device, dtype=torch.float64).reshape(planes, 2).contiguous()
+    v = joints_vis.detach().to(device=device, dtype=torch.float32).reshape(planes, -1)[:, 0].contiguous()
+    hm_w, hm_h = int(heatmap_size[0]), int(heatmap_size[1])
+    target = torch.empty(lead + (hm_h, hm_w), dtype=torch.float32, device=device)
+    weight = torch.empty(lead + (1,), dtype=torch.float32, device=device)
+    if planes > 0:
+        with _lib.on_device(device):
+            st = _lib.load().udape_gauss_target(j.data_ptr(), v.data_ptr(), planes, hm_w, hm_h, float(sigma),
+                                                float(image_size[0]), float(image_size[1]),
+                                                target.data_ptr(), weight.data_ptr(), _lib.stream_ptr(device))
+        _lib.check(st, "generate_target")
+    return target, weight
+
+
+def generate_target(joints, joints_vis, heatmap_size, sigma, image_size):
+    """Reference signature (util.py:12): ``joints (K,2)``, ``joints_vis (K,1)`` numpy arrays →
+    ``(target (K,H,W), target_weight (K,1))`` numpy float32.  Torch inputs return CUDA tensors."""
+    was_numpy = isinstance(joints, np.ndarray)
+    target, weight = generate_target_batched(joints, joints_vis, heatmap_size, sigma, image_size)
+    if was_numpy:
+        return target.cpu().numpy(), weight.cpu().numpy()
+    return target, weight
+
+
+_KINDS = {"Gaussian": 0, "Cauchy": 1}
+
+
+def draw_labelmap_batched(pts, height, width, sigma, type="Gaussian", out=None):
+    """Batched ``draw_labelmap_ori``: ``pts[...,>=2]`` (heatmap pixels) →
+    ``(img[...,H,W] float32, vis[...] int32)``; rejected joints (window touching the border,
+    util.py:337-340) get an all-zero plane and ``vis = 0``.  With ``out`` given, windows are
+    overwritten in place into that existing image batch instead."""
+    if type not in _KINDS:
+        raise ValueError(f"draw_labelmap_ori: unknown type {type!r}")  # reference: g undefined → NameError
+    if isinstance(pts, np.ndarray):
+        pts = torch.from_numpy(pts)
+    device = pts.device if pts.is_cuda else (out.device if out is not None else _default_device())
+    lead = tuple(pts.shape[:-1])
+    planes = int(np.prod(lead)) if lead else 1
+    # util.py:332  pt = pt.to(torch.int32)  (truncation toward zero)
+    p = pts.detach()[..., :2].to(device=device).to(torch.int32).reshape(planes, 2).contiguous()
+    zero_fill = out is None
+    if out is None:
+        out = torch.empty(lead + (int(height), int(width)), dtype=torch.float32, device=device)
+    else:
+        if out.dtype != torch.float32 or not out.is_contiguous() or tuple(out.shape) != lead + (int(height), int(width)):
+            raise ValueError("draw_labelmap_batched: `out` must be a contiguous float32 [...,H,W] tensor")
+        _lib.require_cuda(out)
+    vis = torch.empty(lead, dtype=torch.int32, device=device)
+    if planes > 0:
+        with _lib.on_device(device):
+            st = _lib.load().udape_labelmap(p.data_ptr(), planes, int(height), int(width), float(sigma),
+                                            _KINDS[type], 1 if zero_fill else 0, out.data_ptr(),
+                                            vis.data_ptr(), _lib.stream_ptr(device))
+        _lib.check(st, "draw_labelmap_ori")
+    return out, vis
+
+
+def draw_labelmap_ori(img, pt, sigma, type="Gaussian"):
+    """Reference signature (util.py:326): draws into a copy of ``img [H,W]`` and returns
+    ``(img tensor, vis ∈ {0,1})``.  The returned image lives on the GPU."""
+    if isinstance(img, np.ndarray):
+        img = torch.from_numpy(img)
+    if not isinstance(pt, torch.Tensor):
+        pt = torch.as_tensor(pt)
+    dev = img.device if img.is_cuda else _default_device()
+    canvas = img.detach().to(device=dev, dtype=torch.float32).clone().contiguous()
+    h, w = canvas.shape
+    out, vis = draw_labelmap_batched(pt.reshape(1, -1), h, w, sigma, type, out=canvas.view(1, h, w))
+    return out[0], int(vis.item())
+
+
+def rectify(hm: torch.Tensor, sigma) -> torch.Tensor:
+    """Teacher pseudo-label: per (b,k) plane, zeros + a unit-peak Gaussian at the arg-max
+    (utils.py:77-109).  One fused decode+write launch; same dtype/shape as ``hm``."""
+    if hm.dim() != 4:
+        raise ValueError(f"rectify: expected [B,K,H,W], got {tuple(hm.shape)}")
+    return decode(hm.detach(), rectify_sigma=float(sigma))["rectified"]
