@@ -145,7 +145,7 @@ def test_losses_vs_oracle(dev, cfg, dtype):
     weight = (torch.rand(b, k, 1, generator=torch.Generator().manual_seed(12)) > 0.1).float()
     scale = 65536.0  # GradScaler's initial scale (train_human.py:324,436)
     # oracle: autocast runs mse_loss / pow in fp32 on the (quantised) student output
-    o_ref = y_s.float().requires_grad_(True)
+    o_ref = y_s.float().clone().requires_grad_(True)
     l_ref = R.joints_mse_loss(o_ref, label, weight)
     (l_ref * scale).backward()
     o = y_s.to(dev).requires_grad_(True)
@@ -160,7 +160,7 @@ def test_losses_vs_oracle(dev, cfg, dtype):
     # ConsLoss against a rectified teacher with the k-th value mask
     tea = R.rectify(S.heatmaps(b, k, seed=13, peak=(0.3, 1.2)), S.CONFIGS[cfg]["sigma"])
     tea_mask = torch.rand(b, k, generator=torch.Generator().manual_seed(14)) > 0.5
-    s_ref = y_s.float().requires_grad_(True)
+    s_ref = y_s.float().clone().requires_grad_(True)
     c_ref = R.cons_loss(s_ref, tea, tea_mask=tea_mask)
     (c_ref * scale).backward()
     s = y_s.to(dev).requires_grad_(True)
