@@ -1,0 +1,117 @@
+"""The assembled hot-path step (uda_poseestimation_b200.hotpath) against the CPU oracle running
+the reference's sequence, eagerly (serial and forked streams) and as a replayed CUDA graph with
+device-resident alpha scalars."""
+import numpy as np
+import pytest
+import torch
+
+import uda_poseestimation_b200 as U
+from conftest import assert_close_scaled
+from oracle import reference_port as R
+from uda_poseestimation_b200 import synthetic as S
+from uda_poseestimation_b200.hotpath import HotPathStep, StepInputs, step_algorithmic_bytes
+
+pytestmark = pytest.mark.gpu
+
+
+class Bag(torch.nn.Module):
+    def __init__(self, tensors):
+        super().__init__()
+        self.ps = torch.nn.ParameterList([torch.nn.Parameter(t.clone()) for t in tensors])
+
+
+def _inputs(dev, b=4, k=16, n_feat_c=32, seed=5):
+    src, tgt_style = S.vgg_features(b, seed, channels=n_feat_c)
+    tgt, src_style = S.vgg_features(b, seed + 1, channels=n_feat_c)
+    joints, vis = S.keypoints(b, k, seed + 5)
+    lab = [R.generate_target(joints[i], vis[i], (64, 64), 2, (256, 256)) for i in range(b)]
+    host = dict(feat_src=src, feat_tgt_ori=tgt_style, feat_tgt_tea=tgt, feat_src_ori=src_style,
+                y_s=S.heatmaps(b, k, seed + 2).half(), y_t_stu=S.heatmaps(b, k, seed + 3).half(),
+                y_t_tea=S.heatmaps(b, k, seed + 4, peak=(0.3, 1.2)),
+                label_s=torch.from_numpy(np.stack([x[0] for x in lab])),
+                weight_s=torch.from_numpy(np.stack([x[1] for x in lab])))
+    inp = StepInputs(**{n: t.to(dev) for n, t in host.items()}, alpha_s2t=torch.tensor([0.3], device=dev),
+                     alpha_t2s=torch.tensor([0.8], device=dev))
+    return host, inp
+
+
+def _oracle_step(host, a1, a2, teacher, student, scale=65536.0):
+    t1 = R.adain_mix(host["feat_src"], host["feat_tgt_ori"], a1)
+    t2 = R.adain_mix(host["feat_tgt_tea"], host["feat_src_ori"], a2)
+    conf, pos, table = R.confidence_mask(host["y_t_tea"], 0.9)
+    mask, thresh, act = R.consistency_mask(host["y_t_tea"], 0.5)
+    rect = R.rectify(host["y_t_tea"], 2)
+    y_s = host["y_s"].float().clone().requires_grad_(True)
+    y_t = host["y_t_stu"].float().clone().requires_grad_(True)
+    loss_s = R.joints_mse_loss(y_s, host["label_s"], host["weight_s"])
+    loss_c = R.cons_loss(y_t, rect, tea_mask=mask)
+    ((loss_s + 1.0 * loss_c) * scale).backward()
+    R.ema_step(teacher, student, 0.999)
+    hits, valid, pred = R.pck_counts(host["y_s"].numpy(), host["label_s"].numpy())
+    return dict(t_s2t=t1, t_t2s=t2, conf_table=table, position=pos, tea_mask=mask, rectified=rect,
+                loss_s=loss_s.detach(), loss_c=loss_c.detach(), grad_y_s=y_s.grad, grad_y_t_stu=y_t.grad,
+                hits=hits, valid=valid, pred=pred)
+
+
+def _check(out, ref):
+    assert_close_scaled(out["t_s2t"], ref["t_s2t"], 1e-5, "s2t")
+    assert_close_scaled(out["t_t2s"], ref["t_t2s"], 1e-5, "t2s")
+    assert torch.equal(out["conf_table"].cpu(), ref["conf_table"])
+    assert torch.equal(out["position"].cpu(), ref["position"])
+    assert torch.equal(out["tea_mask"].cpu(), ref["tea_mask"])
+    assert_close_scaled(out["rectified"], ref["rectified"], 1e-5, "rectified")
+    assert_close_scaled(out["loss_s"], ref["loss_s"], 1e-5, "loss_s")
+    assert_close_scaled(out["loss_c"], ref["loss_c"], 1e-5, "loss_c")
+    assert_close_scaled(out["loss_all"], ref["loss_s"] + ref["loss_c"], 1e-5, "loss_all")
+    assert_close_scaled(out["grad_y_s"].float(), ref["grad_y_s"], 1e-2, "grad y_s (fp16)")
+    assert_close_scaled(out["grad_y_t_stu"].float(), ref["grad_y_t_stu"], 1e-2, "grad y_t_stu (fp16)")
+    np.testing.assert_array_equal(out["pck_counts"].cpu().numpy(), np.stack([ref["hits"], ref["valid"]]))
+    np.testing.assert_array_equal(out["pred"].cpu().numpy(), ref["pred"])
+
+
+@pytest.mark.parametrize("parallel", [False, True])
+def test_step_eager_vs_oracle(dev, parallel):
+    host, inp = _inputs(dev)
+    shapes = [(64, 3, 7, 7), (64,), (17,), (256, 64, 1, 1), (5000,)]
+    s_cpu, t_cpu = S.parameter_list(shapes, 1), S.parameter_list(shapes, 2)
+    student, teacher = Bag(s_cpu).to(dev), Bag(t_cpu).to(dev)
+    step = HotPathStep(teacher, student, sigma=2, parallel=parallel)
+    R.ema_init(t_cpu, s_cpu)
+    for it in range(2):
+        out = step.run(inp)
+        torch.cuda.synchronize()
+        ref = _oracle_step(host, 0.3, 0.8, t_cpu, s_cpu)
+        _check(out, ref)
+        for p, e in zip(teacher.parameters(), t_cpu):
+            assert torch.equal(p.detach().cpu(), e)
+
+
+def test_step_graph_replay_with_device_alpha(dev):
+    host, inp = _inputs(dev, seed=11)
+    shapes = [(128, 64, 3, 3), (128,), (33,)]
+    s_cpu, t_cpu = S.parameter_list(shapes, 3), S.parameter_list(shapes, 4)
+    student, teacher = Bag(s_cpu).to(dev), Bag(t_cpu).to(dev)
+    step = HotPathStep(teacher, student, sigma=2)
+    R.ema_init(t_cpu, s_cpu)
+    step.capture(inp, include_ema=True, warmup=2)  # 2 eager warm-up steps + the capture pass do not replay
+    for _ in range(2):
+        R.ema_step(t_cpu, s_cpu, 0.999)
+    for a1, a2 in ((0.3, 0.8), (1.0, 0.0), (0.55, 0.45)):
+        inp.alpha_s2t.fill_(a1)
+        inp.alpha_t2s.fill_(a2)
+        # new inputs in the same static buffers
+        inp.y_s.copy_(torch.roll(inp.y_s, 1, dims=0))
+        host["y_s"] = torch.roll(host["y_s"], 1, dims=0)
+        out = step.replay()
+        torch.cuda.synchronize()
+        ref = _oracle_step(host, a1, a2, t_cpu, s_cpu)
+        _check(out, ref)
+        for p, e in zip(teacher.parameters(), t_cpu):
+            assert torch.equal(p.detach().cpu(), e)
+
+
+def test_step_bytes_accounting(dev):
+    _, inp = _inputs(dev, b=2, k=16)
+    by = step_algorithmic_bytes(inp, n_params=1000)
+    assert by["ema"] == 12000 and by["adain_mix"] == 2 * 3 * inp.feat_src.numel() * 4
+    assert by["total"] == sum(v for k_, v in by.items() if k_ != "total")

@@ -201,17 +201,32 @@ mask_select_kernel(const float* __restrict__ act, int n, int kth, const float* _
             if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned k = s_k, cum = 0u;
-            int b = 0;
-            for (; b < 256; ++b) {
-                const unsigned c = hist[b];
-                if (cum + c >= k) break;
-                cum += c;
+        if (threadIdx.x < 32) {
+            // warp 0 finds the bin holding rank k: lane l owns bins [8l, 8l+8)
+            const unsigned k = s_k;
+            unsigned c[8], lane_sum = 0u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { c[j] = hist[8 * threadIdx.x + j]; lane_sum += c[j]; }
+            unsigned incl = lane_sum;  // inclusive prefix over lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (threadIdx.x >= o) incl += t;
             }
-            s_k = k - cum;
-            s_prefix = prefix | (static_cast<unsigned>(b) << shift);
-            s_mask = mask | (255u << shift);
+            const unsigned excl = incl - lane_sum;
+            const unsigned owner = __ballot_sync(0xffffffffu, incl >= k);
+            if (static_cast<int>(threadIdx.x) == __ffs(owner) - 1) {
+                unsigned cum = excl;
+                int b = 0;
+#pragma unroll
+                for (; b < 7; ++b) {
+                    if (cum + c[b] >= k) break;
+                    cum += c[b];
+                }
+                s_k = k - cum;
+                s_prefix = prefix | (static_cast<unsigned>(8 * threadIdx.x + b) << shift);
+                s_mask = mask | (255u << shift);
+            }
         }
         __syncthreads();
     }

@@ -1,0 +1,166 @@
+"""The per-step hot-path sequence of the reference's ``train()`` (``train_human.py:347-444``)
+assembled from the drop-in operators — everything the trainer does between the cuDNN
+forward/backward passes, on tensors the convolutions would have produced:
+
+    s2t / t2s   AdaIN + alpha mix of relu4_1 features        (:348-356 via Style_net.py:167-168)
+    teacher     conf / position / conf_table, activates,      (:376-383, :427-430)
+                rectify, k-th-value consistency mask
+    student     JointsMSELoss fwd+bwd, ConsLoss fwd+bwd        (:425, :432, :434-436)
+    teacher     EMA update over the PoseResNet parameter list  (:438)
+    metric      PCK hit/valid counts on (y_s, label_s)         (:443-444)
+
+The ResNet/VGG/decoder convolutions and the Adam step are out of scope (cuDNN / torch); their
+outputs are the inputs of this step.  ``HotPathStep.run()`` makes only public-API calls, is
+free of host synchronisation, and can therefore be captured into a CUDA graph
+(``capture()``); alpha scalars live in device memory so each replay can use fresh values.
+"""
+from __future__ import annotations
+
+import dataclasses
+
+import torch
+
+from .adain import adain_mix
+from .ema import OldWeightEMA
+from .keypoint_detection import _pck
+from .loss import cons_loss, joints_mse_loss
+from .mask import teacher_targets
+
+__all__ = ["StepInputs", "HotPathStep", "step_algorithmic_bytes"]
+
+
+@dataclasses.dataclass
+class StepInputs:
+    """Device tensors one step consumes (what the convs / loader hand to the hot path)."""
+    feat_src: torch.Tensor      # [N,512,32,32] relu4_1(x_s)            content of s2t
+    feat_tgt_ori: torch.Tensor  # [N,512,32,32] relu4_1(x_t_teas_ori)   style of s2t
+    feat_tgt_tea: torch.Tensor  # [N,512,32,32] relu4_1(x_t_tea)        content of t2s
+    feat_src_ori: torch.Tensor  # [N,512,32,32] relu4_1(x_s_ori)        style of t2s
+    y_s: torch.Tensor           # [B,K,64,64] student(x_s)      fp16 under autocast
+    y_t_stu: torch.Tensor       # [B,K,64,64] student(x_t_stu)  fp16 under autocast (re-warped)
+    y_t_tea: torch.Tensor       # [B,K,64,64] teacher(x_t_tea)  fp32 (re-warped, averaged over k views)
+    label_s: torch.Tensor       # [B,K,64,64] fp32 Gaussian target
+    weight_s: torch.Tensor      # [B,K,1]     fp32 visibility weight
+    alpha_s2t: torch.Tensor     # [1] fp32 device scalar
+    alpha_t2s: torch.Tensor     # [1] fp32 device scalar
+
+    def tensors(self):
+        return [getattr(self, f.name) for f in dataclasses.fields(self)]
+
+
+def step_algorithmic_bytes(inp: StepInputs, n_params: int, param_bytes: int = 4) -> dict:
+    """Algorithmic HBM bytes of one step, per kernel family."""
+    ef = inp.feat_src.element_size()
+    feat = inp.feat_src.numel() * ef
+    hm = inp.y_t_tea.numel()
+    e_s, e_t, e_l = inp.y_s.element_size(), inp.y_t_tea.element_size(), inp.label_s.element_size()
+    planes = inp.y_s.shape[0] * inp.y_s.shape[1]
+    out = {
+        "adain_mix": 2 * 3 * feat,                        # two directions x (2 reads + 1 write)
+        "decode_rectify": hm * e_t + hm * e_t + 32 * planes,  # 1 read + 1 write (+ per-plane outputs)
+        "mask_select": 9 * planes,
+        "joints_mse_fwd": hm * (e_s + e_l) + 4 * planes,
+        "joints_mse_bwd": hm * (e_s + e_l) + hm * e_s,
+        "cons_fwd": hm * (e_s + e_t) + 4 * planes,
+        "cons_bwd": hm * (e_s + e_t) + hm * e_s,
+        "pck": hm * (e_s + e_l) + 8 * planes,
+        "ema": 3 * n_params * param_bytes,
+    }
+    out["total"] = sum(out.values())
+    return out
+
+
+class HotPathStep:
+    """One mean-teacher hot-path step on a batch shard, through the public operators."""
+
+    # kernels of libudape_b200.so launched by run(): 2 adain, decode(+rectify), mask_select,
+    # mse fwd/bwd, cons fwd/bwd, pck, ema  (memset nodes for tickets/counters not counted)
+    KERNELS_PER_STEP = 10
+
+    def __init__(self, teacher: torch.nn.Module, student: torch.nn.Module, sigma=2, mask_ratio: float = 0.5,
+                 occlude_thresh: float = 0.9, teacher_alpha: float = 0.999, lambda_c: float = 1.0,
+                 loss_scale: float = 65536.0, parallel: bool = True):
+        self.sigma, self.mask_ratio, self.occlude_thresh = sigma, mask_ratio, occlude_thresh
+        self.lambda_c, self.loss_scale = lambda_c, loss_scale
+        self.parallel = parallel
+        self._side = None
+        self.ema = OldWeightEMA(teacher, student, alpha=teacher_alpha)  # train_human.py:141
+        self.n_params = sum(p.numel() for p in teacher.parameters())
+        self.graph = None
+        self.out = None
+        self._graph_inputs = None
+
+    # -- the step, minus the EMA (so that callers can time / place the EMA launch themselves) ------
+    def run_no_ema(self, inp: StepInputs) -> dict:
+        """Three independent chains, forked onto side streams so that the small heatmap kernels
+        (launch/latency-bound at batch 32) overlap the two large AdaIN passes:
+
+            main   : AdaIN+mix s2t, AdaIN+mix t2s
+            teacher: decode+rectify -> k-th mask -> ConsLoss fwd -> bwd
+            student: JointsMSELoss fwd -> bwd -> PCK counts
+
+        The fork/join is plain stream-event ordering, so it behaves the same eagerly and under
+        CUDA-graph capture (where it becomes three parallel graph branches)."""
+        cur = torch.cuda.current_stream()
+        if self._side is None or self._side[0].device != inp.y_s.device:
+            self._side = (torch.cuda.Stream(inp.y_s.device), torch.cuda.Stream(inp.y_s.device))
+        s_tea, s_stu = self._side if self.parallel else (cur, cur)
+        if self.parallel:
+            s_tea.wait_stream(cur)
+            s_stu.wait_stream(cur)
+        with torch.cuda.stream(s_tea):
+            with torch.no_grad():
+                # train_human.py:376-383 and :427-430 — fused decode+rectify pass + k-th value select
+                tt = teacher_targets(inp.y_t_tea, self.sigma, self.mask_ratio, occlude_thresh=self.occlude_thresh)
+            # :432 — consistency loss; its share of `scaler.scale(loss_all).backward()` (:434-436)
+            y_t_stu = inp.y_t_stu.detach().requires_grad_(True)
+            loss_c = cons_loss(y_t_stu, tt["rectified"], tea_mask=tt["tea_mask"])
+            (g_c,) = torch.autograd.grad(loss_c * (self.lambda_c * self.loss_scale), (y_t_stu,))
+        with torch.cuda.stream(s_stu):
+            # :425 — supervised loss and its share of the scaled backward
+            y_s = inp.y_s.detach().requires_grad_(True)
+            loss_s = joints_mse_loss(y_s, inp.label_s, inp.weight_s)
+            (g_s,) = torch.autograd.grad(loss_s * self.loss_scale, (y_s,))
+            with torch.no_grad():
+                # :443-444 — PCK on (y_s, label_s): integer counts stay on the device
+                counts, pred = _pck(inp.y_s, inp.label_s, 0.5)
+        with torch.no_grad():
+            # :348-356 — s2t and t2s feature re-normalisation (the decoder conv follows)
+            t_s2t = adain_mix(inp.feat_src, inp.feat_tgt_ori, inp.alpha_s2t)
+            t_t2s = adain_mix(inp.feat_tgt_tea, inp.feat_src_ori, inp.alpha_t2s)
+        if self.parallel:
+            cur.wait_stream(s_tea)
+            cur.wait_stream(s_stu)
+        with torch.no_grad():
+            loss_all = loss_s.detach() + self.lambda_c * loss_c.detach()  # :434
+        return dict(t_s2t=t_s2t, t_t2s=t_t2s, conf_table=tt["conf_table"], position=tt["position"],
+                    tea_mask=tt["tea_mask"], mask_thresh=tt["mask_thresh"], rectified=tt["rectified"],
+                    loss_s=loss_s.detach(), loss_c=loss_c.detach(), loss_all=loss_all,
+                    grad_y_s=g_s, grad_y_t_stu=g_c, pck_counts=counts, pred=pred)
+
+    def run(self, inp: StepInputs) -> dict:
+        out = self.run_no_ema(inp)
+        self.ema.step()  # :438
+        return out
+
+    # -- CUDA graph of the step (static input/output buffers) ------------------------------------
+    def capture(self, inp: StepInputs, include_ema: bool = True, warmup: int = 3) -> dict:
+        """Capture the step into a CUDA graph reading from ``inp``'s tensors in place; returns the
+        dict of static output tensors that every ``replay()`` overwrites."""
+        fn = self.run if include_ema else self.run_no_ema
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn(inp)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn(inp)
+        self._graph_inputs = inp
+        return self.out
+
+    def replay(self) -> dict:
+        self.graph.replay()
+        return self.out
