@@ -199,14 +199,17 @@ def run_reference_arm(args, cfg, rank):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(cfg, n_gpus, graph=True):
+def workload_config(cfg, n_gpus, graph=True, fused=True, ema="graph"):
     return {"workload": f"{cfg['name']}: mean-teacher hot-path step (AdaIN s2t+t2s mix on 512x32x32 relu4_1 features, "
                         f"teacher decode/conf/kth-mask/rectify, JointsMSE+Cons fwd+bwd, PCK, EMA over PoseResNet-101 "
                         f"params), batch {cfg['batch']}/GPU, {cfg['joints']} keypoints, 256x256 images, 64x64 heatmaps",
             "batch_per_gpu": cfg["batch"], "global_batch": cfg["batch"] * n_gpus, "keypoints": cfg["joints"],
             "sigma": cfg["sigma"], "parallelism": f"dp{n_gpus} (batch sharded, int32 PCK-count allreduce)",
             "l2": "inputs larger than L2: ~1.1 GB streamed per step (the 636 MB EMA pass evicts the 126 MB L2 "
-                  "between steps)", "cuda_graph": graph}
+                  "between steps)", "cuda_graph": graph,
+            "losses": "fused loss step (one launch, teacher map evaluated from the arg-max)" if fused else
+                      "operator by operator (fwd+bwd launches, materialised rectified map)",
+            "ema_launch": ema}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -230,24 +233,25 @@ def run_b200_arm(args, cfg, rank, world, local):
     host["label_s"], host["weight_s"] = label.cpu().pin_memory(), weight.cpu().pin_memory()
     inp = StepInputs(feat_src=d["feat_src"], feat_tgt_ori=d["feat_tgt_ori"], feat_tgt_tea=d["feat_tgt_tea"],
                      feat_src_ori=d["feat_src_ori"], y_s=d["y_s"], y_t_stu=d["y_t_stu"], y_t_tea=d["y_t_tea"],
-                     label_s=label, weight_s=weight,
-                     alpha_s2t=torch.zeros(1, device=dev), alpha_t2s=torch.zeros(1, device=dev))
+                     label_s=label, weight_s=weight, alpha_s2t=None, alpha_t2s=None)
+    alpha_pair = torch.zeros(2, device=dev)  # one 8-byte copy per step sets both directions
+    inp.alpha_s2t, inp.alpha_t2s = alpha_pair[0:1], alpha_pair[1:2]
     shapes = S.pose_resnet_param_shapes(k)
     student = ParamBag(S.parameter_list(shapes, seed + 6, device=dev))
     teacher = ParamBag([torch.empty_like(p) for p in student.parameters()])
-    step = HotPathStep(teacher, student, sigma=sigma)
+    ema_in_graph = args.ema in ("graph", "graph-serial") and not args.no_graph
+    step = HotPathStep(teacher, student, sigma=sigma, fused=not args.unfused, ema_parallel=args.ema == "graph")
     n_steps_total = args.warmup + args.steps
     rng = np.random.RandomState(seed)  # alpha ~ U(0,1) per step (train_human.py:349,354)
     alphas = torch.from_numpy(rng.uniform(0, 1, size=(2 * n_steps_total + 64, 2)).astype(np.float32)).to(dev)
 
     def set_alpha(i):
-        inp.alpha_s2t.copy_(alphas[i, 0:1])
-        inp.alpha_t2s.copy_(alphas[i, 1:2])
+        alpha_pair.copy_(alphas[i])
 
     use_graph = not args.no_graph
     set_alpha(0)
     if use_graph:
-        out = step.capture(inp, include_ema=False, warmup=2)
+        out = step.capture(inp, include_ema=ema_in_graph, warmup=2)
         body = step.replay
     else:
         out = None
@@ -256,11 +260,12 @@ def run_b200_arm(args, cfg, rank, world, local):
     def one_step(i, ev=None):
         set_alpha(i)
         o = body()
-        if ev is not None:
-            ev[0].record()
-        step.ema.step()
-        if ev is not None:
-            ev[1].record()
+        if not ema_in_graph:
+            if ev is not None:
+                ev[0].record()
+            step.ema.step()
+            if ev is not None:
+                ev[1].record()
         if world > 1:
             D.allreduce_counts(o["pck_counts"])  # the path's only per-step exchange (int32 [2,K])
         return o
@@ -284,6 +289,15 @@ def run_b200_arm(args, cfg, rank, world, local):
     if world > 1:
         dist.barrier()
     ms_total = start.elapsed_time(end)
+    if ema_in_graph:
+        # the EMA kernel runs inside the graph (concurrently with the other chains when --ema graph), where
+        # it cannot be bracketed by events: time the same launch on its own right after the step loop
+        # (parameters >> L2, so every launch streams from HBM)
+        for a, b_ in ema_events:
+            a.record()
+            step.ema.step()
+            b_.record()
+        torch.cuda.synchronize()
     ema_ms = float(np.mean([a.elapsed_time(b_) for a, b_ in ema_events]))
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -305,10 +319,10 @@ def run_b200_arm(args, cfg, rank, world, local):
     def e2e_step(i):
         for n in h2d_names:
             getattr(inp, n).copy_(host[n], non_blocking=True)
-        inp.alpha_s2t.copy_(alpha_host[i, 0:1], non_blocking=True)
-        inp.alpha_t2s.copy_(alpha_host[i, 1:2], non_blocking=True)
+        alpha_pair.copy_(alpha_host[i], non_blocking=True)
         o = body()
-        step.ema.step()
+        if not ema_in_graph:
+            step.ema.step()
         if world > 1:
             D.allreduce_counts(o["pck_counts"])
         torch.stack((o["loss_all"], o["loss_s"], o["loss_c"]), out=losses_dev)
@@ -368,7 +382,7 @@ def run_b200_arm(args, cfg, rank, world, local):
         peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = FALLBACK_HBM_GBS, "B200_PROFILING.md fallback (of fallback)"
-    abytes = step_algorithmic_bytes(inp, step.n_params)
+    abytes = step_algorithmic_bytes(inp, step.n_params, fused=step.fused)
     achieved = abytes["ema"] / (ema_ms * 1e-3) / 1e9
     traffic = None
     tf = ROOT / "profiles" / "ema_traffic.json"
@@ -380,6 +394,9 @@ def run_b200_arm(args, cfg, rank, world, local):
     roofline = {"bound": "hbm", "kernel": "ema_multi_kernel<float> (udape_ema_multi)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": abytes["ema"], "avg_launch_ms": ema_ms,
+                "timed": ("CUDA events around each of the K EMA launches inside the timed step loop" if not ema_in_graph else
+                          "CUDA events around K EMA launches issued right after the timed step loop (inside it the "
+                          "kernel is a CUDA-graph node overlapping the other chains and cannot be bracketed)"),
                 "step_algorithmic_bytes": abytes["total"],
                 "step_frac_of_peak": abytes["total"] / (ms_per_step * 1e-3) / 1e9 / peak}
     cpu = None
@@ -390,12 +407,13 @@ def run_b200_arm(args, cfg, rank, world, local):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (fp16 student heatmaps, fp32 accumulation)", "data": "synthetic",
-        "config": workload_config(cfg, world, graph=use_graph),
+        "config": workload_config(cfg, world, graph=use_graph, fused=step.fused,
+                                  ema=args.ema if use_graph else "after"),
         "clocks": clocks,
         "e2e": {"value": world * b / (e2e_ms_per_step / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms_per_step,
                 "last_loss": last[0], "last_avg_pck": last[1]},
-        "gpu_launches": args.steps * HotPathStep.KERNELS_PER_STEP,
+        "gpu_launches": args.steps * step.kernels_per_step,
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
@@ -412,6 +430,11 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--config", choices=sorted(S.CONFIGS), default="C2")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--unfused", action="store_true", help="operator-by-operator losses (separate fwd/bwd launches, "
+                    "materialised rectified teacher map) instead of the fused loss step")
+    ap.add_argument("--ema", choices=["graph", "graph-serial", "after"], default="graph",
+                    help="where the EMA launch sits: a parallel branch of the step graph (default), the last node of "
+                         "the graph, or a separate launch after the graph replay")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=8)
     args = ap.parse_args()

@@ -81,6 +81,14 @@ UDAPE_API int udape_adain_mix(const void* content, const void* style, int dtype,
                     int64_t hw_c, int64_t hw_s, float eps, float alpha,
                     const float* alpha_dev, void* out, void* stream);
 
+/* ---- a3': per-channel clamp after style transfer — train_human.py:276,351,356 -----------
+ * (train_animal.py:301,376,381):  x = maximum(minimum(x.permute(0,2,3,1), recover_max),
+ * recover_min).permute(0,3,1,2).  x[planes = N*C, hw] dense NCHW; lo/hi are DEVICE float
+ * arrays of `channels` entries (recover_min / recover_max); channel of plane p = p % channels.
+ * NaN in x or in a bound propagates like torch.minimum/maximum.  out may alias x. */
+UDAPE_API int udape_channel_clamp(const void* x, int dtype, int64_t planes, int64_t channels, int64_t hw,
+                        const float* lo, const float* hi, void* out, void* stream);
+
 /* ---- a7 + a11 + a6: heatmap decode — lib/keypoint_detection.py:9-37 (get_max_preds),
  * utils.py:54-75 (get_max_preds_torch), train_human.py:376-383 (conf / pred_position /
  * conf_table), utils.py:77-109 (rectify).
@@ -110,19 +118,30 @@ UDAPE_API int udape_mask_select(const float* activates, int64_t n, int64_t kth,
  * Decodes output[B,K,h,w] and target[B,K,h,w] (dtypes may differ), then per (b,k):
  * valid iff target (x>1 and y>1); hit iff ||pred/norm - target/norm||_2 < thr evaluated
  * in float64 with norm = (h/10, w/10) applied to (x, y) as the reference does (:79).
- * hits[K], valid[K] (int32) are zeroed by the call and accumulated with integer atomics,
- * so results are order-independent.  pred[B,K,2] (float32, optional) = decoded output
- * coordinates (accuracy()'s 4th return value); tgt[B,K,2] optional likewise. */
+ * Every (b,k) writes its valid/hit bits to flags[B*K] (caller-owned scratch); the last CTA sums
+ * them per joint into hits[K], valid[K] (int32, fully overwritten) — integer sums, so results
+ * are exact and order-independent, with no atomics on the counts and no memset.
+ * `ticket`: see "tickets" below.  pred[B,K,2] (float32, optional) = decoded output coordinates
+ * (accuracy()'s 4th return value); tgt[B,K,2] optional likewise. */
 UDAPE_API int udape_pck_counts(const void* output, int out_dtype, const void* target, int tgt_dtype,
                      int64_t batch, int64_t joints, int64_t h, int64_t w, double thr,
-                     float* pred, float* tgt, int32_t* hits, int32_t* valid, void* stream);
+                     float* pred, float* tgt, int32_t* hits, int32_t* valid, uint8_t* flags,
+                     uint32_t* ticket, void* stream);
+
+/* ---- tickets ---------------------------------------------------------------------------
+ * Calls that end in a grid-wide reduction (udape_pck_counts, udape_joints_mse_fwd with
+ * loss_mean, udape_cons_fwd, udape_loss_step) take a `ticket`: a caller-owned, 4-byte aligned
+ * device uint32 that MUST BE ZERO ON ENTRY.  The last CTA to finish reduces all partials in a
+ * fixed order (deterministic results) and the counter wraps back to zero, so the same word can
+ * be handed to the next call on the same stream without a memset.  Calls that may run
+ * concurrently (different streams) must use different words. */
 
 /* ---- a9: JointsMSELoss — lib/models/loss.py:11-49 ------------------------------------
  * fwd: plane_loss[p] = weight[p] * 0.5 * mean_i (o[p,i]-t[p,i])^2   (reduction='none');
  *      *loss_mean = mean_p plane_loss[p]                             (reduction='mean').
  * weight (optional, [planes]) may be f32/f16/bf16.  plane_loss is required (it doubles as
- * the deterministic reduction scratch); loss_mean optional; ticket = 4 zero-able bytes of
- * scratch (the call zeroes it).
+ * the deterministic reduction scratch); loss_mean optional; ticket (needed with loss_mean): see
+ * "tickets" above.
  * bwd: grad_in[p,i] = c[p] * weight[p] * (o-t), c[p] = grad_out[0]/(planes*hw) for 'mean'
  * (grad_per_plane=0) or grad_out[p]/hw for 'none' (grad_per_plane=1); grad_out is a device
  * float pointer; grad_in is written in out_dtype. */
@@ -139,7 +158,7 @@ UDAPE_API int udape_joints_mse_bwd(const void* output, int out_dtype, const void
  * loss = mean over (b,i) (only where valid_mask[b,i] != 0 when valid_mask is given).
  * tea_mask optional [B*K] u8 or f32; valid_mask optional [B*hw] u8.
  * plane_partial[B*K] (float scratch), valid_count (int32 scratch, written when valid_mask
- * is given), ticket (4 bytes scratch) are caller-owned.  bwd writes
+ * is given) are caller-owned; ticket: see "tickets" above.  bwd writes
  * grad_stu = 2*g*diff*mask/(K*Nvalid) (0 where invalid) in stu_dtype. */
 UDAPE_API int udape_cons_fwd(const void* stu, int stu_dtype, const void* tea, int tea_dtype,
                    const void* tea_mask, int mask_dtype, const uint8_t* valid_mask,
@@ -149,6 +168,28 @@ UDAPE_API int udape_cons_bwd(const void* stu, int stu_dtype, const void* tea, in
                    const void* tea_mask, int mask_dtype, const uint8_t* valid_mask,
                    int64_t batch, int64_t joints, int64_t hw, const float* grad_out,
                    const int32_t* valid_count, void* grad_stu, void* stream);
+
+/* ---- a9 + a10 fused: both criteria + the seed of the scaled backward in ONE launch ------
+ * train_human.py:425-436:  loss_s = criterion(y_s, label_s, weight_s);
+ *                          loss_c = con_criterion(y_t_stu, rectify(y_t_tea), tea_mask=tea_mask);
+ *                          loss_all = loss_s + lambda_c*loss_c;  scaler.scale(loss_all).backward()
+ * Reads every operand once and writes, besides losses[3] = {loss_all, loss_s, loss_c}:
+ *   grad_y_s     = d(grad_scale*loss_all)/d y_s      [planes_s, h, w]   in stu_dtype (optional)
+ *   grad_y_t_stu = d(grad_scale*loss_all)/d y_t_stu  [batch_t*joints, h, w] in stu_dtype (optional)
+ * y_s / y_t_stu share stu_dtype, label / tea share tgt_dtype.  grad_scale_dev (optional device
+ * float, e.g. GradScaler's scale tensor) overrides grad_scale.  If tea == NULL the rectified
+ * teacher map is never read: it is evaluated on the fly from tea_preds[batch_t*joints,2]
+ * (udape_decode's `preds`) and sigma with the same device functions udape_decode uses to
+ * materialise `rectified`, i.e. bit-identical values (utils.py:77-109).  Either pair may be
+ * absent (planes_s == 0 or batch_t == 0).  partial[planes_s + batch_t*joints] floats are
+ * caller-owned scratch; ticket: see "tickets" above; reductions are deterministic. */
+UDAPE_API int udape_loss_step(const void* y_s, const void* label, const void* weight, int w_dtype,
+                    int64_t planes_s, const void* y_t_stu, const void* tea, const float* tea_preds,
+                    double sigma, const void* tea_mask, int mask_dtype, int64_t batch_t,
+                    int64_t joints, int64_t h, int64_t w, int stu_dtype, int tgt_dtype,
+                    float lambda_c, float grad_scale, const float* grad_scale_dev, float* partial,
+                    float* losses, uint32_t* ticket, void* grad_y_s, void* grad_y_t_stu,
+                    void* stream);
 
 /* ---- a4: generate_target (batched) — lib/datasets/util.py:12-70 ----------------------
  * joints[planes,2] float64 image pixels, vis[planes] float32.  mu = trunc(j/stride+0.5)

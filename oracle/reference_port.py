@@ -56,6 +56,11 @@ def adain_mix(content_feat, style_feat, alpha=1.0):
     return alpha * t + (1 - alpha) * content_feat
 
 
+def channel_clamp(x, recover_min, recover_max):
+    """train_human.py:276,351,356 (train_animal.py:301,376,381) — the expression, verbatim."""
+    return torch.maximum(torch.minimum(x.permute(0, 2, 3, 1), recover_max), recover_min).permute(0, 3, 1, 2)
+
+
 # --------------------------------------------------------------------------------------------------
 # a7-a8  decode + PCK  (lib/keypoint_detection.py:9-94, utils.py:54-75)
 # --------------------------------------------------------------------------------------------------

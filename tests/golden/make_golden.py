@@ -286,14 +286,34 @@ def golden_ema():
     save("ema", **out)
 
 
+def golden_clamp():
+    """train_human.py:276 verbatim, with both trainers' recover_min/max constants (:32-33, train_animal.py:34-35)."""
+    out = {}
+    bounds = {"human": ([-2.1179, -2.0357, -1.8044], [2.2489, 2.4285, 2.64]),
+              "animal": ([-0.3999, -0.3909, -0.3871], [0.6001, 0.6091, 0.6129])}
+    for tag, (lo, hi) in bounds.items():
+        g = torch.Generator().manual_seed(700 + len(tag))
+        x = torch.randn(3, 3, 17, 20, generator=g) * 2.0
+        x[0, 1, 2, 3] = float("nan")
+        x[1, 0, 0, 0] = float("inf")
+        x[2, 2, 5, 5] = -float("inf")
+        recover_min, recover_max = torch.tensor(lo), torch.tensor(hi)
+        y = torch.maximum(torch.minimum(x.permute(0, 2, 3, 1), recover_max), recover_min).permute(0, 3, 1, 2)
+        out[f"{tag}_x"], out[f"{tag}_lo"], out[f"{tag}_hi"], out[f"{tag}_y"] = x, recover_min, recover_max, y.contiguous()
+    save("clamp", **out)
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit(f"reference tree not found at {ref_loader.REFERENCE_ROOT}")
     torch.manual_seed(0)
     np.random.seed(0)
-    for fn in (golden_adain, golden_decode, golden_accuracy, golden_losses, golden_masks, golden_rectify,
-               golden_targets, golden_ema):
-        fn()
+    fns = (golden_adain, golden_decode, golden_accuracy, golden_losses, golden_masks, golden_rectify,
+           golden_targets, golden_ema, golden_clamp)
+    only = set(sys.argv[1:])  # e.g. `make_golden.py clamp` regenerates one fixture
+    for fn in fns:
+        if not only or fn.__name__.removeprefix("golden_") in only:
+            fn()
 
 
 if __name__ == "__main__":

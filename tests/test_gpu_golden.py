@@ -236,3 +236,10 @@ def test_ema_golden(golden, dev):
         g["mema_buffers_after"])
     mema.momentum_update(model, 0.9)
     np.testing.assert_array_equal(_flat(mema.ema.parameters()), g["mema_after_momentum"])
+
+
+@pytest.mark.parametrize("tag", ["human", "animal"])
+def test_channel_clamp_golden(golden, dev, tag):
+    g = golden("clamp")
+    y = U.channel_clamp(C(g[f"{tag}_x"], dev), C(g[f"{tag}_lo"], dev), C(g[f"{tag}_hi"], dev))
+    np.testing.assert_array_equal(y.cpu().numpy(), g[f"{tag}_y"])  # pure selection: bit-exact incl. NaN/Inf

@@ -48,7 +48,7 @@ def _oracle_step(host, a1, a2, teacher, student, scale=65536.0):
     ((loss_s + 1.0 * loss_c) * scale).backward()
     R.ema_step(teacher, student, 0.999)
     hits, valid, pred = R.pck_counts(host["y_s"].numpy(), host["label_s"].numpy())
-    return dict(t_s2t=t1, t_t2s=t2, conf_table=table, position=pos, tea_mask=mask, rectified=rect,
+    return dict(y_t_tea=host["y_t_tea"], t_s2t=t1, t_t2s=t2, conf_table=table, position=pos, tea_mask=mask, rectified=rect,
                 loss_s=loss_s.detach(), loss_c=loss_c.detach(), grad_y_s=y_s.grad, grad_y_t_stu=y_t.grad,
                 hits=hits, valid=valid, pred=pred)
 
@@ -59,7 +59,9 @@ def _check(out, ref):
     assert torch.equal(out["conf_table"].cpu(), ref["conf_table"])
     assert torch.equal(out["position"].cpu(), ref["position"])
     assert torch.equal(out["tea_mask"].cpu(), ref["tea_mask"])
-    assert_close_scaled(out["rectified"], ref["rectified"], 1e-5, "rectified")
+    if out["rectified"] is not None:  # unfused route materialises rectify(y_t_tea)
+        assert_close_scaled(out["rectified"], ref["rectified"], 1e-5, "rectified")
+    np.testing.assert_array_equal(out["tea_preds"].cpu().numpy(), R.get_max_preds_torch(ref["y_t_tea"])[0].numpy())
     assert_close_scaled(out["loss_s"], ref["loss_s"], 1e-5, "loss_s")
     assert_close_scaled(out["loss_c"], ref["loss_c"], 1e-5, "loss_c")
     assert_close_scaled(out["loss_all"], ref["loss_s"] + ref["loss_c"], 1e-5, "loss_all")
@@ -69,13 +71,14 @@ def _check(out, ref):
     np.testing.assert_array_equal(out["pred"].cpu().numpy(), ref["pred"])
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("parallel", [False, True])
-def test_step_eager_vs_oracle(dev, parallel):
+def test_step_eager_vs_oracle(dev, parallel, fused):
     host, inp = _inputs(dev)
     shapes = [(64, 3, 7, 7), (64,), (17,), (256, 64, 1, 1), (5000,)]
     s_cpu, t_cpu = S.parameter_list(shapes, 1), S.parameter_list(shapes, 2)
     student, teacher = Bag(s_cpu).to(dev), Bag(t_cpu).to(dev)
-    step = HotPathStep(teacher, student, sigma=2, parallel=parallel)
+    step = HotPathStep(teacher, student, sigma=2, parallel=parallel, fused=fused)
     R.ema_init(t_cpu, s_cpu)
     for it in range(2):
         out = step.run(inp)
@@ -86,12 +89,13 @@ def test_step_eager_vs_oracle(dev, parallel):
             assert torch.equal(p.detach().cpu(), e)
 
 
-def test_step_graph_replay_with_device_alpha(dev):
+@pytest.mark.parametrize("fused,ema_parallel", [(True, True), (True, False), (False, True)])
+def test_step_graph_replay_with_device_alpha(dev, fused, ema_parallel):
     host, inp = _inputs(dev, seed=11)
     shapes = [(128, 64, 3, 3), (128,), (33,)]
     s_cpu, t_cpu = S.parameter_list(shapes, 3), S.parameter_list(shapes, 4)
     student, teacher = Bag(s_cpu).to(dev), Bag(t_cpu).to(dev)
-    step = HotPathStep(teacher, student, sigma=2)
+    step = HotPathStep(teacher, student, sigma=2, fused=fused, ema_parallel=ema_parallel)
     R.ema_init(t_cpu, s_cpu)
     step.capture(inp, include_ema=True, warmup=2)  # 2 eager warm-up steps + the capture pass do not replay
     for _ in range(2):
@@ -112,6 +116,8 @@ def test_step_graph_replay_with_device_alpha(dev):
 
 def test_step_bytes_accounting(dev):
     _, inp = _inputs(dev, b=2, k=16)
-    by = step_algorithmic_bytes(inp, n_params=1000)
+    for fused in (True, False):
+        by = step_algorithmic_bytes(inp, n_params=1000, fused=fused)
+        assert by["total"] == sum(v for k_, v in by.items() if k_ != "total")
     assert by["ema"] == 12000 and by["adain_mix"] == 2 * 3 * inp.feat_src.numel() * 4
     assert by["total"] == sum(v for k_, v in by.items() if k_ != "total")

@@ -317,3 +317,152 @@ def test_ema_16bit_and_stale_plan(dev):
     before = a.weight.detach().clone()
     opt.step()
     assert torch.equal(a.weight.detach(), before * 0.5 + 3.0 * 0.5)
+
+
+# ---------------------------------------------------------------- clamp + fused loss step ------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(32, 3, 256, 256), (2, 3, 7, 9), (1, 5, 33, 1)])
+def test_channel_clamp_vs_oracle(dev, dtype, shape):
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(*shape, generator=g) * 2).to(dtype)
+    c = shape[1]
+    lo = -torch.rand(c, generator=g) - 0.3
+    hi = torch.rand(c, generator=g) + 0.3
+    ref = R.channel_clamp(x.float(), lo, hi).to(dtype)  # bounds are fp32; selection commutes with rounding of x only
+    # values selected from the bounds are rounded to x's dtype by the store
+    y = U.channel_clamp(x.to(dev), lo.to(dev), hi.to(dev))
+    assert y.is_contiguous() and y.dtype == dtype
+    assert torch.equal(y.cpu(), ref.contiguous())
+    # in place
+    xd = x.to(dev)
+    U.channel_clamp(xd, lo.to(dev), hi.to(dev), out=xd)
+    assert torch.equal(xd.cpu(), ref.contiguous())
+
+
+@pytest.mark.parametrize("cfg", ["C1", "C2", "C4"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_fused_losses_vs_oracle(dev, cfg, dtype):
+    """udape_loss_step == JointsMSELoss + lambda_c*ConsLoss of the reference, and the gradients of
+    scale*loss_all from autograd through the reference modules (train_human.py:425-436)."""
+    b, k, sigma = S.CONFIGS[cfg]["batch"], S.CONFIGS[cfg]["joints"], S.CONFIGS[cfg]["sigma"]
+    rtol = 1e-5 if dtype == torch.float32 else 1e-2
+    scale, lam = 65536.0, 0.7
+    y_s = S.heatmaps(b, k, seed=20).to(dtype)
+    y_t = S.heatmaps(b, k, seed=21).to(dtype)
+    label = S.heatmaps(b, k, seed=22, noise=0.0)
+    weight = (torch.rand(b, k, 1, generator=torch.Generator().manual_seed(23)) > 0.1).float()
+    tea_raw = S.heatmaps(b, k, seed=24, peak=(0.3, 1.2))
+    tea_raw[0, 0] = -1.0  # all-negative plane: rectify pastes at (0, 0)
+    tea = R.rectify(tea_raw, sigma)
+    tea_mask, _, _ = R.consistency_mask(tea_raw, 0.5)
+    o1 = y_s.float().clone().requires_grad_(True)
+    o2 = y_t.float().clone().requires_grad_(True)
+    l_s = R.joints_mse_loss(o1, label, weight)
+    l_c = R.cons_loss(o2, tea, tea_mask=tea_mask)
+    l_all = l_s + lam * l_c
+    (l_all * scale).backward()
+    gs = torch.full((1,), scale, device=dev)
+    for route in ("materialised", "analytic"):
+        if route == "materialised":
+            losses, g1, g2 = U.fused_losses(y_s.to(dev), label.to(dev), weight.to(dev), y_t.to(dev), tea.to(dev),
+                                            tea_mask.to(dev), lambda_c=lam, grad_scale=gs)
+        else:
+            d = U.decode(tea_raw.to(dev), want_preds=True)
+            losses, g1, g2 = U.fused_losses(y_s.to(dev), label.to(dev), weight.to(dev), y_t.to(dev), None,
+                                            tea_mask.to(dev), lambda_c=lam, grad_scale=scale,
+                                            tea_preds=d["preds"], sigma=sigma)
+        assert g1.dtype == dtype and g2.dtype == dtype
+        assert_close_scaled(losses[0], l_all.detach(), 1e-5, f"{route} loss_all")
+        assert_close_scaled(losses[1], l_s.detach(), 1e-5, f"{route} loss_s")
+        assert_close_scaled(losses[2], l_c.detach(), 1e-5, f"{route} loss_c")
+        assert_close_scaled(g1.float(), o1.grad, rtol, f"{route} grad y_s")
+        assert_close_scaled(g2.float(), o2.grad, rtol, f"{route} grad y_t_stu")
+    # the two routes use the same device functions for the rectified values: identical bits
+    la, ga1, ga2 = U.fused_losses(y_s.to(dev), label.to(dev), weight.to(dev), y_t.to(dev), U.rectify(tea_raw.to(dev), sigma),
+                                  tea_mask.to(dev), lambda_c=lam, grad_scale=scale)
+    assert torch.equal(la, losses) and torch.equal(ga2, g2) and torch.equal(ga1, g1)
+
+
+def test_fused_losses_partial_and_odd_shapes(dev):
+    g = torch.Generator().manual_seed(9)
+    for shape in [(2, 3, 5, 7), (1, 1, 1, 1), (3, 2, 9, 13)]:
+        o = torch.randn(*shape, generator=g)
+        t = torch.randn(*shape, generator=g)
+        w = torch.rand(shape[0], shape[1], 1, generator=g)
+        tm = torch.rand(shape[0], shape[1], generator=g) > 0.4
+        o1 = o.clone().requires_grad_(True)
+        l1 = R.joints_mse_loss(o1, t, w)
+        l1.backward()
+        losses, g1, g2 = U.fused_losses(o.to(dev), t.to(dev), w.to(dev), None)
+        assert g2 is None
+        assert_close_scaled(losses[1], l1.detach(), 1e-5, f"mse only {shape}")
+        assert_close_scaled(g1, o1.grad, 1e-5, f"mse-only grad {shape}")
+        assert float(losses[2]) == 0.0
+        s1 = o.clone().requires_grad_(True)
+        c1 = R.cons_loss(s1, t, tea_mask=tm)
+        (2.0 * c1).backward()
+        losses, g1, g2 = U.fused_losses(None, None, None, o.to(dev), t.to(dev), tm.to(dev), lambda_c=2.0)
+        assert g1 is None
+        assert_close_scaled(losses[2], c1.detach(), 1e-5, f"cons only {shape}")
+        assert_close_scaled(losses[0], 2.0 * c1.detach(), 1e-5, f"cons only all {shape}")
+        assert_close_scaled(g2, s1.grad, 1e-5, f"cons-only grad {shape}")
+
+
+# ---------------------------------------------------------------- TMA-staged vs register-staged paths --------
+def _with_env(name, value, fn):
+    import os
+    old = os.environ.get(name)
+    os.environ[name] = value
+    try:
+        return fn()
+    finally:
+        if old is None:
+            del os.environ[name]
+        else:
+            os.environ[name] = old
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_decode_and_pck_tma_equals_generic(dev, dtype):
+    """>= 2048 planes route decode / PCK through the cp.async.bulk pipeline (csrc/pipeline.cuh); both
+    routes must agree bit for bit with each other and with numpy/torch on adversarial planes (ties,
+    -0.0/+0.0, all-negative, NaN/Inf, fp16 quantisation)."""
+    adv = S.adversarial_heatmaps(k=4)                                    # [10,4,64,64]
+    rnd = S.heatmaps(60, 21, seed=77)                                    # 1260 planes
+    x = torch.cat([adv.reshape(-1, 64, 64), rnd.reshape(-1, 64, 64)] * 2).reshape(-1, 20, 64, 64).to(dtype)
+    assert x.shape[0] * x.shape[1] >= 2048
+    xd = x.to(dev)
+    kw = dict(want_idx=True, want_maxvals=True, want_preds=True, want_position=True, occlude_thresh=0.9)
+    tma = _with_env("UDAPE_NO_TMA", "0", lambda: U.decode(xd, **kw))
+    gen = _with_env("UDAPE_NO_TMA", "1", lambda: U.decode(xd, **kw))
+    b, k = x.shape[:2]
+    ref_idx = torch.argmax(x.float().view(b, k, -1), 2)
+    for r in (tma, gen):
+        assert torch.equal(r["idx"].cpu().long(), ref_idx)
+        assert torch.equal(r["preds"].cpu(), R.get_max_preds_torch(x.float())[0])
+        np.testing.assert_array_equal(r["maxvals"].float().cpu().numpy()[..., 0],
+                                      torch.amax(x.view(b, k, -1), 2).float().numpy())
+    for key in tma:
+        a, g = tma[key], gen[key]
+        assert torch.equal(a.view(torch.uint8) if a.dtype == torch.bool else a.float().nan_to_num(nan=12345.0),
+                           g.view(torch.uint8) if g.dtype == torch.bool else g.float().nan_to_num(nan=12345.0)), key
+    other = torch.roll(x, 3, dims=0).float()
+    ref = R.pck_counts(x.float().numpy() if dtype != torch.float16 else x.numpy(), other.numpy())
+    for flag in ("0", "1"):
+        hits, valid, pred = _with_env("UDAPE_NO_TMA", flag, lambda: U.pck_counts(xd, other.to(dev)))
+        np.testing.assert_array_equal(hits.cpu().numpy(), ref[0])
+        np.testing.assert_array_equal(valid.cpu().numpy(), ref[1])
+        np.testing.assert_array_equal(pred.cpu().numpy(), ref[2])
+
+
+def test_tickets_are_self_resetting(dev):
+    """Back-to-back reductions reuse ticket words without any memset (include/udape.h "tickets")."""
+    o = S.heatmaps(8, 16, seed=1).to(dev)
+    t = S.heatmaps(8, 16, seed=2, noise=0.0).to(dev)
+    first = [float(U.JointsMSELoss()(o, t)) for _ in range(3)]
+    many = [float(U.JointsMSELoss()(o, t)) for _ in range(5000)]  # wraps the 4096-slot rotation
+    assert len(set(first + many)) == 1
+    from uda_poseestimation_b200 import _lib
+    pool = _lib._ticket_pools[dev.index or 0]
+    torch.cuda.synchronize()
+    assert int(pool.buf.abs().sum()) == 0

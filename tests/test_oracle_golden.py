@@ -158,3 +158,10 @@ def test_ema(golden):
     model = _split_like(g["mema_model"], protos)
     R.model_ema_update(ema, model, 0.99)
     np.testing.assert_array_equal(np.concatenate([t.numpy().ravel() for t in ema]), g["mema_after"])
+
+
+@pytest.mark.parametrize("tag", ["human", "animal"])
+def test_channel_clamp(golden, tag):
+    g = golden("clamp")
+    y = R.channel_clamp(torch.from_numpy(g[f"{tag}_x"]), torch.from_numpy(g[f"{tag}_lo"]), torch.from_numpy(g[f"{tag}_hi"]))
+    np.testing.assert_array_equal(y.contiguous().numpy(), g[f"{tag}_y"])

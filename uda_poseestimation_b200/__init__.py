@@ -17,23 +17,23 @@ Reference name → module here
     train_human.py:376-383,427-430 (inline)    : confidence_mask, consistency_mask, teacher_targets
 """
 from ._lib import UdapeError, library_path, load as load_library
-from .adain import adain, adain_mix, adaptive_instance_normalization, calc_mean_std
+from .adain import adain, adain_mix, adaptive_instance_normalization, calc_mean_std, channel_clamp
 from .ema import ModelEMA, MultiTensorPlan, OldWeightEMA
 from .heatmap import (draw_labelmap_batched, draw_labelmap_ori, generate_target, generate_target_batched,
                       rectify)
 from .keypoint_detection import (accuracy, accuracy_from_counts, calc_dists, decode, dist_acc, get_max_preds,
                                  get_max_preds_torch, pck_counts)
-from .loss import ConsLoss, JointsMSELoss, cons_loss, joints_mse_loss
+from .loss import ConsLoss, JointsMSELoss, cons_loss, fused_losses, joints_mse_loss
 from .mask import confidence_mask, consistency_mask, teacher_targets
 
 __version__ = "0.1.0"
 
 __all__ = [
     "UdapeError", "library_path", "load_library",
-    "calc_mean_std", "adaptive_instance_normalization", "adain", "adain_mix",
+    "calc_mean_std", "adaptive_instance_normalization", "adain", "adain_mix", "channel_clamp",
     "get_max_preds", "get_max_preds_torch", "calc_dists", "dist_acc", "accuracy", "pck_counts",
     "accuracy_from_counts", "decode",
-    "JointsMSELoss", "ConsLoss", "joints_mse_loss", "cons_loss",
+    "JointsMSELoss", "ConsLoss", "joints_mse_loss", "cons_loss", "fused_losses",
     "generate_target", "generate_target_batched", "draw_labelmap_ori", "draw_labelmap_batched", "rectify",
     "confidence_mask", "consistency_mask", "teacher_targets",
     "OldWeightEMA", "ModelEMA", "MultiTensorPlan",

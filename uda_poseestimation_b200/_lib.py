@@ -47,11 +47,13 @@ PROTOTYPES = {
     "udape_mean_std": (c_int, [c_void_p, c_int, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p]),
     "udape_adain_mix": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p]),
+    "udape_channel_clamp": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
     "udape_decode": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_float, c_void_p, c_double, c_void_p, c_void_p]),
     "udape_mask_select": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "udape_pck_counts": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64,
-                                 c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                 c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "udape_joints_mse_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_int64,
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
     "udape_joints_mse_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_int64,
@@ -60,6 +62,10 @@ PROTOTYPES = {
                                c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "udape_cons_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64,
                                c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "udape_loss_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p,
+                                c_double, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int, c_int,
+                                c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p]),
     "udape_gauss_target": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_double, c_double,
                                    c_double, c_void_p, c_void_p, c_void_p]),
     "udape_labelmap": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_double, c_int, c_int, c_void_p,
@@ -192,3 +198,51 @@ def no_autograd(name: str, *tensors: torch.Tensor) -> None:
             f"{name}: the CUDA operator is forward-only (the trainers call it under torch.no_grad(), "
             "train_human.py:347); wrap the call in torch.no_grad() or detach the inputs"
         )
+
+
+class _TicketPool:
+    """Zero-initialised uint32 words for the kernels' last-CTA-done tickets (include/udape.h:
+    "ticket must be zero on entry; the call leaves it zero").  The words are self-resetting, so a
+    slot can be handed out again without a memset; slots rotate so that kernels running
+    concurrently on different streams never share one, and a slot baked into a CUDA graph during
+    stream capture is retired from the rotation for good."""
+
+    SLOTS = 4096
+
+    def __init__(self, dev: torch.device):
+        self.buf = torch.zeros(self.SLOTS, dtype=torch.int32, device=dev)
+        self.base = self.buf.data_ptr()
+        self.reserved = 0          # [0, reserved) belong to captured graphs
+        self.cursor = 0            # rotation over [reserved, SLOTS)
+        self.spill = []            # extra buffers once graphs have eaten half the pool
+
+    def take(self) -> int:
+        if torch.cuda.is_current_stream_capturing():
+            if self.reserved >= self.SLOTS // 2:
+                extra = torch.zeros(1, dtype=torch.int32, device=self.buf.device)
+                self.spill.append(extra)  # kept alive for the life of the process, like the graph
+                return extra.data_ptr()
+            slot = self.reserved
+            self.reserved += 1
+            return self.base + 4 * slot
+        span = self.SLOTS - self.reserved
+        slot = self.reserved + self.cursor % span
+        self.cursor += 1
+        return self.base + 4 * slot
+
+
+_ticket_pools: dict = {}
+
+
+def ticket(dev: torch.device) -> int:
+    """Device address of a zeroed, self-resetting uint32 ticket word on ``dev``."""
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    with _lock:
+        pool = _ticket_pools.get(idx)
+        if pool is None:
+            with torch.cuda.device(idx):
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("the first loss/PCK call on a device must happen before CUDA-graph capture "
+                                       "(it allocates the ticket pool); run one warm-up step first")
+                pool = _ticket_pools[idx] = _TicketPool(torch.device("cuda", idx))
+        return pool.take()

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["calc_mean_std", "adaptive_instance_normalization", "adain", "adain_mix"]
+__all__ = ["calc_mean_std", "adaptive_instance_normalization", "adain", "adain_mix", "channel_clamp"]
 
 
 def _planes(feat: torch.Tensor, name: str):
@@ -91,3 +91,36 @@ def adaptive_instance_normalization(content_feat: torch.Tensor, style_feat: torc
 
 # lib/models/Style_net.py:21 names the same function `adain`
 adain = adaptive_instance_normalization
+
+
+def channel_clamp(x: torch.Tensor, lo: torch.Tensor, hi: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Per-channel clamp of a stylised image batch, the expression every trainer applies to the
+    style-transfer output (``train_human.py:276,351,356``)::
+
+        torch.maximum(torch.minimum(x.permute(0,2,3,1), recover_max), recover_min).permute(0,3,1,2)
+
+    ``x`` is ``[N,C,H,W]``; ``lo`` / ``hi`` are the ``[C]`` tensors ``recover_min`` / ``recover_max``.
+    One contiguous pass (the reference makes two permuted ones and returns a channels-last view;
+    this returns a contiguous NCHW tensor with the same values).  ``out=x`` clamps in place.
+    """
+    if x.dim() != 4:
+        raise ValueError(f"channel_clamp: expected [N,C,H,W], got {tuple(x.shape)}")
+    n, c, h, w = x.shape
+    dev = _lib.require_cuda(x, lo, hi)
+    _lib.no_autograd("channel_clamp", x)
+    if lo.numel() != c or hi.numel() != c:  # broadcasting against the permuted [..., C] tensor
+        raise RuntimeError(f"channel_clamp: bounds must have C = {c} entries, got {lo.numel()} / {hi.numel()}")
+    x = x.contiguous()
+    lo = lo.detach().to(torch.float32).contiguous()
+    hi = hi.detach().to(torch.float32).contiguous()
+    code = _lib.float_code(x)
+    if out is None:
+        out = torch.empty_like(x)
+    elif out.shape != x.shape or out.dtype != x.dtype or not out.is_contiguous():
+        raise ValueError("channel_clamp: `out` must be a contiguous tensor shaped and typed like x")
+    if x.numel() > 0:
+        with _lib.on_device(dev):
+            st = _lib.load().udape_channel_clamp(x.data_ptr(), code, n * c, c, h * w, lo.data_ptr(), hi.data_ptr(),
+                                                 out.data_ptr(), _lib.stream_ptr(dev))
+        _lib.check(st, "channel_clamp")
+    return out

@@ -1,9 +1,11 @@
 // api.cu — library-level entry points and the error plumbing shared by every op.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
+#include "pipeline.cuh"
 
 namespace udape {
 
@@ -24,6 +26,38 @@ int check_launch(const char* what) {
                     cudaGetErrorString(e));
     }
     return UDAPE_OK;
+}
+
+// ---- persistent-grid sizing for the TMA-staged kernels (pipeline.cuh) ------------------------
+static int sm_count_of_current_device() {
+    static int cached[64] = {0};  // benign race: every thread writes the same value
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+int pipe_grid(int64_t planes) {
+    const int64_t sms = sm_count_of_current_device();
+    // one persistent CTA per SM; with fewer planes than SMs, one plane per CTA
+    const int64_t g = planes < sms ? planes : sms;
+    return static_cast<int>(g > 0 ? g : 1);
+}
+
+int pipe_stage_cap() {
+    const char* e = std::getenv("UDAPE_PIPE_STAGES");
+    const int v = e ? std::atoi(e) : 0;
+    return (v > 0 && v <= kMaxStages) ? v : kMaxStages;
+}
+
+bool pipe_enabled() {
+    // read on every call so that tests can compare both code paths within one process
+    const char* e = std::getenv("UDAPE_NO_TMA");
+    return !(e && e[0] == '1');
 }
 
 }  // namespace udape

@@ -161,6 +161,11 @@ template <typename T, int G> struct Pack {
         if constexpr (BYTES == 16) raw = ldg_stream(p);
         else { const uint2 t = ldg_stream8(p); raw = make_uint4(t.x, t.y, 0u, 0u); }
     }
+    // same slice out of a shared-memory staged plane
+    __device__ __forceinline__ void load_shared(const void* p) {
+        if constexpr (BYTES == 16) raw = *reinterpret_cast<const uint4*>(p);
+        else { const uint2 t = *reinterpret_cast<const uint2*>(p); raw = make_uint4(t.x, t.y, 0u, 0u); }
+    }
     __device__ __forceinline__ void get(float* f) const {
         if constexpr (BYTES == 16) unpack16<T>(raw, f);
         else {  // 4 x 16-bit
@@ -245,6 +250,43 @@ __device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v
     __syncthreads();
     unsigned long long t = (lane < WARPS) ? red[lane] : 0ull;
     return warp_max_u64(t);
+}
+
+
+// Runtime-size variants (any blockDim.x that is a multiple of 32, <= 1024).
+__device__ __forceinline__ float block_sum_rt(float v, float* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // protect `red` against the previous use
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = (lane < warps) ? red[lane] : 0.0f;
+    return warp_sum(t);
+}
+
+// ---- last-CTA-done ticket ------------------------------------------------------------------------
+// Deterministic grid-wide reductions: every CTA publishes its partials, takes a ticket, and the CTA
+// that draws the last one reduces all partials in a fixed order.  `ticket` is a caller-owned uint32
+// that must be ZERO on entry; atomicInc wraps it back to zero with the last ticket, so the same word
+// can be reused by the next launch without a memset (no extra graph node, no extra launch).
+// Call from all threads of the CTA, after the CTA's partials have been written by thread 0 / lane 0s
+// and a __syncthreads().  Returns true in every thread of the last CTA.
+__device__ __forceinline__ bool last_block_done(uint32_t* ticket, unsigned total) {
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+        __threadfence();  // publish this CTA's partials before taking a ticket
+        const unsigned t = atomicInc(ticket, total - 1u);
+        is_last = (t == total - 1u);
+        if (is_last) __threadfence();  // acquire the other CTAs' partials
+    }
+    __syncthreads();
+    return is_last;
+}
+// fixed-order sum of n floats by one CTA (any block size)
+__device__ __forceinline__ float cta_sum_array(const volatile float* v, int64_t n, float* red) {
+    float s = 0.0f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
+    return block_sum_rt(s, red);
 }
 
 }  // namespace udape

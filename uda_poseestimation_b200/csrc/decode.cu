@@ -17,21 +17,37 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "gauss.cuh"
+#include "pipeline.cuh"
 
 namespace udape {
 
 constexpr int kDecThreads = 256;
 constexpr int kDecUnroll = 4;
+constexpr int64_t kTmaMinPlanes = 2048;
 
-// window geometry of the unit-peak Gaussian, derived on the host from sigma exactly as
-// utils.py:81,93-98 derives it in Python
-struct GaussWindow {
-    float tmp;    // 3*sigma                       (utils.py:81)
-    int n;        // len(arange(0, 2*tmp+1, 1))    (utils.py:93-94)
-    float x0;     // (2*tmp+1) // 2                (utils.py:96)
-    float denom;  // 2*sigma**2                    (utils.py:98)
-};
+template <typename T> __device__ __forceinline__ float vec_max_nan(const uint4& v);
+template <> __device__ __forceinline__ float vec_max_nan<float>(const uint4& v) {
+    return fmax_nan(fmax_nan(__uint_as_float(v.x), __uint_as_float(v.y)),
+                    fmax_nan(__uint_as_float(v.z), __uint_as_float(v.w)));
+}
+template <> __device__ __forceinline__ float vec_max_nan<__half>(const uint4& v) {
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+    const __half2 m = __hmax2_nan(__hmax2_nan(h[0], h[1]), __hmax2_nan(h[2], h[3]));
+    return fmax_nan(__low2float(m), __high2float(m));
+}
+template <> __device__ __forceinline__ float vec_max_nan<__nv_bfloat16>(const uint4& v) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+    const __nv_bfloat162 m = __hmax2_nan(__hmax2_nan(h[0], h[1]), __hmax2_nan(h[2], h[3]));
+    return fmax_nan(__low2float(m), __high2float(m));
+}
 
+// One thread's share of a plane -> packed (ordered key of its maximum, ~index of the first
+// occurrence).  The scan itself works at vector granularity with plain float maxima (about 1.5
+// instructions per element): `best` is the NaN-ignoring maximum with strict > (keeps the first
+// vector), `all` the NaN-propagating one.  Only the winning vector is looked at element by
+// element, and only then is the exact ordered key formed — so the block reduction stays the
+// exact, order-independent u64 maximum (first index wins, NaN is the maximum, -0.0 == +0.0).
 template <typename T, bool VEC>
 __device__ __forceinline__ unsigned long long thread_plane_argmax(const T* __restrict__ p, int hw) {
     uint32_t best_key = 0u, best_idx = 0xffffffffu;
@@ -39,6 +55,8 @@ __device__ __forceinline__ unsigned long long thread_plane_argmax(const T* __res
         constexpr int EPV = Vec16<T>::EPV;
         const int nvec = hw / EPV;
         const uint4* p4 = reinterpret_cast<const uint4*>(p);
+        float best = -INFINITY, all = -INFINITY;
+        int bv = -1;
         for (int base = 0; base < nvec; base += kDecThreads * kDecUnroll) {
             uint4 v[kDecUnroll];
 #pragma unroll
@@ -50,16 +68,32 @@ __device__ __forceinline__ unsigned long long thread_plane_argmax(const T* __res
             for (int u = 0; u < kDecUnroll; ++u) {
                 const int i = base + u * kDecThreads + threadIdx.x;
                 if (i < nvec) {
-                    float f[EPV];
-                    unpack16<T>(v[u], f);
-#pragma unroll
-                    for (int e = 0; e < EPV; ++e) {
-                        const uint32_t k = order_key(f[e]);
-                        // indices visited by one thread are increasing: strict > keeps the first
-                        if (k > best_key) { best_key = k; best_idx = i * EPV + e; }
-                    }
+                    const float vm = vec_max_nan<T>(v[u]);
+                    all = fmax_nan(all, vm);
+                    if (vm > best) { best = vm; bv = i; }
                 }
             }
+        }
+        if (all != all) {
+            // rare: this thread's first NaN
+            for (int i = threadIdx.x; i < nvec && best_idx == 0xffffffffu; i += kDecThreads) {
+                float f[EPV];
+                unpack16<T>(ldg_cached(p4 + i), f);
+#pragma unroll
+                for (int e = EPV - 1; e >= 0; --e)
+                    if (f[e] != f[e]) best_idx = static_cast<uint32_t>(i * EPV + e);
+            }
+            best_key = 0xffffffffu;
+        } else if (bv >= 0) {
+            float f[EPV];
+            unpack16<T>(ldg_cached(p4 + bv), f);
+#pragma unroll
+            for (int e = EPV - 1; e >= 0; --e)
+                if (f[e] == best) best_idx = static_cast<uint32_t>(bv * EPV + e);
+            best_key = order_key(best);
+        } else if (static_cast<int>(threadIdx.x) < nvec) {
+            best_key = order_key(-INFINITY);  // everything this thread saw is -inf: its first element
+            best_idx = threadIdx.x * EPV;
         }
     } else {
         for (int i = threadIdx.x; i < hw; i += kDecThreads) {
@@ -70,17 +104,26 @@ __device__ __forceinline__ unsigned long long thread_plane_argmax(const T* __res
     return pack_arg(best_key, best_idx);
 }
 
-// zeros + clipped Gaussian window, following utils.py:84-107 (including its use of h for
-// the x bound and w for the y bound)
+// One 16-byte vector (EPV elements starting at flat index `flat`) of the rectified plane.
+// Almost every vector of a plane lies outside the (6*sigma+1)^2 window: when the vector does not
+// straddle rows and misses the window's clipped range it is zeros without any per-element work.
 template <typename T>
-__device__ __forceinline__ float rectified_value(int x, int y, int ul_x, int ul_y, int x0i, int x1i,
-                                                 int y0i, int y1i, const GaussWindow& g) {
-    if (x < x0i || x >= x1i || y < y0i || y >= y1i) return 0.0f;
-    const int gx = x - ul_x, gy = y - ul_y;
-    if (gx >= g.n || gy >= g.n) return 0.0f;
-    const float dx = static_cast<float>(gx) - g.x0, dy = static_cast<float>(gy) - g.x0;
-    const float d2 = dx * dx + dy * dy;
-    return expf(-(d2 / g.denom));
+__device__ __forceinline__ uint4 rectified_vector_at(int x, int y, int w, const RectGeom& geom, const GaussWindow& gw) {
+    constexpr int EPV = Vec16<T>::EPV;
+    if (x + EPV <= w && (y < geom.y0i || y >= geom.y1i || x + EPV <= geom.x0i || x >= geom.x1i))
+        return make_uint4(0u, 0u, 0u, 0u);
+    float f[EPV];
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) {
+        f[e] = rectified_value(x, y, geom, gw);
+        if (++x == w) { x = 0; ++y; }
+    }
+    return pack16<T>(f);
+}
+template <typename T>
+__device__ __forceinline__ uint4 rectified_vector(int flat, int w, const RectGeom& geom, const GaussWindow& gw) {
+    const int y = flat / w;
+    return rectified_vector_at<T>(flat - y * w, y, w, geom, gw);
 }
 
 template <typename T, bool VEC>
@@ -115,51 +158,151 @@ decode_kernel(const T* __restrict__ hm, int hw, int w, int h, int32_t* __restric
     // ---- rectify: utils.py:84-107 ----
     const float mu_x = positive ? static_cast<float>(ix) : 0.0f;
     const float mu_y = positive ? static_cast<float>(iy) : 0.0f;
-    const int ul_x = static_cast<int>(mu_x - gw.tmp), ul_y = static_cast<int>(mu_y - gw.tmp);
-    const int br_x = static_cast<int>(mu_x + gw.tmp + 1.0f), br_y = static_cast<int>(mu_y + gw.tmp + 1.0f);
-    const bool skip = (mu_x >= static_cast<float>(h)) || (mu_y >= static_cast<float>(w));
-    int x0i = max(0, ul_x), x1i = min(min(br_x, h), w);
-    int y0i = max(0, ul_y), y1i = min(min(br_y, w), h);
-    if (skip) { x1i = x0i = 0; y1i = y0i = 0; }
+    const RectGeom geom = rect_geometry(mu_x, mu_y, h, w, gw);
     T* r = rect + plane * hw;
     if (VEC) {
         constexpr int EPV = Vec16<T>::EPV;
         const int nvec = hw / EPV;
         uint4* r4 = reinterpret_cast<uint4*>(r);
-        for (int i = threadIdx.x; i < nvec; i += kDecThreads) {
-            const int flat = i * EPV;
-            int y = flat / w, x = flat - y * w;
-            float f[EPV];
-#pragma unroll
-            for (int e = 0; e < EPV; ++e) {
-                f[e] = rectified_value<T>(x, y, ul_x, ul_y, x0i, x1i, y0i, y1i, gw);
-                if (++x == w) { x = 0; ++y; }
-            }
-            stg_stream(r4 + i, pack16<T>(f));
-        }
+        for (int i = threadIdx.x; i < nvec; i += kDecThreads)
+            stg_stream(r4 + i, rectified_vector<T>(i * EPV, w, geom, gw));
     } else {
         for (int i = threadIdx.x; i < hw; i += kDecThreads) {
             const int y = i / w, x = i - y * w;
-            r[i] = from_f32<T>(rectified_value<T>(x, y, ul_x, ul_y, x0i, x1i, y0i, y1i, gw));
+            r[i] = from_f32<T>(rectified_value(x, y, geom, gw));
         }
     }
 }
 
+// ---- TMA-staged warp-per-plane arg-max (pipeline.cuh) ---------------------------------------
+// The plane sits in shared memory; a warp scans it once with 128-bit LDS keeping, per lane, the
+// NaN-ignoring running maximum at vector granularity (strict > keeps the first vector) and a
+// NaN-propagating maximum of everything (FMNMX.NAN).  One CREDUX.MAX.F32.NAN gives the plane
+// maximum m (NaN iff the plane holds a NaN); lanes whose maximum equals m look up the first
+// matching element of their winning vector and one integer redux.min yields the first index.
+// Floating-point == makes -0.0 and +0.0 tie, so the first of them wins, like numpy/torch.
+struct PlaneMax {
+    float val;     // plane maximum (NaN if the plane holds a NaN)
+    uint32_t idx;  // flat index of its first occurrence
+};
+
+template <typename T>
+__device__ __forceinline__ PlaneMax warp_argmax_smem(const uint8_t* __restrict__ src, int nvec, int lane) {
+    constexpr int EPV = Vec16<T>::EPV;
+    float best = -INFINITY, all = -INFINITY;
+    int bv = lane;
+#pragma unroll 4
+    for (int v = lane; v < nvec; v += 32) {
+        const float vm = vec_max_nan<T>(lds128(src + 16 * v));
+        all = fmax_nan(all, vm);
+        if (vm > best) { best = vm; bv = v; }
+    }
+    PlaneMax r;
+    r.val = warp_max_nan(all);
+    uint32_t idx = 0xffffffffu;
+    if (r.val != r.val) {
+        // rare: first NaN of the plane
+        for (int v = lane; v < nvec && idx == 0xffffffffu; v += 32) {
+            float f[EPV];
+            unpack16<T>(lds128(src + 16 * v), f);
+#pragma unroll
+            for (int e = EPV - 1; e >= 0; --e)
+                if (f[e] != f[e]) idx = static_cast<uint32_t>(v * EPV + e);
+        }
+    } else if (best == r.val && bv < nvec) {
+        float f[EPV];
+        unpack16<T>(lds128(src + 16 * bv), f);
+#pragma unroll
+        for (int e = EPV - 1; e >= 0; --e)
+            if (f[e] == r.val) idx = static_cast<uint32_t>(bv * EPV + e);
+    }
+    r.idx = __reduce_min_sync(0xffffffffu, idx);
+    return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kPipeThreads, 1)
+decode_tma_kernel(const T* __restrict__ hm, int64_t planes, int hw, int w, int h, int32_t* __restrict__ idx_out,
+                  float* __restrict__ preds, T* __restrict__ maxvals, float* __restrict__ maxvals_f32,
+                  int64_t* __restrict__ position, float occlude_thresh, uint8_t* __restrict__ conf_table,
+                  GaussWindow gw, T* __restrict__ rect, int group, int stages) {
+    constexpr int EPV = Vec16<T>::EPV;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ PipeBarriers bars;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nvec = hw / EPV;
+    const uint32_t plane_bytes = 16u * nvec, stage_bytes = plane_bytes * group;
+    pipe_init(bars, stages);
+    const int n_items = pipe_items((planes + group - 1) / group);
+    if (warp == static_cast<int>(blockDim.x >> 5) - 1) {
+        pipe_produce(bars, stages, n_items, [&](int i, int s, uint64_t* full) {
+            const int64_t first = (blockIdx.x + static_cast<int64_t>(i) * gridDim.x) * group;
+            const uint32_t np = static_cast<uint32_t>(min(static_cast<int64_t>(group), planes - first));
+            mbar_expect_tx(full, np * plane_bytes);
+            bulk_load(smem + static_cast<size_t>(s) * stage_bytes, hm + first * hw, np * plane_bytes, full);
+        });
+        return;
+    }
+    constexpr int kMaxGroup = 8;  // pipe_geometry's max_group
+    PlaneMax pm[kMaxGroup];
+    pipe_consume(
+        bars, stages, n_items, warp,
+        [&](int i, int s) {
+            const int64_t first = (blockIdx.x + static_cast<int64_t>(i) * gridDim.x) * group;
+            const int np = static_cast<int>(min(static_cast<int64_t>(group), planes - first));
+#pragma unroll
+            for (int g = 0; g < kMaxGroup; ++g)
+                if (g < np)
+                    pm[g] = warp_argmax_smem<T>(smem + static_cast<size_t>(s) * stage_bytes +
+                                                    static_cast<size_t>(g) * plane_bytes, nvec, lane);
+        },
+        [&](int i) {
+            // everything below needs only the arg-max: the stage is already being refilled
+            const int64_t first = (blockIdx.x + static_cast<int64_t>(i) * gridDim.x) * group;
+            const int np = static_cast<int>(min(static_cast<int64_t>(group), planes - first));
+#pragma unroll
+            for (int g = 0; g < kMaxGroup; ++g) {
+                if (g >= np) break;
+                const int64_t plane = first + g;
+                const float mv = pm[g].val;
+                const uint32_t idx = pm[g].idx;
+                const int ix = static_cast<int>(idx % static_cast<uint32_t>(w));
+                const int iy = static_cast<int>(idx / static_cast<uint32_t>(w));
+                const bool positive = mv > 0.0f;  // false for NaN, like np.greater / torch.gt
+                if (lane == 0) {
+                    if (idx_out) idx_out[plane] = static_cast<int32_t>(idx);
+                    if (preds) {
+                        preds[2 * plane] = positive ? static_cast<float>(ix) : 0.0f;
+                        preds[2 * plane + 1] = positive ? static_cast<float>(iy) : 0.0f;
+                    }
+                    if (maxvals) maxvals[plane] = from_f32<T>(mv);
+                    if (maxvals_f32) maxvals_f32[plane] = mv;
+                    if (position) { position[2 * plane] = ix; position[2 * plane + 1] = iy; }
+                    if (conf_table) conf_table[plane] = (mv >= occlude_thresh) ? 1 : 0;
+                }
+                if (rect != nullptr) {
+                    // ---- rectify: utils.py:84-107 ----
+                    const RectGeom geom = rect_geometry(positive ? static_cast<float>(ix) : 0.0f,
+                                                        positive ? static_cast<float>(iy) : 0.0f, h, w, gw);
+                    uint4* r4 = reinterpret_cast<uint4*>(rect + plane * hw);
+                    int y = (lane * EPV) / w, x = lane * EPV - y * w;  // one division per plane, then incremental
+                    for (int v = lane; v < nvec; v += 32) {
+                        stg_stream(r4 + v, rectified_vector_at<T>(x, y, w, geom, gw));
+                        x += 32 * EPV;
+                        while (x >= w) { x -= w; ++y; }
+                    }
+                }
+            }
+        });
+}
+
 // ---- PCK -------------------------------------------------------------------------------------
-template <typename TO, typename TT, bool VEC_O, bool VEC_T>
-__global__ void __launch_bounds__(kDecThreads)
-pck_kernel(const TO* __restrict__ output, const TT* __restrict__ target, int joints, int hw, int w,
-           double norm_x, double norm_y, double thr, float* __restrict__ pred_out,
-           float* __restrict__ tgt_out, int32_t* __restrict__ hits, int32_t* __restrict__ valid) {
-    __shared__ unsigned long long red[32];
-    const int64_t plane = blockIdx.x;
-    const unsigned long long bo =
-        block_max_u64<kDecThreads>(thread_plane_argmax<TO, VEC_O>(output + plane * hw, hw), red);
-    const unsigned long long bt =
-        block_max_u64<kDecThreads>(thread_plane_argmax<TT, VEC_T>(target + plane * hw, hw), red);
-    if (threadIdx.x != 0) return;
-    const uint32_t io = arg_idx(bo), it = arg_idx(bt);
-    const bool po = key_value(arg_key(bo)) > 0.0f, pt = key_value(arg_key(bt)) > 0.0f;
+// calc_dists + dist_acc for one (b,k) pair (keypoint_detection.py:40-62): returns bit0 = valid,
+// bit1 = hit, and writes the decoded coordinates.
+__device__ __forceinline__ uint8_t pck_flags(uint32_t io, float vo, uint32_t it, float vt, int w, double norm_x,
+                                             double norm_y, double thr, int64_t plane, float* __restrict__ pred_out,
+                                             float* __restrict__ tgt_out) {
+    const bool po = vo > 0.0f, pt = vt > 0.0f;
     // get_max_preds: float32 coordinates, zeroed when max <= 0 (keypoint_detection.py:28-36)
     const float px = po ? static_cast<float>(io % static_cast<uint32_t>(w)) : 0.0f;
     const float py = po ? static_cast<float>(io / static_cast<uint32_t>(w)) : 0.0f;
@@ -167,6 +310,7 @@ pck_kernel(const TO* __restrict__ output, const TT* __restrict__ target, int joi
     const float ty = pt ? static_cast<float>(it / static_cast<uint32_t>(w)) : 0.0f;
     if (pred_out) { pred_out[2 * plane] = px; pred_out[2 * plane + 1] = py; }
     if (tgt_out) { tgt_out[2 * plane] = tx; tgt_out[2 * plane + 1] = ty; }
+    uint8_t f = 0;
     // calc_dists (keypoint_detection.py:40-52): float64, no contraction
     if (tx > 1.0f && ty > 1.0f) {
         const double d0 = __dsub_rn(__ddiv_rn(static_cast<double>(px), norm_x),
@@ -174,10 +318,87 @@ pck_kernel(const TO* __restrict__ output, const TT* __restrict__ target, int joi
         const double d1 = __dsub_rn(__ddiv_rn(static_cast<double>(py), norm_y),
                                     __ddiv_rn(static_cast<double>(ty), norm_y));
         const double dist = sqrt(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)));
-        const int k = static_cast<int>(plane % joints);
-        atomicAdd(valid + k, 1);
-        if (dist < thr) atomicAdd(hits + k, 1);  // dist_acc: strict < (keypoint_detection.py:60)
+        f = 1;
+        if (dist < thr) f |= 2;  // dist_acc: strict < (keypoint_detection.py:60)
     }
+    return f;
+}
+
+// last CTA: per-joint integer sums of the per-plane flags (exact, order-independent)
+__device__ __forceinline__ void pck_reduce_flags(const volatile uint8_t* flags, int64_t planes, int joints,
+                                                 int32_t* __restrict__ hits, int32_t* __restrict__ valid) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int64_t batch = planes / joints;
+    for (int k = warp; k < joints; k += warps) {
+        int nh = 0, nv = 0;
+        for (int64_t b = lane; b < batch; b += 32) {
+            const uint8_t f = flags[b * joints + k];
+            nv += f & 1;
+            nh += (f >> 1) & 1;
+        }
+        nh = __reduce_add_sync(0xffffffffu, nh);
+        nv = __reduce_add_sync(0xffffffffu, nv);
+        if (lane == 0) { hits[k] = nh; valid[k] = nv; }
+    }
+}
+
+template <typename TO, typename TT, bool VEC_O, bool VEC_T>
+__global__ void __launch_bounds__(kDecThreads)
+pck_kernel(const TO* __restrict__ output, const TT* __restrict__ target, int joints, int hw, int w,
+           double norm_x, double norm_y, double thr, float* __restrict__ pred_out,
+           float* __restrict__ tgt_out, int32_t* __restrict__ hits, int32_t* __restrict__ valid,
+           uint8_t* __restrict__ flags, uint32_t* __restrict__ ticket) {
+    __shared__ unsigned long long red[32];
+    const int64_t plane = blockIdx.x;
+    const unsigned long long bo =
+        block_max_u64<kDecThreads>(thread_plane_argmax<TO, VEC_O>(output + plane * hw, hw), red);
+    const unsigned long long bt =
+        block_max_u64<kDecThreads>(thread_plane_argmax<TT, VEC_T>(target + plane * hw, hw), red);
+    if (threadIdx.x == 0)
+        flags[plane] = pck_flags(arg_idx(bo), key_value(arg_key(bo)), arg_idx(bt), key_value(arg_key(bt)), w, norm_x,
+                                 norm_y, thr, plane, pred_out, tgt_out);
+    if (last_block_done(ticket, gridDim.x)) pck_reduce_flags(flags, gridDim.x, joints, hits, valid);
+}
+
+// TMA-staged: item = [output plane | target plane]; one warp decodes both planes of a pair
+template <typename TO, typename TT>
+__global__ void __launch_bounds__(kPipeThreads, 1)
+pck_tma_kernel(const TO* __restrict__ output, const TT* __restrict__ target, int64_t planes, int joints, int hw, int w,
+               double norm_x, double norm_y, double thr, float* __restrict__ pred_out, float* __restrict__ tgt_out,
+               int32_t* __restrict__ hits, int32_t* __restrict__ valid, uint8_t* __restrict__ flags,
+               uint32_t* __restrict__ ticket, int stages) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ PipeBarriers bars;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bytes_o = static_cast<uint32_t>(hw * sizeof(TO)), bytes_t = static_cast<uint32_t>(hw * sizeof(TT));
+    const uint32_t stage_bytes = bytes_o + bytes_t;
+    pipe_init(bars, stages);
+    const int n_items = pipe_items(planes);
+    if (warp == static_cast<int>(blockDim.x >> 5) - 1) {
+        pipe_produce(bars, stages, n_items, [&](int i, int s, uint64_t* full) {
+            const int64_t plane = blockIdx.x + static_cast<int64_t>(i) * gridDim.x;
+            uint8_t* dst = smem + static_cast<size_t>(s) * stage_bytes;
+            mbar_expect_tx(full, stage_bytes);
+            bulk_load(dst, output + plane * hw, bytes_o, full);
+            bulk_load(dst + bytes_o, target + plane * hw, bytes_t, full);
+        });
+    } else {
+        PlaneMax mo, mt;
+        pipe_consume(
+            bars, stages, n_items, warp,
+            [&](int i, int s) {
+                const uint8_t* src = smem + static_cast<size_t>(s) * stage_bytes;
+                mo = warp_argmax_smem<TO>(src, hw / Vec16<TO>::EPV, lane);
+                mt = warp_argmax_smem<TT>(src + bytes_o, hw / Vec16<TT>::EPV, lane);
+            },
+            [&](int i) {
+                const int64_t plane = blockIdx.x + static_cast<int64_t>(i) * gridDim.x;
+                if (lane == 0)
+                    flags[plane] = pck_flags(mo.idx, mo.val, mt.idx, mt.val, w, norm_x, norm_y, thr, plane, pred_out, tgt_out);
+            });
+    }
+    __syncthreads();
+    if (last_block_done(ticket, gridDim.x)) pck_reduce_flags(flags, planes, joints, hits, valid);
 }
 
 // ---- k-th value + tea_mask ----------------------------------------------------------------------
@@ -240,17 +461,6 @@ mask_select_kernel(const float* __restrict__ act, int n, int kth, const float* _
     }
 }
 
-static GaussWindow make_window(double sigma) {
-    GaussWindow g;
-    const double tmp = 3.0 * sigma;
-    const double size = 2.0 * tmp + 1.0;
-    g.tmp = static_cast<float>(tmp);
-    g.n = static_cast<int>(std::ceil(size));
-    g.x0 = static_cast<float>(std::floor(size / 2.0));
-    g.denom = static_cast<float>(2.0 * sigma * sigma);
-    return g;
-}
-
 template <typename T>
 static int launch_decode(const void* hm, int64_t planes, int64_t h, int64_t w, int32_t* idx,
                          float* preds, void* maxvals, float* maxvals_f32, int64_t* position,
@@ -260,7 +470,20 @@ static int launch_decode(const void* hm, int64_t planes, int64_t h, int64_t w, i
     const bool vec = aligned16(hm) && (hw % Vec16<T>::EPV) == 0 && (rect == nullptr || aligned16(rect));
     const GaussWindow gw = make_window(rect ? sigma : 1.0);
     const unsigned grid = static_cast<unsigned>(planes);
-    if (vec)
+    PipeGeom pg = {1, 0, 0};
+    // TMA staging pays for pure scans over many planes (measured cross-over ~2k planes on B200); with a
+    // rectified map to write, or few planes, the many-warp register path below is faster
+    if (vec && pipe_enabled() && rect == nullptr && planes >= kTmaMinPlanes && hw * static_cast<int>(sizeof(T)) >= 2048)
+        pg = pipe_geometry(hw * static_cast<int64_t>(sizeof(T)), planes);
+    if (pg.stages >= 2) {
+        const size_t smem = static_cast<size_t>(pg.stages) * pg.group * hw * sizeof(T);
+        cudaError_t e = pipe_reserve_smem<&decode_tma_kernel<T>>(smem);
+        if (e != cudaSuccess) return fail(static_cast<int>(e), "udape_decode: smem opt-in: %s", cudaGetErrorString(e));
+        decode_tma_kernel<T><<<pipe_grid((planes + pg.group - 1) / pg.group), pg.threads, smem, st>>>(
+            static_cast<const T*>(hm), planes, hw, static_cast<int>(w), static_cast<int>(h), idx, preds,
+            static_cast<T*>(maxvals), maxvals_f32, position, occlude_thresh, conf_table, gw,
+            static_cast<T*>(rect), pg.group, pg.stages);
+    } else if (vec)
         decode_kernel<T, true><<<grid, kDecThreads, 0, st>>>(
             static_cast<const T*>(hm), hw, static_cast<int>(w), static_cast<int>(h), idx, preds,
             static_cast<T*>(maxvals), maxvals_f32, position, occlude_thresh, conf_table, gw,
@@ -276,7 +499,7 @@ static int launch_decode(const void* hm, int64_t planes, int64_t h, int64_t w, i
 template <typename TO, typename TT>
 static int launch_pck(const void* output, const void* target, int64_t planes, int64_t joints,
                       int64_t h, int64_t w, double thr, float* pred, float* tgt, int32_t* hits,
-                      int32_t* valid, cudaStream_t st) {
+                      int32_t* valid, uint8_t* flags, uint32_t* ticket, cudaStream_t st) {
     const int hw = static_cast<int>(h * w);
     const bool vo = aligned16(output) && (hw % Vec16<TO>::EPV) == 0;
     const bool vt = aligned16(target) && (hw % Vec16<TT>::EPV) == 0;
@@ -286,8 +509,19 @@ static int launch_pck(const void* output, const void* target, int64_t planes, in
     const TO* o = static_cast<const TO*>(output);
     const TT* t = static_cast<const TT*>(target);
     const int ij = static_cast<int>(joints), iw = static_cast<int>(w);
+    PipeGeom pg = {1, 0, 0};
+    if (vo && vt && pipe_enabled() && planes >= kTmaMinPlanes && hw * static_cast<int64_t>(sizeof(TO)) >= 2048)
+        pg = pipe_geometry(hw * static_cast<int64_t>(sizeof(TO) + sizeof(TT)), planes, 1);
+    if (pg.stages >= 2) {
+        const size_t smem = static_cast<size_t>(pg.stages) * hw * (sizeof(TO) + sizeof(TT));
+        cudaError_t e = pipe_reserve_smem<&pck_tma_kernel<TO, TT>>(smem);
+        if (e != cudaSuccess) return fail(static_cast<int>(e), "udape_pck_counts: smem opt-in: %s", cudaGetErrorString(e));
+        pck_tma_kernel<TO, TT><<<pipe_grid(planes), pg.threads, smem, st>>>(o, t, planes, ij, hw, iw, norm_x, norm_y, thr,
+                                                                           pred, tgt, hits, valid, flags, ticket, pg.stages);
+        return check_launch("udape_pck_counts");
+    }
 #define UDAPE_PCK_LAUNCH(VO, VT) \
-    pck_kernel<TO, TT, VO, VT><<<grid, kDecThreads, 0, st>>>(o, t, ij, hw, iw, norm_x, norm_y, thr, pred, tgt, hits, valid)
+    pck_kernel<TO, TT, VO, VT><<<grid, kDecThreads, 0, st>>>(o, t, ij, hw, iw, norm_x, norm_y, thr, pred, tgt, hits, valid, flags, ticket)
     if (vo && vt) UDAPE_PCK_LAUNCH(true, true);
     else if (vo) UDAPE_PCK_LAUNCH(true, false);
     else if (vt) UDAPE_PCK_LAUNCH(false, true);
@@ -337,8 +571,9 @@ extern "C" int udape_mask_select(const float* activates, int64_t n, int64_t kth,
 
 extern "C" int udape_pck_counts(const void* output, int out_dtype, const void* target, int tgt_dtype,
                                 int64_t batch, int64_t joints, int64_t h, int64_t w, double thr,
-                                float* pred, float* tgt, int32_t* hits, int32_t* valid, void* stream) {
-    UDAPE_REQUIRE(output && target && hits && valid, UDAPE_ERR_NULL, "udape_pck_counts: NULL pointer");
+                                float* pred, float* tgt, int32_t* hits, int32_t* valid, uint8_t* flags,
+                                uint32_t* ticket, void* stream) {
+    UDAPE_REQUIRE(output && target && hits && valid && flags && ticket, UDAPE_ERR_NULL, "udape_pck_counts: NULL pointer");
     UDAPE_REQUIRE(batch > 0 && joints > 0 && h > 0 && w > 0 && batch * joints < (1ll << 31) &&
                       h * w < (1ll << 31),
                   UDAPE_ERR_SHAPE, "udape_pck_counts: bad extents B=%lld K=%lld h=%lld w=%lld",
@@ -346,15 +581,13 @@ extern "C" int udape_pck_counts(const void* output, int out_dtype, const void* t
     const int eo = dtype_size(out_dtype), et = dtype_size(tgt_dtype);
     UDAPE_REQUIRE((eo == 2 || eo == 4) && (et == 2 || et == 4), UDAPE_ERR_DTYPE,
                   "udape_pck_counts: unsupported dtype codes %d/%d", out_dtype, tgt_dtype);
-    UDAPE_REQUIRE(aligned_to(output, eo) && aligned_to(target, et), UDAPE_ERR_ALIGN,
-                  "udape_pck_counts: misaligned pointer");
+    UDAPE_REQUIRE(aligned_to(output, eo) && aligned_to(target, et) && aligned_to(ticket, 4) && aligned_to(hits, 4) &&
+                      aligned_to(valid, 4),
+                  UDAPE_ERR_ALIGN, "udape_pck_counts: misaligned pointer");
     cudaStream_t st = as_stream(stream);
-    cudaError_t e = cudaMemsetAsync(hits, 0, sizeof(int32_t) * joints, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(valid, 0, sizeof(int32_t) * joints, st);
-    if (e != cudaSuccess) return fail(static_cast<int>(e), "udape_pck_counts: memset: %s", cudaGetErrorString(e));
     const int64_t planes = batch * joints;
     UDAPE_DISPATCH_FLOAT(out_dtype, TO,
         UDAPE_DISPATCH_FLOAT(tgt_dtype, TT,
-            return launch_pck<TO, TT>(output, target, planes, joints, h, w, thr, pred, tgt, hits, valid, st)));
+            return launch_pck<TO, TT>(output, target, planes, joints, h, w, thr, pred, tgt, hits, valid, flags, ticket, st)));
     return UDAPE_OK;
 }

@@ -11,6 +11,7 @@
 // tree and writes one partial; the last CTA to finish (ticket counter) sums the
 // partials in a fixed order.  No floating-point atomics anywhere.
 #include "common.cuh"
+#include "gauss.cuh"
 
 namespace udape {
 
@@ -87,26 +88,6 @@ __device__ __forceinline__ float thread_sq_diff(const TA* __restrict__ a, const 
         }
     }
     return acc;
-}
-
-// Last-CTA-done final reduction: returns true in every thread of the last CTA.
-__device__ __forceinline__ bool last_block_done(uint32_t* ticket, unsigned total) {
-    __shared__ bool is_last;
-    __threadfence();  // publish this CTA's partial before taking a ticket
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned t = atomicAdd(ticket, 1u);
-        is_last = (t == total - 1);
-    }
-    __syncthreads();
-    if (is_last) __threadfence();
-    return is_last;
-}
-// fixed-order sum of n floats by one CTA
-__device__ __forceinline__ float cta_sum_array(const volatile float* v, int64_t n, float* red) {
-    float s = 0.0f;
-    for (int64_t i = threadIdx.x; i < n; i += kLossThreads) s += v[i];
-    return block_sum<kLossThreads>(s, red);
 }
 
 // ---- JointsMSELoss ------------------------------------------------------------------------
@@ -272,6 +253,144 @@ cons_bwd_kernel(const TS* __restrict__ stu, const TT* __restrict__ tea,
     }
 }
 
+
+// ---- fused loss step ------------------------------------------------------------------------
+// One launch for  loss_s = JointsMSELoss(y_s, label, weight),  loss_c = ConsLoss(y_t_stu, tea,
+// tea_mask),  loss_all = loss_s + lambda_c*loss_c  AND the gradients of  grad_scale*loss_all
+// w.r.t. both student heatmaps (train_human.py:425-436): every operand is read once and each
+// gradient written once.  CTAs [0, planes_s) own a supervised plane, CTAs [planes_s,
+// planes_s+planes_t) a consistency plane.  When `tea` is NULL the rectified teacher map is not
+// read at all: it is evaluated from the decoded arg-max (tea_preds) with the very functions
+// the decode kernel uses to materialise it (gauss.cuh), so both routes give identical values.
+struct LossStepArgs {
+    const void* weight; int w_dtype;
+    const void* tea_mask; int mask_dtype;
+    const float* tea_preds;      // [planes_t, 2] float (x, y), zeroed when max <= 0 (decode's `preds`)
+    GaussWindow gw;
+    int planes_s, planes_t, joints, hw, w, h;
+    float lambda_c, grad_scale;
+    const float* grad_scale_dev;
+    float* partial;              // [planes_s + planes_t]
+    float* losses;               // [3] = loss_all, loss_s, loss_c
+    uint32_t* ticket;
+};
+
+template <typename TS, typename TT, bool VEC>
+__global__ void __launch_bounds__(kLossThreads)
+loss_step_kernel(const TS* __restrict__ y_s, const TT* __restrict__ label, const TS* __restrict__ y_t,
+                 const TT* __restrict__ tea, TS* __restrict__ grad_s, TS* __restrict__ grad_t,
+                 const LossStepArgs a) {
+    __shared__ float red[32];
+    const int hw = a.hw;
+    const bool sup = static_cast<int>(blockIdx.x) < a.planes_s;
+    const int64_t plane = sup ? blockIdx.x : blockIdx.x - a.planes_s;
+    const float g = a.grad_scale_dev ? __ldg(a.grad_scale_dev) : a.grad_scale;
+    const TS* s;
+    const TT* t;
+    TS* gout;
+    float coef, plane_scale;
+    RectGeom geom = {};
+    bool analytic = false;
+    if (sup) {
+        const float wgt = load_plane_scalar(a.weight, a.w_dtype, plane);
+        s = y_s + plane * hw;
+        t = label + plane * hw;
+        gout = grad_s ? grad_s + plane * hw : nullptr;
+        // d/do [0.5*w*(o-t)^2] / (planes*hw)
+        coef = g * wgt / (static_cast<float>(a.planes_s) * static_cast<float>(hw));
+        plane_scale = 0.5f * wgt / static_cast<float>(hw);
+    } else {
+        const float m = load_plane_scalar(a.tea_mask, a.mask_dtype, plane);
+        s = y_t + plane * hw;
+        analytic = (tea == nullptr);
+        t = analytic ? nullptr : tea + plane * hw;
+        gout = grad_t ? grad_t + plane * hw : nullptr;
+        // d/ds [m^2 (s-t)^2] / (K * B*hw)   with B = planes_t / K
+        coef = 2.0f * (g * a.lambda_c) * m * m / (static_cast<float>(a.joints) *
+               (static_cast<float>(a.planes_t / a.joints) * static_cast<float>(hw)));
+        plane_scale = m * m;
+        if (analytic) geom = rect_geometry(a.tea_preds[2 * plane], a.tea_preds[2 * plane + 1], a.h, a.w, a.gw);
+    }
+    float acc = 0.0f;
+    if (VEC) {
+        constexpr int G = PairGroup<TS, TT>::G;
+        const int ngrp = hw / G;
+        for (int base = 0; base < ngrp; base += kLossUnroll * kLossThreads) {
+            Pack<TS, G> gs_[kLossUnroll];
+            Pack<TT, G> gt_[kLossUnroll];
+#pragma unroll
+            for (int u = 0; u < kLossUnroll; ++u) {
+                const int gi = base + u * kLossThreads + threadIdx.x;
+                if (gi < ngrp) {
+                    gs_[u].load(s + G * gi);
+                    if (!analytic) gt_[u].load(t + G * gi);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kLossUnroll; ++u) {
+                const int gi = base + u * kLossThreads + threadIdx.x;
+                if (gi < ngrp) {
+                    float fs[G], ft[G];
+                    gs_[u].get(fs);
+                    if (!analytic) {
+                        gt_[u].get(ft);
+                    } else {
+                        const int flat = gi * G;
+                        int y = flat / a.w, x = flat - y * a.w;
+                        if (x + G <= a.w && (y < geom.y0i || y >= geom.y1i || x + G <= geom.x0i || x >= geom.x1i)) {
+                            // the group misses the (6*sigma+1)^2 window: zeros, no per-element work
+#pragma unroll
+                            for (int e = 0; e < G; ++e) ft[e] = 0.0f;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < G; ++e) {
+                                // rounded through the teacher map's dtype, like the materialised map
+                                ft[e] = to_f32<TT>(from_f32<TT>(rectified_value(x, y, geom, a.gw)));
+                                if (++x == a.w) { x = 0; ++y; }
+                            }
+                        }
+                    }
+                    float tsum = 0.0f;
+#pragma unroll
+                    for (int e = 0; e < G; ++e) {
+                        const float d = fs[e] - ft[e];
+                        tsum = fmaf(d, d, tsum);
+                        fs[e] = coef * d;
+                    }
+                    acc += tsum;
+                    if (gout) Pack<TS, G>::store(gout + G * gi, fs);
+                }
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < hw; i += kLossThreads) {
+            float tv;
+            if (!analytic) tv = to_f32<TT>(t[i]);
+            else {
+                const int y = i / a.w, x = i - y * a.w;
+                tv = to_f32<TT>(from_f32<TT>(rectified_value(x, y, geom, a.gw)));
+            }
+            const float d = to_f32<TS>(s[i]) - tv;
+            acc = fmaf(d, d, acc);
+            if (gout) gout[i] = from_f32<TS>(coef * d);
+        }
+    }
+    acc = block_sum<kLossThreads>(acc, red);
+    if (threadIdx.x == 0) a.partial[blockIdx.x] = plane_scale * acc;
+    if (last_block_done(a.ticket, gridDim.x)) {
+        const float ss = a.planes_s ? cta_sum_array(a.partial, a.planes_s, red) : 0.0f;
+        const float sc = a.planes_t ? cta_sum_array(a.partial + a.planes_s, a.planes_t, red) : 0.0f;
+        if (threadIdx.x == 0) {
+            const float loss_s = a.planes_s ? ss / static_cast<float>(a.planes_s) : 0.0f;
+            const float loss_c = a.planes_t ? sc / static_cast<float>(a.joints) /
+                                     (static_cast<float>(a.planes_t / a.joints) * static_cast<float>(hw)) : 0.0f;
+            a.losses[0] = loss_s + a.lambda_c * loss_c;   // train_human.py:434
+            a.losses[1] = loss_s;
+            a.losses[2] = loss_c;
+        }
+    }
+}
+
 template <typename TA, typename TB>
 static bool pair_vectorizable(const void* a, const void* b, const void* c, const void* vm, int64_t hw) {
     // every plane must start on a 16-byte boundary of the wide operand and hold a whole
@@ -303,10 +422,6 @@ extern "C" int udape_joints_mse_fwd(const void* output, int out_dtype, const voi
     UDAPE_REQUIRE(!loss_mean || ticket, UDAPE_ERR_NULL, "udape_joints_mse_fwd: ticket scratch is NULL");
     UDAPE_REQUIRE(!weight || plane_scalar_dtype_ok(w_dtype), UDAPE_ERR_DTYPE, "udape_joints_mse_fwd: bad weight dtype %d", w_dtype);
     cudaStream_t st = as_stream(stream);
-    if (loss_mean) {
-        cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st);
-        if (e != cudaSuccess) return fail(static_cast<int>(e), "udape_joints_mse_fwd: memset: %s", cudaGetErrorString(e));
-    }
     const unsigned grid = static_cast<unsigned>(planes);
     const int ihw = static_cast<int>(hw);
     UDAPE_DISPATCH_FLOAT(out_dtype, TO, UDAPE_DISPATCH_FLOAT(tgt_dtype, TT, {
@@ -355,9 +470,10 @@ extern "C" int udape_cons_fwd(const void* stu, int stu_dtype, const void* tea, i
     UDAPE_REQUIRE(!valid_mask || valid_count, UDAPE_ERR_NULL, "udape_cons_fwd: valid_count is NULL");
     UDAPE_REQUIRE(!tea_mask || plane_scalar_dtype_ok(mask_dtype), UDAPE_ERR_DTYPE, "udape_cons_fwd: bad mask dtype %d", mask_dtype);
     cudaStream_t st = as_stream(stream);
-    cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st);
-    if (e == cudaSuccess && valid_mask) e = cudaMemsetAsync(valid_count, 0, sizeof(int32_t), st);
-    if (e != cudaSuccess) return fail(static_cast<int>(e), "udape_cons_fwd: memset: %s", cudaGetErrorString(e));
+    if (valid_mask) {
+        cudaError_t e = cudaMemsetAsync(valid_count, 0, sizeof(int32_t), st);
+        if (e != cudaSuccess) return fail(static_cast<int>(e), "udape_cons_fwd: memset: %s", cudaGetErrorString(e));
+    }
     if (valid_mask) {
         const int64_t n = batch * hw;
         const unsigned g = static_cast<unsigned>((n + kLossThreads * 8 - 1) / (kLossThreads * 8));
@@ -399,4 +515,59 @@ extern "C" int udape_cons_bwd(const void* stu, int stu_dtype, const void* tea, i
             cons_bwd_kernel<TS, TT, false><<<grid, kLossThreads, 0, st>>>(s, t, tea_mask, mask_dtype, valid_mask, ij, ihw, batch, grad_out, valid_count, gs);
     }));
     return check_launch("udape_cons_bwd");
+}
+
+extern "C" int udape_loss_step(const void* y_s, const void* label, const void* weight, int w_dtype,
+                               int64_t planes_s, const void* y_t_stu, const void* tea,
+                               const float* tea_preds, double sigma, const void* tea_mask, int mask_dtype,
+                               int64_t batch_t, int64_t joints, int64_t h, int64_t w, int stu_dtype,
+                               int tgt_dtype, float lambda_c, float grad_scale, const float* grad_scale_dev,
+                               float* partial, float* losses, uint32_t* ticket, void* grad_y_s,
+                               void* grad_y_t_stu, void* stream) {
+    const int64_t planes_t = batch_t * joints, hw = h * w;
+    UDAPE_REQUIRE(planes_s >= 0 && batch_t >= 0 && joints > 0 && h > 0 && w > 0 && hw < (1ll << 31) &&
+                      planes_s + planes_t > 0 && planes_s + planes_t < (1ll << 31),
+                  UDAPE_ERR_SHAPE, "udape_loss_step: bad extents planes_s=%lld B_t=%lld K=%lld h=%lld w=%lld",
+                  (long long)planes_s, (long long)batch_t, (long long)joints, (long long)h, (long long)w);
+    const int es = dtype_size(stu_dtype), et = dtype_size(tgt_dtype);
+    UDAPE_REQUIRE((es == 2 || es == 4) && (et == 2 || et == 4), UDAPE_ERR_DTYPE,
+                  "udape_loss_step: unsupported dtype codes %d/%d", stu_dtype, tgt_dtype);
+    UDAPE_REQUIRE(partial && losses && ticket, UDAPE_ERR_NULL, "udape_loss_step: NULL scratch/output pointer");
+    UDAPE_REQUIRE(planes_s == 0 || (y_s && label), UDAPE_ERR_NULL, "udape_loss_step: NULL supervised operand");
+    UDAPE_REQUIRE(planes_t == 0 || (y_t_stu && (tea || tea_preds)), UDAPE_ERR_NULL,
+                  "udape_loss_step: consistency pair needs y_t_stu and either tea or tea_preds");
+    UDAPE_REQUIRE(!weight || plane_scalar_dtype_ok(w_dtype), UDAPE_ERR_DTYPE, "udape_loss_step: bad weight dtype %d", w_dtype);
+    UDAPE_REQUIRE(!tea_mask || plane_scalar_dtype_ok(mask_dtype), UDAPE_ERR_DTYPE, "udape_loss_step: bad mask dtype %d", mask_dtype);
+    UDAPE_REQUIRE(aligned_to(y_s, es) && aligned_to(y_t_stu, es) && aligned_to(grad_y_s, es) &&
+                      aligned_to(grad_y_t_stu, es) && aligned_to(label, et) && aligned_to(tea, et) &&
+                      aligned_to(tea_preds, 4),
+                  UDAPE_ERR_ALIGN, "udape_loss_step: misaligned tensor pointer");
+    if (planes_t && !tea) {
+        UDAPE_REQUIRE(sigma > 0.0 && sigma < 1e4, UDAPE_ERR_ARG, "udape_loss_step: sigma %g out of range", sigma);
+    }
+    cudaStream_t st = as_stream(stream);
+    LossStepArgs a;
+    a.weight = weight; a.w_dtype = w_dtype;
+    a.tea_mask = tea_mask; a.mask_dtype = mask_dtype;
+    a.tea_preds = tea_preds;
+    a.gw = make_window((planes_t && !tea) ? sigma : 1.0);
+    a.planes_s = static_cast<int>(planes_s); a.planes_t = static_cast<int>(planes_t);
+    a.joints = static_cast<int>(joints); a.hw = static_cast<int>(hw);
+    a.w = static_cast<int>(w); a.h = static_cast<int>(h);
+    a.lambda_c = lambda_c; a.grad_scale = grad_scale; a.grad_scale_dev = grad_scale_dev;
+    a.partial = partial; a.losses = losses; a.ticket = ticket;
+    const unsigned grid = static_cast<unsigned>(planes_s + planes_t);
+    const bool vec = (hw % 8) == 0 && aligned16(y_s) && aligned16(label) && aligned16(y_t_stu) && aligned16(tea) &&
+                     aligned16(grad_y_s) && aligned16(grad_y_t_stu);
+    UDAPE_DISPATCH_FLOAT(stu_dtype, TS, UDAPE_DISPATCH_FLOAT(tgt_dtype, TT, {
+        const TS* ys = static_cast<const TS*>(y_s);
+        const TS* yt = static_cast<const TS*>(y_t_stu);
+        const TT* lb = static_cast<const TT*>(label);
+        const TT* te = static_cast<const TT*>(tea);
+        TS* g1 = static_cast<TS*>(grad_y_s);
+        TS* g2 = static_cast<TS*>(grad_y_t_stu);
+        if (vec) loss_step_kernel<TS, TT, true><<<grid, kLossThreads, 0, st>>>(ys, lb, yt, te, g1, g2, a);
+        else loss_step_kernel<TS, TT, false><<<grid, kLossThreads, 0, st>>>(ys, lb, yt, te, g1, g2, a);
+    }));
+    return check_launch("udape_loss_step");
 }

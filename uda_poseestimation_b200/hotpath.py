@@ -23,7 +23,7 @@ import torch
 from .adain import adain_mix
 from .ema import OldWeightEMA
 from .keypoint_detection import _pck
-from .loss import cons_loss, joints_mse_loss
+from .loss import cons_loss, fused_losses, joints_mse_loss
 from .mask import teacher_targets
 
 __all__ = ["StepInputs", "HotPathStep", "step_algorithmic_bytes"]
@@ -48,8 +48,11 @@ class StepInputs:
         return [getattr(self, f.name) for f in dataclasses.fields(self)]
 
 
-def step_algorithmic_bytes(inp: StepInputs, n_params: int, param_bytes: int = 4) -> dict:
-    """Algorithmic HBM bytes of one step, per kernel family."""
+def step_algorithmic_bytes(inp: StepInputs, n_params: int, param_bytes: int = 4, fused: bool = True) -> dict:
+    """Algorithmic HBM bytes of one step, per kernel family.
+
+    ``fused=True`` is the default step (one loss launch, rectified teacher map evaluated on the fly);
+    ``fused=False`` the operator-by-operator sequence (separate fwd/bwd launches, materialised map)."""
     ef = inp.feat_src.element_size()
     feat = inp.feat_src.numel() * ef
     hm = inp.y_t_tea.numel()
@@ -57,15 +60,20 @@ def step_algorithmic_bytes(inp: StepInputs, n_params: int, param_bytes: int = 4)
     planes = inp.y_s.shape[0] * inp.y_s.shape[1]
     out = {
         "adain_mix": 2 * 3 * feat,                        # two directions x (2 reads + 1 write)
-        "decode_rectify": hm * e_t + hm * e_t + 32 * planes,  # 1 read + 1 write (+ per-plane outputs)
         "mask_select": 9 * planes,
-        "joints_mse_fwd": hm * (e_s + e_l) + 4 * planes,
-        "joints_mse_bwd": hm * (e_s + e_l) + hm * e_s,
-        "cons_fwd": hm * (e_s + e_t) + 4 * planes,
-        "cons_bwd": hm * (e_s + e_t) + hm * e_s,
         "pck": hm * (e_s + e_l) + 8 * planes,
         "ema": 3 * n_params * param_bytes,
     }
+    if fused:
+        out["decode"] = hm * e_t + 40 * planes            # 1 read (+ per-plane outputs)
+        # y_s + label read, grad_y_s written; y_t_stu read, grad_y_t_stu written (teacher map analytic)
+        out["loss_step"] = hm * (e_s + e_l + e_s) + hm * (e_s + e_s) + 8 * planes
+    else:
+        out["decode_rectify"] = hm * e_t + hm * e_t + 40 * planes  # 1 read + 1 write (+ per-plane outputs)
+        out["joints_mse_fwd"] = hm * (e_s + e_l) + 4 * planes
+        out["joints_mse_bwd"] = hm * (e_s + e_l) + hm * e_s
+        out["cons_fwd"] = hm * (e_s + e_t) + 4 * planes
+        out["cons_bwd"] = hm * (e_s + e_t) + hm * e_s
     out["total"] = sum(out.values())
     return out
 
@@ -73,16 +81,13 @@ def step_algorithmic_bytes(inp: StepInputs, n_params: int, param_bytes: int = 4)
 class HotPathStep:
     """One mean-teacher hot-path step on a batch shard, through the public operators."""
 
-    # kernels of libudape_b200.so launched by run(): 2 adain, decode(+rectify), mask_select,
-    # mse fwd/bwd, cons fwd/bwd, pck, ema  (memset nodes for tickets/counters not counted)
-    KERNELS_PER_STEP = 10
-
     def __init__(self, teacher: torch.nn.Module, student: torch.nn.Module, sigma=2, mask_ratio: float = 0.5,
                  occlude_thresh: float = 0.9, teacher_alpha: float = 0.999, lambda_c: float = 1.0,
-                 loss_scale: float = 65536.0, parallel: bool = True):
+                 loss_scale: float = 65536.0, parallel: bool = True, fused: bool = True,
+                 ema_parallel: bool = True):
         self.sigma, self.mask_ratio, self.occlude_thresh = sigma, mask_ratio, occlude_thresh
         self.lambda_c, self.loss_scale = lambda_c, loss_scale
-        self.parallel = parallel
+        self.parallel, self.fused, self.ema_parallel = parallel, fused, ema_parallel
         self._side = None
         self.ema = OldWeightEMA(teacher, student, alpha=teacher_alpha)  # train_human.py:141
         self.n_params = sum(p.numel() for p in teacher.parameters())
@@ -90,37 +95,66 @@ class HotPathStep:
         self.out = None
         self._graph_inputs = None
 
-    # -- the step, minus the EMA (so that callers can time / place the EMA launch themselves) ------
-    def run_no_ema(self, inp: StepInputs) -> dict:
-        """Three independent chains, forked onto side streams so that the small heatmap kernels
-        (launch/latency-bound at batch 32) overlap the two large AdaIN passes:
+    @property
+    def kernels_per_step(self) -> int:
+        """Kernels of libudape_b200.so launched by run() (memset nodes for tickets/counters not counted):
+        fused: 2 adain, decode, mask_select, loss_step, pck, ema;  unfused: 2 adain, decode+rectify,
+        mask_select, mse fwd/bwd, cons fwd/bwd, pck, ema."""
+        return 7 if self.fused else 10
+
+    def _streams(self, dev):
+        if self._side is None or self._side[0].device != dev:
+            self._side = tuple(torch.cuda.Stream(dev) for _ in range(3))
+        return self._side
+
+    # -- the step -----------------------------------------------------------------------------------
+    def _run(self, inp: StepInputs, with_ema: bool) -> dict:
+        """Independent chains, forked onto side streams so that the small heatmap kernels
+        (launch/latency-bound at batch 32) and the EMA stream overlap the two large AdaIN passes:
 
             main   : AdaIN+mix s2t, AdaIN+mix t2s
-            teacher: decode+rectify -> k-th mask -> ConsLoss fwd -> bwd
-            student: JointsMSELoss fwd -> bwd -> PCK counts
+            teacher: decode -> k-th mask -> fused loss step (both criteria + both gradients)
+            student: PCK counts            [unfused: JointsMSELoss fwd -> bwd -> PCK]
+            ema    : multi-tensor EMA over the parameter list (after the join if ema_parallel=False)
 
         The fork/join is plain stream-event ordering, so it behaves the same eagerly and under
-        CUDA-graph capture (where it becomes three parallel graph branches)."""
+        CUDA-graph capture (where it becomes parallel graph branches)."""
         cur = torch.cuda.current_stream()
-        if self._side is None or self._side[0].device != inp.y_s.device:
-            self._side = (torch.cuda.Stream(inp.y_s.device), torch.cuda.Stream(inp.y_s.device))
-        s_tea, s_stu = self._side if self.parallel else (cur, cur)
+        s_tea, s_stu, s_ema = self._streams(inp.y_s.device) if self.parallel else (cur, cur, cur)
+        ema_side = with_ema and self.parallel and self.ema_parallel
         if self.parallel:
             s_tea.wait_stream(cur)
             s_stu.wait_stream(cur)
+            if ema_side:
+                s_ema.wait_stream(cur)
+        if ema_side:
+            with torch.cuda.stream(s_ema):
+                # :438 — independent of every other chain of the hot path (in training it follows
+                # scaler.step(stu_optimizer); the student parameters are an input of this step)
+                self.ema.step()
         with torch.cuda.stream(s_tea):
             with torch.no_grad():
-                # train_human.py:376-383 and :427-430 — fused decode+rectify pass + k-th value select
-                tt = teacher_targets(inp.y_t_tea, self.sigma, self.mask_ratio, occlude_thresh=self.occlude_thresh)
-            # :432 — consistency loss; its share of `scaler.scale(loss_all).backward()` (:434-436)
-            y_t_stu = inp.y_t_stu.detach().requires_grad_(True)
-            loss_c = cons_loss(y_t_stu, tt["rectified"], tea_mask=tt["tea_mask"])
-            (g_c,) = torch.autograd.grad(loss_c * (self.lambda_c * self.loss_scale), (y_t_stu,))
+                # train_human.py:376-383 and :427-430 — one decode pass + k-th value select
+                tt = teacher_targets(inp.y_t_tea, self.sigma, self.mask_ratio, occlude_thresh=self.occlude_thresh,
+                                     materialise=not self.fused)
+                if self.fused:
+                    # :425-436 — both criteria, loss_all and the scaled-backward seeds in one launch;
+                    # the rectified teacher map (:428) is evaluated on the fly from the arg-max
+                    losses, g_s, g_c = fused_losses(inp.y_s, inp.label_s, inp.weight_s, inp.y_t_stu, None,
+                                                    tt["tea_mask"], lambda_c=self.lambda_c, grad_scale=self.loss_scale,
+                                                    tea_preds=tt["preds"], sigma=self.sigma)
+                    loss_all, loss_s, loss_c = losses[0], losses[1], losses[2]
+            if not self.fused:
+                # :432 — consistency loss; its share of `scaler.scale(loss_all).backward()` (:434-436)
+                y_t_stu = inp.y_t_stu.detach().requires_grad_(True)
+                loss_c = cons_loss(y_t_stu, tt["rectified"], tea_mask=tt["tea_mask"])
+                (g_c,) = torch.autograd.grad(loss_c * (self.lambda_c * self.loss_scale), (y_t_stu,))
         with torch.cuda.stream(s_stu):
-            # :425 — supervised loss and its share of the scaled backward
-            y_s = inp.y_s.detach().requires_grad_(True)
-            loss_s = joints_mse_loss(y_s, inp.label_s, inp.weight_s)
-            (g_s,) = torch.autograd.grad(loss_s * self.loss_scale, (y_s,))
+            if not self.fused:
+                # :425 — supervised loss and its share of the scaled backward
+                y_s = inp.y_s.detach().requires_grad_(True)
+                loss_s = joints_mse_loss(y_s, inp.label_s, inp.weight_s)
+                (g_s,) = torch.autograd.grad(loss_s * self.loss_scale, (y_s,))
             with torch.no_grad():
                 # :443-444 — PCK on (y_s, label_s): integer counts stay on the device
                 counts, pred = _pck(inp.y_s, inp.label_s, 0.5)
@@ -131,17 +165,24 @@ class HotPathStep:
         if self.parallel:
             cur.wait_stream(s_tea)
             cur.wait_stream(s_stu)
-        with torch.no_grad():
-            loss_all = loss_s.detach() + self.lambda_c * loss_c.detach()  # :434
+            if ema_side:
+                cur.wait_stream(s_ema)
+        if not self.fused:
+            with torch.no_grad():
+                loss_s, loss_c = loss_s.detach(), loss_c.detach()
+                loss_all = loss_s + self.lambda_c * loss_c  # :434
+        if with_ema and not ema_side:
+            self.ema.step()  # :438
         return dict(t_s2t=t_s2t, t_t2s=t_t2s, conf_table=tt["conf_table"], position=tt["position"],
                     tea_mask=tt["tea_mask"], mask_thresh=tt["mask_thresh"], rectified=tt["rectified"],
-                    loss_s=loss_s.detach(), loss_c=loss_c.detach(), loss_all=loss_all,
+                    tea_preds=tt["preds"], loss_s=loss_s, loss_c=loss_c, loss_all=loss_all,
                     grad_y_s=g_s, grad_y_t_stu=g_c, pck_counts=counts, pred=pred)
 
+    def run_no_ema(self, inp: StepInputs) -> dict:
+        return self._run(inp, with_ema=False)
+
     def run(self, inp: StepInputs) -> dict:
-        out = self.run_no_ema(inp)
-        self.ema.step()  # :438
-        return out
+        return self._run(inp, with_ema=True)
 
     # -- CUDA graph of the step (static input/output buffers) ------------------------------------
     def capture(self, inp: StepInputs, include_ema: bool = True, warmup: int = 3) -> dict:

@@ -137,11 +137,12 @@ def _pck(output: torch.Tensor, target: torch.Tensor, thr: float):
     if b * k == 0:
         counts.zero_()
         return counts, pred
+    flags = torch.empty(b * k, dtype=torch.uint8, device=dev)  # per-(b,k) valid/hit bits (scratch)
     with _lib.on_device(dev):
         st = _lib.load().udape_pck_counts(output.data_ptr(), _lib.float_code(output), target.data_ptr(),
                                           _lib.float_code(target), b, k, h, w, float(thr), pred.data_ptr(),
-                                          None, counts[0].data_ptr(), counts[1].data_ptr(),
-                                          _lib.stream_ptr(dev))
+                                          None, counts[0].data_ptr(), counts[1].data_ptr(), flags.data_ptr(),
+                                          _lib.ticket(dev), _lib.stream_ptr(dev))
     _lib.check(st, "accuracy")
     return counts, pred
 

@@ -64,20 +64,24 @@ def consistency_mask(activates: torch.Tensor, mask_ratio: float, tea_mask: torch
 
 
 def teacher_targets(hm: torch.Tensor, sigma, mask_ratio: float, occlude_thresh: float | None = None,
-                    tea_mask: torch.Tensor | None = None) -> dict:
+                    tea_mask: torch.Tensor | None = None, materialise: bool = True) -> dict:
     """Everything the trainers derive from the reconstructed teacher heatmaps
-    (train_human.py:376-383 and :427-430) in two launches: one fused decode+rectify pass over
+    (train_human.py:376-383 and :427-430) in two launches: one fused decode(+rectify) pass over
     ``hm`` and one single-CTA k-th-value select.
 
-    Returns ``activates`` float32[B,K], ``rectified`` (= ``rectify(hm, sigma)``), ``tea_mask``
-    bool[B,K], ``mask_thresh`` (device scalar) and, when ``occlude_thresh`` is given, ``conf``
-    (alias of activates), ``position`` int64[B,K,2] and ``conf_table`` bool[B,K].
+    Returns ``activates`` float32[B,K], ``preds`` float32[B,K,2] (the arg-max ``rectify`` pastes its
+    window at), ``rectified`` (= ``rectify(hm, sigma)``), ``tea_mask`` bool[B,K], ``mask_thresh``
+    (device scalar) and, when ``occlude_thresh`` is given, ``conf`` (alias of activates),
+    ``position`` int64[B,K,2] and ``conf_table`` bool[B,K].  With ``materialise=False`` the
+    rectified map is not written (``rectified`` is None): ``fused_losses(..., tea_preds=preds,
+    sigma=sigma)`` evaluates it on the fly.
     """
-    r = decode(hm.detach(), want_maxvals_f32=True, want_position=occlude_thresh is not None,
-               occlude_thresh=occlude_thresh, rectify_sigma=float(sigma))
+    r = decode(hm.detach(), want_preds=True, want_maxvals_f32=True, want_position=occlude_thresh is not None,
+               occlude_thresh=occlude_thresh, rectify_sigma=float(sigma) if materialise else None)
     act = r["maxvals_f32"]
     mask, thresh = consistency_mask(act, mask_ratio, tea_mask)
-    out = {"activates": act, "rectified": r["rectified"], "tea_mask": mask, "mask_thresh": thresh}
+    out = {"activates": act, "preds": r["preds"], "rectified": r.get("rectified"), "tea_mask": mask,
+           "mask_thresh": thresh}
     if occlude_thresh is not None:
         out.update(conf=act, position=r["position"], conf_table=r["conf_table"])
     return out
