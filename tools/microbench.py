@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--no-sustained", action="store_true", help="isolated launches only (use under ncu)")
     ap.add_argument("--adain-n", default="8,32,64,128", help="feature batch sizes for the AdaIN kernels")
     ap.add_argument("--configs", default="C1,C2,C4,C5", help="heatmap configs to run")
     args = ap.parse_args()
@@ -80,6 +81,10 @@ def main():
         # sustained: back-to-back launches over the rotating buffer sets, replayed as ONE CUDA graph so
         # that the host (Python + ctypes, ~8 us per call) is not what is being measured
         reps = max(1, args.iters)
+        if args.no_sustained:
+            rows.append(dict(kernel=name, shape=shape, mbytes=nbytes / 1e6, us_isolated=iso * 1e3))
+            print(f"{name:<28}{shape:<26}{nbytes / 1e6:9.1f} MB isolated {iso * 1e3:7.1f} us", flush=True)
+            return
         graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())

@@ -43,7 +43,9 @@ def find_nvcc() -> str:
 
 
 def lib_path() -> Path:
-    return LIB_DIR / LIB_NAME
+    # UDAPE_LIB=/path/to/variant.so loads an alternative build (kernel A/B experiments on one box)
+    override = os.environ.get("UDAPE_LIB")
+    return Path(override) if override else LIB_DIR / LIB_NAME
 
 
 def _newest_dep_mtime() -> float:
@@ -53,6 +55,8 @@ def _newest_dep_mtime() -> float:
 
 
 def needs_build() -> bool:
+    if os.environ.get("UDAPE_LIB"):
+        return False
     lp = lib_path()
     return (not lp.exists()) or lp.stat().st_mtime < _newest_dep_mtime()
 

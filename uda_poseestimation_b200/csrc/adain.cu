@@ -92,7 +92,7 @@ mean_std_warp_kernel(const T* __restrict__ feat, T* __restrict__ mean_out, T* __
 }
 
 template <typename T, int J>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
 adain_warp_kernel(const T* __restrict__ content, const T* __restrict__ style, T* __restrict__ out,
                   int64_t planes, int nvec_c, int nvec_s, int hw_c, int hw_s, float eps,
                   float alpha, const float* __restrict__ alpha_dev, int mix) {

@@ -289,4 +289,5 @@ __device__ __forceinline__ float cta_sum_array(const volatile float* v, int64_t 
     return block_sum_rt(s, red);
 }
 
+
 }  // namespace udape

@@ -120,12 +120,6 @@ __device__ __forceinline__ uint4 rectified_vector_at(int x, int y, int w, const 
     }
     return pack16<T>(f);
 }
-template <typename T>
-__device__ __forceinline__ uint4 rectified_vector(int flat, int w, const RectGeom& geom, const GaussWindow& gw) {
-    const int y = flat / w;
-    return rectified_vector_at<T>(flat - y * w, y, w, geom, gw);
-}
-
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(kDecThreads)
 decode_kernel(const T* __restrict__ hm, int hw, int w, int h, int32_t* __restrict__ idx_out,
@@ -164,8 +158,13 @@ decode_kernel(const T* __restrict__ hm, int hw, int w, int h, int32_t* __restric
         constexpr int EPV = Vec16<T>::EPV;
         const int nvec = hw / EPV;
         uint4* r4 = reinterpret_cast<uint4*>(r);
-        for (int i = threadIdx.x; i < nvec; i += kDecThreads)
-            stg_stream(r4 + i, rectified_vector<T>(i * EPV, w, geom, gw));
+        int y = (threadIdx.x * EPV) / w, x = threadIdx.x * EPV - y * w;  // one division, then incremental
+        const int step_y = (kDecThreads * EPV) / w, step_x = kDecThreads * EPV - step_y * w;
+        for (int i = threadIdx.x; i < nvec; i += kDecThreads) {
+            stg_stream(r4 + i, rectified_vector_at<T>(x, y, w, geom, gw));
+            x += step_x; y += step_y;
+            if (x >= w) { x -= w; ++y; }
+        }
     } else {
         for (int i = threadIdx.x; i < hw; i += kDecThreads) {
             const int y = i / w, x = i - y * w;

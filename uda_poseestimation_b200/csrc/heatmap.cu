@@ -66,16 +66,25 @@ gauss_target_kernel(const double* __restrict__ joints, const float* __restrict__
     };
     if ((hw & 3) == 0 && aligned16(target)) {
         uint4* t4 = reinterpret_cast<uint4*>(t);
+        // position of this thread's first vector (one division), then incremental: no per-vector division
+        int y = (threadIdx.x * 4) / hm_w, x = threadIdx.x * 4 - y * hm_w;
+        const int step_y = (kHmThreads * 4) / hm_w, step_x = kHmThreads * 4 - step_y * hm_w;
         for (int i = threadIdx.x; i < (hw >> 2); i += kHmThreads) {
-            const int flat = i << 2;
-            int y = flat / hm_w, x = flat - y * hm_w;
-            float f[4];
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            // almost every vector misses the (6*sigma+1)^2 window: zeros without per-element work
+            if (!(x + 4 <= hm_w && (y < y0i || y >= y1i || x + 4 <= x0i || x >= x1i))) {
+                int xx = x, yy = y;
+                float f[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                f[e] = value(x, y);
-                if (++x == hm_w) { x = 0; ++y; }
+                for (int e = 0; e < 4; ++e) {
+                    f[e] = value(xx, yy);
+                    if (++xx == hm_w) { xx = 0; ++yy; }
+                }
+                v = pack16<float>(f);
             }
-            stg_stream(t4 + i, pack16<float>(f));
+            stg_stream(t4 + i, v);
+            x += step_x; y += step_y;
+            if (x >= hm_w) { x -= hm_w; ++y; }
         }
     } else {
         for (int i = threadIdx.x; i < hw; i += kHmThreads) {
@@ -122,9 +131,32 @@ labelmap_kernel(const int32_t* __restrict__ pts, int h, int w, LabelWindow lw, i
         return x >= x0i && x < x1i && y >= y0i && y < y1i && (x - ul_x) < lw.n && (y - ul_y) < lw.n;
     };
     if (zero_fill) {
-        for (int i = threadIdx.x; i < hw; i += kHmThreads) {
-            const int y = i / w, x = i - y * w;
-            t[i] = inside(x, y) ? value(x, y) : 0.0f;
+        if ((hw & 3) == 0 && aligned16(img)) {
+            uint4* t4 = reinterpret_cast<uint4*>(t);
+            int y = (threadIdx.x * 4) / w, x = threadIdx.x * 4 - y * w;
+            const int step_y = (kHmThreads * 4) / w, step_x = kHmThreads * 4 - step_y * w;
+            for (int i = threadIdx.x; i < (hw >> 2); i += kHmThreads) {
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                // the float64 window is evaluated only where a vector overlaps it
+                if (!(x + 4 <= w && (y < y0i || y >= y1i || x + 4 <= x0i || x >= x1i))) {
+                    int xx = x, yy = y;
+                    float f[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        f[e] = inside(xx, yy) ? value(xx, yy) : 0.0f;
+                        if (++xx == w) { xx = 0; ++yy; }
+                    }
+                    v = pack16<float>(f);
+                }
+                stg_stream(t4 + i, v);
+                x += step_x; y += step_y;
+                if (x >= w) { x -= w; ++y; }
+            }
+        } else {
+            for (int i = threadIdx.x; i < hw; i += kHmThreads) {
+                const int y = i / w, x = i - y * w;
+                t[i] = inside(x, y) ? value(x, y) : 0.0f;
+            }
         }
     } else if (!reject) {
         const int ww = x1i - x0i, wh = y1i - y0i;

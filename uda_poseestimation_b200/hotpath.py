@@ -84,10 +84,14 @@ class HotPathStep:
     def __init__(self, teacher: torch.nn.Module, student: torch.nn.Module, sigma=2, mask_ratio: float = 0.5,
                  occlude_thresh: float = 0.9, teacher_alpha: float = 0.999, lambda_c: float = 1.0,
                  loss_scale: float = 65536.0, parallel: bool = True, fused: bool = True,
-                 ema_parallel: bool = True):
+                 ema_parallel: bool = True, counts_hook=None):
         self.sigma, self.mask_ratio, self.occlude_thresh = sigma, mask_ratio, occlude_thresh
         self.lambda_c, self.loss_scale = lambda_c, loss_scale
         self.parallel, self.fused, self.ema_parallel = parallel, fused, ema_parallel
+        # called with the int32 [2,K] hits||valid tensor right after the PCK launch, on the PCK chain's
+        # stream: the data-parallel integer all-reduce (dist.allreduce_counts) goes here so that it
+        # overlaps the AdaIN / EMA chains instead of trailing the step
+        self.counts_hook = counts_hook
         self._side = None
         self.ema = OldWeightEMA(teacher, student, alpha=teacher_alpha)  # train_human.py:141
         self.n_params = sum(p.numel() for p in teacher.parameters())
@@ -158,6 +162,8 @@ class HotPathStep:
             with torch.no_grad():
                 # :443-444 — PCK on (y_s, label_s): integer counts stay on the device
                 counts, pred = _pck(inp.y_s, inp.label_s, 0.5)
+                if self.counts_hook is not None:
+                    self.counts_hook(counts)
         with torch.no_grad():
             # :348-356 — s2t and t2s feature re-normalisation (the decoder conv follows)
             t_s2t = adain_mix(inp.feat_src, inp.feat_tgt_ori, inp.alpha_s2t)
