@@ -229,6 +229,34 @@ UDAPE_API int64_t udape_ema_plan(void* const* dst, const void* const* src, const
 UDAPE_API int udape_ema_multi(const udape_ema_chunk* chunks_dev, int64_t n_chunks, int64_t chunk_elems,
                     float a, float b, int dtype, int mode, void* stream);
 
+/* ---- f1: batched multi-stage nearest-neighbour affine re-warp ------------------------------
+ * Replaces the per-sample loops of train_human.py:361-372 (teacher recon: k views x three
+ * tF.affine(nearest) calls, mean over views), :418-423 (student recon under autocast, needs
+ * backward) and :385-412 (occlusion: three-stage warp, patch paste, one-stage warp back);
+ * same code in train_animal.py.  A chain of nearest-neighbour resamplings is a composition of
+ * integer source-index maps, so the whole chain is one gather out[p] = in[s1(s2(s3(p)))].
+ * in[v] / theta[v] are HOST arrays of `views` DEVICE pointers: in[v] is [B,C,H,W] of `dtype`,
+ * theta[v] is float32 [B,stages,6] holding, per sample and stage IN EVALUATION ORDER (the stage
+ * applied last by the reference comes first), torchvision's rescaled inverse matrix
+ * theta[r][k] / (0.5*size_r) rounded in that stage's grid dtype.  Bit s of half_mask marks
+ * stage s as computed on a grid_dtype (UDAPE_F16 / UDAPE_BF16) grid — the first tF.affine of a
+ * half tensor under autocast; all other arithmetic is float32 in torchvision's / ATen's CPU op
+ * order (x*r0 -> fma(y,r1,.) -> +r2; ((g+1)*size-1)/2; rint).  out = mean over views
+ * (sequential float32 sum, one division), written in `dtype`.
+ * paste (optional, device int32 [B,6] = dst row0,row1,col0,col1, src row0,col0) is the patch copy
+ * of :409, applied after `paste_after` evaluated stages.  active (optional, device uint8 [B],
+ * views == 1): samples with 0 are copied through unchanged.  The gather cannot run in place. */
+UDAPE_API int udape_rewarp_fwd(const void* const* in, const float* const* theta, int views, int stages,
+                     int half_mask, int grid_dtype, const int32_t* paste, int paste_after,
+                     const uint8_t* active, int64_t B, int64_t C, int64_t H, int64_t W, int dtype,
+                     void* out, void* stream);
+/* Gradient of the single-view re-warp w.r.t. its input: grad_in[s] = sum of grad_out[p] over
+ * {p : source(p) = s}, float32 accumulation in ascending p (deterministic: the composed map is
+ * inverted in shared memory with integer counting, no float atomics).  H*W <= 25600. */
+UDAPE_API int udape_rewarp_bwd(const void* grad_out, const float* theta, int stages, int half_mask,
+                     int grid_dtype, int64_t B, int64_t C, int64_t H, int64_t W, int dtype,
+                     void* grad_in, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -329,3 +329,201 @@ def model_ema_update(ema_tensors, model_tensors, decay, ema_buffers=(), model_bu
             e.copy_(e * decay + (1.0 - decay) * m)
         for e, m in zip(ema_buffers, model_buffers):
             e.copy_(m)
+
+
+# --------------------------------------------------------------------------------------------------
+# f1  affine re-warp loops  (train_human.py:359-372, :385-412, :418-423; same in train_animal.py)
+# --------------------------------------------------------------------------------------------------
+# The reference calls torchvision's ``tF.affine`` (an un-vendored, un-pinned dependency; this image
+# has torchvision 0.26).  The loops below keep the reference's calls — per sample, three tF.affine
+# calls, `.item()` on every parameter — so they ARE the reference semantics as long as torchvision
+# is importable (it is in the build container and on the GPU box).  ``affine_nearest_restated``
+# restates what one such call computes, in numpy, in the float32 op order of torchvision's
+# `_gen_affine_grid` (CPU bmm = FMA chain over k) and ATen's `grid_sample(nearest)`; it is pinned
+# bit-exactly against tF.affine by tests/test_oracle_golden.py and is what csrc/rewarp.cu follows.
+
+
+def student_recon(y_t_stu, aug_param_stu, ratio, autocast=True):
+    """train_human.py:417-423.  `autocast` reproduces the `torch.cuda.amp.autocast()` block on the
+    CPU (`torch.autocast('cpu', float16)` has the same cast policy for bmm / grid_sampler)."""
+    from torchvision.transforms import functional as tF
+
+    angle, [trans_x, trans_y], [shear_x, shear_y], scale = aug_param_stu
+    ctx = torch.autocast("cpu", dtype=y_t_stu.dtype) if (autocast and y_t_stu.dtype != torch.float32) else _null_ctx()
+    with ctx:
+        rows = []
+        for ind in range(y_t_stu.size(0)):
+            _angle, _trans_x, _trans_y, _shear_x, _shear_y, _scale = (angle[ind].item(), trans_x[ind].item(),
+                                                                      trans_y[ind].item(), shear_x[ind].item(),
+                                                                      shear_y[ind].item(), scale[ind].item())
+            temp = tF.affine(y_t_stu[ind], 0., translate=[_trans_x / ratio, _trans_y / ratio], shear=[0., 0.], scale=1.)
+            temp = tF.affine(temp, _angle, translate=[0., 0.], shear=[0., 0.], scale=_scale)
+            # the reference assigns into zeros_like(y_t_stu): a cast back to the student dtype
+            rows.append(tF.affine(temp, 0., translate=[0., 0.], shear=[_shear_x, _shear_y], scale=1.).to(y_t_stu.dtype))
+        return torch.stack(rows, 0)
+
+
+class _null_ctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def teacher_recon(y_t_teas, meta_aug_params, ratio):
+    """train_human.py:359-372 — k views, CPU staging tensor `recons`, mean over views."""
+    from torchvision.transforms import functional as tF
+
+    k = len(y_t_teas)
+    out = torch.zeros_like(y_t_teas[0])
+    for ind in range(y_t_teas[0].size(0)):
+        recons = torch.zeros(k, *y_t_teas[0].size()[1:])
+        for _k in range(k):
+            angle, [trans_x, trans_y], [shear_x, shear_y], scale = meta_aug_params[_k]
+            _angle, _trans_x, _trans_y, _shear_x, _shear_y, _scale = (angle[ind].item(), trans_x[ind].item(),
+                                                                      trans_y[ind].item(), shear_x[ind].item(),
+                                                                      shear_y[ind].item(), scale[ind].item())
+            temp = tF.affine(y_t_teas[_k][ind], 0., translate=[_trans_x / ratio, _trans_y / ratio], shear=[0., 0.], scale=1.)
+            temp = tF.affine(temp, _angle, translate=[0., 0.], shear=[0., 0.], scale=_scale)
+            temp = tF.affine(temp, 0., translate=[0, 0], shear=[_shear_x, _shear_y], scale=1.)
+            recons[_k] = temp
+        out[ind] = torch.mean(recons, dim=0)
+    return out
+
+
+def occlude_keypoints(x_t_stu, conf_table, pred_position, aug_param_stu, ratio, occlude_rate, occlude_size,
+                      image_size, rng=np.random):
+    """train_human.py:385-412 (with `np.int` spelled `int`: the alias is gone from numpy >= 1.24).
+    pred_position is the host int array [B,K,2]; conf_table a bool tensor [B,K].  Returns a new
+    tensor; a sample whose source patch overlaps the destination raises like the reference."""
+    from torchvision.transforms import functional as tF
+
+    x_t_stu = x_t_stu.clone()
+    angle, [trans_x, trans_y], [shear_x, shear_y], scale = aug_param_stu
+    b, k = conf_table.shape
+    for _b in range(b):
+        if conf_table[_b].sum() > 0 and rng.rand() <= occlude_rate:
+            _angle, _trans_x, _trans_y, _shear_x, _shear_y, _scale = (angle[_b].item(), trans_x[_b].item(),
+                                                                      trans_y[_b].item(), shear_x[_b].item(),
+                                                                      shear_y[_b].item(), scale[_b].item())
+            temp = tF.affine(x_t_stu[_b], 0., translate=[_trans_x / ratio, _trans_y / ratio], shear=[0., 0.], scale=1.)
+            temp = tF.affine(temp, _angle, translate=[0., 0.], shear=[0., 0.], scale=_scale)
+            temp = tF.affine(temp, 0., translate=[0., 0.], shear=[_shear_x, _shear_y], scale=1.)
+            candidates = torch.arange(0, k)[conf_table[_b]]
+            _c = rng.choice(candidates)
+            position = (pred_position[_b, _c] * ratio).astype(int)
+            left = max(position[1] - occlude_size, 0)
+            right = min(position[1] + occlude_size, image_size)
+            upper = max(position[0] - occlude_size, 0)
+            bottom = min(position[0] + occlude_size, image_size)
+            left_src = rng.randint(image_size - (right - left) + 1)
+            right_src = left_src + right - left
+            upper_src = rng.randint(image_size - (bottom - upper) + 1)
+            bottom_src = upper_src + bottom - upper
+            temp[:, left:right, upper:bottom] = temp[:, left_src:right_src, upper_src:bottom_src]
+            x_t_stu[_b] = tF.affine(temp, -_angle, translate=[-_trans_x / ratio, -_trans_y / ratio],
+                                    shear=[-_shear_x, -_shear_y], scale=1. / _scale)
+    return x_t_stu
+
+
+def inverse_affine_matrix(center, angle, translate, scale, shear):
+    """torchvision 0.26 transforms/functional.py `_get_inverse_affine_matrix` (inverted=True),
+    reached by the reference through tF.affine (train_human.py:366-368)."""
+    import math
+
+    rot, sx, sy = math.radians(angle), math.radians(shear[0]), math.radians(shear[1])
+    cx, cy = center
+    tx, ty = translate
+    a = math.cos(rot - sy) / math.cos(sy)
+    b = -math.cos(rot - sy) * math.tan(sx) / math.cos(sy) - math.sin(rot)
+    c = math.sin(rot - sy) / math.cos(sy)
+    d = -math.sin(rot - sy) * math.tan(sx) / math.cos(sy) + math.cos(rot)
+    matrix = [d, -b, 0.0, -c, a, 0.0]
+    matrix = [x / scale for x in matrix]
+    matrix[2] += matrix[0] * (-cx - tx) + matrix[1] * (-cy - ty)
+    matrix[5] += matrix[3] * (-cx - tx) + matrix[4] * (-cy - ty)
+    matrix[2] += cx
+    matrix[5] += cy
+    return matrix
+
+
+def affine_source_index(matrix, height, width, theta_dtype=torch.float32, grid_dtype=None):
+    """Source pixel of every output pixel of ONE tF.affine(nearest) call: int64 [H,W] flat index,
+    -1 where grid_sample pads with zero.  torchvision `_gen_affine_grid` + ATen grid_sampler:
+
+        theta = tensor(matrix, theta_dtype)            theta_dtype = dtype of the image tensor
+        r = theta / (0.5*size) per row                 (in theta_dtype)
+        x = linspace(-W/2+.5, W/2-.5, W), y likewise   (stored in theta_dtype)
+        g = base_grid.bmm(r)                           under autocast bmm casts both operands to the
+                                                       autocast dtype (= grid_dtype) and returns it;
+                                                       CPU bmm = float32 FMA chain over k = 3:
+                                                       fma(y, r1, x*r0) + r2, then one rounding
+        ix = ((g + 1) * W - 1) / 2 in float32 (grid_sampler is autocast to float32);
+        nearest = rint(ix); valid iff 0 <= nearest <= W-1
+    """
+    f32 = np.float32
+    grid_dtype = grid_dtype or theta_dtype
+
+    def rnd(a, dt):
+        return a if dt == torch.float32 else torch.from_numpy(np.ascontiguousarray(a)).to(dt).float().numpy()
+
+    theta = torch.tensor(matrix, dtype=theta_dtype).reshape(2, 3)
+    r = (theta / torch.tensor([0.5 * width, 0.5 * height], dtype=theta_dtype).view(2, 1)).to(grid_dtype).float().numpy()
+    x = rnd(rnd((np.arange(width, dtype=np.float64) + (0.5 - 0.5 * width)).astype(f32), theta_dtype), grid_dtype)
+    y = rnd(rnd((np.arange(height, dtype=np.float64) + (0.5 - 0.5 * height)).astype(f32), theta_dtype), grid_dtype)
+    xx, yy = np.meshgrid(x, y)
+    src = []
+    for row, size in ((0, width), (1, height)):
+        t = (xx * r[row, 0]).astype(f32)                                   # rounded product
+        t = (yy.astype(np.float64) * np.float64(r[row, 1]) + t.astype(np.float64)).astype(f32)  # fma (exact product)
+        g = rnd((t + r[row, 2]).astype(f32), grid_dtype)
+        i = ((g + f32(1)) * f32(size) - f32(1)) / f32(2)
+        src.append(np.rint(i))
+    ok = (src[0] >= 0) & (src[0] <= width - 1) & (src[1] >= 0) & (src[1] <= height - 1)
+    flat = np.where(ok, src[1] * width + src[0], -1).astype(np.int64)
+    return flat
+
+
+def affine_nearest_restated(img, angle, translate, scale, shear, autocast_dtype=None):
+    """One tF.affine(img [C,H,W], nearest) through `affine_source_index`; `autocast_dtype` = the
+    dtype of an enclosing torch.autocast block (None: no autocast)."""
+    c, h, w = img.shape
+    m = inverse_affine_matrix([0.0, 0.0], angle, [1.0 * t for t in translate], scale, shear)
+    src = torch.from_numpy(affine_source_index(m, h, w, img.dtype, autocast_dtype or img.dtype)).reshape(-1)
+    flat = img.reshape(c, h * w)
+    out = torch.where(src >= 0, flat[:, src.clamp_min(0)], torch.zeros((), dtype=img.dtype))
+    return out.reshape(c, h, w)
+
+
+def recon_source_index(angle, trans_x, trans_y, shear_x, shear_y, scale, ratio, height, width,
+                       first_dtype=torch.float32, autocast_dtype=None):
+    """Composed source index of the three-call chain (train_human.py:366-368 / :421-423) for one
+    sample: out[p] = in[s1(s2(s3(p)))].  Under autocast the first call sees the half tensor (theta
+    in half); grid_sample returns float32, so the later calls build float32 thetas — but bmm still
+    casts them, and the base grid, to the autocast dtype: every grid is a half grid."""
+    later = torch.float32 if autocast_dtype is not None else first_dtype
+    calls = [(0.0, [trans_x / ratio, trans_y / ratio], 1.0, [0.0, 0.0], first_dtype),
+             (angle, [0.0, 0.0], scale, [0.0, 0.0], later),
+             (0.0, [0.0, 0.0], 1.0, [shear_x, shear_y], later)]
+    maps = [affine_source_index(inverse_affine_matrix([0.0, 0.0], a, [1.0 * t for t in tr], sc, sh), height, width,
+                                td, autocast_dtype or td).reshape(-1) for (a, tr, sc, sh, td) in calls]
+    src = maps[2]                        # last applied call is evaluated first
+    for m in (maps[1], maps[0]):
+        src = np.where(src >= 0, m[np.clip(src, 0, None)], -1)
+    return src
+
+
+def recon_restated(y, aug_param, ratio, autocast_dtype=None):
+    """student/teacher recon of one view through `recon_source_index` (forward), for pinning the
+    composition + autocast rule that csrc/rewarp.cu implements."""
+    angle, [trans_x, trans_y], [shear_x, shear_y], scale = aug_param
+    b, c, h, w = y.shape
+    out = torch.zeros_like(y)
+    for ind in range(b):
+        src = torch.from_numpy(recon_source_index(angle[ind].item(), trans_x[ind].item(), trans_y[ind].item(),
+                                                  shear_x[ind].item(), shear_y[ind].item(), scale[ind].item(),
+                                                  ratio, h, w, y.dtype, autocast_dtype))
+        flat = y[ind].reshape(c, h * w)
+        out[ind] = torch.where(src >= 0, flat[:, src.clamp_min(0)], torch.zeros((), dtype=y.dtype)).reshape(c, h, w)
+    return out

@@ -303,13 +303,123 @@ def golden_clamp():
     save("clamp", **out)
 
 
+def golden_rewarp():
+    """train_human.py:359-372 (teacher recon), :417-423 (student recon under autocast, with autograd)
+    and :385-412 (occlusion) executed as written, through torchvision's tF.affine on the CPU.  The
+    fragments are inline trainer code, so they are restated here line by line; `.cuda()` calls are
+    dropped and `torch.cuda.amp.autocast()` becomes `torch.autocast('cpu', float16)` (same cast
+    policy: bmm stays half, grid_sampler runs in float32)."""
+    from torchvision.transforms import functional as tF
+
+    out = {}
+    ratio = 256 / 64
+
+    def flat_aug(tag, ap):
+        angle, (tx, ty), (sx, sy), sc = ap
+        out[f"{tag}_aug"] = np.stack([angle.numpy(), tx.numpy().astype(np.float64), ty.numpy().astype(np.float64),
+                                      sx.numpy(), sy.numpy(), sc.numpy()], 1)
+
+    # ---- teacher recon, k = 1 and k = 2 views, float32 --------------------------------------------
+    for tag, k, shape in (("tea1", 1, (3, 4, 64, 64)), ("tea2", 2, (2, 3, 64, 64)), ("teaodd", 1, (2, 5, 24, 40))):
+        y_t_teas = [synthetic.heatmaps(shape[0], shape[1], seed=70 + i, h=shape[2], w=shape[3], peak=(0.3, 1.2)) for i in range(k)]
+        meta_t_tea = [{"aug_param_tea": synthetic.aug_params(shape[0], seed=80 + i, shear_y=(tag == "teaodd"))} for i in range(k)]
+        y_t_tea_recon = torch.zeros_like(y_t_teas[0])
+        for ind in range(y_t_teas[0].size(0)):
+            recons = torch.zeros(k, *y_t_teas[0].size()[1:])
+            for _k in range(k):
+                angle, [trans_x, trans_y], [shear_x, shear_y], scale = meta_t_tea[_k]["aug_param_tea"]
+                _angle, _trans_x, _trans_y, _shear_x, _shear_y, _scale = angle[ind].item(), trans_x[ind].item(), trans_y[ind].item(), shear_x[ind].item(), shear_y[ind].item(), scale[ind].item()
+                temp = tF.affine(y_t_teas[_k][ind], 0., translate=[_trans_x / ratio, _trans_y / ratio], shear=[0., 0.], scale=1.)
+                temp = tF.affine(temp, _angle, translate=[0., 0.], shear=[0., 0.], scale=_scale)
+                temp = tF.affine(temp, 0., translate=[0, 0], shear=[_shear_x, _shear_y], scale=1.)
+                recons[_k] = temp
+            y_t_tea_recon[ind] = torch.mean(recons, dim=0)
+        for i in range(k):
+            out[f"{tag}_in{i}"] = y_t_teas[i]
+            flat_aug(f"{tag}_v{i}", meta_t_tea[i]["aug_param_tea"])
+        out[f"{tag}_out"] = y_t_tea_recon
+
+    # ---- student recon under autocast, with the gradient of sum(recon * G) --------------------------
+    for tag, dt in (("stu16", torch.float16), ("stubf", torch.bfloat16), ("stu32", torch.float32)):
+        y_t_stu = synthetic.heatmaps(3, 4, seed=90).to(dt).requires_grad_(True)
+        aug = synthetic.aug_params(3, seed=91)
+        angle, [trans_x, trans_y], [shear_x, shear_y], scale = aug
+        G = torch.randn(3, 4, 64, 64, generator=torch.Generator().manual_seed(92))
+        with torch.autocast("cpu", dtype=dt, enabled=dt != torch.float32):
+            y_t_stu_recon = torch.zeros_like(y_t_stu)
+            rows = []
+            for ind in range(y_t_stu.size(0)):
+                _angle, _trans_x, _trans_y, _shear_x, _shear_y, _scale = angle[ind].item(), trans_x[ind].item(), trans_y[ind].item(), shear_x[ind].item(), shear_y[ind].item(), scale[ind].item()
+                temp = tF.affine(y_t_stu[ind], 0., translate=[_trans_x / ratio, _trans_y / ratio], shear=[0., 0.], scale=1.)
+                temp = tF.affine(temp, _angle, translate=[0., 0.], shear=[0., 0.], scale=_scale)
+                # `y_t_stu_recon[ind] = ...` on a zeros_like(y_t_stu) buffer: a cast to the student dtype
+                rows.append(tF.affine(temp, 0., translate=[0., 0.], shear=[_shear_x, _shear_y], scale=1.).to(dt))
+            y_t_stu_recon = torch.stack(rows, 0)
+        (y_t_stu_recon.float() * G).sum().backward()
+        out[f"{tag}_in"] = y_t_stu.detach().float()
+        flat_aug(tag, aug)
+        out[f"{tag}_G"] = G
+        out[f"{tag}_out"] = y_t_stu_recon.detach().float()
+        out[f"{tag}_grad"] = y_t_stu.grad.float()
+
+    # ---- occlusion, :385-412 (np.int -> int), small images: image_size 64, heatmaps 16 -------------
+    image_size, occlude_size, occlude_rate = 64, 6, 0.7
+    b, k = 4, 5
+    for seed in range(100, 200):
+        x_t_stu = torch.randn(b, 3, image_size, image_size, generator=torch.Generator().manual_seed(seed))
+        x_in = x_t_stu.clone()
+        aug = synthetic.aug_params(b, seed=seed + 1, image=image_size)
+        tea = synthetic.heatmaps(b, k, seed=seed + 2, h=16, w=16, peak=(0.5, 1.4))
+        angle, [trans_x, trans_y], [shear_x, shear_y], scale = aug
+        bb, kk, h, w = tea.size()
+        conf = tea.amax(dim=(2, 3))
+        pred_position = tea.view(bb, kk, -1).argmax(-1)
+        pred_position = torch.stack([pred_position % w, pred_position // w], -1).cpu().numpy()
+        conf_table = conf >= 0.9
+        np.random.seed(seed)
+        try:
+            n_occluded = 0
+            for _b in range(bb):
+                if (conf_table[_b].sum() > 0 and np.random.rand() <= occlude_rate):
+                    _angle, _trans_x, _trans_y, _shear_x, _shear_y, _scale = angle[_b].item(), trans_x[_b].item(), trans_y[_b].item(), shear_x[_b].item(), shear_y[_b].item(), scale[_b].item()
+                    temp = tF.affine(x_t_stu[_b], 0., translate=[_trans_x / ratio, _trans_y / ratio], shear=[0., 0.], scale=1.)
+                    temp = tF.affine(temp, _angle, translate=[0., 0.], shear=[0., 0.], scale=_scale)
+                    temp = tF.affine(temp, 0., translate=[0., 0.], shear=[_shear_x, _shear_y], scale=1.)
+                    candidates = torch.arange(0, kk)[conf_table[_b]]
+                    _c = np.random.choice(candidates)
+                    position = (pred_position[_b, _c] * ratio).astype(int)
+                    left = max(position[1] - occlude_size, 0)
+                    right = min(position[1] + occlude_size, image_size)
+                    upper = max(position[0] - occlude_size, 0)
+                    bottom = min(position[0] + occlude_size, image_size)
+                    left_src = np.random.randint(image_size - (right - left) + 1)
+                    right_src = left_src + right - left
+                    upper_src = np.random.randint(image_size - (bottom - upper) + 1)
+                    bottom_src = upper_src + bottom - upper
+                    temp[:, left:right, upper:bottom] = temp[:, left_src:right_src, upper_src:bottom_src]
+                    x_t_stu[_b] = tF.affine(temp, -_angle, translate=[-_trans_x / ratio, -_trans_y / ratio], shear=[-_shear_x, -_shear_y], scale=1. / _scale)
+                    n_occluded += 1
+        except RuntimeError:
+            continue  # overlapping source / destination patch: torch refuses the copy, try another seed
+        if 2 <= n_occluded < bb:
+            break
+    else:
+        raise SystemExit("no occlusion seed found")
+    out["occ_seed"] = np.int64(seed)
+    out["occ_in"], out["occ_out"] = x_in, x_t_stu
+    out["occ_conf_table"], out["occ_pred_position"] = conf_table, pred_position
+    flat_aug("occ", aug)
+    out["occ_args"] = np.array([ratio, occlude_rate, occlude_size, image_size], dtype=np.float64)
+    save("rewarp", **out)
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit(f"reference tree not found at {ref_loader.REFERENCE_ROOT}")
     torch.manual_seed(0)
     np.random.seed(0)
     fns = (golden_adain, golden_decode, golden_accuracy, golden_losses, golden_masks, golden_rectify,
-           golden_targets, golden_ema, golden_clamp)
+           golden_targets, golden_ema, golden_clamp, golden_rewarp)
     only = set(sys.argv[1:])  # e.g. `make_golden.py clamp` regenerates one fixture
     for fn in fns:
         if not only or fn.__name__.removeprefix("golden_") in only:

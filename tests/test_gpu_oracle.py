@@ -377,10 +377,13 @@ def test_fused_losses_vs_oracle(dev, cfg, dtype):
         assert_close_scaled(losses[2], l_c.detach(), 1e-5, f"{route} loss_c")
         assert_close_scaled(g1.float(), o1.grad, rtol, f"{route} grad y_s")
         assert_close_scaled(g2.float(), o2.grad, rtol, f"{route} grad y_t_stu")
-    # the two routes use the same device functions for the rectified values: identical bits
+    # the two routes use the same device functions for the rectified values: identical gradient bits
+    # (the loss sums run over 8-element instead of 4-element groups on the analytic route: same
+    # addends, different fp32 summation order)
     la, ga1, ga2 = U.fused_losses(y_s.to(dev), label.to(dev), weight.to(dev), y_t.to(dev), U.rectify(tea_raw.to(dev), sigma),
                                   tea_mask.to(dev), lambda_c=lam, grad_scale=scale)
-    assert torch.equal(la, losses) and torch.equal(ga2, g2) and torch.equal(ga1, g1)
+    assert torch.equal(ga2, g2) and torch.equal(ga1, g1)
+    assert_close_scaled(la, losses, 1e-6, "analytic vs materialised losses")
 
 
 def test_fused_losses_partial_and_odd_shapes(dev):

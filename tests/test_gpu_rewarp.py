@@ -1,0 +1,184 @@
+"""GPU parity of the batched affine re-warp (csrc/rewarp.cu) — the trainers' per-sample tF.affine
+loops (train_human.py:359-372, :385-412, :417-423) — against
+
+* the golden fixtures produced by those loops running through torchvision on the CPU
+  (tests/golden/make_golden.py::golden_rewarp), and
+* the oracle's loops (oracle/reference_port.py, torchvision on the CPU) at BASELINE config sizes.
+
+Bars: forward values are gathered, never computed — BIT-EXACT (every source index must match the
+reference's nearest-neighbour choice, including ties and the half-precision grids of the autocast
+block); gradients are float32 sums rounded once — 1e-5 relative in fp32, 1e-2 in fp16 (2e-2 in
+bf16, see tests/test_oracle_golden.py::test_student_recon).
+"""
+import numpy as np
+import pytest
+import torch
+
+import uda_poseestimation_b200 as U
+from conftest import assert_close_scaled
+from oracle import reference_port as R
+from uda_poseestimation_b200 import rewarp as RW
+from uda_poseestimation_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+GRAD_TOL = {torch.float32: 1e-5, torch.float16: 1e-2, torch.bfloat16: 2e-2}
+
+
+def C(a, dev):
+    return torch.from_numpy(np.asarray(a)).to(dev)
+
+
+def aug_of(a):
+    a = torch.from_numpy(np.asarray(a))
+    return [a[:, 0], [a[:, 1].long(), a[:, 2].long()], [a[:, 3], a[:, 4]], a[:, 5]]
+
+
+@pytest.mark.parametrize("tag,k", [("tea1", 1), ("tea2", 2), ("teaodd", 1)])
+def test_teacher_recon_golden(golden, dev, tag, k):
+    g = golden("rewarp")
+    views = [C(g[f"{tag}_in{i}"], dev) for i in range(k)]
+    augs = [aug_of(g[f"{tag}_v{i}_aug"]) for i in range(k)]
+    out = U.teacher_recon(views, augs, 4.0)
+    assert out.dtype == torch.float32 and out.shape == views[0].shape
+    assert torch.equal(out.cpu(), torch.from_numpy(g[f"{tag}_out"]))
+
+
+@pytest.mark.parametrize("tag,dt", [("stu16", torch.float16), ("stubf", torch.bfloat16), ("stu32", torch.float32)])
+def test_student_recon_golden(golden, dev, tag, dt):
+    g = golden("rewarp")
+    y = C(g[f"{tag}_in"], dev).to(dt).requires_grad_(True)
+    aug = aug_of(g[f"{tag}_aug"])
+    ac = None if dt == torch.float32 else dt
+    out = U.student_recon(y, aug, 4.0, autocast=ac)
+    assert out.dtype == dt
+    assert torch.equal(out.detach().float().cpu(), torch.from_numpy(g[f"{tag}_out"]))
+    (out.float() * C(g[f"{tag}_G"], dev)).sum().backward()
+    assert y.grad.dtype == dt
+    assert_close_scaled(y.grad.float(), g[f"{tag}_grad"], GRAD_TOL[dt], f"{tag} grad")
+    if ac is not None:
+        # inside the trainers' autocast block the dtype is picked up from the context
+        with torch.autocast("cuda", dtype=dt):
+            out2 = U.student_recon(y.detach(), aug, 4.0)
+        assert torch.equal(out2, out.detach())
+        with pytest.raises(NotImplementedError):
+            U.student_recon(y.detach(), aug, 4.0)  # a half tensor outside autocast
+
+
+def test_occlusion_golden(golden, dev):
+    g = golden("rewarp")
+    ratio, rate, size, image = g["occ_args"]
+    rng = np.random.RandomState(int(g["occ_seed"]))
+    out = U.occlude_keypoints(C(g["occ_in"], dev), g["occ_conf_table"], g["occ_pred_position"], aug_of(g["occ_aug"]),
+                              float(ratio), float(rate), int(size), int(image), rng=rng)
+    assert torch.equal(out.cpu(), torch.from_numpy(g["occ_out"]))
+    # no sample selected: the batch comes back unchanged (a copy)
+    x = C(g["occ_in"], dev)
+    same = U.occlude_keypoints(x, g["occ_conf_table"], g["occ_pred_position"], aug_of(g["occ_aug"]), float(ratio), -1.0,
+                               int(size), int(image), rng=np.random.RandomState(0))
+    assert torch.equal(same, x) and same.data_ptr() != x.data_ptr()
+
+
+@pytest.mark.parametrize("cfg", ["C2", "C4"])
+def test_recon_vs_oracle_at_config_sizes(dev, cfg):
+    b, k = S.CONFIGS[cfg]["batch"], S.CONFIGS[cfg]["joints"]
+    tea = S.heatmaps(b, k, seed=31, peak=(0.3, 1.2))
+    aug_t = S.aug_params(b, seed=32)
+    assert torch.equal(U.teacher_recon([tea.to(dev)], [aug_t], 4.0).cpu(), R.teacher_recon([tea], [aug_t], 4.0))
+    stu = S.heatmaps(b, k, seed=33).half()
+    aug_s = S.aug_params(b, seed=34, shear_y=True)
+    y = stu.to(dev).requires_grad_(True)
+    out = U.student_recon(y, aug_s, 4.0, autocast=torch.float16)
+    y_ref = stu.clone().requires_grad_(True)
+    ref = R.student_recon(y_ref, aug_s, 4.0)
+    assert torch.equal(out.detach().cpu(), ref.detach())
+    G = torch.randn(b, k, 64, 64, generator=torch.Generator().manual_seed(35)).half()
+    out.backward(G.to(dev))
+    ref.backward(G)
+    assert_close_scaled(y.grad.float(), y_ref.grad.float(), 1e-2, "student recon grad")
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 37, 53), (1, 1, 1, 1), (3, 2, 16, 128), (2, 3, 256, 256)])
+def test_affine_nearest_vs_torchvision(dev, shape):
+    """One-stage batched tF.affine, ragged sizes (scalar path), image-sized planes."""
+    from torchvision.transforms import functional as tF
+
+    rng = np.random.RandomState(shape[2])
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(1))
+    b = shape[0]
+    ang = [float(rng.uniform(-180, 180)) for _ in range(b)]
+    sc = [float(rng.uniform(0.5, 1.7)) for _ in range(b)]
+    sh = [[float(rng.uniform(-30, 30)), float(rng.uniform(-30, 30))] for _ in range(b)]
+    tr = [[float(rng.randint(-13, 14)) / 4, float(rng.randint(-13, 14)) / 4] for _ in range(b)]
+    out = U.affine_nearest(x.to(dev), ang, tr, sc, sh)
+    for i in range(b):
+        assert torch.equal(out[i].cpu(), tF.affine(x[i], ang[i], translate=tr[i], scale=sc[i], shear=sh[i])), i
+    one = U.affine_nearest(x[0].to(dev), ang[0], tr[0], sc[0], sh[0])
+    assert one.shape == x[0].shape and torch.equal(one, out[0])
+
+
+def test_rewarp_properties_full_size(dev):
+    """Size-independent properties at the C5-class size (256x21x64x64)."""
+    b, k = 256, 21
+    y = torch.randn(b, k, 64, 64, device=dev)
+    ident = [torch.zeros(b, dtype=torch.float64), [torch.zeros(b, dtype=torch.int64)] * 2,
+             [torch.zeros(b, dtype=torch.float64)] * 2, torch.ones(b, dtype=torch.float64)]
+    assert torch.equal(U.teacher_recon([y], [ident], 4.0), y)                      # identity parameters
+    shift = [torch.zeros(b, dtype=torch.float64), [torch.full((b,), 8, dtype=torch.int64), torch.full((b,), -12, dtype=torch.int64)],
+             [torch.zeros(b, dtype=torch.float64)] * 2, torch.ones(b, dtype=torch.float64)]
+    out = U.teacher_recon([y], [shift], 4.0)                                       # +2 px in x, -3 px in y
+    want = torch.zeros_like(y)
+    want[:, :, :61, 2:] = y[:, :, 3:, :62]
+    assert torch.equal(out, want)
+    aug = S.aug_params(b, seed=7, shear_y=True)
+    table, half_mask, _ = RW.stage_table(RW.recon_stages(aug, 4.0, b), 64, 64, torch.float32, None)
+    theta = table.to(dev)
+    a_, b_ = torch.randn_like(y), torch.randn_like(y)
+    ra, rb = RW.gather(a_, theta), RW.gather(b_, theta)
+    assert torch.equal(RW.gather(a_ + b_, theta), ra + rb)                         # a gather is linear, exactly
+    # adjoint: <rewarp(x), g> == <x, rewarp^T(g)>, and the backward is deterministic
+    x = a_.clone().requires_grad_(True)
+    g = b_
+    RW.gather(x, theta).backward(g)
+    lhs = (ra.double() * g.double()).sum()
+    rhs = (a_.double() * x.grad.double()).sum()
+    assert abs(float(lhs - rhs)) <= 1e-7 * float(ra.double().norm() * g.double().norm())
+    x2 = a_.clone().requires_grad_(True)
+    RW.gather(x2, theta).backward(g)
+    assert torch.equal(x.grad, x2.grad)
+
+
+def test_rewarp_graph_capture(dev):
+    """theta is a device tensor: a captured re-warp follows fresh augmentation parameters."""
+    b, k = 8, 4
+    y = torch.randn(b, k, 64, 64, device=dev)
+    tables = [RW.stage_table(RW.recon_stages(S.aug_params(b, seed=s), 4.0, b), 64, 64, torch.float32, None)[0] for s in (1, 2)]
+    theta = tables[0].to(dev)
+    eager = [RW.gather(y, t.to(dev)) for t in tables]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        RW.gather(y, theta)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = RW.gather(y, theta)
+    for t, want in zip(tables, eager):
+        theta.copy_(t)
+        graph.replay()
+        assert torch.equal(out, want)
+
+
+def test_rewarp_argument_errors(dev):
+    y = torch.randn(2, 3, 8, 8, device=dev)
+    theta = torch.zeros(2, 3, 6, device=dev)
+    with pytest.raises(RuntimeError):
+        RW.gather(y.cpu(), theta)                       # no CPU fallback
+    with pytest.raises(ValueError):
+        RW.gather(y, torch.zeros(3, 3, 6, device=dev))  # batch mismatch
+    with pytest.raises(ValueError):
+        RW.gather(y, torch.zeros(2, 5, 6, device=dev))  # too many stages
+    with pytest.raises(ValueError):
+        U.teacher_recon([y, y], [None], 4.0)
+    big = torch.randn(1, 1, 256, 256, device=dev, requires_grad=True)
+    with pytest.raises(ValueError):                      # backward keeps the inverted map in shared memory
+        RW.gather(big, torch.zeros(1, 1, 6, device=dev)).sum().backward()

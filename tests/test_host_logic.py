@@ -148,3 +148,105 @@ def test_two_rank_gloo_pck_and_gradient_allreduce():
         vals.append(got[off:off + n])
         off += n
     np.testing.assert_allclose(np.concatenate(vals), expect, rtol=1e-6, atol=1e-7)
+
+
+# ---- re-warp host logic: the stage table the kernel consumes (no GPU) ------------------------------
+def _emulate_table(theta, half_mask, grid_dtype, h, w):
+    """numpy emulation of csrc/rewarp.cu::composed_source for one sample's [S,6] table."""
+    f32 = np.float32
+
+    def rnd(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(grid_dtype).float().numpy()
+
+    jj, ii = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    i, j = ii.reshape(-1).astype(np.int64), jj.reshape(-1).astype(np.int64)
+    alive = np.ones(h * w, dtype=bool)
+    for s in range(theta.shape[0]):
+        r = theta[s]
+        half = (half_mask >> s) & 1
+        x = (i.astype(f32) + f32(0.5 - 0.5 * w)).astype(f32)
+        y = (j.astype(f32) + f32(0.5 - 0.5 * h)).astype(f32)
+        if half:
+            x, y = rnd(x), rnd(y)
+        src = []
+        for row, size in ((0, w), (1, h)):
+            t = (x * r[3 * row]).astype(f32)
+            t = (y.astype(np.float64) * np.float64(r[3 * row + 1]) + t.astype(np.float64)).astype(f32)
+            g = (t + r[3 * row + 2]).astype(f32)
+            if half:
+                g = rnd(g)
+            src.append(np.rint(((g + f32(1)) * f32(size) - f32(1)) * f32(0.5)))
+        ok = (src[0] >= 0) & (src[0] <= w - 1) & (src[1] >= 0) & (src[1] <= h - 1)
+        alive &= ok
+        i = np.where(ok, src[0], 0).astype(np.int64)
+        j = np.where(ok, src[1], 0).astype(np.int64)
+    return np.where(alive, j * w + i, -1)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16, torch.bfloat16])
+def test_rewarp_stage_table_matches_oracle(dt):
+    from oracle import reference_port as R
+    from uda_poseestimation_b200 import rewarp as RW
+    from uda_poseestimation_b200 import synthetic as S
+
+    b, h, w, ratio = 6, 64, 64, 4.0
+    aug = S.aug_params(b, seed=5, shear_y=True)
+    ac = None if dt == torch.float32 else dt
+    table, half_mask, code = RW.stage_table(RW.recon_stages(aug, ratio, b), h, w, dt, ac)
+    assert table.shape == (b, 3, 6) and table.dtype == torch.float32
+    assert half_mask == (0 if ac is None else 7)
+    angle, [tx, ty], [sx, sy], sc = aug
+    for i in range(b):
+        want = R.recon_source_index(angle[i].item(), tx[i].item(), ty[i].item(), sx[i].item(), sy[i].item(),
+                                    sc[i].item(), ratio, h, w, dt, ac)
+        got = _emulate_table(table[i].numpy(), half_mask, dt, h, w)
+        np.testing.assert_array_equal(got, want)
+
+
+def test_rewarp_autocast_argument():
+    from uda_poseestimation_b200 import rewarp as RW
+
+    stages = [[(10.0, [1.0, 2.0], 1.1, [3.0, 0.0])]]
+    with pytest.raises(NotImplementedError):
+        RW.stage_table(stages, 8, 8, torch.float16, "auto")      # half tensor outside autocast
+    with pytest.raises(NotImplementedError):
+        RW.stage_table(stages, 8, 8, torch.float16, None)
+    with pytest.raises(ValueError):
+        RW.stage_table(stages, 8, 8, torch.float32, torch.float64)
+    t32, m32, _ = RW.stage_table(stages, 8, 8, torch.float32, "auto")
+    assert m32 == 0
+    t16, m16, code = RW.stage_table(stages, 8, 8, torch.float32, torch.float16)  # fp32 tensor inside autocast(fp16)
+    assert m16 == 1 and torch.equal(t16, t32.half().float())
+
+
+def test_occlusion_plan_follows_reference_rng(golden):
+    """The host plan draws from np.random in the reference's order (train_human.py:386-407)."""
+    from oracle import reference_port as R
+    from uda_poseestimation_b200 import rewarp as RW
+
+    g = golden("rewarp")
+    ratio, rate, size, image = g["occ_args"]
+    a = torch.from_numpy(g["occ_aug"])
+    aug = [a[:, 0], [a[:, 1].long(), a[:, 2].long()], [a[:, 3], a[:, 4]], a[:, 5]]
+    active, paste, stages = RW.occlusion_plan(g["occ_conf_table"], g["occ_pred_position"], aug, float(ratio), float(rate),
+                                              int(size), int(image), rng=np.random.RandomState(int(g["occ_seed"])))
+    changed = (g["occ_in"] != g["occ_out"]).reshape(len(active), -1).any(1)
+    np.testing.assert_array_equal(active.astype(bool), changed)
+    assert all(len(s) == 4 for s in stages)
+    # emulate the kernel on the host for the occluded samples: warp back, paste remap, three-stage warp
+    table, half_mask, _ = RW.stage_table(stages, int(image), int(image), torch.float32, None)
+    x_in, x_out = g["occ_in"], g["occ_out"]
+    n = int(image)
+    for bi in np.nonzero(active)[0]:
+        th = table[bi].numpy()
+        first = _emulate_table(th[:1], 0, torch.float32, n, n)
+        j, i = first // n, first % n
+        r0, r1, c0, c1, sr, scol = paste[bi]
+        inside = (first >= 0) & (j >= r0) & (j < r1) & (i >= c0) & (i < c1)
+        j = np.where(inside, j + sr - r0, j)
+        i = np.where(inside, i + scol - c0, i)
+        rest = _emulate_table(th[1:], 0, torch.float32, n, n)
+        src = np.where(first >= 0, rest[np.clip(j * n + i, 0, None)], -1)
+        flat = x_in[bi].reshape(3, -1)
+        want = np.where(src >= 0, flat[:, np.clip(src, 0, None)], 0.0).reshape(3, n, n)
+        np.testing.assert_array_equal(want, x_out[bi])

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import assert_close_scaled
 from oracle import reference_port as R
 
 
@@ -165,3 +166,78 @@ def test_channel_clamp(golden, tag):
     g = golden("clamp")
     y = R.channel_clamp(torch.from_numpy(g[f"{tag}_x"]), torch.from_numpy(g[f"{tag}_lo"]), torch.from_numpy(g[f"{tag}_hi"]))
     np.testing.assert_array_equal(y.contiguous().numpy(), g[f"{tag}_y"])
+
+
+# ---- f1: affine re-warp loops (train_human.py:359-372, :385-412, :417-423) ------------------------
+def aug_of(a):
+    a = T(a)
+    return [a[:, 0], [a[:, 1].long(), a[:, 2].long()], [a[:, 3], a[:, 4]], a[:, 5]]
+
+
+@pytest.mark.parametrize("tag,k", [("tea1", 1), ("tea2", 2), ("teaodd", 1)])
+def test_teacher_recon(golden, tag, k):
+    g = golden("rewarp")
+    views = [T(g[f"{tag}_in{i}"]) for i in range(k)]
+    augs = [aug_of(g[f"{tag}_v{i}_aug"]) for i in range(k)]
+    assert torch.equal(R.teacher_recon(views, augs, 4.0), T(g[f"{tag}_out"]))
+    if k == 1:  # the composed-index restatement the CUDA kernel follows
+        assert torch.equal(R.recon_restated(views[0], augs[0], 4.0), T(g[f"{tag}_out"]))
+
+
+@pytest.mark.parametrize("tag,dt", [("stu16", torch.float16), ("stubf", torch.bfloat16), ("stu32", torch.float32)])
+def test_student_recon(golden, tag, dt):
+    g = golden("rewarp")
+    y = T(g[f"{tag}_in"]).to(dt)
+    aug = aug_of(g[f"{tag}_aug"])
+    assert torch.equal(R.student_recon(y, aug, 4.0).float(), T(g[f"{tag}_out"]))
+    # composition of the three source-index maps, first grid in the half dtype (autocast rule)
+    ac = None if dt == torch.float32 else dt
+    assert torch.equal(R.recon_restated(y, aug, 4.0, ac).float(), T(g[f"{tag}_out"]))
+    # gradient = scatter-add along the composed map of G as it arrives in the student dtype (float32
+    # sums, one rounding to dt; the reference rounds to dt after every call, hence the tolerance)
+    G = T(g[f"{tag}_G"]).to(dt).float()
+    b, c, h, w = y.shape
+    grad = torch.zeros(b, c, h * w)
+    angle, [tx, ty], [sx, sy], sc = aug
+    for i in range(b):
+        src = T(R.recon_source_index(angle[i].item(), tx[i].item(), ty[i].item(), sx[i].item(), sy[i].item(),
+                                     sc[i].item(), 4.0, h, w, dt, ac))
+        ok = src >= 0
+        grad[i].index_add_(1, src[ok], G[i].reshape(c, -1)[:, ok])
+    got = grad.reshape(b, c, h, w).to(dt).float()
+    # bf16 (an extension: the trainers autocast to fp16): the reference's three intermediate bf16
+    # roundings of sums of up to ~4 terms differ from one rounding by up to 2 ulp = 1.6 %
+    tol = {torch.float32: 1e-5, torch.float16: 1e-2, torch.bfloat16: 2e-2}[dt]
+    assert_close_scaled(got, T(g[f"{tag}_grad"]), tol, f"{tag} grad")
+
+
+def test_affine_restatement_vs_torchvision():
+    """oracle.affine_nearest_restated == torchvision tF.affine(nearest) bit for bit (float32 grids and
+    half grids under autocast), random parameters, square / ragged sizes."""
+    from torchvision.transforms import functional as tF
+
+    rng = np.random.RandomState(3)
+    for (h, w) in [(64, 64), (37, 53), (16, 128)]:
+        img = torch.randn(2, h, w, generator=torch.Generator().manual_seed(h))
+        for _ in range(25):
+            ang, sc = float(rng.uniform(-180, 180)), float(rng.uniform(0.5, 1.7))
+            sh = [float(rng.uniform(-30, 30)), float(rng.uniform(-30, 30))]
+            tr = [float(rng.randint(-13, 14)) / 4, float(rng.randint(-13, 14)) / 4]
+            assert torch.equal(tF.affine(img, ang, translate=tr, scale=sc, shear=sh),
+                               R.affine_nearest_restated(img, ang, tr, sc, sh))
+            for dt in (torch.float16, torch.bfloat16):
+                with torch.autocast("cpu", dtype=dt):
+                    ref = tF.affine(img.to(dt), ang, translate=tr, scale=sc, shear=sh)   # half image
+                    ref32 = tF.affine(img, ang, translate=tr, scale=sc, shear=sh)       # float32 image, half bmm
+                assert torch.equal(ref, R.affine_nearest_restated(img.to(dt), ang, tr, sc, sh, dt).float())
+                # (torchvision rounds a float32 image through the half grid's dtype before sampling)
+                assert torch.equal(ref32, R.affine_nearest_restated(img.to(dt).float(), ang, tr, sc, sh, dt))
+
+
+def test_occlusion(golden):
+    g = golden("rewarp")
+    ratio, rate, size, image = g["occ_args"]
+    rng = np.random.RandomState(int(g["occ_seed"]))
+    out = R.occlude_keypoints(T(g["occ_in"]), T(g["occ_conf_table"]), g["occ_pred_position"], aug_of(g["occ_aug"]),
+                              float(ratio), float(rate), int(size), int(image), rng=rng)
+    assert torch.equal(out, T(g["occ_out"]))

@@ -17,6 +17,7 @@ Fractions are of the measured copy peak (MEASURED_PEAKS.json) and of the 8 TB/s 
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import sys
 from pathlib import Path
@@ -269,6 +270,32 @@ def main():
         bench("loss_step (analytic teacher)", shape, 2 * (2 * hm16) + hm32, lambda r: mk_step(r, True), "loss")
         bench("gauss_target", shape, hm32 + 24 * planes, mk_gt, "target")
         bench("labelmap", shape, hm32 + 12 * planes, mk_lm, "target")
+        # re-warp (three tF.affine stages composed): teacher fp32 forward, student fp16 forward + backward
+        from uda_poseestimation_b200 import rewarp as RW
+        t32 = RW.stage_table(RW.recon_stages(S.aug_params(b, seed=5), 4.0, b), 64, 64, torch.float32, None)[0].to(dev)
+        t16 = RW.stage_table(RW.recon_stages(S.aug_params(b, seed=6), 4.0, b), 64, 64, torch.float16, torch.float16)[0].to(dev)
+        in_arr = lambda t: (ctypes.c_void_p * 1)(t.data_ptr())  # noqa: E731
+
+        def mk_rw32(r):
+            d = B(r)
+            ia, ta = in_arr(d["tea"]), in_arr(t32)
+            return lambda: chk(lib.udape_rewarp_fwd(ia, ta, 1, 3, 0, _lib.F16, None, 0, None, b, k, 64, 64, _lib.F32,
+                                                    d["rect"].data_ptr(), st()))
+
+        def mk_rw16(r):
+            d = B(r)
+            ia, ta = in_arr(d["stu16"]), in_arr(t16)
+            return lambda: chk(lib.udape_rewarp_fwd(ia, ta, 1, 3, 7, _lib.F16, None, 0, None, b, k, 64, 64, _lib.F16,
+                                                    d["grad16"].data_ptr(), st()))
+
+        def mk_rwb(r):
+            d = B(r)
+            return lambda: chk(lib.udape_rewarp_bwd(d["stu16"].data_ptr(), t16.data_ptr(), 3, 7, _lib.F16, b, k, 64, 64, _lib.F16,
+                                                    d["grad16"].data_ptr(), st()))
+
+        bench("rewarp_fwd f32 (teacher)", shape, 2 * hm32, mk_rw32, "rewarp")
+        bench("rewarp_fwd f16 (student)", shape, 2 * hm16, mk_rw16, "rewarp")
+        bench("rewarp_bwd f16 (student)", shape, 2 * hm16, mk_rwb, "rewarp")
         bundles.clear()
 
     # ---- per-channel clamp of the stylised images (train_human.py:276) -----------------------------------

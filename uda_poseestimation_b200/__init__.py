@@ -15,6 +15,9 @@ Reference name → module here
     lib/models/ema.py                          : ModelEMA
     lib/datasets/util.py                       : generate_target, draw_labelmap_ori
     train_human.py:376-383,427-430 (inline)    : confidence_mask, consistency_mask, teacher_targets
+    train_human.py:359-372,417-423 (inline)    : teacher_recon, student_recon (three tF.affine calls per
+                                                 sample → one gather launch, with backward)
+    train_human.py:385-412 (inline)            : occlude_keypoints;  affine_nearest = batched tF.affine
 """
 from ._lib import UdapeError, library_path, load as load_library
 from .adain import adain, adain_mix, adaptive_instance_normalization, calc_mean_std, channel_clamp
@@ -25,6 +28,7 @@ from .keypoint_detection import (accuracy, accuracy_from_counts, calc_dists, dec
                                  get_max_preds_torch, pck_counts)
 from .loss import ConsLoss, JointsMSELoss, cons_loss, fused_losses, joints_mse_loss
 from .mask import confidence_mask, consistency_mask, teacher_targets
+from .rewarp import affine_nearest, occlude_keypoints, student_recon, teacher_recon
 
 __version__ = "0.1.0"
 
@@ -37,4 +41,5 @@ __all__ = [
     "generate_target", "generate_target_batched", "draw_labelmap_ori", "draw_labelmap_batched", "rectify",
     "confidence_mask", "consistency_mask", "teacher_targets",
     "OldWeightEMA", "ModelEMA", "MultiTensorPlan",
+    "teacher_recon", "student_recon", "occlude_keypoints", "affine_nearest",
 ]

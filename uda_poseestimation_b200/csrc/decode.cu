@@ -108,14 +108,15 @@ __device__ __forceinline__ unsigned long long thread_plane_argmax(const T* __res
 // Almost every vector of a plane lies outside the (6*sigma+1)^2 window: when the vector does not
 // straddle rows and misses the window's clipped range it is zeros without any per-element work.
 template <typename T>
-__device__ __forceinline__ uint4 rectified_vector_at(int x, int y, int w, const RectGeom& geom, const GaussWindow& gw) {
+__device__ __forceinline__ uint4 rectified_vector_at(int x, int y, int w, const RectGeom& geom, const GaussWindow& gw,
+                                                     const float* __restrict__ tab) {
     constexpr int EPV = Vec16<T>::EPV;
     if (x + EPV <= w && (y < geom.y0i || y >= geom.y1i || x + EPV <= geom.x0i || x >= geom.x1i))
         return make_uint4(0u, 0u, 0u, 0u);
     float f[EPV];
 #pragma unroll
     for (int e = 0; e < EPV; ++e) {
-        f[e] = rectified_value(x, y, geom, gw);
+        f[e] = rectified_value(x, y, geom, gw, tab);
         if (++x == w) { x = 0; ++y; }
     }
     return pack16<T>(f);
@@ -129,6 +130,9 @@ decode_kernel(const T* __restrict__ hm, int hw, int w, int h, int32_t* __restric
     __shared__ unsigned long long red[32];
     const int64_t plane = blockIdx.x;
     const T* p = hm + plane * hw;
+    // one plane per CTA: tabulating the window would cost as many expf as evaluating it in place
+    // (measured: 40.7 -> 44.1 us at C5 with a per-CTA table); the persistent kernel below tabulates
+    const float* tab = nullptr;
     const unsigned long long best =
         block_max_u64<kDecThreads>(thread_plane_argmax<T, VEC>(p, hw), red);
     const uint32_t idx = arg_idx(best);
@@ -161,14 +165,14 @@ decode_kernel(const T* __restrict__ hm, int hw, int w, int h, int32_t* __restric
         int y = (threadIdx.x * EPV) / w, x = threadIdx.x * EPV - y * w;  // one division, then incremental
         const int step_y = (kDecThreads * EPV) / w, step_x = kDecThreads * EPV - step_y * w;
         for (int i = threadIdx.x; i < nvec; i += kDecThreads) {
-            stg_stream(r4 + i, rectified_vector_at<T>(x, y, w, geom, gw));
+            stg_stream(r4 + i, rectified_vector_at<T>(x, y, w, geom, gw, tab));
             x += step_x; y += step_y;
             if (x >= w) { x -= w; ++y; }
         }
     } else {
         for (int i = threadIdx.x; i < hw; i += kDecThreads) {
             const int y = i / w, x = i - y * w;
-            r[i] = from_f32<T>(rectified_value(x, y, geom, gw));
+            r[i] = from_f32<T>(rectified_value(x, y, geom, gw, tab));
         }
     }
 }
@@ -228,9 +232,11 @@ decode_tma_kernel(const T* __restrict__ hm, int64_t planes, int hw, int w, int h
     constexpr int EPV = Vec16<T>::EPV;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ PipeBarriers bars;
+    __shared__ float s_tab[kWinTabN * kWinTabN];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nvec = hw / EPV;
     const uint32_t plane_bytes = 16u * nvec, stage_bytes = plane_bytes * group;
+    const float* tab = rect ? build_window_table(s_tab, gw) : nullptr;  // published by pipe_init's barrier
     pipe_init(bars, stages);
     const int n_items = pipe_items((planes + group - 1) / group);
     if (warp == static_cast<int>(blockDim.x >> 5) - 1) {
@@ -286,7 +292,7 @@ decode_tma_kernel(const T* __restrict__ hm, int64_t planes, int hw, int w, int h
                     uint4* r4 = reinterpret_cast<uint4*>(rect + plane * hw);
                     int y = (lane * EPV) / w, x = lane * EPV - y * w;  // one division per plane, then incremental
                     for (int v = lane; v < nvec; v += 32) {
-                        stg_stream(r4 + v, rectified_vector_at<T>(x, y, w, geom, gw));
+                        stg_stream(r4 + v, rectified_vector_at<T>(x, y, w, geom, gw, tab));
                         x += 32 * EPV;
                         while (x >= w) { x -= w; ++y; }
                     }

@@ -256,6 +256,63 @@ cons_bwd_kernel(const TS* __restrict__ stu, const TT* __restrict__ tea,
 }
 
 
+// Consistency plane of the fused step when the rectified teacher map is NOT materialised: only the
+// student heatmap is read (128-bit vectors of the student dtype) and its gradient written; the
+// teacher value is zero for almost every vector and a shared-memory table lookup inside the
+// (6*sigma+1)^2 window around the decoded arg-max.  Returns the thread's sum of (s - t)^2.
+template <typename TS, typename TT, int THREADS>
+__device__ __forceinline__ float cons_plane_analytic(const TS* __restrict__ s, TS* __restrict__ gout, int hw, int w,
+                                                     const RectGeom& geom, const GaussWindow& gw,
+                                                     const float* __restrict__ tab, float coef) {
+    constexpr int G = 16 / static_cast<int>(sizeof(TS));
+    const int ngrp = hw / G;
+    int y = (threadIdx.x * G) / w, x = threadIdx.x * G - y * w;  // one division, then incremental
+    const int step_y = (THREADS * G) / w, step_x = THREADS * G - step_y * w;
+    float acc = 0.0f;
+    for (int base = 0; base < ngrp; base += kLossUnroll * THREADS) {
+        Pack<TS, G> gs_[kLossUnroll];
+#pragma unroll
+        for (int u = 0; u < kLossUnroll; ++u) {
+            const int gi = base + u * THREADS + threadIdx.x;
+            if (gi < ngrp) gs_[u].load(s + G * gi);
+        }
+#pragma unroll
+        for (int u = 0; u < kLossUnroll; ++u) {
+            const int gi = base + u * THREADS + threadIdx.x;
+            if (gi < ngrp) {
+                float fs[G];
+                gs_[u].get(fs);
+                float tsum = 0.0f;
+                if (x + G <= w && (y < geom.y0i || y >= geom.y1i || x + G <= geom.x0i || x >= geom.x1i)) {
+                    // the group misses the window: the teacher map is zero here
+#pragma unroll
+                    for (int e = 0; e < G; ++e) {
+                        tsum = fmaf(fs[e], fs[e], tsum);
+                        fs[e] = coef * fs[e];
+                    }
+                } else {
+                    int xx = x, yy = y;
+#pragma unroll
+                    for (int e = 0; e < G; ++e) {
+                        // rounded through the teacher map's dtype, like the materialised map
+                        const float tv = to_f32<TT>(from_f32<TT>(rectified_value(xx, yy, geom, gw, tab)));
+                        if (++xx == w) { xx = 0; ++yy; }
+                        const float d = fs[e] - tv;
+                        tsum = fmaf(d, d, tsum);
+                        fs[e] = coef * d;
+                    }
+                }
+                acc += tsum;
+                if (gout) Pack<TS, G>::store(gout + G * gi, fs);
+                x += step_x; y += step_y;
+                if (x >= w) { x -= w; ++y; }
+            }
+        }
+    }
+    return acc;
+}
+
+
 // ---- fused loss step ------------------------------------------------------------------------
 // One launch for  loss_s = JointsMSELoss(y_s, label, weight),  loss_c = ConsLoss(y_t_stu, tea,
 // tea_mask),  loss_all = loss_s + lambda_c*loss_c  AND the gradients of  grad_scale*loss_all
@@ -283,8 +340,14 @@ loss_step_kernel(const TS* __restrict__ y_s, const TT* __restrict__ label, const
                  const TT* __restrict__ tea, TS* __restrict__ grad_s, TS* __restrict__ grad_t,
                  const LossStepArgs a) {
     __shared__ float red[32];
+    __shared__ float s_tab[kWinTabN * kWinTabN];
     const int hw = a.hw;
     const bool sup = static_cast<int>(blockIdx.x) < a.planes_s;
+    const float* tab = nullptr;
+    if (!sup && tea == nullptr) {  // CTA-uniform: the window table of the analytic teacher map
+        tab = build_window_table(s_tab, a.gw);
+        __syncthreads();
+    }
     const int64_t plane = sup ? blockIdx.x : blockIdx.x - a.planes_s;
     const float g = a.grad_scale_dev ? __ldg(a.grad_scale_dev) : a.grad_scale;
     const TS* s;
@@ -314,12 +377,11 @@ loss_step_kernel(const TS* __restrict__ y_s, const TT* __restrict__ label, const
         if (analytic) geom = rect_geometry(a.tea_preds[2 * plane], a.tea_preds[2 * plane + 1], a.h, a.w, a.gw);
     }
     float acc = 0.0f;
-    if (VEC) {
+    if (VEC && analytic) {
+        acc = cons_plane_analytic<TS, TT, kStepThreads>(s, gout, hw, a.w, geom, a.gw, tab, coef);
+    } else if (VEC) {
         constexpr int G = PairGroup<TS, TT>::G;
         const int ngrp = hw / G;
-        // analytic route: position of this thread's first group (one division), then incremental
-        int y = (threadIdx.x * G) / a.w, x = threadIdx.x * G - y * a.w;
-        const int step_y = (kStepThreads * G) / a.w, step_x = kStepThreads * G - step_y * a.w;
         for (int base = 0; base < ngrp; base += kLossUnroll * kStepThreads) {
             Pack<TS, G> gs_[kLossUnroll];
             Pack<TT, G> gt_[kLossUnroll];
@@ -328,7 +390,7 @@ loss_step_kernel(const TS* __restrict__ y_s, const TT* __restrict__ label, const
                 const int gi = base + u * kStepThreads + threadIdx.x;
                 if (gi < ngrp) {
                     gs_[u].load(s + G * gi);
-                    if (!analytic) gt_[u].load(t + G * gi);
+                    gt_[u].load(t + G * gi);
                 }
             }
 #pragma unroll
@@ -337,25 +399,7 @@ loss_step_kernel(const TS* __restrict__ y_s, const TT* __restrict__ label, const
                 if (gi < ngrp) {
                     float fs[G], ft[G];
                     gs_[u].get(fs);
-                    if (!analytic) {
-                        gt_[u].get(ft);
-                    } else {
-                        if (x + G <= a.w && (y < geom.y0i || y >= geom.y1i || x + G <= geom.x0i || x >= geom.x1i)) {
-                            // the group misses the (6*sigma+1)^2 window: zeros, no per-element work
-#pragma unroll
-                            for (int e = 0; e < G; ++e) ft[e] = 0.0f;
-                        } else {
-                            int xx = x, yy = y;
-#pragma unroll
-                            for (int e = 0; e < G; ++e) {
-                                // rounded through the teacher map's dtype, like the materialised map
-                                ft[e] = to_f32<TT>(from_f32<TT>(rectified_value(xx, yy, geom, a.gw)));
-                                if (++xx == a.w) { xx = 0; ++yy; }
-                            }
-                        }
-                        x += step_x; y += step_y;
-                        if (x >= a.w) { x -= a.w; ++y; }
-                    }
+                    gt_[u].get(ft);
                     float tsum = 0.0f;
 #pragma unroll
                     for (int e = 0; e < G; ++e) {
@@ -374,7 +418,7 @@ loss_step_kernel(const TS* __restrict__ y_s, const TT* __restrict__ label, const
             if (!analytic) tv = to_f32<TT>(t[i]);
             else {
                 const int y = i / a.w, x = i - y * a.w;
-                tv = to_f32<TT>(from_f32<TT>(rectified_value(x, y, geom, a.gw)));
+                tv = to_f32<TT>(from_f32<TT>(rectified_value(x, y, geom, a.gw, tab)));
             }
             const float d = to_f32<TS>(s[i]) - tv;
             acc = fmaf(d, d, acc);

@@ -63,6 +63,24 @@ def keypoints(b: int, k: int, seed: int, image: int = 256):
     return joints, vis
 
 
+def aug_params(b: int, seed: int, image: int = 256, degrees: float = 180.0, shear=(-30.0, 30.0),
+               translate=(0.05, 0.05), scale=(0.6, 1.3), shear_y: bool = False):
+    """The collated ``meta['aug_param_*']`` of one batch: ``[angle[b], [trans_x[b], trans_y[b]],
+    [shear_x[b], shear_y[b]], scale[b]]`` (float64 / int64 tensors, as the DataLoader collates the
+    Python floats / ints of lib/transforms/keypoint_detection.py:139), drawn like
+    ``RandomAffineRotation.get_params`` (:397-412) with the trainers' default ranges
+    (train_human.py:535-557) and inverted like ``affine()`` (:139)."""
+    rng = np.random.RandomState(int(seed))
+    angle = rng.uniform(-degrees, degrees, size=b)
+    shx = rng.uniform(shear[0], shear[1], size=b)
+    shy = rng.uniform(shear[0], shear[1], size=b) if shear_y else np.zeros(b)
+    tx = np.round(rng.uniform(-translate[0] * image, translate[0] * image, size=b)).astype(np.int64)
+    ty = np.round(rng.uniform(-translate[1] * image, translate[1] * image, size=b)).astype(np.int64)
+    sc = rng.uniform(scale[0], scale[1], size=b)
+    t = torch.from_numpy
+    return [t(-angle), [t(-tx), t(-ty)], [t(-shx), t(-shy)], t(1.0 / sc)]
+
+
 def adversarial_heatmaps(k: int = 4, h: int = 64, w: int = 64, seed: int = 7) -> torch.Tensor:
     """[10,k,h,w] fp32 planes that stress exact arg-max semantics: duplicated maxima (first index
     must win), all-zero, all-negative, NaN (NaN is the maximum, first NaN wins), +/-inf, -0.0/+0.0
