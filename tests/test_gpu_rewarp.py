@@ -182,3 +182,56 @@ def test_rewarp_argument_errors(dev):
     big = torch.randn(1, 1, 256, 256, device=dev, requires_grad=True)
     with pytest.raises(ValueError):                      # backward keeps the inverted map in shared memory
         RW.gather(big, torch.zeros(1, 1, 6, device=dev)).sum().backward()
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16, torch.bfloat16])
+def test_rewarp_routes_agree(dev, dt, monkeypatch):
+    """The shared-memory staged route and the global-gather route are the same function: identical
+    bits forward (1 and 3 views) and backward, including a plane smaller than one pass of the CTA."""
+    for (b, k, h, w) in [(5, 7, 64, 64), (3, 2, 32, 32), (2, 3, 24, 40)]:
+        ys = [(torch.randn(b, k, h, w, device=dev) * 3).to(dt) for _ in range(3)]
+        augs = [S.aug_params(b, seed=50 + i, shear_y=True) for i in range(3)]
+        ac = None if dt == torch.float32 else dt
+        tabs = [RW.stage_table(RW.recon_stages(a_, 4.0, b), h, w, dt, ac) for a_ in augs]
+        thetas = [t[0].to(dev) for t in tabs]
+        half_mask, code = tabs[0][1], tabs[0][2]
+        g = (torch.randn(b, k, h, w, device=dev)).to(dt)
+        res = {}
+        for route in ("smem", "global"):
+            if route == "global":
+                monkeypatch.setenv("UDAPE_REWARP_GLOBAL", "1")
+            else:
+                monkeypatch.delenv("UDAPE_REWARP_GLOBAL", raising=False)
+            one = RW._launch_fwd([ys[0]], [thetas[0]], half_mask, code, torch.empty_like(ys[0]))
+            three = RW._launch_fwd(ys, thetas, half_mask, code, torch.empty_like(ys[0]))
+            x = ys[0].clone().requires_grad_(True)
+            RW._Rewarp.apply(x, thetas[0], half_mask, code).backward(g)
+            res[route] = (one, three, x.grad)
+        monkeypatch.delenv("UDAPE_REWARP_GLOBAL", raising=False)
+        for r_s, r_g in zip(res["smem"], res["global"]):
+            assert torch.equal(r_s, r_g), (b, k, h, w)
+
+
+def test_rewarp_backward_long_lists(dev):
+    """Zoom factors above ~1.7 give source pixels with more than four contributors (the backward kernel
+    keeps four in registers and loops over the rest): checked against autograd through torchvision."""
+    b, k = 4, 3
+    aug = [torch.tensor([10.0, -35.0, 80.0, 0.0], dtype=torch.float64),
+           [torch.tensor([3, -5, 0, 8]), torch.tensor([-2, 7, 0, 1])],
+           [torch.tensor([5.0, 0.0, -12.0, 0.0], dtype=torch.float64), torch.zeros(4, dtype=torch.float64)],
+           torch.tensor([2.9, 2.2, 3.5, 1.0], dtype=torch.float64)]
+    for dt, tol in ((torch.float32, 1e-5), (torch.float16, 1e-2)):
+        x = S.heatmaps(b, k, seed=61).to(dt)
+        G = torch.randn(b, k, 64, 64, generator=torch.Generator().manual_seed(62)).to(dt)
+        ac = None if dt == torch.float32 else dt
+        y = x.to(dev).requires_grad_(True)
+        out = U.student_recon(y, aug, 4.0, autocast=ac)
+        out.backward(G.to(dev))
+        y_ref = x.clone().requires_grad_(True)
+        ref = R.student_recon(y_ref, aug, 4.0)
+        ref.backward(G)
+        assert torch.equal(out.detach().cpu(), ref.detach())
+        assert_close_scaled(y.grad.float(), y_ref.grad.float(), tol, f"long-list grad {dt}")
+        # more than four output pixels really do share a source pixel here
+        src = R.recon_source_index(10.0, 3, -2, 5.0, 0.0, 2.9, 4.0, 64, 64, dt, ac)
+        assert np.bincount(src[src >= 0]).max() > 4

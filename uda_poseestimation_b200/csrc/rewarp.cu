@@ -18,14 +18,31 @@
 //   ix = ((g + 1) * W - 1) / 2 ; nearest = rint(ix) (ties to even) ; valid iff 0 <= nearest <= W-1
 //
 // The source index of a pixel depends only on the sample, not on the channel: every thread
-// computes the composed index of its PX consecutive pixels once (registers) and then loops over
-// the channels of its CTA — gathers from the L1/L2-resident source plane, 128-bit coalesced
-// streaming stores.  HBM-bound: one read and one write of the tensor.
+// computes the composed index of its pixels once (16-bit offsets packed in registers) and then
+// loops over the channels of its CTA.  HBM-bound: one read and one write of the tensor.
+//
+//   heatmap route (rewarp_smem_kernel, planes up to 4096 px fp32 / 8192 px half): a warp-wide
+//     gather along a rotated line touches up to 32 different L1 lines, so gathering from global
+//     memory is bound by L1 wavefronts, not by HBM.  Instead the source plane is staged into
+//     shared memory with coalesced 128-bit loads (register double buffering: the next plane's loads
+//     are in flight while the current one is gathered), rows padded to a stride of +-4 (mod 32)
+//     banks — the sign is chosen per sample from the composed map's direction so that the 32 lanes
+//     of a gather (consecutive output pixels) spread over the banks for every rotation angle —
+//     and consecutive lanes write consecutive pixels (128-byte coalesced stores).
+//   general route (rewarp_fwd_kernel): gathers straight from global memory; used for image-sized
+//     planes (occlusion, 3x256x256), ragged widths and the paste / pass-through options.
 //
 // Backward (student recon): grad_in[s] = sum of grad_out[p] over {p : src(p) = s}.  No float
 // atomics: the CTA inverts the composed map in shared memory (integer counting sort, lists sorted
 // by p) once per sample and every channel then sums its list in ascending p — deterministic.
+// The gradient plane is staged through the same padded shared-memory buffers.
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace udape {
 
@@ -64,23 +81,46 @@ __device__ __forceinline__ bool stage_source(int& i, int& j, const float* __rest
     float gx = __fadd_rn(__fmaf_rn(y, r[1], __fmul_rn(x, r[0])), r[2]);
     float gy = __fadd_rn(__fmaf_rn(y, r[4], __fmul_rn(x, r[3])), r[5]);
     if (half) { gx = round_grid(gx, grid_dtype); gy = round_grid(gy, grid_dtype); }
-    // grid_sampler_unnormalize (align_corners=False) and nearbyint
-    const float fx = rintf(__fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), static_cast<float>(W)), 1.0f), 0.5f));
-    const float fy = rintf(__fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), static_cast<float>(H)), 1.0f), 0.5f));
-    if (!(fx >= 0.0f && fx <= static_cast<float>(W - 1) && fy >= 0.0f && fy <= static_cast<float>(H - 1))) return false;
-    i = static_cast<int>(fx);
-    j = static_cast<int>(fy);
+    // grid_sampler_unnormalize (align_corners=False), then nearbyint: F2I.RN rounds ties to even like
+    // rint and saturates, so the range test on the integers equals ATen's test on the rounded floats
+    const float fx = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), static_cast<float>(W)), 1.0f), 0.5f);
+    const float fy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), static_cast<float>(H)), 1.0f), 0.5f);
+    const int xi = __float2int_rn(fx), yi = __float2int_rn(fy);
+    if (static_cast<unsigned>(xi) >= static_cast<unsigned>(W) || static_cast<unsigned>(yi) >= static_cast<unsigned>(H) ||
+        fx != fx || fy != fy)
+        return false;
+    i = xi;
+    j = yi;
     return true;
 }
 
-// composed source index of output pixel p of sample b through one view's stage table (-1: zero)
-__device__ __forceinline__ int composed_source(int p, int b, const float* __restrict__ theta, const RewarpArgs& a) {
+// a sample's stage table held in registers (rows beyond `stages` are never read)
+struct StageRegs { float r[kRwMaxStages][6]; };
+__device__ __forceinline__ void load_stages(StageRegs& R, const float* __restrict__ r, int stages) {
+#pragma unroll
+    for (int s = 0; s < kRwMaxStages; ++s)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) R.r[s][k] = s < stages ? r[6 * s + k] : 0.0f;
+}
+// composed source pixel of output pixel (i, j), in place (false: zero fill); stages unrolled over the
+// register table
+__device__ __forceinline__ bool composed_source_ij(int& i, int& j, const StageRegs& R, const RewarpArgs& a) {
+#pragma unroll
+    for (int s = 0; s < kRwMaxStages; ++s) {
+        if (s < a.stages) {
+            if (!stage_source(i, j, R.r[s], a.W, a.H, (a.half_mask >> s) & 1, a.grid_dtype)) return false;
+        }
+    }
+    return true;
+}
+
+// composed source index of output pixel p through one sample's stage table r[stages][6] (-1: zero).
+// q (optional) is the sample's paste record: temp[:, row0:row1, col0:col1] = temp[:, srow0:.., scol0:..]
+__device__ __forceinline__ int composed_source(int p, const float* __restrict__ r, const int32_t* __restrict__ q,
+                                               const RewarpArgs& a) {
     int j = p / a.W, i = p - j * a.W;
-    const float* r = theta + static_cast<int64_t>(b) * a.stages * 6;
     for (int s = 0; s < a.stages; ++s) {
-        if (a.paste && s == a.paste_after) {
-            // temp[:, row0:row1, col0:col1] = temp[:, srow0:.., scol0:..]   (train_human.py:409)
-            const int32_t* q = a.paste + 6 * b;
+        if (q && s == a.paste_after) {   // train_human.py:409
             if (j >= q[0] && j < q[1] && i >= q[2] && i < q[3]) { j += q[4] - q[0]; i += q[5] - q[2]; }
         }
         if (!stage_source(i, j, r + 6 * s, a.W, a.H, (a.half_mask >> s) & 1, a.grid_dtype)) return -1;
@@ -88,9 +128,12 @@ __device__ __forceinline__ int composed_source(int p, int b, const float* __rest
     return j * a.W + i;
 }
 
+// ---- general route: gather from global memory ---------------------------------------------------
 template <typename T, int PX>
 __global__ void __launch_bounds__(kRwThreads)
 rewarp_fwd_kernel(const RewarpArgs a, T* __restrict__ out) {
+    __shared__ float s_theta[kRwMaxViews][kRwMaxStages * 6];
+    __shared__ int32_t s_paste[6];
     const int hw = a.H * a.W;
     const int bands = (hw + kRwThreads * PX - 1) / (kRwThreads * PX);
     const int cgroups = (a.C + a.cpc - 1) / a.cpc;
@@ -98,6 +141,12 @@ rewarp_fwd_kernel(const RewarpArgs a, T* __restrict__ out) {
     const int band = bid % bands; bid /= bands;
     const int cg = bid % cgroups;
     const int b = bid / cgroups;
+    if (threadIdx.x < a.views * a.stages * 6) {
+        const int v = threadIdx.x / (a.stages * 6), k = threadIdx.x - v * a.stages * 6;
+        s_theta[v][k] = a.view[v].theta[static_cast<int64_t>(b) * a.stages * 6 + k];
+    }
+    if (a.paste && threadIdx.x >= 32 && threadIdx.x < 38) s_paste[threadIdx.x - 32] = a.paste[6 * b + threadIdx.x - 32];
+    __syncthreads();
     const int p0 = (band * kRwThreads + threadIdx.x) * PX;
     if (p0 >= hw) return;
     const int c0 = cg * a.cpc, c1 = min(a.C, c0 + a.cpc);
@@ -108,7 +157,8 @@ rewarp_fwd_kernel(const RewarpArgs a, T* __restrict__ out) {
         if (v < a.views) {
 #pragma unroll
             for (int e = 0; e < PX; ++e)
-                src[v][e] = through ? p0 + e : (p0 + e < hw ? composed_source(p0 + e, b, a.view[v].theta, a) : -1);
+                src[v][e] = through ? p0 + e
+                                    : (p0 + e < hw ? composed_source(p0 + e, s_theta[v], a.paste ? s_paste : nullptr, a) : -1);
         }
     }
     const float nviews = static_cast<float>(a.views);
@@ -141,38 +191,270 @@ rewarp_fwd_kernel(const RewarpArgs a, T* __restrict__ out) {
     }
 }
 
-// ---- backward --------------------------------------------------------------------------------
-// shared memory: uint32 off[hw + 1] | uint16 map[hw] | uint16 lst[hw]
+// ---- heatmap route: planes staged through padded shared memory -----------------------------------
+constexpr int kRwPix = 16;               // pixels per thread and plane: planes up to 256*16 = 4096 px
+constexpr int kRwMaxVec = 4;             // 16-byte staging copies per thread and plane
+constexpr int kRwRing = 3;               // plane buffers per CTA: two planes in flight behind the one being gathered
+constexpr int kRwBufBytes = 32 * 1024;   // padded plane budget per buffer
+
+// smallest row stride (32-bit words) >= words with stride % 32 == rem (rem % 4 == 0: 16-byte aligned rows)
+__host__ __device__ inline int padded_stride(int words, int rem) {
+    const int s = ((words - rem + 31) / 32) * 32 + rem;
+    return s >= words ? s : s + 32;
+}
+
+// Jacobian of the composed output->source pixel map (evaluation order), from the rescaled thetas
+__device__ __forceinline__ void composed_jacobian(const float* __restrict__ r, const RewarpArgs& a, float J[4]) {
+    J[0] = 1.0f; J[1] = 0.0f; J[2] = 0.0f; J[3] = 1.0f;
+    const float hx = 0.5f * a.W, hy = 0.5f * a.H;
+    for (int s = 0; s < a.stages; ++s) {
+        const float m0 = r[6 * s] * hx, m1 = r[6 * s + 1] * hx, m2 = r[6 * s + 3] * hy, m3 = r[6 * s + 4] * hy;
+        const float n0 = m0 * J[0] + m1 * J[2], n1 = m0 * J[1] + m1 * J[3];
+        const float n2 = m2 * J[0] + m3 * J[2], n3 = m2 * J[1] + m3 * J[3];
+        J[0] = n0; J[1] = n1; J[2] = n2; J[3] = n3;
+    }
+}
+
+// Row padding of the staged plane.  The 32 lanes of a gather read consecutive pixels, i.e. they walk
+// the source plane in steps of (dcol, drow) elements; with a row stride of S words lane l lands in
+// bank (l*dcol/EPW + S*l*drow) mod 32.  No single 16-byte-aligned stride is good for every direction
+// (S = 4 mod 32 puts the whole warp into one bank when dcol = -4 drow), so every warp plays the walk
+// for two candidates (S = 4 and S = 12 mod 32) and keeps the one with the lower conflict degree:
+// average 2-way, worst 5-way over all rotations and scales, against 8-9-way for a fixed stride.
+// Deterministic in (dcol, drow): all CTAs of a cluster agree.
+__device__ __forceinline__ int pick_stride(int row_words, float dcol, float drow, int epw_log2) {
+    const int lane = threadIdx.x & 31;
+    const int px = __float2int_rn(static_cast<float>(lane << epw_log2) * dcol) >> epw_log2;
+    const int py = __float2int_rn(static_cast<float>(lane << epw_log2) * drow);
+    const int sa = padded_stride(row_words, 4), sb = padded_stride(row_words, 12);
+    const int da = __reduce_max_sync(0xffffffffu, __popc(__match_any_sync(0xffffffffu, (py * sa + px) & 31)));
+    const int db = __reduce_max_sync(0xffffffffu, __popc(__match_any_sync(0xffffffffu, (py * sb + px) & 31)));
+    return da <= db ? sa : sb;
+}
+
+// asynchronous 16-byte global -> shared copies (LDGSTS, L2 only) and their group fences
+__device__ __forceinline__ void cp_async16(uint32_t smem_byte_addr, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_byte_addr), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// padded byte offset of each of the thread's 16-byte vectors (-1: none), computed once per CTA
+__device__ __forceinline__ void stage_offsets(int (&so)[kRwMaxVec], int nvec, int vpr, int stride) {
+#pragma unroll
+    for (int q = 0; q < kRwMaxVec; ++q) {
+        const int v = q * kRwThreads + threadIdx.x;
+        const int row = v / vpr;
+        so[q] = v < nvec ? (row * stride + 4 * (v - row * vpr)) * 4 : -1;
+    }
+}
+// one plane, global -> padded shared buffer: coalesced, no registers, completion through the group fence
 template <typename T>
+__device__ __forceinline__ void stage_issue(uint32_t buf_addr, const int (&so)[kRwMaxVec], const T* __restrict__ plane) {
+    const uint4* src = reinterpret_cast<const uint4*>(plane) + threadIdx.x;
+#pragma unroll
+    for (int q = 0; q < kRwMaxVec; ++q)
+        if (so[q] >= 0) cp_async16(buf_addr + so[q], src + q * kRwThreads);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// thread t owns the 32-bit words t + 256*slot of every plane (1 fp32 or 2 halves per word):
+// consecutive lanes, consecutive pixels -> spread gathers, 128-byte coalesced stores
+template <typename T> __device__ __forceinline__ void store_word(T* __restrict__ out, int word, const float* f);
+template <> __device__ __forceinline__ void store_word<float>(float* __restrict__ out, int word, const float* f) {
+    out[word] = f[0];
+}
+template <> __device__ __forceinline__ void store_word<__half>(__half* __restrict__ out, int word, const float* f) {
+    reinterpret_cast<__half2*>(out)[word] = __floats2half2_rn(f[0], f[1]);
+}
+template <> __device__ __forceinline__ void store_word<__nv_bfloat16>(__nv_bfloat16* __restrict__ out, int word,
+                                                                      const float* f) {
+    reinterpret_cast<__nv_bfloat162*>(out)[word] = __floats2bfloat162_rn(f[0], f[1]);
+}
+
+__device__ __forceinline__ int ceil_log2(int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return l;
+}
+
+// Every CTA of the cluster owns the slice [rank << slice_log2, (rank+1) << slice_log2) of a uint16 array
+// that is laid out identically in all CTAs: pull the peers' slices through distributed shared memory
+// with 128-bit loads (scalar 16-bit DSMEM loads cost ~2 us per 4096 on B200).  n % 8 == 0, slices >= 8.
+__device__ __forceinline__ void pull_slices(cg::cluster_group& cluster, uint16_t* arr, int n, int slice_log2, int rank) {
+    for (int vec = threadIdx.x; vec < n / 8; vec += kRwThreads) {
+        const int p = vec * 8, owner = p >> slice_log2;
+        if (owner != rank)
+            reinterpret_cast<uint4*>(arr)[vec] = *reinterpret_cast<const uint4*>(cluster.map_shared_rank(arr + p, owner));
+    }
+}
+
+// The composed map of a sample is shared by all of its channels.  The CTAs that split a sample's
+// channels form a thread-block CLUSTER: each computes 1/n-th of the map into its own shared memory,
+// and after one cluster barrier every CTA reads the offsets of its pixels from its peers through
+// distributed shared memory — the index arithmetic is done once per sample, not once per CTA.
+// dynamic smem: kRwRing padded plane buffers | uint16 map[VIEWS][hw]
+template <typename T, int VIEWS>
 __global__ void __launch_bounds__(kRwThreads)
-rewarp_bwd_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __restrict__ gin) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    const int hw = a.H * a.W;
-    uint32_t* off = reinterpret_cast<uint32_t*>(smem_raw);
-    uint16_t* map = reinterpret_cast<uint16_t*>(off + hw + 1 + ((hw + 1) & 1));
-    uint16_t* lst = map + hw;
-    __shared__ uint32_t s_scan[kRwThreads];
-    const int cgroups = (a.C + a.cpc - 1) / a.cpc;
-    const int cg = blockIdx.x % cgroups, b = blockIdx.x / cgroups;
-    const int c0 = cg * a.cpc, c1 = min(a.C, c0 + a.cpc);
-    // 1. composed map and per-source counts (integer atomics: order-independent)
-    for (int s = threadIdx.x; s <= hw; s += kRwThreads) off[s] = 0u;
+rewarp_smem_kernel(const RewarpArgs a, T* __restrict__ out, int buf_words) {
+    constexpr int EPW = 4 / static_cast<int>(sizeof(T));  // elements per 32-bit word
+    constexpr int SLOTS = kRwPix / EPW;                    // words per thread and plane
+    extern __shared__ __align__(16) uint32_t rw_smem[];
+    __shared__ float s_theta[VIEWS][kRwMaxStages * 6];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int nrank = static_cast<int>(cluster.num_blocks()), rank = static_cast<int>(cluster.block_rank());
+    const int hw = a.H * a.W, nwords = hw / EPW;
+    const int b = blockIdx.x / nrank;                      // one cluster per sample
+    const int c0 = min(a.C, rank * a.cpc), c1 = min(a.C, c0 + a.cpc);
+    uint16_t* s_map = reinterpret_cast<uint16_t*>(rw_smem + kRwRing * buf_words);
+    if (threadIdx.x < VIEWS * a.stages * 6) {
+        const int v = threadIdx.x / (a.stages * 6), k = threadIdx.x - v * a.stages * 6;
+        s_theta[v][k] = a.view[v].theta[static_cast<int64_t>(b) * a.stages * 6 + k];
+    }
+    // the word behind every padded plane stays zero: out-of-bounds pixels gather from it (no select)
+    const uint32_t zero_byte = static_cast<uint32_t>(buf_words - 4) * 4u;
+    if (threadIdx.x < kRwRing) rw_smem[threadIdx.x * buf_words + buf_words - 4] = 0u;
     __syncthreads();
+    const int row_words = a.W / EPW, vpr = row_words / 4, nvec = nwords / 4;
+    int stride[VIEWS], so[VIEWS][kRwMaxVec];
+#pragma unroll
+    for (int v = 0; v < VIEWS; ++v) {
+        float J[4];
+        composed_jacobian(s_theta[v], a, J);
+        stride[v] = pick_stride(row_words, J[0], J[2], EPW - 1);  // one output column = (J[0], J[2]) in the source
+        stage_offsets(so[v], nvec, vpr, stride[v]);
+    }
+    auto issue = [&](int it) {   // item = (channel, view)
+        const int c = c0 + it / VIEWS, v = it - (it / VIEWS) * VIEWS;
+        const T* plane = static_cast<const T*>(a.view[v].in) + (static_cast<int64_t>(b) * a.C + c) * hw;
+        const uint32_t dst = smem_u32(rw_smem + (it % kRwRing) * buf_words);
+        if (VIEWS == 1) { stage_issue<T>(dst, so[0], plane); return; }
+#pragma unroll
+        for (int u = 0; u < VIEWS; ++u)
+            if (u == v) stage_issue<T>(dst, so[u], plane);
+    };
+    const int nitems = (c1 - c0) * VIEWS;
+#pragma unroll
+    for (int it = 0; it < kRwRing - 1; ++it) {   // in flight while the map is built
+        if (it < nitems) issue(it);
+        cp_async_commit();
+    }
+    // this CTA's slice of the map: BYTE offsets into the padded plane, 16 bits each
+    const int slice_log2 = ceil_log2((hw + nrank - 1) / nrank);
+    {
+        const int p_first = (rank << slice_log2) + threadIdx.x, p_end = min(hw, (rank + 1) << slice_log2);
+        const int dj = kRwThreads / a.W, di = kRwThreads - dj * a.W;
+#pragma unroll
+        for (int v = 0; v < VIEWS; ++v) {
+            StageRegs R;
+            load_stages(R, s_theta[v], a.stages);
+            int j0 = p_first / a.W, i0 = p_first - j0 * a.W;
+            for (int p = p_first; p < p_end; p += kRwThreads) {
+                int i = i0, j = j0;
+                uint32_t o = zero_byte;
+                if (composed_source_ij(i, j, R, a)) o = static_cast<uint32_t>(j * stride[v] * 4 + i * static_cast<int>(sizeof(T)));
+                s_map[v * hw + p] = static_cast<uint16_t>(o);
+                i0 += di; j0 += dj;
+                if (i0 >= a.W) { i0 -= a.W; ++j0; }
+            }
+        }
+    }
+    cluster.sync();
+#pragma unroll
+    for (int v = 0; v < VIEWS; ++v) pull_slices(cluster, s_map + v * hw, hw, slice_log2, rank);
+    cluster.sync();   // nobody leaves (or reuses its slice) while a peer is still reading it; also a CTA barrier
+    // offsets of this thread's pixels, two per register
+    uint32_t idx[VIEWS][kRwPix / 2];
+#pragma unroll
+    for (int v = 0; v < VIEWS; ++v) {
+#pragma unroll
+        for (int k = 0; k < kRwPix; ++k) {
+            // pixel k of this thread: word (k / EPW) * 256 + t, element k % EPW of that word
+            const int word = (k / EPW) * kRwThreads + threadIdx.x;
+            const uint32_t o = word < nwords ? s_map[v * hw + word * EPW + (k % EPW)] : zero_byte;
+            if (k & 1) idx[v][k >> 1] |= o << 16;
+            else idx[v][k >> 1] = o;
+        }
+    }
+    for (int c = c0; c < c1; ++c) {
+        uint32_t* o32 = reinterpret_cast<uint32_t*>(out + (static_cast<int64_t>(b) * a.C + c) * hw) + threadIdx.x;
+        float acc[VIEWS == 1 ? 1 : kRwPix];
+#pragma unroll
+        for (int v = 0; v < VIEWS; ++v) {
+            const int it = (c - c0) * VIEWS + v;
+            cp_async_wait<kRwRing - 2>();   // this thread's copies of item `it` have landed ...
+            __syncthreads();                // ... everybody's have, and everybody is done with item it-1
+            if (it + kRwRing - 1 < nitems) issue(it + kRwRing - 1);   // refills the buffer of item it-1
+            cp_async_commit();
+            const uint8_t* bytes = reinterpret_cast<const uint8_t*>(rw_smem + (it % kRwRing) * buf_words);
+            if constexpr (VIEWS == 1) {
+                // single view: the values are moved, never converted
+#pragma unroll
+                for (int sl = 0; sl < SLOTS; ++sl) {
+                    uint32_t w32;
+                    if constexpr (EPW == 1) {
+                        const uint32_t o = (idx[0][sl >> 1] >> (16 * (sl & 1))) & 0xffffu;
+                        w32 = *reinterpret_cast<const uint32_t*>(bytes + o);
+                    } else {
+                        const uint32_t lo = *reinterpret_cast<const uint16_t*>(bytes + (idx[0][sl] & 0xffffu));
+                        const uint32_t hi = *reinterpret_cast<const uint16_t*>(bytes + (idx[0][sl] >> 16));
+                        w32 = lo | (hi << 16);
+                    }
+                    if (sl * kRwThreads + static_cast<int>(threadIdx.x) < nwords) o32[sl * kRwThreads] = w32;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kRwPix; ++k) {
+                    const uint32_t o = (idx[v][k >> 1] >> (16 * (k & 1))) & 0xffffu;
+                    const float val = to_f32<T>(*reinterpret_cast<const T*>(bytes + o));
+                    acc[k] = v == 0 ? val : acc[k] + val;  // torch.mean over the k views: sequential sum ...
+                }
+            }
+        }
+        if constexpr (VIEWS > 1) {
+            const float nviews = static_cast<float>(VIEWS);
+#pragma unroll
+            for (int sl = 0; sl < SLOTS; ++sl) {
+                float f[EPW];
+#pragma unroll
+                for (int e = 0; e < EPW; ++e) f[e] = __fdiv_rn(acc[sl * EPW + e], nviews);  // ... one division (CPU mean)
+                if (sl * kRwThreads + static_cast<int>(threadIdx.x) < nwords)
+                    store_word<T>(reinterpret_cast<T*>(o32 - threadIdx.x), sl * kRwThreads + threadIdx.x, f);
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// ---- backward ------------------------------------------------------------------------------------
+// Inverts the composed map of one sample (map[p] = source pixel of output pixel p) in shared memory:
+// off[s] = end of the list of source pixel s (start = off[s-1]),  lst[] = the output pixels of every
+// list in ascending order, stored as `code(p)`.  Integer atomics only (16-bit counters packed two per
+// word), so the result is independent of scheduling.  Call from all threads.
+template <typename Code>
+__device__ __forceinline__ void invert_map(const uint16_t* map, int hw, int s_lo, int s_hi, uint16_t* off, uint16_t* lst,
+                                           uint32_t* s_scan, Code code) {
+    // only the source pixels [s_lo, s_hi) are inverted (a cluster splits the range); off[] is indexed by
+    // s - s_lo and must be zero on entry (barrier passed)
+    const int ns = s_hi - s_lo;
+    uint32_t* off32 = reinterpret_cast<uint32_t*>(off);
+    // 1. per-source counts
     for (int p = threadIdx.x; p < hw; p += kRwThreads) {
-        const int s = composed_source(p, b, a.view[0].theta, a);
-        map[p] = s < 0 ? 0xffffu : static_cast<uint16_t>(s);
-        if (s >= 0) atomicAdd(&off[s], 1u);
+        const int s = static_cast<int>(map[p]) - s_lo;
+        if (s >= 0 && s < ns) atomicAdd(&off32[s >> 1], 1u << (16 * (s & 1)));
     }
     __syncthreads();
     // 2. exclusive scan of the counts (each thread owns a contiguous run)
-    const int per = (hw + kRwThreads - 1) / kRwThreads;
-    const int lo = min(hw, static_cast<int>(threadIdx.x) * per), hi = min(hw, lo + per);
+    const int per = (ns + kRwThreads - 1) / kRwThreads;
+    const int lo = min(ns, static_cast<int>(threadIdx.x) * per), hi = min(ns, lo + per);
     uint32_t run = 0;
     for (int s = lo; s < hi; ++s) run += off[s];
     s_scan[threadIdx.x] = run;
     __syncthreads();
     if (threadIdx.x < 32) {
-        // 256 partials: 8 per lane, warp scan
         uint32_t part[kRwThreads / 32], tot = 0;
 #pragma unroll
         for (int q = 0; q < kRwThreads / 32; ++q) { part[q] = tot; tot += s_scan[threadIdx.x * (kRwThreads / 32) + q]; }
@@ -188,31 +470,237 @@ rewarp_bwd_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __restrict_
     }
     __syncthreads();
     run = s_scan[threadIdx.x];
-    for (int s = lo; s < hi; ++s) { const uint32_t c = off[s]; off[s] = run; run += c; }
+    for (int s = lo; s < hi; ++s) { const uint32_t c = off[s]; off[s] = static_cast<uint16_t>(run); run += c; }
     __syncthreads();
-    // 3. fill the lists (slot order is arbitrary here ...); afterwards off[s] = end of list s
+    // 3. fill: bump the 16-bit cursor of list s (slot order is arbitrary here ...)
     for (int p = threadIdx.x; p < hw; p += kRwThreads) {
-        const uint16_t s = map[p];
-        if (s != 0xffffu) lst[atomicAdd(&off[s], 1u)] = static_cast<uint16_t>(p);
-    }
-    __syncthreads();
-    // 4. ... so sort every list by p (insertion sort; lists hold ~1/scale^2 entries)
-    for (int s = threadIdx.x; s < hw; s += kRwThreads) {
-        const int st = s == 0 ? 0 : static_cast<int>(off[s - 1]), en = static_cast<int>(off[s]);
-        for (int q = st + 1; q < en; ++q) {
-            const uint16_t v = lst[q];
-            int r = q - 1;
-            while (r >= st && lst[r] > v) { lst[r + 1] = lst[r]; --r; }
-            lst[r + 1] = v;
+        const int s = static_cast<int>(map[p]) - s_lo;
+        if (s >= 0 && s < ns) {
+            const uint32_t old = atomicAdd(&off32[s >> 1], 1u << (16 * (s & 1)));
+            lst[(old >> (16 * (s & 1))) & 0xffffu] = code(p);
         }
     }
     __syncthreads();
-    // 5. every channel: grad_in[s] = sum over its list in ascending p (fp32, one rounding to T)
+    // 4. ... so sort every list (code() is monotone in p); lists hold ~1/scale^2 entries
+    for (int s = threadIdx.x; s < ns; s += kRwThreads) {
+        const int st = s == 0 ? 0 : off[s - 1], en = off[s];
+        for (int q = st + 1; q < en; ++q) {
+            const uint16_t v = lst[q];
+            int k = q - 1;
+            while (k >= st && lst[k] > v) { lst[k + 1] = lst[k]; --k; }
+            lst[k + 1] = v;
+        }
+    }
+    __syncthreads();
+}
+
+// composed map (source pixel of every output pixel, 0xffff = none) of pixels [p0, p1)
+__device__ __forceinline__ void build_map_slice(const float* __restrict__ theta, const RewarpArgs& a, uint16_t* map,
+                                                int p0, int p1) {
+    StageRegs R;
+    load_stages(R, theta, a.stages);
+    const int dj = kRwThreads / a.W, di = kRwThreads - dj * a.W;
+    int p = p0 + threadIdx.x;
+    int j0 = p / a.W, i0 = p - j0 * a.W;
+    for (; p < p1; p += kRwThreads) {
+        int i = i0, j = j0;
+        map[p] = composed_source_ij(i, j, R, a) ? static_cast<uint16_t>(j * a.W + i) : 0xffffu;
+        i0 += di; j0 += dj;
+        if (i0 >= a.W) { i0 -= a.W; ++j0; }
+    }
+}
+
+// heatmap route (planes up to 4096 px): gradient planes staged through padded shared memory; the
+// CTAs of a sample form a cluster and build the composed map together (see rewarp_smem_kernel).
+// dynamic smem: kRwRing plane buffers | uint16 off[hw + 8] | lst_loc[hw] | map[hw] (-> lst)
+template <typename T>
+__global__ void __launch_bounds__(kRwThreads, 2)
+rewarp_bwd_smem_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __restrict__ gin, int buf_words) {
+    constexpr int EPW = 4 / static_cast<int>(sizeof(T));
+    constexpr int SLOTS = kRwPix / EPW;
+    extern __shared__ __align__(16) uint32_t rw_smem[];
+    __shared__ float s_theta[kRwMaxStages * 6];
+    __shared__ uint32_t s_scan[kRwThreads];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int nrank = static_cast<int>(cluster.num_blocks()), rank = static_cast<int>(cluster.block_rank());
+    const int hw = a.H * a.W, nwords = hw / EPW;
+    // off      : list ends, indexed by source pixel; own slice inverted here, the peers' slices pulled
+    // lst_loc  : this CTA's share of the lists (read by the peers)
+    // map->lst : the composed map, later the complete list array
+    uint16_t* off = reinterpret_cast<uint16_t*>(rw_smem + kRwRing * buf_words);
+    uint16_t* lst_loc = off + ((hw + 8 + 7) & ~7);
+    uint16_t* map = lst_loc + ((hw + 7) & ~7);
+    uint16_t* lst = map;
+    __shared__ uint32_t s_total;
+    const int b = blockIdx.x / nrank;
+    const int c0 = min(a.C, rank * a.cpc), c1 = min(a.C, c0 + a.cpc);
+    if (threadIdx.x < a.stages * 6)
+        s_theta[threadIdx.x] = a.view[0].theta[static_cast<int64_t>(b) * a.stages * 6 + threadIdx.x];
+    uint32_t* off32 = reinterpret_cast<uint32_t*>(off);
+    for (int s = threadIdx.x; s < (hw + 8) / 2; s += kRwThreads) off32[s] = 0u;
+    if (threadIdx.x < kRwRing) rw_smem[threadIdx.x * buf_words + buf_words - 4] = 0u;   // the zero word of every buffer
+    __syncthreads();
+    const int row_words = a.W / EPW, vpr = row_words / 4, nvec = nwords / 4;
+    float J[4];
+    composed_jacobian(s_theta, a, J);
+    // consecutive source pixels pull from output pixels one step of the INVERSE map apart:
+    // J^-1 (1,0) = (J[3], -J[2]) / det
+    const float det = J[0] * J[3] - J[1] * J[2];
+    const float inv = det != 0.0f ? 1.0f / det : 0.0f;
+    const int stride = pick_stride(row_words, J[3] * inv, -J[2] * inv, EPW - 1);
+    int so[kRwMaxVec];
+    stage_offsets(so, nvec, vpr, stride);
+    auto issue = [&](int it) {
+        stage_issue<T>(smem_u32(rw_smem + (it % kRwRing) * buf_words), so, gout + (static_cast<int64_t>(b) * a.C + c0 + it) * hw);
+    };
+    const int nitems = c1 - c0;
+#pragma unroll
+    for (int it = 0; it < kRwRing - 1; ++it) {   // in flight during the inversion
+        if (it < nitems) issue(it);
+        cp_async_commit();
+    }
+    // 1. the composed map, built by the cluster together: own slice, then the peers' through DSMEM
+    const int slice_log2 = ceil_log2((hw + nrank - 1) / nrank);
+    const int lo = min(hw, rank << slice_log2), hi = min(hw, (rank + 1) << slice_log2);
+    build_map_slice(s_theta, a, map, lo, hi);
+    cluster.sync();
+    pull_slices(cluster, map, hw, slice_log2, rank);
+    __syncthreads();
+    // 2. every CTA inverts the map for ITS slice of the source pixels only (lists = padded BYTE offsets,
+    //    list ends relative to the start of the share)
+    {
+        const int W = a.W;
+        invert_map(map, hw, lo, hi, off + lo, lst_loc, s_scan, [=](int p) {
+            const int row = p / W;
+            return static_cast<uint16_t>(row * stride * 4 + (p - row * W) * static_cast<int>(sizeof(T)));
+        });
+    }
+    if (threadIdx.x == 0) s_total = hi > lo ? off[hi - 1] : 0u;
+    cluster.sync();   // every share is complete (and nobody reads a peer's map any more: it becomes `lst`)
+    // 3. gather the shares: the lists of rank r follow those of the ranks below it
+    {
+        __shared__ uint32_t s_base[9], s_vbase[9];
+        if (threadIdx.x == 0) {
+            uint32_t run = 0, vrun = 0;
+            for (int r = 0; r < 8; ++r) {
+                const uint32_t tot = r < nrank ? *cluster.map_shared_rank(&s_total, r) : 0u;
+                s_base[r] = run; s_vbase[r] = vrun;
+                run += tot; vrun += (tot + 7) / 8;
+            }
+            s_base[8] = run; s_vbase[8] = vrun;
+        }
+        pull_slices(cluster, off, hw, slice_log2, rank);
+        __syncthreads();
+        // lists: 8-entry vectors of every share, appended at the share's base
+        const int nvecs = static_cast<int>(s_vbase[8]);
+        for (int g = threadIdx.x; g < nvecs; g += kRwThreads) {
+            int r = 0;
+#pragma unroll
+            for (int t = 1; t < 8; ++t) r += static_cast<uint32_t>(g) >= s_vbase[t] ? 1 : 0;
+            const uint32_t bs = s_base[r], tot = s_base[r + 1] - bs;
+            const int q0 = (g - static_cast<int>(s_vbase[r])) * 8;
+            const uint4 v4 = *reinterpret_cast<const uint4*>(cluster.map_shared_rank(lst_loc + q0, r));
+            const uint32_t w[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (static_cast<uint32_t>(q0 + e) < tot) lst[bs + q0 + e] = static_cast<uint16_t>(w[e >> 1] >> (16 * (e & 1)));
+        }
+        // list ends become absolute
+        for (int s = threadIdx.x; s < hw; s += kRwThreads) off[s] = static_cast<uint16_t>(off[s] + s_base[s >> slice_log2]);
+    }
+    cluster.sync();   // the peers are done with this CTA's share; also a CTA-wide barrier
+    if (nitems > 0) {
+        // The first four contributors of each source pixel this thread owns, as padded byte offsets in
+        // registers (missing ones point at the zero word): the per-plane sum is four independent LDS
+        // and three adds per pixel, no data-dependent loop.  Lists longer than four entries (zoom
+        // factors above ~1.7) take the loop for the rest; the order stays ascending p either way.
+        const uint32_t zero_byte = static_cast<uint32_t>(buf_words - 4) * 4u;
+        uint2 slot[kRwPix];
+        bool overflow = false;
+#pragma unroll
+        for (int k = 0; k < kRwPix; ++k) {
+            const int word = (k / EPW) * kRwThreads + threadIdx.x;
+            const int s = word * EPW + (k % EPW);
+            uint32_t o[4] = {zero_byte, zero_byte, zero_byte, zero_byte};
+            if (word < nwords) {
+                const int st = s == 0 ? 0 : off[s - 1], en = off[s];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (st + q < en) o[q] = lst[st + q];
+                overflow |= en - st > 4;
+            }
+            slot[k] = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
+        }
+        const bool any_overflow = __syncthreads_or(overflow);
+        for (int it = 0; it < nitems; ++it) {
+            cp_async_wait<kRwRing - 2>();
+            __syncthreads();
+            if (it + kRwRing - 1 < nitems) issue(it + kRwRing - 1);
+            cp_async_commit();
+            const uint8_t* bytes = reinterpret_cast<const uint8_t*>(rw_smem + (it % kRwRing) * buf_words);
+            T* o = gin + (static_cast<int64_t>(b) * a.C + c0 + it) * hw;
+#pragma unroll
+            for (int sl = 0; sl < SLOTS; ++sl) {
+                float f[EPW];
+#pragma unroll
+                for (int e = 0; e < EPW; ++e) {
+                    const uint2 sq = slot[sl * EPW + e];
+                    const float v0 = to_f32<T>(*reinterpret_cast<const T*>(bytes + (sq.x & 0xffffu)));
+                    const float v1 = to_f32<T>(*reinterpret_cast<const T*>(bytes + (sq.x >> 16)));
+                    const float v2 = to_f32<T>(*reinterpret_cast<const T*>(bytes + (sq.y & 0xffffu)));
+                    const float v3 = to_f32<T>(*reinterpret_cast<const T*>(bytes + (sq.y >> 16)));
+                    f[e] = ((v0 + v1) + v2) + v3;   // ascending p, fp32, one rounding to T
+                }
+                const int word = sl * kRwThreads + threadIdx.x;
+                if (word < nwords) store_word<T>(o, word, f);
+            }
+            if (any_overflow) {
+                // rare: redo the pixels of this thread whose lists hold more than four entries (same order,
+                // all entries) and overwrite the element this thread has just stored
+                for (int k = 0; k < kRwPix; ++k) {
+                    const int word = (k / EPW) * kRwThreads + threadIdx.x;
+                    if (word >= nwords) continue;
+                    const int s = word * EPW + (k % EPW);
+                    const int st = s == 0 ? 0 : off[s - 1], en = off[s];
+                    if (en - st <= 4) continue;
+                    float sum = 0.0f;
+                    for (int q = st; q < en; ++q) sum += to_f32<T>(*reinterpret_cast<const T*>(bytes + lst[q]));
+                    o[s] = from_f32<T>(sum);
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// general route (any plane up to 25600 px): gradient gathered from global memory.
+// dynamic smem: uint16 off[hw + 2] | uint16 lst[hw] | uint16 map[hw]
+template <typename T>
+__global__ void __launch_bounds__(kRwThreads)
+rewarp_bwd_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __restrict__ gin) {
+    extern __shared__ __align__(16) uint32_t rw_smem[];
+    __shared__ float s_theta[kRwMaxStages * 6];
+    __shared__ uint32_t s_scan[kRwThreads];
+    const int hw = a.H * a.W;
+    uint16_t* off = reinterpret_cast<uint16_t*>(rw_smem);
+    uint16_t* lst = off + ((hw + 2 + 7) & ~7);
+    uint16_t* map = lst + ((hw + 7) & ~7);
+    const int cgroups = (a.C + a.cpc - 1) / a.cpc;
+    const int cg = blockIdx.x % cgroups, b = blockIdx.x / cgroups;
+    const int c0 = cg * a.cpc, c1 = min(a.C, c0 + a.cpc);
+    if (threadIdx.x < a.stages * 6)
+        s_theta[threadIdx.x] = a.view[0].theta[static_cast<int64_t>(b) * a.stages * 6 + threadIdx.x];
+    uint32_t* off32 = reinterpret_cast<uint32_t*>(off);
+    for (int s = threadIdx.x; s < (hw + 2) / 2; s += kRwThreads) off32[s] = 0u;
+    __syncthreads();
+    build_map_slice(s_theta, a, map, 0, hw);
+    __syncthreads();
+    invert_map(map, hw, 0, hw, off, lst, s_scan, [](int p) { return static_cast<uint16_t>(p); });
     for (int c = c0; c < c1; ++c) {
         const int64_t base = (static_cast<int64_t>(b) * a.C + c) * hw;
         const T* go = gout + base;
         for (int s = threadIdx.x; s < hw; s += kRwThreads) {
-            const int st = s == 0 ? 0 : static_cast<int>(off[s - 1]), en = static_cast<int>(off[s]);
+            const int st = s == 0 ? 0 : off[s - 1], en = off[s];
             float acc = 0.0f;
             for (int q = st; q < en; ++q) acc += to_f32<T>(go[lst[q]]);
             gin[base + s] = from_f32<T>(acc);
@@ -220,13 +708,35 @@ rewarp_bwd_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __restrict_
     }
 }
 
-static int channels_per_cta(int64_t units, int64_t c) {
-    // aim at ~16 CTAs per SM worth of work items, amortising the index computation over channels
-    int64_t cpc = units * c / (148 * 16);
+// channels per CTA: amortise the per-sample index work over channels while keeping ~`target` CTAs
+static int channels_per_cta(int64_t units, int64_t c, int64_t target) {
+    int64_t cpc = (units * c + target - 1) / target;
     if (cpc < 1) cpc = 1;
     if (cpc > c) cpc = c;
     const int64_t groups = (c + cpc - 1) / cpc;
     return static_cast<int>((c + groups - 1) / groups);  // even split
+}
+
+static int sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+        n = 148;
+    return n;
+}
+
+// the shared-memory route needs 16-byte rows, planes of at most 4096 pixels and a padded plane
+// that fits the per-buffer budget; returns the buffer size in words, 0 if the route does not apply
+static int smem_route_words(int64_t H, int64_t W, int elem_bytes) {
+    if ((W * elem_bytes) % 16 != 0 || H * W > kRwThreads * kRwPix || (H * W) % 8 != 0) return 0;
+    const int row_words = static_cast<int>(W * elem_bytes / 4);
+    const int sa = padded_stride(row_words, 4), sb = padded_stride(row_words, 12);
+    const int64_t words = H * (sa > sb ? sa : sb) + 4;   // either padding per sample, + the zero word (16-byte tail)
+    return words * 4 <= kRwBufBytes ? static_cast<int>(words) : 0;
+}
+
+static bool route_disabled() {
+    const char* e = std::getenv("UDAPE_REWARP_GLOBAL");  // tests compare both routes within one process
+    return e && e[0] == '1';
 }
 
 static int fill_common(RewarpArgs& a, const char* name, int views, int stages, int half_mask, int grid_dtype,
@@ -246,6 +756,65 @@ static int fill_common(RewarpArgs& a, const char* name, int views, int stages, i
     return UDAPE_OK;
 }
 
+// CTAs per sample (= cluster size): the smallest power of two that gives ~4 CTAs per SM, at most the
+// portable cluster limit of 8 and the channel count
+static int cluster_size_for(int64_t B, int64_t C, int64_t hw) {
+    if (const char* e = std::getenv("UDAPE_REWARP_CLUSTER")) {   // tuning / tests: force 1, 2, 4 or 8
+        const int n = std::atoi(e);
+        if (n == 1 || ((n == 2 || n == 4 || n == 8) && n <= C && hw / n >= 8)) return n;
+    }
+    // measured (B200, 64x64 planes): best with 1.5-2 CTAs per SM in total — more CTAs repeat the per-CTA
+    // set-up (offset fetch, stride pick, pipeline fill), fewer leave SMs idle
+    const int64_t want = 3 * static_cast<int64_t>(sm_count()) / 2;
+    int n = 1;
+    while (n < 8 && 2 * n <= C && hw / (2 * n) >= 8 && B * n < want) n *= 2;   // slices of the map hold >= 8 entries
+    return n;
+}
+
+template <typename... KArgs, typename... Args>
+static int launch_cluster(void (*kernel)(KArgs...), unsigned grid, unsigned cluster, size_t smem, cudaStream_t st,
+                          const char* name, Args... args) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: cannot reserve %zu bytes of shared memory", name, smem);
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(kRwThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: %s (%s)", name, cudaGetErrorName(e), cudaGetErrorString(e));
+    return UDAPE_OK;
+}
+
+template <typename K>
+static int reserve_smem(K kernel, size_t bytes, const char* name) {
+    if (bytes <= 48 * 1024) return UDAPE_OK;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: cannot reserve %zu bytes of shared memory", name, bytes);
+    return UDAPE_OK;
+}
+
+template <typename T>
+static int launch_smem_fwd(const RewarpArgs& a, int views, unsigned grid, unsigned cluster, size_t smem, cudaStream_t st,
+                           T* out, int buf_words) {
+    const char* name = "udape_rewarp_fwd";
+    switch (views) {
+        case 1: return launch_cluster(rewarp_smem_kernel<T, 1>, grid, cluster, smem, st, name, a, out, buf_words);
+        case 2: return launch_cluster(rewarp_smem_kernel<T, 2>, grid, cluster, smem, st, name, a, out, buf_words);
+        case 3: return launch_cluster(rewarp_smem_kernel<T, 3>, grid, cluster, smem, st, name, a, out, buf_words);
+        default: return launch_cluster(rewarp_smem_kernel<T, 4>, grid, cluster, smem, st, name, a, out, buf_words);
+    }
+}
+
 }  // namespace udape
 
 using namespace udape;
@@ -259,12 +828,14 @@ extern "C" int udape_rewarp_fwd(const void* const* in, const float* const* theta
     const int rc = fill_common(a, "udape_rewarp_fwd", views, stages, half_mask, grid_dtype, B, C, H, W, dtype);
     if (rc) return rc;
     const int es = dtype_size(dtype);
+    bool all16 = aligned16(out);
     for (int v = 0; v < views; ++v) {
         UDAPE_REQUIRE(in[v] && theta[v], UDAPE_ERR_NULL, "udape_rewarp_fwd: NULL view %d", v);
         UDAPE_REQUIRE(aligned_to(in[v], es) && aligned_to(theta[v], 4), UDAPE_ERR_ALIGN, "udape_rewarp_fwd: misaligned view %d", v);
         UDAPE_REQUIRE(in[v] != out, UDAPE_ERR_ARG, "udape_rewarp_fwd: the gather cannot run in place");
         a.view[v].in = in[v];
         a.view[v].theta = theta[v];
+        all16 = all16 && aligned16(in[v]);
     }
     UDAPE_REQUIRE(aligned_to(out, es) && (!paste || aligned_to(paste, 4)), UDAPE_ERR_ALIGN, "udape_rewarp_fwd: misaligned pointer");
     UDAPE_REQUIRE(!paste || (paste_after >= 0 && paste_after < stages), UDAPE_ERR_ARG,
@@ -273,12 +844,26 @@ extern "C" int udape_rewarp_fwd(const void* const* in, const float* const* theta
     a.paste = paste; a.paste_after = paste_after; a.active = active;
     const int64_t hw = H * W;
     cudaStream_t st = as_stream(stream);
+    const int buf_words = (all16 && !paste && !active && !route_disabled()) ? smem_route_words(H, W, es) : 0;
+    if (buf_words) {
+        // one cluster of `n` CTAs per sample: the channels are split n ways, the map is built once
+        const int n = cluster_size_for(B, C, hw);
+        a.cpc = static_cast<int>((C + n - 1) / n);
+        const int64_t grid = B * n;
+        const size_t smem = kRwRing * sizeof(uint32_t) * static_cast<size_t>(buf_words) + sizeof(uint16_t) * views * ((hw + 7) & ~7ll);
+        UDAPE_DISPATCH_FLOAT(dtype, T, {
+            const int r2 = launch_smem_fwd<T>(a, views, static_cast<unsigned>(grid), static_cast<unsigned>(n), smem, st,
+                                              static_cast<T*>(out), buf_words);
+            if (r2) return r2;
+        });
+        return check_launch("udape_rewarp_fwd");
+    }
     UDAPE_DISPATCH_FLOAT(dtype, T, {
         constexpr int EPV = Vec16<T>::EPV;
         const bool vec = (hw % EPV) == 0 && aligned16(out);
         const int px = vec ? EPV : 1;
         const int64_t bands = (hw + kRwThreads * px - 1) / (kRwThreads * px);
-        a.cpc = channels_per_cta(B * bands, C);
+        a.cpc = channels_per_cta(B * bands, C, 16 * static_cast<int64_t>(sm_count()));
         const int64_t grid = B * bands * ((C + a.cpc - 1) / a.cpc);
         UDAPE_REQUIRE(grid < (1ll << 31), UDAPE_ERR_SHAPE, "udape_rewarp_fwd: grid too large");
         if (vec) rewarp_fwd_kernel<T, EPV><<<static_cast<unsigned>(grid), kRwThreads, 0, st>>>(a, static_cast<T*>(out));
@@ -298,23 +883,32 @@ extern "C" int udape_rewarp_bwd(const void* grad_out, const float* theta, int st
                   "udape_rewarp_bwd: misaligned pointer");
     UDAPE_REQUIRE(grad_out != grad_in, UDAPE_ERR_ARG, "udape_rewarp_bwd: cannot run in place");
     const int64_t hw = H * W;
-    // the inverted map lives in shared memory: 8 bytes per pixel
+    // the inverted map lives in shared memory: 6 bytes per pixel, 16-bit pixel indices
     UDAPE_REQUIRE(hw <= 25600, UDAPE_ERR_SHAPE, "udape_rewarp_bwd: planes above 25600 pixels are not supported (H*W=%lld)",
                   (long long)hw);
     a.view[0].in = grad_out;
     a.view[0].theta = theta;
-    a.cpc = channels_per_cta(B, C);
-    const int64_t grid = B * ((C + a.cpc - 1) / a.cpc);
-    const size_t smem = sizeof(uint32_t) * (hw + 1 + ((hw + 1) & 1)) + 2 * sizeof(uint16_t) * hw;
     cudaStream_t st = as_stream(stream);
+    // 16-bit arrays: smem route off[hw + 8] | lst_loc[hw] | map[hw]; general route off[hw + 2] | lst[hw] | map[hw]
+    const size_t list_bytes = sizeof(uint16_t) * (((hw + 8 + 7) & ~7ll) + 2 * ((hw + 7) & ~7ll));
+    const int buf_words = (aligned16(grad_out) && aligned16(grad_in) && !route_disabled()) ? smem_route_words(H, W, es) : 0;
     UDAPE_DISPATCH_FLOAT(dtype, T, {
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(rewarp_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 static_cast<int>(smem));
-            if (e != cudaSuccess) return fail(static_cast<int>(e), "udape_rewarp_bwd: cannot reserve %zu bytes of shared memory", smem);
+        if (buf_words) {
+            const int n = cluster_size_for(B, C, hw);
+            a.cpc = static_cast<int>((C + n - 1) / n);
+            const size_t smem = kRwRing * sizeof(uint32_t) * static_cast<size_t>(buf_words) + list_bytes;
+            const int r2 = launch_cluster(rewarp_bwd_smem_kernel<T>, static_cast<unsigned>(B * n), static_cast<unsigned>(n), smem, st,
+                                          "udape_rewarp_bwd", a, static_cast<const T*>(grad_out), static_cast<T*>(grad_in), buf_words);
+            if (r2) return r2;
+        } else {
+            a.cpc = channels_per_cta(B, C, 2 * static_cast<int64_t>(sm_count()));
+            const int64_t grid = B * ((C + a.cpc - 1) / a.cpc);
+            const size_t smem = list_bytes;
+            const int r2 = reserve_smem(rewarp_bwd_kernel<T>, smem, "udape_rewarp_bwd");
+            if (r2) return r2;
+            rewarp_bwd_kernel<T><<<static_cast<unsigned>(grid), kRwThreads, smem, st>>>(
+                a, static_cast<const T*>(grad_out), static_cast<T*>(grad_in));
         }
-        rewarp_bwd_kernel<T><<<static_cast<unsigned>(grid), kRwThreads, smem, st>>>(
-            a, static_cast<const T*>(grad_out), static_cast<T*>(grad_in));
     });
     return check_launch("udape_rewarp_bwd");
 }
