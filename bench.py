@@ -4,7 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config C2]
 
 A *step* is one pass of the mean-teacher hot path (uda_poseestimation_b200.hotpath) over one
-synthetic batch shard: AdaIN+mix s2t and t2s, teacher decode/masks/rectify, JointsMSELoss and
+synthetic batch shard: AdaIN+mix s2t and t2s, re-warp of the teacher / student heatmaps to the
+un-augmented frame (with the student's backward), teacher decode/masks/rectify, JointsMSELoss and
 ConsLoss fwd+bwd, PCK counts, EMA over a PoseResNet-101-shaped parameter list.  At N=1 the
 workload is BASELINE.json configs[1] (SURREAL->LSP, 16 keypoints, batch 32); at N>1 every
 rank runs the same per-GPU batch (weak scaling) and the int32 PCK counts are all-reduced
@@ -61,7 +62,20 @@ def make_host_inputs(cfg: dict, seed: int, student_dtype=torch.float16, pin: boo
                 y_t_stu=y_t_stu, y_t_tea=y_t_tea, joints=torch.from_numpy(joints), vis=torch.from_numpy(vis))
     if pin and torch.cuda.is_available():
         host = {n: t.pin_memory() for n, t in host.items()}
+    # meta['aug_param_tea'] / ['aug_param_stu'] of the batch, as the DataLoader collates them
+    host["aug_tea"], host["aug_stu"] = S.aug_params(b, seed + 7), S.aug_params(b, seed + 8)
     return host
+
+
+def stage_tables(host, student_dtype):
+    """Host half of the re-warp: the per-sample tF.affine matrices -> two float32 [B,3,6] tables."""
+    from uda_poseestimation_b200 import rewarp as RW
+
+    b = host["y_t_tea"].shape[0]
+    ac = student_dtype if student_dtype != torch.float32 else None
+    t_tea = RW.stage_table(RW.recon_stages(host["aug_tea"], 4.0, b), 64, 64, torch.float32, None)[0]
+    t_stu = RW.stage_table(RW.recon_stages(host["aug_stu"], 4.0, b), 64, 64, student_dtype, ac)[0]
+    return t_tea, t_stu
 
 
 class ParamBag(torch.nn.Module):
@@ -145,12 +159,14 @@ def cpu_step_factory(cfg: dict, seed: int):
         with torch.no_grad():
             t1 = R.adain_mix(host["feat_src"], host["feat_tgt_ori"], float(rng.uniform(0, 1)))
             t2 = R.adain_mix(host["feat_tgt_tea"], host["feat_src_ori"], float(rng.uniform(0, 1)))
-            conf, pos, table = R.confidence_mask(host["y_t_tea"], 0.9)
-            mask, thresh, act = R.consistency_mask(host["y_t_tea"], 0.5)
-            rect = R.rectify(host["y_t_tea"], sigma)
+            y_t_tea = R.teacher_recon([host["y_t_tea"]], [host["aug_tea"]], 4.0)   # train_human.py:359-372
+            conf, pos, table = R.confidence_mask(y_t_tea, 0.9)
+            mask, thresh, act = R.consistency_mask(y_t_tea, 0.5)
+            rect = R.rectify(y_t_tea, sigma)
         y_s = host["y_s"].detach().requires_grad_(True)
         y_t = host["y_t_stu"].detach().requires_grad_(True)
-        loss = R.joints_mse_loss(y_s, label, weight) + 1.0 * R.cons_loss(y_t, rect, tea_mask=mask)
+        y_t_recon = R.student_recon(y_t, host["aug_stu"], 4.0)                     # :417-423
+        loss = R.joints_mse_loss(y_s, label, weight) + 1.0 * R.cons_loss(y_t_recon, rect, tea_mask=mask)
         (loss * 65536.0).backward()
         R.ema_step(teacher, student, 0.999)
         acc, avg, cnt, pred = R.accuracy(y_s.detach().numpy(), label.numpy())
@@ -201,6 +217,7 @@ def run_reference_arm(args, cfg, rank):
 
 def workload_config(cfg, n_gpus, graph=True, fused=True, ema="graph"):
     return {"workload": f"{cfg['name']}: mean-teacher hot-path step (AdaIN s2t+t2s mix on 512x32x32 relu4_1 features, "
+                        f"three-stage affine re-warp of teacher/student heatmaps (+ backward), "
                         f"teacher decode/conf/kth-mask/rectify, JointsMSE+Cons fwd+bwd, PCK, EMA over PoseResNet-101 "
                         f"params), batch {cfg['batch']}/GPU, {cfg['joints']} keypoints, 256x256 images, 64x64 heatmaps",
             "batch_per_gpu": cfg["batch"], "global_batch": cfg["batch"] * n_gpus, "keypoints": cfg["joints"],
@@ -228,12 +245,15 @@ def run_b200_arm(args, cfg, rank, world, local):
     seed = 1234 + rank
     b, k, sigma = cfg["batch"], cfg["joints"], cfg["sigma"]
     host = make_host_inputs(cfg, seed)
-    d = {n: t.to(dev, non_blocking=True) for n, t in host.items()}
+    d = {n: t.to(dev, non_blocking=True) for n, t in host.items() if torch.is_tensor(t)}
+    t_tea, t_stu = stage_tables(host, torch.float16)
+    host["theta_tea"], host["theta_stu"] = t_tea.pin_memory(), t_stu.pin_memory()
     label, weight = U.generate_target_batched(d["joints"], d["vis"], (64, 64), sigma, (256, 256), device=dev)
     host["label_s"], host["weight_s"] = label.cpu().pin_memory(), weight.cpu().pin_memory()
     inp = StepInputs(feat_src=d["feat_src"], feat_tgt_ori=d["feat_tgt_ori"], feat_tgt_tea=d["feat_tgt_tea"],
                      feat_src_ori=d["feat_src_ori"], y_s=d["y_s"], y_t_stu=d["y_t_stu"], y_t_tea=d["y_t_tea"],
-                     label_s=label, weight_s=weight, alpha_s2t=None, alpha_t2s=None)
+                     label_s=label, weight_s=weight, alpha_s2t=None, alpha_t2s=None,
+                     theta_tea=host["theta_tea"].to(dev), theta_stu=host["theta_stu"].to(dev))
     alpha_pair = torch.zeros(2, device=dev)  # one 8-byte copy per step sets both directions
     inp.alpha_s2t, inp.alpha_t2s = alpha_pair[0:1], alpha_pair[1:2]
     shapes = S.pose_resnet_param_shapes(k)
@@ -325,7 +345,7 @@ def run_b200_arm(args, cfg, rank, world, local):
 
     # ---- e2e: host (pinned) inputs -> device -> step -> results back on the host -----------------
     h2d_names = ["feat_src", "feat_tgt_ori", "feat_tgt_tea", "feat_src_ori", "y_s", "y_t_stu", "y_t_tea",
-                 "label_s", "weight_s"]
+                 "label_s", "weight_s", "theta_tea", "theta_stu"]
     h2d_bytes = sum(host[n].numel() * host[n].element_size() for n in h2d_names) + 8
     res_host = dict(losses=torch.empty(3, dtype=torch.float32).pin_memory(),
                     counts=torch.empty((2, k), dtype=torch.int32).pin_memory(),
@@ -335,7 +355,14 @@ def run_b200_arm(args, cfg, rank, world, local):
     losses_dev = torch.empty(3, dtype=torch.float32, device=dev)
 
     def e2e_step(i):
-        for n in h2d_names:
+        for n in h2d_names[:-2]:
+            getattr(inp, n).copy_(host[n], non_blocking=True)
+        # host half of the re-warp (the reference computes the same matrices inside tF.affine, per sample);
+        # it runs while the asynchronous copies above are on the wire
+        t_tea, t_stu = stage_tables(host, torch.float16)
+        host["theta_tea"].copy_(t_tea)
+        host["theta_stu"].copy_(t_stu)
+        for n in h2d_names[-2:]:
             getattr(inp, n).copy_(host[n], non_blocking=True)
         alpha_pair.copy_(alpha_host[i], non_blocking=True)
         o = body()

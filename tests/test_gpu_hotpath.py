@@ -8,6 +8,7 @@ import torch
 import uda_poseestimation_b200 as U
 from conftest import assert_close_scaled
 from oracle import reference_port as R
+from uda_poseestimation_b200 import rewarp as RW
 from uda_poseestimation_b200 import synthetic as S
 from uda_poseestimation_b200.hotpath import HotPathStep, StepInputs, step_algorithmic_bytes
 
@@ -20,7 +21,7 @@ class Bag(torch.nn.Module):
         self.ps = torch.nn.ParameterList([torch.nn.Parameter(t.clone()) for t in tensors])
 
 
-def _inputs(dev, b=4, k=16, n_feat_c=32, seed=5):
+def _inputs(dev, b=4, k=16, n_feat_c=32, seed=5, rewarp=True):
     src, tgt_style = S.vgg_features(b, seed, channels=n_feat_c)
     tgt, src_style = S.vgg_features(b, seed + 1, channels=n_feat_c)
     joints, vis = S.keypoints(b, k, seed + 5)
@@ -32,28 +33,43 @@ def _inputs(dev, b=4, k=16, n_feat_c=32, seed=5):
                 weight_s=torch.from_numpy(np.stack([x[1] for x in lab])))
     inp = StepInputs(**{n: t.to(dev) for n, t in host.items()}, alpha_s2t=torch.tensor([0.3], device=dev),
                      alpha_t2s=torch.tensor([0.8], device=dev))
+    if rewarp:
+        # the collated meta['aug_param_tea'] / ['aug_param_stu'] of the batch and their device stage tables
+        host["aug_tea"], host["aug_stu"] = S.aug_params(b, seed + 6), S.aug_params(b, seed + 7, shear_y=True)
+        inp.theta_tea = RW.stage_table(RW.recon_stages(host["aug_tea"], 4.0, b), 64, 64, torch.float32, None)[0].to(dev)
+        inp.theta_stu = RW.stage_table(RW.recon_stages(host["aug_stu"], 4.0, b), 64, 64, torch.float16, torch.float16)[0].to(dev)
     return host, inp
 
 
 def _oracle_step(host, a1, a2, teacher, student, scale=65536.0):
     t1 = R.adain_mix(host["feat_src"], host["feat_tgt_ori"], a1)
     t2 = R.adain_mix(host["feat_tgt_tea"], host["feat_src_ori"], a2)
-    conf, pos, table = R.confidence_mask(host["y_t_tea"], 0.9)
-    mask, thresh, act = R.consistency_mask(host["y_t_tea"], 0.5)
-    rect = R.rectify(host["y_t_tea"], 2)
+    y_t_tea = host["y_t_tea"]
+    if "aug_tea" in host:
+        y_t_tea = R.teacher_recon([y_t_tea], [host["aug_tea"]], 4.0)              # train_human.py:359-372
+    conf, pos, table = R.confidence_mask(y_t_tea, 0.9)
+    mask, thresh, act = R.consistency_mask(y_t_tea, 0.5)
+    rect = R.rectify(y_t_tea, 2)
     y_s = host["y_s"].float().clone().requires_grad_(True)
-    y_t = host["y_t_stu"].float().clone().requires_grad_(True)
+    if "aug_stu" in host:
+        y_t = host["y_t_stu"].clone().requires_grad_(True)                        # fp16 leaf, autocast re-warp
+        y_t_recon = R.student_recon(y_t, host["aug_stu"], 4.0)                    # :417-423
+    else:
+        y_t = host["y_t_stu"].float().clone().requires_grad_(True)
+        y_t_recon = y_t
     loss_s = R.joints_mse_loss(y_s, host["label_s"], host["weight_s"])
-    loss_c = R.cons_loss(y_t, rect, tea_mask=mask)
+    loss_c = R.cons_loss(y_t_recon.float(), rect, tea_mask=mask)
     ((loss_s + 1.0 * loss_c) * scale).backward()
     R.ema_step(teacher, student, 0.999)
     hits, valid, pred = R.pck_counts(host["y_s"].numpy(), host["label_s"].numpy())
-    return dict(y_t_tea=host["y_t_tea"], t_s2t=t1, t_t2s=t2, conf_table=table, position=pos, tea_mask=mask, rectified=rect,
-                loss_s=loss_s.detach(), loss_c=loss_c.detach(), grad_y_s=y_s.grad, grad_y_t_stu=y_t.grad,
+    return dict(y_t_tea=y_t_tea, y_t_stu_recon=y_t_recon.detach(), t_s2t=t1, t_t2s=t2, conf_table=table, position=pos, tea_mask=mask, rectified=rect,
+                loss_s=loss_s.detach(), loss_c=loss_c.detach(), grad_y_s=y_s.grad, grad_y_t_stu=y_t.grad.float(),
                 hits=hits, valid=valid, pred=pred)
 
 
 def _check(out, ref):
+    assert torch.equal(out["y_t_tea_recon"].cpu(), ref["y_t_tea"])              # gathers: bit-exact
+    assert torch.equal(out["y_t_stu_recon"].cpu(), ref["y_t_stu_recon"].to(out["y_t_stu_recon"].dtype))
     assert_close_scaled(out["t_s2t"], ref["t_s2t"], 1e-5, "s2t")
     assert_close_scaled(out["t_t2s"], ref["t_t2s"], 1e-5, "t2s")
     assert torch.equal(out["conf_table"].cpu(), ref["conf_table"])
@@ -71,10 +87,11 @@ def _check(out, ref):
     np.testing.assert_array_equal(out["pred"].cpu().numpy(), ref["pred"])
 
 
+@pytest.mark.parametrize("rewarp", [True, False])
 @pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("parallel", [False, True])
-def test_step_eager_vs_oracle(dev, parallel, fused):
-    host, inp = _inputs(dev)
+def test_step_eager_vs_oracle(dev, parallel, fused, rewarp):
+    host, inp = _inputs(dev, rewarp=rewarp)
     shapes = [(64, 3, 7, 7), (64,), (17,), (256, 64, 1, 1), (5000,)]
     s_cpu, t_cpu = S.parameter_list(shapes, 1), S.parameter_list(shapes, 2)
     student, teacher = Bag(s_cpu).to(dev), Bag(t_cpu).to(dev)
@@ -106,6 +123,10 @@ def test_step_graph_replay_with_device_alpha(dev, fused, ema_parallel):
         # new inputs in the same static buffers
         inp.y_s.copy_(torch.roll(inp.y_s, 1, dims=0))
         host["y_s"] = torch.roll(host["y_s"], 1, dims=0)
+        # new augmentation parameters: the stage tables are device tensors the graph reads in place
+        host["aug_tea"], host["aug_stu"] = S.aug_params(4, int(a1 * 100)), S.aug_params(4, int(a2 * 100) + 1)
+        inp.theta_tea.copy_(RW.stage_table(RW.recon_stages(host["aug_tea"], 4.0, 4), 64, 64, torch.float32, None)[0])
+        inp.theta_stu.copy_(RW.stage_table(RW.recon_stages(host["aug_stu"], 4.0, 4), 64, 64, torch.float16, torch.float16)[0])
         out = step.replay()
         torch.cuda.synchronize()
         ref = _oracle_step(host, a1, a2, t_cpu, s_cpu)

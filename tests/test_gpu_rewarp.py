@@ -235,3 +235,31 @@ def test_rewarp_backward_long_lists(dev):
         # more than four output pixels really do share a source pixel here
         src = R.recon_source_index(10.0, 3, -2, 5.0, 0.0, 2.9, 4.0, 64, 64, dt, ac)
         assert np.bincount(src[src >= 0]).max() > 4
+
+
+def test_rewarp_cluster_kernels_under_contention(dev):
+    """The CTAs of a cluster exchange the composed map / the inverted lists through distributed shared
+    memory; when other kernels compete for the SMs the CTAs of a cluster drift apart in time, which is
+    what exposes a missing cluster barrier.  Forward and backward are repeated on two high-priority
+    streams next to a bandwidth hog and must reproduce the quiet result bit for bit."""
+    b, k = 32, 16
+    y = S.heatmaps(b, k, seed=71).to(dev).half()
+    g = torch.randn(b, k, 64, 64, device=dev).half()
+    t = RW.stage_table(RW.recon_stages(S.aug_params(b, seed=72, shear_y=True), 4.0, b), 64, 64, torch.float16, torch.float16)
+    theta = t[0].to(dev)
+    ref_f = RW.gather(y, theta, t[1], torch.float16)
+    ref_b = RW.gather_backward(g, theta, t[1], torch.float16)
+    torch.cuda.synchronize()
+    hog_a, hog_b = torch.empty(64 << 20, device=dev), torch.empty(64 << 20, device=dev)
+    streams = [torch.cuda.Stream(dev, priority=-1) for _ in range(2)]
+    hog = torch.cuda.Stream(dev)
+    outs = []
+    for it in range(40):
+        with torch.cuda.stream(hog):
+            hog_b.copy_(hog_a)
+        for s_ in streams:
+            with torch.cuda.stream(s_):
+                outs.append((RW.gather(y, theta, t[1], torch.float16), RW.gather_backward(g, theta, t[1], torch.float16)))
+    torch.cuda.synchronize()
+    for f, bw in outs:
+        assert torch.equal(f, ref_f) and torch.equal(bw, ref_b)

@@ -605,10 +605,11 @@ rewarp_bwd_smem_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __rest
             for (int e = 0; e < 8; ++e)
                 if (static_cast<uint32_t>(q0 + e) < tot) lst[bs + q0 + e] = static_cast<uint16_t>(w[e >> 1] >> (16 * (e & 1)));
         }
+        cluster.sync();   // the peers have pulled this CTA's list ends and lists: both may change / go away now
         // list ends become absolute
         for (int s = threadIdx.x; s < hw; s += kRwThreads) off[s] = static_cast<uint16_t>(off[s] + s_base[s >> slice_log2]);
+        __syncthreads();
     }
-    cluster.sync();   // the peers are done with this CTA's share; also a CTA-wide barrier
     if (nitems > 0) {
         // The first four contributors of each source pixel this thread owns, as padded byte offsets in
         // registers (missing ones point at the zero word): the per-plane sum is four independent LDS

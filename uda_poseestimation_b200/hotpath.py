@@ -3,8 +3,11 @@ assembled from the drop-in operators — everything the trainer does between the
 forward/backward passes, on tensors the convolutions would have produced:
 
     s2t / t2s   AdaIN + alpha mix of relu4_1 features        (:348-356 via Style_net.py:167-168)
+    teacher     re-warp of the teacher heatmaps to the        (:359-372)
+                un-augmented frame (three tF.affine stages)
     teacher     conf / position / conf_table, activates,      (:376-383, :427-430)
                 rectify, k-th-value consistency mask
+    student     re-warp of the student target heatmaps        (:417-423) + its backward
     student     JointsMSELoss fwd+bwd, ConsLoss fwd+bwd        (:425, :432, :434-436)
     teacher     EMA update over the PoseResNet parameter list  (:438)
     metric      PCK hit/valid counts on (y_s, label_s)         (:443-444)
@@ -17,9 +20,11 @@ free of host synchronisation, and can therefore be captured into a CUDA graph
 from __future__ import annotations
 
 import dataclasses
+import os
 
 import torch
 
+from . import rewarp as _rewarp
 from .adain import adain_mix
 from .ema import OldWeightEMA
 from .keypoint_detection import _pck
@@ -43,9 +48,13 @@ class StepInputs:
     weight_s: torch.Tensor      # [B,K,1]     fp32 visibility weight
     alpha_s2t: torch.Tensor     # [1] fp32 device scalar
     alpha_t2s: torch.Tensor     # [1] fp32 device scalar
+    # re-warp stage tables (rewarp.stage_table of the batch's aug_param_tea / aug_param_stu, float32
+    # [B,3,6] on the device, refreshed per step).  None: y_t_tea / y_t_stu are taken as already re-warped.
+    theta_tea: torch.Tensor | None = None
+    theta_stu: torch.Tensor | None = None
 
     def tensors(self):
-        return [getattr(self, f.name) for f in dataclasses.fields(self)]
+        return [getattr(self, f.name) for f in dataclasses.fields(self) if getattr(self, f.name) is not None]
 
 
 def step_algorithmic_bytes(inp: StepInputs, n_params: int, param_bytes: int = 4, fused: bool = True) -> dict:
@@ -74,6 +83,11 @@ def step_algorithmic_bytes(inp: StepInputs, n_params: int, param_bytes: int = 4,
         out["joints_mse_bwd"] = hm * (e_s + e_l) + hm * e_s
         out["cons_fwd"] = hm * (e_s + e_t) + 4 * planes
         out["cons_bwd"] = hm * (e_s + e_t) + hm * e_s
+    if inp.theta_tea is not None:
+        out["rewarp_teacher"] = 2 * hm * e_t + 72 * inp.y_t_tea.shape[0]       # 1 read + 1 write (+ the stage table)
+    if inp.theta_stu is not None:
+        out["rewarp_student_fwd"] = 2 * hm * e_s + 72 * inp.y_t_stu.shape[0]
+        out["rewarp_student_bwd"] = 2 * hm * e_s + 72 * inp.y_t_stu.shape[0]   # grad read + grad write
     out["total"] = sum(out.values())
     return out
 
@@ -98,17 +112,22 @@ class HotPathStep:
         self.graph = None
         self.out = None
         self._graph_inputs = None
+        self.rewarp_kernels = 0
 
     @property
     def kernels_per_step(self) -> int:
         """Kernels of libudape_b200.so launched by run() (memset nodes for tickets/counters not counted):
         fused: 2 adain, decode, mask_select, loss_step, pck, ema;  unfused: 2 adain, decode+rectify,
-        mask_select, mse fwd/bwd, cons fwd/bwd, pck, ema."""
-        return 7 if self.fused else 10
+        mask_select, mse fwd/bwd, cons fwd/bwd, pck, ema;  + 3 with the re-warp tables (teacher forward,
+        student forward and backward)."""
+        return (7 if self.fused else 10) + self.rewarp_kernels
 
     def _streams(self, dev):
         if self._side is None or self._side[0].device != dev:
-            self._side = tuple(torch.cuda.Stream(dev) for _ in range(3))
+            # the heatmap chains are short, latency-bound kernels on the step's critical path: give them
+            # priority over the bandwidth-bound AdaIN / EMA launches when CTAs compete for SM slots
+            hi = -1 if os.environ.get("UDAPE_STEP_PRIORITY", "1") == "1" else 0
+            self._side = (torch.cuda.Stream(dev, priority=hi), torch.cuda.Stream(dev, priority=hi), torch.cuda.Stream(dev))
         return self._side
 
     # -- the step -----------------------------------------------------------------------------------
@@ -117,8 +136,9 @@ class HotPathStep:
         (launch/latency-bound at batch 32) and the EMA stream overlap the two large AdaIN passes:
 
             main   : AdaIN+mix s2t, AdaIN+mix t2s
-            teacher: decode -> k-th mask -> fused loss step (both criteria + both gradients)
-            student: PCK counts            [unfused: JointsMSELoss fwd -> bwd -> PCK]
+            teacher: [re-warp ->] decode -> k-th mask -> fused loss step (both criteria + both
+                     gradients) [-> re-warp backward of the consistency gradient]
+            student: [re-warp of y_t_stu ->] PCK counts      [unfused: JointsMSELoss fwd -> bwd -> PCK]
             ema    : multi-tensor EMA over the parameter list (after the join if ema_parallel=False)
 
         The fork/join is plain stream-event ordering, so it behaves the same eagerly and under
@@ -136,23 +156,47 @@ class HotPathStep:
                 # :438 — independent of every other chain of the hot path (in training it follows
                 # scaler.step(stu_optimizer); the student parameters are an input of this step)
                 self.ema.step()
+        self.rewarp_kernels = (1 if inp.theta_tea is not None else 0) + (2 if inp.theta_stu is not None else 0)
+        # the student's grids are built under autocast (:414): every stage samples on a half grid
+        stu_half = inp.y_t_stu.dtype in (torch.float16, torch.bfloat16)
+        stu_mask = (1 << inp.theta_stu.shape[1]) - 1 if (inp.theta_stu is not None and stu_half) else 0
+        stu_grid = inp.y_t_stu.dtype if stu_half else None
+        y_t_stu_recon, recon_ready = inp.y_t_stu, None
+        if inp.theta_stu is not None:
+            with torch.cuda.stream(s_stu), torch.no_grad():
+                # :417-423 — y_t_stu_recon (the backward runs after the loss step, below)
+                y_t_stu_recon = _rewarp.gather(inp.y_t_stu.detach(), inp.theta_stu, stu_mask, stu_grid)
+                if self.parallel:
+                    recon_ready = torch.cuda.Event()
+                    recon_ready.record(s_stu)
         with torch.cuda.stream(s_tea):
             with torch.no_grad():
+                y_t_tea = inp.y_t_tea
+                if inp.theta_tea is not None:
+                    # :359-372 — teacher heatmaps warped back to the un-augmented frame (k = 1 view)
+                    y_t_tea = _rewarp.gather(inp.y_t_tea, inp.theta_tea)
                 # train_human.py:376-383 and :427-430 — one decode pass + k-th value select
-                tt = teacher_targets(inp.y_t_tea, self.sigma, self.mask_ratio, occlude_thresh=self.occlude_thresh,
+                tt = teacher_targets(y_t_tea, self.sigma, self.mask_ratio, occlude_thresh=self.occlude_thresh,
                                      materialise=not self.fused)
+                if recon_ready is not None:
+                    s_tea.wait_event(recon_ready)
                 if self.fused:
                     # :425-436 — both criteria, loss_all and the scaled-backward seeds in one launch;
                     # the rectified teacher map (:428) is evaluated on the fly from the arg-max
-                    losses, g_s, g_c = fused_losses(inp.y_s, inp.label_s, inp.weight_s, inp.y_t_stu, None,
+                    losses, g_s, g_c = fused_losses(inp.y_s, inp.label_s, inp.weight_s, y_t_stu_recon, None,
                                                     tt["tea_mask"], lambda_c=self.lambda_c, grad_scale=self.loss_scale,
                                                     tea_preds=tt["preds"], sigma=self.sigma)
                     loss_all, loss_s, loss_c = losses[0], losses[1], losses[2]
             if not self.fused:
                 # :432 — consistency loss; its share of `scaler.scale(loss_all).backward()` (:434-436)
-                y_t_stu = inp.y_t_stu.detach().requires_grad_(True)
+                y_t_stu = y_t_stu_recon.detach().requires_grad_(True)
                 loss_c = cons_loss(y_t_stu, tt["rectified"], tea_mask=tt["tea_mask"])
                 (g_c,) = torch.autograd.grad(loss_c * (self.lambda_c * self.loss_scale), (y_t_stu,))
+            g_recon = g_c
+            if inp.theta_stu is not None:
+                with torch.no_grad():
+                    # backward of :417-423: the consistency gradient scattered back to the student's frame
+                    g_c = _rewarp.gather_backward(g_recon, inp.theta_stu, stu_mask, stu_grid)
         with torch.cuda.stream(s_stu):
             if not self.fused:
                 # :425 — supervised loss and its share of the scaled backward
@@ -182,7 +226,8 @@ class HotPathStep:
         return dict(t_s2t=t_s2t, t_t2s=t_t2s, conf_table=tt["conf_table"], position=tt["position"],
                     tea_mask=tt["tea_mask"], mask_thresh=tt["mask_thresh"], rectified=tt["rectified"],
                     tea_preds=tt["preds"], loss_s=loss_s, loss_c=loss_c, loss_all=loss_all,
-                    grad_y_s=g_s, grad_y_t_stu=g_c, pck_counts=counts, pred=pred)
+                    grad_y_s=g_s, grad_y_t_stu=g_c, grad_y_t_stu_recon=g_recon, y_t_tea_recon=y_t_tea,
+                    y_t_stu_recon=y_t_stu_recon, pck_counts=counts, pred=pred)
 
     def run_no_ema(self, inp: StepInputs) -> dict:
         return self._run(inp, with_ema=False)

@@ -32,7 +32,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["inverse_affine_matrix", "recon_stages", "stage_table", "gather", "student_recon", "teacher_recon",
+__all__ = ["inverse_affine_matrix", "recon_stages", "stage_table", "gather", "gather_backward", "student_recon", "teacher_recon",
            "affine_nearest", "occlusion_plan", "occlude_keypoints"]
 
 
@@ -170,15 +170,28 @@ class _Rewarp(torch.autograd.Function):
     def backward(ctx, grad_out):
         (theta,) = ctx.saved_tensors
         half_mask, grid_code = ctx.meta
-        g = grad_out.contiguous()
-        b, c, h, w = g.shape
-        grad_in = torch.empty_like(g)
-        dev = g.device
-        with _lib.on_device(dev):
-            st = _lib.load().udape_rewarp_bwd(g.data_ptr(), theta.data_ptr(), theta.shape[1], half_mask, grid_code,
-                                              b, c, h, w, _lib.float_code(g), grad_in.data_ptr(), _lib.stream_ptr(dev))
-        _lib.check(st, "udape_rewarp_bwd")
-        return grad_in, None, None, None
+        return _launch_bwd(grad_out.contiguous(), theta, half_mask, grid_code), None, None, None
+
+
+def _launch_bwd(g, theta, half_mask, grid_code):
+    b, c, h, w = g.shape
+    grad_in = torch.empty_like(g)
+    dev = g.device
+    with _lib.on_device(dev):
+        st = _lib.load().udape_rewarp_bwd(g.data_ptr(), theta.data_ptr(), theta.shape[1], half_mask, grid_code,
+                                          b, c, h, w, _lib.float_code(g), grad_in.data_ptr(), _lib.stream_ptr(dev))
+    _lib.check(st, "udape_rewarp_bwd")
+    return grad_in
+
+
+def gather_backward(grad_out: torch.Tensor, theta: torch.Tensor, half_mask: int = 0,
+                    grid_dtype: torch.dtype | None = None) -> torch.Tensor:
+    """Gradient of :func:`gather` w.r.t. its input for an upstream gradient ``grad_out`` (what autograd
+    calls; exposed for callers that drive the backward pass themselves, e.g. the fused loss step)."""
+    _lib.require_cuda(grad_out, theta)
+    _check_theta(grad_out, theta)
+    grid_code = _lib._DTYPE_CODE[grid_dtype] if grid_dtype is not None else _lib.F16
+    return _launch_bwd(grad_out.detach().contiguous(), theta.contiguous(), half_mask, grid_code)
 
 
 def gather(y: torch.Tensor, theta: torch.Tensor, half_mask: int = 0, grid_dtype: torch.dtype | None = None):
