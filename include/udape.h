@@ -245,17 +245,25 @@ UDAPE_API int udape_ema_multi(const udape_ema_chunk* chunks_dev, int64_t n_chunk
  * (sequential float32 sum, one division), written in `dtype`.
  * paste (optional, device int32 [B,6] = dst row0,row1,col0,col1, src row0,col0) is the patch copy
  * of :409, applied after `paste_after` evaluated stages.  active (optional, device uint8 [B],
- * views == 1): samples with 0 are copied through unchanged.  The gather cannot run in place. */
+ * views == 1): samples with 0 are copied through unchanged.  The gather cannot run in place.
+ * inverse_plan (optional, device, B * udape_rewarp_plan_elems(H, W, elem_bytes) uint16, 16-byte aligned):
+ * what autograd saves for the backward — the composed map of every sample inverted once (per source
+ * pixel its contributing output pixels), so that udape_rewarp_bwd is a plain gather.  Single view only. */
 UDAPE_API int udape_rewarp_fwd(const void* const* in, const float* const* theta, int views, int stages,
                      int half_mask, int grid_dtype, const int32_t* paste, int paste_after,
                      const uint8_t* active, int64_t B, int64_t C, int64_t H, int64_t W, int dtype,
-                     void* out, void* stream);
+                     void* out, uint16_t* inverse_plan, void* stream);
+/* uint16 elements per sample of the inverse plan for H x W planes of elem_bytes-sized elements;
+ * 0 if the plan route does not apply (planes above 4096 pixels, rows that are not 16-byte multiples). */
+UDAPE_API int64_t udape_rewarp_plan_elems(int64_t H, int64_t W, int elem_bytes);
 /* Gradient of the single-view re-warp w.r.t. its input: grad_in[s] = sum of grad_out[p] over
  * {p : source(p) = s}, float32 accumulation in ascending p (deterministic: the composed map is
- * inverted in shared memory with integer counting, no float atomics).  H*W <= 25600. */
+ * inverted in shared memory with integer counting, no float atomics).  H*W <= 25600.
+ * inverse_plan (optional): the plan udape_rewarp_fwd wrote for the same theta / shape / element size;
+ * the inversion is then skipped (same sums, same order, same bits). */
 UDAPE_API int udape_rewarp_bwd(const void* grad_out, const float* theta, int stages, int half_mask,
                      int grid_dtype, int64_t B, int64_t C, int64_t H, int64_t W, int dtype,
-                     void* grad_in, void* stream);
+                     void* grad_in, const uint16_t* inverse_plan, void* stream);
 
 #ifdef __cplusplus
 }

@@ -205,8 +205,10 @@ def test_rewarp_routes_agree(dev, dt, monkeypatch):
             one = RW._launch_fwd([ys[0]], [thetas[0]], half_mask, code, torch.empty_like(ys[0]))
             three = RW._launch_fwd(ys, thetas, half_mask, code, torch.empty_like(ys[0]))
             x = ys[0].clone().requires_grad_(True)
-            RW._Rewarp.apply(x, thetas[0], half_mask, code).backward(g)
-            res[route] = (one, three, x.grad)
+            RW._Rewarp.apply(x, thetas[0], half_mask, code).backward(g)   # inverse plan when the plane qualifies
+            noplan = RW._launch_bwd(g, thetas[0], half_mask, code, None)   # the backward inverts the map itself
+            res[route] = (one, three, x.grad, noplan)
+            assert torch.equal(x.grad, noplan)
         monkeypatch.delenv("UDAPE_REWARP_GLOBAL", raising=False)
         for r_s, r_g in zip(res["smem"], res["global"]):
             assert torch.equal(r_s, r_g), (b, k, h, w)
@@ -249,6 +251,7 @@ def test_rewarp_cluster_kernels_under_contention(dev):
     theta = t[0].to(dev)
     ref_f = RW.gather(y, theta, t[1], torch.float16)
     ref_b = RW.gather_backward(g, theta, t[1], torch.float16)
+    plans = [RW.inverse_plan_buffer(y) for _ in range(2)]
     torch.cuda.synchronize()
     hog_a, hog_b = torch.empty(64 << 20, device=dev), torch.empty(64 << 20, device=dev)
     streams = [torch.cuda.Stream(dev, priority=-1) for _ in range(2)]
@@ -257,9 +260,12 @@ def test_rewarp_cluster_kernels_under_contention(dev):
     for it in range(40):
         with torch.cuda.stream(hog):
             hog_b.copy_(hog_a)
-        for s_ in streams:
+        for s_, plan in zip(streams, plans):
             with torch.cuda.stream(s_):
                 outs.append((RW.gather(y, theta, t[1], torch.float16), RW.gather_backward(g, theta, t[1], torch.float16)))
+                # the plan route: forward + cluster-built inverse plan, then the plan-based backward
+                outs.append((RW.gather(y, theta, t[1], torch.float16, plan=plan),
+                             RW.gather_backward(g, theta, t[1], torch.float16, plan=plan)))
     torch.cuda.synchronize()
     for f, bw in outs:
         assert torch.equal(f, ref_f) and torch.equal(bw, ref_b)

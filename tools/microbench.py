@@ -280,22 +280,38 @@ def main():
             d = B(r)
             ia, ta = in_arr(d["tea"]), in_arr(t32)
             return lambda: chk(lib.udape_rewarp_fwd(ia, ta, 1, 3, 0, _lib.F16, None, 0, None, b, k, 64, 64, _lib.F32,
-                                                    d["rect"].data_ptr(), st()))
+                                                    d["rect"].data_ptr(), None, st()))
 
         def mk_rw16(r):
             d = B(r)
             ia, ta = in_arr(d["stu16"]), in_arr(t16)
             return lambda: chk(lib.udape_rewarp_fwd(ia, ta, 1, 3, 7, _lib.F16, None, 0, None, b, k, 64, 64, _lib.F16,
-                                                    d["grad16"].data_ptr(), st()))
+                                                    d["grad16"].data_ptr(), None, st()))
+
+        plan16 = torch.empty(b, lib.udape_rewarp_plan_elems(64, 64, 2), dtype=torch.int16, device=dev)
+
+        def mk_rw16p(r):   # forward that also writes the inverse plan (what autograd runs)
+            d = B(r)
+            ia, ta = in_arr(d["stu16"]), in_arr(t16)
+            return lambda: chk(lib.udape_rewarp_fwd(ia, ta, 1, 3, 7, _lib.F16, None, 0, None, b, k, 64, 64, _lib.F16,
+                                                    d["grad16"].data_ptr(), plan16.data_ptr(), st()))
 
         def mk_rwb(r):
             d = B(r)
             return lambda: chk(lib.udape_rewarp_bwd(d["stu16"].data_ptr(), t16.data_ptr(), 3, 7, _lib.F16, b, k, 64, 64, _lib.F16,
-                                                    d["grad16"].data_ptr(), st()))
+                                                    d["grad16"].data_ptr(), None, st()))
+
+        def mk_rwbp(r):
+            d = B(r)
+            return lambda: chk(lib.udape_rewarp_bwd(d["stu16"].data_ptr(), t16.data_ptr(), 3, 7, _lib.F16, b, k, 64, 64, _lib.F16,
+                                                    d["grad16"].data_ptr(), plan16.data_ptr(), st()))
 
         bench("rewarp_fwd f32 (teacher)", shape, 2 * hm32, mk_rw32, "rewarp")
         bench("rewarp_fwd f16 (student)", shape, 2 * hm16, mk_rw16, "rewarp")
-        bench("rewarp_bwd f16 (student)", shape, 2 * hm16, mk_rwb, "rewarp")
+        bench("rewarp_fwd f16 + inv. plan", shape, 2 * hm16 + plan16.numel() * 2, mk_rw16p, "rewarp")
+        bench("rewarp_bwd f16 (no plan)", shape, 2 * hm16, mk_rwb, "rewarp")
+        mk_rw16p(0)()   # a valid plan for the plan-based backward
+        bench("rewarp_bwd f16 (plan)", shape, 2 * hm16 + plan16.numel() * 2, mk_rwbp, "rewarp")
         bundles.clear()
 
     # ---- per-channel clamp of the stylised images (train_human.py:276) -----------------------------------

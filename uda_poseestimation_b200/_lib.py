@@ -74,9 +74,10 @@ PROTOTYPES = {
                                  c_int64, POINTER(EmaChunk), c_int64]),
     "udape_ema_multi": (c_int, [c_void_p, c_int64, c_int64, c_float, c_float, c_int, c_int, c_void_p]),
     "udape_rewarp_fwd": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p, c_int,
-                                 c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+                                 c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "udape_rewarp_plan_elems": (c_int64, [c_int64, c_int64, c_int]),
     "udape_rewarp_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int,
-                                 c_void_p, c_void_p]),
+                                 c_void_p, c_void_p, c_void_p]),
 }
 
 _lock = threading.Lock()

@@ -510,6 +510,234 @@ __device__ __forceinline__ void build_map_slice(const float* __restrict__ theta,
     }
 }
 
+// The composed map of one sample built and inverted by the whole cluster: every CTA computes its slice
+// of the map, pulls the peers' slices (DSMEM), inverts the map for ITS slice of the source pixels,
+// and the shares are then gathered so that every CTA ends up with the complete result:
+//   off[s]  = end of the list of source pixel s (start = off[s-1]) in lst[]
+//   lst[]   = the output pixels of every list, ascending, as padded byte offsets (row stride `stride`
+//             words, ES-byte elements).  lst aliases map.
+// Preconditions: off[] zeroed over (hw + 8) / 2 words, theta in shared memory, a CTA barrier passed.
+template <size_t ES>
+__device__ __forceinline__ void cluster_invert(cg::cluster_group& cluster, const float* __restrict__ s_theta,
+                                               const RewarpArgs& a, int stride, uint16_t* off, uint16_t* lst_loc,
+                                               uint16_t* map, uint32_t* s_scan) {
+    __shared__ uint32_t s_total, s_base[9], s_vbase[9];
+    const int nrank = static_cast<int>(cluster.num_blocks()), rank = static_cast<int>(cluster.block_rank());
+    const int hw = a.H * a.W;
+    uint16_t* lst = map;
+    // 1. the composed map: own slice, then the peers' through DSMEM
+    const int slice_log2 = ceil_log2((hw + nrank - 1) / nrank);
+    const int lo = min(hw, rank << slice_log2), hi = min(hw, (rank + 1) << slice_log2);
+    build_map_slice(s_theta, a, map, lo, hi);
+    cluster.sync();
+    pull_slices(cluster, map, hw, slice_log2, rank);
+    __syncthreads();
+    // 2. every CTA inverts the map for ITS slice of the source pixels only (list ends relative to the share)
+    {
+        const int W = a.W;
+        invert_map(map, hw, lo, hi, off + lo, lst_loc, s_scan, [=](int p) {
+            const int row = p / W;
+            return static_cast<uint16_t>(row * stride * 4 + (p - row * W) * static_cast<int>(ES));
+        });
+    }
+    if (threadIdx.x == 0) s_total = hi > lo ? off[hi - 1] : 0u;
+    cluster.sync();   // every share is complete (and nobody reads a peer's map any more: it becomes `lst`)
+    // 3. gather the shares: the lists of rank r follow those of the ranks below it
+    if (threadIdx.x == 0) {
+        uint32_t run = 0, vrun = 0;
+        for (int r = 0; r < 8; ++r) {
+            const uint32_t tot = r < nrank ? *cluster.map_shared_rank(&s_total, r) : 0u;
+            s_base[r] = run; s_vbase[r] = vrun;
+            run += tot; vrun += (tot + 7) / 8;
+        }
+        s_base[8] = run; s_vbase[8] = vrun;
+    }
+    pull_slices(cluster, off, hw, slice_log2, rank);
+    __syncthreads();
+    const int nvecs = static_cast<int>(s_vbase[8]);   // 8-entry vectors of every share, appended at the share's base
+    for (int g = threadIdx.x; g < nvecs; g += kRwThreads) {
+        int r = 0;
+#pragma unroll
+        for (int t = 1; t < 8; ++t) r += static_cast<uint32_t>(g) >= s_vbase[t] ? 1 : 0;
+        const uint32_t bs = s_base[r], tot = s_base[r + 1] - bs;
+        const int q0 = (g - static_cast<int>(s_vbase[r])) * 8;
+        const uint4 v4 = *reinterpret_cast<const uint4*>(cluster.map_shared_rank(lst_loc + q0, r));
+        const uint32_t w[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (static_cast<uint32_t>(q0 + e) < tot) lst[bs + q0 + e] = static_cast<uint16_t>(w[e >> 1] >> (16 * (e & 1)));
+    }
+    cluster.sync();   // the peers have pulled this CTA's list ends and lists: both may change / go away now
+    for (int s = threadIdx.x; s < hw; s += kRwThreads)   // list ends become absolute
+        off[s] = static_cast<uint16_t>(off[s] + s_base[s >> slice_log2]);
+    __syncthreads();
+}
+
+// the first four contributors of source pixel s as padded byte offsets (missing ones -> the zero word)
+__device__ __forceinline__ uint2 list_slots(const uint16_t* off, const uint16_t* lst, int s, uint32_t zero_byte, bool& overflow) {
+    const int st = s == 0 ? 0 : off[s - 1], en = off[s];
+    uint32_t o[4] = {zero_byte, zero_byte, zero_byte, zero_byte};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (st + q < en) o[q] = lst[st + q];
+    overflow = en - st > 4;
+    return make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
+}
+
+// Source pixels with more than four contributors (zoom factors above ~1.7; a few per cent of a plane at
+// most): the thread redoes exactly those of its pixels (bit k of `mask`), all entries in ascending
+// order, and overwrites the element it has just stored.
+template <typename T>
+__device__ __forceinline__ void redo_long_lists(uint32_t mask, const uint16_t* __restrict__ off, const uint16_t* __restrict__ lst,
+                                                const uint8_t* bytes, T* __restrict__ o) {
+    constexpr int EPW = 4 / static_cast<int>(sizeof(T));
+    while (mask) {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int s = ((k / EPW) * kRwThreads + threadIdx.x) * EPW + (k % EPW);
+        const int st = s == 0 ? 0 : off[s - 1], en = off[s];
+        float sum = 0.0f;
+        for (int q = st; q < en; ++q) sum += to_f32<T>(*reinterpret_cast<const T*>(bytes + lst[q]));
+        o[s] = from_f32<T>(sum);
+    }
+}
+
+// ---- the inverse plan: what the backward needs, computed once (by the forward) and kept in global memory
+// per sample, uint16:  hdr[8] = {stride, any list > 4 entries, any list > 2 entries, ...} | slots[hw][4] | off[hw8] | lst[hw8]
+__host__ __device__ inline int64_t plan_elems_for(int64_t hw) { return 8 + 4 * hw + 2 * ((hw + 7) & ~7ll); }
+
+// dynamic smem: uint16 off[hw + 8] | lst_loc[hw] | map[hw] (-> lst)
+template <int ES>
+__global__ void __launch_bounds__(kRwThreads)
+rewarp_inverse_plan_kernel(const RewarpArgs a, uint16_t* __restrict__ plan, int buf_words) {
+    constexpr int EPW = 4 / ES;
+    extern __shared__ __align__(16) uint32_t rw_smem[];
+    __shared__ float s_theta[kRwMaxStages * 6];
+    __shared__ uint32_t s_scan[kRwThreads];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int nrank = static_cast<int>(cluster.num_blocks()), rank = static_cast<int>(cluster.block_rank());
+    const int hw = a.H * a.W, hw8 = (hw + 7) & ~7;
+    uint16_t* off = reinterpret_cast<uint16_t*>(rw_smem);
+    uint16_t* lst_loc = off + ((hw + 8 + 7) & ~7);
+    uint16_t* map = lst_loc + hw8;
+    const uint16_t* lst = map;
+    const int b = blockIdx.x / nrank;
+    if (threadIdx.x < a.stages * 6)
+        s_theta[threadIdx.x] = a.view[0].theta[static_cast<int64_t>(b) * a.stages * 6 + threadIdx.x];
+    uint32_t* off32 = reinterpret_cast<uint32_t*>(off);
+    for (int s = threadIdx.x; s < (hw + 8) / 2; s += kRwThreads) off32[s] = 0u;
+    __syncthreads();
+    float J[4];
+    composed_jacobian(s_theta, a, J);
+    const float det = J[0] * J[3] - J[1] * J[2];
+    const float inv = det != 0.0f ? 1.0f / det : 0.0f;
+    const int stride = pick_stride(a.W / EPW, J[3] * inv, -J[2] * inv, EPW - 1);   // see rewarp_bwd_smem_kernel
+    cluster_invert<ES>(cluster, s_theta, a, stride, off, lst_loc, map, s_scan);
+    // every CTA writes its slice of the plan
+    uint16_t* P = plan + static_cast<int64_t>(b) * plan_elems_for(hw);
+    uint16_t* g_slots = P + 8;
+    uint16_t* g_off = g_slots + 4 * static_cast<int64_t>(hw);
+    uint16_t* g_lst = g_off + hw8;
+    const uint32_t zero_byte = static_cast<uint32_t>(buf_words - 4) * 4u;
+    const int slice_log2 = ceil_log2((hw + nrank - 1) / nrank);
+    const int lo = min(hw, rank << slice_log2), hi = min(hw, (rank + 1) << slice_log2);
+    for (int s = lo + threadIdx.x; s < hi; s += kRwThreads) {
+        bool overflow;
+        *reinterpret_cast<uint2*>(g_slots + 4 * static_cast<int64_t>(s)) = list_slots(off, lst, s, zero_byte, overflow);
+    }
+    for (int v = threadIdx.x; v < (hi - lo) / 8; v += kRwThreads) {
+        reinterpret_cast<uint4*>(g_off + lo)[v] = reinterpret_cast<const uint4*>(off + lo)[v];
+        reinterpret_cast<uint4*>(g_lst + lo)[v] = reinterpret_cast<const uint4*>(lst + lo)[v];
+    }
+    if (rank == 0) {
+        // the header: rank 0 looks at every list length (16 per thread)
+        bool any4 = false, any2 = false;
+        for (int s = threadIdx.x; s < hw; s += kRwThreads) {
+            const int len = off[s] - (s == 0 ? 0 : off[s - 1]);
+            any4 |= len > 4;
+            any2 |= len > 2;
+        }
+        const int f4 = __syncthreads_or(any4), f2 = __syncthreads_or(any2);
+        if (threadIdx.x < 8)
+            P[threadIdx.x] = threadIdx.x == 0 ? static_cast<uint16_t>(stride) : (threadIdx.x == 1 ? f4 : (threadIdx.x == 2 ? f2 : 0));
+    }
+}
+
+// backward from the plan: no cluster, no inversion — slots from global memory, gradient planes staged
+// through the padded ring.  dynamic smem: kRwRing plane buffers
+template <typename T>
+__global__ void __launch_bounds__(kRwThreads)   // (capping at 85 registers for 3 CTAs/SM spills and is slower: 17.6 vs 14.7 us)
+rewarp_bwd_plan_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __restrict__ gin, int buf_words,
+                       const uint16_t* __restrict__ plan) {
+    constexpr int EPW = 4 / static_cast<int>(sizeof(T));
+    constexpr int SLOTS = kRwPix / EPW;
+    extern __shared__ __align__(16) uint32_t rw_smem[];
+    const int hw = a.H * a.W, nwords = hw / EPW, hw8 = (hw + 7) & ~7;
+    const int groups = (a.C + a.cpc - 1) / a.cpc;
+    const int b = blockIdx.x / groups, cgp = blockIdx.x - b * groups;
+    const int c0 = cgp * a.cpc, c1 = min(a.C, c0 + a.cpc);
+    const uint16_t* P = plan + static_cast<int64_t>(b) * plan_elems_for(hw);
+    const uint16_t* g_slots = P + 8;
+    const uint16_t* g_off = g_slots + 4 * static_cast<int64_t>(hw);
+    const uint16_t* g_lst = g_off + hw8;
+    const int stride = P[0];
+    const bool any_overflow = P[1] != 0;
+    const bool deep = P[2] != 0;   // zoom-out samples: no source pixel has more than two contributors
+    if (threadIdx.x < kRwRing) rw_smem[threadIdx.x * buf_words + buf_words - 4] = 0u;   // the zero word of every buffer
+    const int row_words = a.W / EPW, vpr = row_words / 4, nvec = nwords / 4;
+    int so[kRwMaxVec];
+    stage_offsets(so, nvec, vpr, stride);
+    auto issue = [&](int it) {
+        stage_issue<T>(smem_u32(rw_smem + (it % kRwRing) * buf_words), so, gout + (static_cast<int64_t>(b) * a.C + c0 + it) * hw);
+    };
+    const int nitems = c1 - c0;
+#pragma unroll
+    for (int it = 0; it < kRwRing - 1; ++it) {
+        if (it < nitems) issue(it);
+        cp_async_commit();
+    }
+    uint2 slot[kRwPix];
+    uint32_t long_mask = 0;
+#pragma unroll
+    for (int k = 0; k < kRwPix; ++k) {
+        const int word = (k / EPW) * kRwThreads + threadIdx.x;
+        const int s = word * EPW + (k % EPW);
+        const uint32_t z = static_cast<uint32_t>(buf_words - 4) * 4u;
+        slot[k] = word < nwords ? __ldg(reinterpret_cast<const uint2*>(g_slots + 4 * static_cast<int64_t>(s)))
+                                : make_uint2(z | (z << 16), z | (z << 16));
+        if (any_overflow && word < nwords && g_off[s] - (s == 0 ? 0 : g_off[s - 1]) > 4) long_mask |= 1u << k;
+    }
+    for (int it = 0; it < nitems; ++it) {
+        cp_async_wait<kRwRing - 2>();
+        __syncthreads();
+        if (it + kRwRing - 1 < nitems) issue(it + kRwRing - 1);
+        cp_async_commit();
+        const uint8_t* bytes = reinterpret_cast<const uint8_t*>(rw_smem + (it % kRwRing) * buf_words);
+        T* o = gin + (static_cast<int64_t>(b) * a.C + c0 + it) * hw;
+#pragma unroll
+        for (int sl = 0; sl < SLOTS; ++sl) {
+            float f[EPW];
+#pragma unroll
+            for (int e = 0; e < EPW; ++e) {
+                const uint2 sq = slot[sl * EPW + e];
+                const float v0 = to_f32<T>(*reinterpret_cast<const T*>(bytes + (sq.x & 0xffffu)));
+                const float v1 = to_f32<T>(*reinterpret_cast<const T*>(bytes + (sq.x >> 16)));
+                float sum = v0 + v1;   // ascending p, fp32, one rounding to T
+                if (deep) {            // CTA-uniform
+                    const float v2 = to_f32<T>(*reinterpret_cast<const T*>(bytes + (sq.y & 0xffffu)));
+                    const float v3 = to_f32<T>(*reinterpret_cast<const T*>(bytes + (sq.y >> 16)));
+                    sum = (sum + v2) + v3;
+                }
+                f[e] = sum;
+            }
+            const int word = sl * kRwThreads + threadIdx.x;
+            if (word < nwords) store_word<T>(o, word, f);
+        }
+        redo_long_lists<T>(long_mask, g_off, g_lst, bytes, o);
+    }
+    cp_async_wait<0>();
+}
+
 // heatmap route (planes up to 4096 px): gradient planes staged through padded shared memory; the
 // CTAs of a sample form a cluster and build the composed map together (see rewarp_smem_kernel).
 // dynamic smem: kRwRing plane buffers | uint16 off[hw + 8] | lst_loc[hw] | map[hw] (-> lst)
@@ -531,7 +759,6 @@ rewarp_bwd_smem_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __rest
     uint16_t* lst_loc = off + ((hw + 8 + 7) & ~7);
     uint16_t* map = lst_loc + ((hw + 7) & ~7);
     uint16_t* lst = map;
-    __shared__ uint32_t s_total;
     const int b = blockIdx.x / nrank;
     const int c0 = min(a.C, rank * a.cpc), c1 = min(a.C, c0 + a.cpc);
     if (threadIdx.x < a.stages * 6)
@@ -559,57 +786,8 @@ rewarp_bwd_smem_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __rest
         if (it < nitems) issue(it);
         cp_async_commit();
     }
-    // 1. the composed map, built by the cluster together: own slice, then the peers' through DSMEM
-    const int slice_log2 = ceil_log2((hw + nrank - 1) / nrank);
-    const int lo = min(hw, rank << slice_log2), hi = min(hw, (rank + 1) << slice_log2);
-    build_map_slice(s_theta, a, map, lo, hi);
-    cluster.sync();
-    pull_slices(cluster, map, hw, slice_log2, rank);
-    __syncthreads();
-    // 2. every CTA inverts the map for ITS slice of the source pixels only (lists = padded BYTE offsets,
-    //    list ends relative to the start of the share)
-    {
-        const int W = a.W;
-        invert_map(map, hw, lo, hi, off + lo, lst_loc, s_scan, [=](int p) {
-            const int row = p / W;
-            return static_cast<uint16_t>(row * stride * 4 + (p - row * W) * static_cast<int>(sizeof(T)));
-        });
-    }
-    if (threadIdx.x == 0) s_total = hi > lo ? off[hi - 1] : 0u;
-    cluster.sync();   // every share is complete (and nobody reads a peer's map any more: it becomes `lst`)
-    // 3. gather the shares: the lists of rank r follow those of the ranks below it
-    {
-        __shared__ uint32_t s_base[9], s_vbase[9];
-        if (threadIdx.x == 0) {
-            uint32_t run = 0, vrun = 0;
-            for (int r = 0; r < 8; ++r) {
-                const uint32_t tot = r < nrank ? *cluster.map_shared_rank(&s_total, r) : 0u;
-                s_base[r] = run; s_vbase[r] = vrun;
-                run += tot; vrun += (tot + 7) / 8;
-            }
-            s_base[8] = run; s_vbase[8] = vrun;
-        }
-        pull_slices(cluster, off, hw, slice_log2, rank);
-        __syncthreads();
-        // lists: 8-entry vectors of every share, appended at the share's base
-        const int nvecs = static_cast<int>(s_vbase[8]);
-        for (int g = threadIdx.x; g < nvecs; g += kRwThreads) {
-            int r = 0;
-#pragma unroll
-            for (int t = 1; t < 8; ++t) r += static_cast<uint32_t>(g) >= s_vbase[t] ? 1 : 0;
-            const uint32_t bs = s_base[r], tot = s_base[r + 1] - bs;
-            const int q0 = (g - static_cast<int>(s_vbase[r])) * 8;
-            const uint4 v4 = *reinterpret_cast<const uint4*>(cluster.map_shared_rank(lst_loc + q0, r));
-            const uint32_t w[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-                if (static_cast<uint32_t>(q0 + e) < tot) lst[bs + q0 + e] = static_cast<uint16_t>(w[e >> 1] >> (16 * (e & 1)));
-        }
-        cluster.sync();   // the peers have pulled this CTA's list ends and lists: both may change / go away now
-        // list ends become absolute
-        for (int s = threadIdx.x; s < hw; s += kRwThreads) off[s] = static_cast<uint16_t>(off[s] + s_base[s >> slice_log2]);
-        __syncthreads();
-    }
+    // the composed map built and inverted by the cluster together: off[] = absolute list ends, lst[] = lists
+    cluster_invert<sizeof(T)>(cluster, s_theta, a, stride, off, lst_loc, map, s_scan);
     if (nitems > 0) {
         // The first four contributors of each source pixel this thread owns, as padded byte offsets in
         // registers (missing ones point at the zero word): the per-plane sum is four independent LDS
@@ -617,22 +795,15 @@ rewarp_bwd_smem_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __rest
         // factors above ~1.7) take the loop for the rest; the order stays ascending p either way.
         const uint32_t zero_byte = static_cast<uint32_t>(buf_words - 4) * 4u;
         uint2 slot[kRwPix];
-        bool overflow = false;
+        uint32_t long_mask = 0;
 #pragma unroll
         for (int k = 0; k < kRwPix; ++k) {
             const int word = (k / EPW) * kRwThreads + threadIdx.x;
-            const int s = word * EPW + (k % EPW);
-            uint32_t o[4] = {zero_byte, zero_byte, zero_byte, zero_byte};
-            if (word < nwords) {
-                const int st = s == 0 ? 0 : off[s - 1], en = off[s];
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (st + q < en) o[q] = lst[st + q];
-                overflow |= en - st > 4;
-            }
-            slot[k] = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
+            bool overflow = false;
+            slot[k] = word < nwords ? list_slots(off, lst, word * EPW + (k % EPW), zero_byte, overflow)
+                                    : make_uint2(zero_byte | (zero_byte << 16), zero_byte | (zero_byte << 16));
+            if (overflow) long_mask |= 1u << k;
         }
-        const bool any_overflow = __syncthreads_or(overflow);
         for (int it = 0; it < nitems; ++it) {
             cp_async_wait<kRwRing - 2>();
             __syncthreads();
@@ -655,20 +826,7 @@ rewarp_bwd_smem_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __rest
                 const int word = sl * kRwThreads + threadIdx.x;
                 if (word < nwords) store_word<T>(o, word, f);
             }
-            if (any_overflow) {
-                // rare: redo the pixels of this thread whose lists hold more than four entries (same order,
-                // all entries) and overwrite the element this thread has just stored
-                for (int k = 0; k < kRwPix; ++k) {
-                    const int word = (k / EPW) * kRwThreads + threadIdx.x;
-                    if (word >= nwords) continue;
-                    const int s = word * EPW + (k % EPW);
-                    const int st = s == 0 ? 0 : off[s - 1], en = off[s];
-                    if (en - st <= 4) continue;
-                    float sum = 0.0f;
-                    for (int q = st; q < en; ++q) sum += to_f32<T>(*reinterpret_cast<const T*>(bytes + lst[q]));
-                    o[s] = from_f32<T>(sum);
-                }
-            }
+            redo_long_lists<T>(long_mask, off, lst, bytes, o);
         }
     }
     cp_async_wait<0>();
@@ -823,7 +981,7 @@ using namespace udape;
 extern "C" int udape_rewarp_fwd(const void* const* in, const float* const* theta, int views, int stages,
                                 int half_mask, int grid_dtype, const int32_t* paste, int paste_after,
                                 const uint8_t* active, int64_t B, int64_t C, int64_t H, int64_t W, int dtype,
-                                void* out, void* stream) {
+                                void* out, uint16_t* inverse_plan, void* stream) {
     RewarpArgs a = {};
     UDAPE_REQUIRE(in && theta && out, UDAPE_ERR_NULL, "udape_rewarp_fwd: NULL pointer");
     const int rc = fill_common(a, "udape_rewarp_fwd", views, stages, half_mask, grid_dtype, B, C, H, W, dtype);
@@ -846,6 +1004,20 @@ extern "C" int udape_rewarp_fwd(const void* const* in, const float* const* theta
     const int64_t hw = H * W;
     cudaStream_t st = as_stream(stream);
     const int buf_words = (all16 && !paste && !active && !route_disabled()) ? smem_route_words(H, W, es) : 0;
+    if (inverse_plan) {
+        UDAPE_REQUIRE(views == 1 && !paste && !active && smem_route_words(H, W, es) != 0 && aligned16(inverse_plan),
+                      UDAPE_ERR_ARG, "udape_rewarp_fwd: an inverse plan needs a single view, no paste / pass-through and a "
+                      "plane udape_rewarp_plan_elems() accepts");
+        // what the backward needs (inverted map: slots + lists per source pixel), built once per batch
+        const int bw = smem_route_words(H, W, es);
+        const int n = cluster_size_for(B, 8, hw);
+        const size_t smem = sizeof(uint16_t) * (((hw + 8 + 7) & ~7ll) + 2 * ((hw + 7) & ~7ll));
+        const int r2 = es == 4 ? launch_cluster(rewarp_inverse_plan_kernel<4>, static_cast<unsigned>(B * n), static_cast<unsigned>(n),
+                                                smem, st, "udape_rewarp_fwd(plan)", a, inverse_plan, bw)
+                               : launch_cluster(rewarp_inverse_plan_kernel<2>, static_cast<unsigned>(B * n), static_cast<unsigned>(n),
+                                                smem, st, "udape_rewarp_fwd(plan)", a, inverse_plan, bw);
+        if (r2) return r2;
+    }
     if (buf_words) {
         // one cluster of `n` CTAs per sample: the channels are split n ways, the map is built once
         const int n = cluster_size_for(B, C, hw);
@@ -873,8 +1045,14 @@ extern "C" int udape_rewarp_fwd(const void* const* in, const float* const* theta
     return check_launch("udape_rewarp_fwd");
 }
 
+extern "C" int64_t udape_rewarp_plan_elems(int64_t H, int64_t W, int elem_bytes) {
+    if (H <= 0 || W <= 0 || (elem_bytes != 2 && elem_bytes != 4)) return 0;
+    return smem_route_words(H, W, elem_bytes) ? plan_elems_for(H * W) : 0;
+}
+
 extern "C" int udape_rewarp_bwd(const void* grad_out, const float* theta, int stages, int half_mask, int grid_dtype,
-                                int64_t B, int64_t C, int64_t H, int64_t W, int dtype, void* grad_in, void* stream) {
+                                int64_t B, int64_t C, int64_t H, int64_t W, int dtype, void* grad_in,
+                                const uint16_t* inverse_plan, void* stream) {
     RewarpArgs a = {};
     UDAPE_REQUIRE(grad_out && theta && grad_in, UDAPE_ERR_NULL, "udape_rewarp_bwd: NULL pointer");
     const int rc = fill_common(a, "udape_rewarp_bwd", 1, stages, half_mask, grid_dtype, B, C, H, W, dtype);
@@ -893,6 +1071,21 @@ extern "C" int udape_rewarp_bwd(const void* grad_out, const float* theta, int st
     // 16-bit arrays: smem route off[hw + 8] | lst_loc[hw] | map[hw]; general route off[hw + 2] | lst[hw] | map[hw]
     const size_t list_bytes = sizeof(uint16_t) * (((hw + 8 + 7) & ~7ll) + 2 * ((hw + 7) & ~7ll));
     const int buf_words = (aligned16(grad_out) && aligned16(grad_in) && !route_disabled()) ? smem_route_words(H, W, es) : 0;
+    if (inverse_plan) {
+        UDAPE_REQUIRE(smem_route_words(H, W, es) != 0 && aligned16(grad_out) && aligned16(grad_in) && aligned16(inverse_plan),
+                      UDAPE_ERR_ARG, "udape_rewarp_bwd: the inverse plan does not apply to this plane / alignment");
+        const int bw = smem_route_words(H, W, es);
+        a.cpc = channels_per_cta(B, C, 2 * static_cast<int64_t>(sm_count()));
+        const int64_t grid = B * ((C + a.cpc - 1) / a.cpc);
+        const size_t smem = kRwRing * sizeof(uint32_t) * static_cast<size_t>(bw);
+        UDAPE_DISPATCH_FLOAT(dtype, T, {
+            const int r2 = reserve_smem(rewarp_bwd_plan_kernel<T>, smem, "udape_rewarp_bwd");
+            if (r2) return r2;
+            rewarp_bwd_plan_kernel<T><<<static_cast<unsigned>(grid), kRwThreads, smem, st>>>(
+                a, static_cast<const T*>(grad_out), static_cast<T*>(grad_in), bw, inverse_plan);
+        });
+        return check_launch("udape_rewarp_bwd");
+    }
     UDAPE_DISPATCH_FLOAT(dtype, T, {
         if (buf_words) {
             const int n = cluster_size_for(B, C, hw);

@@ -118,8 +118,8 @@ class HotPathStep:
     def kernels_per_step(self) -> int:
         """Kernels of libudape_b200.so launched by run() (memset nodes for tickets/counters not counted):
         fused: 2 adain, decode, mask_select, loss_step, pck, ema;  unfused: 2 adain, decode+rectify,
-        mask_select, mse fwd/bwd, cons fwd/bwd, pck, ema;  + 3 with the re-warp tables (teacher forward,
-        student forward and backward)."""
+        mask_select, mse fwd/bwd, cons fwd/bwd, pck, ema;  + 4 with the re-warp tables (teacher forward,
+        student forward, its inverse plan, student backward)."""
         return (7 if self.fused else 10) + self.rewarp_kernels
 
     def _streams(self, dev):
@@ -156,7 +156,8 @@ class HotPathStep:
                 # :438 — independent of every other chain of the hot path (in training it follows
                 # scaler.step(stu_optimizer); the student parameters are an input of this step)
                 self.ema.step()
-        self.rewarp_kernels = (1 if inp.theta_tea is not None else 0) + (2 if inp.theta_stu is not None else 0)
+        # teacher forward; student forward + inverse plan + backward
+        self.rewarp_kernels = (1 if inp.theta_tea is not None else 0) + (3 if inp.theta_stu is not None else 0)
         # the student's grids are built under autocast (:414): every stage samples on a half grid
         stu_half = inp.y_t_stu.dtype in (torch.float16, torch.bfloat16)
         stu_mask = (1 << inp.theta_stu.shape[1]) - 1 if (inp.theta_stu is not None and stu_half) else 0
@@ -165,7 +166,9 @@ class HotPathStep:
         if inp.theta_stu is not None:
             with torch.cuda.stream(s_stu), torch.no_grad():
                 # :417-423 — y_t_stu_recon (the backward runs after the loss step, below)
-                y_t_stu_recon = _rewarp.gather(inp.y_t_stu.detach(), inp.theta_stu, stu_mask, stu_grid)
+                # (the forward also inverts the composed map once: the plan its backward gathers from)
+                stu_plan = _rewarp.inverse_plan_buffer(inp.y_t_stu)
+                y_t_stu_recon = _rewarp.gather(inp.y_t_stu.detach(), inp.theta_stu, stu_mask, stu_grid, plan=stu_plan)
                 if self.parallel:
                     recon_ready = torch.cuda.Event()
                     recon_ready.record(s_stu)
@@ -196,7 +199,7 @@ class HotPathStep:
             if inp.theta_stu is not None:
                 with torch.no_grad():
                     # backward of :417-423: the consistency gradient scattered back to the student's frame
-                    g_c = _rewarp.gather_backward(g_recon, inp.theta_stu, stu_mask, stu_grid)
+                    g_c = _rewarp.gather_backward(g_recon, inp.theta_stu, stu_mask, stu_grid, plan=stu_plan)
         with torch.cuda.stream(s_stu):
             if not self.fused:
                 # :425 — supervised loss and its share of the scaled backward

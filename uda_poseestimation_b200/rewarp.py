@@ -32,7 +32,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["inverse_affine_matrix", "recon_stages", "stage_table", "gather", "gather_backward", "student_recon", "teacher_recon",
+__all__ = ["inverse_affine_matrix", "recon_stages", "stage_table", "gather", "gather_backward", "inverse_plan_buffer", "student_recon", "teacher_recon",
            "affine_nearest", "occlusion_plan", "occlude_keypoints"]
 
 
@@ -135,7 +135,7 @@ def stage_table(stages, height: int, width: int, dtype: torch.dtype = torch.floa
     return table, half_mask, (_lib._DTYPE_CODE[ac] if ac is not None else _lib.F16)
 
 
-def _launch_fwd(views, thetas, half_mask, grid_code, out, paste=None, paste_after=0, active=None):
+def _launch_fwd(views, thetas, half_mask, grid_code, out, paste=None, paste_after=0, active=None, plan=None):
     y0 = views[0]
     b, c, h, w = y0.shape
     n = len(views)
@@ -145,7 +145,7 @@ def _launch_fwd(views, thetas, half_mask, grid_code, out, paste=None, paste_afte
     with _lib.on_device(dev):
         st = _lib.load().udape_rewarp_fwd(in_arr, th_arr, n, thetas[0].shape[1], half_mask, grid_code, _lib.ptr(paste),
                                           paste_after, _lib.ptr(active), b, c, h, w, _lib.float_code(y0),
-                                          out.data_ptr(), _lib.stream_ptr(dev))
+                                          out.data_ptr(), _lib.ptr(plan), _lib.stream_ptr(dev))
     _lib.check(st, "udape_rewarp_fwd")
     return out
 
@@ -159,53 +159,67 @@ def _check_theta(y, theta):
         raise ValueError("1 to 4 stages are supported")
 
 
+def inverse_plan_buffer(y: torch.Tensor) -> torch.Tensor | None:
+    """Device buffer for the inverse plan of a re-warp of ``y`` ([B,C,H,W]) — what the forward saves for
+    the backward (the composed map of every sample, inverted once) — or None when the plan route does
+    not apply to this plane size (the backward then inverts the map itself)."""
+    b, _, h, w = y.shape
+    n = _lib.load().udape_rewarp_plan_elems(h, w, y.element_size())
+    return torch.empty((b, n), dtype=torch.int16, device=y.device) if n > 0 else None
+
+
 class _Rewarp(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y, theta, half_mask, grid_code):
-        ctx.save_for_backward(theta)
+        plan = inverse_plan_buffer(y)
+        ctx.save_for_backward(theta, plan)
         ctx.meta = (half_mask, grid_code)
-        return _launch_fwd([y], [theta], half_mask, grid_code, torch.empty_like(y))
+        return _launch_fwd([y], [theta], half_mask, grid_code, torch.empty_like(y), plan=plan)
 
     @staticmethod
     def backward(ctx, grad_out):
-        (theta,) = ctx.saved_tensors
+        theta, plan = ctx.saved_tensors
         half_mask, grid_code = ctx.meta
-        return _launch_bwd(grad_out.contiguous(), theta, half_mask, grid_code), None, None, None
+        return _launch_bwd(grad_out.contiguous(), theta, half_mask, grid_code, plan), None, None, None
 
 
-def _launch_bwd(g, theta, half_mask, grid_code):
+def _launch_bwd(g, theta, half_mask, grid_code, plan=None):
     b, c, h, w = g.shape
     grad_in = torch.empty_like(g)
     dev = g.device
     with _lib.on_device(dev):
         st = _lib.load().udape_rewarp_bwd(g.data_ptr(), theta.data_ptr(), theta.shape[1], half_mask, grid_code,
-                                          b, c, h, w, _lib.float_code(g), grad_in.data_ptr(), _lib.stream_ptr(dev))
+                                          b, c, h, w, _lib.float_code(g), grad_in.data_ptr(), _lib.ptr(plan),
+                                          _lib.stream_ptr(dev))
     _lib.check(st, "udape_rewarp_bwd")
     return grad_in
 
 
 def gather_backward(grad_out: torch.Tensor, theta: torch.Tensor, half_mask: int = 0,
-                    grid_dtype: torch.dtype | None = None) -> torch.Tensor:
+                    grid_dtype: torch.dtype | None = None, plan: torch.Tensor | None = None) -> torch.Tensor:
     """Gradient of :func:`gather` w.r.t. its input for an upstream gradient ``grad_out`` (what autograd
-    calls; exposed for callers that drive the backward pass themselves, e.g. the fused loss step)."""
-    _lib.require_cuda(grad_out, theta)
+    calls; exposed for callers that drive the backward pass themselves, e.g. the fused loss step).
+    ``plan``: the inverse plan ``gather(..., plan=...)`` filled for the same ``theta``."""
+    _lib.require_cuda(grad_out, theta, plan)
     _check_theta(grad_out, theta)
     grid_code = _lib._DTYPE_CODE[grid_dtype] if grid_dtype is not None else _lib.F16
-    return _launch_bwd(grad_out.detach().contiguous(), theta.contiguous(), half_mask, grid_code)
+    return _launch_bwd(grad_out.detach().contiguous(), theta.contiguous(), half_mask, grid_code, plan)
 
 
-def gather(y: torch.Tensor, theta: torch.Tensor, half_mask: int = 0, grid_dtype: torch.dtype | None = None):
+def gather(y: torch.Tensor, theta: torch.Tensor, half_mask: int = 0, grid_dtype: torch.dtype | None = None,
+           plan: torch.Tensor | None = None):
     """``out[b,c,p] = y[b,c,source_b(p)]`` for a device stage table from :func:`stage_table`
     (differentiable w.r.t. ``y``; graph-capturable: ``theta`` is a device tensor that can be
-    refreshed between replays)."""
-    dev = _lib.require_cuda(y, theta)
+    refreshed between replays).  ``plan`` (from :func:`inverse_plan_buffer`): also fill the inverse
+    plan for a later :func:`gather_backward` — autograd does this by itself."""
+    dev = _lib.require_cuda(y, theta, plan)
     _check_theta(y, theta)
     y = y.contiguous()
     theta = theta.contiguous()
     grid_code = _lib._DTYPE_CODE[grid_dtype] if grid_dtype is not None else _lib.F16
     if y.requires_grad and torch.is_grad_enabled():
         return _Rewarp.apply(y, theta, half_mask, grid_code)
-    return _launch_fwd([y], [theta], half_mask, grid_code, torch.empty_like(y))
+    return _launch_fwd([y], [theta], half_mask, grid_code, torch.empty_like(y), plan=plan)
 
 
 def student_recon(y_t_stu: torch.Tensor, aug_param_stu, ratio: float, autocast="auto") -> torch.Tensor:
