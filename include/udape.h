@@ -229,6 +229,57 @@ UDAPE_API int64_t udape_ema_plan(void* const* dst, const void* const* src, const
 UDAPE_API int udape_ema_multi(const udape_ema_chunk* chunks_dev, int64_t n_chunks, int64_t chunk_elems,
                     float a, float b, int dtype, int mode, void* stream);
 
+/* ---- f2: student update + teacher EMA in one pass — train_human.py:436-440 -----------------
+ * Replaces  scaler.step(stu_optimizer); tea_optimizer.step()  (GradScaler.unscale_ + torch.optim.Adam
+ * / SGD(momentum=0.9, nesterov=True), train_human.py:136-139, + OldWeightEMA.step, utils.py:21-25).
+ * A chunk is a contiguous run of one float32 parameter tensor with its gradient, optimizer state and
+ * teacher copy.  udape_opt_plan (host-only, no CUDA) splits n_tensors tensors into chunks of
+ * <= chunk_elems elements like udape_ema_plan; grad / state1 / state2 / ema may be NULL tables or hold
+ * NULL entries (no gradient: the parameter is only folded into the EMA; no teacher: no EMA).
+ *   state1 = Adam exp_avg | SGD momentum buffer (NULL when momentum == 0),  state2 = Adam exp_avg_sq.
+ * udape_grad_check: *found_inf = 1.0f if any gradient element is non-finite else 0.0f (overwrites;
+ * the read-only half of torch._amp_foreach_non_finite_check_and_unscale_).  ws: 2 zeroed uint32 words,
+ * left zero.
+ * udape_student_step, per element and in torch's single-tensor op order:
+ *   g = grad * (1 / *grad_scale)                       (grad_scale NULL: g = grad)
+ *   g += weight_decay * p
+ *   Adam:  m += (1-beta1)(g-m);  v = beta2 v + (1-beta2) g^2;  p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+ *   SGD :  buf = step==1 ? g : momentum*buf + (1-dampening) g;  g = nesterov ? g + momentum*buf : buf;  p -= lr g
+ *   ema = fl(fl(ema*ema_a) + fl(p*ema_b))              (the updated p, three roundings like utils.py:24-25)
+ * bc1 = 1-beta1^step, bc2 = 1-beta2^step in double.  step = *step_dev + 1 when step_dev is given (the
+ * counter is advanced by the launch, ticket = one zeroed self-resetting uint32), else hyper->step
+ * (1-based).  lr_dev (optional) overrides hyper->lr from device memory (CUDA-graph replays across
+ * MultiStepLR milestones).  If *found_inf != 0 the student, its state and the step counter are left
+ * untouched and only the EMA runs, as scaler.step() + tea_optimizer.step() do.  float32 only. */
+enum { UDAPE_OPT_ADAM = 0, UDAPE_OPT_SGD = 1 };
+typedef struct udape_opt_chunk {
+    void* param;
+    const void* grad;
+    void* state1;
+    void* state2;
+    void* ema;
+    int64_t numel;
+} udape_opt_chunk;
+typedef struct udape_opt_hyper {
+    double lr;
+    double beta1;        /* Adam beta1 | SGD momentum */
+    double beta2;        /* Adam beta2 | SGD dampening */
+    double eps;
+    double weight_decay;
+    float ema_a, ema_b;  /* teacher = teacher*ema_a + student*ema_b */
+    int32_t step;        /* 1-based number of this update (ignored when step_dev is given) */
+    int32_t nesterov;
+} udape_opt_hyper;
+
+UDAPE_API int64_t udape_opt_plan(void* const* param, const void* const* grad, void* const* state1,
+                       void* const* state2, void* const* ema, const int64_t* numel, int64_t n_tensors,
+                       int64_t chunk_elems, udape_opt_chunk* out, int64_t capacity);
+UDAPE_API int udape_grad_check(const udape_opt_chunk* chunks_dev, int64_t n_chunks, float* found_inf,
+                     uint32_t* ws, void* stream);
+UDAPE_API int udape_student_step(const udape_opt_chunk* chunks_dev, int64_t n_chunks, int algo,
+                       const udape_opt_hyper* hyper, const float* lr_dev, const float* grad_scale,
+                       const float* found_inf, int32_t* step_dev, uint32_t* ticket, void* stream);
+
 /* ---- f1: batched multi-stage nearest-neighbour affine re-warp ------------------------------
  * Replaces the per-sample loops of train_human.py:361-372 (teacher recon: k views x three
  * tF.affine(nearest) calls, mean over views), :418-423 (student recon under autocast, needs
@@ -248,7 +299,9 @@ UDAPE_API int udape_ema_multi(const udape_ema_chunk* chunks_dev, int64_t n_chunk
  * views == 1): samples with 0 are copied through unchanged.  The gather cannot run in place.
  * inverse_plan (optional, device, B * udape_rewarp_plan_elems(H, W, elem_bytes) uint16, 16-byte aligned):
  * what autograd saves for the backward — the composed map of every sample inverted once (per source
- * pixel its contributing output pixels), so that udape_rewarp_bwd is a plain gather.  Single view only. */
+ * pixel its contributing output pixels), so that udape_rewarp_bwd is a plain gather.  Single view only.
+ * out == NULL with an inverse_plan builds the plan alone (in[0] may then be NULL too: the plan depends
+ * only on theta and the shape), e.g. on a second stream beside the gather. */
 UDAPE_API int udape_rewarp_fwd(const void* const* in, const float* const* theta, int views, int stages,
                      int half_mask, int grid_dtype, const int32_t* paste, int paste_after,
                      const uint8_t* active, int64_t B, int64_t C, int64_t H, int64_t W, int dtype,

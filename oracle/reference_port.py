@@ -332,6 +332,88 @@ def model_ema_update(ema_tensors, model_tensors, decay, ema_buffers=(), model_bu
 
 
 # --------------------------------------------------------------------------------------------------
+# f2  student update + teacher EMA  (train_human.py:136-141, :436-440)
+# --------------------------------------------------------------------------------------------------
+# ``scaler.step(stu_optimizer); tea_optimizer.step(); scaler.update()``.  The optimizers are
+# torch.optim.Adam(lr) / torch.optim.SGD(lr, momentum=0.9, weight_decay=1e-4, nesterov=True)
+# (un-vendored torch; this image has 2.11).  Restated below from torch/optim/adam.py
+# ``_single_tensor_adam``, torch/optim/sgd.py ``_single_tensor_sgd`` and torch/amp/grad_scaler.py
+# (``_unscale_grads_`` / ``_maybe_opt_step``); pinned against those classes run on the CPU together
+# with the reference's OldWeightEMA by tests/golden/make_golden.py (fixture ``optim.npz``).
+
+
+def unscale_and_check(grads, scale):
+    """GradScaler.unscale_: inv_scale = scale.double().reciprocal().float(); grad *= inv_scale;
+    found_inf = any non-finite element (checked on the scaled gradient, like the ATen kernel)."""
+    inv_scale = torch.as_tensor(scale, dtype=torch.float32).double().reciprocal().float()
+    found_inf = False
+    out = []
+    for g in grads:
+        if g is None:
+            out.append(None)
+            continue
+        found_inf = found_inf or not bool(torch.isfinite(g).all())
+        out.append(g * inv_scale)
+    return out, found_inf
+
+
+def adam_step(params, grads, exp_avgs, exp_avg_sqs, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    """torch/optim/adam.py::_single_tensor_adam (amsgrad=False, maximize=False); ``step`` is the
+    1-based number of this update.  In place on params / exp_avgs / exp_avg_sqs."""
+    beta1, beta2 = betas
+    for param, grad, exp_avg, exp_avg_sq in zip(params, grads, exp_avgs, exp_avg_sqs):
+        if grad is None:
+            continue
+        if weight_decay != 0:
+            grad = grad.add(param, alpha=weight_decay)
+        exp_avg.lerp_(grad, 1 - beta1)
+        exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+        bias_correction1 = 1 - beta1 ** step
+        bias_correction2 = 1 - beta2 ** step
+        step_size = lr / bias_correction1
+        bias_correction2_sqrt = bias_correction2 ** 0.5
+        denom = (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
+        param.addcdiv_(exp_avg, denom, value=-step_size)
+
+
+def sgd_step(params, grads, bufs, step, lr, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False):
+    """torch/optim/sgd.py::_single_tensor_sgd; ``bufs[i]`` is the momentum buffer (ignored on the
+    first update, where torch clones the gradient into it).  In place."""
+    for i, (param, grad) in enumerate(zip(params, grads)):
+        if grad is None:
+            continue
+        if weight_decay != 0:
+            grad = grad.add(param, alpha=weight_decay)
+        if momentum != 0:
+            buf = bufs[i]
+            if step == 1:
+                buf.copy_(grad)
+            else:
+                buf.mul_(momentum).add_(grad, alpha=1 - dampening)
+            grad = grad.add(buf, alpha=momentum) if nesterov else buf
+        param.add_(grad, alpha=-lr)
+
+
+def student_teacher_step(algo, student, grads, state1, state2, teacher, step, scale, ema_alpha, **hyper):
+    """train_human.py:436-438 on tensor lists: unscale + non-finite check, the optimizer update unless
+    a gradient was non-finite (GradScaler._maybe_opt_step), then OldWeightEMA.step with the (possibly
+    unchanged) student.  Returns (found_inf, step after the call)."""
+    with torch.no_grad():
+        if scale is not None:
+            grads, found_inf = unscale_and_check(grads, scale)
+        else:
+            found_inf = False
+        if not found_inf:
+            step += 1
+            if algo == "adam":
+                adam_step(student, grads, state1, state2, step, **hyper)
+            else:
+                sgd_step(student, grads, state1, step, **hyper)
+        ema_step(teacher, student, ema_alpha)
+    return found_inf, step
+
+
+# --------------------------------------------------------------------------------------------------
 # f1  affine re-warp loops  (train_human.py:359-372, :385-412, :418-423; same in train_animal.py)
 # --------------------------------------------------------------------------------------------------
 # The reference calls torchvision's ``tF.affine`` (an un-vendored, un-pinned dependency; this image

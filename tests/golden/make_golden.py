@@ -286,6 +286,60 @@ def golden_ema():
     save("ema", **out)
 
 
+def golden_optim():
+    """train_human.py:136-141 + :436-440 on the CPU: torch.optim.Adam / SGD(nesterov) + the reference's
+    OldWeightEMA driven through torch.amp.GradScaler (scaled gradients are assigned directly; one step
+    carries an inf and must be skipped by scaler.step while the EMA still runs)."""
+    ut = ref_loader.load("utils")
+    out = {}
+
+    def make(seed):
+        torch.manual_seed(seed)
+        return torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.BatchNorm2d(8), torch.nn.Conv2d(8, 5, 1),
+                                   torch.nn.Linear(7, 3))
+
+    def flat(ts):
+        return np.concatenate([t.detach().numpy().ravel() for t in ts])
+
+    configs = {
+        "adam": lambda ps: torch.optim.Adam(ps, lr=1e-3),                               # train_human.py:139
+        "adamwd": lambda ps: torch.optim.Adam(ps, lr=3e-4, betas=(0.8, 0.99), eps=1e-6, weight_decay=1e-2),
+        "sgd": lambda ps: torch.optim.SGD(ps, lr=0.1, momentum=0.9, weight_decay=0.0001, nesterov=True),  # :137
+        "sgdplain": lambda ps: torch.optim.SGD(ps, lr=0.05, momentum=0.8, dampening=0.1),
+    }
+    n_steps, bad_step = 5, 2
+    for tag, mk in configs.items():
+        teacher, student = make(1), make(2)
+        opt = mk(student.parameters())
+        tea = ut.OldWeightEMA(teacher, student, alpha=0.99)
+        scaler = torch.amp.GradScaler("cpu", init_scale=1024.0, growth_interval=2)
+        out[f"{tag}_student0"] = flat(student.parameters())
+        g = torch.Generator().manual_seed(11)
+        for step in range(n_steps):
+            scale = float(scaler.scale(torch.ones(())))   # initialises / reads the current scale
+            grads = [torch.randn(p.shape, generator=g) * 0.1 * scale for p in student.parameters()]
+            if step == bad_step:
+                grads[2].view(-1)[3] = float("inf")
+            for p, gr in zip(student.parameters(), grads):
+                p.grad = gr.clone()
+            out[f"{tag}_scale{step}"] = np.float32(scale)
+            out[f"{tag}_grads{step}"] = flat(grads)
+            scaler.step(opt)       # :437
+            tea.step()             # :438
+            scaler.update()        # :440
+            out[f"{tag}_student{step + 1}"] = flat(student.parameters())
+            out[f"{tag}_teacher{step + 1}"] = flat(teacher.parameters())
+        st = [opt.state[p] for p in student.parameters()]
+        if tag.startswith("adam"):
+            out[f"{tag}_exp_avg"] = flat([x["exp_avg"] for x in st])
+            out[f"{tag}_exp_avg_sq"] = flat([x["exp_avg_sq"] for x in st])
+            out[f"{tag}_steps"] = np.float32(st[0]["step"].item())
+        else:
+            out[f"{tag}_momentum_buffer"] = flat([x["momentum_buffer"] for x in st])
+        out[f"{tag}_final_scale"] = np.float32(scaler.get_scale())
+    save("optim", **out)
+
+
 def golden_clamp():
     """train_human.py:276 verbatim, with both trainers' recover_min/max constants (:32-33, train_animal.py:34-35)."""
     out = {}
@@ -419,7 +473,7 @@ def main():
     torch.manual_seed(0)
     np.random.seed(0)
     fns = (golden_adain, golden_decode, golden_accuracy, golden_losses, golden_masks, golden_rectify,
-           golden_targets, golden_ema, golden_clamp, golden_rewarp)
+           golden_targets, golden_ema, golden_optim, golden_clamp, golden_rewarp)
     only = set(sys.argv[1:])  # e.g. `make_golden.py clamp` regenerates one fixture
     for fn in fns:
         if not only or fn.__name__.removeprefix("golden_") in only:

@@ -238,6 +238,61 @@ def test_ema_golden(golden, dev):
     np.testing.assert_array_equal(_flat(mema.ema.parameters()), g["mema_after_momentum"])
 
 
+OPTIM_CASES = {
+    "adam": (U.Adam, dict(lr=1e-3)),
+    "adamwd": (U.Adam, dict(lr=3e-4, betas=(0.8, 0.99), eps=1e-6, weight_decay=1e-2)),
+    "sgd": (U.SGD, dict(lr=0.1, momentum=0.9, weight_decay=0.0001, nesterov=True)),
+    "sgdplain": (U.SGD, dict(lr=0.05, momentum=0.8, dampening=0.1)),
+}
+
+
+@pytest.mark.parametrize("fuse", [True, False])
+@pytest.mark.parametrize("tag", sorted(OPTIM_CASES))
+def test_student_step_golden(golden, dev, tag, fuse):
+    """train_human.py:436-440 through the drop-in classes, in the reference's call order:
+    scaler.step(stu_optimizer); tea_optimizer.step(); scaler.update().  Fixture = torch.optim + the
+    reference's OldWeightEMA + torch.amp.GradScaler on the CPU, incl. one step with an inf gradient."""
+    g = golden("optim")
+    cls, kw = OPTIM_CASES[tag]
+    teacher, student = _make(1, dev), _make(2, dev)
+    _load_flat(student.parameters(), g[f"{tag}_student0"])
+    opt = cls(student.parameters(), **kw)
+    tea = U.OldWeightEMA(teacher, student, alpha=0.99)
+    if fuse:
+        opt.attach_teacher(tea)
+    scaler = U.GradScaler(init_scale=1024.0, growth_interval=2)
+    ptrs = [p.data_ptr() for p in list(student.parameters()) + list(teacher.parameters())]
+    for p in student.parameters():
+        p.grad = torch.zeros_like(p)
+    for it in range(5):
+        scale = float(scaler.scale(torch.ones((), device=dev)))
+        assert scale == float(g[f"{tag}_scale{it}"])
+        off = 0
+        for p in student.parameters():
+            n = p.numel()
+            p.grad.copy_(torch.from_numpy(g[f"{tag}_grads{it}"][off:off + n]).view(p.shape))
+            off += n
+        scaler.step(opt)
+        tea.step()
+        scaler.update()
+        assert_close_scaled(_flat(student.parameters()), g[f"{tag}_student{it + 1}"], RTOL, f"student after step {it}")
+        assert_close_scaled(_flat(teacher.parameters()), g[f"{tag}_teacher{it + 1}"], RTOL, f"teacher after step {it}")
+        if it == 2:  # the inf step: the student must be bit-identical to the previous state
+            np.testing.assert_array_equal(_flat(student.parameters()), _prev)
+        _prev = _flat(student.parameters())
+    assert scaler.get_scale() == float(g[f"{tag}_final_scale"])
+    assert opt.applied_steps() == 4
+    assert ptrs == [p.data_ptr() for p in list(student.parameters()) + list(teacher.parameters())]
+    st = [opt.state[p] for p in student.parameters()]
+    if tag.startswith("adam"):
+        assert_close_scaled(_flat([x["exp_avg"] for x in st]), g[f"{tag}_exp_avg"], RTOL, "exp_avg")
+        assert_close_scaled(_flat([x["exp_avg_sq"] for x in st]), g[f"{tag}_exp_avg_sq"], RTOL, "exp_avg_sq")
+        sd = opt.state_dict()
+        assert float(sd["state"][0]["step"]) == float(g[f"{tag}_steps"])
+    else:
+        assert_close_scaled(_flat([x["momentum_buffer"] for x in st]), g[f"{tag}_momentum_buffer"], RTOL, "momentum_buffer")
+
+
 @pytest.mark.parametrize("tag", ["human", "animal"])
 def test_channel_clamp_golden(golden, dev, tag):
     g = golden("clamp")

@@ -161,6 +161,43 @@ def test_ema(golden):
     np.testing.assert_array_equal(np.concatenate([t.numpy().ravel() for t in ema]), g["mema_after"])
 
 
+OPTIM_CASES = {
+    "adam": ("adam", dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)),
+    "adamwd": ("adam", dict(lr=3e-4, betas=(0.8, 0.99), eps=1e-6, weight_decay=1e-2)),
+    "sgd": ("sgd", dict(lr=0.1, momentum=0.9, dampening=0.0, weight_decay=0.0001, nesterov=True)),
+    "sgdplain": ("sgd", dict(lr=0.05, momentum=0.8, dampening=0.1, weight_decay=0.0, nesterov=False)),
+}
+OPTIM_SHAPES = [(8, 3, 3, 3), (8,), (8,), (8,), (5, 8, 1, 1), (5,), (3, 7), (3,)]
+
+
+@pytest.mark.parametrize("tag", sorted(OPTIM_CASES))
+def test_student_teacher_step(golden, tag):
+    """scaler.step(Adam | SGD) + OldWeightEMA.step + scaler.update() as run by torch on the CPU
+    (train_human.py:436-440): the restatement must reproduce every intermediate state exactly."""
+    g = golden("optim")
+    algo, hyper = OPTIM_CASES[tag]
+    protos = [torch.empty(s) for s in OPTIM_SHAPES]
+    student = _split_like(g[f"{tag}_student0"], protos)
+    teacher = [s.clone() for s in student]                      # OldWeightEMA.__init__ (utils.py:18-19)
+    state1 = [torch.zeros_like(s) for s in student]
+    state2 = [torch.zeros_like(s) for s in student]
+    step, skipped = 0, []
+    for it in range(5):
+        grads = _split_like(g[f"{tag}_grads{it}"], protos)
+        found_inf, step = R.student_teacher_step(algo, student, grads, state1, state2, teacher, step,
+                                                 float(g[f"{tag}_scale{it}"]), 0.99, **hyper)
+        skipped.append(found_inf)
+        np.testing.assert_array_equal(np.concatenate([t.numpy().ravel() for t in student]), g[f"{tag}_student{it + 1}"])
+        np.testing.assert_array_equal(np.concatenate([t.numpy().ravel() for t in teacher]), g[f"{tag}_teacher{it + 1}"])
+    assert skipped == [False, False, True, False, False] and step == 4
+    if algo == "adam":
+        np.testing.assert_array_equal(np.concatenate([t.numpy().ravel() for t in state1]), g[f"{tag}_exp_avg"])
+        np.testing.assert_array_equal(np.concatenate([t.numpy().ravel() for t in state2]), g[f"{tag}_exp_avg_sq"])
+        assert float(g[f"{tag}_steps"]) == 4.0
+    else:
+        np.testing.assert_array_equal(np.concatenate([t.numpy().ravel() for t in state1]), g[f"{tag}_momentum_buffer"])
+
+
 @pytest.mark.parametrize("tag", ["human", "animal"])
 def test_channel_clamp(golden, tag):
     g = golden("clamp")

@@ -344,6 +344,70 @@ def main():
     big_b = torch.empty(n_params, device=dev)
     bench("torch copy_ (reference pt)", f"{n_params} f32", 2 * n_params * 4, lambda r: (lambda: big_b.copy_(big_a)), "ema")
 
+    # ---- student step: unscale + Adam | SGD + teacher EMA in one launch (train_human.py:436-438) ---------
+    if not only or "optim" in only:
+        import uda_poseestimation_b200 as U
+
+        class Bag(torch.nn.Module):
+            def __init__(self, tensors):
+                super().__init__()
+                self.ps = torch.nn.ParameterList([torch.nn.Parameter(t) for t in tensors])
+
+        stu, tea_m = Bag(student), Bag(teacher)
+        for p_ in stu.parameters():
+            p_.grad = torch.randn_like(p_) * 65.536
+        scale_t = torch.full((), 65536.0, device=dev)
+        for label, mk_opt, passes in (("adam+ema", lambda: U.Adam(stu.parameters(), lr=1e-3), 9),
+                                      ("sgd-nesterov+ema", lambda: U.SGD(stu.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4,
+                                                                         nesterov=True), 7)):
+            opt = mk_opt()
+            ema_o = U.OldWeightEMA(tea_m, stu, alpha=0.999)
+            opt.attach_teacher(ema_o)
+            opt.grad_scale, opt.found_inf = scale_t, opt.check_grads()
+            opt.step()   # builds tables / state outside the timed (and captured) region
+
+            def mk_step(r, opt=opt, ema_o=ema_o):
+                def go():
+                    opt.step()
+                    ema_o.step()
+                return go
+
+            bench(f"student_step {label}", f"PoseResNet-101 {n_params}", passes * n_params * 4, mk_step, "optim")
+            if label.startswith("adam"):
+                bench("grad_check (found_inf)", f"PoseResNet-101 {n_params}", n_params * 4,
+                      lambda r, opt=opt: (lambda: opt.check_grads()), "optim")
+            del opt.grad_scale, opt.found_inf
+            del opt, ema_o
+        # what the reference runs on the same device: GradScaler.unscale_ + foreach Adam + per-tensor EMA
+        ref_opt = torch.optim.Adam(stu.parameters(), lr=1e-3)
+        ref_opt.step()
+        inv = torch.full((), 1.0 / 65536.0, device=dev)
+        finf = torch.zeros((), device=dev)
+        grads_l = [p_.grad for p_ in stu.parameters()]
+        tps, sps = list(tea_m.parameters()), list(stu.parameters())
+
+        def ref_step():
+            torch._amp_foreach_non_finite_check_and_unscale_(grads_l, finf, inv)
+            ref_opt.step()
+            with torch.no_grad():
+                for tp, sp in zip(tps, sps):          # utils.py:21-25
+                    tp.data.mul_(0.999)
+                    tp.data.add_(sp.data * 0.001)
+
+        if not args.no_sustained:
+            for _ in range(2):
+                ref_step()
+            torch.cuda.synchronize()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ts = []
+            for _ in range(5):
+                a_.record(); ref_step(); b_.record(); torch.cuda.synchronize()
+                ts.append(a_.elapsed_time(b_))
+            t_ref = float(np.median(ts))
+            rows.append(dict(kernel="torch eager: unscale_ + Adam(foreach) + OldWeightEMA loop", shape=f"PoseResNet-101 {n_params}",
+                             mbytes=9 * n_params * 4 / 1e6, us=t_ref * 1e3, note="host-launched eager sequence, wall time on the stream"))
+            print(f"{'torch eager unscale+Adam+EMA':<28}{'PoseResNet-101':<26}{9 * n_params * 4 / 1e6:9.1f} MB {t_ref * 1e3:8.1f} us", flush=True)
+
     out = Path(args.out)
     out.parent.mkdir(parents=True, exist_ok=True)
     out.write_text(json.dumps(dict(peak_gbs=peak, device=torch.cuda.get_device_name(0), iters=args.iters,

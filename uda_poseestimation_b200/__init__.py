@@ -18,6 +18,8 @@ Reference name → module here
     train_human.py:359-372,417-423 (inline)    : teacher_recon, student_recon (three tF.affine calls per
                                                  sample → one gather launch, with backward)
     train_human.py:385-412 (inline)            : occlude_keypoints;  affine_nearest = batched tF.affine
+    train_human.py:136-141,260,436-440         : Adam, SGD, GradScaler (torch.optim / torch.cuda.amp drop-ins:
+                                                 unscale + update + teacher EMA in one multi-tensor launch)
 """
 from ._lib import UdapeError, library_path, load as load_library
 from .adain import adain, adain_mix, adaptive_instance_normalization, calc_mean_std, channel_clamp
@@ -28,6 +30,7 @@ from .keypoint_detection import (accuracy, accuracy_from_counts, calc_dists, dec
                                  get_max_preds_torch, pck_counts)
 from .loss import ConsLoss, JointsMSELoss, cons_loss, fused_losses, joints_mse_loss
 from .mask import confidence_mask, consistency_mask, teacher_targets
+from .optim import SGD, Adam, GradScaler
 from .rewarp import affine_nearest, occlude_keypoints, student_recon, teacher_recon
 
 __version__ = "0.1.0"
@@ -42,4 +45,5 @@ __all__ = [
     "confidence_mask", "consistency_mask", "teacher_targets",
     "OldWeightEMA", "ModelEMA", "MultiTensorPlan",
     "teacher_recon", "student_recon", "occlude_keypoints", "affine_nearest",
+    "Adam", "SGD", "GradScaler",
 ]

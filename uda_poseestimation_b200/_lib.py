@@ -39,6 +39,20 @@ class EmaChunk(ctypes.Structure):
     _fields_ = [("dst", c_void_p), ("src", c_void_p), ("numel", c_int64)]
 
 
+class OptChunk(ctypes.Structure):
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("state1", c_void_p), ("state2", c_void_p),
+                ("ema", c_void_p), ("numel", c_int64)]
+
+
+class OptHyper(ctypes.Structure):
+    _fields_ = [("lr", c_double), ("beta1", c_double), ("beta2", c_double), ("eps", c_double),
+                ("weight_decay", c_double), ("ema_a", c_float), ("ema_b", c_float),
+                ("step", ctypes.c_int32), ("nesterov", ctypes.c_int32)]
+
+
+OPT_ADAM, OPT_SGD = 0, 1
+
+
 # name -> (restype, argtypes); must list every UDAPE_API symbol of include/udape.h
 PROTOTYPES = {
     "udape_version": (c_int, []),
@@ -73,6 +87,11 @@ PROTOTYPES = {
     "udape_ema_plan": (c_int64, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_int64, c_int64,
                                  c_int64, POINTER(EmaChunk), c_int64]),
     "udape_ema_multi": (c_int, [c_void_p, c_int64, c_int64, c_float, c_float, c_int, c_int, c_void_p]),
+    "udape_opt_plan": (c_int64, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                                 POINTER(c_void_p), POINTER(c_int64), c_int64, c_int64, POINTER(OptChunk), c_int64]),
+    "udape_grad_check": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "udape_student_step": (c_int, [c_void_p, c_int64, c_int, POINTER(OptHyper), c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p]),
     "udape_rewarp_fwd": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p, c_int,
                                  c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "udape_rewarp_plan_elems": (c_int64, [c_int64, c_int64, c_int]),

@@ -243,6 +243,158 @@ adain_cta_kernel(const T* __restrict__ content, const T* __restrict__ style, T* 
 }
 
 // ------------------------------------------------------------------------------------
+// single-pass streaming statistics for large planes (relu1_1 .. relu3_1 of the AdaIN decoder
+// pre-training job: 256x256 / 128x128 / 64x64 planes, adain/net.py:137-143)
+// ------------------------------------------------------------------------------------
+// A 256 KB plane fits neither a warp's registers nor (with 1000+ CTAs resident) the L2, so the
+// three-sweep kernel above would read it from DRAM up to three times.  Here every element is read
+// ONCE: a thread takes its vectors in batches of kStreamBatch (all loads issued before the first
+// use), computes the batch's exact two-pass (count, mean, M2) in registers and merges it into its
+// running triple with Chan's pairwise update
+//     n = na + nb,  d = mb - ma,  mean = ma + d*nb/n,  M2 = M2a + M2b + d*d*na*nb/n
+// — the same update then merges lanes (shuffles), warps (shared memory) and gives the plane's
+// mean and unbiased variance with the accuracy of a pairwise two-pass sum.
+constexpr int kStreamBatch = 8;
+
+struct Moments { float n, mean, m2; };
+
+__device__ __forceinline__ Moments merge_moments(const Moments& a, const Moments& b) {
+    const float n = a.n + b.n;
+    if (n == 0.0f) return a;
+    const float d = b.mean - a.mean;
+    const float rb = b.n / n;
+    Moments r;
+    r.n = n;
+    r.mean = fmaf(d, rb, a.mean);
+    r.m2 = a.m2 + b.m2 + d * d * a.n * rb;
+    return r;
+}
+
+template <typename T>
+__device__ __forceinline__ Moments cta_plane_moments(const T* __restrict__ p, int64_t hw, Moments* red) {
+    constexpr int EPV = Vec16<T>::EPV;
+    const int64_t nvec = hw / EPV;
+    const uint4* p4 = reinterpret_cast<const uint4*>(p);
+    Moments run = {0.0f, 0.0f, 0.0f};
+    for (int64_t base = threadIdx.x; base < nvec; base += static_cast<int64_t>(kCtaThreads) * kStreamBatch) {
+        uint4 v[kStreamBatch];
+        int cnt = 0;
+#pragma unroll
+        for (int u = 0; u < kStreamBatch; ++u) {
+            const int64_t i = base + static_cast<int64_t>(u) * kCtaThreads;
+            if (i < nvec) { v[u] = ldg_stream(p4 + i); ++cnt; }
+        }
+        float s = 0.0f;
+#pragma unroll
+        for (int u = 0; u < kStreamBatch; ++u) {
+            if (u < cnt) {
+                float f[EPV];
+                unpack16<T>(v[u], f);
+                float t = 0.0f;
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) t += f[e];
+                s += t;
+            }
+        }
+        Moments b;
+        b.n = static_cast<float>(cnt * EPV);
+        b.mean = s / b.n;
+        float m2 = 0.0f;
+#pragma unroll
+        for (int u = 0; u < kStreamBatch; ++u) {
+            if (u < cnt) {
+                float f[EPV];
+                unpack16<T>(v[u], f);
+                float t = 0.0f;
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) {
+                    const float d = f[e] - b.mean;
+                    t = fmaf(d, d, t);
+                }
+                m2 += t;
+            }
+        }
+        b.m2 = m2;
+        run = merge_moments(run, b);
+    }
+    // lanes, then warps (fixed tree: deterministic)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Moments other;
+        other.n = __shfl_xor_sync(0xffffffffu, run.n, o);
+        other.mean = __shfl_xor_sync(0xffffffffu, run.mean, o);
+        other.m2 = __shfl_xor_sync(0xffffffffu, run.m2, o);
+        // both partners must compute the same result: merge in lane order
+        run = (threadIdx.x & o) ? merge_moments(other, run) : merge_moments(run, other);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) red[warp] = run;
+    __syncthreads();
+    Moments tot = red[0];
+#pragma unroll
+    for (int w = 1; w < kCtaThreads / 32; ++w) tot = merge_moments(tot, red[w]);
+    return tot;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kCtaThreads)
+mean_std_stream_kernel(const T* __restrict__ feat, T* __restrict__ mean_out, T* __restrict__ std_out,
+                       int64_t hw, float eps) {
+    __shared__ Moments red[kCtaThreads / 32];
+    const int64_t plane = blockIdx.x;
+    const Moments m = cta_plane_moments<T>(feat + plane * hw, hw, red);
+    if (threadIdx.x == 0) {
+        mean_out[plane] = from_f32<T>(m.mean);
+        std_out[plane] = from_f32<T>(sqrtf(m.m2 / static_cast<float>(hw - 1) + eps));
+    }
+}
+
+// Backward of calc_mean_std (the style loss of adain/net.py:137-143 differentiates through it):
+//   dfeat[p, i] = dmean[p] / hw + dstd[p] * (feat[p, i] - mean[p]) / ((hw - 1) * std[p])
+// (std = sqrt(var_unbiased + eps)  =>  dstd/dx_i = (x_i - mean) / ((hw-1) std)).  One read, one write.
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kCtaThreads)
+mean_std_bwd_kernel(const T* __restrict__ feat, const T* __restrict__ mean, const T* __restrict__ stdv,
+                    const T* __restrict__ dmean, const T* __restrict__ dstd, T* __restrict__ dfeat,
+                    int64_t hw, int splits, int64_t span) {
+    const int64_t plane = blockIdx.x / splits;
+    const int64_t lo = static_cast<int64_t>(blockIdx.x % splits) * span;   // span is a multiple of the vector width
+    const int64_t hi = lo + span < hw ? lo + span : hw;
+    const float mu = to_f32<T>(mean[plane]);
+    const float a = dmean ? to_f32<T>(dmean[plane]) / static_cast<float>(hw) : 0.0f;
+    const float b = dstd ? to_f32<T>(dstd[plane]) / (static_cast<float>(hw - 1) * to_f32<T>(stdv[plane])) : 0.0f;
+    const T* x = feat + plane * hw;
+    T* o = dfeat + plane * hw;
+    if (VEC) {
+        constexpr int EPV = Vec16<T>::EPV;
+        const uint4* x4 = reinterpret_cast<const uint4*>(x);
+        uint4* o4 = reinterpret_cast<uint4*>(o);
+        const int64_t v0 = lo / EPV, v1 = hi / EPV;
+        for (int64_t base = v0 + threadIdx.x; base < v1; base += static_cast<int64_t>(kCtaThreads) * 4) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = base + static_cast<int64_t>(u) * kCtaThreads;
+                if (i < v1) v[u] = ldg_stream(x4 + i);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = base + static_cast<int64_t>(u) * kCtaThreads;
+                if (i < v1) {
+                    float f[EPV];
+                    unpack16<T>(v[u], f);
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e) f[e] = fmaf(b, f[e] - mu, a);
+                    stg_stream(o4 + i, pack16<T>(f));
+                }
+            }
+        }
+    } else {
+        for (int64_t i = lo + threadIdx.x; i < hi; i += kCtaThreads) o[i] = from_f32<T>(fmaf(b, to_f32<T>(x[i]) - mu, a));
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------
 template <typename T>
@@ -276,7 +428,7 @@ static int launch_mean_std(const void* feat, int64_t planes, int64_t hw, float e
             default: mean_std_warp_kernel<T, 8><<<grid, kWarpsPerBlock * 32, 0, st>>>(f, m, s, planes, nvec, ihw, eps); break;
         }
     } else if (vec) {
-        mean_std_cta_kernel<T, true><<<static_cast<unsigned>(planes), kCtaThreads, 0, st>>>(f, m, s, hw, eps);
+        mean_std_stream_kernel<T><<<static_cast<unsigned>(planes), kCtaThreads, 0, st>>>(f, m, s, hw, eps);
     } else {
         mean_std_cta_kernel<T, false><<<static_cast<unsigned>(planes), kCtaThreads, 0, st>>>(f, m, s, hw, eps);
     }
@@ -332,6 +484,41 @@ extern "C" int udape_mean_std(const void* feat, int dtype, int64_t planes, int64
                   "udape_mean_std: pointer not aligned to element size");
     UDAPE_DISPATCH_FLOAT(dtype, T, return launch_mean_std<T>(feat, planes, hw, eps, mean, std, as_stream(stream)));
     return UDAPE_OK;
+}
+
+extern "C" int udape_mean_std_bwd(const void* feat, const void* mean, const void* std, const void* dmean,
+                                  const void* dstd, int dtype, int64_t planes, int64_t hw, void* dfeat, void* stream) {
+    UDAPE_REQUIRE(feat && mean && std && dfeat, UDAPE_ERR_NULL, "udape_mean_std_bwd: NULL pointer");
+    UDAPE_REQUIRE(planes > 0 && hw > 0 && planes < (1ll << 31) && hw < (1ll << 31), UDAPE_ERR_SHAPE,
+                  "udape_mean_std_bwd: bad extents planes=%lld hw=%lld", (long long)planes, (long long)hw);
+    const int es = dtype_size(dtype);
+    UDAPE_REQUIRE(es == 2 || es == 4, UDAPE_ERR_DTYPE, "udape_mean_std_bwd: unsupported dtype code %d", dtype);
+    UDAPE_REQUIRE(aligned_to(feat, es) && aligned_to(mean, es) && aligned_to(std, es) && aligned_to(dfeat, es) &&
+                      (!dmean || aligned_to(dmean, es)) && (!dstd || aligned_to(dstd, es)),
+                  UDAPE_ERR_ALIGN, "udape_mean_std_bwd: pointer not aligned to element size");
+    cudaStream_t st = as_stream(stream);
+    UDAPE_DISPATCH_FLOAT(dtype, T, {
+        constexpr int EPV = Vec16<T>::EPV;
+        const bool vec = plane_vectorizable<T>(feat, hw) && aligned16(dfeat);
+        // a CTA streams up to 16 vectors per thread; larger planes are split so that small batches still fill the GPU
+        const int64_t per_cta = static_cast<int64_t>(kCtaThreads) * 16 * EPV;
+        int64_t splits = (hw + per_cta - 1) / per_cta;
+        if (splits < 1) splits = 1;
+        int64_t span = (hw + splits - 1) / splits;
+        span = (span + EPV - 1) / EPV * EPV;
+        splits = (hw + span - 1) / span;
+        UDAPE_REQUIRE(planes * splits < (1ll << 31), UDAPE_ERR_SHAPE, "udape_mean_std_bwd: grid too large");
+        const unsigned grid = static_cast<unsigned>(planes * splits);
+        const T* f = static_cast<const T*>(feat);
+        const T* m = static_cast<const T*>(mean);
+        const T* s = static_cast<const T*>(std);
+        const T* dm = static_cast<const T*>(dmean);
+        const T* ds = static_cast<const T*>(dstd);
+        T* o = static_cast<T*>(dfeat);
+        if (vec) mean_std_bwd_kernel<T, true><<<grid, kCtaThreads, 0, st>>>(f, m, s, dm, ds, o, hw, static_cast<int>(splits), span);
+        else mean_std_bwd_kernel<T, false><<<grid, kCtaThreads, 0, st>>>(f, m, s, dm, ds, o, hw, static_cast<int>(splits), span);
+    });
+    return check_launch("udape_mean_std_bwd");
 }
 
 extern "C" int udape_adain_mix(const void* content, const void* style, int dtype, int64_t planes,

@@ -1,0 +1,301 @@
+// optim.cu — the student update and the teacher EMA in one multi-tensor pass.
+//
+// Replaces the tail of the reference's train step (train_human.py:436-440):
+//     scaler.scale(loss_all).backward(); scaler.step(stu_optimizer); tea_optimizer.step(); scaler.update()
+// i.e. GradScaler.unscale_ (read + write of every gradient, plus a non-finite check and a host
+// `.item()` sync), torch.optim.Adam / SGD(momentum=0.9, nesterov) (train_human.py:136-139; a dozen
+// foreach passes over param / grad / exp_avg / exp_avg_sq) and OldWeightEMA.step (utils.py:21-25,
+// 969 launches).  Here:
+//   * grad_check_kernel   — one READ-ONLY pass over the gradients -> found_inf (device float; no
+//                           host sync, no unscaled copy written back);
+//   * student_step_kernel — one pass that unscales the gradient in registers, applies Adam or SGD to
+//                           the student, and folds the updated student into the teacher EMA:
+//                           Adam 5 reads + 4 writes per element (36 B) instead of the reference's
+//                           ~20 passes; SGD 4 reads + 3 writes.
+// When found_inf is set the student (and its optimizer state and step count) is left untouched and
+// only the EMA runs — exactly what scaler.step() + tea_optimizer.step() do in the reference.
+//
+// Arithmetic follows torch's single-tensor Adam/SGD op order (torch/optim/adam.py::_single_tensor_adam,
+// sgd.py::_single_tensor_sgd): bias corrections and step size are formed in double precision and
+// rounded to float once; the EMA keeps the three fp32 roundings of  p.mul_(a); p.add_(s*(1-a)).
+#include "common.cuh"
+
+namespace udape {
+
+constexpr int kOptThreads = 256;
+constexpr int kOptUnroll = 2;
+
+struct OptScalars {
+    float inv_scale;   // 1 / grad_scale (1 when no scaler)
+    float lr;
+    float w1;          // Adam: 1 - beta1          SGD: momentum
+    float beta2;       // Adam: beta2              SGD: 1 - dampening
+    float w2;          // Adam: 1 - beta2
+    float eps;
+    float wd;
+    float neg_step;    // Adam: -(lr / bias_correction1)   SGD: -lr
+    float bc2_sqrt;    // Adam: sqrt(bias_correction2)
+    int skip;          // found_inf != 0: leave the student alone
+    int first;         // SGD: this is update number 1 (momentum buffer := grad)
+};
+
+__device__ __forceinline__ float ema_fold(float t, float s, float a, float b) {
+    return __fadd_rn(__fmul_rn(t, a), __fmul_rn(s, b));
+}
+
+__device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, const OptScalars& c) {
+    g *= c.inv_scale;                                   // GradScaler.unscale_: grad.mul_(inv_scale)
+    if (c.wd != 0.0f) g = fmaf(c.wd, p, g);             // grad.add(param, alpha=weight_decay)
+    m = fmaf(c.w1, g - m, m);                           // exp_avg.lerp_(grad, 1 - beta1)
+    v = fmaf(c.w2 * g, g, v * c.beta2);                 // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float denom = sqrtf(v) / c.bc2_sqrt + c.eps;  // (exp_avg_sq.sqrt() / bc2_sqrt).add_(eps)
+    p = fmaf(c.neg_step, m / denom, p);                 // param.addcdiv_(exp_avg, denom, value=-step_size)
+}
+
+template <bool NESTEROV>
+__device__ __forceinline__ void sgd_elem(float& p, float g, float& buf, const OptScalars& c, bool momentum) {
+    g *= c.inv_scale;
+    if (c.wd != 0.0f) g = fmaf(c.wd, p, g);
+    if (momentum) {
+        buf = c.first ? g : fmaf(c.beta2, g, buf * c.w1);   // buf.mul_(momentum).add_(grad, alpha=1-dampening)
+        g = NESTEROV ? fmaf(c.w1, buf, g) : buf;            // grad.add(buf, alpha=momentum)
+    }
+    p = fmaf(-c.lr, g, p);                                  // param.add_(grad, alpha=-lr)
+}
+
+// ALGO 0: Adam, 1: SGD, 2: SGD + Nesterov
+template <int ALGO>
+__global__ void __launch_bounds__(kOptThreads)
+student_step_kernel(const udape_opt_chunk* __restrict__ chunks, udape_opt_hyper h,
+                    const float* __restrict__ lr_dev, const float* __restrict__ grad_scale,
+                    const float* __restrict__ found_inf, int32_t* __restrict__ step_dev,
+                    uint32_t* __restrict__ ticket) {
+    __shared__ OptScalars sc;
+    const udape_opt_chunk c = chunks[blockIdx.x];
+    if (threadIdx.x == 0) {
+        OptScalars s;
+        const double lr = lr_dev ? static_cast<double>(*lr_dev) : h.lr;
+        s.skip = (found_inf && *found_inf != 0.0f) ? 1 : 0;
+        const int step = (step_dev ? *step_dev : h.step - 1) + 1;  // number of THIS update, 1-based
+        // GradScaler: inv_scale = scale.double().reciprocal().float()
+        s.inv_scale = grad_scale ? static_cast<float>(1.0 / static_cast<double>(*grad_scale)) : 1.0f;
+        s.lr = static_cast<float>(lr);
+        s.eps = static_cast<float>(h.eps);
+        s.wd = static_cast<float>(h.weight_decay);
+        s.first = step <= 1;
+        if (ALGO == 0) {
+            s.w1 = static_cast<float>(1.0 - h.beta1);
+            s.beta2 = static_cast<float>(h.beta2);
+            s.w2 = static_cast<float>(1.0 - h.beta2);
+            const double bc1 = 1.0 - pow(h.beta1, static_cast<double>(step));
+            const double bc2 = 1.0 - pow(h.beta2, static_cast<double>(step));
+            s.neg_step = static_cast<float>(-(lr / bc1));
+            s.bc2_sqrt = static_cast<float>(sqrt(bc2));
+        } else {
+            s.w1 = static_cast<float>(h.beta1);          // momentum
+            s.beta2 = static_cast<float>(1.0 - h.beta2);  // 1 - dampening
+            s.w2 = 0.0f;
+            s.neg_step = -s.lr;
+            s.bc2_sqrt = 1.0f;
+        }
+        sc = s;
+    }
+    __syncthreads();
+    const OptScalars s = sc;
+    const float ea = h.ema_a, eb = h.ema_b;
+
+    float* __restrict__ p = static_cast<float*>(c.param);
+    const float* __restrict__ g = static_cast<const float*>(c.grad);
+    float* __restrict__ m = static_cast<float*>(c.state1);
+    float* __restrict__ v = static_cast<float*>(c.state2);
+    float* __restrict__ t = static_cast<float*>(c.ema);
+    const int n = static_cast<int>(c.numel);
+    const bool upd = !s.skip && g != nullptr;            // torch skips parameters whose grad is None
+    const bool has_m = m != nullptr;                     // SGD with momentum == 0 keeps no buffer
+    const bool vec_ok = aligned16(p) && (!upd || (aligned16(g) && (!has_m || aligned16(m)) &&
+                                                  (ALGO != 0 || aligned16(v)))) && (!t || aligned16(t));
+    int done = 0;
+    if (vec_ok) {
+        const int nvec = n >> 2;
+        for (int base = 0; base < nvec; base += kOptThreads * kOptUnroll) {
+            uint4 pv[kOptUnroll], gv[kOptUnroll], mv[kOptUnroll], vv[kOptUnroll], tv[kOptUnroll];
+#pragma unroll
+            for (int u = 0; u < kOptUnroll; ++u) {   // every load of the thread is issued before the first use
+                const int i = base + u * kOptThreads + threadIdx.x;
+                if (i < nvec) {
+                    pv[u] = ldg_cached(reinterpret_cast<const uint4*>(p) + i);
+                    if (upd) {
+                        gv[u] = ldg_stream(reinterpret_cast<const uint4*>(g) + i);
+                        if (has_m) mv[u] = ldg_cached(reinterpret_cast<const uint4*>(m) + i);
+                        if (ALGO == 0) vv[u] = ldg_cached(reinterpret_cast<const uint4*>(v) + i);
+                    }
+                    if (t) tv[u] = ldg_cached(reinterpret_cast<const uint4*>(t) + i);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kOptUnroll; ++u) {
+                const int i = base + u * kOptThreads + threadIdx.x;
+                if (i < nvec) {
+                    float fp[4], fg[4], fm[4], fv[4], ft[4];
+                    unpack16<float>(pv[u], fp);
+                    if (upd) {
+                        unpack16<float>(gv[u], fg);
+                        if (has_m) unpack16<float>(mv[u], fm);
+                        if (ALGO == 0) unpack16<float>(vv[u], fv);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (ALGO == 0) adam_elem(fp[e], fg[e], fm[e], fv[e], s);
+                            else sgd_elem<ALGO == 2>(fp[e], fg[e], fm[e], s, has_m);
+                        }
+                        stg_plain(reinterpret_cast<uint4*>(p) + i, pack16<float>(fp));
+                        if (has_m) stg_plain(reinterpret_cast<uint4*>(m) + i, pack16<float>(fm));
+                        if (ALGO == 0) stg_plain(reinterpret_cast<uint4*>(v) + i, pack16<float>(fv));
+                    }
+                    if (t) {
+                        unpack16<float>(tv[u], ft);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) ft[e] = ema_fold(ft[e], fp[e], ea, eb);
+                        stg_plain(reinterpret_cast<uint4*>(t) + i, pack16<float>(ft));
+                    }
+                }
+            }
+        }
+        done = nvec << 2;
+    }
+    for (int i = done + threadIdx.x; i < n; i += kOptThreads) {
+        float fp = p[i];
+        if (upd) {
+            float fm = has_m ? m[i] : 0.0f;
+            if (ALGO == 0) {
+                float fv = v[i];
+                adam_elem(fp, g[i], fm, fv, s);
+                v[i] = fv;
+            } else {
+                sgd_elem<ALGO == 2>(fp, g[i], fm, s, has_m);
+            }
+            p[i] = fp;
+            if (has_m) m[i] = fm;
+        }
+        if (t) t[i] = ema_fold(t[i], fp, ea, eb);
+    }
+    // the step counter advances once per launch, after every CTA has read it, and only when the
+    // update was applied (torch: state['step'] is not touched when scaler.step() skips)
+    if (step_dev) {
+        if (last_block_done(ticket, gridDim.x) && threadIdx.x == 0 && !s.skip) *step_dev = *step_dev + 1;
+    }
+}
+
+// found_inf := any(!isfinite(grad))  — torch._amp_foreach_non_finite_check_and_unscale_ without the
+// write-back.  ws[0] is a self-resetting ticket, ws[1] the OR word (left zero).
+__global__ void __launch_bounds__(kOptThreads)
+grad_check_kernel(const udape_opt_chunk* __restrict__ chunks, float* __restrict__ found_inf,
+                  uint32_t* __restrict__ ws) {
+    const udape_opt_chunk c = chunks[blockIdx.x];
+    const float* __restrict__ g = static_cast<const float*>(c.grad);
+    const int n = static_cast<int>(c.numel);
+    // a float is non-finite iff its exponent field is all ones: fold with AND over (x & 0x7f800000) == 0x7f800000
+    uint32_t bad = 0;
+    if (g) {
+        int done = 0;
+        if (aligned16(g)) {
+            const int nvec = n >> 2;
+            const uint4* g4 = reinterpret_cast<const uint4*>(g);
+            for (int base = 0; base < nvec; base += kOptThreads * 4) {
+                uint4 x[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + u * kOptThreads + threadIdx.x;
+                    x[u] = i < nvec ? ldg_stream(g4 + i) : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    bad |= ((x[u].x & 0x7f800000u) == 0x7f800000u) | ((x[u].y & 0x7f800000u) == 0x7f800000u) |
+                           ((x[u].z & 0x7f800000u) == 0x7f800000u) | ((x[u].w & 0x7f800000u) == 0x7f800000u);
+                }
+            }
+            done = nvec << 2;
+        }
+        for (int i = done + threadIdx.x; i < n; i += kOptThreads)
+            bad |= (__float_as_uint(g[i]) & 0x7f800000u) == 0x7f800000u;
+    }
+    const int any = __syncthreads_or(static_cast<int>(bad));
+    if (threadIdx.x == 0 && any) atomicOr(ws + 1, 1u);
+    if (last_block_done(ws, gridDim.x) && threadIdx.x == 0) {
+        const uint32_t f = *reinterpret_cast<volatile uint32_t*>(ws + 1);
+        *found_inf = f ? 1.0f : 0.0f;
+        ws[1] = 0u;
+    }
+}
+
+}  // namespace udape
+
+using namespace udape;
+
+extern "C" int64_t udape_opt_plan(void* const* param, const void* const* grad, void* const* state1,
+                                  void* const* state2, void* const* ema, const int64_t* numel,
+                                  int64_t n_tensors, int64_t chunk_elems, udape_opt_chunk* out,
+                                  int64_t capacity) {
+    if (!param || !numel) return fail(UDAPE_ERR_NULL, "udape_opt_plan: NULL table");
+    if (n_tensors < 0 || chunk_elems <= 0 || chunk_elems >= (1ll << 31) || (chunk_elems % 16) != 0)
+        return fail(UDAPE_ERR_ARG, "udape_opt_plan: chunk_elems must be a positive multiple of 16 below 2^31");
+    int64_t n = 0;
+    for (int64_t t = 0; t < n_tensors; ++t) {
+        if (numel[t] < 0) return fail(UDAPE_ERR_SHAPE, "udape_opt_plan: tensor %lld has negative numel", (long long)t);
+        if (numel[t] > 0 && !param[t])
+            return fail(UDAPE_ERR_NULL, "udape_opt_plan: tensor %lld has a NULL parameter pointer", (long long)t);
+        for (int64_t off = 0; off < numel[t]; off += chunk_elems, ++n) {
+            if (out && n < capacity) {
+                const int64_t rem = numel[t] - off;
+                auto at = [off](const void* base) -> void* {
+                    return base ? const_cast<char*>(static_cast<const char*>(base)) + off * 4 : nullptr;
+                };
+                out[n].param = at(param[t]);
+                out[n].grad = grad ? at(grad[t]) : nullptr;
+                out[n].state1 = state1 ? at(state1[t]) : nullptr;
+                out[n].state2 = state2 ? at(state2[t]) : nullptr;
+                out[n].ema = ema ? at(ema[t]) : nullptr;
+                out[n].numel = rem < chunk_elems ? rem : chunk_elems;
+            }
+        }
+    }
+    return n;
+}
+
+extern "C" int udape_grad_check(const udape_opt_chunk* chunks_dev, int64_t n_chunks, float* found_inf,
+                                uint32_t* ws, void* stream) {
+    UDAPE_REQUIRE(found_inf && ws, UDAPE_ERR_NULL, "udape_grad_check: found_inf / ws is NULL");
+    UDAPE_REQUIRE(n_chunks >= 0 && n_chunks < (1ll << 31), UDAPE_ERR_SHAPE, "udape_grad_check: bad n_chunks=%lld", (long long)n_chunks);
+    cudaStream_t st = as_stream(stream);
+    if (n_chunks == 0) {
+        cudaError_t e = cudaMemsetAsync(found_inf, 0, sizeof(float), st);
+        return e == cudaSuccess ? UDAPE_OK : fail(static_cast<int>(e), "udape_grad_check: %s", cudaGetErrorString(e));
+    }
+    UDAPE_REQUIRE(chunks_dev, UDAPE_ERR_NULL, "udape_grad_check: chunk table is NULL");
+    grad_check_kernel<<<static_cast<unsigned>(n_chunks), kOptThreads, 0, st>>>(chunks_dev, found_inf, ws);
+    return check_launch("udape_grad_check");
+}
+
+extern "C" int udape_student_step(const udape_opt_chunk* chunks_dev, int64_t n_chunks, int algo,
+                                  const udape_opt_hyper* hyper, const float* lr_dev, const float* grad_scale,
+                                  const float* found_inf, int32_t* step_dev, uint32_t* ticket, void* stream) {
+    if (n_chunks == 0) return UDAPE_OK;
+    UDAPE_REQUIRE(chunks_dev && hyper, UDAPE_ERR_NULL, "udape_student_step: chunk table / hyper is NULL");
+    UDAPE_REQUIRE(n_chunks > 0 && n_chunks < (1ll << 31), UDAPE_ERR_SHAPE, "udape_student_step: bad n_chunks=%lld", (long long)n_chunks);
+    UDAPE_REQUIRE(algo == UDAPE_OPT_ADAM || algo == UDAPE_OPT_SGD, UDAPE_ERR_ARG, "udape_student_step: algo must be UDAPE_OPT_ADAM or UDAPE_OPT_SGD");
+    UDAPE_REQUIRE(!step_dev || ticket, UDAPE_ERR_NULL, "udape_student_step: a device step counter needs a ticket word");
+    UDAPE_REQUIRE(step_dev || hyper->step >= 1, UDAPE_ERR_ARG, "udape_student_step: hyper.step is 1-based (got %d)", (int)hyper->step);
+    if (algo == UDAPE_OPT_ADAM)
+        UDAPE_REQUIRE(hyper->beta1 >= 0.0 && hyper->beta1 < 1.0 && hyper->beta2 >= 0.0 && hyper->beta2 < 1.0 && hyper->eps >= 0.0,
+                      UDAPE_ERR_ARG, "udape_student_step: Adam needs 0 <= beta < 1 and eps >= 0");
+    UDAPE_REQUIRE(!(hyper->nesterov && algo == UDAPE_OPT_SGD && (hyper->beta1 <= 0.0 || hyper->beta2 != 0.0)),
+                  UDAPE_ERR_ARG, "udape_student_step: Nesterov momentum requires a momentum and zero dampening");
+    cudaStream_t st = as_stream(stream);
+    const unsigned grid = static_cast<unsigned>(n_chunks);
+    if (algo == UDAPE_OPT_ADAM)
+        student_step_kernel<0><<<grid, kOptThreads, 0, st>>>(chunks_dev, *hyper, lr_dev, grad_scale, found_inf, step_dev, ticket);
+    else if (hyper->nesterov)
+        student_step_kernel<2><<<grid, kOptThreads, 0, st>>>(chunks_dev, *hyper, lr_dev, grad_scale, found_inf, step_dev, ticket);
+    else
+        student_step_kernel<1><<<grid, kOptThreads, 0, st>>>(chunks_dev, *hyper, lr_dev, grad_scale, found_inf, step_dev, ticket);
+    return check_launch("udape_student_step");
+}

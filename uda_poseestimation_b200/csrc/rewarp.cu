@@ -983,15 +983,17 @@ extern "C" int udape_rewarp_fwd(const void* const* in, const float* const* theta
                                 const uint8_t* active, int64_t B, int64_t C, int64_t H, int64_t W, int dtype,
                                 void* out, uint16_t* inverse_plan, void* stream) {
     RewarpArgs a = {};
-    UDAPE_REQUIRE(in && theta && out, UDAPE_ERR_NULL, "udape_rewarp_fwd: NULL pointer");
+    // out == NULL with an inverse plan: only the plan is built (it depends on theta alone, so a caller can
+    // run it on another stream, off the chain  gather -> loss -> backward)
+    UDAPE_REQUIRE(in && theta && (out || inverse_plan), UDAPE_ERR_NULL, "udape_rewarp_fwd: NULL pointer");
     const int rc = fill_common(a, "udape_rewarp_fwd", views, stages, half_mask, grid_dtype, B, C, H, W, dtype);
     if (rc) return rc;
     const int es = dtype_size(dtype);
     bool all16 = aligned16(out);
     for (int v = 0; v < views; ++v) {
-        UDAPE_REQUIRE(in[v] && theta[v], UDAPE_ERR_NULL, "udape_rewarp_fwd: NULL view %d", v);
+        UDAPE_REQUIRE((in[v] || !out) && theta[v], UDAPE_ERR_NULL, "udape_rewarp_fwd: NULL view %d", v);
         UDAPE_REQUIRE(aligned_to(in[v], es) && aligned_to(theta[v], 4), UDAPE_ERR_ALIGN, "udape_rewarp_fwd: misaligned view %d", v);
-        UDAPE_REQUIRE(in[v] != out, UDAPE_ERR_ARG, "udape_rewarp_fwd: the gather cannot run in place");
+        UDAPE_REQUIRE(!out || in[v] != out, UDAPE_ERR_ARG, "udape_rewarp_fwd: the gather cannot run in place");
         a.view[v].in = in[v];
         a.view[v].theta = theta[v];
         all16 = all16 && aligned16(in[v]);
@@ -1017,6 +1019,7 @@ extern "C" int udape_rewarp_fwd(const void* const* in, const float* const* theta
                                : launch_cluster(rewarp_inverse_plan_kernel<2>, static_cast<unsigned>(B * n), static_cast<unsigned>(n),
                                                 smem, st, "udape_rewarp_fwd(plan)", a, inverse_plan, bw);
         if (r2) return r2;
+        if (!out) return check_launch("udape_rewarp_fwd(plan)");
     }
     if (buf_words) {
         // one cluster of `n` CTAs per sample: the channels are split n ways, the map is built once

@@ -107,6 +107,7 @@ class OldWeightEMA(object):
         self.source_params = list(source_net.parameters())
         self.alpha = alpha
         self._plan = None
+        self._fused_pending = False  # set by optim.Adam/SGD.step() when it already folded this EMA in
         n = min(len(self.target_params), len(self.source_params))  # zip() semantics
         dst = [p.data for p in self.target_params[:n]]
         src = [p.data for p in self.source_params[:n]]
@@ -127,6 +128,11 @@ class OldWeightEMA(object):
         return plan
 
     def step(self):
+        if self._fused_pending:
+            # the student optimizer this EMA is attached to (optim.attach_teacher) applied it inside its
+            # own launch, with the updated student, exactly once for this step
+            self._fused_pending = False
+            return
         one_minus_alpha = 1.0 - self.alpha
         self._get_plan().run(float(self.alpha), float(one_minus_alpha), 0)
 

@@ -127,7 +127,8 @@ class HotPathStep:
             # the heatmap chains are short, latency-bound kernels on the step's critical path: give them
             # priority over the bandwidth-bound AdaIN / EMA launches when CTAs compete for SM slots
             hi = -1 if os.environ.get("UDAPE_STEP_PRIORITY", "1") == "1" else 0
-            self._side = (torch.cuda.Stream(dev, priority=hi), torch.cuda.Stream(dev, priority=hi), torch.cuda.Stream(dev))
+            self._side = (torch.cuda.Stream(dev, priority=hi), torch.cuda.Stream(dev, priority=hi), torch.cuda.Stream(dev),
+                          torch.cuda.Stream(dev, priority=hi))
         return self._side
 
     # -- the step -----------------------------------------------------------------------------------
@@ -144,7 +145,7 @@ class HotPathStep:
         The fork/join is plain stream-event ordering, so it behaves the same eagerly and under
         CUDA-graph capture (where it becomes parallel graph branches)."""
         cur = torch.cuda.current_stream()
-        s_tea, s_stu, s_ema = self._streams(inp.y_s.device) if self.parallel else (cur, cur, cur)
+        s_tea, s_stu, s_ema, s_plan = self._streams(inp.y_s.device) if self.parallel else (cur, cur, cur, cur)
         ema_side = with_ema and self.parallel and self.ema_parallel
         if self.parallel:
             s_tea.wait_stream(cur)
@@ -162,13 +163,21 @@ class HotPathStep:
         stu_half = inp.y_t_stu.dtype in (torch.float16, torch.bfloat16)
         stu_mask = (1 << inp.theta_stu.shape[1]) - 1 if (inp.theta_stu is not None and stu_half) else 0
         stu_grid = inp.y_t_stu.dtype if stu_half else None
-        y_t_stu_recon, recon_ready = inp.y_t_stu, None
+        y_t_stu_recon, recon_ready, plan_ready = inp.y_t_stu, None, None
         if inp.theta_stu is not None:
+            # the composed map of every sample inverted once — what the backward gathers from.  It depends
+            # on theta alone, so it is built on its own branch, off the  gather -> loss -> backward  chain
+            stu_plan = _rewarp.inverse_plan_buffer(inp.y_t_stu)
+            if self.parallel:
+                s_plan.wait_stream(cur)
+            with torch.cuda.stream(s_plan), torch.no_grad():
+                _rewarp.build_inverse_plan(inp.y_t_stu, inp.theta_stu, stu_mask, stu_grid, plan=stu_plan)
+                if self.parallel:
+                    plan_ready = torch.cuda.Event()
+                    plan_ready.record(s_plan)
             with torch.cuda.stream(s_stu), torch.no_grad():
                 # :417-423 — y_t_stu_recon (the backward runs after the loss step, below)
-                # (the forward also inverts the composed map once: the plan its backward gathers from)
-                stu_plan = _rewarp.inverse_plan_buffer(inp.y_t_stu)
-                y_t_stu_recon = _rewarp.gather(inp.y_t_stu.detach(), inp.theta_stu, stu_mask, stu_grid, plan=stu_plan)
+                y_t_stu_recon = _rewarp.gather(inp.y_t_stu.detach(), inp.theta_stu, stu_mask, stu_grid)
                 if self.parallel:
                     recon_ready = torch.cuda.Event()
                     recon_ready.record(s_stu)
@@ -197,6 +206,8 @@ class HotPathStep:
                 (g_c,) = torch.autograd.grad(loss_c * (self.lambda_c * self.loss_scale), (y_t_stu,))
             g_recon = g_c
             if inp.theta_stu is not None:
+                if plan_ready is not None:
+                    s_tea.wait_event(plan_ready)
                 with torch.no_grad():
                     # backward of :417-423: the consistency gradient scattered back to the student's frame
                     g_c = _rewarp.gather_backward(g_recon, inp.theta_stu, stu_mask, stu_grid, plan=stu_plan)

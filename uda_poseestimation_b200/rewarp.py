@@ -145,7 +145,7 @@ def _launch_fwd(views, thetas, half_mask, grid_code, out, paste=None, paste_afte
     with _lib.on_device(dev):
         st = _lib.load().udape_rewarp_fwd(in_arr, th_arr, n, thetas[0].shape[1], half_mask, grid_code, _lib.ptr(paste),
                                           paste_after, _lib.ptr(active), b, c, h, w, _lib.float_code(y0),
-                                          out.data_ptr(), _lib.ptr(plan), _lib.stream_ptr(dev))
+                                          _lib.ptr(out), _lib.ptr(plan), _lib.stream_ptr(dev))
     _lib.check(st, "udape_rewarp_fwd")
     return out
 
@@ -166,6 +166,22 @@ def inverse_plan_buffer(y: torch.Tensor) -> torch.Tensor | None:
     b, _, h, w = y.shape
     n = _lib.load().udape_rewarp_plan_elems(h, w, y.element_size())
     return torch.empty((b, n), dtype=torch.int16, device=y.device) if n > 0 else None
+
+
+def build_inverse_plan(y: torch.Tensor, theta: torch.Tensor, half_mask: int = 0, grid_dtype: torch.dtype | None = None,
+                       plan: torch.Tensor | None = None) -> torch.Tensor | None:
+    """Fill (and return) the inverse plan of ``gather(y, theta, ...)`` without running the gather: the
+    plan depends only on ``theta`` and ``y``'s shape / element size, so it can be built on another stream
+    while the forward and the loss run (the backward is its only consumer)."""
+    dev = _lib.require_cuda(y, theta, plan)
+    _check_theta(y, theta)
+    if plan is None:
+        plan = inverse_plan_buffer(y)
+    if plan is None:
+        return None
+    grid_code = _lib._DTYPE_CODE[grid_dtype] if grid_dtype is not None else _lib.F16
+    _launch_fwd([y], [theta.contiguous()], half_mask, grid_code, None, plan=plan)
+    return plan
 
 
 class _Rewarp(torch.autograd.Function):
