@@ -71,6 +71,15 @@ UDAPE_API int udape_last_error(char* buf, size_t buf_bytes);
 UDAPE_API int udape_mean_std(const void* feat, int dtype, int64_t planes, int64_t hw, float eps,
                    void* mean, void* std, void* stream);
 
+/* ---- f4: backward of calc_mean_std — the style loss of the AdaIN decoder pre-training job
+ * (adain/net.py:137-143: mse(mean_in, mean_tgt) + mse(std_in, std_tgt) on relu1_1..relu4_1, planes of
+ * 256x256 .. 32x32) differentiates through a1:
+ *   dfeat[p,i] = dmean[p] / hw + dstd[p] * (feat[p,i] - mean[p]) / ((hw - 1) * std[p])
+ * mean / std are the outputs of udape_mean_std for the same feat; dmean / dstd (either may be NULL = 0)
+ * are the upstream gradients, all [planes] of `dtype`.  One read and one write of the feature tensor. */
+UDAPE_API int udape_mean_std_bwd(const void* feat, const void* mean, const void* std, const void* dmean,
+                       const void* dstd, int dtype, int64_t planes, int64_t hw, void* dfeat, void* stream);
+
 /* ---- a2+a3: adaptive_instance_normalization (+ alpha mix) ---------------------------
  * adain/function.py:14-22, lib/models/Style_net.py:21-29 and :167-168.
  * out[p,i] = alpha * ((c[p,i]-mean_c[p])/std_c[p]*std_s[p]+mean_s[p]) + (1-alpha)*c[p,i]

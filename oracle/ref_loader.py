@@ -28,6 +28,7 @@ _FILES = {
     "ema": "lib/models/ema.py",
     "utils": "utils.py",
     "dataset_util": "lib/datasets/util.py",
+    "adain_net": "adain/net.py",
 }
 
 
@@ -41,6 +42,9 @@ def load(name: str) -> types.ModuleType:
     if mod_name in sys.modules:
         return sys.modules[mod_name]
     path = REFERENCE_ROOT / _FILES[name]
+    if name == "adain_net":
+        # adain/net.py does `from function import ...` (it is run with adain/ as the working directory)
+        sys.modules.setdefault("function", load("function"))
     spec = importlib.util.spec_from_file_location(mod_name, path)
     mod = importlib.util.module_from_spec(spec)
     sys.modules[mod_name] = mod

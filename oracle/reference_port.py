@@ -49,6 +49,17 @@ def adaptive_instance_normalization(content_feat, style_feat):
     return normalised * s_std.expand(shape) + s_mean.expand(shape)
 
 
+def calc_style_loss(input, target):
+    """adain/net.py:137-143 (``Net.calc_style_loss``): MSE of the channel statistics; autograd flows to
+    ``input`` through calc_mean_std."""
+    assert input.size() == target.size()
+    assert target.requires_grad is False
+    input_mean, input_std = calc_mean_std(input)
+    target_mean, target_std = calc_mean_std(target)
+    mse = torch.nn.MSELoss()
+    return mse(input_mean, target_mean) + mse(input_std, target_std)
+
+
 def adain_mix(content_feat, style_feat, alpha=1.0):
     """Style_net.py:164,167-168 — t = adain(c, s); t = alpha * t + (1 - alpha) * c."""
     assert 0 <= alpha <= 1

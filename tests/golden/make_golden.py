@@ -340,6 +340,31 @@ def golden_optim():
     save("optim", **out)
 
 
+def golden_style_loss():
+    """adain/net.py:137-143 called on the real class (unbound, with the module's own MSELoss) + torch
+    autograd through the reference's calc_mean_std: loss and d loss / d input."""
+    import types
+    net = ref_loader.load("adain_net")
+    fake_self = types.SimpleNamespace(mse_loss=torch.nn.MSELoss())
+    out = {}
+    cases = {"warp": (2, 3, 8, 8), "ragged": (1, 2, 5, 7), "stream": (1, 2, 40, 40), "mid": (2, 2, 32, 32)}
+    for tag, shape in cases.items():
+        g = torch.Generator().manual_seed(300 + len(tag))
+        x = torch.relu(torch.randn(*shape, generator=g) + 0.3).requires_grad_(True)
+        t = torch.relu(torch.randn(*shape, generator=g) * 1.5 + 0.1)
+        loss = net.Net.calc_style_loss(fake_self, x, t)
+        (gx,) = torch.autograd.grad(loss * 100.0, (x,))
+        out[f"{tag}_input"], out[f"{tag}_target"], out[f"{tag}_loss"], out[f"{tag}_grad"] = x.detach(), t, loss.detach(), gx
+        # the statistics' own backward with arbitrary upstream gradients
+        fn = ref_loader.load("function")
+        x2 = x.detach().clone().requires_grad_(True)
+        m, s_ = fn.calc_mean_std(x2)
+        dm, ds = torch.randn(m.shape, generator=g), torch.randn(s_.shape, generator=g)
+        (g2,) = torch.autograd.grad([m, s_], (x2,), [dm, ds])
+        out[f"{tag}_dmean"], out[f"{tag}_dstd"], out[f"{tag}_dfeat"] = dm, ds, g2
+    save("style_loss", **out)
+
+
 def golden_clamp():
     """train_human.py:276 verbatim, with both trainers' recover_min/max constants (:32-33, train_animal.py:34-35)."""
     out = {}
@@ -473,7 +498,7 @@ def main():
     torch.manual_seed(0)
     np.random.seed(0)
     fns = (golden_adain, golden_decode, golden_accuracy, golden_losses, golden_masks, golden_rectify,
-           golden_targets, golden_ema, golden_optim, golden_clamp, golden_rewarp)
+           golden_targets, golden_ema, golden_optim, golden_style_loss, golden_clamp, golden_rewarp)
     only = set(sys.argv[1:])  # e.g. `make_golden.py clamp` regenerates one fixture
     for fn in fns:
         if not only or fn.__name__.removeprefix("golden_") in only:

@@ -293,6 +293,22 @@ def test_student_step_golden(golden, dev, tag, fuse):
         assert_close_scaled(_flat([x["momentum_buffer"] for x in st]), g[f"{tag}_momentum_buffer"], RTOL, "momentum_buffer")
 
 
+@pytest.mark.parametrize("tag", ["warp", "ragged", "stream", "mid"])
+def test_style_loss_golden(golden, dev, tag):
+    """adain/net.py:137-143 with backward (decoder pre-training job): warp, three-sweep (ragged) and
+    single-pass streaming statistics kernels + the elementwise backward."""
+    g = golden("style_loss")
+    x = C(g[f"{tag}_input"], dev).requires_grad_(True)
+    loss = U.calc_style_loss(x, C(g[f"{tag}_target"], dev))
+    (gx,) = torch.autograd.grad(loss * 100.0, (x,))
+    assert_close_scaled(loss.detach(), g[f"{tag}_loss"], RTOL, "style loss")
+    assert_close_scaled(gx, g[f"{tag}_grad"], RTOL, "d style loss / d input")
+    x2 = C(g[f"{tag}_input"], dev).requires_grad_(True)
+    m, s = U.calc_mean_std(x2)
+    (g2,) = torch.autograd.grad([m, s], (x2,), [C(g[f"{tag}_dmean"], dev), C(g[f"{tag}_dstd"], dev)])
+    assert_close_scaled(g2, g[f"{tag}_dfeat"], RTOL, "calc_mean_std backward")
+
+
 @pytest.mark.parametrize("tag", ["human", "animal"])
 def test_channel_clamp_golden(golden, dev, tag):
     g = golden("clamp")

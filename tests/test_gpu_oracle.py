@@ -319,6 +319,52 @@ def test_ema_16bit_and_stale_plan(dev):
     assert torch.equal(a.weight.detach(), before * 0.5 + 3.0 * 0.5)
 
 
+@pytest.mark.parametrize("shape", [(4, 64, 256, 256), (4, 128, 128, 128), (4, 256, 64, 64), (4, 512, 32, 32)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_style_loss_pretrain_sizes_vs_oracle(dev, shape, dtype):
+    """The four encoder levels of the decoder pre-training job (adain/net.py:158-161; relu1_1 .. relu4_1
+    of a 256x256 crop): statistics, style loss and its gradient against the CPU oracle."""
+    g = torch.Generator().manual_seed(shape[1])
+    x = torch.relu(torch.randn(*shape, generator=g) + 0.2)
+    t = torch.relu(torch.randn(*shape, generator=g) * 1.5 + 0.4)
+    rtol = 1e-5 if dtype == torch.float32 else 1e-2
+    xr = x.to(dtype).float().requires_grad_(True)
+    tr = t.to(dtype).float()
+    loss_ref = R.calc_style_loss(xr, tr)
+    (g_ref,) = torch.autograd.grad(loss_ref, (xr,))
+    xd = x.to(dtype).to(dev).requires_grad_(True)
+    mean, std = U.calc_mean_std(xd.detach())
+    m_ref, s_ref = R.calc_mean_std(xr.detach())
+    assert_close_scaled(mean.float(), m_ref, rtol, "mean")
+    assert_close_scaled(std.float(), s_ref, rtol, "std")
+    loss = U.calc_style_loss(xd, t.to(dtype).to(dev))
+    (gx,) = torch.autograd.grad(loss, (xd,))
+    assert gx.dtype == dtype and gx.shape == xd.shape
+    assert_close_scaled(loss.float(), loss_ref, 10 * rtol if dtype != torch.float32 else rtol, "style loss")
+    if dtype == torch.float32:
+        assert_close_scaled(gx, g_ref, rtol, "style-loss gradient")
+
+
+def test_mean_std_backward_properties(dev):
+    """Size-independent properties of the backward: the gradient of sum(mean) is 1/hw everywhere, the
+    gradient of a plane's std is orthogonal to constants (sums to zero) and has norm 1/sqrt(hw-1)
+    (up to the eps term), and planes do not leak into each other."""
+    torch.manual_seed(1)
+    x = (torch.randn(3, 5, 48, 48, device=dev) * 2 + 1).requires_grad_(True)
+    mean, std = U.calc_mean_std(x)
+    (g,) = torch.autograd.grad(mean.sum(), (x,), retain_graph=True)
+    assert torch.equal(g, torch.full_like(g, 1.0 / (48 * 48)))
+    w = torch.zeros_like(std)
+    w[1, 2] = 1.0
+    (g,) = torch.autograd.grad((std * w).sum(), (x,))
+    assert g[0].abs().max() == 0 and g[2].abs().max() == 0 and g[1, :2].abs().max() == 0
+    plane = g[1, 2].double()
+    assert abs(plane.sum().item()) < 1e-6
+    var = x[1, 2].double().var().item()
+    expect = (var / (var + 1e-5)) ** 0.5 / (48 * 48 - 1) ** 0.5
+    assert abs(plane.norm().item() - expect) < 1e-6 * expect + 1e-9
+
+
 # ---------------------------------------------------------------- clamp + fused loss step ------------
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("shape", [(32, 3, 256, 256), (2, 3, 7, 9), (1, 5, 33, 1)])

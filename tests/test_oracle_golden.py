@@ -198,6 +198,21 @@ def test_student_teacher_step(golden, tag):
         np.testing.assert_array_equal(np.concatenate([t.numpy().ravel() for t in state1]), g[f"{tag}_momentum_buffer"])
 
 
+@pytest.mark.parametrize("tag", ["warp", "ragged", "stream", "mid"])
+def test_style_loss(golden, tag):
+    """adain/net.py:137-143 + autograd through calc_mean_std (the decoder pre-training job)."""
+    g = golden("style_loss")
+    x = T(g[f"{tag}_input"]).clone().requires_grad_(True)
+    loss = R.calc_style_loss(x, T(g[f"{tag}_target"]))
+    (gx,) = torch.autograd.grad(loss * 100.0, (x,))
+    assert torch.equal(loss.detach(), T(g[f"{tag}_loss"]))
+    assert torch.equal(gx, T(g[f"{tag}_grad"]))
+    x2 = T(g[f"{tag}_input"]).clone().requires_grad_(True)
+    m, s = R.calc_mean_std(x2)
+    (g2,) = torch.autograd.grad([m, s], (x2,), [T(g[f"{tag}_dmean"]), T(g[f"{tag}_dstd"])])
+    assert torch.equal(g2, T(g[f"{tag}_dfeat"]))
+
+
 @pytest.mark.parametrize("tag", ["human", "animal"])
 def test_channel_clamp(golden, tag):
     g = golden("clamp")

@@ -314,6 +314,35 @@ def main():
         bench("rewarp_bwd f16 (plan)", shape, 2 * hm16 + plan16.numel() * 2, mk_rwbp, "rewarp")
         bundles.clear()
 
+    # ---- decoder pre-training job: statistics of relu1_1..relu4_1 (N=8, 256x256 crops) + their backward ----
+    for shp in ((8, 64, 256, 256), (8, 128, 128, 128), (8, 256, 64, 64), (8, 512, 32, 32)):
+        n_, c_, h_, w_ = shp
+        cache = {}
+
+        def stat_bufs(r, shp=shp, cache=cache):
+            if r not in cache:
+                x = torch.relu(torch.randn(*shp, device=dev))
+                pl = shp[0] * shp[1]
+                cache[r] = (x, torch.empty(pl, device=dev), torch.empty(pl, device=dev), torch.randn(pl, device=dev),
+                            torch.randn(pl, device=dev), torch.empty_like(x))
+            return cache[r]
+
+        def mk_stat(r, shp=shp, stat_bufs=stat_bufs):
+            x, m, s_, _, _, _ = stat_bufs(r)
+            return lambda: chk(lib.udape_mean_std(x.data_ptr(), _lib.F32, shp[0] * shp[1], shp[2] * shp[3], 1e-5,
+                                                  m.data_ptr(), s_.data_ptr(), st()))
+
+        def mk_stat_bwd(r, shp=shp, stat_bufs=stat_bufs):
+            x, m, s_, dm, ds, dx = stat_bufs(r)
+            chk(lib.udape_mean_std(x.data_ptr(), _lib.F32, shp[0] * shp[1], shp[2] * shp[3], 1e-5, m.data_ptr(), s_.data_ptr(), st()))
+            return lambda: chk(lib.udape_mean_std_bwd(x.data_ptr(), m.data_ptr(), s_.data_ptr(), dm.data_ptr(), ds.data_ptr(),
+                                                      _lib.F32, shp[0] * shp[1], shp[2] * shp[3], dx.data_ptr(), st()))
+
+        nb = n_ * c_ * h_ * w_ * 4
+        bench("mean_std (pre-training)", f"{n_}x{c_}x{h_}x{w_} f32", nb, mk_stat, "stats")
+        bench("mean_std_bwd", f"{n_}x{c_}x{h_}x{w_} f32", 2 * nb, mk_stat_bwd, "stats")
+        cache.clear()
+
     # ---- per-channel clamp of the stylised images (train_human.py:276) -----------------------------------
     for n in (32, 64):
         cache = {}

@@ -9,6 +9,7 @@ first use.
 Reference name → module here
     adain/function.py, lib/models/Style_net.py : calc_mean_std, adaptive_instance_normalization, adain
                                                  (+ adain_mix = Style_net.py:167-168)
+    adain/net.py:137-143                       : calc_style_loss (calc_mean_std with backward, planes up to 256x256)
     lib/keypoint_detection.py                  : get_max_preds, calc_dists, dist_acc, accuracy
     utils.py                                   : get_max_preds_torch, rectify, OldWeightEMA
     lib/models/loss.py                         : JointsMSELoss, ConsLoss
@@ -22,7 +23,8 @@ Reference name → module here
                                                  unscale + update + teacher EMA in one multi-tensor launch)
 """
 from ._lib import UdapeError, library_path, load as load_library
-from .adain import adain, adain_mix, adaptive_instance_normalization, calc_mean_std, channel_clamp
+from .adain import (adain, adain_mix, adaptive_instance_normalization, calc_mean_std, calc_style_loss,
+                    channel_clamp)
 from .ema import ModelEMA, MultiTensorPlan, OldWeightEMA
 from .heatmap import (draw_labelmap_batched, draw_labelmap_ori, generate_target, generate_target_batched,
                       rectify)
@@ -37,7 +39,7 @@ __version__ = "0.1.0"
 
 __all__ = [
     "UdapeError", "library_path", "load_library",
-    "calc_mean_std", "adaptive_instance_normalization", "adain", "adain_mix", "channel_clamp",
+    "calc_mean_std", "calc_style_loss", "adaptive_instance_normalization", "adain", "adain_mix", "channel_clamp",
     "get_max_preds", "get_max_preds_torch", "calc_dists", "dist_acc", "accuracy", "pck_counts",
     "accuracy_from_counts", "decode",
     "JointsMSELoss", "ConsLoss", "joints_mse_loss", "cons_loss", "fused_losses",

@@ -59,6 +59,8 @@ PROTOTYPES = {
     "udape_build_info": (c_char_p, []),
     "udape_last_error": (c_int, [c_char_p, c_size_t]),
     "udape_mean_std": (c_int, [c_void_p, c_int, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p]),
+    "udape_mean_std_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p,
+                                   c_void_p]),
     "udape_adain_mix": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p]),
     "udape_channel_clamp": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,

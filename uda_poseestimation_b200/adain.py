@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["calc_mean_std", "adaptive_instance_normalization", "adain", "adain_mix", "channel_clamp"]
+__all__ = ["calc_mean_std", "calc_style_loss", "adaptive_instance_normalization", "adain", "adain_mix", "channel_clamp"]
 
 
 def _planes(feat: torch.Tensor, name: str):
@@ -22,23 +22,70 @@ def _planes(feat: torch.Tensor, name: str):
     return n, c, h * w
 
 
-def calc_mean_std(feat: torch.Tensor, eps: float = 1e-5):
-    """Per-(n,c) mean and ``sqrt(unbiased var + eps)`` over H*W → two ``[N,C,1,1]`` tensors.
-
-    Same signature and return convention as ``adain/function.py:3-11``.
-    """
-    n, c, hw = _planes(feat, "calc_mean_std")
-    dev = _lib.require_cuda(feat)
-    _lib.no_autograd("calc_mean_std", feat)
-    feat = feat.contiguous()
-    code = _lib.float_code(feat)
+def _mean_std_launch(feat: torch.Tensor, eps: float):
+    n, c, h, w = feat.shape
+    dev = feat.device
     out = torch.empty((2, n, c, 1, 1), dtype=feat.dtype, device=dev)
     if n * c > 0:
         with _lib.on_device(dev):
-            st = _lib.load().udape_mean_std(feat.data_ptr(), code, n * c, hw, float(eps),
+            st = _lib.load().udape_mean_std(feat.data_ptr(), _lib.float_code(feat), n * c, h * w, float(eps),
                                             out[0].data_ptr(), out[1].data_ptr(), _lib.stream_ptr(dev))
         _lib.check(st, "calc_mean_std")
     return out[0], out[1]
+
+
+class _MeanStd(torch.autograd.Function):
+    """calc_mean_std with a hand-written backward (``udape_mean_std_bwd``): what the style loss of the
+    AdaIN decoder pre-training job differentiates through (adain/net.py:137-143)."""
+
+    @staticmethod
+    def forward(ctx, feat, eps):
+        mean, std = _mean_std_launch(feat, eps)
+        ctx.save_for_backward(feat, mean, std)
+        return mean, std
+
+    @staticmethod
+    def backward(ctx, dmean, dstd):
+        feat, mean, std = ctx.saved_tensors
+        n, c, h, w = feat.shape
+        dev = feat.device
+        dfeat = torch.empty_like(feat)
+        if feat.numel() > 0:
+            dm = dmean.to(feat.dtype).contiguous() if dmean is not None else None
+            ds = dstd.to(feat.dtype).contiguous() if dstd is not None else None
+            with _lib.on_device(dev):
+                st = _lib.load().udape_mean_std_bwd(feat.data_ptr(), mean.data_ptr(), std.data_ptr(), _lib.ptr(dm),
+                                                    _lib.ptr(ds), _lib.float_code(feat), n * c, h * w,
+                                                    dfeat.data_ptr(), _lib.stream_ptr(dev))
+            _lib.check(st, "calc_mean_std (backward)")
+        return dfeat, None
+
+
+def calc_mean_std(feat: torch.Tensor, eps: float = 1e-5):
+    """Per-(n,c) mean and ``sqrt(unbiased var + eps)`` over H*W → two ``[N,C,1,1]`` tensors.
+
+    Same signature and return convention as ``adain/function.py:3-11``.  Differentiable: when ``feat``
+    requires grad the backward is one elementwise launch (``adain/net.py:137-143`` back-propagates
+    the style loss through these statistics into the decoder).
+    """
+    _planes(feat, "calc_mean_std")
+    _lib.require_cuda(feat)
+    _lib.float_code(feat)
+    feat = feat.contiguous()
+    if feat.requires_grad and torch.is_grad_enabled():
+        return _MeanStd.apply(feat, float(eps))
+    return _mean_std_launch(feat, eps)
+
+
+def calc_style_loss(input: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """``Net.calc_style_loss`` of the decoder pre-training job (adain/net.py:137-143):
+    ``mse(mean(input), mean(target)) + mse(std(input), std(target))``; gradients flow to ``input``
+    only (the reference asserts ``target.requires_grad is False``)."""
+    assert input.size() == target.size()
+    assert target.requires_grad is False
+    input_mean, input_std = calc_mean_std(input)
+    target_mean, target_std = calc_mean_std(target)
+    return torch.nn.functional.mse_loss(input_mean, target_mean) + torch.nn.functional.mse_loss(input_std, target_std)
 
 
 def adain_mix(content_feat: torch.Tensor, style_feat: torch.Tensor, alpha=1.0, eps: float = 1e-5,

@@ -29,7 +29,7 @@ int check_launch(const char* what) {
 }
 
 // ---- persistent-grid sizing for the TMA-staged kernels (pipeline.cuh) ------------------------
-static int sm_count_of_current_device() {
+int sm_count_of_current_device() {
     static int cached[64] = {0};  // benign race: every thread writes the same value
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;

@@ -20,6 +20,7 @@ namespace udape {
 // ---- host-side error plumbing (api.cu) -------------------------------------------
 int fail(int code, const char* fmt, ...);
 int check_launch(const char* what);
+int sm_count_of_current_device();  // api.cu (cached per device)
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 __host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline bool aligned_to(const void* p, size_t a) {

@@ -113,6 +113,14 @@ class HotPathStep:
         self.out = None
         self._graph_inputs = None
         self.rewarp_kernels = 0
+        self.skip = frozenset()   # profiling only (tools/step_probe.py): chains left out of the step
+        self.marks = None         # profiling only: list of (name, external timing event) filled while capturing
+
+    def _mark(self, name: str):
+        if self.marks is not None:
+            ev = torch.cuda.Event(enable_timing=True, external=True)
+            ev.record(torch.cuda.current_stream())
+            self.marks.append((name, ev))
 
     @property
     def kernels_per_step(self) -> int:
@@ -126,9 +134,14 @@ class HotPathStep:
         if self._side is None or self._side[0].device != dev:
             # the heatmap chains are short, latency-bound kernels on the step's critical path: give them
             # priority over the bandwidth-bound AdaIN / EMA launches when CTAs compete for SM slots
-            hi = -1 if os.environ.get("UDAPE_STEP_PRIORITY", "1") == "1" else 0
+            # ... and the two AdaIN passes priority over the EMA, which then fills whatever the others leave
+            # (measured on B200, tools/step_probe.py: 214 -> 199 us per step; equal priorities make the
+            # block scheduler drain the EMA's 13k CTAs before the first AdaIN CTA is dispatched)
+            on = os.environ.get("UDAPE_STEP_PRIORITY", "1") == "1"
+            hi = int(os.environ.get("UDAPE_CHAIN_PRIORITY", "-2")) if on else 0
+            ad = int(os.environ.get("UDAPE_ADAIN_PRIORITY", "-1")) if on else 0
             self._side = (torch.cuda.Stream(dev, priority=hi), torch.cuda.Stream(dev, priority=hi), torch.cuda.Stream(dev),
-                          torch.cuda.Stream(dev, priority=hi))
+                          torch.cuda.Stream(dev, priority=hi), torch.cuda.Stream(dev, priority=ad))
         return self._side
 
     # -- the step -----------------------------------------------------------------------------------
@@ -145,8 +158,10 @@ class HotPathStep:
         The fork/join is plain stream-event ordering, so it behaves the same eagerly and under
         CUDA-graph capture (where it becomes parallel graph branches)."""
         cur = torch.cuda.current_stream()
-        s_tea, s_stu, s_ema, s_plan = self._streams(inp.y_s.device) if self.parallel else (cur, cur, cur, cur)
+        s_tea, s_stu, s_ema, s_plan, s_adain = self._streams(inp.y_s.device) if self.parallel else (cur, cur, cur, cur, cur)
+
         ema_side = with_ema and self.parallel and self.ema_parallel
+        self._mark("start")
         if self.parallel:
             s_tea.wait_stream(cur)
             s_stu.wait_stream(cur)
@@ -157,6 +172,7 @@ class HotPathStep:
                 # :438 — independent of every other chain of the hot path (in training it follows
                 # scaler.step(stu_optimizer); the student parameters are an input of this step)
                 self.ema.step()
+                self._mark("ema done")
         # teacher forward; student forward + inverse plan + backward
         self.rewarp_kernels = (1 if inp.theta_tea is not None else 0) + (3 if inp.theta_stu is not None else 0)
         # the student's grids are built under autocast (:414): every stage samples on a half grid
@@ -171,13 +187,17 @@ class HotPathStep:
             if self.parallel:
                 s_plan.wait_stream(cur)
             with torch.cuda.stream(s_plan), torch.no_grad():
+                self._mark("plan start")
                 _rewarp.build_inverse_plan(inp.y_t_stu, inp.theta_stu, stu_mask, stu_grid, plan=stu_plan)
+                self._mark("plan done")
                 if self.parallel:
                     plan_ready = torch.cuda.Event()
                     plan_ready.record(s_plan)
             with torch.cuda.stream(s_stu), torch.no_grad():
                 # :417-423 — y_t_stu_recon (the backward runs after the loss step, below)
+                self._mark("stu gather start")
                 y_t_stu_recon = _rewarp.gather(inp.y_t_stu.detach(), inp.theta_stu, stu_mask, stu_grid)
+                self._mark("stu gather done")
                 if self.parallel:
                     recon_ready = torch.cuda.Event()
                     recon_ready.record(s_stu)
@@ -186,10 +206,13 @@ class HotPathStep:
                 y_t_tea = inp.y_t_tea
                 if inp.theta_tea is not None:
                     # :359-372 — teacher heatmaps warped back to the un-augmented frame (k = 1 view)
+                    self._mark("tea gather start")
                     y_t_tea = _rewarp.gather(inp.y_t_tea, inp.theta_tea)
+                    self._mark("tea gather done")
                 # train_human.py:376-383 and :427-430 — one decode pass + k-th value select
                 tt = teacher_targets(y_t_tea, self.sigma, self.mask_ratio, occlude_thresh=self.occlude_thresh,
                                      materialise=not self.fused)
+                self._mark("decode+mask done")
                 if recon_ready is not None:
                     s_tea.wait_event(recon_ready)
                 if self.fused:
@@ -199,6 +222,7 @@ class HotPathStep:
                                                     tt["tea_mask"], lambda_c=self.lambda_c, grad_scale=self.loss_scale,
                                                     tea_preds=tt["preds"], sigma=self.sigma)
                     loss_all, loss_s, loss_c = losses[0], losses[1], losses[2]
+                    self._mark("loss step done")
             if not self.fused:
                 # :432 — consistency loss; its share of `scaler.scale(loss_all).backward()` (:434-436)
                 y_t_stu = y_t_stu_recon.detach().requires_grad_(True)
@@ -211,6 +235,7 @@ class HotPathStep:
                 with torch.no_grad():
                     # backward of :417-423: the consistency gradient scattered back to the student's frame
                     g_c = _rewarp.gather_backward(g_recon, inp.theta_stu, stu_mask, stu_grid, plan=stu_plan)
+                    self._mark("rewarp bwd done")
         with torch.cuda.stream(s_stu):
             if not self.fused:
                 # :425 — supervised loss and its share of the scaled backward
@@ -219,18 +244,29 @@ class HotPathStep:
                 (g_s,) = torch.autograd.grad(loss_s * self.loss_scale, (y_s,))
             with torch.no_grad():
                 # :443-444 — PCK on (y_s, label_s): integer counts stay on the device
+                self._mark("pck start")
                 counts, pred = _pck(inp.y_s, inp.label_s, 0.5)
+                self._mark("pck done")
                 if self.counts_hook is not None:
                     self.counts_hook(counts)
-        with torch.no_grad():
+        t_s2t = t_t2s = None
+        if s_adain is not cur:
+            s_adain.wait_stream(cur)
+        with torch.cuda.stream(s_adain), torch.no_grad():
             # :348-356 — s2t and t2s feature re-normalisation (the decoder conv follows)
-            t_s2t = adain_mix(inp.feat_src, inp.feat_tgt_ori, inp.alpha_s2t)
-            t_t2s = adain_mix(inp.feat_tgt_tea, inp.feat_src_ori, inp.alpha_t2s)
+            if "adain" not in self.skip:
+                t_s2t = adain_mix(inp.feat_src, inp.feat_tgt_ori, inp.alpha_s2t)
+                self._mark("adain s2t done")
+                t_t2s = adain_mix(inp.feat_tgt_tea, inp.feat_src_ori, inp.alpha_t2s)
+                self._mark("adain t2s done")
+        if s_adain is not cur:
+            cur.wait_stream(s_adain)
         if self.parallel:
             cur.wait_stream(s_tea)
             cur.wait_stream(s_stu)
             if ema_side:
                 cur.wait_stream(s_ema)
+        self._mark("join")
         if not self.fused:
             with torch.no_grad():
                 loss_s, loss_c = loss_s.detach(), loss_c.detach()
@@ -262,6 +298,8 @@ class HotPathStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
+        if self.marks is not None:
+            self.marks.clear()     # keep only the events recorded by the captured pass
         with torch.cuda.graph(self.graph):
             self.out = fn(inp)
         self._graph_inputs = inp
