@@ -212,7 +212,7 @@ def run_reference_arm(args, cfg, rank):
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
 
 
 def workload_config(cfg, n_gpus, graph=True, fused=True, ema="graph"):
@@ -465,7 +465,30 @@ def run_b200_arm(args, cfg, rank, world, local):
     if grad_ar is not None:
         line["grad_allreduce"] = grad_ar
         line["config"]["pck_allreduce"] = "inside the step graph (PCK chain)" if (ar_in_step and use_graph) else "after the step"
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The driver parses stdout as ONE JSON line.  Native libraries write there too (NCCL prints its
+    version banner on fd 1 at NCCL_DEBUG=VERSION and above), so fd 1 is pointed at stderr for the whole
+    run and the JSON line is written to a private duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json_line(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -490,6 +513,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    relaunch = args.impl == "b200" and args.gpus > 1 and "WORLD_SIZE" not in os.environ
+    if not relaunch:
+        claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args, cfg, rank)  # rank 0 alone works; the others exit 0
         return
