@@ -239,8 +239,11 @@ def test_rewarp_backward_long_lists(dev):
         assert np.bincount(src[src >= 0]).max() > 4
 
 
-def test_rewarp_cluster_kernels_under_contention(dev):
-    """The CTAs of a cluster exchange the composed map / the inverted lists through distributed shared
+@pytest.mark.parametrize("cluster", ["1", "2", "4", "8"])
+def test_rewarp_cluster_kernels_under_contention(dev, cluster, monkeypatch):
+    """Every cluster size gives the same bits (the default policy picks one CTA per sample at this batch
+    size; smaller batches split a sample's channels over a cluster of 2, 4 or 8 CTAs).
+    The CTAs of a cluster exchange the composed map / the inverted lists through distributed shared
     memory; when other kernels compete for the SMs the CTAs of a cluster drift apart in time, which is
     what exposes a missing cluster barrier.  Forward and backward are repeated on two high-priority
     streams next to a bandwidth hog and must reproduce the quiet result bit for bit."""
@@ -249,8 +252,11 @@ def test_rewarp_cluster_kernels_under_contention(dev):
     g = torch.randn(b, k, 64, 64, device=dev).half()
     t = RW.stage_table(RW.recon_stages(S.aug_params(b, seed=72, shear_y=True), 4.0, b), 64, 64, torch.float16, torch.float16)
     theta = t[0].to(dev)
+    monkeypatch.setenv("UDAPE_REWARP_GLOBAL", "1")      # reference bits: the route without clusters
     ref_f = RW.gather(y, theta, t[1], torch.float16)
     ref_b = RW.gather_backward(g, theta, t[1], torch.float16)
+    monkeypatch.delenv("UDAPE_REWARP_GLOBAL")
+    monkeypatch.setenv("UDAPE_REWARP_CLUSTER", cluster)
     plans = [RW.inverse_plan_buffer(y) for _ in range(2)]
     torch.cuda.synchronize()
     hog_a, hog_b = torch.empty(64 << 20, device=dev), torch.empty(64 << 20, device=dev)

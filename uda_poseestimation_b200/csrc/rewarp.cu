@@ -915,16 +915,20 @@ static int fill_common(RewarpArgs& a, const char* name, int views, int stages, i
     return UDAPE_OK;
 }
 
-// CTAs per sample (= cluster size): the smallest power of two that gives ~4 CTAs per SM, at most the
+// CTAs per sample (= cluster size): the smallest power of two that gives at least 32 CTAs, at most the
 // portable cluster limit of 8 and the channel count
 static int cluster_size_for(int64_t B, int64_t C, int64_t hw) {
     if (const char* e = std::getenv("UDAPE_REWARP_CLUSTER")) {   // tuning / tests: force 1, 2, 4 or 8
         const int n = std::atoi(e);
         if (n == 1 || ((n == 2 || n == 4 || n == 8) && n <= C && hw / n >= 8)) return n;
     }
-    // measured (B200, 64x64 planes): best with 1.5-2 CTAs per SM in total — more CTAs repeat the per-CTA
-    // set-up (offset fetch, stride pick, pipeline fill), fewer leave SMs idle
-    const int64_t want = 3 * static_cast<int64_t>(sm_count()) / 2;
+    // Measured on B200 (64x64 planes, batch 32, tools/step_probe.py): timed ALONE the gather is fastest with
+    // 1.5-2 CTAs per SM (clusters of 8: 7.7 us against ~12 us for one CTA per sample), but inside the step —
+    // beside the AdaIN / EMA streams and the other heatmap chains — every doubling of the cluster costs
+    // ~6 us of step time (184 / 190 / 197 / 214 us for clusters of 1 / 2 / 4 / 8): a cluster needs all of its
+    // CTAs placed in one GPC at once, which stalls the block scheduler of a busy GPU, and its CTAs hold SM
+    // slots while moving little data.  One CTA per sample from 32 samples up; smaller batches still split.
+    const int64_t want = 32;
     int n = 1;
     while (n < 8 && 2 * n <= C && hw / (2 * n) >= 8 && B * n < want) n *= 2;   // slices of the map hold >= 8 entries
     return n;
@@ -1078,6 +1082,7 @@ extern "C" int udape_rewarp_bwd(const void* grad_out, const float* theta, int st
         UDAPE_REQUIRE(smem_route_words(H, W, es) != 0 && aligned16(grad_out) && aligned16(grad_in) && aligned16(inverse_plan),
                       UDAPE_ERR_ARG, "udape_rewarp_bwd: the inverse plan does not apply to this plane / alignment");
         const int bw = smem_route_words(H, W, es);
+        // (2 CTAs per SM measured best inside the step as well: 184 / 188 / 204 / 238 us for 296 / 148 / 64 / 32 CTAs)
         a.cpc = channels_per_cta(B, C, 2 * static_cast<int64_t>(sm_count()));
         const int64_t grid = B * ((C + a.cpc - 1) / a.cpc);
         const size_t smem = kRwRing * sizeof(uint32_t) * static_cast<size_t>(bw);
