@@ -1,2 +1,2 @@
-export PROBE_TIMELINE=0
-for n in 1 2; do for t in 296 148 64 32; do echo "#### rewarp cluster $n bwd target $t"; UDAPE_REWARP_CLUSTER=$n UDAPE_REWARP_BWD_TARGET=$t python tools/step_probe.py 2>&1 | grep -E "^full step|^no EMA|heatmap chains alone"; done; done
+export PROBE_TIMELINE=1
+for n in 1 2 4 8; do echo "#### plan cluster $n"; UDAPE_REWARP_PLAN_CLUSTER=$n python tools/step_probe.py 2>&1 | grep -vE "^--|ema ctas|serial|no re-warp|no AdaIN  |^no EMA" | head -24; done
