@@ -368,6 +368,49 @@ def main():
     bench("ema_multi f32", f"PoseResNet-101 {n_params}", 3 * n_params * 4, lambda r: (lambda: plan.run(0.999, 0.001, 0)), "ema")
     plan_c = MultiTensorPlan(teacher, student, as_bytes=True)
     bench("ema_multi copy", f"PoseResNet-101 {n_params}", 2 * n_params * 4, lambda r: (lambda: plan_c.run(0.0, 1.0, 1)), "ema")
+    # what the reference runs for the same work on the same device (eager torch op sequences, written
+    # out here from adain/function.py:3-22 + Style_net.py:167-168 and utils.py:21-25; wall time on the stream)
+    if (not only or "ema" in only or "adain" in only) and not args.no_sustained:
+        def eager_time(fn, reps=5):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record(); fn(); b_.record(); torch.cuda.synchronize()
+                ts.append(a_.elapsed_time(b_))
+            return float(np.median(ts)) * 1e3
+
+        c_ = torch.relu(torch.randn(32, 512, 32, 32, device=dev))
+        s_ = torch.relu(torch.randn(32, 512, 32, 32, device=dev) * 2)
+
+        def eager_stats(feat, eps=1e-5):
+            n_, ch = feat.size()[:2]
+            var = feat.view(n_, ch, -1).var(dim=2) + eps
+            return feat.view(n_, ch, -1).mean(dim=2).view(n_, ch, 1, 1), var.sqrt().view(n_, ch, 1, 1)
+
+        def eager_adain_mix():
+            size = c_.size()
+            sm, ss = eager_stats(s_)
+            cm, cs = eager_stats(c_)
+            t = (c_ - cm.expand(size)) / cs.expand(size) * ss.expand(size) + sm.expand(size)
+            return 0.37 * t + (1 - 0.37) * c_
+
+        def eager_ema():
+            with torch.no_grad():
+                for tp, sp in zip(teacher, student):
+                    tp.mul_(0.999)
+                    tp.add_(sp * 0.001)
+
+        for label, fn, nb in (("torch eager adain+mix (reference ops)", eager_adain_mix, 3 * c_.numel() * 4),
+                              ("torch eager OldWeightEMA loop (969 launches)", eager_ema, 3 * n_params * 4)):
+            us = eager_time(fn)
+            rows.append(dict(kernel=label, shape="32x512x32x32 f32" if "adain" in label else f"PoseResNet-101 {n_params}",
+                             mbytes=nb / 1e6, us=us, gbs=nb / us / 1e3, note="eager reference op sequence, not a udape kernel"))
+            print(f"{label:<48}{nb / 1e6:9.1f} MB {us:8.1f} us {nb / us / 1e3:7.0f} GB/s (algorithmic bytes)", flush=True)
+        del c_, s_
+
     # reference point: torch's own copy of the same bytes (what MEASURED_PEAKS measures)
     big_a = torch.empty(n_params, device=dev)
     big_b = torch.empty(n_params, device=dev)
