@@ -115,6 +115,15 @@ UDAPE_API int udape_decode(const void* hm, int dtype, int64_t planes, int64_t h,
                  int64_t* position, float occlude_thresh, uint8_t* conf_table,
                  double sigma, void* rectified, void* stream);
 
+/* udape_decode + udape_mask_select (below) in ONE launch: the CTA that finishes last selects the kth
+ * smallest of maxvals_f32[planes] (required here) and writes thresh_out / tea_mask_out exactly as
+ * udape_mask_select does.  ticket: one zeroed uint32, left zero (self-resetting). */
+UDAPE_API int udape_decode_select(const void* hm, int dtype, int64_t planes, int64_t h, int64_t w,
+                        int32_t* idx, float* preds, void* maxvals, float* maxvals_f32,
+                        int64_t* position, float occlude_thresh, uint8_t* conf_table,
+                        double sigma, void* rectified, int64_t kth, const float* tea_mask_in,
+                        float* thresh_out, uint8_t* tea_mask_out, uint32_t* ticket, void* stream);
+
 /* ---- a11: consistency mask — train_human.py:427-430 ----------------------------------
  * thresh = kth smallest (1-based kth, NaN sorts last: torch.kthvalue) of activates[n];
  * tea_mask_out[i] = (tea_mask_in[i] * activates[i]) > thresh   (tea_mask_in NULL = ones).

@@ -242,6 +242,40 @@ def test_mask_select_all_ranks(dev):
 
 
 # ---------------------------------------------------------------- target writers ----------------------
+@pytest.mark.parametrize("cfg,rectify", [("C1", True), ("C2", False), ("C4", True), ("C5", False), ("C5", True)])
+def test_decode_select_equals_decode_then_select(dev, cfg, rectify):
+    """udape_decode_select (k-th select in the last CTA of the decode launch; C5 without a rectified map takes
+    the TMA-staged persistent kernel) against the two-launch sequence and the oracle: identical bits, also
+    when the ticket word is reused by back-to-back launches and with a tea_mask_in / NaN planes."""
+    from uda_poseestimation_b200.keypoint_detection import decode
+    c = S.CONFIGS[cfg]
+    b, k = c["batch"], c["joints"]
+    hm = S.heatmaps(b, k, seed=33, peak=(0.3, 1.2))
+    hm[0, 1] = float("nan")
+    hm[1, 0] = -1.0
+    tm = (torch.rand(b, k, generator=torch.Generator().manual_seed(3)) > 0.3).float()
+    x = hm.to(dev)
+    for ratio in (0.5, 1.0 / (b * k) + 1e-9, 1.0):
+        kth = max(1, int(ratio * b * k))
+        for tea_mask in (None, tm):
+            two = decode(x, want_preds=True, want_maxvals_f32=True, rectify_sigma=2.0 if rectify else None)
+            m2, t2 = U.consistency_mask(two["maxvals_f32"], kth / (b * k) + 1e-12, None if tea_mask is None else tea_mask.to(dev))
+            for _ in range(3):
+                one = decode(x, want_preds=True, want_maxvals_f32=True, rectify_sigma=2.0 if rectify else None,
+                             select_kth=kth, select_tea_mask=None if tea_mask is None else tea_mask.to(dev))
+                assert torch.equal(one["tea_mask"], m2)
+                assert torch.equal(one["mask_thresh"].view(1).view(torch.int32), t2.view(1).view(torch.int32))
+                assert torch.equal(one["preds"], two["preds"])
+                assert torch.equal(one["maxvals_f32"].view(torch.int32), two["maxvals_f32"].view(torch.int32))
+                if rectify:
+                    assert torch.equal(one["rectified"].view(torch.int32), two["rectified"].view(torch.int32))
+    # oracle: torch.kthvalue + the reference expression
+    ref_mask, ref_thresh, _ = R.consistency_mask(hm, 0.5)
+    one = decode(x, want_maxvals_f32=True, select_kth=int(0.5 * b * k))
+    assert torch.equal(one["tea_mask"].cpu(), ref_mask)
+    assert float(one["mask_thresh"]) == float(ref_thresh) or (np.isnan(float(ref_thresh)) and np.isnan(float(one["mask_thresh"])))
+
+
 @pytest.mark.parametrize("cfg", ["C1", "C4"])
 def test_generate_target_vs_oracle(dev, cfg):
     b, k, sigma = S.CONFIGS[cfg]["batch"], S.CONFIGS[cfg]["joints"], S.CONFIGS[cfg]["sigma"]

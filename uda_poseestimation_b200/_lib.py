@@ -67,6 +67,9 @@ PROTOTYPES = {
                                     c_void_p]),
     "udape_decode": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_float, c_void_p, c_double, c_void_p, c_void_p]),
+    "udape_decode_select": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_float, c_void_p, c_double, c_void_p, c_int64, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     "udape_mask_select": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "udape_pck_counts": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64,
                                  c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

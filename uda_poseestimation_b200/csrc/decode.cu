@@ -121,12 +121,87 @@ __device__ __forceinline__ uint4 rectified_vector_at(int x, int y, int w, const 
     }
     return pack16<T>(f);
 }
+// ---- k-th value + tea_mask ----------------------------------------------------------------------
+// 4-pass radix select on the ordered key by ONE CTA of any size (exact; NaN sorts last like
+// torch.kthvalue), then tea_mask = (tea_mask_in * activates) > thresh.  Runs as its own single-CTA
+// kernel (udape_mask_select) or in the last CTA of the decode launch (udape_decode_select), where
+// `act` was written by the other CTAs of the same grid: read through L2 (__ldcg).
+struct SelectArgs {
+    int kth;                    // 1-based rank
+    const float* tm_in;         // optional
+    float* thresh_out;          // optional
+    uint8_t* tm_out;            // optional
+    uint32_t* ticket;           // decode launch only: zeroed, self-resetting; NULL = no select
+};
+
+__device__ __forceinline__ void select_body(const float* __restrict__ act, int n, const SelectArgs& sa) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned int s_prefix, s_mask, s_k;
+    const int nthreads = blockDim.x;
+    if (threadIdx.x == 0) { s_prefix = 0u; s_mask = 0u; s_k = static_cast<unsigned>(sa.kth); }
+    for (int pass = 3; pass >= 0; --pass) {
+        const int shift = pass * 8;
+        for (int i = threadIdx.x; i < 256; i += nthreads) hist[i] = 0u;
+        __syncthreads();
+        const unsigned prefix = s_prefix, mask = s_mask;
+        for (int i = threadIdx.x; i < n; i += nthreads) {
+            const uint32_t key = order_key(__ldcg(act + i));
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            // warp 0 finds the bin holding rank k: lane l owns bins [8l, 8l+8)
+            const unsigned k = s_k;
+            unsigned c[8], lane_sum = 0u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { c[j] = hist[8 * threadIdx.x + j]; lane_sum += c[j]; }
+            unsigned incl = lane_sum;  // inclusive prefix over lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (threadIdx.x >= o) incl += t;
+            }
+            const unsigned excl = incl - lane_sum;
+            const unsigned owner = __ballot_sync(0xffffffffu, incl >= k);
+            if (static_cast<int>(threadIdx.x) == __ffs(owner) - 1) {
+                unsigned cum = excl;
+                int b = 0;
+#pragma unroll
+                for (; b < 7; ++b) {
+                    if (cum + c[b] >= k) break;
+                    cum += c[b];
+                }
+                s_k = k - cum;
+                s_prefix = prefix | (static_cast<unsigned>(8 * threadIdx.x + b) << shift);
+                s_mask = mask | (255u << shift);
+            }
+        }
+        __syncthreads();
+    }
+    const float thresh = key_value(s_prefix);
+    if (threadIdx.x == 0 && sa.thresh_out) *sa.thresh_out = thresh;
+    if (sa.tm_out) {
+        for (int i = threadIdx.x; i < n; i += nthreads) {
+            const float v = __ldcg(act + i);
+            const float a = sa.tm_in ? sa.tm_in[i] * v : v;
+            sa.tm_out[i] = (a > thresh) ? 1 : 0;
+        }
+    }
+}
+
+constexpr int kSelThreads = 1024;
+
+__global__ void __launch_bounds__(kSelThreads)
+mask_select_kernel(const float* __restrict__ act, int n, SelectArgs sa) {
+    select_body(act, n, sa);
+}
+
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(kDecThreads)
 decode_kernel(const T* __restrict__ hm, int hw, int w, int h, int32_t* __restrict__ idx_out,
               float* __restrict__ preds, T* __restrict__ maxvals, float* __restrict__ maxvals_f32,
               int64_t* __restrict__ position, float occlude_thresh, uint8_t* __restrict__ conf_table,
-              GaussWindow gw, T* __restrict__ rect) {
+              GaussWindow gw, T* __restrict__ rect, SelectArgs sel) {
     __shared__ unsigned long long red[32];
     const int64_t plane = blockIdx.x;
     const T* p = hm + plane * hw;
@@ -151,8 +226,7 @@ decode_kernel(const T* __restrict__ hm, int hw, int w, int h, int32_t* __restric
         if (position) { position[2 * plane] = ix; position[2 * plane + 1] = iy; }
         if (conf_table) conf_table[plane] = (mv >= occlude_thresh) ? 1 : 0;
     }
-    if (rect == nullptr) return;
-
+    if (rect != nullptr) {
     // ---- rectify: utils.py:84-107 ----
     const float mu_x = positive ? static_cast<float>(ix) : 0.0f;
     const float mu_y = positive ? static_cast<float>(iy) : 0.0f;
@@ -175,6 +249,10 @@ decode_kernel(const T* __restrict__ hm, int hw, int w, int h, int32_t* __restric
             r[i] = from_f32<T>(rectified_value(x, y, geom, gw, tab));
         }
     }
+    }
+    // train_human.py:427-430 in the same launch: the CTA that finishes last selects the k-th activation
+    if (sel.ticket != nullptr && last_block_done(sel.ticket, gridDim.x))
+        select_body(maxvals_f32, static_cast<int>(gridDim.x), sel);
 }
 
 // ---- TMA-staged warp-per-plane arg-max (pipeline.cuh) ---------------------------------------
@@ -228,7 +306,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 decode_tma_kernel(const T* __restrict__ hm, int64_t planes, int hw, int w, int h, int32_t* __restrict__ idx_out,
                   float* __restrict__ preds, T* __restrict__ maxvals, float* __restrict__ maxvals_f32,
                   int64_t* __restrict__ position, float occlude_thresh, uint8_t* __restrict__ conf_table,
-                  GaussWindow gw, T* __restrict__ rect, int group, int stages) {
+                  GaussWindow gw, T* __restrict__ rect, int group, int stages, SelectArgs sel) {
     constexpr int EPV = Vec16<T>::EPV;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ PipeBarriers bars;
@@ -246,8 +324,7 @@ decode_tma_kernel(const T* __restrict__ hm, int64_t planes, int hw, int w, int h
             mbar_expect_tx(full, np * plane_bytes);
             bulk_load(smem + static_cast<size_t>(s) * stage_bytes, hm + first * hw, np * plane_bytes, full);
         });
-        return;
-    }
+    } else {
     constexpr int kMaxGroup = 8;  // pipe_geometry's max_group
     PlaneMax pm[kMaxGroup];
     pipe_consume(
@@ -299,6 +376,9 @@ decode_tma_kernel(const T* __restrict__ hm, int64_t planes, int hw, int w, int h
                 }
             }
         });
+    }
+    if (sel.ticket != nullptr && last_block_done(sel.ticket, gridDim.x))
+        select_body(maxvals_f32, static_cast<int>(planes), sel);
 }
 
 // ---- PCK -------------------------------------------------------------------------------------
@@ -406,71 +486,11 @@ pck_tma_kernel(const TO* __restrict__ output, const TT* __restrict__ target, int
     if (last_block_done(ticket, gridDim.x)) pck_reduce_flags(flags, planes, joints, hits, valid);
 }
 
-// ---- k-th value + tea_mask ----------------------------------------------------------------------
-// Single-CTA 4-pass radix select on the ordered key (exact; NaN sorts last like
-// torch.kthvalue), then tea_mask = (tea_mask_in * activates) > thresh.
-constexpr int kSelThreads = 1024;
-
-__global__ void __launch_bounds__(kSelThreads)
-mask_select_kernel(const float* __restrict__ act, int n, int kth, const float* __restrict__ tm_in,
-                   float* __restrict__ thresh_out, uint8_t* __restrict__ tm_out) {
-    __shared__ unsigned int hist[256];
-    __shared__ unsigned int s_prefix, s_mask, s_k;
-    if (threadIdx.x == 0) { s_prefix = 0u; s_mask = 0u; s_k = static_cast<unsigned>(kth); }
-    for (int pass = 3; pass >= 0; --pass) {
-        const int shift = pass * 8;
-        if (threadIdx.x < 256) hist[threadIdx.x] = 0u;
-        __syncthreads();
-        const unsigned prefix = s_prefix, mask = s_mask;
-        for (int i = threadIdx.x; i < n; i += kSelThreads) {
-            const uint32_t key = order_key(act[i]);
-            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
-        }
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            // warp 0 finds the bin holding rank k: lane l owns bins [8l, 8l+8)
-            const unsigned k = s_k;
-            unsigned c[8], lane_sum = 0u;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { c[j] = hist[8 * threadIdx.x + j]; lane_sum += c[j]; }
-            unsigned incl = lane_sum;  // inclusive prefix over lanes
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (threadIdx.x >= o) incl += t;
-            }
-            const unsigned excl = incl - lane_sum;
-            const unsigned owner = __ballot_sync(0xffffffffu, incl >= k);
-            if (static_cast<int>(threadIdx.x) == __ffs(owner) - 1) {
-                unsigned cum = excl;
-                int b = 0;
-#pragma unroll
-                for (; b < 7; ++b) {
-                    if (cum + c[b] >= k) break;
-                    cum += c[b];
-                }
-                s_k = k - cum;
-                s_prefix = prefix | (static_cast<unsigned>(8 * threadIdx.x + b) << shift);
-                s_mask = mask | (255u << shift);
-            }
-        }
-        __syncthreads();
-    }
-    const float thresh = key_value(s_prefix);
-    if (threadIdx.x == 0 && thresh_out) *thresh_out = thresh;
-    if (tm_out) {
-        for (int i = threadIdx.x; i < n; i += kSelThreads) {
-            const float a = tm_in ? tm_in[i] * act[i] : act[i];
-            tm_out[i] = (a > thresh) ? 1 : 0;
-        }
-    }
-}
-
 template <typename T>
 static int launch_decode(const void* hm, int64_t planes, int64_t h, int64_t w, int32_t* idx,
                          float* preds, void* maxvals, float* maxvals_f32, int64_t* position,
                          float occlude_thresh, uint8_t* conf_table, double sigma, void* rect,
-                         cudaStream_t st) {
+                         const SelectArgs& sel, cudaStream_t st) {
     const int hw = static_cast<int>(h * w);
     const bool vec = aligned16(hm) && (hw % Vec16<T>::EPV) == 0 && (rect == nullptr || aligned16(rect));
     const GaussWindow gw = make_window(rect ? sigma : 1.0);
@@ -487,17 +507,17 @@ static int launch_decode(const void* hm, int64_t planes, int64_t h, int64_t w, i
         decode_tma_kernel<T><<<pipe_grid((planes + pg.group - 1) / pg.group), pg.threads, smem, st>>>(
             static_cast<const T*>(hm), planes, hw, static_cast<int>(w), static_cast<int>(h), idx, preds,
             static_cast<T*>(maxvals), maxvals_f32, position, occlude_thresh, conf_table, gw,
-            static_cast<T*>(rect), pg.group, pg.stages);
+            static_cast<T*>(rect), pg.group, pg.stages, sel);
     } else if (vec)
         decode_kernel<T, true><<<grid, kDecThreads, 0, st>>>(
             static_cast<const T*>(hm), hw, static_cast<int>(w), static_cast<int>(h), idx, preds,
             static_cast<T*>(maxvals), maxvals_f32, position, occlude_thresh, conf_table, gw,
-            static_cast<T*>(rect));
+            static_cast<T*>(rect), sel);
     else
         decode_kernel<T, false><<<grid, kDecThreads, 0, st>>>(
             static_cast<const T*>(hm), hw, static_cast<int>(w), static_cast<int>(h), idx, preds,
             static_cast<T*>(maxvals), maxvals_f32, position, occlude_thresh, conf_table, gw,
-            static_cast<T*>(rect));
+            static_cast<T*>(rect), sel);
     return check_launch("udape_decode");
 }
 
@@ -539,10 +559,10 @@ static int launch_pck(const void* output, const void* target, int64_t planes, in
 
 using namespace udape;
 
-extern "C" int udape_decode(const void* hm, int dtype, int64_t planes, int64_t h, int64_t w,
-                            int32_t* idx, float* preds, void* maxvals, float* maxvals_f32,
-                            int64_t* position, float occlude_thresh, uint8_t* conf_table,
-                            double sigma, void* rectified, void* stream) {
+static int decode_entry(const void* hm, int dtype, int64_t planes, int64_t h, int64_t w,
+                        int32_t* idx, float* preds, void* maxvals, float* maxvals_f32,
+                        int64_t* position, float occlude_thresh, uint8_t* conf_table,
+                        double sigma, void* rectified, const SelectArgs& sel, void* stream) {
     UDAPE_REQUIRE(hm, UDAPE_ERR_NULL, "udape_decode: hm is NULL");
     UDAPE_REQUIRE(planes > 0 && h > 0 && w > 0 && planes < (1ll << 31) && h * w < (1ll << 31),
                   UDAPE_ERR_SHAPE, "udape_decode: bad extents planes=%lld h=%lld w=%lld",
@@ -557,8 +577,33 @@ extern "C" int udape_decode(const void* hm, int dtype, int64_t planes, int64_t h
     if (rectified) {
         UDAPE_REQUIRE(sigma > 0.0 && sigma < 1e4, UDAPE_ERR_ARG, "udape_decode: sigma %g out of range", sigma);
     }
-    UDAPE_DISPATCH_FLOAT(dtype, T, return launch_decode<T>(hm, planes, h, w, idx, preds, maxvals, maxvals_f32, position, occlude_thresh, conf_table, sigma, rectified, as_stream(stream)));
+    UDAPE_DISPATCH_FLOAT(dtype, T, return launch_decode<T>(hm, planes, h, w, idx, preds, maxvals, maxvals_f32, position, occlude_thresh, conf_table, sigma, rectified, sel, as_stream(stream)));
     return UDAPE_OK;
+}
+
+extern "C" int udape_decode(const void* hm, int dtype, int64_t planes, int64_t h, int64_t w,
+                            int32_t* idx, float* preds, void* maxvals, float* maxvals_f32,
+                            int64_t* position, float occlude_thresh, uint8_t* conf_table,
+                            double sigma, void* rectified, void* stream) {
+    const SelectArgs none = {0, nullptr, nullptr, nullptr, nullptr};
+    return decode_entry(hm, dtype, planes, h, w, idx, preds, maxvals, maxvals_f32, position, occlude_thresh, conf_table,
+                        sigma, rectified, none, stream);
+}
+
+extern "C" int udape_decode_select(const void* hm, int dtype, int64_t planes, int64_t h, int64_t w,
+                                   int32_t* idx, float* preds, void* maxvals, float* maxvals_f32,
+                                   int64_t* position, float occlude_thresh, uint8_t* conf_table,
+                                   double sigma, void* rectified, int64_t kth, const float* tea_mask_in,
+                                   float* thresh_out, uint8_t* tea_mask_out, uint32_t* ticket, void* stream) {
+    UDAPE_REQUIRE(maxvals_f32 && ticket, UDAPE_ERR_NULL, "udape_decode_select: maxvals_f32 and ticket are required");
+    UDAPE_REQUIRE(aligned_to(ticket, 4) && (!thresh_out || aligned_to(thresh_out, 4)) && (!tea_mask_in || aligned_to(tea_mask_in, 4)),
+                  UDAPE_ERR_ALIGN, "udape_decode_select: misaligned pointer");
+    // torch.kthvalue raises for k outside [1, n]
+    UDAPE_REQUIRE(kth >= 1 && kth <= planes, UDAPE_ERR_ARG, "udape_decode_select: kth=%lld outside [1,%lld]",
+                  (long long)kth, (long long)planes);
+    const SelectArgs sel = {static_cast<int>(kth), tea_mask_in, thresh_out, tea_mask_out, ticket};
+    return decode_entry(hm, dtype, planes, h, w, idx, preds, maxvals, maxvals_f32, position, occlude_thresh, conf_table,
+                        sigma, rectified, sel, stream);
 }
 
 extern "C" int udape_mask_select(const float* activates, int64_t n, int64_t kth,
@@ -569,8 +614,8 @@ extern "C" int udape_mask_select(const float* activates, int64_t n, int64_t kth,
     // torch.kthvalue raises for k outside [1, n]
     UDAPE_REQUIRE(kth >= 1 && kth <= n, UDAPE_ERR_ARG, "udape_mask_select: kth=%lld outside [1,%lld]",
                   (long long)kth, (long long)n);
-    mask_select_kernel<<<1, kSelThreads, 0, as_stream(stream)>>>(
-        activates, static_cast<int>(n), static_cast<int>(kth), tea_mask_in, thresh_out, tea_mask_out);
+    const SelectArgs sa = {static_cast<int>(kth), tea_mask_in, thresh_out, tea_mask_out, nullptr};
+    mask_select_kernel<<<1, kSelThreads, 0, as_stream(stream)>>>(activates, static_cast<int>(n), sa);
     return check_launch("udape_mask_select");
 }
 

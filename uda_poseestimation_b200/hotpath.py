@@ -125,10 +125,10 @@ class HotPathStep:
     @property
     def kernels_per_step(self) -> int:
         """Kernels of libudape_b200.so launched by run() (memset nodes for tickets/counters not counted):
-        fused: 2 adain, decode, mask_select, loss_step, pck, ema;  unfused: 2 adain, decode+rectify,
-        mask_select, mse fwd/bwd, cons fwd/bwd, pck, ema;  + 4 with the re-warp tables (teacher forward,
+        fused: 2 adain, decode (+ k-th select in its last CTA), loss_step, pck, ema;  unfused: 2 adain,
+        decode+rectify(+select), mse fwd/bwd, cons fwd/bwd, pck, ema;  + 4 with the re-warp tables (teacher forward,
         student forward, its inverse plan, student backward)."""
-        return (7 if self.fused else 10) + self.rewarp_kernels
+        return (6 if self.fused else 9) + self.rewarp_kernels
 
     def _streams(self, dev):
         if self._side is None or self._side[0].device != dev:

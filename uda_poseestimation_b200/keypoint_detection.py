@@ -43,12 +43,15 @@ def _as_cuda_heatmap(x, name: str):
 
 def decode(hm: torch.Tensor, *, want_idx=False, want_preds=False, want_maxvals=False,
            want_maxvals_f32=False, want_position=False, occlude_thresh: float | None = None,
-           rectify_sigma: float | None = None) -> dict:
+           rectify_sigma: float | None = None, select_kth: int | None = None,
+           select_tea_mask: torch.Tensor | None = None) -> dict:
     """One launch of ``udape_decode`` over ``hm[B,K,H,W]``; returns only the requested outputs.
 
     Keys: ``idx`` int32[B,K], ``preds`` float32[B,K,2], ``maxvals`` hm.dtype[B,K,1],
     ``maxvals_f32`` float32[B,K], ``position`` int64[B,K,2], ``conf_table`` bool[B,K],
-    ``rectified`` hm.dtype[B,K,H,W].
+    ``rectified`` hm.dtype[B,K,H,W].  With ``select_kth`` (1-based rank, train_human.py:429) the same
+    launch also selects the k-th smallest activation (``udape_decode_select``): ``mask_thresh`` 0-dim
+    float32 and ``tea_mask`` bool[B,K] = ``(select_tea_mask * maxvals) > mask_thresh``.
     """
     dev = _lib.require_cuda(hm)
     if hm.dim() != 4:
@@ -65,7 +68,32 @@ def decode(hm: torch.Tensor, *, want_idx=False, want_preds=False, want_maxvals=F
     pos = torch.empty((b, k, 2), dtype=torch.int64, device=dev) if want_position else None
     conf = torch.empty((b, k), dtype=torch.bool, device=dev) if occlude_thresh is not None else None
     rect = torch.empty_like(hm) if rectify_sigma is not None else None
-    if planes > 0 and h * w > 0:
+    tea_mask = thresh = None
+    if select_kth is not None:
+        if not (1 <= select_kth <= planes):
+            raise IndexError(f"kthvalue(): selected number k out of range for dimension 0 (k={select_kth}, n={planes})")
+        if mv32 is None:
+            mv32 = torch.empty((b, k), dtype=torch.float32, device=dev)
+        tm_in = None
+        if select_tea_mask is not None:
+            _lib.require_cuda(hm, select_tea_mask)
+            if select_tea_mask.numel() != planes:
+                raise ValueError("decode: select_tea_mask must have one entry per (b, k)")
+            tm_in = select_tea_mask.detach().to(torch.float32).contiguous()
+        tea_mask = torch.empty((b, k), dtype=torch.bool, device=dev)
+        thresh = torch.empty((), dtype=torch.float32, device=dev)
+        with _lib.on_device(dev):
+            st = _lib.load().udape_decode_select(
+                hm.data_ptr(), code, planes, h, w, _lib.ptr(idx), _lib.ptr(preds), _lib.ptr(maxvals),
+                _lib.ptr(mv32), _lib.ptr(pos), float(occlude_thresh if occlude_thresh is not None else 0.0),
+                _lib.ptr(conf), float(rectify_sigma if rectify_sigma is not None else 1.0), _lib.ptr(rect),
+                int(select_kth), _lib.ptr(tm_in), thresh.data_ptr(), tea_mask.data_ptr(), _lib.ticket(dev),
+                _lib.stream_ptr(dev))
+        _lib.check(st, "decode")
+        out["tea_mask"], out["mask_thresh"] = tea_mask, thresh
+        if want_maxvals_f32:
+            out["maxvals_f32"] = mv32
+    elif planes > 0 and h * w > 0:
         with _lib.on_device(dev):
             st = _lib.load().udape_decode(
                 hm.data_ptr(), code, planes, h, w, _lib.ptr(idx), _lib.ptr(preds), _lib.ptr(maxvals),
@@ -73,7 +101,7 @@ def decode(hm: torch.Tensor, *, want_idx=False, want_preds=False, want_maxvals=F
                 _lib.ptr(conf), float(rectify_sigma if rectify_sigma is not None else 1.0), _lib.ptr(rect),
                 _lib.stream_ptr(dev))
         _lib.check(st, "decode")
-    for key, val in (("idx", idx), ("preds", preds), ("maxvals", maxvals), ("maxvals_f32", mv32),
+    for key, val in (("idx", idx), ("preds", preds), ("maxvals", maxvals), ("maxvals_f32", mv32 if want_maxvals_f32 else None),
                      ("position", pos), ("conf_table", conf), ("rectified", rect)):
         if val is not None:
             out[key] = val

@@ -66,8 +66,8 @@ def consistency_mask(activates: torch.Tensor, mask_ratio: float, tea_mask: torch
 def teacher_targets(hm: torch.Tensor, sigma, mask_ratio: float, occlude_thresh: float | None = None,
                     tea_mask: torch.Tensor | None = None, materialise: bool = True) -> dict:
     """Everything the trainers derive from the reconstructed teacher heatmaps
-    (train_human.py:376-383 and :427-430) in two launches: one fused decode(+rectify) pass over
-    ``hm`` and one single-CTA k-th-value select.
+    (train_human.py:376-383 and :427-430) in ONE launch: a fused decode(+rectify) pass over ``hm`` whose
+    last CTA runs the k-th-value select (``udape_decode_select``).
 
     Returns ``activates`` float32[B,K], ``preds`` float32[B,K,2] (the arg-max ``rectify`` pastes its
     window at), ``rectified`` (= ``rectify(hm, sigma)``), ``tea_mask`` bool[B,K], ``mask_thresh``
@@ -76,10 +76,12 @@ def teacher_targets(hm: torch.Tensor, sigma, mask_ratio: float, occlude_thresh: 
     rectified map is not written (``rectified`` is None): ``fused_losses(..., tea_preds=preds,
     sigma=sigma)`` evaluates it on the fly.
     """
+    kth = int(mask_ratio * hm.shape[0] * hm.shape[1])   # train_human.py:429
     r = decode(hm.detach(), want_preds=True, want_maxvals_f32=True, want_position=occlude_thresh is not None,
-               occlude_thresh=occlude_thresh, rectify_sigma=float(sigma) if materialise else None)
+               occlude_thresh=occlude_thresh, rectify_sigma=float(sigma) if materialise else None,
+               select_kth=kth, select_tea_mask=tea_mask)
     act = r["maxvals_f32"]
-    mask, thresh = consistency_mask(act, mask_ratio, tea_mask)
+    mask, thresh = r["tea_mask"], r["mask_thresh"]
     out = {"activates": act, "preds": r["preds"], "rectified": r.get("rectified"), "tea_mask": mask,
            "mask_thresh": thresh}
     if occlude_thresh is not None:
