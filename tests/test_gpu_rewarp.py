@@ -214,6 +214,22 @@ def test_rewarp_routes_agree(dev, dt, monkeypatch):
             assert torch.equal(r_s, r_g), (b, k, h, w)
 
 
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16])
+def test_rewarp_ring_depths_agree(dev, dt, monkeypatch):
+    """A CTA that owns six or more planes (one CTA per sample at batch 32) stages them through a six-buffer
+    ring instead of three: same bits, also for channel counts that are not a multiple of the ring."""
+    for (b, k) in [(32, 16), (33, 7), (40, 21), (148, 6)]:
+        y = (torch.randn(b, k, 64, 64, device=dev) * 3).to(dt)
+        ac = None if dt == torch.float32 else dt
+        tab = RW.stage_table(RW.recon_stages(S.aug_params(b, seed=90 + k, shear_y=True), 4.0, b), 64, 64, dt, ac)
+        theta = tab[0].to(dev)
+        monkeypatch.setenv("UDAPE_REWARP_RING", "3")
+        shallow = RW._launch_fwd([y], [theta], tab[1], tab[2], torch.empty_like(y))
+        monkeypatch.delenv("UDAPE_REWARP_RING")
+        deep = RW._launch_fwd([y], [theta], tab[1], tab[2], torch.empty_like(y))
+        assert torch.equal(shallow, deep), (b, k)
+
+
 def test_rewarp_backward_long_lists(dev):
     """Zoom factors above ~1.7 give source pixels with more than four contributors (the backward kernel
     keeps four in registers and loops over the rest): checked against autograd through torchvision."""

@@ -296,8 +296,10 @@ __device__ __forceinline__ void pull_slices(cg::cluster_group& cluster, uint16_t
 // channels form a thread-block CLUSTER: each computes 1/n-th of the map into its own shared memory,
 // and after one cluster barrier every CTA reads the offsets of its pixels from its peers through
 // distributed shared memory — the index arithmetic is done once per sample, not once per CTA.
-// dynamic smem: kRwRing padded plane buffers | uint16 map[VIEWS][hw]
-template <typename T, int VIEWS>
+// dynamic smem: RING padded plane buffers | uint16 map[VIEWS][hw].  RING - 1 planes are in flight behind the
+// one being gathered: 2 when a CTA owns few planes, 5 when it walks all channels of a sample (one CTA per sample
+// from batch 32 up: 32 CTAs must keep enough bytes in flight on their own)
+template <typename T, int VIEWS, int RING>
 __global__ void __launch_bounds__(kRwThreads)
 rewarp_smem_kernel(const RewarpArgs a, T* __restrict__ out, int buf_words) {
     constexpr int EPW = 4 / static_cast<int>(sizeof(T));  // elements per 32-bit word
@@ -309,14 +311,14 @@ rewarp_smem_kernel(const RewarpArgs a, T* __restrict__ out, int buf_words) {
     const int hw = a.H * a.W, nwords = hw / EPW;
     const int b = blockIdx.x / nrank;                      // one cluster per sample
     const int c0 = min(a.C, rank * a.cpc), c1 = min(a.C, c0 + a.cpc);
-    uint16_t* s_map = reinterpret_cast<uint16_t*>(rw_smem + kRwRing * buf_words);
+    uint16_t* s_map = reinterpret_cast<uint16_t*>(rw_smem + RING * buf_words);
     if (threadIdx.x < VIEWS * a.stages * 6) {
         const int v = threadIdx.x / (a.stages * 6), k = threadIdx.x - v * a.stages * 6;
         s_theta[v][k] = a.view[v].theta[static_cast<int64_t>(b) * a.stages * 6 + k];
     }
     // the word behind every padded plane stays zero: out-of-bounds pixels gather from it (no select)
     const uint32_t zero_byte = static_cast<uint32_t>(buf_words - 4) * 4u;
-    if (threadIdx.x < kRwRing) rw_smem[threadIdx.x * buf_words + buf_words - 4] = 0u;
+    if (threadIdx.x < RING) rw_smem[threadIdx.x * buf_words + buf_words - 4] = 0u;
     __syncthreads();
     const int row_words = a.W / EPW, vpr = row_words / 4, nvec = nwords / 4;
     int stride[VIEWS], so[VIEWS][kRwMaxVec];
@@ -330,7 +332,7 @@ rewarp_smem_kernel(const RewarpArgs a, T* __restrict__ out, int buf_words) {
     auto issue = [&](int it) {   // item = (channel, view)
         const int c = c0 + it / VIEWS, v = it - (it / VIEWS) * VIEWS;
         const T* plane = static_cast<const T*>(a.view[v].in) + (static_cast<int64_t>(b) * a.C + c) * hw;
-        const uint32_t dst = smem_u32(rw_smem + (it % kRwRing) * buf_words);
+        const uint32_t dst = smem_u32(rw_smem + (it % RING) * buf_words);
         if (VIEWS == 1) { stage_issue<T>(dst, so[0], plane); return; }
 #pragma unroll
         for (int u = 0; u < VIEWS; ++u)
@@ -338,7 +340,7 @@ rewarp_smem_kernel(const RewarpArgs a, T* __restrict__ out, int buf_words) {
     };
     const int nitems = (c1 - c0) * VIEWS;
 #pragma unroll
-    for (int it = 0; it < kRwRing - 1; ++it) {   // in flight while the map is built
+    for (int it = 0; it < RING - 1; ++it) {   // in flight while the map is built
         if (it < nitems) issue(it);
         cp_async_commit();
     }
@@ -385,11 +387,11 @@ rewarp_smem_kernel(const RewarpArgs a, T* __restrict__ out, int buf_words) {
 #pragma unroll
         for (int v = 0; v < VIEWS; ++v) {
             const int it = (c - c0) * VIEWS + v;
-            cp_async_wait<kRwRing - 2>();   // this thread's copies of item `it` have landed ...
+            cp_async_wait<RING - 2>();   // this thread's copies of item `it` have landed ...
             __syncthreads();                // ... everybody's have, and everybody is done with item it-1
-            if (it + kRwRing - 1 < nitems) issue(it + kRwRing - 1);   // refills the buffer of item it-1
+            if (it + RING - 1 < nitems) issue(it + RING - 1);   // refills the buffer of item it-1
             cp_async_commit();
-            const uint8_t* bytes = reinterpret_cast<const uint8_t*>(rw_smem + (it % kRwRing) * buf_words);
+            const uint8_t* bytes = reinterpret_cast<const uint8_t*>(rw_smem + (it % RING) * buf_words);
             if constexpr (VIEWS == 1) {
                 // single view: the values are moved, never converted
 #pragma unroll
@@ -966,15 +968,20 @@ static int reserve_smem(K kernel, size_t bytes, const char* name) {
     return UDAPE_OK;
 }
 
+constexpr int kRwDeepRing = 6;   // single view, a CTA that owns >= 6 planes
+
 template <typename T>
-static int launch_smem_fwd(const RewarpArgs& a, int views, unsigned grid, unsigned cluster, size_t smem, cudaStream_t st,
+static int launch_smem_fwd(const RewarpArgs& a, int views, int ring, unsigned grid, unsigned cluster, size_t smem, cudaStream_t st,
                            T* out, int buf_words) {
     const char* name = "udape_rewarp_fwd";
     switch (views) {
-        case 1: return launch_cluster(rewarp_smem_kernel<T, 1>, grid, cluster, smem, st, name, a, out, buf_words);
-        case 2: return launch_cluster(rewarp_smem_kernel<T, 2>, grid, cluster, smem, st, name, a, out, buf_words);
-        case 3: return launch_cluster(rewarp_smem_kernel<T, 3>, grid, cluster, smem, st, name, a, out, buf_words);
-        default: return launch_cluster(rewarp_smem_kernel<T, 4>, grid, cluster, smem, st, name, a, out, buf_words);
+        case 1:
+            if (ring == kRwDeepRing)
+                return launch_cluster(rewarp_smem_kernel<T, 1, kRwDeepRing>, grid, cluster, smem, st, name, a, out, buf_words);
+            return launch_cluster(rewarp_smem_kernel<T, 1, kRwRing>, grid, cluster, smem, st, name, a, out, buf_words);
+        case 2: return launch_cluster(rewarp_smem_kernel<T, 2, kRwRing>, grid, cluster, smem, st, name, a, out, buf_words);
+        case 3: return launch_cluster(rewarp_smem_kernel<T, 3, kRwRing>, grid, cluster, smem, st, name, a, out, buf_words);
+        default: return launch_cluster(rewarp_smem_kernel<T, 4, kRwRing>, grid, cluster, smem, st, name, a, out, buf_words);
     }
 }
 
@@ -1030,9 +1037,15 @@ extern "C" int udape_rewarp_fwd(const void* const* in, const float* const* theta
         const int n = cluster_size_for(B, C, hw);
         a.cpc = static_cast<int>((C + n - 1) / n);
         const int64_t grid = B * n;
-        const size_t smem = kRwRing * sizeof(uint32_t) * static_cast<size_t>(buf_words) + sizeof(uint16_t) * views * ((hw + 7) & ~7ll);
+        const char* e_ring = std::getenv("UDAPE_REWARP_RING");   // tests: force the shallow ring ("3")
+        // deep ring only when the launch has at most one CTA per SM (few fat CTAs must keep the bytes in flight
+        // themselves); with many CTAs the shallow ring fits three of them per SM and is faster (C5 fp32:
+        // 35.7 us shallow, 39.8 us deep)
+        const int ring = (views == 1 && a.cpc >= kRwDeepRing && B * n <= sm_count() && !(e_ring && e_ring[0] == '3'))
+                             ? kRwDeepRing : kRwRing;
+        const size_t smem = ring * sizeof(uint32_t) * static_cast<size_t>(buf_words) + sizeof(uint16_t) * views * ((hw + 7) & ~7ll);
         UDAPE_DISPATCH_FLOAT(dtype, T, {
-            const int r2 = launch_smem_fwd<T>(a, views, static_cast<unsigned>(grid), static_cast<unsigned>(n), smem, st,
+            const int r2 = launch_smem_fwd<T>(a, views, ring, static_cast<unsigned>(grid), static_cast<unsigned>(n), smem, st,
                                               static_cast<T*>(out), buf_words);
             if (r2) return r2;
         });
