@@ -114,6 +114,73 @@ def test_ema_plan_host_only():
     assert lib.udape_ema_plan(None, src, ne, n_t, 4, 4096, None, 0) < 0
 
 
+def test_opt_plan_host_only_and_argument_errors():
+    """udape_opt_plan is a host-only helper; udape_student_step / udape_grad_check / udape_decode_select /
+    udape_mean_std_bwd validate their arguments before touching CUDA, so the error paths run without a GPU."""
+    lib = _lib.load()
+    numel = [18, 4096, 4097, 0, 5]
+    n_t = len(numel)
+    mk = lambda off, holes=(): (ctypes.c_void_p * n_t)(*[None if i in holes else 0x10000 + 0x100000 * i + off for i in range(n_t)])  # noqa: E731
+    param, grad, m, v, ema = mk(0), mk(0x20000, holes=(1,)), mk(0x40000, holes=(1,)), mk(0x60000, holes=(1,)), mk(0x80000, holes=(4,))
+    ne = (ctypes.c_int64 * n_t)(*numel)
+    need = lib.udape_opt_plan(param, grad, m, v, ema, ne, n_t, 4096, None, 0)
+    assert need == 1 + 1 + 2 + 0 + 1
+    table = (_lib.OptChunk * need)()
+    assert lib.udape_opt_plan(param, grad, m, v, ema, ne, n_t, 4096, table, need) == need
+    rows = [(c.param, c.grad, c.state1, c.state2, c.ema, c.numel) for c in table]
+    assert rows[0] == (0x10000, 0x30000, 0x50000, 0x70000, 0x90000, 18)
+    assert rows[1][1:4] == (None, None, None) and rows[1][4] == 0x110000 + 0x80000 and rows[1][5] == 4096   # no gradient: EMA only
+    assert rows[3] == (0x210000 + 4096 * 4, 0x230000 + 4096 * 4, 0x250000 + 4096 * 4, 0x270000 + 4096 * 4, 0x290000 + 4096 * 4, 1)
+    assert rows[4][4] is None and rows[4][5] == 5                                                           # no teacher: no EMA
+    assert sum(r[5] for r in rows) == sum(numel)
+    assert lib.udape_opt_plan(param, None, None, None, ema, ne, n_t, 4096, table, need) == need            # NULL tables allowed
+    assert all(c.grad is None and c.state1 is None for c in table)
+    assert lib.udape_opt_plan(None, grad, m, v, ema, ne, n_t, 4096, None, 0) == -1
+    assert lib.udape_opt_plan(param, grad, m, v, ema, ne, n_t, 1000, None, 0) == -5
+    # student step: argument validation
+    h = _lib.OptHyper()
+    h.lr, h.beta1, h.beta2, h.eps, h.step = 1e-3, 0.9, 0.999, 1e-8, 1
+    fake = ctypes.c_void_p(0x1000)
+    assert lib.udape_student_step(None, 0, _lib.OPT_ADAM, ctypes.byref(h), None, None, None, None, None, None) == 0   # nothing to do
+    assert lib.udape_student_step(None, 4, _lib.OPT_ADAM, ctypes.byref(h), None, None, None, None, None, None) == -1
+    assert lib.udape_student_step(fake, 4, 7, ctypes.byref(h), None, None, None, None, None, None) == -5
+    assert lib.udape_student_step(fake, 4, _lib.OPT_ADAM, ctypes.byref(h), None, None, None, fake, None, None) == -1  # counter needs a ticket
+    h.step = 0
+    assert lib.udape_student_step(fake, 4, _lib.OPT_ADAM, ctypes.byref(h), None, None, None, None, None, None) == -5
+    h.step, h.beta1 = 1, 1.5
+    assert lib.udape_student_step(fake, 4, _lib.OPT_ADAM, ctypes.byref(h), None, None, None, None, None, None) == -5
+    h.beta1, h.beta2, h.nesterov = 0.0, 0.0, 1
+    assert lib.udape_student_step(fake, 4, _lib.OPT_SGD, ctypes.byref(h), None, None, None, None, None, None) == -5   # nesterov without momentum
+    assert "Nesterov" in _lib.last_error()
+    assert lib.udape_grad_check(fake, 4, None, None, None) == -1
+    # decode_select / mean_std_bwd
+    assert lib.udape_decode_select(fake, 0, 8, 4, 4, None, None, None, None, None, 0.0, None, 2.0, None, 3, None, None, None, fake, None) == -1
+    assert lib.udape_decode_select(fake, 0, 8, 4, 4, None, None, None, fake, None, 0.0, None, 2.0, None, 9, None, None, None, fake, None) == -5
+    assert lib.udape_mean_std_bwd(fake, fake, fake, None, None, 0, 0, 16, fake, None) == -3
+    assert lib.udape_mean_std_bwd(fake, fake, fake, None, None, 3, 4, 16, fake, None) == -2
+
+
+def test_fused_optimizer_host_side():
+    """Constructor validation and torch.optim plumbing of the drop-in optimizers (no launch involved)."""
+    import uda_poseestimation_b200 as U
+    m = torch.nn.Linear(3, 2)
+    with pytest.raises(ValueError):
+        U.Adam(m.parameters(), lr=-1.0)
+    with pytest.raises(ValueError):
+        U.Adam(m.parameters(), betas=(1.0, 0.9))
+    with pytest.raises(ValueError):
+        U.SGD(m.parameters(), lr=0.1, nesterov=True)
+    opt = U.SGD(m.parameters(), lr=0.1, momentum=0.9, nesterov=True)
+    assert isinstance(opt, torch.optim.Optimizer) and opt._step_supports_amp_scaling
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, [1], 0.1)      # train_human.py:143
+    assert opt.param_groups[0]["lr"] == 0.1 and sched.get_last_lr() == [0.1]
+    with pytest.raises(TypeError):
+        opt.attach_teacher(object())
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        opt.step()
+    assert issubclass(U.GradScaler, torch.amp.GradScaler)
+
+
 def test_cpu_tensors_are_rejected_loudly():
     import uda_poseestimation_b200 as U
     x = torch.randn(2, 3, 8, 8)
