@@ -242,6 +242,10 @@ def run_b200_arm(args, cfg, rank, world, local):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     U.load_library()
+    numa_cpus = None
+    if world > 1 and os.environ.get("UDAPE_NUMA_BIND", "1") == "1":
+        # before any pinned allocation: this rank's host buffers belong in the memory next to its GPU
+        numa_cpus = D.bind_to_gpu_numa(local)
     seed = 1234 + rank
     b, k, sigma = cfg["batch"], cfg["joints"], cfg["sigma"]
     host = make_host_inputs(cfg, seed)
@@ -457,7 +461,9 @@ def run_b200_arm(args, cfg, rank, world, local):
         "clocks": clocks,
         "e2e": {"value": world * b / (e2e_ms_per_step / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms_per_step,
-                "last_loss": last[0], "last_avg_pck": last[1]},
+                "last_loss": last[0], "last_avg_pck": last[1],
+                "host_numa_binding": (f"rank 0 pinned to {len(numa_cpus)} CPUs local to its GPU (NVML affinity)"
+                                      if numa_cpus else "none")},
         "gpu_launches": args.steps * step.kernels_per_step,
         "roofline": roofline,
         "cpu_baseline": cpu,

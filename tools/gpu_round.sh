@@ -4,6 +4,7 @@
 TAG=${1:-r01x}
 O=gpurun_out
 mkdir -p $O
+python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; echo "smoke exit $?"; tail -2 $O/${TAG}_smoke.log
 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest.log 2>&1; echo "pytest exit $?" >> $O/${TAG}_pytest.log
 tail -3 $O/${TAG}_pytest.log
 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; tail -c 600 $O/${TAG}_bench.json

@@ -23,7 +23,7 @@ import torch.distributed as dist
 
 from .keypoint_detection import _pck, accuracy_from_counts
 
-__all__ = ["init_from_env", "shard_bounds", "shard", "allreduce_counts", "distributed_accuracy",
+__all__ = ["init_from_env", "bind_to_gpu_numa", "shard_bounds", "shard", "allreduce_counts", "distributed_accuracy",
            "FlatGradBucket", "mean_scalar"]
 
 
@@ -44,6 +44,36 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
             kwargs["device_id"] = torch.device("cuda", local)
         dist.init_process_group(backend=backend, rank=rank, world_size=world, **kwargs)
     return rank, world, local
+
+
+def bind_to_gpu_numa(local_rank: int) -> list[int] | None:
+    """Pin this process to the CPUs NVML reports as local to GPU ``local_rank`` (its NUMA node / PCIe
+    root).  Call before allocating pinned host buffers: first touch then places them in the memory of
+    that node, so with one process per GPU the ranks' host->device copies do not all pull from one
+    socket (8 ranks x 52 GB/s exceeds a single socket's memory and inter-socket bandwidth).  Returns the
+    CPU list, or None when NVML / affinity is unavailable (the call is best-effort and never raises)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = local_rank
+        if visible:
+            ids = [v.strip() for v in visible.split(",") if v.strip()]
+            if local_rank < len(ids) and ids[local_rank].isdigit():
+                index = int(ids[local_rank])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = (n_cpu + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
 
 
 def shard_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
