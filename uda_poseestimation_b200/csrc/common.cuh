@@ -78,6 +78,34 @@ __device__ __forceinline__ void stg_stream(void* p, const uint4& v) {
                  "r"(v.z), "r"(v.w)
                  : "memory");
 }
+// L2 evict-first variants for the big streaming passes of the step (EMA, AdaIN): their bytes are touched
+// once, and marking them as the first victims keeps the small tensors the heatmap chains hand from kernel
+// to kernel (re-warped maps, gradients, the inverse plan: a few MB each) resident in the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint4 ldg_stream_ef(const void* p, uint64_t pol) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_ef(const void* p, uint64_t pol) {
+    uint4 r;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol)
+                 : "memory");
+    return r;
+}
+__device__ __forceinline__ void stg_ef(void* p, const uint4& v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w), "l"(pol)
+                 : "memory");
+}
 // Cached variants (data that is re-read by the same CTA, or read-modify-write).
 __device__ __forceinline__ uint4 ldg_cached(const void* p) {
     return *reinterpret_cast<const uint4*>(p);

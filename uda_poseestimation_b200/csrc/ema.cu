@@ -9,6 +9,8 @@
 // Arithmetic is  fl(fl(dst*a) + fl(src*b))  — the same three fp32 roundings as the
 // reference's  p.mul_(alpha); p.add_(src * (1-alpha))  — so fp32 results are bit-identical
 // to the eager reference (no FMA contraction).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace udape {
@@ -22,8 +24,9 @@ __device__ __forceinline__ float ema_op(float p, float s, float a, float b) {
 
 template <typename T, bool COPY>
 __global__ void __launch_bounds__(kEmaThreads)
-ema_multi_kernel(const udape_ema_chunk* __restrict__ chunks, float a, float b) {
+ema_multi_kernel(const udape_ema_chunk* __restrict__ chunks, float a, float b, int evict_first) {
     constexpr int EPV = Vec16<T>::EPV;
+    const uint64_t pol = l2_evict_first_policy();
     const udape_ema_chunk c = chunks[blockIdx.x];
     T* __restrict__ dst = static_cast<T*>(c.dst);
     const T* __restrict__ src = static_cast<const T*>(c.src);
@@ -38,8 +41,13 @@ ema_multi_kernel(const udape_ema_chunk* __restrict__ chunks, float a, float b) {
             for (int u = 0; u < kEmaUnroll; ++u) {
                 const int i = base + u * kEmaThreads + threadIdx.x;
                 if (i < nvec) {
-                    sv[u] = ldg_stream(s4 + i);
-                    if (!COPY) pv[u] = ldg_cached(d4 + i);
+                    if (evict_first) {
+                        sv[u] = ldg_stream_ef(s4 + i, pol);
+                        if (!COPY) pv[u] = ldg_ef(d4 + i, pol);
+                    } else {
+                        sv[u] = ldg_stream(s4 + i);
+                        if (!COPY) pv[u] = ldg_cached(d4 + i);
+                    }
                 }
             }
 #pragma unroll
@@ -47,14 +55,14 @@ ema_multi_kernel(const udape_ema_chunk* __restrict__ chunks, float a, float b) {
                 const int i = base + u * kEmaThreads + threadIdx.x;
                 if (i < nvec) {
                     if (COPY) {
-                        stg_plain(d4 + i, sv[u]);
+                        if (evict_first) stg_ef(d4 + i, sv[u], pol); else stg_plain(d4 + i, sv[u]);
                     } else {
                         float fp[EPV], fs[EPV];
                         unpack16<T>(pv[u], fp);
                         unpack16<T>(sv[u], fs);
 #pragma unroll
                         for (int e = 0; e < EPV; ++e) fp[e] = ema_op(fp[e], fs[e], a, b);
-                        stg_plain(d4 + i, pack16<T>(fp));
+                        if (evict_first) stg_ef(d4 + i, pack16<T>(fp), pol); else stg_plain(d4 + i, pack16<T>(fp));
                     }
                 }
             }
@@ -127,9 +135,11 @@ extern "C" int udape_ema_multi(const udape_ema_chunk* chunks_dev, int64_t n_chun
         copy_multi_kernel<<<grid, kEmaThreads, 0, st>>>(chunks_dev);
         return check_launch("udape_ema_multi");
     }
+    const char* e_ef = std::getenv("UDAPE_EMA_EVICT_FIRST");
+    const int ef = e_ef ? std::atoi(e_ef) : 0;
     UDAPE_DISPATCH_FLOAT(dtype, T, {
-        if (mode == 0) ema_multi_kernel<T, false><<<grid, kEmaThreads, 0, st>>>(chunks_dev, a, b);
-        else ema_multi_kernel<T, true><<<grid, kEmaThreads, 0, st>>>(chunks_dev, a, b);
+        if (mode == 0) ema_multi_kernel<T, false><<<grid, kEmaThreads, 0, st>>>(chunks_dev, a, b, ef);
+        else ema_multi_kernel<T, true><<<grid, kEmaThreads, 0, st>>>(chunks_dev, a, b, ef);
     });
     return check_launch("udape_ema_multi");
 }
