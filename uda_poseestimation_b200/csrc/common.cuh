@@ -78,9 +78,11 @@ __device__ __forceinline__ void stg_stream(void* p, const uint4& v) {
                  "r"(v.z), "r"(v.w)
                  : "memory");
 }
-// L2 evict-first variants for the big streaming passes of the step (EMA, AdaIN): their bytes are touched
-// once, and marking them as the first victims keeps the small tensors the heatmap chains hand from kernel
-// to kernel (re-warped maps, gradients, the inverse plan: a few MB each) resident in the 126 MB L2.
+// L2 evict-first variants for the EMA, the biggest streaming pass of the step: its bytes are touched once,
+// and marking them as the first victims keeps the small tensors the heatmap chains hand from kernel to
+// kernel (re-warped maps, gradients, the inverse plan: a few MB each) resident in the 126 MB L2.
+// Measured inside the step (tools/step_probe.py): 181.0 -> 178.8 us.  The same hint on the AdaIN loads made
+// the step slower (183.5 us), plain instead of streaming stores for the chain's outputs changed nothing.
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));

@@ -135,8 +135,9 @@ extern "C" int udape_ema_multi(const udape_ema_chunk* chunks_dev, int64_t n_chun
         copy_multi_kernel<<<grid, kEmaThreads, 0, st>>>(chunks_dev);
         return check_launch("udape_ema_multi");
     }
+    // L2 evict-first for the EMA's once-touched bytes (common.cuh); UDAPE_EMA_EVICT_FIRST=0 turns the hint off
     const char* e_ef = std::getenv("UDAPE_EMA_EVICT_FIRST");
-    const int ef = e_ef ? std::atoi(e_ef) : 0;
+    const int ef = e_ef ? std::atoi(e_ef) : 1;
     UDAPE_DISPATCH_FLOAT(dtype, T, {
         if (mode == 0) ema_multi_kernel<T, false><<<grid, kEmaThreads, 0, st>>>(chunks_dev, a, b, ef);
         else ema_multi_kernel<T, true><<<grid, kEmaThreads, 0, st>>>(chunks_dev, a, b, ef);

@@ -333,10 +333,13 @@ rewarp_smem_kernel(const RewarpArgs a, T* __restrict__ out, int buf_words) {
         const int c = c0 + it / VIEWS, v = it - (it / VIEWS) * VIEWS;
         const T* plane = static_cast<const T*>(a.view[v].in) + (static_cast<int64_t>(b) * a.C + c) * hw;
         const uint32_t dst = smem_u32(rw_smem + (it % RING) * buf_words);
-        if (VIEWS == 1) { stage_issue<T>(dst, so[0], plane); return; }
+        if constexpr (VIEWS == 1) {
+            stage_issue<T>(dst, so[0], plane);
+        } else {
 #pragma unroll
-        for (int u = 0; u < VIEWS; ++u)
-            if (u == v) stage_issue<T>(dst, so[u], plane);
+            for (int u = 0; u < VIEWS; ++u)
+                if (u == v) stage_issue<T>(dst, so[u], plane);
+        }
     };
     const int nitems = (c1 - c0) * VIEWS;
 #pragma unroll

@@ -141,8 +141,7 @@ class HotPathStep:
             hi = int(os.environ.get("UDAPE_CHAIN_PRIORITY", "-2")) if on else 0
             ad = int(os.environ.get("UDAPE_ADAIN_PRIORITY", "-1")) if on else 0
             self._side = (torch.cuda.Stream(dev, priority=hi), torch.cuda.Stream(dev, priority=hi), torch.cuda.Stream(dev),
-                          torch.cuda.Stream(dev, priority=hi), torch.cuda.Stream(dev, priority=ad),
-                          torch.cuda.Stream(dev, priority=ad))
+                          torch.cuda.Stream(dev, priority=hi), torch.cuda.Stream(dev, priority=ad))
         return self._side
 
     # -- the step -----------------------------------------------------------------------------------
@@ -159,10 +158,7 @@ class HotPathStep:
         The fork/join is plain stream-event ordering, so it behaves the same eagerly and under
         CUDA-graph capture (where it becomes parallel graph branches)."""
         cur = torch.cuda.current_stream()
-        s_tea, s_stu, s_ema, s_plan, s_adain, s_adain2 = (self._streams(inp.y_s.device) if self.parallel
-                                                          else (cur, cur, cur, cur, cur, cur))
-        if os.environ.get("UDAPE_ADAIN_SPLIT", "1") != "1":
-            s_adain2 = s_adain
+        s_tea, s_stu, s_ema, s_plan, s_adain = self._streams(inp.y_s.device) if self.parallel else (cur, cur, cur, cur, cur)
 
         ema_side = with_ema and self.parallel and self.ema_parallel
         self._mark("start")
@@ -256,22 +252,16 @@ class HotPathStep:
         t_s2t = t_t2s = None
         if s_adain is not cur:
             s_adain.wait_stream(cur)
-            if s_adain2 is not s_adain:
-                s_adain2.wait_stream(cur)
-        # :348-356 — s2t and t2s feature re-normalisation (the decoder conv follows).  The two directions are
-        # independent: on two streams of one priority the second launch fills the SM slots the first one's
-        # last partial wave leaves idle (2048 CTAs over 444 slots = 4.6 waves each)
+        # :348-356 — s2t and t2s feature re-normalisation (the decoder conv follows).  (The two directions on two
+        # streams of one priority, so that the second fills the first one's last partial wave: no change, 180.8 vs 180.1 us)
         if "adain" not in self.skip:
             with torch.cuda.stream(s_adain), torch.no_grad():
                 t_s2t = adain_mix(inp.feat_src, inp.feat_tgt_ori, inp.alpha_s2t)
                 self._mark("adain s2t done")
-            with torch.cuda.stream(s_adain2), torch.no_grad():
                 t_t2s = adain_mix(inp.feat_tgt_tea, inp.feat_src_ori, inp.alpha_t2s)
                 self._mark("adain t2s done")
         if s_adain is not cur:
             cur.wait_stream(s_adain)
-            if s_adain2 is not s_adain:
-                cur.wait_stream(s_adain2)
         if self.parallel:
             cur.wait_stream(s_tea)
             cur.wait_stream(s_stu)
