@@ -269,11 +269,23 @@ def run_b200_arm(args, cfg, rank, world, local):
     rng = np.random.RandomState(seed)  # alpha ~ U(0,1) per step (train_human.py:349,354)
     alphas = torch.from_numpy(rng.uniform(0, 1, size=(2 * n_steps_total + 64, 2)).astype(np.float32)).to(dev)
 
-    def set_alpha(i):
-        alpha_pair.copy_(alphas[i])
-
     use_graph = not args.no_graph
-    set_alpha(0)
+    # alpha ~ U(0,1) per step (train_human.py:349,354).  With the graph, the row of a device table is loaded for
+    # the NEXT replay by three tiny torch kernels behind the AdaIN launches (a device step counter picks it), so a
+    # replay needs no launch in front of it; eagerly, one 8-byte copy in front of the step
+    alpha_row = torch.ones(1, dtype=torch.int64, device=dev)
+
+    def alpha_feed():
+        alpha_pair.copy_(alphas.index_select(0, alpha_row).view(2))
+        alpha_row.add_(1).remainder_(alphas.shape[0])
+
+    def set_alpha(i):
+        if not use_graph:
+            alpha_pair.copy_(alphas[i])
+
+    if use_graph:
+        step.alpha_feed = alpha_feed
+    alpha_pair.copy_(alphas[0])
     # the path's only per-step exchange: int32 [2,K] PCK counts, summed over ranks.  It is issued on the
     # PCK chain (inside the graph when NCCL capture works) so that it overlaps the AdaIN / EMA chains.
     ar_in_step = False
@@ -283,6 +295,8 @@ def run_b200_arm(args, cfg, rank, world, local):
         torch.cuda.synchronize()
         step.counts_hook = D.allreduce_counts
         ar_in_step = True
+    if os.environ.get("UDAPE_BENCH_DEBUG") == "1":
+        step.marks = []
     if use_graph:
         try:
             out = step.capture(inp, include_ema=ema_in_graph, warmup=2)
@@ -331,6 +345,26 @@ def run_b200_arm(args, cfg, rank, world, local):
     if world > 1:
         dist.barrier()
     ms_total = start.elapsed_time(end)
+    if os.environ.get("UDAPE_BENCH_DEBUG") == "1" and use_graph:
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a_.record()
+        for _ in range(args.steps):
+            step.replay()
+        b_.record()
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        acc = {}
+        for _ in range(20):
+            step.replay()
+            torch.cuda.synchronize()
+            for name, ev in step.marks[1:]:
+                acc.setdefault(name, []).append(step.marks[0][1].elapsed_time(ev) * 1e3)
+        for name, ts in sorted(acc.items(), key=lambda kv: np.median(kv[1])):
+            print(f"[debug]   {name:<22}{np.median(ts):8.1f}", file=sys.stderr)
+        print(f"[debug] tight replay loop: {a_.elapsed_time(b_) / args.steps * 1e3:.1f} us/step on the device, "
+              f"{(t1 - t0) / args.steps * 1e6:.1f} us/step of host launch time; timed loop {ms_total / args.steps * 1e3:.1f} us/step",
+              file=sys.stderr)
     if ema_in_graph:
         # the EMA kernel runs inside the graph (concurrently with the other chains when --ema graph), where
         # it cannot be bracketed by events: time the same launch on its own right after the step loop
@@ -368,7 +402,7 @@ def run_b200_arm(args, cfg, rank, world, local):
         host["theta_stu"].copy_(t_stu)
         for n in h2d_names[-2:]:
             getattr(inp, n).copy_(host[n], non_blocking=True)
-        alpha_pair.copy_(alpha_host[i], non_blocking=True)
+        alpha_pair.copy_(alpha_host[i], non_blocking=True)   # this step's alpha comes from the host
         o = body()
         if not ema_in_graph:
             step.ema.step()

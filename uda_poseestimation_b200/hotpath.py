@@ -113,6 +113,12 @@ class HotPathStep:
         self.out = None
         self._graph_inputs = None
         self.rewarp_kernels = 0
+        # optional callable run on the AdaIN stream right AFTER the two AdaIN launches (inside the captured
+        # graph): loads the device-resident alpha scalars of the NEXT replay, e.g. from a device table indexed
+        # by a device step counter, so that a replay needs no separate launch in front of it.  (In front of the
+        # AdaIN launches it would delay them behind the EMA's 13k CTAs: a lower-priority grid that has started
+        # is not displaced, measured 188 -> 199 us.)
+        self.alpha_feed = None
         self.skip = frozenset()   # profiling only (tools/step_probe.py): chains left out of the step
         self.marks = None         # profiling only: list of (name, external timing event) filled while capturing
 
@@ -260,6 +266,8 @@ class HotPathStep:
                 self._mark("adain s2t done")
                 t_t2s = adain_mix(inp.feat_tgt_tea, inp.feat_src_ori, inp.alpha_t2s)
                 self._mark("adain t2s done")
+                if self.alpha_feed is not None:
+                    self.alpha_feed()
         if s_adain is not cur:
             cur.wait_stream(s_adain)
         if self.parallel:
