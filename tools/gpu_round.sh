@@ -8,6 +8,7 @@ python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; e
 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest.log 2>&1; echo "pytest exit $?" >> $O/${TAG}_pytest.log
 tail -3 $O/${TAG}_pytest.log
 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; tail -c 600 $O/${TAG}_bench.json
+python bench.py --impl reference --steps 4 --warmup 3 > $O/${TAG}_bench_reference.json 2>/dev/null; tail -c 300 $O/${TAG}_bench_reference.json
 python tools/microbench.py --out $O/${TAG}_microbench.json > $O/${TAG}_microbench.log 2>&1; tail -70 $O/${TAG}_microbench.log
 # launch list of the bench command (graph replay: kernels inside the graph are listed individually)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${TAG}_launches_bench.csv \
