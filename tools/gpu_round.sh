@@ -13,7 +13,8 @@ python tools/microbench.py --out $O/${TAG}_microbench.json > $O/${TAG}_microbenc
 # launch list of the bench command (graph replay: kernels inside the graph are listed individually)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${TAG}_launches_bench.csv \
     python bench.py --steps 3 --warmup 3 --skip-cpu-baseline > $O/${TAG}_bench_under_ncu.log 2>&1
-# full-section capture of one launch of every kernel family at the microbench sizes
+# full-section capture of one launch of every kernel family at the microbench sizes (NOFULL=1 skips it)
+[ "${NOFULL:-0}" = "1" ] && { ls -la $O | tail -20; exit 0; }
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'adain|mean_std|decode|pck|mse|cons_|loss_step|ema_multi|gauss_target|labelmap|mask_select|clamp|rewarp|student_step|grad_check' -o $O/${TAG}_full -f \
     python tools/microbench.py --warmup 0 --iters 1 --no-flush --no-sustained --adain-n 32 --configs C5 --out $O/${TAG}_mb_under_ncu.json > $O/${TAG}_full.log 2>&1
 # gpurun_out/ merges at most 64 MiB back: keep the raw-page CSV, drop the report itself when it is large
