@@ -382,9 +382,11 @@ def run_b200_arm(args, cfg, rank, world, local):
     value = world * b / (ms_per_step / 1e3)
 
     # ---- e2e: host (pinned) inputs -> device -> step -> results back on the host -----------------
+    # the source labels travel as keypoints (12 KB) and become heatmaps on the device (udape_gauss_target, row
+    # a4): the reference builds them in its loader workers and ships 8.4 MB of float32 heatmaps per step
     h2d_names = ["feat_src", "feat_tgt_ori", "feat_tgt_tea", "feat_src_ori", "y_s", "y_t_stu", "y_t_tea",
-                 "label_s", "weight_s", "theta_tea", "theta_stu"]
-    h2d_bytes = sum(host[n].numel() * host[n].element_size() for n in h2d_names) + 8
+                 "theta_tea", "theta_stu"]
+    h2d_bytes = sum(host[n].numel() * host[n].element_size() for n in h2d_names + ["joints", "vis"]) + 8
     res_host = dict(losses=torch.empty(3, dtype=torch.float32).pin_memory(),
                     counts=torch.empty((2, k), dtype=torch.int32).pin_memory(),
                     pred=torch.empty((b, k, 2), dtype=torch.float32).pin_memory())
@@ -395,6 +397,9 @@ def run_b200_arm(args, cfg, rank, world, local):
     def e2e_step(i):
         for n in h2d_names[:-2]:
             getattr(inp, n).copy_(host[n], non_blocking=True)
+        d["joints"].copy_(host["joints"], non_blocking=True)
+        d["vis"].copy_(host["vis"], non_blocking=True)
+        U.generate_target_batched(d["joints"], d["vis"], (64, 64), sigma, (256, 256), out=(inp.label_s, inp.weight_s))
         # host half of the re-warp (the reference computes the same matrices inside tF.affine, per sample);
         # it runs while the asynchronous copies above are on the wire
         t_tea, t_stu = stage_tables(host, torch.float16)
@@ -496,6 +501,7 @@ def run_b200_arm(args, cfg, rank, world, local):
         "e2e": {"value": world * b / (e2e_ms_per_step / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms_per_step,
                 "last_loss": last[0], "last_avg_pck": last[1],
+                "labels": "keypoints copied per step, heatmaps generated on the device (udape_gauss_target)",
                 "host_numa_binding": (f"rank 0 pinned to {len(numa_cpus)} CPUs local to its GPU (NVML affinity)"
                                       if numa_cpus else "none")},
         "gpu_launches": args.steps * step.kernels_per_step,

@@ -276,6 +276,16 @@ def test_decode_select_equals_decode_then_select(dev, cfg, rectify):
     assert float(one["mask_thresh"]) == float(ref_thresh) or (np.isnan(float(ref_thresh)) and np.isnan(float(one["mask_thresh"])))
 
 
+def test_generate_target_out_argument(dev):
+    joints, vis = S.keypoints(4, 16, seed=8)
+    t0, w0 = U.generate_target_batched(joints, vis, (64, 64), 2, (256, 256), device=dev)
+    t1, w1 = torch.full_like(t0, 7.0), torch.full_like(w0, 7.0)
+    r = U.generate_target_batched(joints, vis, (64, 64), 2, (256, 256), device=dev, out=(t1, w1))
+    assert r[0] is t1 and torch.equal(t0, t1) and torch.equal(w0, w1)
+    with pytest.raises(ValueError):
+        U.generate_target_batched(joints, vis, (64, 64), 2, (256, 256), device=dev, out=(t1[:, :8], w1))
+
+
 @pytest.mark.parametrize("cfg", ["C1", "C4"])
 def test_generate_target_vs_oracle(dev, cfg):
     b, k, sigma = S.CONFIGS[cfg]["batch"], S.CONFIGS[cfg]["joints"], S.CONFIGS[cfg]["sigma"]

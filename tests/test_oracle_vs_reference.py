@@ -1,0 +1,128 @@
+"""Pins the CPU oracle (oracle/reference_port.py) against the REAL reference functions, imported by file
+path from the reference tree (oracle/ref_loader.py), on fresh random inputs — in addition to the committed
+golden fixtures, which were produced by the same functions.  The tree exists only in the build container:
+everywhere else (the GPU box) this module is skipped.  Equality is exact: the oracle calls the same
+torch / numpy primitives in the same order.
+"""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_loader
+from oracle import reference_port as R
+from uda_poseestimation_b200 import synthetic as S
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present on this box")
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_adain_and_statistics(seed):
+    fn, sn = ref_loader.load("function"), ref_loader.load("style_net")
+    g = torch.Generator().manual_seed(seed)
+    c = torch.relu(torch.randn(3, 6, 17 + seed, 9, generator=g) + 0.2)
+    s = torch.relu(torch.randn(3, 6, 8, 11 + seed, generator=g) * 2 + 0.5)
+    for a, b in zip(R.calc_mean_std(c), fn.calc_mean_std(c)):
+        assert torch.equal(a, b)
+    assert torch.equal(R.adaptive_instance_normalization(c, s), fn.adaptive_instance_normalization(c, s))
+    alpha = 0.1 + 0.4 * seed
+    t = sn.adain(c, s)
+    assert torch.equal(R.adain_mix(c, s, alpha), alpha * t + (1 - alpha) * c)      # Style_net.py:167-168
+
+
+@pytest.mark.parametrize("seed", [3, 4])
+def test_decode_accuracy_rectify(seed):
+    kd, ut = ref_loader.load("keypoint_detection"), ref_loader.load("utils")
+    hm = S.heatmaps(5, 7, seed=seed, peak=(0.2, 1.2))
+    hm[0, 0] = 0.0
+    hm[1, 2] = -1.0
+    tgt = S.heatmaps(5, 7, seed=seed + 10)
+    for x in (hm.numpy(), hm.half().numpy()):
+        for a, b in zip(R.get_max_preds(x), kd.get_max_preds(x)):
+            np.testing.assert_array_equal(a, b)
+    for a, b in zip(R.get_max_preds_torch(hm), ut.get_max_preds_torch(hm)):
+        assert torch.equal(a, b)
+    ra, rb = R.accuracy(hm.numpy(), tgt.numpy()), kd.accuracy(hm.numpy(), tgt.numpy())
+    np.testing.assert_array_equal(ra[0], rb[0])
+    assert ra[1] == rb[1] and ra[2] == rb[2]
+    np.testing.assert_array_equal(ra[3], rb[3])
+    for sigma in (2, 1.0):
+        assert torch.equal(R.rectify(hm.clone(), sigma), ut.rectify(hm.clone(), sigma))
+
+
+@pytest.mark.parametrize("seed", [5, 6])
+def test_losses(seed):
+    lo = ref_loader.load("loss")
+    g = torch.Generator().manual_seed(seed)
+    o = torch.randn(4, 5, 16, 16, generator=g).requires_grad_(True)
+    o2 = o.detach().clone().requires_grad_(True)
+    t = torch.rand(4, 5, 16, 16, generator=g)
+    w = (torch.rand(4, 5, 1, generator=g) > 0.3).float()
+    for red in ("mean", "none"):
+        a, b = R.joints_mse_loss(o, t, w, reduction=red), lo.JointsMSELoss(reduction=red)(o2, t, w)
+        assert torch.equal(a, b)
+    a, b = R.joints_mse_loss(o, t, w), lo.JointsMSELoss()(o2, t, w)
+    ga, gb = torch.autograd.grad(a, o)[0], torch.autograd.grad(b, o2)[0]
+    assert torch.equal(ga, gb)
+    m = torch.rand(4, 5, generator=g) > 0.5
+    a, b = R.cons_loss(o, t, tea_mask=m), lo.ConsLoss()(o2, t, tea_mask=m)
+    assert torch.equal(a, b)
+    assert torch.equal(torch.autograd.grad(a, o)[0], torch.autograd.grad(b, o2)[0])
+
+
+@pytest.mark.parametrize("sigma", [2, 1.0])
+def test_target_heatmaps(sigma, capsys):
+    du = ref_loader.load("dataset_util")
+    joints, vis = S.keypoints(6, 9, seed=17)
+    for i in range(6):
+        a = R.generate_target(joints[i], vis[i], (64, 64), sigma, (256, 256))
+        b = du.generate_target(joints[i], vis[i], (64, 64), sigma, (256, 256))
+        np.testing.assert_array_equal(a[0], b[0])
+        np.testing.assert_array_equal(a[1], b[1])
+    pts = torch.tensor([[20.0, 30.0], [0.0, 0.0], [63.0, 63.0], [3.2, 60.9], [31.5, 31.5]])
+    for p in pts:
+        for kind in ("Gaussian", "Cauchy"):
+            a = R.draw_labelmap_ori(torch.zeros(64, 64), p, sigma, type=kind)
+            b = du.draw_labelmap_ori(torch.zeros(64, 64), p, sigma, type=kind)
+            assert torch.equal(torch.as_tensor(a[0]), torch.as_tensor(b[0])) and a[1] == b[1]
+
+
+def test_ema_and_student_step():
+    ut = ref_loader.load("utils")
+
+    def make(seed):
+        torch.manual_seed(seed)
+        return torch.nn.Sequential(torch.nn.Linear(9, 7), torch.nn.Linear(7, 3))
+
+    teacher, student = make(1), make(2)
+    tea = ut.OldWeightEMA(teacher, student, alpha=0.97)
+    opt = torch.optim.Adam(student.parameters(), lr=2e-3)
+    s_cpu = [p.detach().clone() for p in student.parameters()]
+    t_cpu = [p.detach().clone() for p in teacher.parameters()]
+    m = [torch.zeros_like(p) for p in s_cpu]
+    v = [torch.zeros_like(p) for p in s_cpu]
+    g = torch.Generator().manual_seed(3)
+    step = 0
+    for _ in range(4):
+        grads = [torch.randn(p.shape, generator=g) for p in s_cpu]
+        for p, gr in zip(student.parameters(), grads):
+            p.grad = gr.clone()
+        opt.step()        # train_human.py:437 without a scaler
+        tea.step()        # :438
+        _, step = R.student_teacher_step("adam", s_cpu, grads, m, v, t_cpu, step, None, 0.97,
+                                         lr=2e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
+        for a, b in zip(s_cpu + t_cpu, list(student.parameters()) + list(teacher.parameters())):
+            assert torch.equal(a, b.detach())
+
+
+def test_style_loss():
+    net = ref_loader.load("adain_net")
+    fake_self = types.SimpleNamespace(mse_loss=torch.nn.MSELoss())
+    g = torch.Generator().manual_seed(8)
+    x = torch.relu(torch.randn(2, 4, 24, 24, generator=g)).requires_grad_(True)
+    x2 = x.detach().clone().requires_grad_(True)
+    t = torch.relu(torch.randn(2, 4, 24, 24, generator=g) * 1.3)
+    a, b = R.calc_style_loss(x, t), net.Net.calc_style_loss(fake_self, x2, t)
+    assert torch.equal(a, b)
+    assert torch.equal(torch.autograd.grad(a, x)[0], torch.autograd.grad(b, x2)[0])

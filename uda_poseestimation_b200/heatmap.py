@@ -24,13 +24,14 @@ def _default_device() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def generate_target_batched(joints, joints_vis, heatmap_size, sigma, image_size, device=None):
+def generate_target_batched(joints, joints_vis, heatmap_size, sigma, image_size, device=None, out=None):
     """Batched ``generate_target``: ``joints[...,K,2]`` (image pixels), ``joints_vis[...,K,1]``
     → ``(target[...,K,H,W] float32, target_weight[...,K,1] float32)`` on the GPU.
 
     ``heatmap_size`` and ``image_size`` are ``(W, H)`` as in the reference.  Placement is
     evaluated in float64 (``mu = int(joint / stride + 0.5)``, util.py:38-39), so pass float64
-    keypoints when they come from numpy.
+    keypoints when they come from numpy.  ``out=(target, weight)``: write into existing contiguous float32
+    CUDA tensors of those shapes (e.g. the static inputs of a captured step graph).
     """
     if isinstance(joints, np.ndarray):
         joints = torch.from_numpy(np.ascontiguousarray(joints, dtype=np.float64))
@@ -48,8 +49,14 @@ def generate_target_batched(joints, joints_vis, heatmap_size, sigma, image_size,
     j = joints.detach().to(device=device, dtype=torch.float64).reshape(planes, 2).contiguous()
     v = joints_vis.detach().to(device=device, dtype=torch.float32).reshape(planes, -1)[:, 0].contiguous()
     hm_w, hm_h = int(heatmap_size[0]), int(heatmap_size[1])
-    target = torch.empty(lead + (hm_h, hm_w), dtype=torch.float32, device=device)
-    weight = torch.empty(lead + (1,), dtype=torch.float32, device=device)
+    if out is not None:
+        target, weight = out
+        for t, shape in ((target, lead + (hm_h, hm_w)), (weight, lead + (1,))):
+            if (tuple(t.shape) != shape or t.dtype != torch.float32 or not t.is_contiguous() or t.device != device):
+                raise ValueError(f"generate_target: out tensors must be contiguous float32 {shape} on {device}")
+    else:
+        target = torch.empty(lead + (hm_h, hm_w), dtype=torch.float32, device=device)
+        weight = torch.empty(lead + (1,), dtype=torch.float32, device=device)
     if planes > 0:
         with _lib.on_device(device):
             st = _lib.load().udape_gauss_target(j.data_ptr(), v.data_ptr(), planes, hm_w, hm_h, float(sigma),
