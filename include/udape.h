@@ -264,9 +264,10 @@ UDAPE_API int udape_ema_multi(const udape_ema_chunk* chunks_dev, int64_t n_chunk
  *   Adam:  m += (1-beta1)(g-m);  v = beta2 v + (1-beta2) g^2;  p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
  *   SGD :  buf = step==1 ? g : momentum*buf + (1-dampening) g;  g = nesterov ? g + momentum*buf : buf;  p -= lr g
  *   ema = fl(fl(ema*ema_a) + fl(p*ema_b))              (the updated p, three roundings like utils.py:24-25)
- * bc1 = 1-beta1^step, bc2 = 1-beta2^step in double.  step = *step_dev + 1 when step_dev is given (the
- * counter is advanced by the launch, ticket = one zeroed self-resetting uint32), else hyper->step
- * (1-based).  lr_dev (optional) overrides hyper->lr from device memory (CUDA-graph replays across
+ * bc1 = 1-beta1^step, bc2 = 1-beta2^step in double.  step = *step_dev + 1 when step_dev is given, else
+ * hyper->step (1-based).  With a ticket (one zeroed, self-resetting uint32) the launch advances *step_dev
+ * once all CTAs have read it; with ticket == NULL the counter is only read (several param groups share
+ * one counter: only the last launch of a step advances it).  lr_dev (optional) overrides hyper->lr from device memory (CUDA-graph replays across
  * MultiStepLR milestones).  If *found_inf != 0 the student, its state and the step counter are left
  * untouched and only the EMA runs, as scaler.step() + tea_optimizer.step() do.  float32 only. */
 enum { UDAPE_OPT_ADAM = 0, UDAPE_OPT_SGD = 1 };

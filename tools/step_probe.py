@@ -78,20 +78,15 @@ def main():
 
     from uda_poseestimation_b200.ema import MultiTensorPlan
     plan = MultiTensorPlan([p.data for p in teacher.parameters()], [p.data for p in student.parameters()])
-    for ctas in os.environ.get("PROBE_EMA_CTAS", "0").split(","):
-        os.environ["UDAPE_EMA_CTAS_PER_SM"] = ctas
+    plan.run(0.999, 0.001, 0)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(20):
         plan.run(0.999, 0.001, 0)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(20):
-            plan.run(0.999, 0.001, 0)
-        b.record()
-        torch.cuda.synchronize()
-        print(f"-- UDAPE_EMA_CTAS_PER_SM={ctas}: EMA alone {a.elapsed_time(b) / 20 * 1e3:7.1f} us")
-        variant(f"   full step (ema ctas/sm {ctas})")
-        variant(f"   no AdaIN  (ema ctas/sm {ctas})", skip=("adain",))
-    os.environ["UDAPE_EMA_CTAS_PER_SM"] = "0"
+    b.record()
+    torch.cuda.synchronize()
+    print(f"EMA alone (eager launches)                          {a.elapsed_time(b) / 20 * 1e3:9.1f} us")
     variant("full step")
     variant("no EMA", ema=False)
     variant("no re-warp", rewarp=False)

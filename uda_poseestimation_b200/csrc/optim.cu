@@ -180,7 +180,8 @@ student_step_kernel(const udape_opt_chunk* __restrict__ chunks, udape_opt_hyper 
     }
     // the step counter advances once per launch, after every CTA has read it, and only when the
     // update was applied (torch: state['step'] is not touched when scaler.step() skips)
-    if (step_dev) {
+    // (ticket == NULL: the counter is only read — the launches of all but the last param group of a step)
+    if (step_dev && ticket) {
         if (last_block_done(ticket, gridDim.x) && threadIdx.x == 0 && !s.skip) *step_dev = *step_dev + 1;
     }
 }
@@ -282,7 +283,6 @@ extern "C" int udape_student_step(const udape_opt_chunk* chunks_dev, int64_t n_c
     UDAPE_REQUIRE(chunks_dev && hyper, UDAPE_ERR_NULL, "udape_student_step: chunk table / hyper is NULL");
     UDAPE_REQUIRE(n_chunks > 0 && n_chunks < (1ll << 31), UDAPE_ERR_SHAPE, "udape_student_step: bad n_chunks=%lld", (long long)n_chunks);
     UDAPE_REQUIRE(algo == UDAPE_OPT_ADAM || algo == UDAPE_OPT_SGD, UDAPE_ERR_ARG, "udape_student_step: algo must be UDAPE_OPT_ADAM or UDAPE_OPT_SGD");
-    UDAPE_REQUIRE(!step_dev || ticket, UDAPE_ERR_NULL, "udape_student_step: a device step counter needs a ticket word");
     UDAPE_REQUIRE(step_dev || hyper->step >= 1, UDAPE_ERR_ARG, "udape_student_step: hyper.step is 1-based (got %d)", (int)hyper->step);
     if (algo == UDAPE_OPT_ADAM)
         UDAPE_REQUIRE(hyper->beta1 >= 0.0 && hyper->beta1 < 1.0 && hyper->beta2 >= 0.0 && hyper->beta2 < 1.0 && hyper->eps >= 0.0,

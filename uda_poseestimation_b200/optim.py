@@ -38,7 +38,6 @@ class _FusedStudentOptimizer(torch.optim.Optimizer):
     # torch.amp.GradScaler.step(): hand grad_scale / found_inf to step() instead of unscaling itself
     _step_supports_amp_scaling = True
     _algo = _lib.OPT_ADAM
-    _state_keys: tuple = ()
 
     def __init__(self, params, defaults, capturable: bool = False):
         super().__init__(params, defaults)
@@ -212,26 +211,16 @@ class _FusedStudentOptimizer(torch.optim.Optimizer):
             h = self._hyper(group)
             h.ema_a, h.ema_b, h.step = ema_a, ema_b, 1
             lr_dev = self._lr_dev[gi].data_ptr() if self.capturable else None
-            # every group reads the counter; only the last launch of the step advances it
-            step_ptr = self._step_dev.data_ptr()
+            # every group reads the device step counter; only the last launch of the step (the one that is
+            # handed a ticket) advances it
             with _lib.on_device(dev):
-                if gi == last:
-                    st = lib.udape_student_step(table.data_ptr(), n, self._algo, ctypes.byref(h), lr_dev,
-                                                _lib.ptr(grad_scale), _lib.ptr(found_inf), step_ptr,
-                                                _lib.ticket(dev), _lib.stream_ptr(dev))
-                else:
-                    st = self._launch_frozen_counter(lib, table, n, h, lr_dev, grad_scale, found_inf, dev)
+                st = lib.udape_student_step(table.data_ptr(), n, self._algo, ctypes.byref(h), lr_dev,
+                                            _lib.ptr(grad_scale), _lib.ptr(found_inf), self._step_dev.data_ptr(),
+                                            _lib.ticket(dev) if gi == last else None, _lib.stream_ptr(dev))
             _lib.check(st, "udape_student_step")
         if self._teacher is not None:
             self._teacher._fused_pending = True
         return loss
-
-    def _launch_frozen_counter(self, lib, table, n, h, lr_dev, grad_scale, found_inf, dev):
-        # groups before the last one must see the same step number without advancing it: they read a
-        # snapshot of the counter (device copy, stream-ordered) and advance only the snapshot
-        snap = self._step_dev.clone()
-        return lib.udape_student_step(table.data_ptr(), n, self._algo, ctypes.byref(h), lr_dev, _lib.ptr(grad_scale),
-                                      _lib.ptr(found_inf), snap.data_ptr(), _lib.ticket(dev), _lib.stream_ptr(dev))
 
     def zero_grad(self, set_to_none: bool = False):
         """Zeroes the gradients IN PLACE by default (torch's default frees them): the chunk tables
