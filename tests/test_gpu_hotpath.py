@@ -135,6 +135,33 @@ def test_step_graph_replay_with_device_alpha(dev, fused, ema_parallel):
             assert torch.equal(p.detach().cpu(), e)
 
 
+def test_step_graph_alpha_feed(dev):
+    """alpha_feed runs inside the captured graph behind the AdaIN launches and loads the NEXT replay's scalars
+    from a device table (what bench.py uses): replay r must see row r of the table."""
+    host, inp = _inputs(dev, seed=21, rewarp=False)
+    shapes = [(64,)]
+    student, teacher = Bag(S.parameter_list(shapes, 3)).to(dev), Bag(S.parameter_list(shapes, 4)).to(dev)
+    step = HotPathStep(teacher, student, sigma=2)
+    table = torch.tensor([[0.1, 0.9], [0.5, 0.25], [1.0, 0.0], [0.0, 1.0], [0.7, 0.3], [0.2, 0.6]], device=dev)
+    pair = torch.zeros(2, device=dev)
+    inp.alpha_s2t, inp.alpha_t2s = pair[0:1], pair[1:2]
+    row = torch.ones(1, dtype=torch.int64, device=dev)
+
+    def feed():
+        pair.copy_(table.index_select(0, row).view(2))
+        row.add_(1).remainder_(table.shape[0])
+
+    step.alpha_feed = feed
+    pair.copy_(table[0])
+    step.capture(inp, include_ema=False, warmup=2)     # the two eager warm-up passes consume rows 0 and 1
+    for r in (2, 3, 4):
+        out = step.replay()
+        torch.cuda.synchronize()
+        a1, a2 = float(table[r, 0]), float(table[r, 1])
+        assert_close_scaled(out["t_s2t"], R.adain_mix(host["feat_src"], host["feat_tgt_ori"], a1), 1e-5, f"s2t replay row {r}")
+        assert_close_scaled(out["t_t2s"], R.adain_mix(host["feat_tgt_tea"], host["feat_src_ori"], a2), 1e-5, f"t2s replay row {r}")
+
+
 def test_step_bytes_accounting(dev):
     _, inp = _inputs(dev, b=2, k=16)
     for fused in (True, False):

@@ -20,7 +20,10 @@ from . import _lib
 
 __all__ = ["OldWeightEMA", "ModelEMA", "MultiTensorPlan"]
 
-CHUNK_ELEMS = 4096  # elements per CTA: 256 threads x 4 x 128-bit vectors (fp32)
+import os
+
+# elements per CTA: 256 threads x 4 x 128-bit vectors (fp32).  UDAPE_EMA_CHUNK overrides it (tuning).
+CHUNK_ELEMS = int(os.environ.get("UDAPE_EMA_CHUNK", "4096"))
 
 
 def _dense_like(p: torch.Tensor, s: torch.Tensor) -> bool:
