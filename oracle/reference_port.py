@@ -60,6 +60,22 @@ def calc_style_loss(input, target):
     return mse(input_mean, target_mean) + mse(input_std, target_std)
 
 
+def style_transfer(encoder, decoder, content, style, alpha, recover_min=None, recover_max=None):
+    """What the trainers keep of ``Style_net.Net.forward`` (Style_net.py:163-170; the content / Gram losses
+    of :171-177 are discarded by every caller, train_human.py:275,350,355) followed by the clamp of :276.
+    ``encoder`` is sliced like Net.__init__ (:122-126)."""
+    enc = torch.nn.Sequential(*list(encoder.children())[:31])
+    with torch.no_grad():
+        style_feat = enc(style)
+        content_feat = enc(content)
+        t = adaptive_instance_normalization(content_feat, style_feat)
+        t = alpha * t + (1 - alpha) * content_feat
+        g_t = decoder(t)
+        if recover_min is not None:
+            g_t = channel_clamp(g_t, recover_min, recover_max)
+    return g_t
+
+
 def adain_mix(content_feat, style_feat, alpha=1.0):
     """Style_net.py:164,167-168 — t = adain(c, s); t = alpha * t + (1 - alpha) * c."""
     assert 0 <= alpha <= 1

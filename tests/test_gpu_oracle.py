@@ -409,6 +409,47 @@ def test_mean_std_backward_properties(dev):
     assert abs(plane.norm().item() - expect) < 1e-6 * expect + 1e-9
 
 
+def test_style_transfer_forward_only_vs_oracle(dev):
+    """StyleTransfer = what the trainers keep of Style_net.Net.forward (element [2]) + the clamp: a small
+    encoder with the reference's 31-layer slicing and a mirrored decoder, cuDNN convolutions in fp32."""
+    nn = torch.nn
+
+    def make():
+        torch.manual_seed(7)
+        layers, c = [nn.Conv2d(3, 3, 1)], 3
+        for i, width in enumerate((8, 8, 12, 12, 16, 16, 16, 16, 16, 24)):   # 1 + 10 * 3 = 31 children
+            layers += [nn.ReflectionPad2d(1), nn.Conv2d(c, width, 3), nn.ReLU()]
+            c = width
+        enc = nn.Sequential(*layers, nn.Conv2d(c, c, 1))                     # a 32nd child the slicing must ignore
+        dec = nn.Sequential(nn.ReflectionPad2d(1), nn.Conv2d(24, 8, 3), nn.ReLU(), nn.Conv2d(8, 3, 1))
+        return enc, dec
+
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        enc, dec = make()
+        g = torch.Generator().manual_seed(2)
+        content = torch.randn(3, 3, 40, 40, generator=g)
+        style = torch.randn(3, 3, 40, 40, generator=g) * 1.5 + 0.3
+        lo, hi = torch.tensor([-0.4, -0.5, -0.3]), torch.tensor([0.5, 0.4, 0.6])
+        enc_d, dec_d = make()
+        st = U.StyleTransfer(enc_d, dec_d).to(dev).eval()
+        assert all(not p.requires_grad for n_, p in st.named_parameters() if n_.startswith("enc_"))
+        with torch.no_grad():
+            out = st(content.to(dev), style.to(dev), 0.6)
+            assert out[0] is None and out[1] is None
+            assert_close_scaled(out[2], R.style_transfer(enc, dec, content, style, 0.6), 1e-4, "g_t")
+            y = st.stylize(content.to(dev), style.to(dev), 0.6, lo.to(dev), hi.to(dev))
+            assert y.is_contiguous()
+            assert_close_scaled(y, R.style_transfer(enc, dec, content, style, 0.6, lo, hi).contiguous(), 1e-4, "stylize")
+            # different spatial sizes for content and style take the two-pass encode
+            style2 = torch.randn(3, 3, 24, 56, generator=g)
+            assert_close_scaled(st(content.to(dev), style2.to(dev), 1.0)[2], R.style_transfer(enc, dec, content, style2, 1.0),
+                                1e-4, "g_t (ragged style)")
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
 # ---------------------------------------------------------------- clamp + fused loss step ------------
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("shape", [(32, 3, 256, 256), (2, 3, 7, 9), (1, 5, 33, 1)])

@@ -126,3 +126,19 @@ def test_style_loss():
     a, b = R.calc_style_loss(x, t), net.Net.calc_style_loss(fake_self, x2, t)
     assert torch.equal(a, b)
     assert torch.equal(torch.autograd.grad(a, x)[0], torch.autograd.grad(b, x2)[0])
+
+
+def test_style_transfer_forward_only():
+    """The part of Style_net.Net.forward the trainers keep (element [2]) + the clamp of train_human.py:276,
+    against the real class with the reference module's own (randomly initialised) VGG-19 / decoder."""
+    sn = ref_loader.load("style_net")
+    torch.manual_seed(0)
+    net = sn.Net(sn.vgg, sn.decoder).eval()
+    g = torch.Generator().manual_seed(1)
+    content, style = torch.randn(2, 3, 32, 32, generator=g), torch.randn(2, 3, 32, 32, generator=g)
+    lo, hi = torch.tensor([-2.1179, -2.0357, -1.8044]), torch.tensor([2.2489, 2.4285, 2.64])
+    with torch.no_grad():
+        g_t = net(content, style, 0.6)[2]
+        ref = torch.maximum(torch.minimum(g_t.permute(0, 2, 3, 1), hi), lo).permute(0, 3, 1, 2)
+    assert torch.equal(R.style_transfer(sn.vgg, sn.decoder, content, style, 0.6), g_t)
+    assert torch.equal(R.style_transfer(sn.vgg, sn.decoder, content, style, 0.6, lo, hi), ref)

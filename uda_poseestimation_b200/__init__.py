@@ -19,6 +19,7 @@ Reference name → module here
     train_human.py:359-372,417-423 (inline)    : teacher_recon, student_recon (three tF.affine calls per
                                                  sample → one gather launch, with backward)
     train_human.py:385-412 (inline)            : occlude_keypoints;  affine_nearest = batched tF.affine
+    lib/models/Style_net.py:121-177 (as used)  : StyleTransfer (forward-only Net: encode, fused AdaIN+mix, decode; + clamp)
     train_human.py:136-141,260,436-440         : Adam, SGD, GradScaler (torch.optim / torch.cuda.amp drop-ins:
                                                  unscale + update + teacher EMA in one multi-tensor launch)
 """
@@ -33,6 +34,7 @@ from .keypoint_detection import (accuracy, accuracy_from_counts, calc_dists, dec
 from .loss import ConsLoss, JointsMSELoss, cons_loss, fused_losses, joints_mse_loss
 from .mask import confidence_mask, consistency_mask, teacher_targets
 from .optim import SGD, Adam, GradScaler
+from .stylize import StyleTransfer
 from .rewarp import affine_nearest, occlude_keypoints, student_recon, teacher_recon
 
 __version__ = "0.1.0"
@@ -47,5 +49,5 @@ __all__ = [
     "confidence_mask", "consistency_mask", "teacher_targets",
     "OldWeightEMA", "ModelEMA", "MultiTensorPlan",
     "teacher_recon", "student_recon", "occlude_keypoints", "affine_nearest",
-    "Adam", "SGD", "GradScaler",
+    "Adam", "SGD", "GradScaler", "StyleTransfer",
 ]
