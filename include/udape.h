@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define UDAPE_VERSION 100 /* major*10000 + minor*100 + patch */
+#define UDAPE_VERSION 200 /* major*10000 + minor*100 + patch */
 
 #if defined(__GNUC__)
 #define UDAPE_API __attribute__((visibility("default")))

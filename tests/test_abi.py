@@ -43,7 +43,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_build_info():
     lib = _lib.load()
-    assert lib.udape_version() == 100
+    assert lib.udape_version() == 200
     info = lib.udape_build_info().decode()
     assert "sm_100a" in info and "udape-b200" in info
 
