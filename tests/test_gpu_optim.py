@@ -248,3 +248,41 @@ def test_grad_check_patterns(dev):
             assert float(opt.check_grads()) == expect, (ti, idx, val)
         p.grad.view(-1)[idx] = old
     assert float(opt.check_grads()) == 0.0
+
+
+@pytest.mark.parametrize("algo", ["adam", "sgd"])
+def test_state_dict_round_trip(dev, algo):
+    """Checkpoint / resume (train_human.py:150-160,226-235 save and reload the optimizer state): an optimizer
+    restored from state_dict() continues exactly like the uninterrupted one, including the device step count."""
+    torch.manual_seed(13)
+    cpu = [torch.randn(300), torch.randn(17, 9)]
+    mk = (lambda ps: U.Adam(ps, lr=1e-2)) if algo == "adam" else (lambda ps: U.SGD(ps, lr=0.05, momentum=0.9, nesterov=True))
+    g = torch.Generator().manual_seed(5)
+    grads = [[torch.randn(t.shape, generator=g) for t in cpu] for _ in range(5)]
+
+    def run(model, opt, its):
+        for it in its:
+            for p, gr in zip(model.parameters(), grads[it]):
+                p.grad = gr.to(dev)
+            opt.step()
+
+    a = Bag(cpu).to(dev)
+    opt_a = mk(a.parameters())
+    run(a, opt_a, range(5))
+    b = Bag(cpu).to(dev)
+    opt_b = mk(b.parameters())
+    run(b, opt_b, range(3))
+    sd = opt_b.state_dict()
+    assert all(float(st["step"]) == 3.0 for st in sd["state"].values())
+    weights = [p.detach().clone() for p in b.parameters()]
+    c = Bag([w.cpu() for w in weights]).to(dev)
+    opt_c = mk(c.parameters())
+    opt_c.load_state_dict(sd)
+    assert opt_c.applied_steps() == 3
+    run(c, opt_c, range(3, 5))
+    assert opt_c.applied_steps() == 5
+    for pa, pc in zip(a.parameters(), c.parameters()):
+        assert torch.equal(pa.detach(), pc.detach())
+    # torch's own optimizer accepts the same state (same keys)
+    ref = (torch.optim.Adam if algo == "adam" else torch.optim.SGD)(c.parameters(), lr=1e-2, **({} if algo == "adam" else {"momentum": 0.9, "nesterov": True}))
+    ref.load_state_dict(sd)
