@@ -188,14 +188,20 @@ student_step_kernel(const udape_opt_chunk* __restrict__ chunks, udape_opt_hyper 
 
 // found_inf := any(!isfinite(grad))  — torch._amp_foreach_non_finite_check_and_unscale_ without the
 // write-back.  ws[0] is a self-resetting ticket, ws[1] the OR word (left zero).
+constexpr int kCheckChunksPerCta = 4;   // one barrier + one ticket per 4 chunks (64 KB of gradients)
+
 __global__ void __launch_bounds__(kOptThreads)
-grad_check_kernel(const udape_opt_chunk* __restrict__ chunks, float* __restrict__ found_inf,
+grad_check_kernel(const udape_opt_chunk* __restrict__ chunks, int64_t n_chunks, float* __restrict__ found_inf,
                   uint32_t* __restrict__ ws) {
-    const udape_opt_chunk c = chunks[blockIdx.x];
-    const float* __restrict__ g = static_cast<const float*>(c.grad);
-    const int n = static_cast<int>(c.numel);
     // a float is non-finite iff its exponent field is all ones: fold with AND over (x & 0x7f800000) == 0x7f800000
     uint32_t bad = 0;
+#pragma unroll 1
+    for (int k = 0; k < kCheckChunksPerCta; ++k) {
+    const int64_t ci = static_cast<int64_t>(blockIdx.x) * kCheckChunksPerCta + k;
+    if (ci >= n_chunks) break;
+    const udape_opt_chunk c = chunks[ci];
+    const float* __restrict__ g = static_cast<const float*>(c.grad);
+    const int n = static_cast<int>(c.numel);
     if (g) {
         int done = 0;
         if (aligned16(g)) {
@@ -218,6 +224,7 @@ grad_check_kernel(const udape_opt_chunk* __restrict__ chunks, float* __restrict_
         }
         for (int i = done + threadIdx.x; i < n; i += kOptThreads)
             bad |= (__float_as_uint(g[i]) & 0x7f800000u) == 0x7f800000u;
+    }
     }
     const int any = __syncthreads_or(static_cast<int>(bad));
     if (threadIdx.x == 0 && any) atomicOr(ws + 1, 1u);
@@ -272,7 +279,8 @@ extern "C" int udape_grad_check(const udape_opt_chunk* chunks_dev, int64_t n_chu
         return e == cudaSuccess ? UDAPE_OK : fail(static_cast<int>(e), "udape_grad_check: %s", cudaGetErrorString(e));
     }
     UDAPE_REQUIRE(chunks_dev, UDAPE_ERR_NULL, "udape_grad_check: chunk table is NULL");
-    grad_check_kernel<<<static_cast<unsigned>(n_chunks), kOptThreads, 0, st>>>(chunks_dev, found_inf, ws);
+    const unsigned grid = static_cast<unsigned>((n_chunks + kCheckChunksPerCta - 1) / kCheckChunksPerCta);
+    grad_check_kernel<<<grid, kOptThreads, 0, st>>>(chunks_dev, n_chunks, found_inf, ws);
     return check_launch("udape_grad_check");
 }
 
