@@ -70,17 +70,29 @@ struct RewarpArgs {
 __device__ __forceinline__ float round_grid(float v, int grid_dtype) {
     return grid_dtype == UDAPE_F16 ? __half2float(__float2half_rn(v)) : __bfloat162float(__float2bfloat16_rn(v));
 }
+template <int GD> __device__ __forceinline__ float round_grid_t(float v, int grid_dtype) {
+    if (GD == UDAPE_F16) return __half2float(__float2half_rn(v));
+    if (GD == UDAPE_BF16) return __bfloat162float(__float2bfloat16_rn(v));
+    return round_grid(v, grid_dtype);
+}
 
-// one tF.affine(nearest) stage: source pixel of output pixel (i, j), or false when out of bounds
-__device__ __forceinline__ bool stage_source(int& i, int& j, const float* __restrict__ r, int W, int H, bool half,
-                                             int grid_dtype) {
+// one tF.affine(nearest) stage: source pixel of output pixel (i, j), or false when out of bounds.
+// HM: 0 = no stage rounds its grid, 1 = this stage does, 2 = decided at run time by `half`;
+// GD: the grid dtype when it is known at compile time (UDAPE_F16 / UDAPE_BF16), -1 = run time.
+// The composed map costs ~75 instructions per stage and pixel when both variants are compiled in under
+// predicates; it was 59 % of the gather kernel's executed instructions at 21 channels per sample
+// (profiles/r01v_rewarp_ncu_summary.txt), so the common cases are specialised.
+template <int HM, int GD>
+__device__ __forceinline__ bool stage_source_t(int& i, int& j, const float* __restrict__ r, int W, int H, bool half,
+                                               int grid_dtype) {
+    const bool rnd = HM == 2 ? half : (HM == 1);
     float x = static_cast<float>(i) + (0.5f - 0.5f * static_cast<float>(W));
     float y = static_cast<float>(j) + (0.5f - 0.5f * static_cast<float>(H));
-    if (half) { x = round_grid(x, grid_dtype); y = round_grid(y, grid_dtype); }
+    if (rnd) { x = round_grid_t<GD>(x, grid_dtype); y = round_grid_t<GD>(y, grid_dtype); }
     // bmm over k = 3 with an FMA chain:  x*r0 -> fma(y, r1, .) -> + 1*r2
     float gx = __fadd_rn(__fmaf_rn(y, r[1], __fmul_rn(x, r[0])), r[2]);
     float gy = __fadd_rn(__fmaf_rn(y, r[4], __fmul_rn(x, r[3])), r[5]);
-    if (half) { gx = round_grid(gx, grid_dtype); gy = round_grid(gy, grid_dtype); }
+    if (rnd) { gx = round_grid_t<GD>(gx, grid_dtype); gy = round_grid_t<GD>(gy, grid_dtype); }
     // grid_sampler_unnormalize (align_corners=False), then nearbyint: F2I.RN rounds ties to even like
     // rint and saturates, so the range test on the integers equals ATen's test on the rounded floats
     const float fx = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), static_cast<float>(W)), 1.0f), 0.5f);
@@ -93,6 +105,10 @@ __device__ __forceinline__ bool stage_source(int& i, int& j, const float* __rest
     j = yi;
     return true;
 }
+__device__ __forceinline__ bool stage_source(int& i, int& j, const float* __restrict__ r, int W, int H, bool half,
+                                             int grid_dtype) {
+    return stage_source_t<2, -1>(i, j, r, W, H, half, grid_dtype);
+}
 
 // a sample's stage table held in registers (rows beyond `stages` are never read)
 struct StageRegs { float r[kRwMaxStages][6]; };
@@ -104,14 +120,25 @@ __device__ __forceinline__ void load_stages(StageRegs& R, const float* __restric
 }
 // composed source pixel of output pixel (i, j), in place (false: zero fill); stages unrolled over the
 // register table
-__device__ __forceinline__ bool composed_source_ij(int& i, int& j, const StageRegs& R, const RewarpArgs& a) {
+template <int HM, int GD>
+__device__ __forceinline__ bool composed_source_ij_t(int& i, int& j, const StageRegs& R, const RewarpArgs& a) {
 #pragma unroll
     for (int s = 0; s < kRwMaxStages; ++s) {
         if (s < a.stages) {
-            if (!stage_source(i, j, R.r[s], a.W, a.H, (a.half_mask >> s) & 1, a.grid_dtype)) return false;
+            if (!stage_source_t<HM, GD>(i, j, R.r[s], a.W, a.H, (a.half_mask >> s) & 1, a.grid_dtype)) return false;
         }
     }
     return true;
+}
+// kernel-uniform dispatch: no rounding (float32 images), every stage on a half grid (the student under
+// autocast), or the per-stage mask (anything else)
+__device__ __forceinline__ bool composed_source_ij(int& i, int& j, const StageRegs& R, const RewarpArgs& a) {
+    if (a.half_mask == 0) return composed_source_ij_t<0, -1>(i, j, R, a);
+    if (a.half_mask == (1 << a.stages) - 1) {
+        if (a.grid_dtype == UDAPE_F16) return composed_source_ij_t<1, UDAPE_F16>(i, j, R, a);
+        return composed_source_ij_t<1, UDAPE_BF16>(i, j, R, a);
+    }
+    return composed_source_ij_t<2, -1>(i, j, R, a);
 }
 
 // composed source index of output pixel p through one sample's stage table r[stages][6] (-1: zero).
