@@ -153,13 +153,15 @@ class HotPathStep:
     # -- the step -----------------------------------------------------------------------------------
     def _run(self, inp: StepInputs, with_ema: bool) -> dict:
         """Independent chains, forked onto side streams so that the small heatmap kernels
-        (launch/latency-bound at batch 32) and the EMA stream overlap the two large AdaIN passes:
+        (launch/latency-bound at batch 32) and the EMA stream overlap the two large AdaIN passes
+        (stream priority in brackets):
 
-            main   : AdaIN+mix s2t, AdaIN+mix t2s
-            teacher: [re-warp ->] decode -> k-th mask -> fused loss step (both criteria + both
-                     gradients) [-> re-warp backward of the consistency gradient]
-            student: [re-warp of y_t_stu ->] PCK counts      [unfused: JointsMSELoss fwd -> bwd -> PCK]
-            ema    : multi-tensor EMA over the parameter list (after the join if ema_parallel=False)
+            adain  [-1]: AdaIN+mix s2t, AdaIN+mix t2s [, alpha_feed for the next replay]
+            teacher[-2]: [re-warp ->] decode + k-th select (one launch) -> fused loss step (both criteria +
+                         both gradients) [-> re-warp backward of the consistency gradient]
+            student[-2]: [re-warp of y_t_stu ->] PCK counts   [unfused: JointsMSELoss fwd -> bwd -> PCK]
+            plan   [-2]: [inverse plan of the student re-warp, consumed by its backward]
+            ema    [ 0]: multi-tensor EMA over the parameter list (after the join if ema_parallel=False)
 
         The fork/join is plain stream-event ordering, so it behaves the same eagerly and under
         CUDA-graph capture (where it becomes parallel graph branches)."""
