@@ -250,3 +250,33 @@ def test_occlusion_plan_follows_reference_rng(golden):
         flat = x_in[bi].reshape(3, -1)
         want = np.where(src >= 0, flat[:, np.clip(src, 0, None)], 0.0).reshape(3, n, n)
         np.testing.assert_array_equal(want, x_out[bi])
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """Driver contract: stdout of bench.py is ONE JSON line (fd 1 is re-pointed at stderr for everything
+    else); the reference arm runs the CPU path and needs no GPU."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "hot_path_images_per_sec" and d["unit"] == "images/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_numa_binding_is_best_effort():
+    from uda_poseestimation_b200 import dist as D
+    import os
+    before = os.sched_getaffinity(0)
+    cpus = D.bind_to_gpu_numa(0)          # no NVML / no GPU here: must not raise and must not shrink the mask to nothing
+    assert cpus is None or len(cpus) >= 1
+    assert len(os.sched_getaffinity(0)) >= 1
+    os.sched_setaffinity(0, before)
