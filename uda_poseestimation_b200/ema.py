@@ -12,6 +12,7 @@ fp32 arithmetic ``fl(fl(p*a) + fl(s*(1-a)))`` is bit-identical to the eager refe
 from __future__ import annotations
 
 import ctypes
+import os
 from copy import deepcopy
 
 import torch
@@ -19,8 +20,6 @@ import torch
 from . import _lib
 
 __all__ = ["OldWeightEMA", "ModelEMA", "MultiTensorPlan"]
-
-import os
 
 # elements per CTA: 256 threads x 4 x 128-bit vectors (fp32).  UDAPE_EMA_CHUNK overrides it (tuning).
 CHUNK_ELEMS = int(os.environ.get("UDAPE_EMA_CHUNK", "4096"))
