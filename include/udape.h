@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define UDAPE_VERSION 200 /* major*10000 + minor*100 + patch */
+#define UDAPE_VERSION 300 /* major*10000 + minor*100 + patch */
 
 #if defined(__GNUC__)
 #define UDAPE_API __attribute__((visibility("default")))
@@ -262,12 +262,16 @@ UDAPE_API int udape_ema_multi(const udape_ema_chunk* chunks_dev, int64_t n_chunk
  *   g = grad * (1 / *grad_scale)                       (grad_scale NULL: g = grad)
  *   g += weight_decay * p
  *   Adam:  m += (1-beta1)(g-m);  v = beta2 v + (1-beta2) g^2;  p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
- *   SGD :  buf = step==1 ? g : momentum*buf + (1-dampening) g;  g = nesterov ? g + momentum*buf : buf;  p -= lr g
+ *   SGD :  buf = *fresh ? g : momentum*buf + (1-dampening) g;  g = nesterov ? g + momentum*buf : buf;  p -= lr g
+ *          (fresh: per-TENSOR int32 word, non-zero while the tensor's momentum buffer has never been written —
+ *          torch clones the gradient into it the first time the parameter is updated, per parameter, and a
+ *          loaded checkpoint's buffers are never fresh; NULL = not fresh)
  *   ema = fl(fl(ema*ema_a) + fl(p*ema_b))              (the updated p, three roundings like utils.py:24-25)
  * bc1 = 1-beta1^step, bc2 = 1-beta2^step in double.  step = *step_dev + 1 when step_dev is given, else
- * hyper->step (1-based).  With a ticket (one zeroed, self-resetting uint32) the launch advances *step_dev
- * once all CTAs have read it; with ticket == NULL the counter is only read (several param groups share
- * one counter: only the last launch of a step advances it).  lr_dev (optional) overrides hyper->lr from device memory (CUDA-graph replays across
+ * hyper->step (1-based).  With a ticket (one zeroed, self-resetting uint32) the last CTA of the launch, once
+ * every CTA has read them and only if the update was applied, advances *step_dev (advance_step != 0; several
+ * param groups share one counter: only the last launch of a step advances it) and zeroes the n_fresh words at
+ * fresh_flags (the launch's own tensors).  ticket == NULL: counter and flags are only read.  lr_dev (optional) overrides hyper->lr from device memory (CUDA-graph replays across
  * MultiStepLR milestones).  If *found_inf != 0 the student, its state and the step counter are left
  * untouched and only the EMA runs, as scaler.step() + tea_optimizer.step() do.  float32 only. */
 enum { UDAPE_OPT_ADAM = 0, UDAPE_OPT_SGD = 1 };
@@ -277,6 +281,7 @@ typedef struct udape_opt_chunk {
     void* state1;
     void* state2;
     void* ema;
+    const int32_t* fresh; /* SGD: the tensor's "momentum buffer not written yet" word (same for all its chunks) */
     int64_t numel;
 } udape_opt_chunk;
 typedef struct udape_opt_hyper {
@@ -291,13 +296,15 @@ typedef struct udape_opt_hyper {
 } udape_opt_hyper;
 
 UDAPE_API int64_t udape_opt_plan(void* const* param, const void* const* grad, void* const* state1,
-                       void* const* state2, void* const* ema, const int64_t* numel, int64_t n_tensors,
-                       int64_t chunk_elems, udape_opt_chunk* out, int64_t capacity);
+                       void* const* state2, void* const* ema, const int32_t* const* fresh,
+                       const int64_t* numel, int64_t n_tensors, int64_t chunk_elems, udape_opt_chunk* out,
+                       int64_t capacity);
 UDAPE_API int udape_grad_check(const udape_opt_chunk* chunks_dev, int64_t n_chunks, float* found_inf,
                      uint32_t* ws, void* stream);
 UDAPE_API int udape_student_step(const udape_opt_chunk* chunks_dev, int64_t n_chunks, int algo,
                        const udape_opt_hyper* hyper, const float* lr_dev, const float* grad_scale,
-                       const float* found_inf, int32_t* step_dev, uint32_t* ticket, void* stream);
+                       const float* found_inf, int32_t* step_dev, int advance_step, int32_t* fresh_flags,
+                       int64_t n_fresh, uint32_t* ticket, void* stream);
 
 /* ---- f1: batched multi-stage nearest-neighbour affine re-warp ------------------------------
  * Replaces the per-sample loops of train_human.py:361-372 (teacher recon: k views x three

@@ -43,7 +43,9 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_build_info():
     lib = _lib.load()
-    assert lib.udape_version() == 200
+    import re
+    declared = int(re.search(r"#define UDAPE_VERSION (\d+)", (ROOT / "include" / "udape.h").read_text()).group(1))
+    assert lib.udape_version() == declared >= 300
     info = lib.udape_build_info().decode()
     assert "sm_100a" in info and "udape-b200" in info
 
@@ -122,35 +124,40 @@ def test_opt_plan_host_only_and_argument_errors():
     n_t = len(numel)
     mk = lambda off, holes=(): (ctypes.c_void_p * n_t)(*[None if i in holes else 0x10000 + 0x100000 * i + off for i in range(n_t)])  # noqa: E731
     param, grad, m, v, ema = mk(0), mk(0x20000, holes=(1,)), mk(0x40000, holes=(1,)), mk(0x60000, holes=(1,)), mk(0x80000, holes=(4,))
+    fresh = (ctypes.c_void_p * n_t)(*[None if i == 1 else 0x900000 + 4 * i for i in range(n_t)])
     ne = (ctypes.c_int64 * n_t)(*numel)
-    need = lib.udape_opt_plan(param, grad, m, v, ema, ne, n_t, 4096, None, 0)
+    need = lib.udape_opt_plan(param, grad, m, v, ema, fresh, ne, n_t, 4096, None, 0)
     assert need == 1 + 1 + 2 + 0 + 1
     table = (_lib.OptChunk * need)()
-    assert lib.udape_opt_plan(param, grad, m, v, ema, ne, n_t, 4096, table, need) == need
+    assert lib.udape_opt_plan(param, grad, m, v, ema, fresh, ne, n_t, 4096, table, need) == need
+    # the per-tensor "momentum buffer not written yet" word is the SAME address for every chunk of a tensor
+    assert [c.fresh for c in table] == [0x900000, None, 0x900008, 0x900008, 0x900010]
     rows = [(c.param, c.grad, c.state1, c.state2, c.ema, c.numel) for c in table]
     assert rows[0] == (0x10000, 0x30000, 0x50000, 0x70000, 0x90000, 18)
     assert rows[1][1:4] == (None, None, None) and rows[1][4] == 0x110000 + 0x80000 and rows[1][5] == 4096   # no gradient: EMA only
     assert rows[3] == (0x210000 + 4096 * 4, 0x230000 + 4096 * 4, 0x250000 + 4096 * 4, 0x270000 + 4096 * 4, 0x290000 + 4096 * 4, 1)
     assert rows[4][4] is None and rows[4][5] == 5                                                           # no teacher: no EMA
     assert sum(r[5] for r in rows) == sum(numel)
-    assert lib.udape_opt_plan(param, None, None, None, ema, ne, n_t, 4096, table, need) == need            # NULL tables allowed
-    assert all(c.grad is None and c.state1 is None for c in table)
-    assert lib.udape_opt_plan(None, grad, m, v, ema, ne, n_t, 4096, None, 0) == -1
-    assert lib.udape_opt_plan(param, grad, m, v, ema, ne, n_t, 1000, None, 0) == -5
+    assert lib.udape_opt_plan(param, None, None, None, ema, None, ne, n_t, 4096, table, need) == need      # NULL tables allowed
+    assert all(c.grad is None and c.state1 is None and c.fresh is None for c in table)
+    assert lib.udape_opt_plan(None, grad, m, v, ema, None, ne, n_t, 4096, None, 0) == -1
+    assert lib.udape_opt_plan(param, grad, m, v, ema, None, ne, n_t, 1000, None, 0) == -5
     # student step: argument validation
     h = _lib.OptHyper()
     h.lr, h.beta1, h.beta2, h.eps, h.step = 1e-3, 0.9, 0.999, 1e-8, 1
     fake = ctypes.c_void_p(0x1000)
-    assert lib.udape_student_step(None, 0, _lib.OPT_ADAM, ctypes.byref(h), None, None, None, None, None, None) == 0   # nothing to do
-    assert lib.udape_student_step(None, 4, _lib.OPT_ADAM, ctypes.byref(h), None, None, None, None, None, None) == -1
-    assert lib.udape_student_step(fake, 4, 7, ctypes.byref(h), None, None, None, None, None, None) == -5
+    assert lib.udape_student_step(None, 0, _lib.OPT_ADAM, ctypes.byref(h), None, None, None, None, 0, None, 0, None, None) == 0   # nothing to do
+    assert lib.udape_student_step(None, 4, _lib.OPT_ADAM, ctypes.byref(h), None, None, None, None, 0, None, 0, None, None) == -1
+    assert lib.udape_student_step(fake, 4, 7, ctypes.byref(h), None, None, None, None, 0, None, 0, None, None) == -5
     h.step = 0
-    assert lib.udape_student_step(fake, 4, _lib.OPT_ADAM, ctypes.byref(h), None, None, None, None, None, None) == -5
+    assert lib.udape_student_step(fake, 4, _lib.OPT_ADAM, ctypes.byref(h), None, None, None, None, 0, None, 0, None, None) == -5
     h.step, h.beta1 = 1, 1.5
-    assert lib.udape_student_step(fake, 4, _lib.OPT_ADAM, ctypes.byref(h), None, None, None, None, None, None) == -5
+    assert lib.udape_student_step(fake, 4, _lib.OPT_ADAM, ctypes.byref(h), None, None, None, None, 0, None, 0, None, None) == -5
     h.beta1, h.beta2, h.nesterov = 0.0, 0.0, 1
-    assert lib.udape_student_step(fake, 4, _lib.OPT_SGD, ctypes.byref(h), None, None, None, None, None, None) == -5   # nesterov without momentum
+    assert lib.udape_student_step(fake, 4, _lib.OPT_SGD, ctypes.byref(h), None, None, None, None, 0, None, 0, None, None) == -5   # nesterov without momentum
     assert "Nesterov" in _lib.last_error()
+    h.beta1, h.nesterov = 0.9, 0
+    assert lib.udape_student_step(fake, 4, _lib.OPT_SGD, ctypes.byref(h), None, None, None, None, 0, fake, 3, None, None) == -5   # flags without a ticket
     assert lib.udape_grad_check(fake, 4, None, None, None) == -1
     # decode_select / mean_std_bwd
     assert lib.udape_decode_select(fake, 0, 8, 4, 4, None, None, None, None, None, 0.0, None, 2.0, None, 3, None, None, None, fake, None) == -1

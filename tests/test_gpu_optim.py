@@ -286,3 +286,82 @@ def test_state_dict_round_trip(dev, algo):
     # torch's own optimizer accepts the same state (same keys)
     ref = (torch.optim.Adam if algo == "adam" else torch.optim.SGD)(c.parameters(), lr=1e-2, **({} if algo == "adam" else {"momentum": 0.9, "nesterov": True}))
     ref.load_state_dict(sd)
+
+
+def test_sgd_resumes_a_torch_checkpoint_and_clones_per_parameter(dev):
+    """torch.optim.SGD keeps no 'step' in its state and clones the gradient into the momentum buffer the first
+    time EACH parameter is updated (`if buf is None`), also with dampening != 0.  (1) Resuming a torch SGD
+    checkpoint must keep the loaded buffers (the old global `step <= 1` test overwrote them); (2) a parameter
+    whose gradient first shows up at step 3 gets buf = grad then, the others keep dampening."""
+    torch.manual_seed(3)
+    cpu = [torch.randn(5000), torch.randn(33, 7), torch.randn(64)]
+    kw = dict(lr=0.05, momentum=0.9, dampening=0.3, weight_decay=1e-3)
+    g = torch.Generator().manual_seed(9)
+    grads = [[torch.randn(t.shape, generator=g) for t in cpu] for _ in range(6)]
+
+    def run(model, opt, its, late=None):
+        for it in its:
+            for i, (p, gr) in enumerate(zip(model.parameters(), grads[it])):
+                p.grad = None if (late is not None and i == late and it < 3) else gr.to(dev)
+            opt.step()
+
+    # (1) torch writes the checkpoint after 2 steps, the drop-in resumes it
+    ref = Bag(cpu).to(dev)
+    ref_opt = torch.optim.SGD(ref.parameters(), **kw)
+    run(ref, ref_opt, range(2))
+    sd = ref_opt.state_dict()
+    assert all("step" not in st for st in sd["state"].values())
+    new = Bag([p.detach().cpu() for p in ref.parameters()]).to(dev)
+    new_opt = U.SGD(new.parameters(), **kw)
+    new_opt.load_state_dict(sd)
+    run(ref, ref_opt, range(2, 5))
+    run(new, new_opt, range(2, 5))
+    for a, b in zip(ref.parameters(), new.parameters()):
+        assert_close_scaled(b.detach().cpu(), a.detach().cpu(), RTOL, "resumed SGD vs torch")
+    # (2) parameter 1 has no gradient for three steps
+    ref, new = Bag(cpu).to(dev), Bag(cpu).to(dev)
+    ref_opt, new_opt = torch.optim.SGD(ref.parameters(), **kw), U.SGD(new.parameters(), **kw)
+    run(ref, ref_opt, range(6), late=1)
+    run(new, new_opt, range(6), late=1)
+    for a, b in zip(ref.parameters(), new.parameters()):
+        assert_close_scaled(b.detach().cpu(), a.detach().cpu(), RTOL, "SGD with a late gradient vs torch")
+    for a, b in zip(ref.parameters(), new.parameters()):
+        assert_close_scaled(new_opt.state[b]["momentum_buffer"].cpu(), ref_opt.state[a]["momentum_buffer"].cpu(), RTOL, "buffers")
+    # (3) a skipped first step (found_inf) leaves the buffers "never written": the checkpoint carries none
+    fresh = Bag(cpu).to(dev)
+    fresh_opt = U.SGD(fresh.parameters(), **kw)
+    for p, gr in zip(fresh.parameters(), grads[0]):
+        p.grad = gr.to(dev)
+    fresh_opt.grad_scale, fresh_opt.found_inf = torch.ones((), device=dev), torch.ones((), device=dev)
+    fresh_opt.step()
+    assert all("momentum_buffer" not in st for st in fresh_opt.state_dict()["state"].values())
+    fresh_opt.found_inf = torch.zeros((), device=dev)
+    fresh_opt.step()
+    assert all("momentum_buffer" in st for st in fresh_opt.state_dict()["state"].values())
+    ref1 = Bag(cpu).to(dev)
+    ref1_opt = torch.optim.SGD(ref1.parameters(), **kw)
+    run(ref1, ref1_opt, range(1))
+    for a, b in zip(ref1.parameters(), fresh.parameters()):
+        assert_close_scaled(b.detach().cpu(), a.detach().cpu(), RTOL, "first applied step after a skipped one")
+
+
+def test_detach_teacher_restores_the_plain_ema(dev):
+    """pretrain() steps the student optimizer without tea_optimizer.step() (train_human.py:243-300): after
+    detach_teacher() the optimizer leaves the teacher alone and tea.step() is the plain EMA launch again."""
+    cpu = [torch.randn(1000), torch.randn(40, 3)]
+    s, t = Bag(cpu).to(dev), Bag(cpu).to(dev)
+    opt = U.Adam(s.parameters(), lr=1e-2)
+    tea = U.OldWeightEMA(t, s, alpha=0.9)
+    opt.attach_teacher(tea)
+    for p in s.parameters():
+        p.grad = torch.ones_like(p)
+    opt.step()
+    tea.step()                                   # no-op: already folded in
+    after_fused = _cat(t.parameters())
+    assert not torch.equal(after_fused, _cat(cpu))
+    opt.detach_teacher()
+    opt.step()                                   # pretrain-style step: teacher untouched
+    assert torch.equal(_cat(t.parameters()), after_fused)
+    tea.step()                                   # and the EMA object works on its own again
+    want = after_fused * 0.9 + _cat(s.parameters()) * (1 - 0.9)
+    assert_close_scaled(_cat(t.parameters()), want, RTOL, "plain EMA after detach")

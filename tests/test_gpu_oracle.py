@@ -217,6 +217,22 @@ def test_teacher_targets_vs_oracle(dev, cfg):
     assert_close_scaled(U.rectify(hm.to(dev), sigma), rect_ref, 1e-5, "rectify()")
 
 
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_conf_table_threshold_is_rounded_like_torch_for_half_maps(dev, dt):
+    """`conf >= occlude_thresh` on a half tensor compares in half: torch rounds 0.9 to half(0.9) first, so a
+    plane whose maximum IS half(0.9) passes (it fails against the float32 0.9).  Bit-exact bar."""
+    b, k = 4, 5
+    hm = (torch.rand(b, k, 16, 16) * 0.5).to(dt)
+    edge = torch.tensor(0.9, dtype=dt)
+    below = (edge.view(torch.int16) - 1).view(dt)      # the next representable value below half(0.9)
+    hm[0, 0, 3, 3], hm[0, 1, 4, 4], hm[1, 2, 5, 5] = edge, below, 1.0
+    conf_ref, pos_ref, table_ref = R.confidence_mask(hm, 0.9)
+    assert bool(table_ref[0, 0]) and not bool(table_ref[0, 1]) and bool(table_ref[1, 2])
+    conf, pos, table = U.confidence_mask(hm.to(dev), 0.9)
+    assert torch.equal(table.cpu(), table_ref) and torch.equal(pos.cpu(), pos_ref)
+    assert torch.equal(conf.cpu().to(dt), conf_ref)
+
+
 def test_mask_select_all_ranks(dev):
     """every k of kthvalue on data with ties, NaN and infinities (bit-exact)"""
     g = torch.Generator().manual_seed(8)

@@ -280,3 +280,17 @@ def test_numa_binding_is_best_effort():
     assert cpus is None or len(cpus) >= 1
     assert len(os.sched_getaffinity(0)) >= 1
     os.sched_setaffinity(0, before)
+
+
+def test_old_weight_ema_is_constructible_before_the_models_move_to_the_gpu():
+    """train_human.py:141 builds OldWeightEMA(teacher, student) BEFORE DataParallel(...).cuda() (:145-146): the
+    constructor's initial copy (utils.py:18-19) must work on CPU modules; only step() is the CUDA operator."""
+    import uda_poseestimation_b200 as U
+    torch.manual_seed(0)
+    student, teacher = torch.nn.Linear(7, 5), torch.nn.Linear(7, 5)
+    ema = U.OldWeightEMA(teacher, student, alpha=0.999)
+    for t, s in zip(teacher.parameters(), student.parameters()):
+        assert torch.equal(t.data, s.data) and t.data_ptr() != s.data_ptr()
+    assert ema.target_params[0] is next(teacher.parameters())      # the live Parameter objects (they survive .cuda())
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        ema.step()                                                  # no CPU fallback for the operator itself

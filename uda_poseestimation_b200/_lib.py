@@ -41,7 +41,7 @@ class EmaChunk(ctypes.Structure):
 
 class OptChunk(ctypes.Structure):
     _fields_ = [("param", c_void_p), ("grad", c_void_p), ("state1", c_void_p), ("state2", c_void_p),
-                ("ema", c_void_p), ("numel", c_int64)]
+                ("ema", c_void_p), ("fresh", c_void_p), ("numel", c_int64)]
 
 
 class OptHyper(ctypes.Structure):
@@ -93,10 +93,11 @@ PROTOTYPES = {
                                  c_int64, POINTER(EmaChunk), c_int64]),
     "udape_ema_multi": (c_int, [c_void_p, c_int64, c_int64, c_float, c_float, c_int, c_int, c_void_p]),
     "udape_opt_plan": (c_int64, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
-                                 POINTER(c_void_p), POINTER(c_int64), c_int64, c_int64, POINTER(OptChunk), c_int64]),
+                                 POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_int64, c_int64,
+                                 POINTER(OptChunk), c_int64]),
     "udape_grad_check": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "udape_student_step": (c_int, [c_void_p, c_int64, c_int, POINTER(OptHyper), c_void_p, c_void_p, c_void_p,
-                                   c_void_p, c_void_p, c_void_p]),
+                                   c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     "udape_rewarp_fwd": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p, c_int,
                                  c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "udape_rewarp_plan_elems": (c_int64, [c_int64, c_int64, c_int]),

@@ -62,12 +62,29 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every CUDA source for sm_100a and link the shared library. Idempotent."""
+    """Compile every CUDA source for sm_100a and link the shared library. Idempotent.
+
+    One process per GPU means several ranks may get here at once on a fresh checkout: the build runs under an
+    exclusive file lock (the others wait, then find the library current), and the library is linked to a
+    temporary name and renamed into place, so no rank can ``dlopen`` a half-written file."""
     if not force and not needs_build():
         return lib_path()
-    nvcc = find_nvcc()
+    import fcntl
+
     OBJ_DIR.mkdir(parents=True, exist_ok=True)
     LIB_DIR.mkdir(parents=True, exist_ok=True)
+    with open(OBJ_DIR / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():   # another rank built it while this one waited
+                return lib_path()
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> Path:
+    nvcc = find_nvcc()
     header_mtime = max(
         [p.stat().st_mtime for p in CSRC.glob("*.cuh")]
         + [p.stat().st_mtime for p in (REPO_DIR / "include").glob("*.h")]
@@ -93,11 +110,14 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     with ThreadPoolExecutor(max_workers=min(8, len(sources))) as ex:
         objs = list(ex.map(compile_one, sources))
     # default visibility is hidden; the extern "C" entry points are exported explicitly
-    cmd = [nvcc, "-shared", "-o", str(lib_path()), *map(str, objs), "-cudart", "static",
+    tmp = lib_path().with_name(f".{LIB_NAME}.{os.getpid()}.tmp")
+    cmd = [nvcc, "-shared", "-o", str(tmp), *map(str, objs), "-cudart", "static",
            "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
+        tmp.unlink(missing_ok=True)
         raise RuntimeError(f"link failed:\n{r.stdout}{r.stderr}")
+    os.replace(tmp, lib_path())
     return lib_path()
 
 

@@ -36,7 +36,6 @@ struct OptScalars {
     float neg_step;    // Adam: -(lr / bias_correction1)   SGD: -lr
     float bc2_sqrt;    // Adam: sqrt(bias_correction2)
     int skip;          // found_inf != 0: leave the student alone
-    int first;         // SGD: this is update number 1 (momentum buffer := grad)
 };
 
 __device__ __forceinline__ float ema_fold(float t, float s, float a, float b) {
@@ -53,11 +52,13 @@ __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v,
 }
 
 template <bool NESTEROV>
-__device__ __forceinline__ void sgd_elem(float& p, float g, float& buf, const OptScalars& c, bool momentum) {
+__device__ __forceinline__ void sgd_elem(float& p, float g, float& buf, const OptScalars& c, bool momentum,
+                                         bool first) {
     g *= c.inv_scale;
     if (c.wd != 0.0f) g = fmaf(c.wd, p, g);
     if (momentum) {
-        buf = c.first ? g : fmaf(c.beta2, g, buf * c.w1);   // buf.mul_(momentum).add_(grad, alpha=1-dampening)
+        // first update of THIS parameter: buf = clone(grad); else buf.mul_(momentum).add_(grad, alpha=1-dampening)
+        buf = first ? g : fmaf(c.beta2, g, buf * c.w1);
         g = NESTEROV ? fmaf(c.w1, buf, g) : buf;            // grad.add(buf, alpha=momentum)
     }
     p = fmaf(-c.lr, g, p);                                  // param.add_(grad, alpha=-lr)
@@ -68,8 +69,8 @@ template <int ALGO>
 __global__ void __launch_bounds__(kOptThreads)
 student_step_kernel(const udape_opt_chunk* __restrict__ chunks, udape_opt_hyper h,
                     const float* __restrict__ lr_dev, const float* __restrict__ grad_scale,
-                    const float* __restrict__ found_inf, int32_t* __restrict__ step_dev,
-                    uint32_t* __restrict__ ticket) {
+                    const float* __restrict__ found_inf, int32_t* __restrict__ step_dev, int advance_step,
+                    int32_t* __restrict__ fresh_flags, int n_fresh, uint32_t* __restrict__ ticket) {
     __shared__ OptScalars sc;
     const udape_opt_chunk c = chunks[blockIdx.x];
     if (threadIdx.x == 0) {
@@ -82,7 +83,6 @@ student_step_kernel(const udape_opt_chunk* __restrict__ chunks, udape_opt_hyper 
         s.lr = static_cast<float>(lr);
         s.eps = static_cast<float>(h.eps);
         s.wd = static_cast<float>(h.weight_decay);
-        s.first = step <= 1;
         if (ALGO == 0) {
             s.w1 = static_cast<float>(1.0 - h.beta1);
             s.beta2 = static_cast<float>(h.beta2);
@@ -112,6 +112,8 @@ student_step_kernel(const udape_opt_chunk* __restrict__ chunks, udape_opt_hyper 
     const int n = static_cast<int>(c.numel);
     const bool upd = !s.skip && g != nullptr;            // torch skips parameters whose grad is None
     const bool has_m = m != nullptr;                     // SGD with momentum == 0 keeps no buffer
+    // torch/optim/sgd.py: `if buf is None: buf = torch.clone(grad)` — per parameter, the first time it is updated
+    const bool first = ALGO != 0 && c.fresh != nullptr && *c.fresh != 0;
     const bool vec_ok = aligned16(p) && (!upd || (aligned16(g) && (!has_m || aligned16(m)) &&
                                                   (ALGO != 0 || aligned16(v)))) && (!t || aligned16(t));
     int done = 0;
@@ -145,7 +147,7 @@ student_step_kernel(const udape_opt_chunk* __restrict__ chunks, udape_opt_hyper 
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             if (ALGO == 0) adam_elem(fp[e], fg[e], fm[e], fv[e], s);
-                            else sgd_elem<ALGO == 2>(fp[e], fg[e], fm[e], s, has_m);
+                            else sgd_elem<ALGO == 2>(fp[e], fg[e], fm[e], s, has_m, first);
                         }
                         stg_plain(reinterpret_cast<uint4*>(p) + i, pack16<float>(fp));
                         if (has_m) stg_plain(reinterpret_cast<uint4*>(m) + i, pack16<float>(fm));
@@ -171,7 +173,7 @@ student_step_kernel(const udape_opt_chunk* __restrict__ chunks, udape_opt_hyper 
                 adam_elem(fp, g[i], fm, fv, s);
                 v[i] = fv;
             } else {
-                sgd_elem<ALGO == 2>(fp, g[i], fm, s, has_m);
+                sgd_elem<ALGO == 2>(fp, g[i], fm, s, has_m, first);
             }
             p[i] = fp;
             if (has_m) m[i] = fm;
@@ -181,8 +183,11 @@ student_step_kernel(const udape_opt_chunk* __restrict__ chunks, udape_opt_hyper 
     // the step counter advances once per launch, after every CTA has read it, and only when the
     // update was applied (torch: state['step'] is not touched when scaler.step() skips)
     // (ticket == NULL: the counter is only read — the launches of all but the last param group of a step)
-    if (step_dev && ticket) {
-        if (last_block_done(ticket, gridDim.x) && threadIdx.x == 0 && !s.skip) *step_dev = *step_dev + 1;
+    if (ticket) {
+        if (last_block_done(ticket, gridDim.x) && !s.skip) {
+            if (threadIdx.x == 0 && step_dev && advance_step) *step_dev = *step_dev + 1;
+            for (int i = threadIdx.x; i < n_fresh; i += kOptThreads) fresh_flags[i] = 0;
+        }
     }
 }
 
@@ -240,9 +245,9 @@ grad_check_kernel(const udape_opt_chunk* __restrict__ chunks, int64_t n_chunks, 
 using namespace udape;
 
 extern "C" int64_t udape_opt_plan(void* const* param, const void* const* grad, void* const* state1,
-                                  void* const* state2, void* const* ema, const int64_t* numel,
-                                  int64_t n_tensors, int64_t chunk_elems, udape_opt_chunk* out,
-                                  int64_t capacity) {
+                                  void* const* state2, void* const* ema, const int32_t* const* fresh,
+                                  const int64_t* numel, int64_t n_tensors, int64_t chunk_elems,
+                                  udape_opt_chunk* out, int64_t capacity) {
     if (!param || !numel) return fail(UDAPE_ERR_NULL, "udape_opt_plan: NULL table");
     if (n_tensors < 0 || chunk_elems <= 0 || chunk_elems >= (1ll << 31) || (chunk_elems % 16) != 0)
         return fail(UDAPE_ERR_ARG, "udape_opt_plan: chunk_elems must be a positive multiple of 16 below 2^31");
@@ -262,6 +267,7 @@ extern "C" int64_t udape_opt_plan(void* const* param, const void* const* grad, v
                 out[n].state1 = state1 ? at(state1[t]) : nullptr;
                 out[n].state2 = state2 ? at(state2[t]) : nullptr;
                 out[n].ema = ema ? at(ema[t]) : nullptr;
+                out[n].fresh = fresh ? fresh[t] : nullptr;
                 out[n].numel = rem < chunk_elems ? rem : chunk_elems;
             }
         }
@@ -286,7 +292,8 @@ extern "C" int udape_grad_check(const udape_opt_chunk* chunks_dev, int64_t n_chu
 
 extern "C" int udape_student_step(const udape_opt_chunk* chunks_dev, int64_t n_chunks, int algo,
                                   const udape_opt_hyper* hyper, const float* lr_dev, const float* grad_scale,
-                                  const float* found_inf, int32_t* step_dev, uint32_t* ticket, void* stream) {
+                                  const float* found_inf, int32_t* step_dev, int advance_step,
+                                  int32_t* fresh_flags, int64_t n_fresh, uint32_t* ticket, void* stream) {
     if (n_chunks == 0) return UDAPE_OK;
     UDAPE_REQUIRE(chunks_dev && hyper, UDAPE_ERR_NULL, "udape_student_step: chunk table / hyper is NULL");
     UDAPE_REQUIRE(n_chunks > 0 && n_chunks < (1ll << 31), UDAPE_ERR_SHAPE, "udape_student_step: bad n_chunks=%lld", (long long)n_chunks);
@@ -297,13 +304,16 @@ extern "C" int udape_student_step(const udape_opt_chunk* chunks_dev, int64_t n_c
                       UDAPE_ERR_ARG, "udape_student_step: Adam needs 0 <= beta < 1 and eps >= 0");
     UDAPE_REQUIRE(!(hyper->nesterov && algo == UDAPE_OPT_SGD && (hyper->beta1 <= 0.0 || hyper->beta2 != 0.0)),
                   UDAPE_ERR_ARG, "udape_student_step: Nesterov momentum requires a momentum and zero dampening");
+    UDAPE_REQUIRE(n_fresh >= 0 && n_fresh < (1ll << 31) && (n_fresh == 0 || (fresh_flags && ticket)), UDAPE_ERR_ARG,
+                  "udape_student_step: n_fresh=%lld needs fresh_flags and a ticket", (long long)n_fresh);
     cudaStream_t st = as_stream(stream);
     const unsigned grid = static_cast<unsigned>(n_chunks);
+    const int nf = static_cast<int>(n_fresh);
     if (algo == UDAPE_OPT_ADAM)
-        student_step_kernel<0><<<grid, kOptThreads, 0, st>>>(chunks_dev, *hyper, lr_dev, grad_scale, found_inf, step_dev, ticket);
+        student_step_kernel<0><<<grid, kOptThreads, 0, st>>>(chunks_dev, *hyper, lr_dev, grad_scale, found_inf, step_dev, advance_step, fresh_flags, nf, ticket);
     else if (hyper->nesterov)
-        student_step_kernel<2><<<grid, kOptThreads, 0, st>>>(chunks_dev, *hyper, lr_dev, grad_scale, found_inf, step_dev, ticket);
+        student_step_kernel<2><<<grid, kOptThreads, 0, st>>>(chunks_dev, *hyper, lr_dev, grad_scale, found_inf, step_dev, advance_step, fresh_flags, nf, ticket);
     else
-        student_step_kernel<1><<<grid, kOptThreads, 0, st>>>(chunks_dev, *hyper, lr_dev, grad_scale, found_inf, step_dev, ticket);
+        student_step_kernel<1><<<grid, kOptThreads, 0, st>>>(chunks_dev, *hyper, lr_dev, grad_scale, found_inf, step_dev, advance_step, fresh_flags, nf, ticket);
     return check_launch("udape_student_step");
 }

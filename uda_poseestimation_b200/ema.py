@@ -113,8 +113,14 @@ class OldWeightEMA(object):
         n = min(len(self.target_params), len(self.source_params))  # zip() semantics
         dst = [p.data for p in self.target_params[:n]]
         src = [p.data for p in self.source_params[:n]]
-        if n:
+        if n and all(t.is_cuda for t in dst + src):
             MultiTensorPlan(dst, src, as_bytes=True).run(0.0, 1.0, 1)  # p.data[:] = src_p.data[:]
+        else:
+            # the trainers build this object BEFORE the models move to the GPU (train_human.py:141 vs
+            # :145-146): the one-off initial copy of utils.py:18-19 is then a host copy; step() is the
+            # CUDA operator and plans lazily, on the storages the parameters have by then
+            for d, s in zip(dst, src):
+                d.copy_(s)
 
     def _get_plan(self) -> MultiTensorPlan:
         plan = self._plan

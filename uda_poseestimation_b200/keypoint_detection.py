@@ -67,6 +67,11 @@ def decode(hm: torch.Tensor, *, want_idx=False, want_preds=False, want_maxvals=F
     mv32 = torch.empty((b, k), dtype=torch.float32, device=dev) if want_maxvals_f32 else None
     pos = torch.empty((b, k, 2), dtype=torch.int64, device=dev) if want_position else None
     conf = torch.empty((b, k), dtype=torch.bool, device=dev) if occlude_thresh is not None else None
+    if occlude_thresh is not None and hm.dtype != torch.float32:
+        # `conf >= args.occlude_thresh` on a half tensor compares in the tensor's dtype: torch rounds the Python
+        # scalar to half first (a plane whose maximum is half(0.9) = 0.89990234 passes).  The kernel compares
+        # the exactly-widened maximum in float32, so the threshold is rounded here
+        occlude_thresh = float(torch.tensor(float(occlude_thresh), dtype=hm.dtype))
     rect = torch.empty_like(hm) if rectify_sigma is not None else None
     tea_mask = thresh = None
     if select_kth is not None:

@@ -49,6 +49,11 @@ class _FusedStudentOptimizer(torch.optim.Optimizer):
         self._lr_dev = {}
         self._ws = None             # grad_check workspace (ticket + OR word)
         self._found_inf = None
+        # SGD: one int32 word per parameter (all groups, in order), non-zero while its momentum buffer has
+        # never been written: torch clones the gradient into the buffer the first time THAT parameter is
+        # updated (torch/optim/sgd.py `if buf is None`), and the buffers of a loaded checkpoint are never fresh
+        self._fresh = None
+        self._fresh_index = {}
 
     # -- teacher -----------------------------------------------------------------------------------
     def attach_teacher(self, tea_optimizer: OldWeightEMA):
@@ -57,6 +62,16 @@ class _FusedStudentOptimizer(torch.optim.Optimizer):
         if not isinstance(tea_optimizer, OldWeightEMA):
             raise TypeError("attach_teacher expects the package's OldWeightEMA")
         self._teacher = tea_optimizer
+        self._plans = None
+        return self
+
+    def detach_teacher(self):
+        """Stop folding the EMA into this optimizer's step (``tea_optimizer.step()`` is the plain EMA launch
+        again).  The reference's ``pretrain()`` phase (train_human.py:243-300) steps the student optimizer
+        WITHOUT ``tea_optimizer.step()``: attach for ``train()`` only, or detach around ``pretrain()``."""
+        if self._teacher is not None:
+            self._teacher._fused_pending = False
+        self._teacher = None
         self._plans = None
         return self
 
@@ -90,8 +105,22 @@ class _FusedStudentOptimizer(torch.optim.Optimizer):
                 pair[id(s)] = t
         claimed = set()
         plans = []
+        n_all = sum(len(g["params"]) for g in self.param_groups)
+        if self._fresh is None or self._fresh.numel() != n_all or self._fresh.device != dev:
+            old, old_index = self._fresh, self._fresh_index
+            self._fresh = torch.zeros(max(n_all, 1), dtype=torch.int32, device=dev)
+            self._fresh_index, k = {}, 0
+            for g_ in self.param_groups:
+                for p in g_["params"]:
+                    self._fresh_index[id(p)] = k
+                    if old is not None and id(p) in old_index:
+                        self._fresh[k] = old[old_index[id(p)]]     # add_param_group: keep what is known
+                    k += 1
+        fresh_base = 0
         for gi, group in enumerate(self.param_groups):
             rows = []
+            group_fresh = (fresh_base, len(group["params"]))
+            fresh_base += len(group["params"])
             for p in group["params"]:
                 if _lib.require_cuda(p) != dev:
                     raise RuntimeError("all parameters of a fused optimizer must live on one device")
@@ -112,9 +141,12 @@ class _FusedStudentOptimizer(torch.optim.Optimizer):
                     claimed.add(id(p))
                 if g is None and t is None:
                     continue
+                fresh = None
+                if self._algo == _lib.OPT_SGD and s1 is not None:
+                    fresh = self._fresh.data_ptr() + 4 * self._fresh_index[id(p)]
                 rows.append((p.data_ptr(), g.data_ptr() if g is not None else None,
                              s1.data_ptr() if s1 is not None else None, s2.data_ptr() if s2 is not None else None,
-                             t.data_ptr() if t is not None else None, p.numel()))
+                             t.data_ptr() if t is not None else None, p.numel(), fresh))
             if gi == 0 and self._teacher is not None:
                 # EMA pairs whose student parameter this optimizer does not own (frozen layers): EMA only
                 for t, s in zip(self._teacher.target_params, self._teacher.source_params):
@@ -122,13 +154,14 @@ class _FusedStudentOptimizer(torch.optim.Optimizer):
                         _lib.require_cuda(t, s)
                         if s.dtype != torch.float32 or not (s.is_contiguous() and t.is_contiguous()):
                             raise TypeError("fused student step: EMA-only pairs must be contiguous float32")
-                        rows.append((s.data_ptr(), None, None, None, t.data_ptr(), s.numel()))
+                        rows.append((s.data_ptr(), None, None, None, t.data_ptr(), s.numel(), None))
             rows = [r for r in rows if r[5] > 0]
             n_t = len(rows)
             if n_t == 0:
-                plans.append((group, None, 0))
+                plans.append((group, None, 0, group_fresh))
                 continue
             cols = [(ctypes.c_void_p * n_t)(*[r[c] for r in rows]) for c in range(5)]
+            cols.append((ctypes.c_void_p * n_t)(*[r[6] for r in rows]))
             numel = (ctypes.c_int64 * n_t)(*[r[5] for r in rows])
             need = lib.udape_opt_plan(*cols, numel, n_t, CHUNK_ELEMS, None, 0)
             if need < 0:
@@ -138,7 +171,7 @@ class _FusedStudentOptimizer(torch.optim.Optimizer):
             if got != need:
                 _lib.check(int(got) if got < 0 else -3, "udape_opt_plan")
             host = torch.frombuffer(table, dtype=torch.uint8).clone()
-            plans.append((group, host.to(dev), int(need)))
+            plans.append((group, host.to(dev), int(need), group_fresh))
         if self._step_dev is None:
             self._step_dev = torch.zeros((), dtype=torch.int32, device=dev)
             self._ws = torch.zeros(2, dtype=torch.int32, device=dev)
@@ -163,7 +196,7 @@ class _FusedStudentOptimizer(torch.optim.Optimizer):
         dev = self._step_dev.device
         lib = _lib.load()
         acc = None
-        for i, (_, table, n) in enumerate(plans):
+        for i, (_, table, n, _f) in enumerate(plans):
             out = self._found_inf if i == 0 else torch.zeros((), dtype=torch.float32, device=dev)
             with _lib.on_device(dev):
                 st = lib.udape_grad_check(_lib.ptr(table), n, out.data_ptr(), self._ws.data_ptr(), _lib.stream_ptr(dev))
@@ -204,19 +237,24 @@ class _FusedStudentOptimizer(torch.optim.Optimizer):
             ema_b = float(1.0 - self._teacher.alpha)      # utils.py:22
         if self.capturable and len(self._lr_dev) != len(self.param_groups):
             self.sync_lr()
-        last = max((i for i, (_, _, n) in enumerate(plans) if n), default=-1)
-        for gi, (group, table, n) in enumerate(plans):
+        last = max((i for i, p_ in enumerate(plans) if p_[2]), default=-1)
+        for gi, (group, table, n, (f0, nf)) in enumerate(plans):
             if n == 0:
                 continue
             h = self._hyper(group)
             h.ema_a, h.ema_b, h.step = ema_a, ema_b, 1
             lr_dev = self._lr_dev[gi].data_ptr() if self.capturable else None
-            # every group reads the device step counter; only the last launch of the step (the one that is
-            # handed a ticket) advances it
+            # every group reads the device step counter; only the last launch of the step advances it.  SGD:
+            # each launch clears the "momentum buffer not written yet" words of its own group
+            sgd_flags = self._algo == _lib.OPT_SGD and nf > 0
             with _lib.on_device(dev):
                 st = lib.udape_student_step(table.data_ptr(), n, self._algo, ctypes.byref(h), lr_dev,
                                             _lib.ptr(grad_scale), _lib.ptr(found_inf), self._step_dev.data_ptr(),
-                                            _lib.ticket(dev) if gi == last else None, _lib.stream_ptr(dev))
+                                            1 if gi == last else 0,
+                                            self._fresh.data_ptr() + 4 * f0 if sgd_flags else None,
+                                            nf if sgd_flags else 0,
+                                            _lib.ticket(dev) if (gi == last or sgd_flags) else None,
+                                            _lib.stream_ptr(dev))
             _lib.check(st, "udape_student_step")
         if self._teacher is not None:
             self._teacher._fused_pending = True
@@ -238,12 +276,27 @@ class _FusedStudentOptimizer(torch.optim.Optimizer):
         for st in self.state.values():
             if st:
                 st["step"] = torch.tensor(step)
-        return super().state_dict()
+        sd = super().state_dict()
+        if self._algo == _lib.OPT_SGD and self._fresh is not None:
+            # a momentum buffer that was never written does not exist for torch.optim.SGD: drop it, so that the
+            # first update after a reload clones the gradient (and the file reads like torch's own)
+            fresh = self._fresh.cpu().tolist()
+            k = 0
+            for g in self.param_groups:
+                for p in g["params"]:
+                    if fresh[self._fresh_index[id(p)]] and k in sd["state"]:
+                        sd["state"][k] = {n: v for n, v in sd["state"][k].items() if n != "momentum_buffer"}
+                    k += 1
+        return sd
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
         steps = [float(st["step"]) for st in self.state.values() if "step" in st]
         self._plans = None
+        # every momentum buffer that came with the checkpoint has been written (torch.optim.SGD files carry
+        # no 'step'); parameters without one get their flag when _init_state creates the buffer
+        self._fresh = None
+        self._fresh_index = {}
         if steps:
             dev = self._device()
             if self._step_dev is None:
@@ -307,9 +360,10 @@ class SGD(_FusedStudentOptimizer):
         if group["momentum"] == 0:
             return None, None
         st = self.state[p]
-        if "momentum_buffer" not in st:
-            st["step"] = torch.tensor(0.0)
+        if st.get("momentum_buffer") is None:
+            st.setdefault("step", torch.tensor(0.0))
             st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            self._fresh[self._fresh_index[id(p)]] = 1   # torch: `buf = torch.clone(grad)` on its first update
         return st["momentum_buffer"], None
 
     def _hyper(self, group):
