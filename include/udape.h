@@ -64,6 +64,11 @@ UDAPE_API const char* udape_build_info(void);
 /* copies the calling thread's last error message (NUL-terminated) into buf; returns its length */
 UDAPE_API int udape_last_error(char* buf, size_t buf_bytes);
 
+/* Per-step scalars of a captured CUDA graph (the alpha of train_human.py:349,354 is drawn per step): one tiny launch
+ * copies row (*counter % rows) of a device float32 table [rows, cols] to `out` and advances *counter, so that a
+ * replay needs neither a host copy nor framework kernels in front of it. */
+UDAPE_API int udape_table_feed(const float* table, int rows, int cols, uint32_t* counter, float* out, void* stream);
+
 /* ---- a1: calc_mean_std — adain/function.py:3-11, lib/models/Style_net.py:4-12 ------
  * mean[p] = mean(feat[p,:]); std[p] = sqrt(var_unbiased(feat[p,:]) + eps), p < planes.
  * mean/std are written in `dtype` (the reference returns feat's dtype).  hw == 1 gives
@@ -305,6 +310,74 @@ UDAPE_API int udape_student_step(const udape_opt_chunk* chunks_dev, int64_t n_ch
                        const udape_opt_hyper* hyper, const float* lr_dev, const float* grad_scale,
                        const float* found_inf, int32_t* step_dev, int advance_step, int32_t* fresh_flags,
                        int64_t n_fresh, uint32_t* ticket, void* stream);
+
+/* ---- e: the data-parallel tail of the step over peer memory (NVLink / NVSwitch) ----------------------
+ * One process per GPU replaces nn.DataParallel (train_human.py:145-148: replicate, scatter, reduce-add of
+ * the gradients onto GPU 0) and the  scaler.step(stu_optimizer); tea_optimizer.step()  tail (:436-438).
+ * Every rank keeps its flat float32 gradient bucket, its flat student parameters and a signal pad of
+ * UDAPE_DP_PAD_BYTES (zeroed once) in memory the other ranks have mapped (udape_peer_*, CUDA IPC; any other
+ * mapping of peer memory works as well — the kernels only see pointers).  udape_dp_peers holds, for every
+ * rank, those three addresses AS MAPPED IN THE CALLING PROCESS (entry `rank` is the local memory).
+ * n_total = elements of the flat buffers (multiple of 4); rank r owns the slice
+ *   [r*S, min((r+1)*S, n_total)),  S = udape_dp_shard_elems(n_total, world)  (a multiple of 4096).
+ * One step on one stream of every rank, all ranks taking the same sequence (epoch_dev: a uint32 on this
+ * device, zero at start, advanced by udape_dp_gather_ema; flags in the pads are these step numbers):
+ *   udape_dp_barrier(READY)         every rank's bucket is complete (backward done) before anyone reads it
+ *   udape_dp_reduce_scatter         reduced[i] = (g_0[i] + g_1[i] + ... in rank order) * (1/world) for the own
+ *                                   slice, by 128-bit loads from every rank's bucket; non-finite check of the
+ *                                   result; posts REDUCED + the flag to every rank.  reduced: local, S floats.
+ *                                   ws: 2 zeroed uint32 (left zero).
+ *   udape_dp_wait(REDUCED, &found)  every slice is reduced (and nobody reads this rank's bucket any more);
+ *                                   *found_inf = 1.0f if any rank's slice has a non-finite value else 0.0f
+ *   udape_dp_shard_step             udape_student_step's arithmetic (unscale, Adam | SGD, same scalars) on the
+ *                                   own slice of params with state1 / state2 = this rank's S-element shards of
+ *                                   exp_avg | momentum buffer / exp_avg_sq; skipped if *found_inf != 0; advances
+ *                                   *step_dev when applied; posts PARAMS.  (SGD: buf = grad on update number 1.)
+ *   udape_dp_wait(PARAMS, NULL)     every slice is updated
+ *   udape_dp_gather_ema             params_local[i] = params_owner(i)[i] by 128-bit peer loads for the other ranks'
+ *                                   slices, and teacher[i] = fl(fl(teacher[i]*ema_a) + fl(params[i]*ema_b)) in the
+ *                                   same pass (teacher NULL: gather only; *found_inf != 0: EMA only — nothing
+ *                                   changed anywhere).  Advances *epoch_dev.
+ * Results do not depend on the world size when it is a power of two (exact 1/world) and are bit-identical on
+ * every rank; the replicated form is udape_student_step on the same averaged gradient.
+ * udape_dp_allreduce_counts: out[i] = sum over ranks (rank order) of counts[i], i < n <= 64 int32 — the PCK
+ * hits || valid exchange (keypoint_detection.py:82-92 forms the ratios AFTER summing) in ONE single-CTA launch;
+ * its own epoch word (zero at start).  Every wait is bounded by timeout_ns (0 = unbounded): on expiry the
+ * pad's error word (UDAPE_DP_PAD_ERR) is set to 1 + phase and the kernel carries on — a missing rank costs a
+ * wrong result plus an error the caller can read, never a hung GPU. */
+#define UDAPE_DP_MAX_RANKS 8
+#define UDAPE_DP_PAD_BYTES 8192
+enum { UDAPE_DP_READY = 0, UDAPE_DP_REDUCED = 1, UDAPE_DP_PARAMS = 2, UDAPE_DP_COUNTS = 3, UDAPE_DP_PHASES = 4 };
+#define UDAPE_DP_PAD_ERR (UDAPE_DP_PHASES * UDAPE_DP_MAX_RANKS + UDAPE_DP_MAX_RANKS) /* uint32 index of the error word */
+typedef struct udape_dp_peers {
+    int32_t rank, world;
+    float* grads[UDAPE_DP_MAX_RANKS];
+    float* params[UDAPE_DP_MAX_RANKS];
+    uint32_t* pads[UDAPE_DP_MAX_RANKS];
+} udape_dp_peers;
+
+UDAPE_API int64_t udape_dp_shard_elems(int64_t n_total, int world);
+UDAPE_API int udape_dp_barrier(const udape_dp_peers* peers, int phase, const uint32_t* epoch_dev, uint64_t timeout_ns,
+                     void* stream);
+UDAPE_API int udape_dp_wait(const udape_dp_peers* peers, int phase, const uint32_t* epoch_dev, float* found_inf,
+                  uint64_t timeout_ns, void* stream);
+UDAPE_API int udape_dp_reduce_scatter(const udape_dp_peers* peers, int64_t n_total, float* reduced,
+                            const uint32_t* epoch_dev, uint32_t* ws, void* stream);
+UDAPE_API int udape_dp_shard_step(const udape_dp_peers* peers, int64_t n_total, int algo, const udape_opt_hyper* hyper,
+                        const float* lr_dev, const float* grad_scale, const float* found_inf, int32_t* step_dev,
+                        const float* reduced, float* state1, float* state2, const uint32_t* epoch_dev,
+                        uint32_t* ticket, void* stream);
+UDAPE_API int udape_dp_gather_ema(const udape_dp_peers* peers, int64_t n_total, float* teacher, float ema_a, float ema_b,
+                        const float* found_inf, uint32_t* epoch_dev, uint32_t* ticket, void* stream);
+UDAPE_API int udape_dp_allreduce_counts(const udape_dp_peers* peers, const int32_t* counts, int n, int32_t* out,
+                              uint32_t* epoch_dev, uint64_t timeout_ns, void* stream);
+/* Peer-mappable device memory: cudaMalloc'ed (zeroed) arena, 64-byte CUDA IPC handle to hand to the other
+ * processes of the node, which map it with udape_peer_open (peer access is enabled on first use). */
+UDAPE_API int udape_peer_alloc(size_t bytes, void** ptr);
+UDAPE_API int udape_peer_free(void* ptr);
+UDAPE_API int udape_peer_export(const void* ptr, unsigned char* handle64);
+UDAPE_API int udape_peer_open(const unsigned char* handle64, void** ptr);
+UDAPE_API int udape_peer_close(void* ptr);
 
 /* ---- f1: batched multi-stage nearest-neighbour affine re-warp ------------------------------
  * Replaces the per-sample loops of train_human.py:361-372 (teacher recon: k views x three

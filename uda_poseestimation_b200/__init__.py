@@ -22,6 +22,9 @@ Reference name → module here
     lib/models/Style_net.py:121-177 (as used)  : StyleTransfer (forward-only Net: encode, fused AdaIN+mix, decode; + clamp)
     train_human.py:136-141,260,436-440         : Adam, SGD, GradScaler (torch.optim / torch.cuda.amp drop-ins:
                                                  unscale + update + teacher EMA in one multi-tensor launch)
+    train_human.py:145-148 (nn.DataParallel)   : PeerGroup, ShardedStudentStep (one process per GPU: gradient
+                                                 reduce-scatter, sharded update and parameter all-gather + EMA
+                                                 as peer-memory kernels over NVLink)
 """
 from ._lib import UdapeError, library_path, load as load_library
 from .adain import (adain, adain_mix, adaptive_instance_normalization, calc_mean_std, calc_style_loss,
@@ -33,6 +36,7 @@ from .keypoint_detection import (accuracy, accuracy_from_counts, calc_dists, dec
                                  get_max_preds_torch, pck_counts)
 from .loss import ConsLoss, JointsMSELoss, cons_loss, fused_losses, joints_mse_loss
 from .mask import confidence_mask, consistency_mask, teacher_targets
+from .dp import PeerGroup, ShardedStudentStep
 from .optim import SGD, Adam, GradScaler
 from .stylize import StyleTransfer
 from .rewarp import affine_nearest, occlude_keypoints, student_recon, teacher_recon
@@ -50,4 +54,5 @@ __all__ = [
     "OldWeightEMA", "ModelEMA", "MultiTensorPlan",
     "teacher_recon", "student_recon", "occlude_keypoints", "affine_nearest",
     "Adam", "SGD", "GradScaler", "StyleTransfer",
+    "PeerGroup", "ShardedStudentStep",
 ]

@@ -50,6 +50,11 @@ class OptHyper(ctypes.Structure):
                 ("step", ctypes.c_int32), ("nesterov", ctypes.c_int32)]
 
 
+class DpPeers(ctypes.Structure):
+    _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("grads", c_void_p * 8), ("params", c_void_p * 8),
+                ("pads", c_void_p * 8)]
+
+
 OPT_ADAM, OPT_SGD = 0, 1
 
 
@@ -58,6 +63,7 @@ PROTOTYPES = {
     "udape_version": (c_int, []),
     "udape_build_info": (c_char_p, []),
     "udape_last_error": (c_int, [c_char_p, c_size_t]),
+    "udape_table_feed": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "udape_mean_std": (c_int, [c_void_p, c_int, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p]),
     "udape_mean_std_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p,
                                    c_void_p]),
@@ -98,6 +104,21 @@ PROTOTYPES = {
     "udape_grad_check": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "udape_student_step": (c_int, [c_void_p, c_int64, c_int, POINTER(OptHyper), c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+    "udape_dp_shard_elems": (c_int64, [c_int64, c_int]),
+    "udape_dp_barrier": (c_int, [POINTER(DpPeers), c_int, c_void_p, ctypes.c_uint64, c_void_p]),
+    "udape_dp_wait": (c_int, [POINTER(DpPeers), c_int, c_void_p, c_void_p, ctypes.c_uint64, c_void_p]),
+    "udape_dp_reduce_scatter": (c_int, [POINTER(DpPeers), c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "udape_dp_shard_step": (c_int, [POINTER(DpPeers), c_int64, c_int, POINTER(OptHyper), c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "udape_dp_gather_ema": (c_int, [POINTER(DpPeers), c_int64, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
+    "udape_dp_allreduce_counts": (c_int, [POINTER(DpPeers), c_void_p, c_int, c_void_p, c_void_p, ctypes.c_uint64,
+                                          c_void_p]),
+    "udape_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
+    "udape_peer_free": (c_int, [c_void_p]),
+    "udape_peer_export": (c_int, [c_void_p, POINTER(ctypes.c_ubyte)]),
+    "udape_peer_open": (c_int, [POINTER(ctypes.c_ubyte), POINTER(c_void_p)]),
+    "udape_peer_close": (c_int, [c_void_p]),
     "udape_rewarp_fwd": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p, c_int,
                                  c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "udape_rewarp_plan_elems": (c_int64, [c_int64, c_int64, c_int]),

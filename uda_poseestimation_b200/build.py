@@ -22,7 +22,7 @@ LIB_DIR = PKG_DIR / "lib"
 OBJ_DIR = REPO_DIR / "build" / "udape_obj"
 LIB_NAME = "libudape_b200.so"
 
-SOURCES = ["api.cu", "adain.cu", "clamp.cu", "decode.cu", "loss.cu", "heatmap.cu", "ema.cu", "optim.cu", "rewarp.cu"]
+SOURCES = ["api.cu", "adain.cu", "clamp.cu", "decode.cu", "loss.cu", "heatmap.cu", "ema.cu", "optim.cu", "dp.cu", "rewarp.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -60,9 +60,25 @@ bool pipe_enabled() {
     return !(e && e[0] == '1');
 }
 
+// out[0..cols) = table[(*counter % rows)][0..cols);  *counter += 1   (one warp)
+__global__ void table_feed_kernel(const float* __restrict__ table, int rows, int cols, uint32_t* __restrict__ counter,
+                                  float* __restrict__ out) {
+    const uint32_t r = *counter % static_cast<uint32_t>(rows);
+    for (int i = threadIdx.x; i < cols; i += 32) out[i] = table[static_cast<size_t>(r) * cols + i];
+    __syncwarp();
+    if (threadIdx.x == 0) *counter = *counter + 1u;
+}
+
 }  // namespace udape
 
 extern "C" {
+
+int udape_table_feed(const float* table, int rows, int cols, uint32_t* counter, float* out, void* stream) {
+    UDAPE_REQUIRE(table && counter && out, UDAPE_ERR_NULL, "udape_table_feed: NULL argument");
+    UDAPE_REQUIRE(rows > 0 && cols > 0 && cols <= 1024, UDAPE_ERR_SHAPE, "udape_table_feed: rows=%d cols=%d", rows, cols);
+    udape::table_feed_kernel<<<1, 32, 0, udape::as_stream(stream)>>>(table, rows, cols, counter, out);
+    return udape::check_launch("udape_table_feed");
+}
 
 int udape_version(void) { return UDAPE_VERSION; }
 

@@ -19,11 +19,13 @@ free of host synchronisation, and can therefore be captured into a CUDA graph
 """
 from __future__ import annotations
 
+import ctypes
 import dataclasses
 import os
 
 import torch
 
+from . import _lib
 from . import rewarp as _rewarp
 from .adain import adain_mix
 from .ema import OldWeightEMA
@@ -31,7 +33,101 @@ from .keypoint_detection import _pck
 from .loss import cons_loss, fused_losses, joints_mse_loss
 from .mask import teacher_targets
 
-__all__ = ["StepInputs", "HotPathStep", "step_algorithmic_bytes"]
+__all__ = ["StepInputs", "HotPathStep", "step_algorithmic_bytes", "ScalarFeed", "ReplicatedTail", "PeerTail"]
+
+
+class ScalarFeed:
+    """Per-step scalars of a captured step: row ``counter % rows`` of a device table is copied to ``out`` and
+    the counter advances, in ONE single-warp launch (``udape_table_feed``) — alpha ~ U(0,1) per step
+    (train_human.py:349,354) without a host copy or framework kernels in front of a graph replay."""
+
+    def __init__(self, table: torch.Tensor):
+        if table.dim() != 2 or table.dtype != torch.float32 or not table.is_contiguous():
+            raise TypeError("ScalarFeed: contiguous float32 [rows, cols] table")
+        self.dev = _lib.require_cuda(table)
+        self.table = table
+        self.out = table[0].clone()
+        self.counter = torch.ones(1, dtype=torch.int32, device=self.dev)   # row 0 is loaded; the next load is row 1
+
+    def __call__(self):
+        t = self.table
+        with _lib.on_device(self.dev):
+            st = _lib.load().udape_table_feed(t.data_ptr(), t.shape[0], t.shape[1], self.counter.data_ptr(),
+                                              self.out.data_ptr(), _lib.stream_ptr(self.dev))
+        _lib.check(st, "udape_table_feed")
+
+
+class ReplicatedTail:
+    """``scaler.step(stu_optimizer); tea_optimizer.step()`` (train_human.py:436-438) with every rank holding the
+    whole optimizer state: [NCCL all-reduce of the flat gradient bucket (world > 1)] -> ``udape_grad_check`` ->
+    ``udape_student_step`` (unscale + Adam | SGD + teacher EMA in one multi-tensor launch)."""
+
+    name = "replicated"
+
+    def __init__(self, student, ema: OldWeightEMA, algo: str = "adam", loss_scale: float = 65536.0, group=None, **hyper):
+        from . import dist as D
+        from .optim import SGD, Adam
+
+        self.world = D.dist.get_world_size(group) if (D.dist.is_available() and D.dist.is_initialized()) else 1
+        self.group = group
+        self.bucket = D.FlatGradBucket(list(student.parameters()))
+        self.opt = (Adam if algo == "adam" else SGD)(student.parameters(), **hyper)
+        self.opt.attach_teacher(ema)
+        self.ema, self.algo = ema, algo
+        self.n_params = self.bucket.flat.numel()
+        self.scale = torch.full((), float(loss_scale), dtype=torch.float32, device=self.bucket.flat.device)
+        self.kernels = 2   # grad_check + student_step (the NCCL kernel is the library's, not counted)
+
+    @property
+    def found_inf(self):
+        return self.opt._found_inf
+
+    def run(self):
+        if self.world > 1:
+            self.bucket.allreduce_(average=True, group=self.group)      # DataParallel's reduce-add, as a mean
+        self.opt.grad_scale, self.opt.found_inf = self.scale, self.opt.check_grads()
+        self.opt.step()
+        self.ema._fused_pending = False   # tea_optimizer.step() is not called separately by the assembled step
+
+    def bytes(self) -> dict:
+        p4 = 4 * self.n_params
+        passes = 9 if self.algo == "adam" else 7
+        out = {"grad_check": p4, "student_step": passes * p4}
+        if self.world > 1:
+            out["allreduce_hbm (NCCL ring: ~2 reads + 2 writes of the bucket)"] = 4 * p4
+        return out
+
+
+class PeerTail:
+    """The same tail as three peer-memory kernels over NVLink (``dp.ShardedStudentStep``): gradient
+    reduce-scatter + non-finite check, the update on this rank's 1/W slice, parameter all-gather + EMA."""
+
+    name = "peer"
+
+    def __init__(self, student, teacher, peers, algo: str = "adam", alpha: float = 0.999, loss_scale: float = 65536.0, **hyper):
+        from .dp import ShardedStudentStep
+
+        self.opt = ShardedStudentStep(student.parameters(), peers, algo=algo, teacher_params=list(teacher.parameters()),
+                                      alpha=alpha, **hyper)
+        self.algo, self.world = algo, peers.world
+        self.n_params = self.opt.n_total
+        self.scale = torch.full((), float(loss_scale), dtype=torch.float32, device=peers.dev)
+        self.kernels = self.opt.kernels_per_step
+
+    @property
+    def found_inf(self):
+        return self.opt.found_inf
+
+    def run(self):
+        self.opt.grad_scale = self.scale
+        self.opt.step()
+
+    def bytes(self) -> dict:
+        w, p4, s4 = self.world, 4 * self.n_params, 4 * self.opt.shard_elems
+        state = 7 if self.algo == "adam" else 5      # p, g, m(, v) read; p, m(, v) written
+        return {"reduce_scatter": (w + 1) * s4, "shard_step": state * s4,
+                "gather_ema": p4 + (w - 1) * s4 + 2 * p4,
+                "nvlink_in": 2 * (w - 1) * s4}
 
 
 @dataclasses.dataclass
@@ -57,11 +153,12 @@ class StepInputs:
         return [getattr(self, f.name) for f in dataclasses.fields(self) if getattr(self, f.name) is not None]
 
 
-def step_algorithmic_bytes(inp: StepInputs, n_params: int, param_bytes: int = 4, fused: bool = True) -> dict:
+def step_algorithmic_bytes(inp: StepInputs, n_params: int, param_bytes: int = 4, fused: bool = True, tail=None) -> dict:
     """Algorithmic HBM bytes of one step, per kernel family.
 
     ``fused=True`` is the default step (one loss launch, rectified teacher map evaluated on the fly);
-    ``fused=False`` the operator-by-operator sequence (separate fwd/bwd launches, materialised map)."""
+    ``fused=False`` the operator-by-operator sequence (separate fwd/bwd launches, materialised map).
+    ``tail``: the ReplicatedTail / PeerTail of the step (its kernels replace the bare EMA pass)."""
     ef = inp.feat_src.element_size()
     feat = inp.feat_src.numel() * ef
     hm = inp.y_t_tea.numel()
@@ -71,8 +168,13 @@ def step_algorithmic_bytes(inp: StepInputs, n_params: int, param_bytes: int = 4,
         "adain_mix": 2 * 3 * feat,                        # two directions x (2 reads + 1 write)
         "mask_select": 9 * planes,
         "pck": hm * (e_s + e_l) + 8 * planes,
-        "ema": 3 * n_params * param_bytes,
     }
+    if tail is None:
+        out["ema"] = 3 * n_params * param_bytes
+    else:
+        for name, nbytes in tail.bytes().items():
+            if name != "nvlink_in":      # bytes over NVLink are not HBM bytes of this rank (reported separately)
+                out[name] = nbytes
     if fused:
         out["decode"] = hm * e_t + 40 * planes            # 1 read (+ per-plane outputs)
         # y_s + label read, grad_y_s written; y_t_stu read, grad_y_t_stu written (teacher map analytic)
@@ -88,7 +190,7 @@ def step_algorithmic_bytes(inp: StepInputs, n_params: int, param_bytes: int = 4,
     if inp.theta_stu is not None:
         out["rewarp_student_fwd"] = 2 * hm * e_s + 72 * inp.y_t_stu.shape[0]
         out["rewarp_student_bwd"] = 2 * hm * e_s + 72 * inp.y_t_stu.shape[0]   # grad read + grad write
-    out["total"] = sum(out.values())
+    out["total"] = sum(v for k, v in out.items())
     return out
 
 
@@ -98,7 +200,7 @@ class HotPathStep:
     def __init__(self, teacher: torch.nn.Module, student: torch.nn.Module, sigma=2, mask_ratio: float = 0.5,
                  occlude_thresh: float = 0.9, teacher_alpha: float = 0.999, lambda_c: float = 1.0,
                  loss_scale: float = 65536.0, parallel: bool = True, fused: bool = True,
-                 ema_parallel: bool = True, counts_hook=None):
+                 ema_parallel: bool = True, counts_hook=None, tail=None, ema: OldWeightEMA | None = None):
         self.sigma, self.mask_ratio, self.occlude_thresh = sigma, mask_ratio, occlude_thresh
         self.lambda_c, self.loss_scale = lambda_c, loss_scale
         self.parallel, self.fused, self.ema_parallel = parallel, fused, ema_parallel
@@ -107,7 +209,11 @@ class HotPathStep:
         # overlaps the AdaIN / EMA chains instead of trailing the step
         self.counts_hook = counts_hook
         self._side = None
-        self.ema = OldWeightEMA(teacher, student, alpha=teacher_alpha)  # train_human.py:141
+        # tail: what follows backward — None: the bare EMA (:438, the student update left to torch);
+        # ReplicatedTail / PeerTail: gradient exchange + unscale + Adam | SGD + EMA (:436-438)
+        self.tail = tail
+        self.ema = ema if ema is not None else (getattr(tail, "ema", None) or
+                                                (OldWeightEMA(teacher, student, alpha=teacher_alpha) if tail is None else None))  # :141
         self.n_params = sum(p.numel() for p in teacher.parameters())
         self.graph = None
         self.out = None
@@ -134,7 +240,7 @@ class HotPathStep:
         fused: 2 adain, decode (+ k-th select in its last CTA), loss_step, pck, ema;  unfused: 2 adain,
         decode+rectify(+select), mse fwd/bwd, cons fwd/bwd, pck, ema;  + 4 with the re-warp tables (teacher forward,
         student forward, its inverse plan, student backward)."""
-        return (6 if self.fused else 9) + self.rewarp_kernels
+        return (6 if self.fused else 9) + self.rewarp_kernels + (self.tail.kernels - 1 if self.tail is not None else 0)
 
     def _streams(self, dev):
         if self._side is None or self._side[0].device != dev:
@@ -179,7 +285,7 @@ class HotPathStep:
             with torch.cuda.stream(s_ema):
                 # :438 — independent of every other chain of the hot path (in training it follows
                 # scaler.step(stu_optimizer); the student parameters are an input of this step)
-                self.ema.step()
+                self._tail_or_ema()
                 self._mark("ema done")
         # teacher forward; student forward + inverse plan + backward
         self.rewarp_kernels = (1 if inp.theta_tea is not None else 0) + (3 if inp.theta_stu is not None else 0)
@@ -283,12 +389,18 @@ class HotPathStep:
                 loss_s, loss_c = loss_s.detach(), loss_c.detach()
                 loss_all = loss_s + self.lambda_c * loss_c  # :434
         if with_ema and not ema_side:
-            self.ema.step()  # :438
+            self._tail_or_ema()  # :438
         return dict(t_s2t=t_s2t, t_t2s=t_t2s, conf_table=tt["conf_table"], position=tt["position"],
                     tea_mask=tt["tea_mask"], mask_thresh=tt["mask_thresh"], rectified=tt["rectified"],
                     tea_preds=tt["preds"], loss_s=loss_s, loss_c=loss_c, loss_all=loss_all,
                     grad_y_s=g_s, grad_y_t_stu=g_c, grad_y_t_stu_recon=g_recon, y_t_tea_recon=y_t_tea,
                     y_t_stu_recon=y_t_stu_recon, pck_counts=counts, pred=pred)
+
+    def _tail_or_ema(self):
+        if self.tail is not None:
+            self.tail.run()      # :436-438 — gradient exchange, student update, teacher EMA
+        else:
+            self.ema.step()      # :438 alone
 
     def run_no_ema(self, inp: StepInputs) -> dict:
         return self._run(inp, with_ema=False)

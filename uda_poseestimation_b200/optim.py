@@ -382,6 +382,13 @@ class GradScaler(torch.amp.GradScaler):
         super().__init__(device, **kwargs)
 
     def _check_inf_per_device(self, optimizer):
+        from .dp import ShardedStudentStep
+        if isinstance(optimizer, ShardedStudentStep):
+            # the data-parallel step checks the REDUCED gradient inside step() (between its reduce-scatter and
+            # the update); update() reads this same device scalar afterwards
+            state = self._per_optimizer_states[id(optimizer)]
+            state["found_inf_per_device"] = {optimizer.found_inf.device: optimizer.found_inf}
+            return state["found_inf_per_device"]
         if isinstance(optimizer, _FusedStudentOptimizer):
             found = optimizer.check_grads()
             state = self._per_optimizer_states[id(optimizer)]
