@@ -8,8 +8,14 @@ Markers
 """
 from __future__ import annotations
 
+import os
 import sys
 from pathlib import Path
+
+# PeerGroup.virtual runs up to 8 ranks as 8 streams of ONE device whose kernels wait for each other: give every
+# stream its own hardware queue (the default of 8 connections lets unrelated streams alias and serialise).
+# Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np
 import pytest

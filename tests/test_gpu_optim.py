@@ -309,7 +309,8 @@ def test_sgd_resumes_a_torch_checkpoint_and_clones_per_parameter(dev):
     ref = Bag(cpu).to(dev)
     ref_opt = torch.optim.SGD(ref.parameters(), **kw)
     run(ref, ref_opt, range(2))
-    sd = ref_opt.state_dict()
+    import copy
+    sd = copy.deepcopy(ref_opt.state_dict())     # state_dict() hands out the LIVE buffers; load_state_dict keeps them
     assert all("step" not in st for st in sd["state"].values())
     new = Bag([p.detach().cpu() for p in ref.parameters()]).to(dev)
     new_opt = U.SGD(new.parameters(), **kw)

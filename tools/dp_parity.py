@@ -104,8 +104,9 @@ def check(dev: torch.device, keypoints: int = 16, batch: int = 32, steps: int = 
     for q in range(world):
         j, v = S.keypoints(batch, keypoints, 1234 + q + 5)
         lab.append(U.generate_target_batched(torch.from_numpy(j).to(dev), torch.from_numpy(v).to(dev), (64, 64), 2, (256, 256), device=dev)[0])
-    whole, _ = U.pck_counts(torch.cat(hm), torch.cat(lab))
-    mine, _ = U.pck_counts(hm[rank], lab[rank])
+    from uda_poseestimation_b200.keypoint_detection import _pck
+    whole, _ = _pck(torch.cat(hm), torch.cat(lab), 0.5)      # int32 [2,K] = hits || valid
+    mine, _ = _pck(hm[rank], lab[rank], 0.5)
     got = opt.allreduce_counts(mine)
     torch.cuda.synchronize()
     opt.check()

@@ -52,10 +52,13 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
     asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// 128-bit load of data another GPU wrote (or owns): never served from a stale L1 line
+// 128-bit load of data another GPU owns.  A plain (weak) load that does not allocate in L1: the data was complete
+// before this kernel started (the flag wait is an earlier kernel of the same stream, and L1 is invalidated at
+// kernel boundaries; peer addresses bypass the local L2), so no stale line can serve it.  (ld.relaxed.sys moved
+// the same bytes ~20 % slower: 583 GB/s vs the 770 GB/s a peer copy reaches.)
 __device__ __forceinline__ uint4 ld_peer(const void* p) {
     uint4 r;
-    asm volatile("ld.relaxed.sys.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p)
                  : "memory");
@@ -88,20 +91,6 @@ __device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t e, uint
         }
     }
     return true;
-}
-
-// last-CTA ticket whose partials must be visible to OTHER GPUS afterwards (system-scope fences)
-__device__ __forceinline__ bool last_block_done_sys(uint32_t* ticket, unsigned total) {
-    __shared__ bool is_last_sys;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        const unsigned t = atomicInc(ticket, total - 1u);
-        is_last_sys = (t == total - 1u);
-        if (is_last_sys) __threadfence_system();
-    }
-    __syncthreads();
-    return is_last_sys;
 }
 
 // post step number e of `phase` into every rank's pad (threads 0..W-1 of the calling CTA)
@@ -255,8 +244,13 @@ dp_shard_step_kernel(udape_dp_peers pr, long long lo, long long n, udape_opt_hyp
             }
         }
     }
-    // the updated slice must be visible to the peers' loads before they are told it is ready
-    if (last_block_done_sys(ticket, gridDim.x)) {
+    // The updated slice must be visible to the peers' loads before they are told it is ready.  Every CTA's stores
+    // are ordered before its ticket by a device-scope fence (they are in this GPU's L2, which is where peer loads
+    // are served from); the last CTA, having observed every ticket, fences at SYSTEM scope (post_all) before the
+    // release store of the flag — fence cumulativity carries the other CTAs' stores along.  (A system-scope
+    // fence in every CTA cost ~110 us of the 230 us this kernel took at N=2.)
+    __syncthreads();
+    if (last_block_done(ticket, gridDim.x)) {
         const uint32_t e = *epoch_dev + 1u;
         post_all(pr, UDAPE_DP_PARAMS, e);
         if (threadIdx.x == 0 && !s.skip) *step_dev = *step_dev + 1;
@@ -269,12 +263,19 @@ dp_gather_ema_kernel(udape_dp_peers pr, long long n_total, long long shard_elems
                      float ema_a, float ema_b, const float* __restrict__ found_inf, uint32_t* __restrict__ epoch_dev,
                      uint32_t* __restrict__ ticket) {
     const bool skip = found_inf && *found_inf != 0.0f;     // nothing was updated anywhere: only the EMA runs
-    const long long cta_lo = static_cast<long long>(blockIdx.x) * kDpChunk;
-    const int owner = static_cast<int>(cta_lo / shard_elems);
+    // Consecutive CTAs take chunks of DIFFERENT owners (chunk j of owner 0, chunk j of owner 1, ...), so at any
+    // moment this rank pulls from every peer at once — every link of the switch carries its share and the local
+    // slice's HBM-bound chunks overlap the NVLink-bound ones.  (In plain chunk order all ranks would pull from
+    // the same owner at the same time and share that one GPU's egress.)
+    // The grid is world x (chunks per slice); the few CTAs past the end of the short last slice only take a ticket.
+    const int world = pr.world;
+    const long long per = shard_elems / kDpChunk;                        // chunks per slice
+    const int owner = static_cast<int>(blockIdx.x % world);
+    const long long cta_lo = (static_cast<long long>(owner) * per + blockIdx.x / world) * kDpChunk;
     const bool remote = owner != pr.rank && !skip;
     const long long rem = n_total - cta_lo;
-    const int nvec = static_cast<int>((rem < kDpChunk ? rem : kDpChunk) >> 2);
-    if (remote || teacher) {
+    const int nvec = rem > 0 ? static_cast<int>((rem < kDpChunk ? rem : kDpChunk) >> 2) : 0;
+    if (nvec > 0 && (remote || teacher)) {
         const uint4* src = reinterpret_cast<const uint4*>(remote ? pr.params[owner] : pr.params[pr.rank]) + (cta_lo >> 2);
         uint4* dst = reinterpret_cast<uint4*>(pr.params[pr.rank]) + (cta_lo >> 2);
         uint4* t4 = teacher ? reinterpret_cast<uint4*>(teacher) + (cta_lo >> 2) : nullptr;
@@ -330,7 +331,40 @@ dp_counts_kernel(udape_dp_peers pr, const int32_t* __restrict__ counts, int n, i
     if (i == 0) *epoch_dev = e;
 }
 
+// CUDA loads kernels lazily, and loading one may wait for the kernels that are running.  A rank's barrier
+// kernel can be spinning on a peer while the host goes on to launch the next kernel of the chain: if that
+// launch had to load its code first, the host would stall until the spin ends — and with several ranks driven
+// by ONE host thread (PeerGroup.virtual) the peer's kernels are launched by that same thread, so the spin would
+// only end by its timeout.  Every entry point therefore makes sure, once per device, that all kernels of this
+// file are resident before anything is launched.
+template <typename K> static cudaError_t preload(K kernel) {
+    cudaFuncAttributes a;
+    return cudaFuncGetAttributes(&a, kernel);
+}
+static int ensure_loaded() {
+    static bool done[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return UDAPE_OK;
+    if (done[dev]) return UDAPE_OK;
+    cudaError_t e = cudaSuccess;
+    auto acc = [&e](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    acc(preload(dp_barrier_kernel));
+    acc(preload(dp_wait_kernel));
+    acc(preload(dp_reduce_scatter_kernel<2>));
+    acc(preload(dp_reduce_scatter_kernel<4>));
+    acc(preload(dp_reduce_scatter_kernel<8>));
+    acc(preload(dp_shard_step_kernel<0>));
+    acc(preload(dp_shard_step_kernel<1>));
+    acc(preload(dp_shard_step_kernel<2>));
+    acc(preload(dp_gather_ema_kernel));
+    acc(preload(dp_counts_kernel));
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "udape_dp: loading the kernels failed: %s", cudaGetErrorString(e));
+    done[dev] = true;
+    return UDAPE_OK;
+}
+
 static int check_peers(const udape_dp_peers* p, const char* what, bool need_data) {
+    if (int e = ensure_loaded()) return e;
     UDAPE_REQUIRE(p, UDAPE_ERR_NULL, "%s: peers is NULL", what);
     UDAPE_REQUIRE(p->world >= 1 && p->world <= UDAPE_DP_MAX_RANKS && p->rank >= 0 && p->rank < p->world, UDAPE_ERR_ARG,
                   "%s: bad rank %d / world %d (world <= %d)", what, (int)p->rank, (int)p->world, UDAPE_DP_MAX_RANKS);
@@ -435,7 +469,7 @@ extern "C" int udape_dp_gather_ema(const udape_dp_peers* peers, int64_t n_total,
     UDAPE_REQUIRE(n_total > 0 && (n_total & 3) == 0, UDAPE_ERR_SHAPE, "udape_dp_gather_ema: n_total must be a positive multiple of 4");
     UDAPE_REQUIRE(!teacher || aligned16(teacher), UDAPE_ERR_ALIGN, "udape_dp_gather_ema: teacher must be 16-byte aligned");
     const int64_t shard = udape_dp_shard_elems(n_total, peers->world);
-    const unsigned grid = static_cast<unsigned>((n_total + kDpChunk - 1) / kDpChunk);
+    const unsigned grid = static_cast<unsigned>(shard / kDpChunk * peers->world);
     dp_gather_ema_kernel<<<grid, kDpThreads, 0, as_stream(stream)>>>(*peers, n_total, shard, teacher, ema_a, ema_b, found_inf, epoch_dev, ticket);
     return check_launch("udape_dp_gather_ema");
 }

@@ -277,40 +277,61 @@ class ShardedStudentStep(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        lib, dev = _lib.load(), self.peers.dev
+        ev = iter(_events) if _events is not None else None
+        self.step_begin(ev)
+        self.step_finish(None, ev)
+        return loss
+
+    def _launch_args(self):
+        dev = self.peers.dev
         grad_scale = getattr(self, "grad_scale", None)
         if grad_scale is not None and (grad_scale.device != dev or grad_scale.dtype != torch.float32):
             raise RuntimeError("grad_scale must be a float32 tensor on the parameters' device")
-        h = self._hyper()
-        algo = _lib.OPT_ADAM if self.algo == "adam" else _lib.OPT_SGD
-        c, epoch, t_ns = ctypes.byref(self._c), self._word(0), self.timeout_ns
-        ev = iter(_events) if _events is not None else None
+        return _lib.load(), dev, grad_scale, ctypes.byref(self._c), self._word(0), self.timeout_ns
 
-        def mark():
-            if ev is not None:
-                next(ev).record(torch.cuda.current_stream(dev))
+    @staticmethod
+    def _mark(ev, dev):
+        if ev is not None:
+            next(ev).record(torch.cuda.current_stream(dev))
 
+    @torch.no_grad()
+    def step_begin(self, _ev=None):
+        """First half of ``step()``: the READY barrier and the gradient reduce-scatter.  A caller that has other
+        work to enqueue (e.g. the PCK launch whose counts ``step_finish`` exchanges) does it between the halves."""
+        lib, dev, _, c, epoch, t_ns = self._launch_args()
         with _lib.on_device(dev):
             st = _lib.stream_ptr(dev)
-            mark()
+            self._mark(_ev, dev)
             _lib.check(lib.udape_dp_barrier(c, READY, epoch, t_ns, st), "udape_dp_barrier")
-            mark()
+            self._mark(_ev, dev)
             _lib.check(lib.udape_dp_reduce_scatter(c, self.n_total, self.reduced.data_ptr(), epoch, self._word(2), st),
                        "udape_dp_reduce_scatter")
-            mark()
+            self._mark(_ev, dev)
+
+    @torch.no_grad()
+    def step_finish(self, counts: torch.Tensor | None = None, _ev=None):
+        """Second half: [the PCK-count exchange of ``counts`` (in place), on this same stream so that every rank
+        meets its peers in ONE order and no two waiting kernels of a rank can ever wait for each other,] the
+        non-finite verdict, the update of this rank's slice, the parameter all-gather + EMA."""
+        lib, dev, grad_scale, c, epoch, t_ns = self._launch_args()
+        h = self._hyper()
+        algo = _lib.OPT_ADAM if self.algo == "adam" else _lib.OPT_SGD
+        if counts is not None:
+            self.allreduce_counts(counts, out=counts)
+        with _lib.on_device(dev):
+            st = _lib.stream_ptr(dev)
             _lib.check(lib.udape_dp_wait(c, REDUCED, epoch, self.found_inf.data_ptr(), t_ns, st), "udape_dp_wait")
-            mark()
+            self._mark(_ev, dev)
             _lib.check(lib.udape_dp_shard_step(c, self.n_total, algo, ctypes.byref(h), _lib.ptr(self._lr_dev),
                                                _lib.ptr(grad_scale), self.found_inf.data_ptr(), self._step_dev.data_ptr(),
                                                self.reduced.data_ptr(), _lib.ptr(self.state1), _lib.ptr(self.state2), epoch,
                                                self._word(4), st), "udape_dp_shard_step")
-            mark()
+            self._mark(_ev, dev)
             _lib.check(lib.udape_dp_wait(c, PARAMS, epoch, None, t_ns, st), "udape_dp_wait")
-            mark()
+            self._mark(_ev, dev)
             _lib.check(lib.udape_dp_gather_ema(c, self.n_total, _lib.ptr(self.flat_teacher), h.ema_a, h.ema_b,
                                                self.found_inf.data_ptr(), epoch, self._word(5), st), "udape_dp_gather_ema")
-            mark()
-        return loss
+            self._mark(_ev, dev)
 
     kernels_per_step = 6
 

@@ -82,12 +82,19 @@ class ReplicatedTail:
     def found_inf(self):
         return self.opt._found_inf
 
-    def run(self):
+    def begin(self):
         if self.world > 1:
             self.bucket.allreduce_(average=True, group=self.group)      # DataParallel's reduce-add, as a mean
+
+    def finish(self, counts=None):
+        # (the PCK counts of this tail travel by ncclAllReduce from the PCK chain: HotPathStep.counts_hook)
         self.opt.grad_scale, self.opt.found_inf = self.scale, self.opt.check_grads()
         self.opt.step()
         self.ema._fused_pending = False   # tea_optimizer.step() is not called separately by the assembled step
+
+    def run(self):
+        self.begin()
+        self.finish()
 
     def bytes(self) -> dict:
         p4 = 4 * self.n_params
@@ -118,9 +125,18 @@ class PeerTail:
     def found_inf(self):
         return self.opt.found_inf
 
-    def run(self):
+    exchanges_counts = True   # finish(counts) sums the PCK counts over the ranks on the tail's own stream
+
+    def begin(self):
         self.opt.grad_scale = self.scale
-        self.opt.step()
+        self.opt.step_begin()
+
+    def finish(self, counts=None):
+        self.opt.step_finish(counts if self.world > 1 else None)
+
+    def run(self):
+        self.begin()
+        self.finish()
 
     def bytes(self) -> dict:
         w, p4, s4 = self.world, 4 * self.n_params, 4 * self.opt.shard_elems
@@ -285,8 +301,11 @@ class HotPathStep:
             with torch.cuda.stream(s_ema):
                 # :438 — independent of every other chain of the hot path (in training it follows
                 # scaler.step(stu_optimizer); the student parameters are an input of this step)
-                self._tail_or_ema()
-                self._mark("ema done")
+                if self.tail is not None:
+                    self.tail.begin()      # :436 — the gradient exchange starts with the step
+                else:
+                    self.ema.step()
+                    self._mark("ema done")
         # teacher forward; student forward + inverse plan + backward
         self.rewarp_kernels = (1 if inp.theta_tea is not None else 0) + (3 if inp.theta_stu is not None else 0)
         # the student's grids are built under autocast (:414): every stage samples on a half grid
@@ -363,6 +382,10 @@ class HotPathStep:
                 self._mark("pck done")
                 if self.counts_hook is not None:
                     self.counts_hook(counts)
+                pck_done = None
+                if ema_side and getattr(self.tail, "exchanges_counts", False):
+                    pck_done = torch.cuda.Event()
+                    pck_done.record(s_stu)
         t_s2t = t_t2s = None
         if s_adain is not cur:
             s_adain.wait_stream(cur)
@@ -376,6 +399,14 @@ class HotPathStep:
                 self._mark("adain t2s done")
                 if self.alpha_feed is not None:
                     self.alpha_feed()
+        if ema_side and self.tail is not None:
+            with torch.cuda.stream(s_ema):
+                # :437-438 — update + EMA; a peer tail first sums the PCK counts over the ranks (same stream: every
+                # rank meets its peers in one order)
+                if pck_done is not None:
+                    s_ema.wait_event(pck_done)
+                self.tail.finish(counts if pck_done is not None else None)
+                self._mark("ema done")
         if s_adain is not cur:
             cur.wait_stream(s_adain)
         if self.parallel:
@@ -398,6 +429,8 @@ class HotPathStep:
 
     def _tail_or_ema(self):
         if self.tail is not None:
+            if getattr(self.tail, "exchanges_counts", False) and self.tail.world > 1:
+                raise RuntimeError("a peer tail needs parallel=True, ema_parallel=True (its count exchange joins the PCK chain)")
             self.tail.run()      # :436-438 — gradient exchange, student update, teacher EMA
         else:
             self.ema.step()      # :438 alone
