@@ -259,8 +259,8 @@ def run_reference_arm(args, cfg, rank):
 
 
 def workload_config(cfg, n_gpus, graph=True, fused=True, tail="peer", sets=2):
-    tails = {"peer": "gradient reduce-scatter + non-finite check -> Adam on the rank's 1/N slice -> parameter all-gather + "
-                     "EMA, three peer-memory kernels over NVLink (no NCCL in the step)",
+    tails = {"peer": "gradient reduce-scatter + non-finite check + Adam on the rank's 1/N slice (one kernel) -> parameter "
+                     "all-gather + EMA (one kernel), peer loads over NVLink, no NCCL in the step",
              "nccl": "NCCL all-reduce of the flat fp32 gradient bucket -> grad check -> unscale + Adam + EMA (one launch)",
              "replicated": "grad check -> unscale + Adam + EMA in one multi-tensor launch",
              "ema": "bare EMA (round-1 step definition: no gradient exchange, no optimizer)",
@@ -599,14 +599,14 @@ def probe_tail(main, world, dev, reps):
                              "timed": f"CUDA events around {reps} back-to-back replays of a one-kernel CUDA graph, right after the "
                                       "timed loop (parameters >> L2)"},
                 "kernels_ms": kms, "kernels_per_step": kernels_per_step}
-    # peer tail: events between the six launches
+    # peer tail: events between its four launches
     opt = tail.opt
-    names = ["barrier", "reduce_scatter", "wait_reduced", "shard_step", "wait_params", "gather_ema"]
+    names = ["barrier", "reduce_step", "wait_reduced", "gather_ema"]
     acc = {n: [] for n in names}
     if world > 1:
         dist.barrier()
     for _ in range(reps):
-        evs = [mk() for _ in range(7)]
+        evs = [mk() for _ in range(5)]
         opt.grad_scale = tail.scale
         opt.step(_events=evs)
         torch.cuda.synchronize()
@@ -623,14 +623,18 @@ def probe_tail(main, world, dev, reps):
     w, s4 = world, 4 * opt.shard_elems
     pulled = (w - 1) * s4
     nv = {"bytes_in_per_kernel": pulled, "peak_GBps_per_direction": NVLINK_PEER_GBS,
-          "peak_source": "B200_PROFILING.md measured peer copy (900 nominal)",
-          "reduce_scatter_GBps": pulled / (kms["reduce_scatter"] * 1e-3) / 1e9 if pulled else None,
+          "peak_source": "B200_PROFILING.md measured peer copy, one direction (900 nominal); here every GPU pulls and "
+                         "serves at once, so read requests share each link with the data flowing the other way",
+          "reduce_step_GBps": pulled / (kms["reduce_step"] * 1e-3) / 1e9 if pulled else None,
           "gather_ema_GBps": pulled / (kms["gather_ema"] * 1e-3) / 1e9 if pulled else None}
     if pulled:
-        nv["reduce_scatter_frac"] = nv["reduce_scatter_GBps"] / NVLINK_PEER_GBS
+        nv["reduce_step_frac"] = nv["reduce_step_GBps"] / NVLINK_PEER_GBS
         nv["gather_ema_frac"] = nv["gather_ema_GBps"] / NVLINK_PEER_GBS
-    return {"dominant": {"kernel": "dp_gather_ema_kernel (udape_dp_gather_ema: parameter all-gather by peer loads + teacher EMA)",
-                         "bytes": bts["gather_ema"], "ms": kms["gather_ema"], "traffic_key": "dp_gather_ema",
+    dom = "gather_ema" if kms["gather_ema"] >= kms["reduce_step"] else "reduce_step"
+    kernel = {"gather_ema": "dp_gather_ema_kernel (udape_dp_gather_ema: parameter all-gather by peer loads + teacher EMA)",
+              "reduce_step": "dp_reduce_step_kernel (udape_dp_reduce_step: gradient reduce-scatter by peer loads + non-finite "
+                             "check + unscale + Adam on the rank's slice)"}[dom]
+    return {"dominant": {"kernel": kernel, "bytes": bts[dom], "ms": kms[dom], "traffic_key": "dp_" + dom,
                          "timed": f"CUDA events between the tail's launches, {reps} eager tails right after the timed loop, max over ranks"},
             "kernels_ms": kms, "nvlink": nv if world > 1 else None, "kernels_per_step": kernels_per_step}
 

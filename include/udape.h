@@ -314,30 +314,31 @@ UDAPE_API int udape_student_step(const udape_opt_chunk* chunks_dev, int64_t n_ch
 /* ---- e: the data-parallel tail of the step over peer memory (NVLink / NVSwitch) ----------------------
  * One process per GPU replaces nn.DataParallel (train_human.py:145-148: replicate, scatter, reduce-add of
  * the gradients onto GPU 0) and the  scaler.step(stu_optimizer); tea_optimizer.step()  tail (:436-438).
- * Every rank keeps its flat float32 gradient bucket, its flat student parameters and a signal pad of
+ * Every rank keeps its flat float32 gradient bucket, its flat student parameters, a shadow of its slice and a signal pad of
  * UDAPE_DP_PAD_BYTES (zeroed once) in memory the other ranks have mapped (udape_peer_*, CUDA IPC; any other
  * mapping of peer memory works as well — the kernels only see pointers).  udape_dp_peers holds, for every
- * rank, those three addresses AS MAPPED IN THE CALLING PROCESS (entry `rank` is the local memory).
+ * rank, those four addresses AS MAPPED IN THE CALLING PROCESS (entry `rank` is the local memory).
  * n_total = elements of the flat buffers (multiple of 4); rank r owns the slice
  *   [r*S, min((r+1)*S, n_total)),  S = udape_dp_shard_elems(n_total, world)  (a multiple of 4096).
  * One step on one stream of every rank, all ranks taking the same sequence (epoch_dev: a uint32 on this
  * device, zero at start, advanced by udape_dp_gather_ema; flags in the pads are these step numbers):
  *   udape_dp_barrier(READY)         every rank's bucket is complete (backward done) before anyone reads it
- *   udape_dp_reduce_scatter         reduced[i] = (g_0[i] + g_1[i] + ... in rank order) * (1/world) for the own
- *                                   slice, by 128-bit loads from every rank's bucket; non-finite check of the
- *                                   result; posts REDUCED + the flag to every rank.  reduced: local, S floats.
- *                                   ws: 2 zeroed uint32 (left zero).
- *   udape_dp_wait(REDUCED, &found)  every slice is reduced (and nobody reads this rank's bucket any more);
+ *   udape_dp_reduce_step            g[i] = (g_0[i] + g_1[i] + ... in rank order) * (1/world) for the own slice, by
+ *                                   128-bit loads from every rank's bucket; non-finite test of g; and, in the same
+ *                                   registers, udape_student_step's arithmetic (unscale, Adam | SGD, same scalars)
+ *                                   SPECULATIVELY: new parameters -> this rank's `shadow` slice (S floats, peer-
+ *                                   mapped), new state -> the other half of state1 / state2 ([2][S] floats each:
+ *                                   exp_avg | momentum buffer / exp_avg_sq shards, half (*step_dev & 1) is current).
+ *                                   Posts REDUCED + the non-finite flag to every rank.  ws: 2 zeroed uint32 (left zero).
+ *                                   (SGD: buf = grad while *step_dev == 0.)
+ *   udape_dp_wait(REDUCED, &found)  every slice is done (and nobody reads this rank's bucket any more);
  *                                   *found_inf = 1.0f if any rank's slice has a non-finite value else 0.0f
- *   udape_dp_shard_step             udape_student_step's arithmetic (unscale, Adam | SGD, same scalars) on the
- *                                   own slice of params with state1 / state2 = this rank's S-element shards of
- *                                   exp_avg | momentum buffer / exp_avg_sq; skipped if *found_inf != 0; advances
- *                                   *step_dev when applied; posts PARAMS.  (SGD: buf = grad on update number 1.)
- *   udape_dp_wait(PARAMS, NULL)     every slice is updated
- *   udape_dp_gather_ema             params_local[i] = params_owner(i)[i] by 128-bit peer loads for the other ranks'
- *                                   slices, and teacher[i] = fl(fl(teacher[i]*ema_a) + fl(params[i]*ema_b)) in the
- *                                   same pass (teacher NULL: gather only; *found_inf != 0: EMA only — nothing
- *                                   changed anywhere).  Advances *epoch_dev.
+ *   udape_dp_gather_ema             the commit: params_local[i] = shadow_owner(i)[i - owner's lo] by 128-bit peer
+ *                                   loads (own slice: local), and teacher[i] = fl(fl(teacher[i]*ema_a) +
+ *                                   fl(params[i]*ema_b)) in the same pass (teacher NULL: gather only).  *found_inf != 0:
+ *                                   nothing is committed, the EMA runs on the unchanged parameters, the state halves do
+ *                                   not flip — scaler.step() skipping the update.  Advances *step_dev when committed,
+ *                                   and *epoch_dev.
  * Results do not depend on the world size when it is a power of two (exact 1/world) and are bit-identical on
  * every rank; the replicated form is udape_student_step on the same averaged gradient.
  * udape_dp_allreduce_counts: out[i] = sum over ranks (rank order) of counts[i], i < n <= 64 int32 — the PCK
@@ -353,6 +354,7 @@ typedef struct udape_dp_peers {
     int32_t rank, world;
     float* grads[UDAPE_DP_MAX_RANKS];
     float* params[UDAPE_DP_MAX_RANKS];
+    float* shadow[UDAPE_DP_MAX_RANKS]; /* S floats: the rank's slice after the speculative update */
     uint32_t* pads[UDAPE_DP_MAX_RANKS];
 } udape_dp_peers;
 
@@ -361,14 +363,12 @@ UDAPE_API int udape_dp_barrier(const udape_dp_peers* peers, int phase, const uin
                      void* stream);
 UDAPE_API int udape_dp_wait(const udape_dp_peers* peers, int phase, const uint32_t* epoch_dev, float* found_inf,
                   uint64_t timeout_ns, void* stream);
-UDAPE_API int udape_dp_reduce_scatter(const udape_dp_peers* peers, int64_t n_total, float* reduced,
-                            const uint32_t* epoch_dev, uint32_t* ws, void* stream);
-UDAPE_API int udape_dp_shard_step(const udape_dp_peers* peers, int64_t n_total, int algo, const udape_opt_hyper* hyper,
-                        const float* lr_dev, const float* grad_scale, const float* found_inf, int32_t* step_dev,
-                        const float* reduced, float* state1, float* state2, const uint32_t* epoch_dev,
-                        uint32_t* ticket, void* stream);
+UDAPE_API int udape_dp_reduce_step(const udape_dp_peers* peers, int64_t n_total, int algo, const udape_opt_hyper* hyper,
+                         const float* lr_dev, const float* grad_scale, const int32_t* step_dev, float* state1,
+                         float* state2, const uint32_t* epoch_dev, uint32_t* ws, void* stream);
 UDAPE_API int udape_dp_gather_ema(const udape_dp_peers* peers, int64_t n_total, float* teacher, float ema_a, float ema_b,
-                        const float* found_inf, uint32_t* epoch_dev, uint32_t* ticket, void* stream);
+                        const float* found_inf, int32_t* step_dev, uint32_t* epoch_dev, uint32_t* ticket,
+                        void* stream);
 UDAPE_API int udape_dp_allreduce_counts(const udape_dp_peers* peers, const int32_t* counts, int n, int32_t* out,
                               uint32_t* epoch_dev, uint64_t timeout_ns, void* stream);
 /* Peer-mappable device memory: cudaMalloc'ed (zeroed) arena, 64-byte CUDA IPC handle to hand to the other

@@ -104,14 +104,25 @@ def test_sharded_step_equals_the_replicated_step(dev, world, algo):
         for r in range(world):
             assert torch.equal(_cat(stu[r].parameters()), _cat(ref_s.parameters())), f"student, rank {r}, step {it}"
             assert torch.equal(_cat(tea[r].parameters()), _cat(ref_t.parameters())), f"teacher, rank {r}, step {it}"
-        # the reduced slice every rank kept is the rank-ordered mean of its range
-        flat_mean = torch.zeros(n_total, device=dev)
-        for off, m in zip(opts[0].offsets, mean):
-            flat_mean[off:off + m.numel()] = m.reshape(-1)
+        # the gradient buckets are inputs: the step leaves them as backward wrote them
         for r in range(world):
-            lo, hi = opts[r].shard_bounds()
-            assert torch.equal(opts[r].reduced[:hi - lo], flat_mean[lo:hi]) or it == 1
+            for p, gr in zip(stu[r].parameters(), per_rank[r]):
+                assert torch.equal(p.grad, gr.to(dev)) or it == 1
     assert all(o.applied_steps() == 2 for o in opts) and ref_opt.applied_steps() == 2
+    # the sharded optimizer state, put back together, is the replicated optimizer's state
+    key1 = "exp_avg" if algo == "adam" else "momentum_buffer"
+    flat1 = torch.zeros(n_total, device=dev)
+    flat2 = torch.zeros(n_total, device=dev)
+    for off, p in zip(opts[0].offsets, ref_s.parameters()):
+        flat1[off:off + p.numel()] = ref_opt.state[p][key1].reshape(-1)
+        if algo == "adam":
+            flat2[off:off + p.numel()] = ref_opt.state[p]["exp_avg_sq"].reshape(-1)
+    for r in range(world):
+        lo, hi = opts[r].shard_bounds()
+        s1, s2 = opts[r].state_shards()
+        assert torch.equal(s1[:hi - lo], flat1[lo:hi]), f"state1 shard of rank {r}"
+        if algo == "adam":
+            assert torch.equal(s2[:hi - lo], flat2[lo:hi]), f"state2 shard of rank {r}"
     for grp in groups:
         grp.close()
 

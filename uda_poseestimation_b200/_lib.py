@@ -52,7 +52,7 @@ class OptHyper(ctypes.Structure):
 
 class DpPeers(ctypes.Structure):
     _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("grads", c_void_p * 8), ("params", c_void_p * 8),
-                ("pads", c_void_p * 8)]
+                ("shadow", c_void_p * 8), ("pads", c_void_p * 8)]
 
 
 OPT_ADAM, OPT_SGD = 0, 1
@@ -107,11 +107,10 @@ PROTOTYPES = {
     "udape_dp_shard_elems": (c_int64, [c_int64, c_int]),
     "udape_dp_barrier": (c_int, [POINTER(DpPeers), c_int, c_void_p, ctypes.c_uint64, c_void_p]),
     "udape_dp_wait": (c_int, [POINTER(DpPeers), c_int, c_void_p, c_void_p, ctypes.c_uint64, c_void_p]),
-    "udape_dp_reduce_scatter": (c_int, [POINTER(DpPeers), c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "udape_dp_shard_step": (c_int, [POINTER(DpPeers), c_int64, c_int, POINTER(OptHyper), c_void_p, c_void_p, c_void_p,
-                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "udape_dp_reduce_step": (c_int, [POINTER(DpPeers), c_int64, c_int, POINTER(OptHyper), c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "udape_dp_gather_ema": (c_int, [POINTER(DpPeers), c_int64, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p,
-                                    c_void_p]),
+                                    c_void_p, c_void_p]),
     "udape_dp_allreduce_counts": (c_int, [POINTER(DpPeers), c_void_p, c_int, c_void_p, c_void_p, ctypes.c_uint64,
                                           c_void_p]),
     "udape_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),

@@ -7,24 +7,23 @@
 //     grads[P]   its flat gradient bucket (what backward wrote),
 //     params[P]  its flat student parameters,
 //     pad        a small signal pad the other ranks write flags into,
-// and the step is three kernels that READ / WRITE THE OTHER GPUS' MEMORY DIRECTLY (ld/st on mapped peer
+// and the step is two kernels that READ THE OTHER GPUS' MEMORY DIRECTLY (ld/st on mapped peer
 // pointers; NVSwitch gives every pair the full link) instead of an all-reduce followed by a replicated
 // optimizer pass:
-//   K1 reduce_scatter : rank r sums slice r of every rank's gradient bucket in rank order (deterministic,
-//                       identical on every world size that is a power of two after the exact 1/W scaling),
-//                       checks the result for non-finite values (GradScaler's found_inf — free here,
-//                       the data is in registers) and keeps the averaged slice in place;
-//   K2 shard_step     : unscale + Adam | SGD on slice r only — optimizer state is sharded, each rank streams
-//                       1/W of exp_avg / exp_avg_sq (ZeRO-1 layout; results are bit-identical to the
-//                       replicated update because the update is elementwise);
-//   K3 gather_ema     : all-gather of the updated slices by peer loads fused with the teacher EMA
-//                       (utils.py:21-25): the pulled student value is written to the local replica and folded
-//                       into the teacher in the same pass.
-// Bytes over NVLink per rank and step: (W-1)/W * P * 4 in K1 and again in K3 — what a ring all-reduce
-// moves — but HBM traffic drops from ~13 P*4 (NCCL in + out, grad check, replicated 9-pass step) to
-// ~(4 + 8/W) P*4.  Cross-rank ordering uses monotonic step numbers in the signal pads (release / acquire
-// at system scope); waiting is done by single-CTA kernels so that a rank that is late never parks a
-// grid of spinning CTAs on the other GPUs, and every wait is bounded (timeout -> error word, no hang).
+//   K1 reduce_step : rank r sums slice r of every rank's gradient bucket in rank order (deterministic, and the same
+//                    on every power-of-two world size after the exact 1/W scaling), tests the result for non-finite
+//                    values (GradScaler's found_inf — free here, the data is in registers) and applies unscale +
+//                    Adam | SGD to slice r in the same registers, speculatively, into a shadow slice; optimizer
+//                    state is sharded (ZeRO-1 layout: each rank streams 1/W of exp_avg / exp_avg_sq; bit-identical
+//                    to the replicated update because the update is elementwise);
+//   K2 gather_ema  : once every rank's verdict is in: all-gather of the shadow slices by peer loads = the commit,
+//                    fused with the teacher EMA (utils.py:21-25): the pulled value is written to the local replica
+//                    and folded into the teacher in the same pass.
+// Bytes over NVLink per rank and step: (W-1)/W * P * 4 in K1 and again in K2 — what a ring all-reduce moves —
+// but HBM traffic drops from ~13 P*4 (NCCL in + out, grad check, replicated 9-pass step) to ~(4 + 8/W) P*4 and the
+// step has two cross-rank waits.  Cross-rank ordering uses monotonic step numbers in the signal pads (release /
+// acquire at system scope); waiting is done by single-CTA kernels so that a rank that is late never parks a grid
+// of spinning CTAs on the other GPUs, and every wait is bounded (timeout -> error word, no hang).
 #include <cstring>
 
 #include "optim.cuh"
@@ -33,7 +32,7 @@ namespace udape {
 
 constexpr int kDpThreads = 256;
 constexpr int kDpChunk = 4096;    // elements per CTA in K2 / K3 (256 threads x 4 x 128-bit)
-constexpr int kRsChunk = 8192;    // elements per CTA in K1 (16 peer loads in flight per thread)
+constexpr int kRsChunk = 8192;    // elements per CTA in K1
 
 // ---- system-scope access ---------------------------------------------------------------------
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -125,21 +124,53 @@ dp_wait_kernel(udape_dp_peers pr, int phase, const uint32_t* __restrict__ epoch_
     if (found_inf && threadIdx.x == 0) *found_inf = any ? 1.0f : 0.0f;
 }
 
-// ---- K1: reduce-scatter of the gradient buckets, averaged, with the non-finite check ------------------
-// Rank r owns elements [lo, lo + n).  UN vectors x world ranks = 16 x 128-bit loads in flight per thread.
-template <int WMAX>
-__global__ void __launch_bounds__(kDpThreads)
-dp_reduce_scatter_kernel(udape_dp_peers pr, long long lo, long long n, float inv_world, float* __restrict__ reduced,
-                         const uint32_t* __restrict__ epoch_dev, uint32_t* __restrict__ ws) {
-    constexpr int UN = 16 / WMAX;
+// ---- K1: reduce-scatter of the gradient buckets fused with the optimizer --------------------------------
+// Rank r owns elements [lo, lo + n).  Per element: g = ((g_0 + g_1) + ...) * (1/W) summed in rank order from every
+// rank's bucket (UN vectors x world ranks = 8 x 128-bit peer loads in flight per thread), non-finite test of g
+// (GradScaler's found_inf — whether ANY rank's slice trips it is only known after the cross-rank wait that
+// follows), and — without waiting for that verdict — the update itself, SPECULATIVELY: the new parameters go
+// to this rank's `shadow` slice and the new optimizer state to the other half of the double-buffered state
+// shards.  The gather kernel commits (copies shadow -> parameters everywhere, flips the state halves by
+// advancing *step_dev) only if no rank saw a non-finite value; otherwise everything written here is simply
+// never looked at again — exactly `scaler.step()` skipping the update.  Against reduce-scatter -> wait ->
+// separate optimizer pass this saves the write + re-read of the reduced slice, one pass over p / m / v
+// (742 MB per rank at N=2) and one cross-rank round trip.
+// ALGO 0: Adam, 1: SGD, 2: SGD + Nesterov.  m / v: [2][S] shards; half (*step_dev & 1) is current.
+template <int WMAX, int ALGO>
+__global__ void __launch_bounds__(kDpThreads, 2)
+dp_reduce_step_kernel(udape_dp_peers pr, long long lo, long long n, long long shard_elems, float inv_world,
+                      udape_opt_hyper h, const float* __restrict__ lr_dev, const float* __restrict__ grad_scale,
+                      const int32_t* __restrict__ step_dev, float* __restrict__ m, float* __restrict__ v,
+                      const uint32_t* __restrict__ epoch_dev, uint32_t* __restrict__ ws) {
+    // vectors per thread and pass: 8 gradient loads (peer) + 3 * UN local loads (p, m, v) in flight per thread,
+    // at <= 128 registers so that two CTAs share an SM (loads of one overlap the arithmetic / stores of the other)
+    constexpr int UN = 8 / WMAX;
+    __shared__ OptScalars sc;
+    __shared__ int cur_s;
+    if (threadIdx.x == 0) {
+        sc = make_opt_scalars<ALGO>(h, lr_dev, grad_scale, nullptr, step_dev);
+        cur_s = *step_dev;
+    }
+    __syncthreads();
+    const OptScalars s = sc;
+    const bool first = cur_s == 0;        // the flat bucket gives every parameter a gradient from the first step on
+    const long long half_in = static_cast<long long>(cur_s & 1) * shard_elems;
+    const long long half_out = static_cast<long long>((cur_s & 1) ^ 1) * shard_elems;
+    const bool has_m = m != nullptr;
     const int world = pr.world;
     const long long cta_lo = static_cast<long long>(blockIdx.x) * kRsChunk;
     const long long rem = n - cta_lo;
-    const int nvec = static_cast<int>((rem < kRsChunk ? rem : kRsChunk) >> 2);
+    const int nvec = rem > 0 ? static_cast<int>((rem < kRsChunk ? rem : kRsChunk) >> 2) : 0;
     const long long vbase = (lo + cta_lo) >> 2;
+    const uint4* p4 = reinterpret_cast<const uint4*>(pr.params[pr.rank]) + vbase;
+    uint4* out4 = reinterpret_cast<uint4*>(pr.shadow[pr.rank]) + (cta_lo >> 2);
+    const uint4* mi = has_m ? reinterpret_cast<const uint4*>(m + half_in) + (cta_lo >> 2) : nullptr;
+    uint4* mo = has_m ? reinterpret_cast<uint4*>(m + half_out) + (cta_lo >> 2) : nullptr;
+    const uint4* vi = ALGO == 0 ? reinterpret_cast<const uint4*>(v + half_in) + (cta_lo >> 2) : nullptr;
+    uint4* vo = ALGO == 0 ? reinterpret_cast<uint4*>(v + half_out) + (cta_lo >> 2) : nullptr;
     uint32_t bad = 0;
     for (int base = 0; base < nvec; base += kDpThreads * UN) {
-        uint4 x[WMAX][UN];
+        uint4 x[WMAX][UN], pv[UN], mv[UN], vv[UN];
 #pragma unroll
         for (int q = 0; q < WMAX; ++q) {
             if (q < world) {
@@ -155,29 +186,50 @@ dp_reduce_scatter_kernel(udape_dp_peers pr, long long lo, long long n, float inv
         for (int u = 0; u < UN; ++u) {
             const int i = base + u * kDpThreads + threadIdx.x;
             if (i < nvec) {
-                float acc[4], t[4];
-                unpack16<float>(x[0][u], acc);
+                pv[u] = ldg_cached(p4 + i);
+                if (has_m) mv[u] = ldg_stream(mi + i);
+                if (ALGO == 0) vv[u] = ldg_stream(vi + i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int i = base + u * kDpThreads + threadIdx.x;
+            if (i < nvec) {
+                float g[4], t[4], fp[4], fm[4], fv[4];
+                unpack16<float>(x[0][u], g);
 #pragma unroll
                 for (int q = 1; q < WMAX; ++q) {       // rank order: ((g0 + g1) + g2) + ...
                     if (q < world) {
                         unpack16<float>(x[q][u], t);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) acc[k] = __fadd_rn(acc[k], t[k]);
+                        for (int k = 0; k < 4; ++k) g[k] = __fadd_rn(g[k], t[k]);
                     }
                 }
+                unpack16<float>(pv[u], fp);
+                if (has_m) unpack16<float>(mv[u], fm);
+                if (ALGO == 0) unpack16<float>(vv[u], fv);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    acc[k] = __fmul_rn(acc[k], inv_world);
-                    bad |= (__float_as_uint(acc[k]) & 0x7f800000u) == 0x7f800000u;
+                    g[k] = __fmul_rn(g[k], inv_world);
+                    bad |= (__float_as_uint(g[k]) & 0x7f800000u) == 0x7f800000u;
+                    if (ALGO == 0) adam_elem(fp[k], g[k], fm[k], fv[k], s);
+                    else sgd_elem<ALGO == 2>(fp[k], g[k], fm[k], s, has_m, first);
                 }
-                stg_plain(reinterpret_cast<uint4*>(reduced) + (cta_lo >> 2) + i, pack16<float>(acc));
+                stg_plain(out4 + i, pack16<float>(fp));
+                if (has_m) stg_stream(mo + i, pack16<float>(fm));
+                if (ALGO == 0) stg_stream(vo + i, pack16<float>(fv));
             }
         }
     }
     const int any = __syncthreads_or(static_cast<int>(bad));
     if (threadIdx.x == 0 && any) atomicOr(ws + 1, 1u);
+    // Every CTA's shadow stores are ordered before its ticket by a device-scope fence (they sit in this GPU's L2,
+    // where peer loads are served from); the last CTA, having observed every ticket, fences at SYSTEM scope
+    // (post_all) before the release store of the flag — fence cumulativity carries the other CTAs' stores along.
+    // (A system-scope fence in every CTA cost ~110 us of a 230 us kernel at N=2.)
     if (last_block_done(ws, gridDim.x)) {
-        // every rank learns (a) that this rank no longer reads its bucket, (b) whether slice r is finite
+        // every rank learns (a) that this rank no longer reads its bucket, (b) that slice r's candidate values
+        // are in place, (c) whether slice r's gradient is finite
         const uint32_t e = *epoch_dev + 1u;
         const uint32_t f = *reinterpret_cast<volatile uint32_t*>(ws + 1);
         if (threadIdx.x < static_cast<unsigned>(world)) st_relaxed_sys(pr.pads[threadIdx.x] + kPadInf + pr.rank, f);
@@ -187,82 +239,16 @@ dp_reduce_scatter_kernel(udape_dp_peers pr, long long lo, long long n, float inv
     }
 }
 
-// ---- K2: the optimizer on this rank's slice -------------------------------------------------------------
-// ALGO 0: Adam, 1: SGD, 2: SGD + Nesterov.  m / v are this rank's state shards (index 0 = element lo).
-template <int ALGO>
-__global__ void __launch_bounds__(kDpThreads)
-dp_shard_step_kernel(udape_dp_peers pr, long long lo, long long n, udape_opt_hyper h, const float* __restrict__ lr_dev,
-                     const float* __restrict__ grad_scale, const float* __restrict__ found_inf,
-                     int32_t* __restrict__ step_dev, const float* __restrict__ reduced, float* __restrict__ m,
-                     float* __restrict__ v, const uint32_t* __restrict__ epoch_dev, uint32_t* __restrict__ ticket) {
-    __shared__ OptScalars sc;
-    __shared__ int first_s;
-    if (threadIdx.x == 0) {
-        sc = make_opt_scalars<ALGO>(h, lr_dev, grad_scale, found_inf, step_dev);
-        first_s = *step_dev == 0;      // the flat bucket gives every parameter a gradient from the first step on
-    }
-    __syncthreads();
-    const OptScalars s = sc;
-    const bool first = first_s != 0;
-    const bool has_m = m != nullptr;
-    if (!s.skip) {
-        const long long cta_lo = static_cast<long long>(blockIdx.x) * kDpChunk;
-        const long long rem = n - cta_lo;
-        const int nvec = static_cast<int>((rem < kDpChunk ? rem : kDpChunk) >> 2);
-        uint4* p4 = reinterpret_cast<uint4*>(pr.params[pr.rank]) + ((lo + cta_lo) >> 2);
-        const uint4* g4 = reinterpret_cast<const uint4*>(reduced) + (cta_lo >> 2);
-        uint4* m4 = has_m ? reinterpret_cast<uint4*>(m) + (cta_lo >> 2) : nullptr;
-        uint4* v4 = ALGO == 0 ? reinterpret_cast<uint4*>(v) + (cta_lo >> 2) : nullptr;
-        uint4 pv[4], gv[4], mv[4], vv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = u * kDpThreads + threadIdx.x;
-            if (i < nvec) {
-                pv[u] = ldg_cached(p4 + i);
-                gv[u] = ldg_cached(g4 + i);
-                if (has_m) mv[u] = ldg_cached(m4 + i);
-                if (ALGO == 0) vv[u] = ldg_cached(v4 + i);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = u * kDpThreads + threadIdx.x;
-            if (i < nvec) {
-                float fp[4], fg[4], fm[4], fv[4];
-                unpack16<float>(pv[u], fp);
-                unpack16<float>(gv[u], fg);
-                if (has_m) unpack16<float>(mv[u], fm);
-                if (ALGO == 0) unpack16<float>(vv[u], fv);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    if (ALGO == 0) adam_elem(fp[e], fg[e], fm[e], fv[e], s);
-                    else sgd_elem<ALGO == 2>(fp[e], fg[e], fm[e], s, has_m, first);
-                }
-                stg_plain(p4 + i, pack16<float>(fp));
-                if (has_m) stg_plain(m4 + i, pack16<float>(fm));
-                if (ALGO == 0) stg_plain(v4 + i, pack16<float>(fv));
-            }
-        }
-    }
-    // The updated slice must be visible to the peers' loads before they are told it is ready.  Every CTA's stores
-    // are ordered before its ticket by a device-scope fence (they are in this GPU's L2, which is where peer loads
-    // are served from); the last CTA, having observed every ticket, fences at SYSTEM scope (post_all) before the
-    // release store of the flag — fence cumulativity carries the other CTAs' stores along.  (A system-scope
-    // fence in every CTA cost ~110 us of the 230 us this kernel took at N=2.)
-    __syncthreads();
-    if (last_block_done(ticket, gridDim.x)) {
-        const uint32_t e = *epoch_dev + 1u;
-        post_all(pr, UDAPE_DP_PARAMS, e);
-        if (threadIdx.x == 0 && !s.skip) *step_dev = *step_dev + 1;
-    }
-}
-
-// ---- K3: all-gather of the updated slices by peer loads, fused with the teacher EMA ----------------------
+// ---- K2: all-gather of the updated slices by peer loads — the commit — fused with the teacher EMA ----------
+// params_local[i] = shadow_owner(i)[i - owner's lo] for EVERY slice (the own one too: K1 left its candidates in
+// the shadow), and teacher[i] = fl(fl(teacher[i]*a) + fl(params[i]*b)) in the same pass.  *found_inf != 0: nothing
+// is committed anywhere, the EMA runs with the unchanged parameters — what scaler.step() + tea_optimizer.step()
+// do.  The last CTA advances *step_dev (which also flips the optimizer-state halves) and *epoch_dev.
 __global__ void __launch_bounds__(kDpThreads)
 dp_gather_ema_kernel(udape_dp_peers pr, long long n_total, long long shard_elems, float* __restrict__ teacher,
-                     float ema_a, float ema_b, const float* __restrict__ found_inf, uint32_t* __restrict__ epoch_dev,
-                     uint32_t* __restrict__ ticket) {
-    const bool skip = found_inf && *found_inf != 0.0f;     // nothing was updated anywhere: only the EMA runs
+                     float ema_a, float ema_b, const float* __restrict__ found_inf, int32_t* __restrict__ step_dev,
+                     uint32_t* __restrict__ epoch_dev, uint32_t* __restrict__ ticket) {
+    const bool skip = found_inf && *found_inf != 0.0f;
     // Consecutive CTAs take chunks of DIFFERENT owners (chunk j of owner 0, chunk j of owner 1, ...), so at any
     // moment this rank pulls from every peer at once — every link of the switch carries its share and the local
     // slice's HBM-bound chunks overlap the NVLink-bound ones.  (In plain chunk order all ranks would pull from
@@ -271,20 +257,21 @@ dp_gather_ema_kernel(udape_dp_peers pr, long long n_total, long long shard_elems
     const int world = pr.world;
     const long long per = shard_elems / kDpChunk;                        // chunks per slice
     const int owner = static_cast<int>(blockIdx.x % world);
-    const long long cta_lo = (static_cast<long long>(owner) * per + blockIdx.x / world) * kDpChunk;
-    const bool remote = owner != pr.rank && !skip;
+    const long long in_slice = (blockIdx.x / world) * static_cast<long long>(kDpChunk);
+    const long long cta_lo = static_cast<long long>(owner) * per * kDpChunk + in_slice;
     const long long rem = n_total - cta_lo;
     const int nvec = rem > 0 ? static_cast<int>((rem < kDpChunk ? rem : kDpChunk) >> 2) : 0;
-    if (nvec > 0 && (remote || teacher)) {
-        const uint4* src = reinterpret_cast<const uint4*>(remote ? pr.params[owner] : pr.params[pr.rank]) + (cta_lo >> 2);
+    if (nvec > 0 && (!skip || teacher)) {
+        const bool remote = owner != pr.rank;
         uint4* dst = reinterpret_cast<uint4*>(pr.params[pr.rank]) + (cta_lo >> 2);
+        const uint4* src = skip ? dst : reinterpret_cast<const uint4*>(pr.shadow[owner]) + (in_slice >> 2);
         uint4* t4 = teacher ? reinterpret_cast<uint4*>(teacher) + (cta_lo >> 2) : nullptr;
         uint4 sv[4], tv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int i = u * kDpThreads + threadIdx.x;
             if (i < nvec) {
-                sv[u] = remote ? ld_peer(src + i) : ldg_cached(src + i);
+                sv[u] = (remote && !skip) ? ld_peer(src + i) : ldg_cached(src + i);
                 if (t4) tv[u] = ldg_cached(t4 + i);
             }
         }
@@ -292,7 +279,7 @@ dp_gather_ema_kernel(udape_dp_peers pr, long long n_total, long long shard_elems
         for (int u = 0; u < 4; ++u) {
             const int i = u * kDpThreads + threadIdx.x;
             if (i < nvec) {
-                if (remote) stg_plain(dst + i, sv[u]);
+                if (!skip) stg_plain(dst + i, sv[u]);
                 if (t4) {
                     float fs[4], ft[4];
                     unpack16<float>(sv[u], fs);
@@ -304,7 +291,10 @@ dp_gather_ema_kernel(udape_dp_peers pr, long long n_total, long long shard_elems
             }
         }
     }
-    if (last_block_done(ticket, gridDim.x) && threadIdx.x == 0) *epoch_dev = *epoch_dev + 1u;   // the step is over on this rank
+    if (last_block_done(ticket, gridDim.x) && threadIdx.x == 0) {
+        if (!skip) *step_dev = *step_dev + 1;      // the update counts — and the state halves flip
+        *epoch_dev = *epoch_dev + 1u;              // the step is over on this rank
+    }
 }
 
 // ---- integer all-reduce of the PCK counts (<= 64 int32) in one single-CTA kernel --------------------------
@@ -350,12 +340,15 @@ static int ensure_loaded() {
     auto acc = [&e](cudaError_t r) { if (e == cudaSuccess) e = r; };
     acc(preload(dp_barrier_kernel));
     acc(preload(dp_wait_kernel));
-    acc(preload(dp_reduce_scatter_kernel<2>));
-    acc(preload(dp_reduce_scatter_kernel<4>));
-    acc(preload(dp_reduce_scatter_kernel<8>));
-    acc(preload(dp_shard_step_kernel<0>));
-    acc(preload(dp_shard_step_kernel<1>));
-    acc(preload(dp_shard_step_kernel<2>));
+    acc(preload(dp_reduce_step_kernel<2, 0>));
+    acc(preload(dp_reduce_step_kernel<4, 0>));
+    acc(preload(dp_reduce_step_kernel<8, 0>));
+    acc(preload(dp_reduce_step_kernel<2, 1>));
+    acc(preload(dp_reduce_step_kernel<4, 1>));
+    acc(preload(dp_reduce_step_kernel<8, 1>));
+    acc(preload(dp_reduce_step_kernel<2, 2>));
+    acc(preload(dp_reduce_step_kernel<4, 2>));
+    acc(preload(dp_reduce_step_kernel<8, 2>));
     acc(preload(dp_gather_ema_kernel));
     acc(preload(dp_counts_kernel));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "udape_dp: loading the kernels failed: %s", cudaGetErrorString(e));
@@ -371,8 +364,9 @@ static int check_peers(const udape_dp_peers* p, const char* what, bool need_data
     for (int q = 0; q < p->world; ++q) {
         UDAPE_REQUIRE(p->pads[q], UDAPE_ERR_NULL, "%s: pad of rank %d is NULL", what, q);
         if (need_data) {
-            UDAPE_REQUIRE(p->grads[q] && p->params[q], UDAPE_ERR_NULL, "%s: grads / params of rank %d is NULL", what, q);
-            UDAPE_REQUIRE(aligned16(p->grads[q]) && aligned16(p->params[q]), UDAPE_ERR_ALIGN, "%s: buffers must be 16-byte aligned", what);
+            UDAPE_REQUIRE(p->grads[q] && p->params[q] && p->shadow[q], UDAPE_ERR_NULL, "%s: grads / params / shadow of rank %d is NULL", what, q);
+            UDAPE_REQUIRE(aligned16(p->grads[q]) && aligned16(p->params[q]) && aligned16(p->shadow[q]), UDAPE_ERR_ALIGN,
+                          "%s: buffers must be 16-byte aligned", what);
         }
     }
     return UDAPE_OK;
@@ -412,65 +406,56 @@ extern "C" int udape_dp_wait(const udape_dp_peers* peers, int phase, const uint3
     return check_launch("udape_dp_wait");
 }
 
-extern "C" int udape_dp_reduce_scatter(const udape_dp_peers* peers, int64_t n_total, float* reduced,
-                                       const uint32_t* epoch_dev, uint32_t* ws, void* stream) {
-    if (int e = check_peers(peers, "udape_dp_reduce_scatter", true)) return e;
-    UDAPE_REQUIRE(reduced && epoch_dev && ws, UDAPE_ERR_NULL, "udape_dp_reduce_scatter: reduced / epoch / ws is NULL");
-    UDAPE_REQUIRE(aligned16(reduced), UDAPE_ERR_ALIGN, "udape_dp_reduce_scatter: reduced must be 16-byte aligned");
-    UDAPE_REQUIRE(n_total > 0 && (n_total & 3) == 0, UDAPE_ERR_SHAPE, "udape_dp_reduce_scatter: n_total must be a positive multiple of 4");
+template <int WMAX>
+static void launch_reduce_step(int variant, unsigned grid, cudaStream_t st, const udape_dp_peers& pr, int64_t lo, int64_t n,
+                               int64_t shard, float inv, const udape_opt_hyper& h, const float* lr_dev, const float* grad_scale,
+                               const int32_t* step_dev, float* m, float* v, const uint32_t* epoch_dev, uint32_t* ws) {
+    if (variant == 0) dp_reduce_step_kernel<WMAX, 0><<<grid, kDpThreads, 0, st>>>(pr, lo, n, shard, inv, h, lr_dev, grad_scale, step_dev, m, v, epoch_dev, ws);
+    else if (variant == 1) dp_reduce_step_kernel<WMAX, 1><<<grid, kDpThreads, 0, st>>>(pr, lo, n, shard, inv, h, lr_dev, grad_scale, step_dev, m, v, epoch_dev, ws);
+    else dp_reduce_step_kernel<WMAX, 2><<<grid, kDpThreads, 0, st>>>(pr, lo, n, shard, inv, h, lr_dev, grad_scale, step_dev, m, v, epoch_dev, ws);
+}
+
+extern "C" int udape_dp_reduce_step(const udape_dp_peers* peers, int64_t n_total, int algo, const udape_opt_hyper* hyper,
+                                    const float* lr_dev, const float* grad_scale, const int32_t* step_dev, float* state1,
+                                    float* state2, const uint32_t* epoch_dev, uint32_t* ws, void* stream) {
+    if (int e = check_peers(peers, "udape_dp_reduce_step", true)) return e;
+    UDAPE_REQUIRE(hyper && step_dev && epoch_dev && ws, UDAPE_ERR_NULL, "udape_dp_reduce_step: hyper / step_dev / epoch / ws is NULL");
+    UDAPE_REQUIRE(n_total > 0 && (n_total & 3) == 0, UDAPE_ERR_SHAPE, "udape_dp_reduce_step: n_total must be a positive multiple of 4");
+    UDAPE_REQUIRE(algo == UDAPE_OPT_ADAM || algo == UDAPE_OPT_SGD, UDAPE_ERR_ARG, "udape_dp_reduce_step: algo must be UDAPE_OPT_ADAM or UDAPE_OPT_SGD");
+    if (algo == UDAPE_OPT_ADAM) {
+        UDAPE_REQUIRE(state1 && state2, UDAPE_ERR_NULL, "udape_dp_reduce_step: Adam needs exp_avg and exp_avg_sq shards");
+        UDAPE_REQUIRE(hyper->beta1 >= 0.0 && hyper->beta1 < 1.0 && hyper->beta2 >= 0.0 && hyper->beta2 < 1.0 && hyper->eps >= 0.0,
+                      UDAPE_ERR_ARG, "udape_dp_reduce_step: Adam needs 0 <= beta < 1 and eps >= 0");
+    } else {
+        UDAPE_REQUIRE((hyper->beta1 == 0.0) == (state1 == nullptr), UDAPE_ERR_ARG, "udape_dp_reduce_step: SGD momentum buffer given iff momentum != 0");
+        UDAPE_REQUIRE(!(hyper->nesterov && (hyper->beta1 <= 0.0 || hyper->beta2 != 0.0)), UDAPE_ERR_ARG,
+                      "udape_dp_reduce_step: Nesterov momentum requires a momentum and zero dampening");
+    }
+    UDAPE_REQUIRE((!state1 || aligned16(state1)) && (!state2 || aligned16(state2)), UDAPE_ERR_ALIGN, "udape_dp_reduce_step: state shards must be 16-byte aligned");
     int64_t lo, n;
     shard_range(peers, n_total, &lo, &n);
+    const int64_t shard = udape_dp_shard_elems(n_total, peers->world);
     cudaStream_t st = as_stream(stream);
     // a rank whose slice is empty (tiny buckets) still takes part in the signalling: one CTA, no elements
     const unsigned grid = static_cast<unsigned>(n > 0 ? (n + kRsChunk - 1) / kRsChunk : 1);
     const float inv = 1.0f / static_cast<float>(peers->world);
-    if (peers->world <= 2) dp_reduce_scatter_kernel<2><<<grid, kDpThreads, 0, st>>>(*peers, lo, n, inv, reduced, epoch_dev, ws);
-    else if (peers->world <= 4) dp_reduce_scatter_kernel<4><<<grid, kDpThreads, 0, st>>>(*peers, lo, n, inv, reduced, epoch_dev, ws);
-    else dp_reduce_scatter_kernel<8><<<grid, kDpThreads, 0, st>>>(*peers, lo, n, inv, reduced, epoch_dev, ws);
-    return check_launch("udape_dp_reduce_scatter");
-}
-
-extern "C" int udape_dp_shard_step(const udape_dp_peers* peers, int64_t n_total, int algo, const udape_opt_hyper* hyper,
-                                   const float* lr_dev, const float* grad_scale, const float* found_inf,
-                                   int32_t* step_dev, const float* reduced, float* state1, float* state2,
-                                   const uint32_t* epoch_dev, uint32_t* ticket, void* stream) {
-    if (int e = check_peers(peers, "udape_dp_shard_step", true)) return e;
-    UDAPE_REQUIRE(hyper && step_dev && reduced && epoch_dev && ticket, UDAPE_ERR_NULL, "udape_dp_shard_step: hyper / step_dev / reduced / epoch / ticket is NULL");
-    UDAPE_REQUIRE(aligned16(reduced), UDAPE_ERR_ALIGN, "udape_dp_shard_step: reduced must be 16-byte aligned");
-    UDAPE_REQUIRE(n_total > 0 && (n_total & 3) == 0, UDAPE_ERR_SHAPE, "udape_dp_shard_step: n_total must be a positive multiple of 4");
-    UDAPE_REQUIRE(algo == UDAPE_OPT_ADAM || algo == UDAPE_OPT_SGD, UDAPE_ERR_ARG, "udape_dp_shard_step: algo must be UDAPE_OPT_ADAM or UDAPE_OPT_SGD");
-    if (algo == UDAPE_OPT_ADAM) {
-        UDAPE_REQUIRE(state1 && state2, UDAPE_ERR_NULL, "udape_dp_shard_step: Adam needs exp_avg and exp_avg_sq shards");
-        UDAPE_REQUIRE(hyper->beta1 >= 0.0 && hyper->beta1 < 1.0 && hyper->beta2 >= 0.0 && hyper->beta2 < 1.0 && hyper->eps >= 0.0,
-                      UDAPE_ERR_ARG, "udape_dp_shard_step: Adam needs 0 <= beta < 1 and eps >= 0");
-    } else {
-        UDAPE_REQUIRE((hyper->beta1 == 0.0) == (state1 == nullptr), UDAPE_ERR_ARG, "udape_dp_shard_step: SGD momentum buffer given iff momentum != 0");
-        UDAPE_REQUIRE(!(hyper->nesterov && (hyper->beta1 <= 0.0 || hyper->beta2 != 0.0)), UDAPE_ERR_ARG,
-                      "udape_dp_shard_step: Nesterov momentum requires a momentum and zero dampening");
-    }
-    UDAPE_REQUIRE((!state1 || aligned16(state1)) && (!state2 || aligned16(state2)), UDAPE_ERR_ALIGN, "udape_dp_shard_step: state shards must be 16-byte aligned");
-    int64_t lo, n;
-    shard_range(peers, n_total, &lo, &n);
-    cudaStream_t st = as_stream(stream);
-    const unsigned grid = static_cast<unsigned>(n > 0 ? (n + kDpChunk - 1) / kDpChunk : 1);
-    if (algo == UDAPE_OPT_ADAM)
-        dp_shard_step_kernel<0><<<grid, kDpThreads, 0, st>>>(*peers, lo, n, *hyper, lr_dev, grad_scale, found_inf, step_dev, reduced, state1, state2, epoch_dev, ticket);
-    else if (hyper->nesterov)
-        dp_shard_step_kernel<2><<<grid, kDpThreads, 0, st>>>(*peers, lo, n, *hyper, lr_dev, grad_scale, found_inf, step_dev, reduced, state1, state2, epoch_dev, ticket);
-    else
-        dp_shard_step_kernel<1><<<grid, kDpThreads, 0, st>>>(*peers, lo, n, *hyper, lr_dev, grad_scale, found_inf, step_dev, reduced, state1, state2, epoch_dev, ticket);
-    return check_launch("udape_dp_shard_step");
+    const int variant = algo == UDAPE_OPT_ADAM ? 0 : (hyper->nesterov ? 2 : 1);
+    if (peers->world <= 2) launch_reduce_step<2>(variant, grid, st, *peers, lo, n, shard, inv, *hyper, lr_dev, grad_scale, step_dev, state1, state2, epoch_dev, ws);
+    else if (peers->world <= 4) launch_reduce_step<4>(variant, grid, st, *peers, lo, n, shard, inv, *hyper, lr_dev, grad_scale, step_dev, state1, state2, epoch_dev, ws);
+    else launch_reduce_step<8>(variant, grid, st, *peers, lo, n, shard, inv, *hyper, lr_dev, grad_scale, step_dev, state1, state2, epoch_dev, ws);
+    return check_launch("udape_dp_reduce_step");
 }
 
 extern "C" int udape_dp_gather_ema(const udape_dp_peers* peers, int64_t n_total, float* teacher, float ema_a, float ema_b,
-                                   const float* found_inf, uint32_t* epoch_dev, uint32_t* ticket, void* stream) {
+                                   const float* found_inf, int32_t* step_dev, uint32_t* epoch_dev, uint32_t* ticket,
+                                   void* stream) {
     if (int e = check_peers(peers, "udape_dp_gather_ema", true)) return e;
-    UDAPE_REQUIRE(epoch_dev && ticket, UDAPE_ERR_NULL, "udape_dp_gather_ema: epoch / ticket is NULL");
+    UDAPE_REQUIRE(step_dev && epoch_dev && ticket, UDAPE_ERR_NULL, "udape_dp_gather_ema: step_dev / epoch / ticket is NULL");
     UDAPE_REQUIRE(n_total > 0 && (n_total & 3) == 0, UDAPE_ERR_SHAPE, "udape_dp_gather_ema: n_total must be a positive multiple of 4");
     UDAPE_REQUIRE(!teacher || aligned16(teacher), UDAPE_ERR_ALIGN, "udape_dp_gather_ema: teacher must be 16-byte aligned");
     const int64_t shard = udape_dp_shard_elems(n_total, peers->world);
     const unsigned grid = static_cast<unsigned>(shard / kDpChunk * peers->world);
-    dp_gather_ema_kernel<<<grid, kDpThreads, 0, as_stream(stream)>>>(*peers, n_total, shard, teacher, ema_a, ema_b, found_inf, epoch_dev, ticket);
+    dp_gather_ema_kernel<<<grid, kDpThreads, 0, as_stream(stream)>>>(*peers, n_total, shard, teacher, ema_a, ema_b, found_inf, step_dev, epoch_dev, ticket);
     return check_launch("udape_dp_gather_ema");
 }
 

@@ -7,9 +7,10 @@ mapped (CUDA IPC, exchanged once through ``torch.distributed``); ``ShardedStuden
 parameters and gradients out flat inside it and runs the step as the three peer-memory kernels of
 ``csrc/dp.cu`` (``include/udape.h`` section e):
 
-    reduce-scatter of the gradient buckets (+ GradScaler's non-finite check, on the reduced slice)
-    -> unscale + Adam | SGD on this rank's 1/W slice (optimizer state is sharded)
-    -> all-gather of the updated slices fused with the teacher EMA (``OldWeightEMA``, utils.py:21-25)
+    reduce-scatter of the gradient buckets fused with GradScaler's non-finite check and unscale + Adam | SGD on
+       this rank's 1/W slice (optimizer state is sharded; the update is speculative, into a shadow slice)
+    -> all-gather of the shadow slices (the commit, unless any rank saw a non-finite gradient) fused with the
+       teacher EMA (``OldWeightEMA``, utils.py:21-25)
 
 with NVLink loads between the GPUs and no NCCL call.  The student / teacher ``Parameter`` objects stay the
 ones the model owns: their ``.data`` is re-pointed at views of the flat buffers (``state_dict()``,
@@ -59,9 +60,10 @@ def flat_layout(params) -> tuple[list[int], int]:
     return offsets, _round_up(total, 4)
 
 
-def arena_bytes(n_total: int) -> int:
-    """pad | gradient bucket | student parameters, each 256-byte aligned."""
-    return PAD_BYTES + 2 * _round_up(4 * n_total, _ALIGN)
+def arena_bytes(n_total: int, world: int = 1) -> int:
+    """pad | gradient bucket | student parameters | shadow of the rank's slice, each 256-byte aligned.  (The
+    shadow is sized for world = 1, the largest slice, so one arena serves any world size.)"""
+    return PAD_BYTES + 3 * _round_up(4 * _round_up(n_total, 4096), _ALIGN)
 
 
 class PeerGroup:
@@ -173,7 +175,7 @@ class ShardedStudentStep(torch.optim.Optimizer):
     """``stu_optimizer`` + ``tea_optimizer`` of ``train_human.py:136-141`` for one-process-per-GPU training:
     ``torch.optim.Adam(lr, betas, eps, weight_decay)`` or ``SGD(lr, momentum, dampening, weight_decay,
     nesterov)`` on the rank-averaged gradient, with ``OldWeightEMA(alpha)`` folded into the parameter
-    exchange.  One param group (what the trainers build).  ``step()`` is six launches, no host sync, CUDA-graph
+    exchange.  One param group (what the trainers build).  ``step()`` is four launches, no host sync, CUDA-graph
     capturable; ``torch.amp.GradScaler`` support through ``uda_poseestimation_b200.GradScaler``
     (``found_inf`` is produced inside the step, on the reduced gradient).
 
@@ -208,7 +210,10 @@ class ShardedStudentStep(torch.optim.Optimizer):
         lib = _lib.load()
         self.shard_elems = int(lib.udape_dp_shard_elems(self.n_total, peers.world))
         self._g_off = PAD_BYTES
-        self._p_off = PAD_BYTES + _round_up(4 * self.n_total, _ALIGN)
+        self._p_off = self._g_off + _round_up(4 * self.n_total, _ALIGN)
+        self._s_off = self._p_off + _round_up(4 * self.n_total, _ALIGN)
+        if self._s_off + 4 * self.shard_elems > peers.nbytes:
+            raise ValueError(f"peer arena too small for the shadow slice: {peers.nbytes} bytes")
         self.flat_grads = peers.tensor(peers.rank, self._g_off, self.n_total)
         self.flat_params = peers.tensor(peers.rank, self._p_off, self.n_total)
         with torch.no_grad():
@@ -228,10 +233,11 @@ class ShardedStudentStep(torch.optim.Optimizer):
                     view = self.flat_teacher[off:off + t.numel()].view(t.shape)
                     view.copy_(t.data)
                     t.data = view
-        self.reduced = torch.zeros(self.shard_elems, dtype=torch.float32, device=dev)
+        self.shadow = peers.tensor(peers.rank, self._s_off, self.shard_elems)
         need1 = algo == "adam" or momentum != 0
-        self.state1 = torch.zeros(self.shard_elems, dtype=torch.float32, device=dev) if need1 else None
-        self.state2 = torch.zeros(self.shard_elems, dtype=torch.float32, device=dev) if algo == "adam" else None
+        # [2, S]: the update writes the half that is not current; committing a step flips them (step count parity)
+        self.state1 = torch.zeros((2, self.shard_elems), dtype=torch.float32, device=dev) if need1 else None
+        self.state2 = torch.zeros((2, self.shard_elems), dtype=torch.float32, device=dev) if algo == "adam" else None
         self.found_inf = torch.zeros((), dtype=torch.float32, device=dev)
         self._step_dev = torch.zeros((), dtype=torch.int32, device=dev)
         self._words = torch.zeros(8, dtype=torch.int32, device=dev)   # epoch, counts epoch, ws[2], ticket K2, ticket K3
@@ -242,6 +248,7 @@ class ShardedStudentStep(torch.optim.Optimizer):
             self._c.pads[q] = peers.bases[q]
             self._c.grads[q] = peers.bases[q] + self._g_off
             self._c.params[q] = peers.bases[q] + self._p_off
+            self._c.shadow[q] = peers.bases[q] + self._s_off
         if capturable:
             self.sync_lr()
 
@@ -272,7 +279,7 @@ class ShardedStudentStep(torch.optim.Optimizer):
     # -- the step ------------------------------------------------------------------------------------
     @torch.no_grad()
     def step(self, closure=None, _events=None):
-        """``_events`` (profiling, eager only): seven CUDA events recorded around the six launches."""
+        """``_events`` (profiling, eager only): five CUDA events recorded around the four launches."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -296,44 +303,45 @@ class ShardedStudentStep(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step_begin(self, _ev=None):
-        """First half of ``step()``: the READY barrier and the gradient reduce-scatter.  A caller that has other
+        """First half of ``step()``: the READY barrier and the gradient reduce-scatter + update.  A caller that has other
         work to enqueue (e.g. the PCK launch whose counts ``step_finish`` exchanges) does it between the halves."""
-        lib, dev, _, c, epoch, t_ns = self._launch_args()
+        lib, dev, grad_scale, c, epoch, t_ns = self._launch_args()
         with _lib.on_device(dev):
             st = _lib.stream_ptr(dev)
             self._mark(_ev, dev)
             _lib.check(lib.udape_dp_barrier(c, READY, epoch, t_ns, st), "udape_dp_barrier")
             self._mark(_ev, dev)
-            _lib.check(lib.udape_dp_reduce_scatter(c, self.n_total, self.reduced.data_ptr(), epoch, self._word(2), st),
-                       "udape_dp_reduce_scatter")
+            h = self._hyper()
+            algo = _lib.OPT_ADAM if self.algo == "adam" else _lib.OPT_SGD
+            _lib.check(lib.udape_dp_reduce_step(c, self.n_total, algo, ctypes.byref(h), _lib.ptr(self._lr_dev),
+                                                _lib.ptr(grad_scale), self._step_dev.data_ptr(), _lib.ptr(self.state1),
+                                                _lib.ptr(self.state2), epoch, self._word(2), st), "udape_dp_reduce_step")
             self._mark(_ev, dev)
 
     @torch.no_grad()
     def step_finish(self, counts: torch.Tensor | None = None, _ev=None):
         """Second half: [the PCK-count exchange of ``counts`` (in place), on this same stream so that every rank
         meets its peers in ONE order and no two waiting kernels of a rank can ever wait for each other,] the
-        non-finite verdict, the update of this rank's slice, the parameter all-gather + EMA."""
-        lib, dev, grad_scale, c, epoch, t_ns = self._launch_args()
+        non-finite verdict and the parameter all-gather (the commit) + EMA."""
+        lib, dev, _, c, epoch, t_ns = self._launch_args()
         h = self._hyper()
-        algo = _lib.OPT_ADAM if self.algo == "adam" else _lib.OPT_SGD
         if counts is not None:
             self.allreduce_counts(counts, out=counts)
         with _lib.on_device(dev):
             st = _lib.stream_ptr(dev)
             _lib.check(lib.udape_dp_wait(c, REDUCED, epoch, self.found_inf.data_ptr(), t_ns, st), "udape_dp_wait")
             self._mark(_ev, dev)
-            _lib.check(lib.udape_dp_shard_step(c, self.n_total, algo, ctypes.byref(h), _lib.ptr(self._lr_dev),
-                                               _lib.ptr(grad_scale), self.found_inf.data_ptr(), self._step_dev.data_ptr(),
-                                               self.reduced.data_ptr(), _lib.ptr(self.state1), _lib.ptr(self.state2), epoch,
-                                               self._word(4), st), "udape_dp_shard_step")
-            self._mark(_ev, dev)
-            _lib.check(lib.udape_dp_wait(c, PARAMS, epoch, None, t_ns, st), "udape_dp_wait")
-            self._mark(_ev, dev)
             _lib.check(lib.udape_dp_gather_ema(c, self.n_total, _lib.ptr(self.flat_teacher), h.ema_a, h.ema_b,
-                                               self.found_inf.data_ptr(), epoch, self._word(5), st), "udape_dp_gather_ema")
+                                               self.found_inf.data_ptr(), self._step_dev.data_ptr(), epoch, self._word(5),
+                                               st), "udape_dp_gather_ema")
             self._mark(_ev, dev)
 
-    kernels_per_step = 6
+    def state_shards(self):
+        """This rank's CURRENT optimizer-state shards ``(exp_avg | momentum_buffer, exp_avg_sq)`` (views, host sync)."""
+        cur = self.applied_steps() & 1
+        return (self.state1[cur] if self.state1 is not None else None, self.state2[cur] if self.state2 is not None else None)
+
+    kernels_per_step = 4
 
     def allreduce_counts(self, counts: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """SUM over ranks of an int32 tensor of <= 64 elements (PCK ``hits || valid``) in one single-CTA launch

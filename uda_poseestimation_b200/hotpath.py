@@ -106,8 +106,8 @@ class ReplicatedTail:
 
 
 class PeerTail:
-    """The same tail as three peer-memory kernels over NVLink (``dp.ShardedStudentStep``): gradient
-    reduce-scatter + non-finite check, the update on this rank's 1/W slice, parameter all-gather + EMA."""
+    """The same tail as two peer-memory kernels over NVLink (``dp.ShardedStudentStep``): gradient reduce-scatter +
+    non-finite check + the update of this rank's 1/W slice in one kernel, parameter all-gather + EMA in the other."""
 
     name = "peer"
 
@@ -140,9 +140,9 @@ class PeerTail:
 
     def bytes(self) -> dict:
         w, p4, s4 = self.world, 4 * self.n_params, 4 * self.opt.shard_elems
-        state = 7 if self.algo == "adam" else 5      # p, g, m(, v) read; p, m(, v) written
-        return {"reduce_scatter": (w + 1) * s4, "shard_step": state * s4,
-                "gather_ema": p4 + (w - 1) * s4 + 2 * p4,
+        state = 6 if self.algo == "adam" else 4      # p, m(, v) read; p', m'(, v') written  (+ w gradient slices read)
+        return {"reduce_step": (w + state) * s4,     # of which (w - 1) * s4 arrive over NVLink
+                "gather_ema": p4 + p4 + 2 * p4,      # shadow read (NVLink but for the own slice), params written, teacher r+w
                 "nvlink_in": 2 * (w - 1) * s4}
 
 
