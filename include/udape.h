@@ -230,6 +230,34 @@ UDAPE_API int udape_gauss_target(const double* joints, const float* vis, int64_t
 UDAPE_API int udape_labelmap(const int32_t* pts, int64_t planes, int64_t h, int64_t w, double sigma,
                    int kind, int zero_fill, float* img, int32_t* vis_out, void* stream);
 
+/* ---- f4: every target set a loader builds per sample, in one launch --------------------------
+ * lib/datasets/rendered_hand_pose_mt.py:99,103,115,134,147 calls generate_target five times per sample (the
+ * student's, the un-augmented and the teacher view's (64,64) targets plus two (8,8) "small" targets);
+ * lib/datasets/real_animal_all_mt.py:275-283,306-311 calls draw_labelmap_ori per joint for three views inside
+ * `if tpts[i, 1] > 0`.  A job is one such set over the whole batch: planes = B*K (sample, joint) pairs, the same
+ * for every job; jobs is a HOST array of n_jobs <= UDAPE_MAX_TARGET_JOBS entries of DEVICE pointers.  Per plane
+ * the arithmetic is udape_gauss_target's / udape_labelmap's (zero-filling form).  gate (optional, uint8 [planes]):
+ * 0 = the caller's `if` skipped the joint — the plane is all zero and vis_out is 1, so that the
+ * `target_weight *= vis` of :282-283 leaves the weight alone. */
+#define UDAPE_MAX_TARGET_JOBS 8
+typedef struct udape_target_job {
+    const double* joints; /* [planes, 2] image pixels */
+    const float* vis;     /* [planes] */
+    float* target;        /* [planes, hm_h, hm_w] */
+    float* weight;        /* [planes] */
+    int32_t hm_w, hm_h;
+} udape_target_job;
+typedef struct udape_labelmap_job {
+    const int32_t* pts;  /* [planes, 2] heatmap pixels, already truncated to int32 (util.py:332) */
+    const uint8_t* gate; /* optional [planes] */
+    float* img;          /* [planes, h, w] */
+    int32_t* vis_out;    /* optional [planes] */
+} udape_labelmap_job;
+UDAPE_API int udape_gauss_target_multi(const udape_target_job* jobs, int n_jobs, int64_t planes, double sigma,
+                             double image_w, double image_h, void* stream);
+UDAPE_API int udape_labelmap_multi(const udape_labelmap_job* jobs, int n_jobs, int64_t planes, int64_t h, int64_t w,
+                         double sigma, int kind, void* stream);
+
 /* ---- a12/a13: EMA teacher update — utils.py:9-25 (OldWeightEMA), lib/models/ema.py ----
  * A chunk is a contiguous run of one parameter tensor.  udape_ema_plan (host-only helper,
  * no CUDA) splits n_tensors tensors of elem_bytes-sized elements into chunks of

@@ -440,6 +440,34 @@ def student_teacher_step(algo, student, grads, state1, state2, teacher, step, sc
     return found_inf, step
 
 
+
+def loader_targets_hand(kp_stu, kp_ori, kp_tea, visible, heatmap_size, sigma, image_size):
+    """lib/datasets/rendered_hand_pose_mt.py:99,103,115,134,147 for a batch (k = 1 teacher view): the five
+    generate_target calls of one __getitem__, per sample.  Returns [(target [B,K,H,W], weight [B,K,1])] x 5 in
+    the reference's call order: stu, ori, small stu (8, 8), tea, small tea (8, 8)."""
+    calls = [(kp_stu, heatmap_size), (kp_ori, heatmap_size), (kp_stu, (8, 8)), (kp_tea, heatmap_size), (kp_tea, (8, 8))]
+    out = []
+    for kp, size in calls:
+        tg, wt = zip(*[generate_target(kp[i], visible[i], size, sigma, image_size) for i in range(kp.shape[0])])
+        out.append((np.stack(tg), np.stack(wt)))
+    return out
+
+
+def loader_labelmaps_animal(pts, gate, weight0, res, sigma, type="Gaussian"):
+    """lib/datasets/real_animal_all_mt.py:268-283 / :300-311 for one view of a batch: zero target, per joint
+    `if gate: target[i], vis = draw_labelmap_ori(target[i], tpts[i] - 1, sigma, type); weight[i, 0] *= vis`.
+    pts [B,K,>=2] (the 1-based `tpts`), gate [B,K] bool, weight0 [B,K] -> (target [B,K,res,res], weight [B,K,1])."""
+    pts = torch.as_tensor(pts)
+    b, k = pts.shape[:2]
+    target = torch.zeros(b, k, res, res)
+    weight = torch.as_tensor(weight0).clone().float().view(b, k, 1)
+    for bi in range(b):
+        for i in range(k):
+            if bool(gate[bi][i]):
+                target[bi, i], vis = draw_labelmap_ori(target[bi, i], pts[bi, i] - 1, sigma, type=type)
+                weight[bi, i, 0] *= vis
+    return target, weight
+
 # --------------------------------------------------------------------------------------------------
 # f1  affine re-warp loops  (train_human.py:359-372, :385-412, :418-423; same in train_animal.py)
 # --------------------------------------------------------------------------------------------------

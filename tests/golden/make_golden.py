@@ -237,6 +237,51 @@ def golden_targets():
     save("targets", **out)
 
 
+def golden_loader_targets():
+    """The loader-side call patterns, verbatim: rendered_hand_pose_mt.py:99,103,115,134,147 (five generate_target
+    calls per sample: three at heatmap_size, two at (8, 8)) and real_animal_all_mt.py:268-283,306-311 (three
+    draw_labelmap_ori calls per joint inside `if tpts[i, 1] > 0`, weights multiplied by the returned vis)."""
+    du = ref_loader.load("dataset_util")
+    out = {}
+    b, k = 4, 21
+    rng = np.random.RandomState(71)
+    visible = (rng.uniform(size=(b, k, 1)) >= 0.1).astype(np.float32)
+    sets = {n: synthetic.keypoints(b, k, seed=72 + i)[0] for i, n in enumerate(("stu", "ori", "tea"))}
+    sets["stu"][0, 0] = [-2.1, 300.0]
+    sets["tea"][1, 3] = [255.9, 0.4]
+    hs, sigma, image = (64, 64), 2, (256, 256)
+    for n, kp in sets.items():
+        out[f"hand_kp_{n}"] = kp
+    out["hand_visible"] = visible
+    calls = [("stu", hs), ("ori", hs), ("stu", (8, 8)), ("tea", hs), ("tea", (8, 8))]    # :99, :103, :115, :134, :147
+    for ci, (n, size) in enumerate(calls):
+        tg, wt = zip(*[du.generate_target(sets[n][i], visible[i], size, sigma, image) for i in range(b)])
+        out[f"hand_target_{ci}"], out[f"hand_weight_{ci}"] = np.stack(tg), np.stack(wt)
+    # animal variant: pts [K,3] = (x, y, visible) per sample, already in heatmap pixels + 1 (the reference's
+    # `transform(...)` output is 1-based; it passes tpts[i] - 1)
+    nparts, res, sig = 18, 64, 1.0
+    for kind in ("Gaussian", "Cauchy"):
+        views = {v: rng.uniform(-3.0, 68.0, size=(b, nparts, 3)).astype(np.float32) for v in ("ori", "stu", "tea")}
+        for v in views.values():
+            v[..., 2] = (rng.uniform(size=(b, nparts)) >= 0.15)
+            v[rng.uniform(size=(b, nparts)) < 0.1, 1] = -1.0      # `if tpts[i, 1] > 0` skips these
+        # the reference gates all three draws of :280-281 on the STUDENT's y and :310 on the teacher's y
+        gate = {"ori": views["stu"][..., 1] > 0, "stu": views["stu"][..., 1] > 0, "tea": views["tea"][..., 1] > 0}
+        for v, pts in views.items():
+            target = torch.zeros(b, nparts, res, res)
+            weight = torch.tensor(views["stu" if v != "tea" else "tea"][..., 2]).clone().view(b, nparts, 1)
+            tp = torch.tensor(pts)
+            for bi in range(b):
+                for i in range(nparts):
+                    if gate[v][bi, i]:
+                        target[bi, i], vis = du.draw_labelmap_ori(target[bi, i], tp[bi, i] - 1, sig, type=kind)
+                        weight[bi, i, 0] *= vis
+            out[f"animal_{kind}_pts_{v}"], out[f"animal_{kind}_gate_{v}"] = pts, gate[v]
+            out[f"animal_{kind}_w0_{v}"] = views["stu" if v != "tea" else "tea"][..., 2]
+            out[f"animal_{kind}_target_{v}"], out[f"animal_{kind}_weight_{v}"] = target, weight
+    save("loader_targets", **out)
+
+
 def golden_ema():
     ut = ref_loader.load("utils")
     em = ref_loader.load("ema")
@@ -498,7 +543,7 @@ def main():
     torch.manual_seed(0)
     np.random.seed(0)
     fns = (golden_adain, golden_decode, golden_accuracy, golden_losses, golden_masks, golden_rectify,
-           golden_targets, golden_ema, golden_optim, golden_style_loss, golden_clamp, golden_rewarp)
+           golden_targets, golden_loader_targets, golden_ema, golden_optim, golden_style_loss, golden_clamp, golden_rewarp)
     only = set(sys.argv[1:])  # e.g. `make_golden.py clamp` regenerates one fixture
     for fn in fns:
         if not only or fn.__name__.removeprefix("golden_") in only:

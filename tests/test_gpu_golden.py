@@ -167,6 +167,38 @@ def test_generate_target_golden(golden, dev, case):
     np.testing.assert_array_equal(w1, ref_w[0])
 
 
+def test_loader_side_target_sets_in_one_launch(golden, dev):
+    """SURVEY.md §8f-4, second half: the five generate_target calls per sample of rendered_hand_pose_mt.py:99-147
+    (three 64x64, two 8x8) as ONE launch over the batch, and the gated draw_labelmap_ori triples of
+    real_animal_all_mt.py:275-283,306-311 as one launch — against the fixture made by the reference's functions."""
+    g = golden("loader_targets")
+    sets = [g["hand_kp_stu"], g["hand_kp_ori"], g["hand_kp_stu"], g["hand_kp_tea"], g["hand_kp_tea"]]
+    sizes = [(64, 64), (64, 64), (8, 8), (64, 64), (8, 8)]
+    outs = U.generate_targets_multi(sets, g["hand_visible"], sizes, 2, (256, 256))
+    assert len(outs) == 5
+    for ci, (t, w) in enumerate(outs):
+        ref_t, ref_w = g[f"hand_target_{ci}"], g[f"hand_weight_{ci}"]
+        assert tuple(t.shape) == ref_t.shape and tuple(w.shape) == ref_w.shape
+        np.testing.assert_array_equal(w.cpu().numpy(), ref_w)                    # weights: exact
+        np.testing.assert_array_equal(t.cpu().numpy() != 0, ref_t != 0)          # integer placement: exact
+        np.testing.assert_array_equal(t.cpu().numpy() == 1.0, ref_t == 1.0)
+        assert_close_scaled(t, ref_t, RTOL, f"hand target set {ci}")
+        # and equal to the single-set launch, bit for bit
+        t1, w1 = U.generate_target_batched(sets[ci], g["hand_visible"], sizes[ci], 2, (256, 256))
+        assert torch.equal(t, t1) and torch.equal(w, w1)
+    for kind in ("Gaussian", "Cauchy"):
+        views = ("ori", "stu", "tea")
+        pts = [torch.from_numpy(g[f"animal_{kind}_pts_{v}"]) - 1 for v in views]      # the reference passes tpts[i] - 1
+        gates = [g[f"animal_{kind}_gate_{v}"] for v in views]
+        outs = U.draw_labelmaps_multi(pts, 64, 64, 1.0, kind, gates=gates)
+        for v, (img, vis) in zip(views, outs):
+            ref_t, ref_w = g[f"animal_{kind}_target_{v}"], g[f"animal_{kind}_weight_{v}"]
+            np.testing.assert_array_equal(img.cpu().numpy() != 0, ref_t != 0)
+            assert_close_scaled(img, ref_t, 1e-6, f"animal {kind} {v}")
+            w = torch.from_numpy(g[f"animal_{kind}_w0_{v}"]).float().view(ref_w.shape) * vis.cpu().view(ref_w.shape)   # :282-283
+            np.testing.assert_array_equal(w.numpy(), ref_w)
+
+
 @pytest.mark.parametrize("case", [("g1", 1.0, "Gaussian"), ("g2", 2, "Gaussian"), ("c1", 1.0, "Cauchy")])
 def test_draw_labelmap_golden(golden, dev, case):
     g = golden("targets")

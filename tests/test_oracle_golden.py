@@ -133,6 +133,21 @@ def test_draw_labelmap(golden, case, capsys):
     np.testing.assert_array_equal(img.numpy(), g["lm_canvas"])
 
 
+def test_loader_side_target_sets(golden, capsys):
+    """the loader call patterns (five generate_target calls per hand sample; gated draw_labelmap_ori triples per
+    animal joint) restated by the oracle == the fixture produced by the reference's own functions"""
+    g = golden("loader_targets")
+    got = R.loader_targets_hand(g["hand_kp_stu"], g["hand_kp_ori"], g["hand_kp_tea"], g["hand_visible"], (64, 64), 2, (256, 256))
+    for ci, (t, w) in enumerate(got):
+        np.testing.assert_array_equal(t, g[f"hand_target_{ci}"])
+        np.testing.assert_array_equal(w, g[f"hand_weight_{ci}"])
+    for kind in ("Gaussian", "Cauchy"):
+        for v in ("ori", "stu", "tea"):
+            t, w = R.loader_labelmaps_animal(g[f"animal_{kind}_pts_{v}"], g[f"animal_{kind}_gate_{v}"], g[f"animal_{kind}_w0_{v}"], 64, 1.0, kind)
+            np.testing.assert_array_equal(t.numpy(), g[f"animal_{kind}_target_{v}"])
+            np.testing.assert_array_equal(w.numpy(), g[f"animal_{kind}_weight_{v}"])
+
+
 def _split_like(flat, params):
     out, off = [], 0
     for p in params:

@@ -270,6 +270,39 @@ def main():
         bench("loss_step (analytic teacher)", shape, 2 * (2 * hm16) + hm32, lambda r: mk_step(r, True), "loss")
         bench("gauss_target", shape, hm32 + 24 * planes, mk_gt, "target")
         bench("labelmap", shape, hm32 + 12 * planes, mk_lm, "target")
+
+        # every target set of a loader in one launch: three 64x64 + two 8x8 sets (rendered_hand_pose_mt.py:99-147),
+        # three gated 64x64 label-map views (real_animal_all_mt.py:275-283,306-311)
+        multi_cache = {}
+
+        def multi_bufs(r):
+            if r not in multi_cache:
+                multi_cache[r] = dict(big=[torch.empty(planes * 4096, dtype=torch.float32, device=dev) for _ in range(3)],
+                                      small=[torch.empty(planes * 64, dtype=torch.float32, device=dev) for _ in range(2)],
+                                      w=[torch.empty(planes, dtype=torch.float32, device=dev) for _ in range(5)],
+                                      v=[torch.empty(planes, dtype=torch.int32, device=dev) for _ in range(3)])
+            return multi_cache[r]
+        gate = (vd > 0.5).to(torch.uint8).contiguous()
+
+        def mk_gt_multi(r):
+            d = multi_bufs(r)
+            jobs = (_lib.TargetJob * 5)()
+            outs = [d["big"][0], d["big"][1], d["small"][0], d["big"][2], d["small"][1]]
+            for i, o in enumerate(outs):
+                jobs[i].joints, jobs[i].vis, jobs[i].target, jobs[i].weight = jd.data_ptr(), vd.data_ptr(), o.data_ptr(), d["w"][i].data_ptr()
+                jobs[i].hm_w = jobs[i].hm_h = 64 if o.numel() == planes * 4096 else 8
+            return lambda: chk(lib.udape_gauss_target_multi(jobs, 5, planes, float(sigma), 256.0, 256.0, st()))
+
+        def mk_lm_multi(r):
+            d = multi_bufs(r)
+            jobs = (_lib.LabelmapJob * 3)()
+            for i in range(3):
+                jobs[i].pts, jobs[i].gate, jobs[i].img, jobs[i].vis_out = pts.data_ptr(), gate.data_ptr(), d["big"][i].data_ptr(), d["v"][i].data_ptr()
+            return lambda: chk(lib.udape_labelmap_multi(jobs, 3, planes, 64, 64, float(sigma), 0, st()))
+
+        multi_bytes = 3 * hm32 + 2 * planes * 64 * 4 + 5 * 24 * planes
+        bench("gauss_target x5 (1 launch)", shape, multi_bytes, mk_gt_multi, "target")
+        bench("labelmap x3 (1 launch)", shape, 3 * hm32 + 3 * 13 * planes, mk_lm_multi, "target")
         # re-warp (three tF.affine stages composed): teacher fp32 forward, student fp16 forward + backward
         from uda_poseestimation_b200 import rewarp as RW
         t32 = RW.stage_table(RW.recon_stages(S.aug_params(b, seed=5), 4.0, b), 64, 64, torch.float32, None)[0].to(dev)

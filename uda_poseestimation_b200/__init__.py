@@ -30,8 +30,8 @@ from ._lib import UdapeError, library_path, load as load_library
 from .adain import (adain, adain_mix, adaptive_instance_normalization, calc_mean_std, calc_style_loss,
                     channel_clamp)
 from .ema import ModelEMA, MultiTensorPlan, OldWeightEMA
-from .heatmap import (draw_labelmap_batched, draw_labelmap_ori, generate_target, generate_target_batched,
-                      rectify)
+from .heatmap import (draw_labelmap_batched, draw_labelmap_ori, draw_labelmaps_multi, generate_target,
+                      generate_target_batched, generate_targets_multi, rectify)
 from .keypoint_detection import (accuracy, accuracy_from_counts, calc_dists, decode, dist_acc, get_max_preds,
                                  get_max_preds_torch, pck_counts)
 from .loss import ConsLoss, JointsMSELoss, cons_loss, fused_losses, joints_mse_loss
@@ -50,6 +50,7 @@ __all__ = [
     "accuracy_from_counts", "decode",
     "JointsMSELoss", "ConsLoss", "joints_mse_loss", "cons_loss", "fused_losses",
     "generate_target", "generate_target_batched", "draw_labelmap_ori", "draw_labelmap_batched", "rectify",
+    "generate_targets_multi", "draw_labelmaps_multi",
     "confidence_mask", "consistency_mask", "teacher_targets",
     "OldWeightEMA", "ModelEMA", "MultiTensorPlan",
     "teacher_recon", "student_recon", "occlude_keypoints", "affine_nearest",

@@ -50,6 +50,15 @@ class OptHyper(ctypes.Structure):
                 ("step", ctypes.c_int32), ("nesterov", ctypes.c_int32)]
 
 
+class TargetJob(ctypes.Structure):
+    _fields_ = [("joints", c_void_p), ("vis", c_void_p), ("target", c_void_p), ("weight", c_void_p),
+                ("hm_w", ctypes.c_int32), ("hm_h", ctypes.c_int32)]
+
+
+class LabelmapJob(ctypes.Structure):
+    _fields_ = [("pts", c_void_p), ("gate", c_void_p), ("img", c_void_p), ("vis_out", c_void_p)]
+
+
 class DpPeers(ctypes.Structure):
     _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("grads", c_void_p * 8), ("params", c_void_p * 8),
                 ("shadow", c_void_p * 8), ("pads", c_void_p * 8)]
@@ -95,6 +104,8 @@ PROTOTYPES = {
                                    c_double, c_void_p, c_void_p, c_void_p]),
     "udape_labelmap": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_double, c_int, c_int, c_void_p,
                                c_void_p, c_void_p]),
+    "udape_gauss_target_multi": (c_int, [POINTER(TargetJob), c_int, c_int64, c_double, c_double, c_double, c_void_p]),
+    "udape_labelmap_multi": (c_int, [POINTER(LabelmapJob), c_int, c_int64, c_int64, c_int64, c_double, c_int, c_void_p]),
     "udape_ema_plan": (c_int64, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_int64, c_int64,
                                  c_int64, POINTER(EmaChunk), c_int64]),
     "udape_ema_multi": (c_int, [c_void_p, c_int64, c_int64, c_float, c_float, c_int, c_int, c_void_p]),

@@ -14,8 +14,8 @@ import torch
 from . import _lib
 from .keypoint_detection import decode
 
-__all__ = ["generate_target", "generate_target_batched", "draw_labelmap_ori", "draw_labelmap_batched",
-           "rectify"]
+__all__ = ["generate_target", "generate_target_batched", "generate_targets_multi", "draw_labelmap_ori",
+           "draw_labelmap_batched", "draw_labelmaps_multi", "rectify"]
 
 
 def _default_device() -> torch.device:
@@ -66,6 +66,50 @@ def generate_target_batched(joints, joints_vis, heatmap_size, sigma, image_size,
     return target, weight
 
 
+def generate_targets_multi(joint_sets, joints_vis, heatmap_sizes, sigma, image_size, device=None):
+    """Every target set a loader builds per sample, for the whole batch, in ONE launch
+    (``rendered_hand_pose_mt.py:99,103,115,134,147``: five ``generate_target`` calls per sample — student,
+    un-augmented and teacher-view keypoints at ``(64, 64)``, student and teacher view again at ``(8, 8)``).
+
+    ``joint_sets``: list of ``[B,K,2]`` keypoint arrays (image pixels), ``joints_vis [B,K,1]`` shared by all sets
+    (the reference passes the same ``visible``), ``heatmap_sizes``: one ``(W, H)`` per set.  Returns a list of
+    ``(target [B,K,H,W] float32, target_weight [B,K,1] float32)`` CUDA tensors, one pair per set."""
+    if len(joint_sets) != len(heatmap_sizes) or not 1 <= len(joint_sets) <= 8:
+        raise ValueError("generate_targets_multi: one heatmap size per keypoint set, 1..8 sets")
+    if device is None:
+        first = joint_sets[0]
+        device = first.device if (torch.is_tensor(first) and first.is_cuda) else _default_device()
+    device = torch.device(device)
+
+    def as_dev(x, dt):
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x))
+        return x.detach().to(device=device, dtype=dt)
+
+    lead = tuple(joint_sets[0].shape[:-1])
+    planes = int(np.prod(lead))
+    v = as_dev(joints_vis, torch.float32).reshape(planes, -1)[:, 0].contiguous()
+    # one [S, planes, 2] float64 upload for all sets
+    js = torch.stack([as_dev(j, torch.float64).reshape(planes, 2) for j in joint_sets]).contiguous()
+    jobs = (_lib.TargetJob * len(joint_sets))()
+    outs = []
+    for i, (w, h) in enumerate(heatmap_sizes):
+        if tuple(joint_sets[i].shape[:-1]) != lead or joint_sets[i].shape[-1] != 2:
+            raise ValueError("generate_targets_multi: every keypoint set must be [..., K, 2] with the same leading shape")
+        target = torch.empty(lead + (int(h), int(w)), dtype=torch.float32, device=device)
+        weight = torch.empty(lead + (1,), dtype=torch.float32, device=device)
+        jobs[i].joints, jobs[i].vis = js[i].data_ptr(), v.data_ptr()
+        jobs[i].target, jobs[i].weight = target.data_ptr(), weight.data_ptr()
+        jobs[i].hm_w, jobs[i].hm_h = int(w), int(h)
+        outs.append((target, weight))
+    if planes > 0:
+        with _lib.on_device(device):
+            st = _lib.load().udape_gauss_target_multi(jobs, len(joint_sets), planes, float(sigma), float(image_size[0]),
+                                                      float(image_size[1]), _lib.stream_ptr(device))
+        _lib.check(st, "generate_targets_multi")
+    return outs
+
+
 def generate_target(joints, joints_vis, heatmap_size, sigma, image_size):
     """Reference signature (util.py:12): ``joints (K,2)``, ``joints_vis (K,1)`` numpy arrays →
     ``(target (K,H,W), target_weight (K,1))`` numpy float32.  Torch inputs return CUDA tensors."""
@@ -108,6 +152,54 @@ def draw_labelmap_batched(pts, height, width, sigma, type="Gaussian", out=None):
                                             vis.data_ptr(), _lib.stream_ptr(device))
         _lib.check(st, "draw_labelmap_ori")
     return out, vis
+
+
+def draw_labelmaps_multi(pt_sets, height, width, sigma, type="Gaussian", gates=None, device=None):
+    """The label maps of several views of a batch in ONE launch (``real_animal_all_mt.py:275-283,306-311``:
+    ``draw_labelmap_ori`` per joint for the un-augmented, the student's and each teacher view's keypoints, inside
+    ``if tpts[i, 1] > 0``).
+
+    ``pt_sets``: list of ``[B,K,>=2]`` point arrays in heatmap pixels (what the reference passes as
+    ``tpts[i] - 1``), ``gates``: optional list (one per set, or one shared array) of ``[B,K]`` booleans — the
+    reference's ``if``; a gated-off joint keeps an all-zero plane and ``vis = 1`` so that
+    ``target_weight *= vis`` leaves its weight alone.  Returns a list of ``(img [B,K,H,W] float32, vis [B,K] int32)``."""
+    if type not in _KINDS:
+        raise ValueError(f"draw_labelmap_ori: unknown type {type!r}")
+    if not 1 <= len(pt_sets) <= 8:
+        raise ValueError("draw_labelmaps_multi: 1..8 point sets")
+    if device is None:
+        first = pt_sets[0]
+        device = first.device if (torch.is_tensor(first) and first.is_cuda) else _default_device()
+    device = torch.device(device)
+    lead = tuple(pt_sets[0].shape[:-1])
+    planes = int(np.prod(lead))
+
+    def as_t(x):
+        return torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x
+
+    # util.py:332  pt = pt.to(torch.int32)  (truncation toward zero), one upload for all sets
+    ps = torch.stack([as_t(p).detach()[..., :2].to(torch.int32).reshape(planes, 2) for p in pt_sets]).to(device).contiguous()
+    if gates is not None and not isinstance(gates, (list, tuple)):
+        gates = [gates] * len(pt_sets)
+    gs = None
+    if gates is not None:
+        gs = torch.stack([as_t(g).detach().reshape(planes).to(torch.uint8) for g in gates]).to(device).contiguous()
+    jobs = (_lib.LabelmapJob * len(pt_sets))()
+    outs = []
+    for i in range(len(pt_sets)):
+        if tuple(pt_sets[i].shape[:-1]) != lead:
+            raise ValueError("draw_labelmaps_multi: every point set must have the same leading shape")
+        img = torch.empty(lead + (int(height), int(width)), dtype=torch.float32, device=device)
+        vis = torch.empty(lead, dtype=torch.int32, device=device)
+        jobs[i].pts, jobs[i].gate = ps[i].data_ptr(), (gs[i].data_ptr() if gs is not None else None)
+        jobs[i].img, jobs[i].vis_out = img.data_ptr(), vis.data_ptr()
+        outs.append((img, vis))
+    if planes > 0:
+        with _lib.on_device(device):
+            st = _lib.load().udape_labelmap_multi(jobs, len(pt_sets), planes, int(height), int(width), float(sigma),
+                                                  _KINDS[type], _lib.stream_ptr(device))
+        _lib.check(st, "draw_labelmaps_multi")
+    return outs
 
 
 def draw_labelmap_ori(img, pt, sigma, type="Gaussian"):

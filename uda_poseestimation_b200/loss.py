@@ -113,6 +113,8 @@ class JointsMSELoss(nn.Module):
 
     def __init__(self, reduction="mean"):
         super().__init__()
+        # kept for the module's attribute / repr / state_dict contract (loss.py:36); forward() does not call it
+        self.criterion = nn.MSELoss(reduction="none")
         self.reduction = reduction
 
     def forward(self, output, target, target_weight=None):
