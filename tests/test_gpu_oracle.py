@@ -198,6 +198,23 @@ def test_loss_odd_shapes_and_reduction_none(dev):
         assert_close_scaled(s2.grad, s1.grad, 1e-5, f"cons grad {shape}")
 
 
+def test_adain_both_directions_in_one_launch(dev):
+    """s2t and t2s (train_human.py:348-356) as ONE launch == two adain_mix launches, bit for bit, with a float and
+    a device-resident alpha; and both against the oracle."""
+    c1, s1 = S.vgg_features(3, seed=31, channels=64)
+    c2, s2 = S.vgg_features(3, seed=32, channels=64)
+    a2 = torch.tensor([0.8], device=dev)
+    o1, o2 = U.adain_mix_multi([(c1.to(dev), s1.to(dev), 0.3), (c2.to(dev), s2.to(dev), a2)])
+    assert torch.equal(o1, U.adain_mix(c1.to(dev), s1.to(dev), 0.3))
+    assert torch.equal(o2, U.adain_mix(c2.to(dev), s2.to(dev), a2))
+    assert_close_scaled(o1, R.adain_mix(c1, s1, 0.3), 1e-5, "s2t")
+    assert_close_scaled(o2, R.adain_mix(c2, s2, 0.8), 1e-5, "t2s")
+    # ragged planes take the generic path, one launch per job: same results
+    r1, r2 = torch.rand(2, 5, 7, 9), torch.rand(2, 5, 3, 11)
+    (g1,) = U.adain_mix_multi([(r1.to(dev), r2.to(dev), 0.5)])
+    assert_close_scaled(g1, R.adain_mix(r1, r2, 0.5), 1e-5, "ragged")
+
+
 # ---------------------------------------------------------------- masks / rectify --------------------
 @pytest.mark.parametrize("cfg", ["C1", "C4"])
 def test_teacher_targets_vs_oracle(dev, cfg):

@@ -27,7 +27,7 @@ Reference name → module here
                                                  as peer-memory kernels over NVLink)
 """
 from ._lib import UdapeError, library_path, load as load_library
-from .adain import (adain, adain_mix, adaptive_instance_normalization, calc_mean_std, calc_style_loss,
+from .adain import (adain, adain_mix, adain_mix_multi, adaptive_instance_normalization, calc_mean_std, calc_style_loss,
                     channel_clamp)
 from .ema import ModelEMA, MultiTensorPlan, OldWeightEMA
 from .heatmap import (draw_labelmap_batched, draw_labelmap_ori, draw_labelmaps_multi, generate_target,
@@ -45,7 +45,7 @@ __version__ = "0.3.0"
 
 __all__ = [
     "UdapeError", "library_path", "load_library",
-    "calc_mean_std", "calc_style_loss", "adaptive_instance_normalization", "adain", "adain_mix", "channel_clamp",
+    "calc_mean_std", "calc_style_loss", "adaptive_instance_normalization", "adain", "adain_mix", "adain_mix_multi", "channel_clamp",
     "get_max_preds", "get_max_preds_torch", "calc_dists", "dist_acc", "accuracy", "pck_counts",
     "accuracy_from_counts", "decode",
     "JointsMSELoss", "ConsLoss", "joints_mse_loss", "cons_loss", "fused_losses",

@@ -50,6 +50,10 @@ class OptHyper(ctypes.Structure):
                 ("step", ctypes.c_int32), ("nesterov", ctypes.c_int32)]
 
 
+class AdainJob(ctypes.Structure):
+    _fields_ = [("content", c_void_p), ("style", c_void_p), ("out", c_void_p), ("alpha_dev", c_void_p), ("alpha", c_float)]
+
+
 class TargetJob(ctypes.Structure):
     _fields_ = [("joints", c_void_p), ("vis", c_void_p), ("target", c_void_p), ("weight", c_void_p),
                 ("hm_w", ctypes.c_int32), ("hm_h", ctypes.c_int32)]
@@ -78,6 +82,7 @@ PROTOTYPES = {
                                    c_void_p]),
     "udape_adain_mix": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p]),
+    "udape_adain_mix_multi": (c_int, [POINTER(AdainJob), c_int, c_int, c_int64, c_int64, c_int64, c_float, c_void_p]),
     "udape_channel_clamp": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),
     "udape_decode": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
@@ -130,7 +135,8 @@ PROTOTYPES = {
     "udape_peer_open": (c_int, [POINTER(ctypes.c_ubyte), POINTER(c_void_p)]),
     "udape_peer_close": (c_int, [c_void_p]),
     "udape_rewarp_fwd": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p, c_int,
-                                 c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+                                 c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
+                                 c_void_p]),
     "udape_rewarp_plan_elems": (c_int64, [c_int64, c_int64, c_int]),
     "udape_rewarp_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int,
                                  c_void_p, c_void_p, c_void_p]),

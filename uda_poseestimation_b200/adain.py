@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["calc_mean_std", "calc_style_loss", "adaptive_instance_normalization", "adain", "adain_mix", "channel_clamp"]
+__all__ = ["calc_mean_std", "calc_style_loss", "adaptive_instance_normalization", "adain", "adain_mix", "adain_mix_multi", "channel_clamp"]
 
 
 def _planes(feat: torch.Tensor, name: str):
@@ -129,6 +129,47 @@ def adain_mix(content_feat: torch.Tensor, style_feat: torch.Tensor, alpha=1.0, e
                                              out.data_ptr(), _lib.stream_ptr(dev))
         _lib.check(st, "adain")
     return out
+
+
+def adain_mix_multi(jobs, eps: float = 1e-5):
+    """Several independent ``adain_mix`` calls of ONE shape and dtype as one launch — the s2t and the t2s direction
+    of a train step (``train_human.py:348-356``).  ``jobs``: sequence of ``(content, style, alpha)`` (alpha: float or
+    1-element float32 CUDA tensor, as in :func:`adain_mix`); returns the list of outputs."""
+    import ctypes
+
+    jobs = list(jobs)
+    if not 1 <= len(jobs) <= 4:
+        raise ValueError("adain_mix_multi: 1..4 jobs")
+    c0, s0, _ = jobs[0]
+    n, c, hw_c = _planes(c0, "adain")
+    _, _, hw_s = _planes(s0, "adain")
+    dev = _lib.require_cuda(*[t for j in jobs for t in j[:2]])
+    code = _lib.float_code(c0)
+    table = (_lib.AdainJob * len(jobs))()
+    outs, keep = [], []
+    for i, (content, style, alpha) in enumerate(jobs):
+        if content.shape != c0.shape or style.shape != s0.shape or content.dtype != c0.dtype or style.dtype != c0.dtype:
+            raise ValueError("adain_mix_multi: every job must have the shapes and dtype of the first")
+        if content.shape[:2] != style.shape[:2]:  # function.py:15
+            raise AssertionError("adain: content and style must agree in N and C")
+        _lib.no_autograd("adain", content, style)
+        content, style = content.contiguous(), style.contiguous()
+        out = torch.empty_like(content)
+        keep += [content, style]
+        table[i].content, table[i].style, table[i].out = content.data_ptr(), style.data_ptr(), out.data_ptr()
+        if isinstance(alpha, torch.Tensor):
+            if not (alpha.is_cuda and alpha.dtype == torch.float32 and alpha.numel() == 1):
+                raise TypeError("adain_mix: a tensor alpha must be a 1-element float32 CUDA tensor")
+            table[i].alpha_dev, table[i].alpha = alpha.data_ptr(), 1.0
+        else:
+            assert 0 <= float(alpha) <= 1  # Style_net.py:164
+            table[i].alpha_dev, table[i].alpha = None, float(alpha)
+        outs.append(out)
+    if n * c > 0:
+        with _lib.on_device(dev):
+            st = _lib.load().udape_adain_mix_multi(table, len(jobs), code, n * c, hw_c, hw_s, float(eps), _lib.stream_ptr(dev))
+        _lib.check(st, "adain")
+    return outs
 
 
 def adaptive_instance_normalization(content_feat: torch.Tensor, style_feat: torch.Tensor) -> torch.Tensor:

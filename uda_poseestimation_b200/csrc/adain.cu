@@ -14,6 +14,8 @@
 //   * block-per-plane (any plane size / alignment): three sweeps over the plane, the
 //     2nd and 3rd served by L1/L2 (a plane is at most a few hundred KB), so DRAM still
 //     sees one read.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace udape {
@@ -91,21 +93,37 @@ mean_std_warp_kernel(const T* __restrict__ feat, T* __restrict__ mean_out, T* __
     }
 }
 
-template <typename T, int J>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
-adain_warp_kernel(const T* __restrict__ content, const T* __restrict__ style, T* __restrict__ out,
-                  int64_t planes, int nvec_c, int nvec_s, int hw_c, int hw_s, float eps,
-                  float alpha, const float* __restrict__ alpha_dev, int mix) {
+// up to UDAPE_MAX_ADAIN_JOBS independent (content, style, alpha) -> out jobs of one shape in ONE launch
+// (blockIdx.y = job): the s2t and t2s directions of a train step (train_human.py:348-356) are independent, and a
+// launch of this size spends ~10 % of its time ramping up and draining — paid once instead of twice.
+struct AdainJobs {
+    const void* content[UDAPE_MAX_ADAIN_JOBS];
+    const void* style[UDAPE_MAX_ADAIN_JOBS];
+    void* out[UDAPE_MAX_ADAIN_JOBS];
+    const float* alpha_dev[UDAPE_MAX_ADAIN_JOBS];
+    float alpha[UDAPE_MAX_ADAIN_JOBS];
+    int mix[UDAPE_MAX_ADAIN_JOBS];
+};
+
+template <typename T, int J, int WPB>
+__global__ void __launch_bounds__(WPB * 32, 24 / WPB)
+adain_warp_kernel(const AdainJobs jobs, int64_t planes, int nvec_c, int nvec_s, int hw_c, int hw_s, float eps) {
     constexpr int EPV = Vec16<T>::EPV;
     const int lane = threadIdx.x & 31;
-    const int64_t plane = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t plane = static_cast<int64_t>(blockIdx.x) * WPB + (threadIdx.x >> 5);
     if (plane >= planes) return;
+    const int job = blockIdx.y;
+    const T* content = static_cast<const T*>(jobs.content[job]);
+    const T* style = static_cast<const T*>(jobs.style[job]);
+    T* out = static_cast<T*>(jobs.out[job]);
+    const float* alpha_dev = jobs.alpha_dev[job];
+    const int mix = jobs.mix[job];
 
     // issue every load of both planes before the first use
     uint4 cv[J], sv[J];
     warp_load_plane<T, J>(content + plane * hw_c, nvec_c, lane, cv);
     warp_load_plane<T, J>(style + plane * hw_s, nvec_s, lane, sv);
-    const float a = alpha_dev ? __ldg(alpha_dev) : alpha;
+    const float a = alpha_dev ? __ldg(alpha_dev) : jobs.alpha[job];
 
     float mean_s, std_s, mean_c, std_c;
     warp_plane_stats<T, J>(sv, nvec_s, hw_s, lane, eps, mean_s, std_s);
@@ -452,36 +470,57 @@ static int launch_mean_std(const void* feat, int64_t planes, int64_t hw, float e
     return check_launch("udape_mean_std");
 }
 
+static int adain_warps_per_block() {
+    const char* e = std::getenv("UDAPE_ADAIN_WARPS");   // tuning: 4 | 8 (default)
+    const int v = e ? std::atoi(e) : 0;
+    return v == 4 ? 4 : 8;
+}
+
+template <typename T, int J>
+static void launch_adain_warp(const AdainJobs& jobs, int n_jobs, int64_t planes, int nvc, int nvs, int ihc, int ihs, float eps,
+                              cudaStream_t st) {
+    const int wpb = adain_warps_per_block();
+    const dim3 grid(static_cast<unsigned>((planes + wpb - 1) / wpb), static_cast<unsigned>(n_jobs));
+    if (wpb == 4) adain_warp_kernel<T, J, 4><<<grid, 4 * 32, 0, st>>>(jobs, planes, nvc, nvs, ihc, ihs, eps);
+    else adain_warp_kernel<T, J, 8><<<grid, 8 * 32, 0, st>>>(jobs, planes, nvc, nvs, ihc, ihs, eps);
+}
+
+// n_jobs jobs of one shape; the register path takes them in one launch, the generic path one launch per job
 template <typename T>
-static int launch_adain(const void* content, const void* style, int64_t planes, int64_t hw_c,
-                        int64_t hw_s, float eps, float alpha, const float* alpha_dev, int mix,
-                        void* out, cudaStream_t st) {
-    const T* c = static_cast<const T*>(content);
-    const T* s = static_cast<const T*>(style);
-    T* o = static_cast<T*>(out);
-    const bool vec_c = plane_vectorizable<T>(content, hw_c) && aligned16(out);
-    const bool vec_s = plane_vectorizable<T>(style, hw_s);
+static int launch_adain(const AdainJobs& jobs, int n_jobs, int64_t planes, int64_t hw_c, int64_t hw_s, float eps, cudaStream_t st) {
+    bool vec_c = true, vec_s = true;
+    for (int i = 0; i < n_jobs; ++i) {
+        vec_c = vec_c && plane_vectorizable<T>(jobs.content[i], hw_c) && aligned16(jobs.out[i]);
+        vec_s = vec_s && plane_vectorizable<T>(jobs.style[i], hw_s);
+    }
     int j = 0;
     if (vec_c && vec_s) {
         const int64_t nv = (hw_c > hw_s ? hw_c : hw_s) / Vec16<T>::EPV;
         j = pick_j(nv);
     }
     if (j) {
-        const unsigned grid = static_cast<unsigned>((planes + kWarpsPerBlock - 1) / kWarpsPerBlock);
         const int nvc = static_cast<int>(hw_c / Vec16<T>::EPV), nvs = static_cast<int>(hw_s / Vec16<T>::EPV);
         const int ihc = static_cast<int>(hw_c), ihs = static_cast<int>(hw_s);
         switch (j) {
-            case 1: adain_warp_kernel<T, 1><<<grid, kWarpsPerBlock * 32, 0, st>>>(c, s, o, planes, nvc, nvs, ihc, ihs, eps, alpha, alpha_dev, mix); break;
-            case 2: adain_warp_kernel<T, 2><<<grid, kWarpsPerBlock * 32, 0, st>>>(c, s, o, planes, nvc, nvs, ihc, ihs, eps, alpha, alpha_dev, mix); break;
-            case 4: adain_warp_kernel<T, 4><<<grid, kWarpsPerBlock * 32, 0, st>>>(c, s, o, planes, nvc, nvs, ihc, ihs, eps, alpha, alpha_dev, mix); break;
-            default: adain_warp_kernel<T, 8><<<grid, kWarpsPerBlock * 32, 0, st>>>(c, s, o, planes, nvc, nvs, ihc, ihs, eps, alpha, alpha_dev, mix); break;
+            case 1: launch_adain_warp<T, 1>(jobs, n_jobs, planes, nvc, nvs, ihc, ihs, eps, st); break;
+            case 2: launch_adain_warp<T, 2>(jobs, n_jobs, planes, nvc, nvs, ihc, ihs, eps, st); break;
+            case 4: launch_adain_warp<T, 4>(jobs, n_jobs, planes, nvc, nvs, ihc, ihs, eps, st); break;
+            default: launch_adain_warp<T, 8>(jobs, n_jobs, planes, nvc, nvs, ihc, ihs, eps, st); break;
         }
     } else {
         const unsigned grid = static_cast<unsigned>(planes);
-        if (vec_c && vec_s) adain_cta_kernel<T, true, true><<<grid, kCtaThreads, 0, st>>>(c, s, o, hw_c, hw_s, eps, alpha, alpha_dev, mix);
-        else if (vec_c) adain_cta_kernel<T, true, false><<<grid, kCtaThreads, 0, st>>>(c, s, o, hw_c, hw_s, eps, alpha, alpha_dev, mix);
-        else if (vec_s) adain_cta_kernel<T, false, true><<<grid, kCtaThreads, 0, st>>>(c, s, o, hw_c, hw_s, eps, alpha, alpha_dev, mix);
-        else adain_cta_kernel<T, false, false><<<grid, kCtaThreads, 0, st>>>(c, s, o, hw_c, hw_s, eps, alpha, alpha_dev, mix);
+        for (int i = 0; i < n_jobs; ++i) {
+            const T* c = static_cast<const T*>(jobs.content[i]);
+            const T* sy = static_cast<const T*>(jobs.style[i]);
+            T* o = static_cast<T*>(jobs.out[i]);
+            const float alpha = jobs.alpha[i];
+            const float* alpha_dev = jobs.alpha_dev[i];
+            const int mix = jobs.mix[i];
+            if (vec_c && vec_s) adain_cta_kernel<T, true, true><<<grid, kCtaThreads, 0, st>>>(c, sy, o, hw_c, hw_s, eps, alpha, alpha_dev, mix);
+            else if (vec_c) adain_cta_kernel<T, true, false><<<grid, kCtaThreads, 0, st>>>(c, sy, o, hw_c, hw_s, eps, alpha, alpha_dev, mix);
+            else if (vec_s) adain_cta_kernel<T, false, true><<<grid, kCtaThreads, 0, st>>>(c, sy, o, hw_c, hw_s, eps, alpha, alpha_dev, mix);
+            else adain_cta_kernel<T, false, false><<<grid, kCtaThreads, 0, st>>>(c, sy, o, hw_c, hw_s, eps, alpha, alpha_dev, mix);
+        }
     }
     return check_launch("udape_adain_mix");
 }
@@ -538,23 +577,43 @@ extern "C" int udape_mean_std_bwd(const void* feat, const void* mean, const void
     return check_launch("udape_mean_std_bwd");
 }
 
+static int adain_entry(const udape_adain_job* in_jobs, int n_jobs, int dtype, int64_t planes, int64_t hw_c, int64_t hw_s,
+                       float eps, void* stream, const char* name) {
+    UDAPE_REQUIRE(in_jobs, UDAPE_ERR_NULL, "%s: jobs is NULL", name);
+    UDAPE_REQUIRE(n_jobs >= 1 && n_jobs <= UDAPE_MAX_ADAIN_JOBS, UDAPE_ERR_ARG, "%s: n_jobs=%d (1..%d)", name, n_jobs, UDAPE_MAX_ADAIN_JOBS);
+    UDAPE_REQUIRE(planes > 0 && hw_c > 0 && hw_s > 0 && planes < (1ll << 31) && hw_c < (1ll << 31) &&
+                      hw_s < (1ll << 31),
+                  UDAPE_ERR_SHAPE, "%s: bad extents planes=%lld hw_c=%lld hw_s=%lld", name,
+                  (long long)planes, (long long)hw_c, (long long)hw_s);
+    const int es = dtype_size(dtype);
+    UDAPE_REQUIRE(es == 2 || es == 4, UDAPE_ERR_DTYPE, "%s: unsupported dtype code %d", name, dtype);
+    AdainJobs jobs = {};
+    for (int i = 0; i < n_jobs; ++i) {
+        const udape_adain_job& j = in_jobs[i];
+        UDAPE_REQUIRE(j.content && j.style && j.out, UDAPE_ERR_NULL, "%s: NULL pointer (job %d)", name, i);
+        UDAPE_REQUIRE(aligned_to(j.content, es) && aligned_to(j.style, es) && aligned_to(j.out, es), UDAPE_ERR_ALIGN,
+                      "%s: pointer not aligned to element size (job %d)", name, i);
+        if (!j.alpha_dev) {
+            // Style_net.py:164 asserts 0 <= alpha <= 1
+            UDAPE_REQUIRE(j.alpha >= 0.0f && j.alpha <= 1.0f, UDAPE_ERR_ARG, "%s: alpha %g outside [0,1]", name, (double)j.alpha);
+        }
+        jobs.content[i] = j.content; jobs.style[i] = j.style; jobs.out[i] = j.out;
+        jobs.alpha_dev[i] = j.alpha_dev; jobs.alpha[i] = j.alpha;
+        jobs.mix[i] = (j.alpha_dev != nullptr) || (j.alpha != 1.0f);
+    }
+    UDAPE_DISPATCH_FLOAT(dtype, T, return launch_adain<T>(jobs, n_jobs, planes, hw_c, hw_s, eps, as_stream(stream)));
+    return UDAPE_OK;
+}
+
 extern "C" int udape_adain_mix(const void* content, const void* style, int dtype, int64_t planes,
                                int64_t hw_c, int64_t hw_s, float eps, float alpha,
                                const float* alpha_dev, void* out, void* stream) {
     UDAPE_REQUIRE(content && style && out, UDAPE_ERR_NULL, "udape_adain_mix: NULL pointer");
-    UDAPE_REQUIRE(planes > 0 && hw_c > 0 && hw_s > 0 && planes < (1ll << 31) && hw_c < (1ll << 31) &&
-                      hw_s < (1ll << 31),
-                  UDAPE_ERR_SHAPE, "udape_adain_mix: bad extents planes=%lld hw_c=%lld hw_s=%lld",
-                  (long long)planes, (long long)hw_c, (long long)hw_s);
-    const int es = dtype_size(dtype);
-    UDAPE_REQUIRE(es == 2 || es == 4, UDAPE_ERR_DTYPE, "udape_adain_mix: unsupported dtype code %d", dtype);
-    UDAPE_REQUIRE(aligned_to(content, es) && aligned_to(style, es) && aligned_to(out, es), UDAPE_ERR_ALIGN,
-                  "udape_adain_mix: pointer not aligned to element size");
-    if (!alpha_dev) {
-        // Style_net.py:164 asserts 0 <= alpha <= 1
-        UDAPE_REQUIRE(alpha >= 0.0f && alpha <= 1.0f, UDAPE_ERR_ARG, "udape_adain_mix: alpha %g outside [0,1]", (double)alpha);
-    }
-    const int mix = (alpha_dev != nullptr) || (alpha != 1.0f);
-    UDAPE_DISPATCH_FLOAT(dtype, T, return launch_adain<T>(content, style, planes, hw_c, hw_s, eps, alpha, alpha_dev, mix, out, as_stream(stream)));
-    return UDAPE_OK;
+    const udape_adain_job job = {content, style, out, alpha_dev, alpha};
+    return adain_entry(&job, 1, dtype, planes, hw_c, hw_s, eps, stream, "udape_adain_mix");
+}
+
+extern "C" int udape_adain_mix_multi(const udape_adain_job* jobs, int n_jobs, int dtype, int64_t planes, int64_t hw_c,
+                                     int64_t hw_s, float eps, void* stream) {
+    return adain_entry(jobs, n_jobs, dtype, planes, hw_c, hw_s, eps, stream, "udape_adain_mix_multi");
 }

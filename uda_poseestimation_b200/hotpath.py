@@ -27,7 +27,7 @@ import torch
 
 from . import _lib
 from . import rewarp as _rewarp
-from .adain import adain_mix
+from .adain import adain_mix, adain_mix_multi
 from .ema import OldWeightEMA
 from .keypoint_detection import _pck
 from .loss import cons_loss, fused_losses, joints_mse_loss
@@ -241,6 +241,7 @@ class HotPathStep:
         # AdaIN launches it would delay them behind the EMA's 13k CTAs: a lower-priority grid that has started
         # is not displaced, measured 188 -> 199 us.)
         self.alpha_feed = None
+        self.adain_one_launch = os.environ.get("UDAPE_ADAIN_ONE_LAUNCH", "1") == "1"
         self.skip = frozenset()   # profiling only (tools/step_probe.py): chains left out of the step
         self.marks = None         # profiling only: list of (name, external timing event) filled while capturing
 
@@ -256,7 +257,8 @@ class HotPathStep:
         fused: 2 adain, decode (+ k-th select in its last CTA), loss_step, pck, ema;  unfused: 2 adain,
         decode+rectify(+select), mse fwd/bwd, cons fwd/bwd, pck, ema;  + 4 with the re-warp tables (teacher forward,
         student forward, its inverse plan, student backward)."""
-        return (6 if self.fused else 9) + self.rewarp_kernels + (self.tail.kernels - 1 if self.tail is not None else 0)
+        return ((6 if self.fused else 9) + self.rewarp_kernels + (self.tail.kernels - 1 if self.tail is not None else 0)
+                - (1 if self.adain_one_launch else 0))
 
     def _streams(self, dev):
         if self._side is None or self._side[0].device != dev:
@@ -393,9 +395,14 @@ class HotPathStep:
         # streams of one priority, so that the second fills the first one's last partial wave: no change, 180.8 vs 180.1 us)
         if "adain" not in self.skip:
             with torch.cuda.stream(s_adain), torch.no_grad():
-                t_s2t = adain_mix(inp.feat_src, inp.feat_tgt_ori, inp.alpha_s2t)
-                self._mark("adain s2t done")
-                t_t2s = adain_mix(inp.feat_tgt_tea, inp.feat_src_ori, inp.alpha_t2s)
+                if self.adain_one_launch and inp.feat_src.shape == inp.feat_tgt_tea.shape:
+                    # both directions are independent: one launch pays the ramp-up / drain of a launch once
+                    t_s2t, t_t2s = adain_mix_multi([(inp.feat_src, inp.feat_tgt_ori, inp.alpha_s2t),
+                                                    (inp.feat_tgt_tea, inp.feat_src_ori, inp.alpha_t2s)])
+                else:
+                    t_s2t = adain_mix(inp.feat_src, inp.feat_tgt_ori, inp.alpha_s2t)
+                    self._mark("adain s2t done")
+                    t_t2s = adain_mix(inp.feat_tgt_tea, inp.feat_src_ori, inp.alpha_t2s)
                 self._mark("adain t2s done")
                 if self.alpha_feed is not None:
                     self.alpha_feed()
