@@ -169,3 +169,78 @@ def test_step_bytes_accounting(dev):
         assert by["total"] == sum(v for k_, v in by.items() if k_ != "total")
     assert by["ema"] == 12000 and by["adain_mix"] == 2 * 3 * inp.feat_src.numel() * 4
     assert by["total"] == sum(v for k_, v in by.items() if k_ != "total")
+
+
+def _c2_inputs(dev, seed=41, k_views=2):
+    """BASELINE.json configs[1] shapes (batch 32, 16 keypoints; 512x32x32 features are cut to 64 channels to keep
+    the CPU oracle quick — planes are independent, the full tensor is covered by test_gpu_oracle), k teacher views
+    each with its own augmentation, and the student's target images for the occlusion stage."""
+    b, k = S.CONFIGS["C2"]["batch"], S.CONFIGS["C2"]["joints"]
+    host, inp = _inputs(dev, b=b, k=k, n_feat_c=64, seed=seed, rewarp=True)
+    # peaks up to 2.4: the mean over two views that disagree on the position still clears occlude_thresh = 0.9 somewhere
+    views = [S.heatmaps(b, k, seed + 20 + v, peak=(1.0, 2.4)) for v in range(k_views)]
+    augs = [S.aug_params(b, seed + 30 + v) for v in range(k_views)]
+    host["y_t_teas"], host["aug_teas"] = views, augs
+    inp.y_t_tea = [v.to(dev) for v in views]
+    inp.theta_tea = [RW.stage_table(RW.recon_stages(a, 4.0, b), 64, 64, torch.float32, None)[0].to(dev) for a in augs]
+    g = torch.Generator().manual_seed(seed + 40)
+    host["x_t_stu"] = torch.randn(b, 3, 256, 256, generator=g)
+    return host, inp
+
+
+def _oracle_c2(host, a1, a2, teacher, student, occlusion_seed=None):
+    h = dict(host)
+    h["y_t_tea"] = R.teacher_recon(host["y_t_teas"], host["aug_teas"], 4.0)      # train_human.py:359-372, k views
+    h.pop("aug_tea", None)
+    ref = _oracle_step(h, a1, a2, teacher, student)
+    if occlusion_seed is not None:
+        ref["x_t_stu"] = R.occlude_keypoints(host["x_t_stu"], ref["conf_table"], ref["position"].numpy(), host["aug_stu"], 4.0,
+                                             0.5, 10, 256, rng=np.random.RandomState(occlusion_seed))    # :385-412
+    return ref
+
+
+def test_step_at_c2_size_with_k2_views_and_occlusion_eager(dev):
+    """One eager step at the BASELINE config's batch / keypoint count with k = 2 teacher views (mean over the
+    re-warped views) and the occlusion paste driven by the reference's np.random draws."""
+    host, inp = _c2_inputs(dev)
+    inp.x_t_stu, inp.aug_param_stu = host["x_t_stu"].to(dev), host["aug_stu"]
+    shapes = [(64, 3, 7, 7), (64,), (17,), (256, 64, 1, 1), (5000,)]
+    s_cpu, t_cpu = S.parameter_list(shapes, 1), S.parameter_list(shapes, 2)
+    student, teacher = Bag(s_cpu).to(dev), Bag(t_cpu).to(dev)
+    step = HotPathStep(teacher, student, sigma=2, rng=np.random.RandomState(77))
+    R.ema_init(t_cpu, s_cpu)
+    out = step.run(inp)
+    torch.cuda.synchronize()
+    ref = _oracle_c2(host, 0.3, 0.8, t_cpu, s_cpu, occlusion_seed=77)
+    _check(out, ref)
+    assert out["x_t_stu"] is not None and not torch.equal(out["x_t_stu"].cpu(), host["x_t_stu"]), "no sample was occluded"
+    assert torch.equal(out["x_t_stu"].cpu(), ref["x_t_stu"])                     # gather + paste: bit-exact
+    for p, e in zip(teacher.parameters(), t_cpu):
+        assert torch.equal(p.detach().cpu(), e)
+
+
+def test_step_at_c2_size_with_k2_views_graph(dev):
+    """The same step (without the host-driven occlusion stage) captured once and replayed with new inputs."""
+    host, inp = _c2_inputs(dev, seed=43)
+    shapes = [(128, 64, 3, 3), (128,), (33,)]
+    s_cpu, t_cpu = S.parameter_list(shapes, 3), S.parameter_list(shapes, 4)
+    student, teacher = Bag(s_cpu).to(dev), Bag(t_cpu).to(dev)
+    step = HotPathStep(teacher, student, sigma=2)
+    R.ema_init(t_cpu, s_cpu)
+    step.capture(inp, include_ema=True, warmup=2)
+    for _ in range(2):
+        R.ema_step(t_cpu, s_cpu, 0.999)
+    b = S.CONFIGS["C2"]["batch"]
+    for rep in range(2):
+        host["y_t_teas"] = [torch.roll(v, rep + 1, dims=0) for v in host["y_t_teas"]]
+        for dst, src in zip(inp.y_t_tea, host["y_t_teas"]):
+            dst.copy_(src)
+        host["aug_teas"] = [S.aug_params(b, 500 + 10 * rep + v) for v in range(2)]
+        for dst, a in zip(inp.theta_tea, host["aug_teas"]):
+            dst.copy_(RW.stage_table(RW.recon_stages(a, 4.0, b), 64, 64, torch.float32, None)[0])
+        out = step.replay()
+        torch.cuda.synchronize()
+        ref = _oracle_c2(host, 0.3, 0.8, t_cpu, s_cpu)
+        _check(out, ref)
+        for p, e in zip(teacher.parameters(), t_cpu):
+            assert torch.equal(p.detach().cpu(), e)

@@ -702,21 +702,31 @@ rewarp_inverse_plan_kernel(const RewarpArgs a, uint16_t* __restrict__ plan, int 
 // Here the index arithmetic is a launch of its own with one pixel per thread (B * HW / 256 CTAs), and the
 // gather / the plan builder read the finished map from global memory (L2-resident: 8 KB per sample), so their
 // CTAs are small, plane-granular and plentiful.
+constexpr int kMapPx = 8;   // consecutive pixels per thread: the stage table is loaded and the variant dispatched once per 8
 __global__ void __launch_bounds__(kRwThreads)
 rewarp_map_kernel(const RewarpArgs a, uint16_t* __restrict__ pix) {
     __shared__ float s_theta[kRwMaxStages * 6];
     const int hw = a.H * a.W;
-    const int bands = (hw + kRwThreads - 1) / kRwThreads;
+    const int bands = (hw + kRwThreads * kMapPx - 1) / (kRwThreads * kMapPx);
     const int b = blockIdx.x / bands, band = blockIdx.x - b * bands;
     if (threadIdx.x < a.stages * 6)
         s_theta[threadIdx.x] = a.view[0].theta[static_cast<int64_t>(b) * a.stages * 6 + threadIdx.x];
     __syncthreads();
-    const int p = band * kRwThreads + threadIdx.x;
-    if (p >= hw) return;
+    const int p0 = (band * kRwThreads + threadIdx.x) * kMapPx;
+    if (p0 >= hw) return;     // (hw % 8 == 0 on this route)
     StageRegs R;
     load_stages(R, s_theta, a.stages);
-    int j = p / a.W, i = p - j * a.W;
-    pix[static_cast<int64_t>(b) * hw + p] = composed_source_ij(i, j, R, a) ? static_cast<uint16_t>(j * a.W + i) : 0xffffu;
+    int j0 = p0 / a.W, i0 = p0 - j0 * a.W;
+    uint32_t w[kMapPx / 2];
+#pragma unroll
+    for (int e = 0; e < kMapPx; ++e) {
+        int i = i0, j = j0;
+        const uint32_t sp = composed_source_ij(i, j, R, a) ? static_cast<uint32_t>(j * a.W + i) : 0xffffu;
+        if (e & 1) w[e >> 1] |= sp << 16;
+        else w[e >> 1] = sp;
+        if (++i0 == a.W) { i0 = 0; ++j0; }
+    }
+    *reinterpret_cast<uint4*>(pix + static_cast<int64_t>(b) * hw + p0) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 // gather of `cpc` consecutive planes of one sample from the finished map.  dynamic smem: kRwRing plane buffers
@@ -754,6 +764,7 @@ rewarp_gather_map_kernel(const RewarpArgs a, const uint16_t* __restrict__ pix, T
     }
     // padded byte offsets of this thread's pixels (words t + 256*slot of the plane), two per register
     const uint16_t* mp = pix + static_cast<int64_t>(b) * hw;
+    const int wlog = (a.W & (a.W - 1)) == 0 ? 31 - __clz(a.W) : -1;   // power-of-two rows: a shift instead of a division
     uint32_t idx[kRwPix / 2];
 #pragma unroll
     for (int sl = 0; sl < SLOTS; ++sl) {
@@ -766,7 +777,7 @@ rewarp_gather_map_kernel(const RewarpArgs a, const uint16_t* __restrict__ pix, T
                 const uint32_t sp = EPW == 2 ? ((__ldg(reinterpret_cast<const uint32_t*>(mp) + word) >> (16 * e)) & 0xffffu)
                                              : static_cast<uint32_t>(__ldg(mp + word));
                 if (sp != 0xffffu) {
-                    const uint32_t row = sp / static_cast<uint32_t>(a.W);
+                    const uint32_t row = wlog >= 0 ? sp >> wlog : sp / static_cast<uint32_t>(a.W);
                     o = row * static_cast<uint32_t>(stride) * 4u + (sp - row * a.W) * static_cast<uint32_t>(sizeof(T));
                 }
             }
@@ -1159,7 +1170,7 @@ static int reserve_smem(K kernel, size_t bytes, const char* name) {
 static int64_t bwd_ctas_per_sm() {
     const char* e = std::getenv("UDAPE_REWARP_BWD_CTAS");   // tuning
     const int v = e ? std::atoi(e) : 0;
-    return v > 0 ? v : 6;
+    return v > 0 ? v : 12;   // C5 (5376 planes): 85 / 72 / 66 us for 3 / 6 / 12 CTAs per SM worth of CTAs
 }
 
 constexpr int kRwDeepRing = 6;   // single view, a CTA that owns >= 6 planes
@@ -1216,7 +1227,7 @@ extern "C" int udape_rewarp_fwd(const void* const* in, const float* const* theta
         (!out || buf_words) && aligned16(map_ws) && (!inverse_plan || aligned16(inverse_plan))) {
         // map route: index arithmetic once per sample in its own launch, then plane-granular CTAs
         const int bw = smem_route_words(H, W, es);
-        const int64_t bands = (hw + kRwThreads - 1) / kRwThreads;
+        const int64_t bands = (hw + kRwThreads * kMapPx - 1) / (kRwThreads * kMapPx);
         rewarp_map_kernel<<<static_cast<unsigned>(B * bands), kRwThreads, 0, st>>>(a, map_ws);
         if (inverse_plan) {
             const size_t smem = sizeof(uint16_t) * (((hw + 8 + 7) & ~7ll) + 2 * ((hw + 7) & ~7ll));

@@ -155,18 +155,34 @@ class StepInputs:
     feat_src_ori: torch.Tensor  # [N,512,32,32] relu4_1(x_s_ori)        style of t2s
     y_s: torch.Tensor           # [B,K,64,64] student(x_s)      fp16 under autocast
     y_t_stu: torch.Tensor       # [B,K,64,64] student(x_t_stu)  fp16 under autocast (re-warped)
-    y_t_tea: torch.Tensor       # [B,K,64,64] teacher(x_t_tea)  fp32 (re-warped, averaged over k views)
+    y_t_tea: torch.Tensor       # [B,K,64,64] teacher(x_t_tea)  fp32 — or a list of k views (train_human.py:358,361:
+                                # every view is re-warped with its own table and the views are averaged)
     label_s: torch.Tensor       # [B,K,64,64] fp32 Gaussian target
     weight_s: torch.Tensor      # [B,K,1]     fp32 visibility weight
     alpha_s2t: torch.Tensor     # [1] fp32 device scalar
     alpha_t2s: torch.Tensor     # [1] fp32 device scalar
     # re-warp stage tables (rewarp.stage_table of the batch's aug_param_tea / aug_param_stu, float32
     # [B,3,6] on the device, refreshed per step).  None: y_t_tea / y_t_stu are taken as already re-warped.
-    theta_tea: torch.Tensor | None = None
+    theta_tea: torch.Tensor | None = None      # one table, or a list of k tables when y_t_tea is a list of views
     theta_stu: torch.Tensor | None = None
+    # occlusion (train_human.py:385-412; eager runs only — it needs the host's np.random stream, like the reference):
+    # the student's target images and the collated meta['aug_param_stu'] of the batch
+    x_t_stu: torch.Tensor | None = None        # [B,3,256,256]
+    aug_param_stu: list | None = None
 
     def tensors(self):
-        return [getattr(self, f.name) for f in dataclasses.fields(self) if getattr(self, f.name) is not None]
+        out = []
+        for f in dataclasses.fields(self):
+            v = getattr(self, f.name)
+            if torch.is_tensor(v):
+                out.append(v)
+            elif isinstance(v, (list, tuple)) and v and all(torch.is_tensor(t) for t in v):
+                out.extend(v)
+        return out
+
+    @property
+    def teacher_views(self):
+        return list(self.y_t_tea) if isinstance(self.y_t_tea, (list, tuple)) else [self.y_t_tea]
 
 
 def step_algorithmic_bytes(inp: StepInputs, n_params: int, param_bytes: int = 4, fused: bool = True, tail=None) -> dict:
@@ -177,8 +193,9 @@ def step_algorithmic_bytes(inp: StepInputs, n_params: int, param_bytes: int = 4,
     ``tail``: the ReplicatedTail / PeerTail of the step (its kernels replace the bare EMA pass)."""
     ef = inp.feat_src.element_size()
     feat = inp.feat_src.numel() * ef
-    hm = inp.y_t_tea.numel()
-    e_s, e_t, e_l = inp.y_s.element_size(), inp.y_t_tea.element_size(), inp.label_s.element_size()
+    tea0 = inp.teacher_views[0]
+    hm = tea0.numel()
+    e_s, e_t, e_l = inp.y_s.element_size(), tea0.element_size(), inp.label_s.element_size()
     planes = inp.y_s.shape[0] * inp.y_s.shape[1]
     out = {
         "adain_mix": 2 * 3 * feat,                        # two directions x (2 reads + 1 write)
@@ -202,7 +219,8 @@ def step_algorithmic_bytes(inp: StepInputs, n_params: int, param_bytes: int = 4,
         out["cons_fwd"] = hm * (e_s + e_t) + 4 * planes
         out["cons_bwd"] = hm * (e_s + e_t) + hm * e_s
     if inp.theta_tea is not None:
-        out["rewarp_teacher"] = 2 * hm * e_t + 72 * inp.y_t_tea.shape[0]       # 1 read + 1 write (+ the stage table)
+        k_views = len(inp.teacher_views)
+        out["rewarp_teacher"] = (k_views + 1) * hm * e_t + 72 * k_views * tea0.shape[0]   # k reads + 1 write (+ the stage tables)
     if inp.theta_stu is not None:
         out["rewarp_student_fwd"] = 2 * hm * e_s + 72 * inp.y_t_stu.shape[0]
         out["rewarp_student_bwd"] = 2 * hm * e_s + 72 * inp.y_t_stu.shape[0]   # grad read + grad write
@@ -216,7 +234,8 @@ class HotPathStep:
     def __init__(self, teacher: torch.nn.Module, student: torch.nn.Module, sigma=2, mask_ratio: float = 0.5,
                  occlude_thresh: float = 0.9, teacher_alpha: float = 0.999, lambda_c: float = 1.0,
                  loss_scale: float = 65536.0, parallel: bool = True, fused: bool = True,
-                 ema_parallel: bool = True, counts_hook=None, tail=None, ema: OldWeightEMA | None = None):
+                 ema_parallel: bool = True, counts_hook=None, tail=None, ema: OldWeightEMA | None = None,
+                 occlude_rate: float = 0.5, occlude_size: int = 10, image_size: int = 256, rng=None):
         self.sigma, self.mask_ratio, self.occlude_thresh = sigma, mask_ratio, occlude_thresh
         self.lambda_c, self.loss_scale = lambda_c, loss_scale
         self.parallel, self.fused, self.ema_parallel = parallel, fused, ema_parallel
@@ -224,6 +243,8 @@ class HotPathStep:
         # stream: the data-parallel integer all-reduce (dist.allreduce_counts) goes here so that it
         # overlaps the AdaIN / EMA chains instead of trailing the step
         self.counts_hook = counts_hook
+        self.occlude_rate, self.occlude_size, self.image_size = occlude_rate, occlude_size, image_size
+        self.rng = rng          # np.random-like stream of the occlusion draws (None: numpy's global one, as the reference)
         self._side = None
         # tail: what follows backward — None: the bare EMA (:438, the student update left to torch);
         # ReplicatedTail / PeerTail: gradient exchange + unscale + Adam | SGD + EMA (:436-438)
@@ -309,7 +330,8 @@ class HotPathStep:
                     self.ema.step()
                     self._mark("ema done")
         # teacher forward; student forward + inverse plan + backward
-        self.rewarp_kernels = (1 if inp.theta_tea is not None else 0) + (3 if inp.theta_stu is not None else 0)
+        self.rewarp_kernels = ((1 if inp.theta_tea is not None else 0) + (3 if inp.theta_stu is not None else 0)
+                               + (1 if inp.x_t_stu is not None else 0))
         # the student's grids are built under autocast (:414): every stage samples on a half grid
         stu_half = inp.y_t_stu.dtype in (torch.float16, torch.bfloat16)
         stu_mask = (1 << inp.theta_stu.shape[1]) - 1 if (inp.theta_stu is not None and stu_half) else 0
@@ -338,16 +360,31 @@ class HotPathStep:
                     recon_ready.record(s_stu)
         with torch.cuda.stream(s_tea):
             with torch.no_grad():
-                y_t_tea = inp.y_t_tea
+                views = inp.teacher_views
+                y_t_tea = views[0]
                 if inp.theta_tea is not None:
-                    # :359-372 — teacher heatmaps warped back to the un-augmented frame (k = 1 view)
+                    # :359-372 — every teacher view warped back to the un-augmented frame, mean over the k views
                     self._mark("tea gather start")
-                    y_t_tea = _rewarp.gather(inp.y_t_tea, inp.theta_tea)
+                    if len(views) == 1:
+                        y_t_tea = _rewarp.gather(views[0], inp.theta_tea if torch.is_tensor(inp.theta_tea) else inp.theta_tea[0])
+                    else:
+                        y_t_tea = _rewarp.gather_views(views, list(inp.theta_tea))
                     self._mark("tea gather done")
+                elif len(views) > 1:
+                    raise ValueError("k teacher views need their re-warp tables (theta_tea: one per view)")
                 # train_human.py:376-383 and :427-430 — one decode pass + k-th value select
                 tt = teacher_targets(y_t_tea, self.sigma, self.mask_ratio, occlude_thresh=self.occlude_thresh,
                                      materialise=not self.fused)
                 self._mark("decode+mask done")
+                x_t_stu_occ = None
+                if inp.x_t_stu is not None and not torch.cuda.is_current_stream_capturing():
+                    # :385-412 — a random patch pasted over one confident keypoint of the student's target image (the
+                    # student network runs on the result).  conf_table / position go to the host for the reference's
+                    # np.random draws, so this stage exists in eager runs only; a captured step ends before it.
+                    x_t_stu_occ = _rewarp.occlude_keypoints(inp.x_t_stu, tt["conf_table"], tt["position"], inp.aug_param_stu,
+                                                            self.image_size / y_t_tea.shape[-1], self.occlude_rate,
+                                                            self.occlude_size, self.image_size,
+                                                            **({"rng": self.rng} if self.rng is not None else {}))
                 if recon_ready is not None:
                     s_tea.wait_event(recon_ready)
                 if self.fused:
@@ -432,7 +469,7 @@ class HotPathStep:
                     tea_mask=tt["tea_mask"], mask_thresh=tt["mask_thresh"], rectified=tt["rectified"],
                     tea_preds=tt["preds"], loss_s=loss_s, loss_c=loss_c, loss_all=loss_all,
                     grad_y_s=g_s, grad_y_t_stu=g_c, grad_y_t_stu_recon=g_recon, y_t_tea_recon=y_t_tea,
-                    y_t_stu_recon=y_t_stu_recon, pck_counts=counts, pred=pred)
+                    y_t_stu_recon=y_t_stu_recon, pck_counts=counts, pred=pred, x_t_stu=x_t_stu_occ)
 
     def _tail_or_ema(self):
         if self.tail is not None:

@@ -33,7 +33,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["inverse_affine_matrix", "recon_stages", "stage_table", "gather", "gather_backward", "inverse_plan_buffer", "student_recon", "teacher_recon",
+__all__ = ["inverse_affine_matrix", "recon_stages", "stage_table", "gather", "gather_views", "gather_backward", "inverse_plan_buffer", "student_recon", "teacher_recon",
            "affine_nearest", "occlusion_plan", "occlude_keypoints"]
 
 
@@ -246,6 +246,23 @@ def gather(y: torch.Tensor, theta: torch.Tensor, half_mask: int = 0, grid_dtype:
     if y.requires_grad and torch.is_grad_enabled():
         return _Rewarp.apply(y, theta, half_mask, grid_code)
     return _launch_fwd([y], [theta], half_mask, grid_code, torch.empty_like(y), plan=plan)
+
+
+def gather_views(views: Sequence[torch.Tensor], thetas: Sequence[torch.Tensor], half_mask: int = 0,
+                 grid_dtype: torch.dtype | None = None) -> torch.Tensor:
+    """Mean over ``k`` views of ``gather(view_i, theta_i)`` in one launch (``teacher_recon`` with device stage
+    tables: graph-capturable, the tables can be refreshed between replays).  Forward only."""
+    if len(views) != len(thetas) or not (1 <= len(views) <= 4):
+        raise ValueError("gather_views: one stage table per view, 1 to 4 views")
+    _lib.require_cuda(*views, *thetas)
+    _lib.no_autograd("gather_views", *views)
+    vs = [v.detach().contiguous() for v in views]
+    if any(v.shape != vs[0].shape or v.dtype != vs[0].dtype for v in vs):
+        raise ValueError("gather_views: all views must share shape and dtype")
+    for v, t in zip(vs, thetas):
+        _check_theta(v, t)
+    grid_code = _lib._DTYPE_CODE[grid_dtype] if grid_dtype is not None else _lib.F16
+    return _launch_fwd(vs, [t.contiguous() for t in thetas], half_mask, grid_code, torch.empty_like(vs[0]))
 
 
 def student_recon(y_t_stu: torch.Tensor, aug_param_stu, ratio: float, autocast="auto") -> torch.Tensor:
