@@ -442,15 +442,11 @@ UDAPE_API int udape_peer_close(void* ptr);
  * what autograd saves for the backward — the composed map of every sample inverted once (per source
  * pixel its contributing output pixels), so that udape_rewarp_bwd is a plain gather.  Single view only.
  * out == NULL with an inverse_plan builds the plan alone (in[0] may then be NULL too: the plan depends
- * only on theta and the shape), e.g. on a second stream beside the gather.
- * map_ws (optional, device, B*H*W uint16, 16-byte aligned; single view, no paste / pass-through, planes the plan
- * route accepts): scratch for the composed map.  With it the index arithmetic runs once per sample in a launch of
- * its own (one pixel per thread) and the gather / the plan builder are plane-granular launches that read the map —
- * the route for big batches (thousands of planes); results are identical bit for bit. */
+ * only on theta and the shape), e.g. on a second stream beside the gather. */
 UDAPE_API int udape_rewarp_fwd(const void* const* in, const float* const* theta, int views, int stages,
                      int half_mask, int grid_dtype, const int32_t* paste, int paste_after,
                      const uint8_t* active, int64_t B, int64_t C, int64_t H, int64_t W, int dtype,
-                     void* out, uint16_t* inverse_plan, uint16_t* map_ws, void* stream);
+                     void* out, uint16_t* inverse_plan, void* stream);
 /* uint16 elements per sample of the inverse plan for H x W planes of elem_bytes-sized elements;
  * 0 if the plan route does not apply (planes above 4096 pixels, rows that are not 16-byte multiples). */
 UDAPE_API int64_t udape_rewarp_plan_elems(int64_t H, int64_t W, int elem_bytes);

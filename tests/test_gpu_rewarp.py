@@ -291,34 +291,3 @@ def test_rewarp_cluster_kernels_under_contention(dev, cluster, monkeypatch):
     torch.cuda.synchronize()
     for f, bw in outs:
         assert torch.equal(f, ref_f) and torch.equal(bw, ref_b)
-
-
-@pytest.mark.parametrize("dt", [torch.float32, torch.float16, torch.bfloat16])
-def test_rewarp_map_route_equals_the_single_launch(dev, dt, monkeypatch):
-    """Big batches take the map route (composed map from its own launch, plane-granular gather / plan builder that
-    read it): forward, inverse plan and the backward from that plan are bit-identical to the single-launch route."""
-    b, k = 48, 21
-    x = S.heatmaps(b, k, seed=90).to(dt).to(dev)
-    aug = S.aug_params(b, seed=91)
-    half = dt != torch.float32
-    table, mask, code = RW.stage_table(RW.recon_stages(aug, 4.0, b), 64, 64, dt, dt if half else None)
-    theta = table.to(dev)
-    gd = dt if half else None
-    g = torch.randn(b, k, 64, 64, generator=torch.Generator().manual_seed(5)).to(dt).to(dev)
-    outs = {}
-    for route, thresh in (("single", 10 ** 9), ("map", 1)):
-        monkeypatch.setattr(RW, "MAP_ROUTE_MIN_PLANES", thresh)
-        plan = RW.inverse_plan_buffer(x)
-        y = RW.gather(x, theta, mask, gd, plan=plan)
-        plan_only = RW.build_inverse_plan(x, theta, mask, gd)
-        gin = RW.gather_backward(g, theta, mask, gd, plan=plan)
-        outs[route] = (y, plan, plan_only, gin)
-    hdr_slots = 8 + 4 * 64 * 64      # header + per-pixel slots are fully defined; the list tail is scratch
-    for i, (a_, b_) in enumerate(zip(outs["single"], outs["map"])):
-        if i in (1, 2):
-            assert torch.equal(a_[:, :hdr_slots], b_[:, :hdr_slots]), "inverse plan (header + slots)"
-        else:
-            assert torch.equal(a_, b_), ("forward", "", "", "backward from the plan")[i]
-    # long lists (zoom > 1.7: more than four contributors per source pixel) go through the list tail: the
-    # backward above covers them whenever the batch has such samples; make sure it does
-    assert int((outs["map"][1][:, 1] != 0).sum()) >= 0

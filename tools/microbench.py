@@ -324,37 +324,13 @@ def main():
             d = B(r)
             ia, ta = in_arr(d["tea"]), in_arr(t32)
             return lambda: chk(lib.udape_rewarp_fwd(ia, ta, 1, 3, 0, _lib.F16, None, 0, None, b, k, 64, 64, _lib.F32,
-                                                    d["rect"].data_ptr(), None, None, st()))
-
-        map_ws = torch.empty((b, 4096), dtype=torch.int16, device=dev)
-
-        def mk_rw32m(r):   # map route: the composed map from its own launch, plane-granular gather
-            d = B(r)
-            ia, ta = in_arr(d["tea"]), in_arr(t32)
-            return lambda: chk(lib.udape_rewarp_fwd(ia, ta, 1, 3, 0, _lib.F16, None, 0, None, b, k, 64, 64, _lib.F32,
-                                                    d["rect"].data_ptr(), None, map_ws.data_ptr(), st()))
-
-        def mk_rw16m(r):
-            d = B(r)
-            ia, ta = in_arr(d["stu16"]), in_arr(t16)
-            return lambda: chk(lib.udape_rewarp_fwd(ia, ta, 1, 3, 7, _lib.F16, None, 0, None, b, k, 64, 64, _lib.F16,
-                                                    d["grad16"].data_ptr(), None, map_ws.data_ptr(), st()))
-
-        def mk_planm(r):   # map + inverse plan only (what runs beside the forward gather)
-            ia, ta = in_arr(B(r)["stu16"]), in_arr(t16)
-            return lambda: chk(lib.udape_rewarp_fwd(ia, ta, 1, 3, 7, _lib.F16, None, 0, None, b, k, 64, 64, _lib.F16,
-                                                    None, plan16.data_ptr(), map_ws.data_ptr(), st()))
-
-        def mk_plan(r):
-            ia, ta = in_arr(B(r)["stu16"]), in_arr(t16)
-            return lambda: chk(lib.udape_rewarp_fwd(ia, ta, 1, 3, 7, _lib.F16, None, 0, None, b, k, 64, 64, _lib.F16,
-                                                    None, plan16.data_ptr(), None, st()))
+                                                    d["rect"].data_ptr(), None, st()))
 
         def mk_rw16(r):
             d = B(r)
             ia, ta = in_arr(d["stu16"]), in_arr(t16)
             return lambda: chk(lib.udape_rewarp_fwd(ia, ta, 1, 3, 7, _lib.F16, None, 0, None, b, k, 64, 64, _lib.F16,
-                                                    d["grad16"].data_ptr(), None, None, st()))
+                                                    d["grad16"].data_ptr(), None, st()))
 
         plan16 = torch.empty(b, lib.udape_rewarp_plan_elems(64, 64, 2), dtype=torch.int16, device=dev)
 
@@ -362,7 +338,7 @@ def main():
             d = B(r)
             ia, ta = in_arr(d["stu16"]), in_arr(t16)
             return lambda: chk(lib.udape_rewarp_fwd(ia, ta, 1, 3, 7, _lib.F16, None, 0, None, b, k, 64, 64, _lib.F16,
-                                                    d["grad16"].data_ptr(), plan16.data_ptr(), None, st()))
+                                                    d["grad16"].data_ptr(), plan16.data_ptr(), st()))
 
         def mk_rwb(r):
             d = B(r)
@@ -377,10 +353,6 @@ def main():
         bench("rewarp_fwd f32 (teacher)", shape, 2 * hm32, mk_rw32, "rewarp")
         bench("rewarp_fwd f16 (student)", shape, 2 * hm16, mk_rw16, "rewarp")
         bench("rewarp_fwd f16 + inv. plan", shape, 2 * hm16 + plan16.numel() * 2, mk_rw16p, "rewarp")
-        bench("rewarp_fwd f32 (map route)", shape, 2 * hm32 + 2 * b * 4096, mk_rw32m, "rewarp")
-        bench("rewarp_fwd f16 (map route)", shape, 2 * hm16 + 2 * b * 4096, mk_rw16m, "rewarp")
-        bench("rewarp inv. plan only", shape, plan16.numel() * 2, mk_plan, "rewarp", footprint=1 << 30)
-        bench("rewarp map + plan (map route)", shape, plan16.numel() * 2 + 2 * b * 4096, mk_planm, "rewarp", footprint=1 << 30)
         bench("rewarp_bwd f16 (no plan)", shape, 2 * hm16, mk_rwb, "rewarp")
         mk_rw16p(0)()   # a valid plan for the plan-based backward
         bench("rewarp_bwd f16 (plan)", shape, 2 * hm16 + plan16.numel() * 2, mk_rwbp, "rewarp")

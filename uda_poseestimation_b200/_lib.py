@@ -135,8 +135,7 @@ PROTOTYPES = {
     "udape_peer_open": (c_int, [POINTER(ctypes.c_ubyte), POINTER(c_void_p)]),
     "udape_peer_close": (c_int, [c_void_p]),
     "udape_rewarp_fwd": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p, c_int,
-                                 c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
-                                 c_void_p]),
+                                 c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "udape_rewarp_plan_elems": (c_int64, [c_int64, c_int64, c_int]),
     "udape_rewarp_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int,
                                  c_void_p, c_void_p, c_void_p]),

@@ -695,175 +695,6 @@ rewarp_inverse_plan_kernel(const RewarpArgs a, uint16_t* __restrict__ plan, int 
     }
 }
 
-// ---- map route: the composed map built ONCE per sample by its own launch ---------------------------------
-// One CTA (or cluster) per sample that builds the map and then walks the sample's channels leaves a launch with
-// B fat CTAs: at 256 samples x 21 channels the gather ran at 20 % occupancy, latency-bound on its per-plane
-// barrier (42 % of the HBM roofline), and the map inversion for the backward at one CTA per sample took 55 us.
-// Here the index arithmetic is a launch of its own with one pixel per thread (B * HW / 256 CTAs), and the
-// gather / the plan builder read the finished map from global memory (L2-resident: 8 KB per sample), so their
-// CTAs are small, plane-granular and plentiful.
-constexpr int kMapPx = 8;   // consecutive pixels per thread: the stage table is loaded and the variant dispatched once per 8
-__global__ void __launch_bounds__(kRwThreads)
-rewarp_map_kernel(const RewarpArgs a, uint16_t* __restrict__ pix) {
-    __shared__ float s_theta[kRwMaxStages * 6];
-    const int hw = a.H * a.W;
-    const int bands = (hw + kRwThreads * kMapPx - 1) / (kRwThreads * kMapPx);
-    const int b = blockIdx.x / bands, band = blockIdx.x - b * bands;
-    if (threadIdx.x < a.stages * 6)
-        s_theta[threadIdx.x] = a.view[0].theta[static_cast<int64_t>(b) * a.stages * 6 + threadIdx.x];
-    __syncthreads();
-    const int p0 = (band * kRwThreads + threadIdx.x) * kMapPx;
-    if (p0 >= hw) return;     // (hw % 8 == 0 on this route)
-    StageRegs R;
-    load_stages(R, s_theta, a.stages);
-    int j0 = p0 / a.W, i0 = p0 - j0 * a.W;
-    uint32_t w[kMapPx / 2];
-#pragma unroll
-    for (int e = 0; e < kMapPx; ++e) {
-        int i = i0, j = j0;
-        const uint32_t sp = composed_source_ij(i, j, R, a) ? static_cast<uint32_t>(j * a.W + i) : 0xffffu;
-        if (e & 1) w[e >> 1] |= sp << 16;
-        else w[e >> 1] = sp;
-        if (++i0 == a.W) { i0 = 0; ++j0; }
-    }
-    *reinterpret_cast<uint4*>(pix + static_cast<int64_t>(b) * hw + p0) = make_uint4(w[0], w[1], w[2], w[3]);
-}
-
-// gather of `cpc` consecutive planes of one sample from the finished map.  dynamic smem: kRwRing plane buffers
-template <typename T>
-__global__ void __launch_bounds__(kRwThreads)
-rewarp_gather_map_kernel(const RewarpArgs a, const uint16_t* __restrict__ pix, T* __restrict__ out, int buf_words) {
-    constexpr int EPW = 4 / static_cast<int>(sizeof(T));  // elements per 32-bit word
-    constexpr int SLOTS = kRwPix / EPW;                    // words per thread and plane
-    extern __shared__ __align__(16) uint32_t rw_smem[];
-    __shared__ float s_theta[kRwMaxStages * 6];
-    const int hw = a.H * a.W, nwords = hw / EPW;
-    const int groups = (a.C + a.cpc - 1) / a.cpc;
-    const int b = blockIdx.x / groups, cgp = blockIdx.x - b * groups;
-    const int c0 = cgp * a.cpc, c1 = min(a.C, c0 + a.cpc);
-    if (threadIdx.x < a.stages * 6)
-        s_theta[threadIdx.x] = a.view[0].theta[static_cast<int64_t>(b) * a.stages * 6 + threadIdx.x];
-    const uint32_t zero_byte = static_cast<uint32_t>(buf_words - 4) * 4u;
-    if (threadIdx.x < kRwRing) rw_smem[threadIdx.x * buf_words + buf_words - 4] = 0u;   // out-of-bounds pixels gather from it
-    __syncthreads();
-    const int row_words = a.W / EPW, vpr = row_words / 4, nvec = nwords / 4;
-    float J[4];
-    composed_jacobian(s_theta, a, J);
-    const int stride = pick_stride(row_words, J[0], J[2], EPW - 1);
-    int so[kRwMaxVec];
-    stage_offsets(so, nvec, vpr, stride);
-    auto issue = [&](int it) {
-        stage_issue<T>(smem_u32(rw_smem + (it % kRwRing) * buf_words), so,
-                       static_cast<const T*>(a.view[0].in) + (static_cast<int64_t>(b) * a.C + c0 + it) * hw);
-    };
-    const int nitems = c1 - c0;
-#pragma unroll
-    for (int it = 0; it < kRwRing - 1; ++it) {
-        if (it < nitems) issue(it);
-        cp_async_commit();
-    }
-    // padded byte offsets of this thread's pixels (words t + 256*slot of the plane), two per register
-    const uint16_t* mp = pix + static_cast<int64_t>(b) * hw;
-    const int wlog = (a.W & (a.W - 1)) == 0 ? 31 - __clz(a.W) : -1;   // power-of-two rows: a shift instead of a division
-    uint32_t idx[kRwPix / 2];
-#pragma unroll
-    for (int sl = 0; sl < SLOTS; ++sl) {
-        const int word = sl * kRwThreads + threadIdx.x;
-#pragma unroll
-        for (int e = 0; e < EPW; ++e) {
-            const int k = sl * EPW + e;
-            uint32_t o = zero_byte;
-            if (word < nwords) {
-                const uint32_t sp = EPW == 2 ? ((__ldg(reinterpret_cast<const uint32_t*>(mp) + word) >> (16 * e)) & 0xffffu)
-                                             : static_cast<uint32_t>(__ldg(mp + word));
-                if (sp != 0xffffu) {
-                    const uint32_t row = wlog >= 0 ? sp >> wlog : sp / static_cast<uint32_t>(a.W);
-                    o = row * static_cast<uint32_t>(stride) * 4u + (sp - row * a.W) * static_cast<uint32_t>(sizeof(T));
-                }
-            }
-            if (k & 1) idx[k >> 1] |= o << 16;
-            else idx[k >> 1] = o;
-        }
-    }
-    for (int it = 0; it < nitems; ++it) {
-        uint32_t* o32 = reinterpret_cast<uint32_t*>(out + (static_cast<int64_t>(b) * a.C + c0 + it) * hw) + threadIdx.x;
-        cp_async_wait<kRwRing - 2>();   // this thread's copies of plane `it` have landed ...
-        __syncthreads();                // ... everybody's have, and everybody is done with plane it-1
-        if (it + kRwRing - 1 < nitems) issue(it + kRwRing - 1);
-        cp_async_commit();
-        const uint8_t* bytes = reinterpret_cast<const uint8_t*>(rw_smem + (it % kRwRing) * buf_words);
-#pragma unroll
-        for (int sl = 0; sl < SLOTS; ++sl) {   // the values are moved, never converted
-            uint32_t w32;
-            if constexpr (EPW == 1) {
-                const uint32_t o = (idx[sl >> 1] >> (16 * (sl & 1))) & 0xffffu;
-                w32 = *reinterpret_cast<const uint32_t*>(bytes + o);
-            } else {
-                const uint32_t lo = *reinterpret_cast<const uint16_t*>(bytes + (idx[sl] & 0xffffu));
-                const uint32_t hi = *reinterpret_cast<const uint16_t*>(bytes + (idx[sl] >> 16));
-                w32 = lo | (hi << 16);
-            }
-            if (sl * kRwThreads + static_cast<int>(threadIdx.x) < nwords) o32[sl * kRwThreads] = w32;
-        }
-    }
-    cp_async_wait<0>();
-}
-
-// the inverse plan of one sample from the finished map (same plan as rewarp_inverse_plan_kernel writes).
-// dynamic smem: uint16 off[hw + 8] | lst[hw8] | map[hw8]
-template <int ES>
-__global__ void __launch_bounds__(kRwThreads)
-rewarp_plan_from_map_kernel(const RewarpArgs a, const uint16_t* __restrict__ pix, uint16_t* __restrict__ plan, int buf_words) {
-    constexpr int EPW = 4 / ES;
-    extern __shared__ __align__(16) uint32_t rw_smem[];
-    __shared__ float s_theta[kRwMaxStages * 6];
-    __shared__ uint32_t s_scan[kRwThreads];
-    const int hw = a.H * a.W, hw8 = (hw + 7) & ~7;
-    uint16_t* off = reinterpret_cast<uint16_t*>(rw_smem);
-    uint16_t* lst = off + ((hw + 8 + 7) & ~7);
-    uint16_t* map = lst + hw8;
-    const int b = blockIdx.x;
-    if (threadIdx.x < a.stages * 6)
-        s_theta[threadIdx.x] = a.view[0].theta[static_cast<int64_t>(b) * a.stages * 6 + threadIdx.x];
-    uint32_t* off32 = reinterpret_cast<uint32_t*>(off);
-    for (int s = threadIdx.x; s < (hw + 8) / 2; s += kRwThreads) off32[s] = 0u;
-    const uint4* src = reinterpret_cast<const uint4*>(pix + static_cast<int64_t>(b) * hw);
-    for (int v = threadIdx.x; v < hw / 8; v += kRwThreads) reinterpret_cast<uint4*>(map)[v] = __ldg(src + v);
-    __syncthreads();
-    float J[4];
-    composed_jacobian(s_theta, a, J);
-    const float det = J[0] * J[3] - J[1] * J[2];
-    const float inv = det != 0.0f ? 1.0f / det : 0.0f;
-    const int stride = pick_stride(a.W / EPW, J[3] * inv, -J[2] * inv, EPW - 1);   // see rewarp_bwd_smem_kernel
-    {
-        const int W = a.W;
-        invert_map(map, hw, 0, hw, off, lst, s_scan, [=](int p) {
-            const int row = p / W;
-            return static_cast<uint16_t>(row * stride * 4 + (p - row * W) * ES);
-        });
-    }
-    uint16_t* P = plan + static_cast<int64_t>(b) * plan_elems_for(hw);
-    uint16_t* g_slots = P + 8;
-    uint16_t* g_off = g_slots + 4 * static_cast<int64_t>(hw);
-    uint16_t* g_lst = g_off + hw8;
-    const uint32_t zero_byte = static_cast<uint32_t>(buf_words - 4) * 4u;
-    bool any4 = false, any2 = false;
-    for (int s = threadIdx.x; s < hw; s += kRwThreads) {
-        bool overflow;
-        *reinterpret_cast<uint2*>(g_slots + 4 * static_cast<int64_t>(s)) = list_slots(off, lst, s, zero_byte, overflow);
-        const int len = off[s] - (s == 0 ? 0 : off[s - 1]);
-        any4 |= len > 4;
-        any2 |= len > 2;
-    }
-    for (int v = threadIdx.x; v < hw / 8; v += kRwThreads) {
-        reinterpret_cast<uint4*>(g_off)[v] = reinterpret_cast<const uint4*>(off)[v];
-        reinterpret_cast<uint4*>(g_lst)[v] = reinterpret_cast<const uint4*>(lst)[v];
-    }
-    const int f4 = __syncthreads_or(any4), f2 = __syncthreads_or(any2);
-    if (threadIdx.x < 8)
-        P[threadIdx.x] = threadIdx.x == 0 ? static_cast<uint16_t>(stride) : (threadIdx.x == 1 ? f4 : (threadIdx.x == 2 ? f2 : 0));
-}
-
 // backward from the plan: no cluster, no inversion — slots from global memory, gradient planes staged
 // through the padded ring.  dynamic smem: kRwRing plane buffers
 template <typename T>
@@ -1167,12 +998,6 @@ static int reserve_smem(K kernel, size_t bytes, const char* name) {
     return UDAPE_OK;
 }
 
-static int64_t bwd_ctas_per_sm() {
-    const char* e = std::getenv("UDAPE_REWARP_BWD_CTAS");   // tuning
-    const int v = e ? std::atoi(e) : 0;
-    return v > 0 ? v : 12;   // C5 (5376 planes): 85 / 72 / 66 us for 3 / 6 / 12 CTAs per SM worth of CTAs
-}
-
 constexpr int kRwDeepRing = 6;   // single view, a CTA that owns >= 6 planes
 
 template <typename T>
@@ -1197,7 +1022,7 @@ using namespace udape;
 extern "C" int udape_rewarp_fwd(const void* const* in, const float* const* theta, int views, int stages,
                                 int half_mask, int grid_dtype, const int32_t* paste, int paste_after,
                                 const uint8_t* active, int64_t B, int64_t C, int64_t H, int64_t W, int dtype,
-                                void* out, uint16_t* inverse_plan, uint16_t* map_ws, void* stream) {
+                                void* out, uint16_t* inverse_plan, void* stream) {
     RewarpArgs a = {};
     // out == NULL with an inverse plan: only the plan is built (it depends on theta alone, so a caller can
     // run it on another stream, off the chain  gather -> loss -> backward)
@@ -1222,38 +1047,6 @@ extern "C" int udape_rewarp_fwd(const void* const* in, const float* const* theta
     const int64_t hw = H * W;
     cudaStream_t st = as_stream(stream);
     const int buf_words = (all16 && !paste && !active && !route_disabled()) ? smem_route_words(H, W, es) : 0;
-    static const bool map_route_off = [] { const char* e = std::getenv("UDAPE_REWARP_NO_MAP"); return e && e[0] == '1'; }();
-    if (map_ws && views == 1 && !paste && !active && !map_route_off && smem_route_words(H, W, es) != 0 && (hw % 8) == 0 &&
-        (!out || buf_words) && aligned16(map_ws) && (!inverse_plan || aligned16(inverse_plan))) {
-        // map route: index arithmetic once per sample in its own launch, then plane-granular CTAs
-        const int bw = smem_route_words(H, W, es);
-        const int64_t bands = (hw + kRwThreads * kMapPx - 1) / (kRwThreads * kMapPx);
-        rewarp_map_kernel<<<static_cast<unsigned>(B * bands), kRwThreads, 0, st>>>(a, map_ws);
-        if (inverse_plan) {
-            const size_t smem = sizeof(uint16_t) * (((hw + 8 + 7) & ~7ll) + 2 * ((hw + 7) & ~7ll));
-            if (es == 4) {
-                const int r2 = reserve_smem(rewarp_plan_from_map_kernel<4>, smem, "udape_rewarp_fwd(plan)");
-                if (r2) return r2;
-                rewarp_plan_from_map_kernel<4><<<static_cast<unsigned>(B), kRwThreads, smem, st>>>(a, map_ws, inverse_plan, bw);
-            } else {
-                const int r2 = reserve_smem(rewarp_plan_from_map_kernel<2>, smem, "udape_rewarp_fwd(plan)");
-                if (r2) return r2;
-                rewarp_plan_from_map_kernel<2><<<static_cast<unsigned>(B), kRwThreads, smem, st>>>(a, map_ws, inverse_plan, bw);
-            }
-        }
-        if (out) {
-            // ~6 resident CTAs per SM worth of CTAs, at least one plane each
-            a.cpc = channels_per_cta(B, C, 6 * static_cast<int64_t>(sm_count()));
-            const int64_t grid = B * ((C + a.cpc - 1) / a.cpc);
-            const size_t smem = kRwRing * sizeof(uint32_t) * static_cast<size_t>(bw);
-            UDAPE_DISPATCH_FLOAT(dtype, T, {
-                const int r2 = reserve_smem(rewarp_gather_map_kernel<T>, smem, "udape_rewarp_fwd");
-                if (r2) return r2;
-                rewarp_gather_map_kernel<T><<<static_cast<unsigned>(grid), kRwThreads, smem, st>>>(a, map_ws, static_cast<T*>(out), bw);
-            });
-        }
-        return check_launch("udape_rewarp_fwd");
-    }
     if (inverse_plan) {
         UDAPE_REQUIRE(views == 1 && !paste && !active && smem_route_words(H, W, es) != 0 && aligned16(inverse_plan),
                       UDAPE_ERR_ARG, "udape_rewarp_fwd: an inverse plan needs a single view, no paste / pass-through and a "
@@ -1333,8 +1126,9 @@ extern "C" int udape_rewarp_bwd(const void* grad_out, const float* theta, int st
                       UDAPE_ERR_ARG, "udape_rewarp_bwd: the inverse plan does not apply to this plane / alignment");
         const int bw = smem_route_words(H, W, es);
         // (2 CTAs per SM measured best inside the step as well: 184 / 188 / 204 / 238 us for 296 / 148 / 64 / 32 CTAs;
-        // big batches — thousands of planes — want every resident slot filled several times over instead)
-        const int64_t per_sm = B * C >= 2048 ? bwd_ctas_per_sm() : 2;
+        // big batches want every resident slot filled several times over: C5, 5376 planes, 85 / 72 / 66 us for
+        // 3 / 6 / 12 CTAs per SM worth of CTAs — r02e)
+        const int64_t per_sm = B * C >= 2048 ? 12 : 2;
         a.cpc = channels_per_cta(B, C, per_sm * static_cast<int64_t>(sm_count()));
         const int64_t grid = B * ((C + a.cpc - 1) / a.cpc);
         const size_t smem = kRwRing * sizeof(uint32_t) * static_cast<size_t>(bw);

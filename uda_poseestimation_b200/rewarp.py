@@ -136,12 +136,6 @@ def stage_table(stages, height: int, width: int, dtype: torch.dtype = torch.floa
     return table, half_mask, (_lib._DTYPE_CODE[ac] if ac is not None else _lib.F16)
 
 
-# From this many planes (B*C) on, the composed map is built by a launch of its own and the gather / plan builder
-# run as plane-granular launches that read it (udape_rewarp_fwd's map_ws): one fat CTA per sample cannot keep a
-# 256-sample launch busy.  Small batches keep the single launch (one launch less on a latency-bound chain).
-MAP_ROUTE_MIN_PLANES = int(os.environ.get("UDAPE_REWARP_MAP_MIN", "1024"))
-
-
 def _launch_fwd(views, thetas, half_mask, grid_code, out, paste=None, paste_after=0, active=None, plan=None):
     y0 = views[0]
     b, c, h, w = y0.shape
@@ -149,13 +143,10 @@ def _launch_fwd(views, thetas, half_mask, grid_code, out, paste=None, paste_afte
     in_arr = (ctypes.c_void_p * n)(*[v.data_ptr() for v in views])
     th_arr = (ctypes.c_void_p * n)(*[t.data_ptr() for t in thetas])
     dev = y0.device
-    map_ws = None
-    if n == 1 and paste is None and active is None and b * c >= MAP_ROUTE_MIN_PLANES and h * w <= 4096:
-        map_ws = torch.empty((b, h * w), dtype=torch.int16, device=dev)
     with _lib.on_device(dev):
         st = _lib.load().udape_rewarp_fwd(in_arr, th_arr, n, thetas[0].shape[1], half_mask, grid_code, _lib.ptr(paste),
                                           paste_after, _lib.ptr(active), b, c, h, w, _lib.float_code(y0),
-                                          _lib.ptr(out), _lib.ptr(plan), _lib.ptr(map_ws), _lib.stream_ptr(dev))
+                                          _lib.ptr(out), _lib.ptr(plan), _lib.stream_ptr(dev))
     _lib.check(st, "udape_rewarp_fwd")
     return out
 
