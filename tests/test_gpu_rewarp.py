@@ -218,6 +218,7 @@ def test_rewarp_routes_agree(dev, dt, monkeypatch):
 def test_rewarp_ring_depths_agree(dev, dt, monkeypatch):
     """A CTA that owns six or more planes (one CTA per sample at batch 32) stages them through a six-buffer
     ring instead of three: same bits, also for channel counts that are not a multiple of the ring."""
+    monkeypatch.setenv("UDAPE_REWARP_WIDE", "0")      # the ring depths belong to the 256-thread kernels
     for (b, k) in [(32, 16), (33, 7), (40, 21), (148, 6)]:
         y = (torch.randn(b, k, 64, 64, device=dev) * 3).to(dt)
         ac = None if dt == torch.float32 else dt
@@ -272,6 +273,7 @@ def test_rewarp_cluster_kernels_under_contention(dev, cluster, monkeypatch):
     ref_f = RW.gather(y, theta, t[1], torch.float16)
     ref_b = RW.gather_backward(g, theta, t[1], torch.float16)
     monkeypatch.delenv("UDAPE_REWARP_GLOBAL")
+    monkeypatch.setenv("UDAPE_REWARP_WIDE", "0")        # the cluster kernels are the 256-thread route
     monkeypatch.setenv("UDAPE_REWARP_CLUSTER", cluster)
     plans = [RW.inverse_plan_buffer(y) for _ in range(2)]
     torch.cuda.synchronize()
@@ -291,3 +293,33 @@ def test_rewarp_cluster_kernels_under_contention(dev, cluster, monkeypatch):
     torch.cuda.synchronize()
     for f, bw in outs:
         assert torch.equal(f, ref_f) and torch.equal(bw, ref_b)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16, torch.bfloat16])
+def test_rewarp_wide_route_equals_the_256_thread_kernels(dev, dt, monkeypatch):
+    """The wide forward route (one 512-thread CTA per sample, compact map builder) against the 256-thread cluster
+    kernels and the global-memory route, and the backward with / without an inverse plan on every route: identical
+    bits for full and small planes, odd batch / channel counts, and zoom factors that give long contributor lists."""
+    for (b, k, h, w) in [(37, 21, 64, 64), (5, 3, 32, 32), (3, 2, 24, 40), (2, 5, 16, 8)]:
+        x = (torch.randn(b, k, h, w, generator=torch.Generator().manual_seed(b)) * 3).to(dt).to(dev)
+        g = torch.randn(b, k, h, w, generator=torch.Generator().manual_seed(b + 1)).to(dt).to(dev)
+        aug = S.aug_params(b, seed=130 + b, shear_y=True, scale=(0.3, 1.6))      # 1 / 0.3: lists of ten and more
+        half = dt != torch.float32
+        table, mask, _ = RW.stage_table(RW.recon_stages(aug, 4.0, b), h, w, dt, dt if half else None)
+        theta = table.to(dev)
+        gd = dt if half else None
+        res = {}
+        for route, env in (("wide", {}), ("cta256", {"UDAPE_REWARP_WIDE": "0"}), ("global", {"UDAPE_REWARP_GLOBAL": "1"})):
+            for name in ("UDAPE_REWARP_WIDE", "UDAPE_REWARP_GLOBAL"):
+                monkeypatch.delenv(name, raising=False)
+            for name, val in env.items():
+                monkeypatch.setenv(name, val)
+            res[route] = (RW.gather(x, theta, mask, gd), RW.gather_backward(g, theta, mask, gd))
+        monkeypatch.setenv("UDAPE_REWARP_WIDE", "0")
+        plan = RW.build_inverse_plan(x, theta, mask, gd)
+        if plan is not None:
+            res["plan"] = (res["wide"][0], RW.gather_backward(g, theta, mask, gd, plan=plan))
+        monkeypatch.delenv("UDAPE_REWARP_WIDE")
+        for route, (f, bw) in res.items():
+            assert torch.equal(f, res["wide"][0]), (route, "forward", b, k, h, w)
+            assert torch.equal(bw, res["wide"][1]), (route, "backward", b, k, h, w)

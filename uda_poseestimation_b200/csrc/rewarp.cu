@@ -864,6 +864,136 @@ rewarp_bwd_smem_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __rest
     cp_async_wait<0>();
 }
 
+// ---- wide forward route: one CTA of kWideThreads per sample ------------------------------------------------
+// With 256 threads a sample's CTA spends three quarters of its instructions on the composed map (16 pixels per
+// thread, ~250 issue slots each on a half grid: four fp16 roundings, two int->float and two float->int
+// conversions per stage and pixel, all quarter-rate) and only then starts moving data; 256 such CTAs leave the
+// SMs at 8 warps each (IPC 1.3, 42-47 % of the HBM roofline for fp16 planes, profiles/r02f_rewarp_*).  Here a
+// sample gets 512 threads (8 pixels each): no cluster, no DSMEM exchange, two CTAs share an SM (one in its
+// arithmetic phase while the other streams planes), and 256 samples fit one wave.  Measured (r02k, C5 / C2):
+// fp16 26.3 / 12.2 us against 28.4 / 14.0 us for the 256-thread kernel, fp32 33.7 us (80 % of the HBM roofline)
+// against 35.0.  The same idea for the backward (map + inversion + ordered sums in one 512-thread CTA, no plan)
+// was slower than the plan route (C5 91-119 us against 66 us; C2 56-69 us against 15 us): the inversion is a
+// chain of dependent shared-memory phases per sample and gains nothing from more threads — dropped.
+constexpr int kWideThreads = 512;
+constexpr int kWidePix = 8;                // pixels per thread: planes up to 512 * 8 = 4096 px
+
+// The composed map of one sample into shared memory, one pixel per loop trip and NOT unrolled: inlining the
+// per-pixel arithmetic (four stage bodies x four variants) once per pixel of a thread made the wide kernels 17 000
+// SASS instructions long, and they stalled on instruction fetch (ncu "no_instruction", profiles/r02j_*).
+// CODE(i, j) -> uint16: what is stored for a pixel whose source is (i, j); `none` for pixels that leave the image.
+template <int HM, int GD, typename Code>
+__device__ __noinline__ void build_map_variant(const float* __restrict__ s_theta, int W, int H, int stages, int half_mask,
+                                               int grid_dtype, uint16_t* __restrict__ map, uint16_t none, Code code) {
+    const int hw = H * W;
+    const int nt = blockDim.x;
+    const int dj = nt / W, di = nt - dj * W;
+    int p = threadIdx.x;
+    int j0 = p / W, i0 = p - j0 * W;
+#pragma unroll 1
+    for (; p < hw; p += nt) {
+        int i = i0, j = j0;
+        bool ok = true;
+#pragma unroll 1
+        for (int st = 0; st < stages && ok; ++st)
+            ok = stage_source_t<HM, GD>(i, j, s_theta + 6 * st, W, H, (half_mask >> st) & 1, grid_dtype);
+        map[p] = ok ? code(i, j) : none;
+        i0 += di; j0 += dj;
+        if (i0 >= W) { i0 -= W; ++j0; }
+    }
+}
+template <typename Code>
+__device__ __forceinline__ void build_map_compact(const float* __restrict__ s_theta, const RewarpArgs& a, uint16_t* __restrict__ map,
+                                                  uint16_t none, Code code) {
+    if (a.half_mask == 0) build_map_variant<0, -1>(s_theta, a.W, a.H, a.stages, a.half_mask, a.grid_dtype, map, none, code);
+    else if (a.half_mask == (1 << a.stages) - 1) {
+        if (a.grid_dtype == UDAPE_F16) build_map_variant<1, UDAPE_F16>(s_theta, a.W, a.H, a.stages, a.half_mask, a.grid_dtype, map, none, code);
+        else build_map_variant<1, UDAPE_BF16>(s_theta, a.W, a.H, a.stages, a.half_mask, a.grid_dtype, map, none, code);
+    } else build_map_variant<2, -1>(s_theta, a.W, a.H, a.stages, a.half_mask, a.grid_dtype, map, none, code);
+}
+
+// dynamic smem: kRwRing padded plane buffers | uint16 map[hw8].  Single view, no paste / pass-through (the heatmap re-warps).
+template <typename T>
+__global__ void __launch_bounds__(kWideThreads, 2)
+rewarp_wide_kernel(const RewarpArgs a, T* __restrict__ out, int buf_words) {
+    constexpr int EPW = 4 / static_cast<int>(sizeof(T));
+    constexpr int SLOTS = kWidePix / EPW;                  // words per thread and plane
+    constexpr int VEC = (kWidePix * static_cast<int>(sizeof(T)) * kWideThreads / 16 + kWideThreads - 1) / kWideThreads;  // 16-byte copies per thread and plane
+    extern __shared__ __align__(16) uint32_t rw_smem[];
+    __shared__ float s_theta[kRwMaxStages * 6];
+    const int hw = a.H * a.W, nwords = hw / EPW;
+    const int b = blockIdx.x;
+    if (threadIdx.x < a.stages * 6)
+        s_theta[threadIdx.x] = a.view[0].theta[static_cast<int64_t>(b) * a.stages * 6 + threadIdx.x];
+    const uint32_t zero_byte = static_cast<uint32_t>(buf_words - 4) * 4u;
+    if (threadIdx.x < kRwRing) rw_smem[threadIdx.x * buf_words + buf_words - 4] = 0u;   // out-of-bounds pixels gather from it
+    __syncthreads();
+    const int row_words = a.W / EPW, vpr = row_words / 4, nvec = nwords / 4;
+    float J[4];
+    composed_jacobian(s_theta, a, J);
+    const int stride = pick_stride(row_words, J[0], J[2], EPW - 1);
+    int so[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+        const int v = q * kWideThreads + threadIdx.x;
+        const int row = v / vpr;
+        so[q] = v < nvec ? (row * stride + 4 * (v - row * vpr)) * 4 : -1;
+    }
+    auto issue = [&](int it) {
+        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const T*>(a.view[0].in) + (static_cast<int64_t>(b) * a.C + it) * hw) + threadIdx.x;
+        const uint32_t dst = smem_u32(rw_smem + (it % kRwRing) * buf_words);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q)
+            if (so[q] >= 0) cp_async16(dst + so[q], src + q * kWideThreads);
+    };
+    const int nitems = a.C;
+#pragma unroll
+    for (int it = 0; it < kRwRing - 1; ++it) {   // in flight while the map is computed
+        if (it < nitems) issue(it);
+        cp_async_commit();
+    }
+    // the composed source of every pixel as a padded byte offset, then this thread's 8 (words t + NT*slot) in registers
+    uint16_t* map = reinterpret_cast<uint16_t*>(rw_smem + kRwRing * buf_words);
+    build_map_compact(s_theta, a, map, static_cast<uint16_t>(zero_byte), [=](int i, int j) {
+        return static_cast<uint16_t>(j * stride * 4 + i * static_cast<int>(sizeof(T)));
+    });
+    __syncthreads();
+    uint32_t idx[kWidePix / 2];
+#pragma unroll
+    for (int sl = 0; sl < SLOTS; ++sl) {
+        const int word = sl * kWideThreads + threadIdx.x;
+#pragma unroll
+        for (int e = 0; e < EPW; ++e) {
+            const int k = sl * EPW + e;
+            const uint32_t o = word < nwords ? map[word * EPW + e] : zero_byte;
+            if (k & 1) idx[k >> 1] |= o << 16;
+            else idx[k >> 1] = o;
+        }
+    }
+    for (int it = 0; it < nitems; ++it) {
+        uint32_t* o32 = reinterpret_cast<uint32_t*>(out + (static_cast<int64_t>(b) * a.C + it) * hw) + threadIdx.x;
+        cp_async_wait<kRwRing - 2>();   // this thread's copies of plane `it` have landed ...
+        __syncthreads();                // ... everybody's have, and everybody is done with plane it-1
+        if (it + kRwRing - 1 < nitems) issue(it + kRwRing - 1);
+        cp_async_commit();
+        const uint8_t* bytes = reinterpret_cast<const uint8_t*>(rw_smem + (it % kRwRing) * buf_words);
+#pragma unroll
+        for (int sl = 0; sl < SLOTS; ++sl) {   // the values are moved, never converted
+            uint32_t w32;
+            if constexpr (EPW == 1) {
+                const uint32_t o = (idx[sl >> 1] >> (16 * (sl & 1))) & 0xffffu;
+                w32 = *reinterpret_cast<const uint32_t*>(bytes + o);
+            } else {
+                const uint32_t lo = *reinterpret_cast<const uint16_t*>(bytes + (idx[sl] & 0xffffu));
+                const uint32_t hi = *reinterpret_cast<const uint16_t*>(bytes + (idx[sl] >> 16));
+                w32 = lo | (hi << 16);
+            }
+            if (sl * kWideThreads + static_cast<int>(threadIdx.x) < nwords) o32[sl * kWideThreads] = w32;
+        }
+    }
+    cp_async_wait<0>();
+}
+
 // general route (any plane up to 25600 px): gradient gathered from global memory.
 // dynamic smem: uint16 off[hw + 2] | uint16 lst[hw] | uint16 map[hw]
 template <typename T>
@@ -998,6 +1128,13 @@ static int reserve_smem(K kernel, size_t bytes, const char* name) {
     return UDAPE_OK;
 }
 
+// the wide route takes planes of exactly kWideThreads * kWidePix pixels or fewer in whole 8-pixel groups
+static bool wide_route(int64_t B, int64_t hw) {
+    const char* e = std::getenv("UDAPE_REWARP_WIDE");   // tests / tuning: "0" keeps the 256-thread kernels
+    if (e && e[0] == '0') return false;
+    return hw <= kWideThreads * kWidePix && (hw % 8) == 0 && B >= 1;
+}
+
 constexpr int kRwDeepRing = 6;   // single view, a CTA that owns >= 6 planes
 
 template <typename T>
@@ -1061,6 +1198,16 @@ extern "C" int udape_rewarp_fwd(const void* const* in, const float* const* theta
                                                 smem, st, "udape_rewarp_fwd(plan)", a, inverse_plan, bw);
         if (r2) return r2;
         if (!out) return check_launch("udape_rewarp_fwd(plan)");
+    }
+    if (buf_words && views == 1 && wide_route(B, hw)) {
+        // wide route: one CTA of 512 threads per sample
+        const size_t smem = kRwRing * sizeof(uint32_t) * static_cast<size_t>(buf_words) + sizeof(uint16_t) * ((hw + 7) & ~7ll);
+        UDAPE_DISPATCH_FLOAT(dtype, T, {
+            const int r2 = reserve_smem(rewarp_wide_kernel<T>, smem, "udape_rewarp_fwd");
+            if (r2) return r2;
+            rewarp_wide_kernel<T><<<static_cast<unsigned>(B), kWideThreads, smem, st>>>(a, static_cast<T*>(out), buf_words);
+        });
+        return check_launch("udape_rewarp_fwd");
     }
     if (buf_words) {
         // one cluster of `n` CTAs per sample: the channels are split n ways, the map is built once

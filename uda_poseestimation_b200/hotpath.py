@@ -330,7 +330,8 @@ class HotPathStep:
                     self.ema.step()
                     self._mark("ema done")
         # teacher forward; student forward + inverse plan + backward
-        self.rewarp_kernels = ((1 if inp.theta_tea is not None else 0) + (3 if inp.theta_stu is not None else 0)
+        self.rewarp_kernels = ((1 if inp.theta_tea is not None else 0)
+                               + ((3 if _rewarp.USE_INVERSE_PLAN else 2) if inp.theta_stu is not None else 0)
                                + (1 if inp.x_t_stu is not None else 0))
         # the student's grids are built under autocast (:414): every stage samples on a half grid
         stu_half = inp.y_t_stu.dtype in (torch.float16, torch.bfloat16)
@@ -340,16 +341,18 @@ class HotPathStep:
         if inp.theta_stu is not None:
             # the composed map of every sample inverted once — what the backward gathers from.  It depends
             # on theta alone, so it is built on its own branch, off the  gather -> loss -> backward  chain
-            stu_plan = _rewarp.inverse_plan_buffer(inp.y_t_stu)
-            if self.parallel:
-                s_plan.wait_stream(cur)
-            with torch.cuda.stream(s_plan), torch.no_grad():
-                self._mark("plan start")
-                _rewarp.build_inverse_plan(inp.y_t_stu, inp.theta_stu, stu_mask, stu_grid, plan=stu_plan)
-                self._mark("plan done")
+            # (only with rewarp.USE_INVERSE_PLAN: by default the backward inverts the map itself, in its own launch)
+            stu_plan = _rewarp.inverse_plan_buffer(inp.y_t_stu) if _rewarp.USE_INVERSE_PLAN else None
+            if stu_plan is not None:
                 if self.parallel:
-                    plan_ready = torch.cuda.Event()
-                    plan_ready.record(s_plan)
+                    s_plan.wait_stream(cur)
+                with torch.cuda.stream(s_plan), torch.no_grad():
+                    self._mark("plan start")
+                    _rewarp.build_inverse_plan(inp.y_t_stu, inp.theta_stu, stu_mask, stu_grid, plan=stu_plan)
+                    self._mark("plan done")
+                    if self.parallel:
+                        plan_ready = torch.cuda.Event()
+                        plan_ready.record(s_plan)
             with torch.cuda.stream(s_stu), torch.no_grad():
                 # :417-423 — y_t_stu_recon (the backward runs after the loss step, below)
                 self._mark("stu gather start")

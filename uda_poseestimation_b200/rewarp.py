@@ -136,6 +136,12 @@ def stage_table(stages, height: int, width: int, dtype: torch.dtype = torch.floa
     return table, half_mask, (_lib._DTYPE_CODE[ac] if ac is not None else _lib.F16)
 
 
+# The backward reads an inverse plan the forward (or build_inverse_plan, on another stream) wrote: the composed map
+# of every sample inverted once per batch.  UDAPE_REWARP_PLAN=0 makes the backward invert the map itself instead
+# (one launch less, but 85-120 us against 15-66 us at the trainers' / the microbench sizes on B200).
+USE_INVERSE_PLAN = os.environ.get("UDAPE_REWARP_PLAN", "1") == "1"
+
+
 def _launch_fwd(views, thetas, half_mask, grid_code, out, paste=None, paste_after=0, active=None, plan=None):
     y0 = views[0]
     b, c, h, w = y0.shape
@@ -188,7 +194,7 @@ def build_inverse_plan(y: torch.Tensor, theta: torch.Tensor, half_mask: int = 0,
 class _Rewarp(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y, theta, half_mask, grid_code):
-        plan = inverse_plan_buffer(y)
+        plan = inverse_plan_buffer(y) if USE_INVERSE_PLAN else None
         ctx.save_for_backward(theta, plan)
         ctx.meta = (half_mask, grid_code)
         return _launch_fwd([y], [theta], half_mask, grid_code, torch.empty_like(y), plan=plan)
