@@ -110,6 +110,36 @@ __device__ __forceinline__ bool stage_source(int& i, int& j, const float* __rest
     return stage_source_t<2, -1>(i, j, r, W, H, half, grid_dtype);
 }
 
+// The same stage with the pixel carried as FLOATS (exact small integers): conversions run at a quarter of the
+// FP32 rate on the SM and were most of the ~350 issue slots a pixel of a half-grid map cost (per stage two
+// int->float, two float->int and eight half roundings), so
+//   * the nearest index stays a float (rintf == F2I.RN for every in-range value; the range test on the floats
+//     rejects NaN / inf / out-of-range exactly like the test on the saturated integers),
+//   * the rounding of x = i + (0.5 - W/2) to the grid dtype is skipped where it is the identity: x is a
+//     half-integer below 512 in magnitude (W, H <= 1024), i.e. 2x has at most 10 bits — exact in fp16 (11-bit
+//     significand) always, in bf16 (8 bits) when W, H <= 256 (`xy_exact`).
+// Bit-identical to stage_source_t (tests/test_gpu_rewarp.py compares every route against torchvision).
+template <int HM, int GD>
+__device__ __forceinline__ bool stage_source_f(float& fi, float& fj, const float* __restrict__ r, float Wf, float Hf, float cx,
+                                               float cy, bool half, int grid_dtype, bool xy_exact) {
+    const bool rnd = HM == 2 ? half : (HM == 1);
+    float x = fi + cx, y = fj + cy;
+    if (rnd && !xy_exact) { x = round_grid_t<GD>(x, grid_dtype); y = round_grid_t<GD>(y, grid_dtype); }
+    float gx = __fadd_rn(__fmaf_rn(y, r[1], __fmul_rn(x, r[0])), r[2]);
+    float gy = __fadd_rn(__fmaf_rn(y, r[4], __fmul_rn(x, r[3])), r[5]);
+    if (rnd) { gx = round_grid_t<GD>(gx, grid_dtype); gy = round_grid_t<GD>(gy, grid_dtype); }
+    const float fx = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), Wf), 1.0f), 0.5f);
+    const float fy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), Hf), 1.0f), 0.5f);
+    const float xr = rintf(fx), yr = rintf(fy);
+    if (!(xr >= 0.0f && xr <= Wf - 1.0f && yr >= 0.0f && yr <= Hf - 1.0f)) return false;   // NaN fails every comparison
+    fi = xr;
+    fj = yr;
+    return true;
+}
+__device__ __forceinline__ bool grid_xy_exact(int W, int H, int grid_dtype) {
+    return grid_dtype == UDAPE_F16 || (W <= 256 && H <= 256);
+}
+
 // a sample's stage table held in registers (rows beyond `stages` are never read)
 struct StageRegs { float r[kRwMaxStages][6]; };
 __device__ __forceinline__ void load_stages(StageRegs& R, const float* __restrict__ r, int stages) {
@@ -122,12 +152,18 @@ __device__ __forceinline__ void load_stages(StageRegs& R, const float* __restric
 // register table
 template <int HM, int GD>
 __device__ __forceinline__ bool composed_source_ij_t(int& i, int& j, const StageRegs& R, const RewarpArgs& a) {
+    const float Wf = static_cast<float>(a.W), Hf = static_cast<float>(a.H);
+    const float cx = 0.5f - 0.5f * Wf, cy = 0.5f - 0.5f * Hf;
+    const bool xy_exact = GD == UDAPE_F16 ? true : grid_xy_exact(a.W, a.H, a.grid_dtype);
+    float fi = static_cast<float>(i), fj = static_cast<float>(j);
 #pragma unroll
     for (int s = 0; s < kRwMaxStages; ++s) {
         if (s < a.stages) {
-            if (!stage_source_t<HM, GD>(i, j, R.r[s], a.W, a.H, (a.half_mask >> s) & 1, a.grid_dtype)) return false;
+            if (!stage_source_f<HM, GD>(fi, fj, R.r[s], Wf, Hf, cx, cy, (a.half_mask >> s) & 1, a.grid_dtype, xy_exact)) return false;
         }
     }
+    i = static_cast<int>(fi);
+    j = static_cast<int>(fj);
     return true;
 }
 // kernel-uniform dispatch: no rounding (float32 images), every stage on a half grid (the student under
@@ -222,6 +258,7 @@ rewarp_fwd_kernel(const RewarpArgs a, T* __restrict__ out) {
 constexpr int kRwPix = 16;               // pixels per thread and plane: planes up to 256*16 = 4096 px
 constexpr int kRwMaxVec = 4;             // 16-byte staging copies per thread and plane
 constexpr int kRwRing = 3;               // plane buffers per CTA: two planes in flight behind the one being gathered
+constexpr int kWideRingHalf = 6;         // ... five for the 8 KB planes of the 2-byte types where few CTAs share an SM (rewarp_wide_kernel)
 constexpr int kRwBufBytes = 32 * 1024;   // padded plane budget per buffer
 
 // smallest row stride (32-bit words) >= words with stride % 32 == rem (rem % 4 == 0: 16-byte aligned rows)
@@ -697,7 +734,7 @@ rewarp_inverse_plan_kernel(const RewarpArgs a, uint16_t* __restrict__ plan, int 
 
 // backward from the plan: no cluster, no inversion — slots from global memory, gradient planes staged
 // through the padded ring.  dynamic smem: kRwRing plane buffers
-template <typename T>
+template <typename T, int RING>   // RING - 1 gradient planes in flight per CTA: 6 for the 8 KB fp16 planes, see rewarp_wide_kernel
 __global__ void __launch_bounds__(kRwThreads)   // (capping at 85 registers for 3 CTAs/SM spills and is slower: 17.6 vs 14.7 us)
 rewarp_bwd_plan_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __restrict__ gin, int buf_words,
                        const uint16_t* __restrict__ plan) {
@@ -715,16 +752,16 @@ rewarp_bwd_plan_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __rest
     const int stride = P[0];
     const bool any_overflow = P[1] != 0;
     const bool deep = P[2] != 0;   // zoom-out samples: no source pixel has more than two contributors
-    if (threadIdx.x < kRwRing) rw_smem[threadIdx.x * buf_words + buf_words - 4] = 0u;   // the zero word of every buffer
+    if (threadIdx.x < RING) rw_smem[threadIdx.x * buf_words + buf_words - 4] = 0u;   // the zero word of every buffer
     const int row_words = a.W / EPW, vpr = row_words / 4, nvec = nwords / 4;
     int so[kRwMaxVec];
     stage_offsets(so, nvec, vpr, stride);
     auto issue = [&](int it) {
-        stage_issue<T>(smem_u32(rw_smem + (it % kRwRing) * buf_words), so, gout + (static_cast<int64_t>(b) * a.C + c0 + it) * hw);
+        stage_issue<T>(smem_u32(rw_smem + (it % RING) * buf_words), so, gout + (static_cast<int64_t>(b) * a.C + c0 + it) * hw);
     };
     const int nitems = c1 - c0;
 #pragma unroll
-    for (int it = 0; it < kRwRing - 1; ++it) {
+    for (int it = 0; it < RING - 1; ++it) {
         if (it < nitems) issue(it);
         cp_async_commit();
     }
@@ -740,11 +777,11 @@ rewarp_bwd_plan_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __rest
         if (any_overflow && word < nwords && g_off[s] - (s == 0 ? 0 : g_off[s - 1]) > 4) long_mask |= 1u << k;
     }
     for (int it = 0; it < nitems; ++it) {
-        cp_async_wait<kRwRing - 2>();
+        cp_async_wait<RING - 2>();
         __syncthreads();
-        if (it + kRwRing - 1 < nitems) issue(it + kRwRing - 1);
+        if (it + RING - 1 < nitems) issue(it + RING - 1);
         cp_async_commit();
-        const uint8_t* bytes = reinterpret_cast<const uint8_t*>(rw_smem + (it % kRwRing) * buf_words);
+        const uint8_t* bytes = reinterpret_cast<const uint8_t*>(rw_smem + (it % RING) * buf_words);
         T* o = gin + (static_cast<int64_t>(b) * a.C + c0 + it) * hw;
 #pragma unroll
         for (int sl = 0; sl < SLOTS; ++sl) {
@@ -888,16 +925,19 @@ __device__ __noinline__ void build_map_variant(const float* __restrict__ s_theta
     const int hw = H * W;
     const int nt = blockDim.x;
     const int dj = nt / W, di = nt - dj * W;
+    const float Wf = static_cast<float>(W), Hf = static_cast<float>(H);
+    const float cx = 0.5f - 0.5f * Wf, cy = 0.5f - 0.5f * Hf;
+    const bool xy_exact = GD == UDAPE_F16 ? true : grid_xy_exact(W, H, grid_dtype);
     int p = threadIdx.x;
     int j0 = p / W, i0 = p - j0 * W;
 #pragma unroll 1
     for (; p < hw; p += nt) {
-        int i = i0, j = j0;
+        float fi = static_cast<float>(i0), fj = static_cast<float>(j0);
         bool ok = true;
 #pragma unroll 1
         for (int st = 0; st < stages && ok; ++st)
-            ok = stage_source_t<HM, GD>(i, j, s_theta + 6 * st, W, H, (half_mask >> st) & 1, grid_dtype);
-        map[p] = ok ? code(i, j) : none;
+            ok = stage_source_f<HM, GD>(fi, fj, s_theta + 6 * st, Wf, Hf, cx, cy, (half_mask >> st) & 1, grid_dtype, xy_exact);
+        map[p] = ok ? code(static_cast<int>(fi), static_cast<int>(fj)) : none;
         i0 += di; j0 += dj;
         if (i0 >= W) { i0 -= W; ++j0; }
     }
@@ -913,7 +953,10 @@ __device__ __forceinline__ void build_map_compact(const float* __restrict__ s_th
 }
 
 // dynamic smem: kRwRing padded plane buffers | uint16 map[hw8].  Single view, no paste / pass-through (the heatmap re-warps).
-template <typename T>
+// RING - 1 planes are in flight per CTA: with two CTAs per SM a ring of 3 keeps 32 KB of 8 KB fp16 planes in
+// flight per SM — 4.7 MB on the chip, which at ~1.5 us of loaded latency is 3.2 TB/s, exactly where the fp16
+// gather sat (51 % of the roofline) while the fp32 gather (16 KB planes) reached 80 %: fp16 / bf16 take a ring of 6.
+template <typename T, int RING>
 __global__ void __launch_bounds__(kWideThreads, 2)
 rewarp_wide_kernel(const RewarpArgs a, T* __restrict__ out, int buf_words) {
     constexpr int EPW = 4 / static_cast<int>(sizeof(T));
@@ -926,7 +969,7 @@ rewarp_wide_kernel(const RewarpArgs a, T* __restrict__ out, int buf_words) {
     if (threadIdx.x < a.stages * 6)
         s_theta[threadIdx.x] = a.view[0].theta[static_cast<int64_t>(b) * a.stages * 6 + threadIdx.x];
     const uint32_t zero_byte = static_cast<uint32_t>(buf_words - 4) * 4u;
-    if (threadIdx.x < kRwRing) rw_smem[threadIdx.x * buf_words + buf_words - 4] = 0u;   // out-of-bounds pixels gather from it
+    if (threadIdx.x < RING) rw_smem[threadIdx.x * buf_words + buf_words - 4] = 0u;   // out-of-bounds pixels gather from it
     __syncthreads();
     const int row_words = a.W / EPW, vpr = row_words / 4, nvec = nwords / 4;
     float J[4];
@@ -941,19 +984,19 @@ rewarp_wide_kernel(const RewarpArgs a, T* __restrict__ out, int buf_words) {
     }
     auto issue = [&](int it) {
         const uint4* src = reinterpret_cast<const uint4*>(static_cast<const T*>(a.view[0].in) + (static_cast<int64_t>(b) * a.C + it) * hw) + threadIdx.x;
-        const uint32_t dst = smem_u32(rw_smem + (it % kRwRing) * buf_words);
+        const uint32_t dst = smem_u32(rw_smem + (it % RING) * buf_words);
 #pragma unroll
         for (int q = 0; q < VEC; ++q)
             if (so[q] >= 0) cp_async16(dst + so[q], src + q * kWideThreads);
     };
     const int nitems = a.C;
 #pragma unroll
-    for (int it = 0; it < kRwRing - 1; ++it) {   // in flight while the map is computed
+    for (int it = 0; it < RING - 1; ++it) {   // in flight while the map is computed
         if (it < nitems) issue(it);
         cp_async_commit();
     }
     // the composed source of every pixel as a padded byte offset, then this thread's 8 (words t + NT*slot) in registers
-    uint16_t* map = reinterpret_cast<uint16_t*>(rw_smem + kRwRing * buf_words);
+    uint16_t* map = reinterpret_cast<uint16_t*>(rw_smem + RING * buf_words);
     build_map_compact(s_theta, a, map, static_cast<uint16_t>(zero_byte), [=](int i, int j) {
         return static_cast<uint16_t>(j * stride * 4 + i * static_cast<int>(sizeof(T)));
     });
@@ -972,11 +1015,11 @@ rewarp_wide_kernel(const RewarpArgs a, T* __restrict__ out, int buf_words) {
     }
     for (int it = 0; it < nitems; ++it) {
         uint32_t* o32 = reinterpret_cast<uint32_t*>(out + (static_cast<int64_t>(b) * a.C + it) * hw) + threadIdx.x;
-        cp_async_wait<kRwRing - 2>();   // this thread's copies of plane `it` have landed ...
+        cp_async_wait<RING - 2>();   // this thread's copies of plane `it` have landed ...
         __syncthreads();                // ... everybody's have, and everybody is done with plane it-1
-        if (it + kRwRing - 1 < nitems) issue(it + kRwRing - 1);
+        if (it + RING - 1 < nitems) issue(it + RING - 1);
         cp_async_commit();
-        const uint8_t* bytes = reinterpret_cast<const uint8_t*>(rw_smem + (it % kRwRing) * buf_words);
+        const uint8_t* bytes = reinterpret_cast<const uint8_t*>(rw_smem + (it % RING) * buf_words);
 #pragma unroll
         for (int sl = 0; sl < SLOTS; ++sl) {   // the values are moved, never converted
             uint32_t w32;
@@ -1201,11 +1244,12 @@ extern "C" int udape_rewarp_fwd(const void* const* in, const float* const* theta
     }
     if (buf_words && views == 1 && wide_route(B, hw)) {
         // wide route: one CTA of 512 threads per sample
-        const size_t smem = kRwRing * sizeof(uint32_t) * static_cast<size_t>(buf_words) + sizeof(uint16_t) * ((hw + 7) & ~7ll);
         UDAPE_DISPATCH_FLOAT(dtype, T, {
-            const int r2 = reserve_smem(rewarp_wide_kernel<T>, smem, "udape_rewarp_fwd");
+            constexpr int RING = sizeof(T) == 2 ? kWideRingHalf : kRwRing;
+            const size_t smem = RING * sizeof(uint32_t) * static_cast<size_t>(buf_words) + sizeof(uint16_t) * ((hw + 7) & ~7ll);
+            const int r2 = reserve_smem(rewarp_wide_kernel<T, RING>, smem, "udape_rewarp_fwd");
             if (r2) return r2;
-            rewarp_wide_kernel<T><<<static_cast<unsigned>(B), kWideThreads, smem, st>>>(a, static_cast<T*>(out), buf_words);
+            rewarp_wide_kernel<T, RING><<<static_cast<unsigned>(B), kWideThreads, smem, st>>>(a, static_cast<T*>(out), buf_words);
         });
         return check_launch("udape_rewarp_fwd");
     }
@@ -1278,11 +1322,12 @@ extern "C" int udape_rewarp_bwd(const void* grad_out, const float* theta, int st
         const int64_t per_sm = B * C >= 2048 ? 12 : 2;
         a.cpc = channels_per_cta(B, C, per_sm * static_cast<int64_t>(sm_count()));
         const int64_t grid = B * ((C + a.cpc - 1) / a.cpc);
-        const size_t smem = kRwRing * sizeof(uint32_t) * static_cast<size_t>(bw);
         UDAPE_DISPATCH_FLOAT(dtype, T, {
-            const int r2 = reserve_smem(rewarp_bwd_plan_kernel<T>, smem, "udape_rewarp_bwd");
+            constexpr int RING = sizeof(T) == 2 ? kWideRingHalf : kRwRing;
+            const size_t smem = RING * sizeof(uint32_t) * static_cast<size_t>(bw);
+            const int r2 = reserve_smem(rewarp_bwd_plan_kernel<T, RING>, smem, "udape_rewarp_bwd");
             if (r2) return r2;
-            rewarp_bwd_plan_kernel<T><<<static_cast<unsigned>(grid), kRwThreads, smem, st>>>(
+            rewarp_bwd_plan_kernel<T, RING><<<static_cast<unsigned>(grid), kRwThreads, smem, st>>>(
                 a, static_cast<const T*>(grad_out), static_cast<T*>(grad_in), bw, inverse_plan);
         });
         return check_launch("udape_rewarp_bwd");
