@@ -202,3 +202,43 @@ def test_product_package_does_not_import_the_oracle():
     for f in (ROOT / "uda_poseestimation_b200").rglob("*.py"):
         text = f.read_text()
         assert "reference_port" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_dp_host_helpers_and_argument_errors():
+    """The data-parallel entry points validate their arguments before touching CUDA; the slice geometry is a
+    host-only helper: S = a multiple of 4096 elements, world slices cover the bucket, the last one may be short."""
+    from uda_poseestimation_b200 import dp as DP
+    lib = _lib.load()
+    for n_total, world in [(52_991_568, 8), (52_991_568, 2), (4096, 8), (4100, 3), (64, 8), (8192 * 8, 8)]:
+        s = lib.udape_dp_shard_elems(n_total, world)
+        assert s % 4096 == 0 and s * world >= n_total and s * (world - 1) < max(n_total, 1) + 4096 * world
+    assert lib.udape_dp_shard_elems(100, 0) == -5 and lib.udape_dp_shard_elems(100, 9) == -5
+    offsets, total = DP.flat_layout([torch.zeros(3), torch.zeros(5, 2), torch.zeros(1), torch.zeros(8)])
+    assert offsets == [0, 4, 16, 20] and total == 28                     # every tensor starts on a 16-byte boundary
+    assert DP.arena_bytes(28) == DP.PAD_BYTES + 3 * 4 * 4096             # pad | grads | params | shadow, 4096-element granules
+    peers = _lib.DpPeers()
+    peers.rank, peers.world = 0, 2
+    fake = ctypes.c_void_p(0x1000)
+    h = _lib.OptHyper()
+    h.lr, h.beta1, h.beta2, h.eps, h.step = 1e-3, 0.9, 0.999, 1e-8, 1
+    # NULL pads / buffers
+    assert lib.udape_dp_barrier(ctypes.byref(peers), 0, fake, 0, None) == -1
+    for q in range(2):
+        peers.pads[q] = 0x10000 + 0x2000 * q
+    assert lib.udape_dp_barrier(ctypes.byref(peers), 9, fake, 0, None) == -5          # bad phase
+    assert lib.udape_dp_reduce_step(ctypes.byref(peers), 4096, _lib.OPT_ADAM, ctypes.byref(h), None, None, fake, fake, fake, fake, fake, None) == -1  # no buffers
+    for q in range(2):
+        peers.grads[q], peers.params[q], peers.shadow[q] = 0x100000 + 0x10000 * q, 0x200000 + 0x10000 * q, 0x300000 + 0x10000 * q
+    assert lib.udape_dp_reduce_step(ctypes.byref(peers), 4098, _lib.OPT_ADAM, ctypes.byref(h), None, None, fake, fake, fake, fake, fake, None) == -3  # n_total % 4
+    assert lib.udape_dp_reduce_step(ctypes.byref(peers), 4096, _lib.OPT_ADAM, ctypes.byref(h), None, None, fake, None, None, fake, fake, None) == -1  # Adam state
+    assert lib.udape_dp_gather_ema(ctypes.byref(peers), 4096, None, 0.9, 0.1, None, None, fake, fake, None) == -1                                   # step_dev
+    assert lib.udape_dp_allreduce_counts(ctypes.byref(peers), fake, 65, fake, fake, 0, None) == -3                                                     # > 64 counts
+    peers.world = 9
+    assert lib.udape_dp_wait(ctypes.byref(peers), 1, fake, None, 0, None) == -5
+    # multi-job entry points
+    assert lib.udape_gauss_target_multi(None, 1, 8, 2.0, 256.0, 256.0, None) == -1
+    jobs = (_lib.TargetJob * 1)()
+    assert lib.udape_gauss_target_multi(jobs, 9, 8, 2.0, 256.0, 256.0, None) == -5
+    assert lib.udape_gauss_target_multi(jobs, 1, 8, 2.0, 256.0, 256.0, None) == -1    # job with NULL pointers
+    assert lib.udape_adain_mix_multi(None, 1, 0, 8, 16, 16, 1e-5, None) == -1
+    assert lib.udape_table_feed(None, 1, 1, None, None, None) == -1

@@ -244,3 +244,25 @@ def test_step_at_c2_size_with_k2_views_graph(dev):
         _check(out, ref)
         for p, e in zip(teacher.parameters(), t_cpu):
             assert torch.equal(p.detach().cpu(), e)
+
+
+def test_ticket_words_are_zero_between_launches(dev):
+    """Self-resetting last-CTA tickets: after any number of launches every word of the pool is zero again; a word
+    left dirty (a launch that aborted mid-grid) is reported by check_tickets() and cleared by reset=True."""
+    from uda_poseestimation_b200 import _lib
+    host, inp = _inputs(dev, seed=31)
+    student, teacher = Bag(S.parameter_list([(64,)], 3)).to(dev), Bag(S.parameter_list([(64,)], 4)).to(dev)
+    step = HotPathStep(teacher, student, sigma=2)
+    for _ in range(3):
+        step.run(inp)
+    U.accuracy(inp.y_s, inp.label_s)
+    U.check_tickets()                                   # all zero
+    pool = _lib._ticket_pools[dev.index if dev.index is not None else torch.cuda.current_device()]
+    pool.buf[pool.SLOTS - 1] = 7                        # what an aborted launch would leave behind
+    with pytest.raises(U.UdapeError, match="ticket"):
+        U.check_tickets()
+    U.check_tickets(reset=True)
+    U.check_tickets()
+    out = step.run(inp)                                 # and the pool keeps working
+    torch.cuda.synchronize()
+    assert torch.isfinite(out["loss_all"]).all()

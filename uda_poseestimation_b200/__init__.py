@@ -26,7 +26,7 @@ Reference name → module here
                                                  reduce-scatter, sharded update and parameter all-gather + EMA
                                                  as peer-memory kernels over NVLink)
 """
-from ._lib import UdapeError, library_path, load as load_library
+from ._lib import UdapeError, check_tickets, library_path, load as load_library
 from .adain import (adain, adain_mix, adain_mix_multi, adaptive_instance_normalization, calc_mean_std, calc_style_loss,
                     channel_clamp)
 from .ema import ModelEMA, MultiTensorPlan, OldWeightEMA
@@ -44,7 +44,7 @@ from .rewarp import affine_nearest, occlude_keypoints, student_recon, teacher_re
 __version__ = "0.3.0"
 
 __all__ = [
-    "UdapeError", "library_path", "load_library",
+    "UdapeError", "library_path", "load_library", "check_tickets",
     "calc_mean_std", "calc_style_loss", "adaptive_instance_normalization", "adain", "adain_mix", "adain_mix_multi", "channel_clamp",
     "get_max_preds", "get_max_preds_torch", "calc_dists", "dist_acc", "accuracy", "pck_counts",
     "accuracy_from_counts", "decode",

@@ -300,6 +300,27 @@ class _TicketPool:
 _ticket_pools: dict = {}
 
 
+def check_tickets(reset: bool = False) -> None:
+    """Every ticket word must be zero between launches ("ticket must be zero on entry; the call leaves it zero").
+    A launch that aborted mid-grid (a sticky CUDA error, a killed context) can leave one non-zero, and every later
+    reduction that draws that slot would elect the wrong "last CTA" without any other symptom.  Call this after
+    recovering from a CUDA error, or at checkpoints (it synchronises the device): raises ``UdapeError`` naming the
+    dirty slots; ``reset=True`` zeroes them instead (only when no launch is in flight)."""
+    with _lock:
+        pools = list(_ticket_pools.items())
+    for idx, pool in pools:
+        with torch.cuda.device(idx):
+            torch.cuda.synchronize(idx)
+            bufs = [pool.buf] + list(pool.spill)
+            dirty = [(i, int(n)) for i, b in enumerate(bufs) for n in torch.nonzero(b).flatten().tolist()]
+            if dirty and reset:
+                for b in bufs:
+                    b.zero_()
+            elif dirty:
+                raise UdapeError(f"cuda:{idx}: {len(dirty)} ticket word(s) are not zero between launches (buffer, slot): "
+                                 f"{dirty[:8]} — a launch aborted mid-grid; call check_tickets(reset=True) after recovery")
+
+
 def ticket(dev: torch.device) -> int:
     """Device address of a zeroed, self-resetting uint32 ticket word on ``dev``."""
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
