@@ -169,6 +169,12 @@ template <> __device__ __forceinline__ uint4 pack16<__nv_bfloat16>(const float* 
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// 32-bit streaming load (lane-consecutive words: still 128 bytes per warp)
+__device__ __forceinline__ uint32_t ldg_stream_u32(const void* p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
 // 64-bit streaming access (the narrow operand of a mixed-dtype pair)
 __device__ __forceinline__ uint2 ldg_stream8(const void* p) {
     uint2 r;

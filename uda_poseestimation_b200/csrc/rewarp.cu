@@ -671,142 +671,6 @@ __device__ __forceinline__ void redo_long_lists(uint32_t mask, const uint16_t* _
     }
 }
 
-// ---- the inverse plan: what the backward needs, computed once (by the forward) and kept in global memory
-// per sample, uint16:  hdr[8] = {stride, any list > 4 entries, any list > 2 entries, ...} | slots[hw][4] | off[hw8] | lst[hw8]
-__host__ __device__ inline int64_t plan_elems_for(int64_t hw) { return 8 + 4 * hw + 2 * ((hw + 7) & ~7ll); }
-
-// dynamic smem: uint16 off[hw + 8] | lst_loc[hw] | map[hw] (-> lst)
-template <int ES>
-__global__ void __launch_bounds__(kRwThreads)
-rewarp_inverse_plan_kernel(const RewarpArgs a, uint16_t* __restrict__ plan, int buf_words) {
-    constexpr int EPW = 4 / ES;
-    extern __shared__ __align__(16) uint32_t rw_smem[];
-    __shared__ float s_theta[kRwMaxStages * 6];
-    __shared__ uint32_t s_scan[kRwThreads];
-    cg::cluster_group cluster = cg::this_cluster();
-    const int nrank = static_cast<int>(cluster.num_blocks()), rank = static_cast<int>(cluster.block_rank());
-    const int hw = a.H * a.W, hw8 = (hw + 7) & ~7;
-    uint16_t* off = reinterpret_cast<uint16_t*>(rw_smem);
-    uint16_t* lst_loc = off + ((hw + 8 + 7) & ~7);
-    uint16_t* map = lst_loc + hw8;
-    const uint16_t* lst = map;
-    const int b = blockIdx.x / nrank;
-    if (threadIdx.x < a.stages * 6)
-        s_theta[threadIdx.x] = a.view[0].theta[static_cast<int64_t>(b) * a.stages * 6 + threadIdx.x];
-    uint32_t* off32 = reinterpret_cast<uint32_t*>(off);
-    for (int s = threadIdx.x; s < (hw + 8) / 2; s += kRwThreads) off32[s] = 0u;
-    __syncthreads();
-    float J[4];
-    composed_jacobian(s_theta, a, J);
-    const float det = J[0] * J[3] - J[1] * J[2];
-    const float inv = det != 0.0f ? 1.0f / det : 0.0f;
-    const int stride = pick_stride(a.W / EPW, J[3] * inv, -J[2] * inv, EPW - 1);   // see rewarp_bwd_smem_kernel
-    cluster_invert<ES>(cluster, s_theta, a, stride, off, lst_loc, map, s_scan);
-    // every CTA writes its slice of the plan
-    uint16_t* P = plan + static_cast<int64_t>(b) * plan_elems_for(hw);
-    uint16_t* g_slots = P + 8;
-    uint16_t* g_off = g_slots + 4 * static_cast<int64_t>(hw);
-    uint16_t* g_lst = g_off + hw8;
-    const uint32_t zero_byte = static_cast<uint32_t>(buf_words - 4) * 4u;
-    const int slice_log2 = ceil_log2((hw + nrank - 1) / nrank);
-    const int lo = min(hw, rank << slice_log2), hi = min(hw, (rank + 1) << slice_log2);
-    for (int s = lo + threadIdx.x; s < hi; s += kRwThreads) {
-        bool overflow;
-        *reinterpret_cast<uint2*>(g_slots + 4 * static_cast<int64_t>(s)) = list_slots(off, lst, s, zero_byte, overflow);
-    }
-    for (int v = threadIdx.x; v < (hi - lo) / 8; v += kRwThreads) {
-        reinterpret_cast<uint4*>(g_off + lo)[v] = reinterpret_cast<const uint4*>(off + lo)[v];
-        reinterpret_cast<uint4*>(g_lst + lo)[v] = reinterpret_cast<const uint4*>(lst + lo)[v];
-    }
-    if (rank == 0) {
-        // the header: rank 0 looks at every list length (16 per thread)
-        bool any4 = false, any2 = false;
-        for (int s = threadIdx.x; s < hw; s += kRwThreads) {
-            const int len = off[s] - (s == 0 ? 0 : off[s - 1]);
-            any4 |= len > 4;
-            any2 |= len > 2;
-        }
-        const int f4 = __syncthreads_or(any4), f2 = __syncthreads_or(any2);
-        if (threadIdx.x < 8)
-            P[threadIdx.x] = threadIdx.x == 0 ? static_cast<uint16_t>(stride) : (threadIdx.x == 1 ? f4 : (threadIdx.x == 2 ? f2 : 0));
-    }
-}
-
-// backward from the plan: no cluster, no inversion — slots from global memory, gradient planes staged
-// through the padded ring.  dynamic smem: kRwRing plane buffers
-template <typename T, int RING>   // RING - 1 gradient planes in flight per CTA: 6 for the 8 KB fp16 planes, see rewarp_wide_kernel
-__global__ void __launch_bounds__(kRwThreads)   // (capping at 85 registers for 3 CTAs/SM spills and is slower: 17.6 vs 14.7 us)
-rewarp_bwd_plan_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __restrict__ gin, int buf_words,
-                       const uint16_t* __restrict__ plan) {
-    constexpr int EPW = 4 / static_cast<int>(sizeof(T));
-    constexpr int SLOTS = kRwPix / EPW;
-    extern __shared__ __align__(16) uint32_t rw_smem[];
-    const int hw = a.H * a.W, nwords = hw / EPW, hw8 = (hw + 7) & ~7;
-    const int groups = (a.C + a.cpc - 1) / a.cpc;
-    const int b = blockIdx.x / groups, cgp = blockIdx.x - b * groups;
-    const int c0 = cgp * a.cpc, c1 = min(a.C, c0 + a.cpc);
-    const uint16_t* P = plan + static_cast<int64_t>(b) * plan_elems_for(hw);
-    const uint16_t* g_slots = P + 8;
-    const uint16_t* g_off = g_slots + 4 * static_cast<int64_t>(hw);
-    const uint16_t* g_lst = g_off + hw8;
-    const int stride = P[0];
-    const bool any_overflow = P[1] != 0;
-    const bool deep = P[2] != 0;   // zoom-out samples: no source pixel has more than two contributors
-    if (threadIdx.x < RING) rw_smem[threadIdx.x * buf_words + buf_words - 4] = 0u;   // the zero word of every buffer
-    const int row_words = a.W / EPW, vpr = row_words / 4, nvec = nwords / 4;
-    int so[kRwMaxVec];
-    stage_offsets(so, nvec, vpr, stride);
-    auto issue = [&](int it) {
-        stage_issue<T>(smem_u32(rw_smem + (it % RING) * buf_words), so, gout + (static_cast<int64_t>(b) * a.C + c0 + it) * hw);
-    };
-    const int nitems = c1 - c0;
-#pragma unroll
-    for (int it = 0; it < RING - 1; ++it) {
-        if (it < nitems) issue(it);
-        cp_async_commit();
-    }
-    uint2 slot[kRwPix];
-    uint32_t long_mask = 0;
-#pragma unroll
-    for (int k = 0; k < kRwPix; ++k) {
-        const int word = (k / EPW) * kRwThreads + threadIdx.x;
-        const int s = word * EPW + (k % EPW);
-        const uint32_t z = static_cast<uint32_t>(buf_words - 4) * 4u;
-        slot[k] = word < nwords ? __ldg(reinterpret_cast<const uint2*>(g_slots + 4 * static_cast<int64_t>(s)))
-                                : make_uint2(z | (z << 16), z | (z << 16));
-        if (any_overflow && word < nwords && g_off[s] - (s == 0 ? 0 : g_off[s - 1]) > 4) long_mask |= 1u << k;
-    }
-    for (int it = 0; it < nitems; ++it) {
-        cp_async_wait<RING - 2>();
-        __syncthreads();
-        if (it + RING - 1 < nitems) issue(it + RING - 1);
-        cp_async_commit();
-        const uint8_t* bytes = reinterpret_cast<const uint8_t*>(rw_smem + (it % RING) * buf_words);
-        T* o = gin + (static_cast<int64_t>(b) * a.C + c0 + it) * hw;
-#pragma unroll
-        for (int sl = 0; sl < SLOTS; ++sl) {
-            float f[EPW];
-#pragma unroll
-            for (int e = 0; e < EPW; ++e) {
-                const uint2 sq = slot[sl * EPW + e];
-                const float v0 = to_f32<T>(*reinterpret_cast<const T*>(bytes + (sq.x & 0xffffu)));
-                const float v1 = to_f32<T>(*reinterpret_cast<const T*>(bytes + (sq.x >> 16)));
-                float sum = v0 + v1;   // ascending p, fp32, one rounding to T
-                if (deep) {            // CTA-uniform
-                    const float v2 = to_f32<T>(*reinterpret_cast<const T*>(bytes + (sq.y & 0xffffu)));
-                    const float v3 = to_f32<T>(*reinterpret_cast<const T*>(bytes + (sq.y >> 16)));
-                    sum = (sum + v2) + v3;
-                }
-                f[e] = sum;
-            }
-            const int word = sl * kRwThreads + threadIdx.x;
-            if (word < nwords) store_word<T>(o, word, f);
-        }
-        redo_long_lists<T>(long_mask, g_off, g_lst, bytes, o);
-    }
-    cp_async_wait<0>();
-}
-
 // heatmap route (planes up to 4096 px): gradient planes staged through padded shared memory; the
 // CTAs of a sample form a cluster and build the composed map together (see rewarp_smem_kernel).
 // dynamic smem: kRwRing plane buffers | uint16 off[hw + 8] | lst_loc[hw] | map[hw] (-> lst)
@@ -950,6 +814,437 @@ __device__ __forceinline__ void build_map_compact(const float* __restrict__ s_th
         if (a.grid_dtype == UDAPE_F16) build_map_variant<1, UDAPE_F16>(s_theta, a.W, a.H, a.stages, a.half_mask, a.grid_dtype, map, none, code);
         else build_map_variant<1, UDAPE_BF16>(s_theta, a.W, a.H, a.stages, a.half_mask, a.grid_dtype, map, none, code);
     } else build_map_variant<2, -1>(s_theta, a.W, a.H, a.stages, a.half_mask, a.grid_dtype, map, none, code);
+}
+
+// ---- the push plan: what the backward needs, computed once per batch and kept in global memory ----------------
+// The backward is a SCATTER  grad_in[src(p)] += grad_out[p].  It is made deterministic — and free of atomics,
+// sorting and per-pixel branches — by giving every output pixel p its own SLOT in shared memory:
+//   * the first contributor of a source pixel (rank 0, the smallest p) is stored straight into the padded fp32
+//     accumulator plane at the source pixel;
+//   * every later contributor (rank >= 1) is stored into a TAIL array ordered by (source pixel, rank);
+//   * pixels without a source are stored into a dummy word.
+// One barrier later the thread that owns a GROUP (a source pixel with two or more contributors) folds the group's
+// tail entries — contiguous, ascending p — into the accumulator:  ((v0 + v1) + v2) + ...  the same fp32 order, bit
+// for bit, as the list-based kernels below and as a sequential CPU scatter.  Source pixels without contributors
+// keep the zero the previous read-out left.
+//   per sample, uint16 units:  hdr[8] = {row stride of the accumulator plane in words, groups, tail entries,
+//                                        groups with a single tail entry, 0 ...}
+//                              | uint16 code[hw8]        byte offset of pixel p's slot in a plane's shared memory
+//                              | uint2  group[hw8/2]     {source-pixel byte offset | first tail slot << 16, tail entries};
+//                                                        the groups with ONE tail entry first (their warps run no
+//                                                        inner loop), then the longer ones, each part in source order
+// The ranks come from max-key rounds in shared memory (integer atomicMax, scheduling-independent): in round r every
+// pending pixel offers key = (r+1) << 16 | (0xffff - p) to owner[src]; the largest key of the round is the smallest
+// pending p, it takes rank r and retires.  Keys of earlier rounds are smaller than any key of round r, so owner[]
+// is never cleared, and after the last round owner[src] >> 16 is the contributor count of src.
+// (Measured on B200 with the reference's augmentation range — rotation 180, scale .6-1.3, shear 30: a sample has
+// ~1400 tail entries and lists of up to 16; rank-by-rank scatter rounds straight from registers, the first
+// version of this kernel, spent 20 instructions per pixel on divergent per-rank branches: 93-135 us at C5.)
+__host__ __device__ inline int64_t plan_elems_for(int64_t hw) { const int64_t hw8 = (hw + 7) & ~7ll; return 8 + 3 * hw8; }
+// shared memory of one plane in the backward: accumulator plane | tail (one slot per pixel) | dummy word (16 bytes)
+__host__ __device__ inline int push_pitch_bytes(int acc_words, int hw) { return acc_words * 4 + ((hw + 7) & ~7) * 4 + 16; }
+
+constexpr int kPlanThreads = 512;
+constexpr int kPlanPix = 8;   // pixels per thread: planes up to 4096 px
+
+// dynamic smem: uint32 owner[acc_words] | uint16 map[hw8]
+template <int ES>
+__global__ void __launch_bounds__(kPlanThreads, 2)
+rewarp_push_plan_kernel(const RewarpArgs a, uint16_t* __restrict__ plan, int acc_words) {
+    constexpr int EPW = 4 / ES;
+    extern __shared__ __align__(16) uint32_t rw_smem[];
+    __shared__ float s_theta[kRwMaxStages * 6];
+    __shared__ uint32_t s_warp[kPlanThreads / 32], s_warp_t[kPlanThreads / 32];
+    const int hw = a.H * a.W, hw8 = (hw + 7) & ~7;
+    const int b = blockIdx.x;
+    uint32_t* owner = rw_smem;
+    uint16_t* map = reinterpret_cast<uint16_t*>(rw_smem + acc_words);
+    if (threadIdx.x < a.stages * 6)
+        s_theta[threadIdx.x] = a.view[0].theta[static_cast<int64_t>(b) * a.stages * 6 + threadIdx.x];
+    for (int i = threadIdx.x; i < acc_words / 4; i += kPlanThreads) reinterpret_cast<uint4*>(owner)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    // the backward's lanes own consecutive 32-bit words of the gradient plane (EPW pixels): one lane step moves
+    // the source by EPW columns of the composed Jacobian
+    float J[4];
+    composed_jacobian(s_theta, a, J);
+    const int stride = pick_stride(a.W, static_cast<float>(EPW) * J[0], static_cast<float>(EPW) * J[2], 0);
+    build_map_compact(s_theta, a, map, static_cast<uint16_t>(0xffffu), [=](int i, int j) {
+        return static_cast<uint16_t>((j * stride + i) * 4);
+    });
+    __syncthreads();
+    // 1. ranks
+    uint32_t code[kPlanPix];   // source byte offset | rank << 16 ; 0xffffffff: no source
+    uint32_t pending = 0;
+#pragma unroll
+    for (int k = 0; k < kPlanPix; ++k) {
+        const int p = k * kPlanThreads + threadIdx.x;
+        code[k] = p < hw ? map[p] : 0xffffu;
+        if (code[k] != 0xffffu) pending |= 1u << k;
+        else code[k] = 0xffffffffu;
+    }
+    for (uint32_t r = 0;; ++r) {
+        const uint32_t key_hi = (r + 1) << 16;
+#pragma unroll
+        for (int k = 0; k < kPlanPix; ++k)
+            if (pending & (1u << k)) atomicMax(&owner[code[k] >> 2], key_hi | (0xffffu - static_cast<uint32_t>(k * kPlanThreads + threadIdx.x)));
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kPlanPix; ++k)
+            if ((pending & (1u << k)) && owner[code[k] >> 2] == (key_hi | (0xffffu - static_cast<uint32_t>(k * kPlanThreads + threadIdx.x)))) {
+                code[k] |= r << 16;
+                pending &= ~(1u << k);
+            }
+        if (!__syncthreads_or(pending != 0)) break;   // also: this round's reads are over before the next round's atomics
+    }
+    // 2. groups (source pixels with >= 2 contributors): exclusive scans of (single-tail groups | longer groups << 16)
+    //    and of the tail entries over the accumulator words, a contiguous run per thread
+    const int per = (acc_words + kPlanThreads - 1) / kPlanThreads;
+    const int lo = min(acc_words, static_cast<int>(threadIdx.x) * per), hi = min(acc_words, lo + per);
+    uint32_t run_g = 0, run_t = 0;
+    for (int w = lo; w < hi; ++w) {
+        const uint32_t cnt = owner[w] >> 16;
+        if (cnt >= 2u) { run_g += cnt == 2u ? 1u : (1u << 16); run_t += cnt - 1u; }
+    }
+    uint32_t incl_g = run_g, incl_t = run_t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t tg = __shfl_up_sync(0xffffffffu, incl_g, o), tt = __shfl_up_sync(0xffffffffu, incl_t, o);
+        if (static_cast<int>(threadIdx.x & 31) >= o) { incl_g += tg; incl_t += tt; }
+    }
+    if ((threadIdx.x & 31) == 31) { s_warp[threadIdx.x >> 5] = incl_g; s_warp_t[threadIdx.x >> 5] = incl_t; }
+    __syncthreads();
+    uint32_t base_g = 0, base_t = 0, total_g = 0, total_t = 0;
+#pragma unroll
+    for (int q = 0; q < kPlanThreads / 32; ++q) {
+        const uint32_t tg = s_warp[q], tt = s_warp_t[q];
+        if (q < static_cast<int>(threadIdx.x >> 5)) { base_g += tg; base_t += tt; }
+        total_g += tg; total_t += tt;
+    }
+    const uint32_t nsingle = total_g & 0xffffu, ngroups = nsingle + (total_g >> 16);
+    uint16_t* P = plan + static_cast<int64_t>(b) * plan_elems_for(hw);
+    uint16_t* g_code = P + 8;
+    uint2* g_group = reinterpret_cast<uint2*>(P + 8 + hw8);
+    run_g = base_g + incl_g - run_g;   // exclusive
+    run_t = base_t + incl_t - run_t;
+    for (int w = lo; w < hi; ++w) {
+        const uint32_t cnt = owner[w] >> 16;
+        if (cnt >= 2u) {
+            const uint32_t gi = cnt == 2u ? (run_g & 0xffffu) : nsingle + (run_g >> 16);
+            g_group[gi] = make_uint2(static_cast<uint32_t>(w * 4) | (run_t << 16), cnt - 1u);
+            owner[w] = run_t;        // read back by the group's contributors below
+            run_g += cnt == 2u ? 1u : (1u << 16);
+            run_t += cnt - 1u;
+        }
+    }
+    __syncthreads();
+    // 3. slots
+    const uint32_t tail0 = static_cast<uint32_t>(acc_words) * 4u, dummy = tail0 + static_cast<uint32_t>(hw8) * 4u;
+#pragma unroll
+    for (int k = 0; k < kPlanPix; ++k) {
+        const int p = k * kPlanThreads + threadIdx.x;
+        uint32_t slot = dummy;
+        if (code[k] != 0xffffffffu) {
+            const uint32_t src = code[k] & 0xffffu, rk = code[k] >> 16;
+            slot = rk == 0u ? src : tail0 + (owner[src >> 2] + rk - 1u) * 4u;
+        }
+        if (p < hw8) g_code[p] = static_cast<uint16_t>(slot);
+    }
+    if (threadIdx.x < 8) {
+        const uint32_t t = threadIdx.x;
+        P[t] = static_cast<uint16_t>(t == 0 ? static_cast<uint32_t>(stride) : (t == 1 ? ngroups : (t == 2 ? total_t : (t == 3 ? nsingle : 0u))));
+    }
+}
+
+template <typename T> __device__ __forceinline__ float word_elem(uint32_t w, int e);
+template <> __device__ __forceinline__ float word_elem<float>(uint32_t w, int) { return __uint_as_float(w); }
+template <> __device__ __forceinline__ float word_elem<__half>(uint32_t w, int e) {
+    return __half2float(__ushort_as_half(static_cast<unsigned short>(e ? (w >> 16) : (w & 0xffffu))));
+}
+template <> __device__ __forceinline__ float word_elem<__nv_bfloat16>(uint32_t w, int e) {
+    return __uint_as_float(e ? (w & 0xffff0000u) : (w << 16));
+}
+// four accumulators -> four elements of T, stored at vector index vi of the plane; "+ 0" turns a lone -0.0 into
+// +0.0 like the zero-initialised scatter target of the reference (done on the packed pairs for the 2-byte types)
+template <typename T> __device__ __forceinline__ void store_quad(T* __restrict__ plane, int vi, float4 x);
+template <> __device__ __forceinline__ void store_quad<float>(float* __restrict__ plane, int vi, float4 x) {
+    x.x = __fadd_rn(x.x, 0.0f); x.y = __fadd_rn(x.y, 0.0f); x.z = __fadd_rn(x.z, 0.0f); x.w = __fadd_rn(x.w, 0.0f);
+    reinterpret_cast<float4*>(plane)[vi] = x;
+}
+template <> __device__ __forceinline__ void store_quad<__half>(__half* __restrict__ plane, int vi, float4 x) {
+    const __half2 z = __floats2half2_rn(0.0f, 0.0f);
+    const __half2 lo = __hadd2(__floats2half2_rn(x.x, x.y), z), hi = __hadd2(__floats2half2_rn(x.z, x.w), z);
+    reinterpret_cast<uint2*>(plane)[vi] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+}
+template <> __device__ __forceinline__ void store_quad<__nv_bfloat16>(__nv_bfloat16* __restrict__ plane, int vi, float4 x) {
+    const __nv_bfloat162 z = __floats2bfloat162_rn(0.0f, 0.0f);
+    const __nv_bfloat162 lo = __hadd2(__floats2bfloat162_rn(x.x, x.y), z), hi = __hadd2(__floats2bfloat162_rn(x.z, x.w), z);
+    reinterpret_cast<uint2*>(plane)[vi] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+}
+
+// backward from the push plan.  The work is cut into PASSES of NP gradient planes of one sample; the grid is one
+// wave of CTAs and CTA i owns a contiguous, equal share of the passes (a sample's passes may be split between
+// CTAs; a CTA reloads its per-sample state — 8 registers of slots — when its run crosses into the next sample).
+// Per pass: the planes come straight from global memory into registers (coalesced 32-bit words; the next pass's
+// loads are issued as soon as the registers are free), every pixel is pushed into its slot, the groups are
+// folded, and the accumulators are read out with 128-bit loads (re-zeroed in the same instruction pair) and
+// stored coalesced.  dynamic smem: NP x (float acc[acc_words] | float tail[hw8] | 16 bytes)
+template <typename T, int NP>
+__global__ void __launch_bounds__(kRwThreads, 3)
+rewarp_bwd_push_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __restrict__ gin, int acc_words,
+                       const uint16_t* __restrict__ plan) {
+    constexpr int EPW = 4 / static_cast<int>(sizeof(T));
+    constexpr int SLOTS = kRwPix / EPW;
+    constexpr int QUADS = kRwPix / 4;
+    extern __shared__ __align__(16) uint32_t rw_smem[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(rw_smem);
+    const int hw = a.H * a.W, hw8 = (hw + 7) & ~7, nwords = hw / EPW, nquads = hw / 4;
+    const int ppc = (a.C + NP - 1) / NP;                      // passes per sample
+    const int64_t npass = static_cast<int64_t>(a.B) * ppc;
+    const int pass0 = static_cast<int>(npass * blockIdx.x / gridDim.x), pass1 = static_cast<int>(npass * (blockIdx.x + 1) / gridDim.x);
+    if (pass0 >= pass1) return;
+    const int pitch = push_pitch_bytes(acc_words, hw);
+    const uint32_t tail0 = static_cast<uint32_t>(acc_words) * 4u, dummy = tail0 + static_cast<uint32_t>(hw8) * 4u;
+    // the accumulator quads this thread reads out: row and 4 * column of quad t + 256 * v
+    int ro_row[QUADS], ro_col[QUADS];
+#pragma unroll
+    for (int v = 0; v < QUADS; ++v) {
+        const int vi = v * kRwThreads + threadIdx.x;
+        ro_row[v] = vi < nquads ? (vi * 4) / a.W : -1;
+        ro_col[v] = (vi * 4 - ro_row[v] * a.W) * 4;
+    }
+#pragma unroll
+    for (int n = 0; n < NP; ++n)
+        for (int i = threadIdx.x; i < acc_words / 4; i += kRwThreads) reinterpret_cast<uint4*>(smem + n * pitch)[i] = make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t* g32 = reinterpret_cast<const uint32_t*>(gout);
+    uint32_t g[NP][SLOTS];
+    auto load = [&](int pass) {
+        const int b = pass / ppc, c = (pass - b * ppc) * NP;
+#pragma unroll
+        for (int n = 0; n < NP; ++n) {
+            const uint32_t* src = g32 + (static_cast<int64_t>(b) * a.C + c + n) * nwords + threadIdx.x;
+#pragma unroll
+            for (int sl = 0; sl < SLOTS; ++sl)
+                g[n][sl] = (c + n < a.C && sl * kRwThreads + static_cast<int>(threadIdx.x) < nwords) ? ldg_stream_u32(src + sl * kRwThreads) : 0u;
+        }
+    };
+    load(pass0);
+    uint32_t cw[kRwPix / 2];   // this thread's pixels: word t + 256*slot of every plane, EPW pixels per word; two 16-bit slots per register
+    int cur_b = -1, stride4 = 0, ngroups = 0;
+    const uint2* g_group = nullptr;
+    __syncthreads();
+    for (int pass = pass0; pass < pass1; ++pass) {
+        const int b = pass / ppc, c = (pass - b * ppc) * NP;
+        const int np = min(NP, a.C - c);
+        if (b != cur_b) {   // CTA-uniform: the per-sample state
+            cur_b = b;
+            const uint16_t* P = plan + static_cast<int64_t>(b) * plan_elems_for(hw);
+            const uint16_t* g_code = P + 8;
+            g_group = reinterpret_cast<const uint2*>(P + 8 + hw8);
+            stride4 = 4 * static_cast<int>(P[0]);
+            ngroups = P[1];
+#pragma unroll
+            for (int m = 0; m < kRwPix / 2; ++m) {
+                if constexpr (EPW == 2) {
+                    const int word = m * kRwThreads + threadIdx.x;
+                    cw[m] = word < nwords ? __ldg(reinterpret_cast<const uint32_t*>(g_code) + word) : (dummy | (dummy << 16));
+                } else {
+                    const int w0 = (2 * m) * kRwThreads + threadIdx.x, w1 = (2 * m + 1) * kRwThreads + threadIdx.x;
+                    const uint32_t lo = w0 < nwords ? __ldg(g_code + w0) : dummy, hi = w1 < nwords ? __ldg(g_code + w1) : dummy;
+                    cw[m] = lo | (hi << 16);
+                }
+            }
+        }
+        // push: every pixel into its own slot
+#pragma unroll
+        for (int k = 0; k < kRwPix; ++k) {
+            const uint32_t off = (cw[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+#pragma unroll
+            for (int n = 0; n < NP; ++n) *reinterpret_cast<float*>(smem + n * pitch + off) = word_elem<T>(g[n][k / EPW], k % EPW);
+        }
+        __syncthreads();
+        if (pass + 1 < pass1) load(pass + 1);   // in flight while the groups are folded and the sums leave
+        // groups: tails folded in ascending p
+        for (int i = threadIdx.x; i < ngroups; i += kRwThreads) {
+            const uint2 e = __ldg(g_group + i);
+            const uint32_t q = e.x & 0xffffu;
+            uint32_t t = tail0 + (e.x >> 16) * 4u;
+            float acc[NP];
+#pragma unroll
+            for (int n = 0; n < NP; ++n) acc[n] = *reinterpret_cast<const float*>(smem + n * pitch + q);
+#pragma unroll 1
+            for (uint32_t j = e.y; j != 0u; --j, t += 4u) {
+#pragma unroll
+                for (int n = 0; n < NP; ++n) acc[n] += *reinterpret_cast<const float*>(smem + n * pitch + t);
+            }
+#pragma unroll
+            for (int n = 0; n < NP; ++n) *reinterpret_cast<float*>(smem + n * pitch + q) = acc[n];
+        }
+        __syncthreads();
+        // read-out: the sums leave as T, the accumulators return to zero for the next pass
+#pragma unroll
+        for (int v = 0; v < QUADS; ++v) {
+            if (ro_row[v] >= 0) {
+                const int ro = ro_row[v] * stride4 + ro_col[v];
+#pragma unroll
+                for (int n = 0; n < NP; ++n) {
+                    if (n < np) {
+                        float4* sp = reinterpret_cast<float4*>(smem + n * pitch + ro);
+                        const float4 x = *sp;
+                        *sp = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        store_quad<T>(gin + (static_cast<int64_t>(b) * a.C + c + n) * hw, v * kRwThreads + threadIdx.x, x);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// The same backward for the 2-byte types, with TWO planes per 32-bit slot.  A slot only has to hold a pixel's
+// ORIGINAL value: the sums are formed in fp32 registers by the thread that folds a group (ascending p, exactly as
+// above) and rounded to T once — so nothing is lost by keeping the slots in T, and the planes (2m, 2m+1) of a pass
+// share one word per slot: one PRMT + one STS pushes a pixel of both planes, shared-memory traffic per pixel halves
+// (the scatter's bank conflicts made shared-memory wavefronts the floor of the fp32-slot version: 18 us of 38 at
+// C5), and a pass covers 2 * NPAIR planes in the footprint of NPAIR.
+// dynamic smem: NPAIR x (uint32 acc[acc_words] | uint32 tail[hw8] | 16 bytes)
+template <typename T> struct Pair2;
+template <> struct Pair2<__half> {
+    static __device__ __forceinline__ float lo(uint32_t w) { return __half2float(__ushort_as_half(static_cast<unsigned short>(w & 0xffffu))); }
+    static __device__ __forceinline__ float hi(uint32_t w) { return __half2float(__ushort_as_half(static_cast<unsigned short>(w >> 16))); }
+    static __device__ __forceinline__ uint32_t pack(float a, float b) { const __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h); }
+    static __device__ __forceinline__ uint32_t plus_zero(uint32_t w) {   // -0.0 -> +0.0 in both halves
+        const __half2 z = __floats2half2_rn(0.0f, 0.0f);
+        const __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&w), z);
+        return *reinterpret_cast<const uint32_t*>(&r);
+    }
+};
+template <> struct Pair2<__nv_bfloat16> {
+    static __device__ __forceinline__ float lo(uint32_t w) { return __uint_as_float(w << 16); }
+    static __device__ __forceinline__ float hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+    static __device__ __forceinline__ uint32_t pack(float a, float b) { const __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h); }
+    static __device__ __forceinline__ uint32_t plus_zero(uint32_t w) {
+        const __nv_bfloat162 z = __floats2bfloat162_rn(0.0f, 0.0f);
+        const __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&w), z);
+        return *reinterpret_cast<const uint32_t*>(&r);
+    }
+};
+
+template <typename T, int NPAIR>
+__global__ void __launch_bounds__(kRwThreads, 3)
+rewarp_bwd_push2_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __restrict__ gin, int acc_words,
+                        const uint16_t* __restrict__ plan) {
+    static_assert(sizeof(T) == 2, "packed pairs of 2-byte elements");
+    constexpr int NP = 2 * NPAIR;
+    constexpr int SLOTS = kRwPix / 2;
+    constexpr int QUADS = kRwPix / 4;
+    extern __shared__ __align__(16) uint32_t rw_smem[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(rw_smem);
+    const int hw = a.H * a.W, hw8 = (hw + 7) & ~7, nwords = hw / 2, nquads = hw / 4;
+    const int ppc = (a.C + NP - 1) / NP;                      // passes per sample
+    const int64_t npass = static_cast<int64_t>(a.B) * ppc;
+    const int pass0 = static_cast<int>(npass * blockIdx.x / gridDim.x), pass1 = static_cast<int>(npass * (blockIdx.x + 1) / gridDim.x);
+    if (pass0 >= pass1) return;
+    const int pitch = push_pitch_bytes(acc_words, hw);
+    const uint32_t tail0 = static_cast<uint32_t>(acc_words) * 4u, dummy = tail0 + static_cast<uint32_t>(hw8) * 4u;
+    int ro_row[QUADS], ro_col[QUADS];
+#pragma unroll
+    for (int v = 0; v < QUADS; ++v) {
+        const int vi = v * kRwThreads + threadIdx.x;
+        ro_row[v] = vi < nquads ? (vi * 4) / a.W : -1;
+        ro_col[v] = (vi * 4 - ro_row[v] * a.W) * 4;
+    }
+#pragma unroll
+    for (int m = 0; m < NPAIR; ++m)
+        for (int i = threadIdx.x; i < acc_words / 4; i += kRwThreads) reinterpret_cast<uint4*>(smem + m * pitch)[i] = make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t* g32 = reinterpret_cast<const uint32_t*>(gout);
+    uint32_t g[NP][SLOTS];
+    auto load = [&](int pass) {
+        const int b = pass / ppc, c = (pass - b * ppc) * NP;
+#pragma unroll
+        for (int n = 0; n < NP; ++n) {
+            const uint32_t* src = g32 + (static_cast<int64_t>(b) * a.C + c + n) * nwords + threadIdx.x;
+#pragma unroll
+            for (int sl = 0; sl < SLOTS; ++sl)
+                g[n][sl] = (c + n < a.C && sl * kRwThreads + static_cast<int>(threadIdx.x) < nwords) ? ldg_stream_u32(src + sl * kRwThreads) : 0u;
+        }
+    };
+    load(pass0);
+    uint32_t cw[SLOTS];   // the slots of this thread's pixels (word t + 256*slot: pixels 2w, 2w+1), 16 bits each
+    int cur_b = -1, stride4 = 0, ngroups = 0;
+    const uint2* g_group = nullptr;
+    __syncthreads();
+    for (int pass = pass0; pass < pass1; ++pass) {
+        const int b = pass / ppc, c = (pass - b * ppc) * NP;
+        if (b != cur_b) {   // CTA-uniform: the per-sample state
+            cur_b = b;
+            const uint16_t* P = plan + static_cast<int64_t>(b) * plan_elems_for(hw);
+            g_group = reinterpret_cast<const uint2*>(P + 8 + hw8);
+            stride4 = 4 * static_cast<int>(P[0]);
+            ngroups = P[1];
+#pragma unroll
+            for (int m = 0; m < SLOTS; ++m) {
+                const int word = m * kRwThreads + threadIdx.x;
+                cw[m] = word < nwords ? __ldg(reinterpret_cast<const uint32_t*>(P + 8) + word) : (dummy | (dummy << 16));
+            }
+        }
+        // push: pixel (2w + e) of planes (2m, 2m + 1) as one word into its slot
+#pragma unroll
+        for (int sl = 0; sl < SLOTS; ++sl) {
+            const uint32_t o0 = cw[sl] & 0xffffu, o1 = cw[sl] >> 16;
+#pragma unroll
+            for (int m = 0; m < NPAIR; ++m) {
+                *reinterpret_cast<uint32_t*>(smem + m * pitch + o0) = __byte_perm(g[2 * m][sl], g[2 * m + 1][sl], 0x5410);
+                *reinterpret_cast<uint32_t*>(smem + m * pitch + o1) = __byte_perm(g[2 * m][sl], g[2 * m + 1][sl], 0x7632);
+            }
+        }
+        __syncthreads();
+        if (pass + 1 < pass1) load(pass + 1);   // in flight while the groups are folded and the sums leave
+        // groups: fp32 sums in ascending p, one rounding, back into the source pixel's slot
+        for (int i = threadIdx.x; i < ngroups; i += kRwThreads) {
+            const uint2 e = __ldg(g_group + i);
+            const uint32_t q = e.x & 0xffffu;
+            uint32_t t = tail0 + (e.x >> 16) * 4u;
+            float s0[NPAIR], s1[NPAIR];
+#pragma unroll
+            for (int m = 0; m < NPAIR; ++m) {
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(smem + m * pitch + q);
+                s0[m] = Pair2<T>::lo(w); s1[m] = Pair2<T>::hi(w);
+            }
+#pragma unroll 1
+            for (uint32_t j = e.y; j != 0u; --j, t += 4u) {
+#pragma unroll
+                for (int m = 0; m < NPAIR; ++m) {
+                    const uint32_t w = *reinterpret_cast<const uint32_t*>(smem + m * pitch + t);
+                    s0[m] += Pair2<T>::lo(w); s1[m] += Pair2<T>::hi(w);
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < NPAIR; ++m) *reinterpret_cast<uint32_t*>(smem + m * pitch + q) = Pair2<T>::pack(s0[m], s1[m]);
+        }
+        __syncthreads();
+        // read-out: four source pixels of a plane pair per 128-bit load, planes separated by PRMT, slots re-zeroed
+#pragma unroll
+        for (int v = 0; v < QUADS; ++v) {
+            if (ro_row[v] >= 0) {
+                const int ro = ro_row[v] * stride4 + ro_col[v];
+                const int vi = v * kRwThreads + threadIdx.x;
+#pragma unroll
+                for (int m = 0; m < NPAIR; ++m) {
+                    if (c + 2 * m < a.C) {
+                        uint4* sp = reinterpret_cast<uint4*>(smem + m * pitch + ro);
+                        uint4 w = *sp;
+                        *sp = make_uint4(0u, 0u, 0u, 0u);
+                        w.x = Pair2<T>::plus_zero(w.x); w.y = Pair2<T>::plus_zero(w.y); w.z = Pair2<T>::plus_zero(w.z); w.w = Pair2<T>::plus_zero(w.w);
+                        T* o = gin + (static_cast<int64_t>(b) * a.C + c + 2 * m) * hw;
+                        reinterpret_cast<uint2*>(o)[vi] = make_uint2(__byte_perm(w.x, w.y, 0x5410), __byte_perm(w.z, w.w, 0x5410));
+                        if (c + 2 * m + 1 < a.C)
+                            reinterpret_cast<uint2*>(o + hw)[vi] = make_uint2(__byte_perm(w.x, w.y, 0x7632), __byte_perm(w.z, w.w, 0x7632));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
 }
 
 // dynamic smem: kRwRing padded plane buffers | uint16 map[hw8].  Single view, no paste / pass-through (the heatmap re-warps).
@@ -1098,6 +1393,17 @@ static int smem_route_words(int64_t H, int64_t W, int elem_bytes) {
     return words * 4 <= kRwBufBytes ? static_cast<int>(words) : 0;
 }
 
+// The push plan / scatter backward: 16-byte rows, planes of at most 4096 pixels, and a padded fp32 accumulator
+// plane small enough that the slot offsets (accumulators | tail | dummy) fit 16 bits and two planes fit a CTA.
+// Returns the accumulator plane in words (a multiple of 4), 0 if the route does not apply.
+constexpr int kRankAccBytes = 40 * 1024;
+static int rank_route_words(int64_t H, int64_t W, int elem_bytes) {
+    if ((W * elem_bytes) % 16 != 0 || H * W > kRwThreads * kRwPix || (H * W) % 8 != 0) return 0;
+    const int sa = padded_stride(static_cast<int>(W), 4), sb = padded_stride(static_cast<int>(W), 12);
+    const int64_t words = (H * (sa > sb ? sa : sb) + 3) & ~3ll;
+    return words * 4 <= kRankAccBytes ? static_cast<int>(words) : 0;
+}
+
 static bool route_disabled() {
     const char* e = std::getenv("UDAPE_REWARP_GLOBAL");  // tests compare both routes within one process
     return e && e[0] == '1';
@@ -1228,19 +1534,23 @@ extern "C" int udape_rewarp_fwd(const void* const* in, const float* const* theta
     cudaStream_t st = as_stream(stream);
     const int buf_words = (all16 && !paste && !active && !route_disabled()) ? smem_route_words(H, W, es) : 0;
     if (inverse_plan) {
-        UDAPE_REQUIRE(views == 1 && !paste && !active && smem_route_words(H, W, es) != 0 && aligned16(inverse_plan),
+        const int acc_words = rank_route_words(H, W, es);
+        UDAPE_REQUIRE(views == 1 && !paste && !active && acc_words != 0 && aligned16(inverse_plan),
                       UDAPE_ERR_ARG, "udape_rewarp_fwd: an inverse plan needs a single view, no paste / pass-through and a "
                       "plane udape_rewarp_plan_elems() accepts");
-        // what the backward needs (inverted map: slots + lists per source pixel), built once per batch
-        const int bw = smem_route_words(H, W, es);
-        const int n = cluster_size_for(B, 8, hw);
-        const size_t smem = sizeof(uint16_t) * (((hw + 8 + 7) & ~7ll) + 2 * ((hw + 7) & ~7ll));
-        const int r2 = es == 4 ? launch_cluster(rewarp_inverse_plan_kernel<4>, static_cast<unsigned>(B * n), static_cast<unsigned>(n),
-                                                smem, st, "udape_rewarp_fwd(plan)", a, inverse_plan, bw)
-                               : launch_cluster(rewarp_inverse_plan_kernel<2>, static_cast<unsigned>(B * n), static_cast<unsigned>(n),
-                                                smem, st, "udape_rewarp_fwd(plan)", a, inverse_plan, bw);
-        if (r2) return r2;
-        if (!out) return check_launch("udape_rewarp_fwd(plan)");
+        // what the backward needs (a shared-memory slot for every output pixel + the groups to fold), built once per batch
+        const size_t smem = sizeof(uint32_t) * static_cast<size_t>(acc_words) + sizeof(uint16_t) * ((hw + 7) & ~7ll);
+        if (es == 4) {
+            const int r2 = reserve_smem(rewarp_push_plan_kernel<4>, smem, "udape_rewarp_fwd(plan)");
+            if (r2) return r2;
+            rewarp_push_plan_kernel<4><<<static_cast<unsigned>(B), kPlanThreads, smem, st>>>(a, inverse_plan, acc_words);
+        } else {
+            const int r2 = reserve_smem(rewarp_push_plan_kernel<2>, smem, "udape_rewarp_fwd(plan)");
+            if (r2) return r2;
+            rewarp_push_plan_kernel<2><<<static_cast<unsigned>(B), kPlanThreads, smem, st>>>(a, inverse_plan, acc_words);
+        }
+        const int r3 = check_launch("udape_rewarp_fwd(plan)");
+        if (r3 || !out) return r3;
     }
     if (buf_words && views == 1 && wide_route(B, hw)) {
         // wide route: one CTA of 512 threads per sample
@@ -1288,7 +1598,7 @@ extern "C" int udape_rewarp_fwd(const void* const* in, const float* const* theta
 
 extern "C" int64_t udape_rewarp_plan_elems(int64_t H, int64_t W, int elem_bytes) {
     if (H <= 0 || W <= 0 || (elem_bytes != 2 && elem_bytes != 4)) return 0;
-    return smem_route_words(H, W, elem_bytes) ? plan_elems_for(H * W) : 0;
+    return rank_route_words(H, W, elem_bytes) ? plan_elems_for(H * W) : 0;
 }
 
 extern "C" int udape_rewarp_bwd(const void* grad_out, const float* theta, int stages, int half_mask, int grid_dtype,
@@ -1313,22 +1623,31 @@ extern "C" int udape_rewarp_bwd(const void* grad_out, const float* theta, int st
     const size_t list_bytes = sizeof(uint16_t) * (((hw + 8 + 7) & ~7ll) + 2 * ((hw + 7) & ~7ll));
     const int buf_words = (aligned16(grad_out) && aligned16(grad_in) && !route_disabled()) ? smem_route_words(H, W, es) : 0;
     if (inverse_plan) {
-        UDAPE_REQUIRE(smem_route_words(H, W, es) != 0 && aligned16(grad_out) && aligned16(grad_in) && aligned16(inverse_plan),
+        const int acc_words = rank_route_words(H, W, es);
+        UDAPE_REQUIRE(acc_words != 0 && aligned16(grad_out) && aligned16(grad_in) && aligned16(inverse_plan),
                       UDAPE_ERR_ARG, "udape_rewarp_bwd: the inverse plan does not apply to this plane / alignment");
-        const int bw = smem_route_words(H, W, es);
-        // (2 CTAs per SM measured best inside the step as well: 184 / 188 / 204 / 238 us for 296 / 148 / 64 / 32 CTAs;
-        // big batches want every resident slot filled several times over: C5, 5376 planes, 85 / 72 / 66 us for
-        // 3 / 6 / 12 CTAs per SM worth of CTAs — r02e)
-        const int64_t per_sm = B * C >= 2048 ? 12 : 2;
-        a.cpc = channels_per_cta(B, C, per_sm * static_cast<int64_t>(sm_count()));
-        const int64_t grid = B * ((C + a.cpc - 1) / a.cpc);
+        // a pass = 4 planes as two packed pairs (2-byte types) or 2 planes (float32): 2 x (17 KB accumulators + 16 KB
+        // tail) of shared memory per CTA, three CTAs per SM; one wave of CTAs, every CTA an equal share of the passes
+        const int planes_per_pass = es == 2 ? 4 : 2;
+        int64_t per_sm = 3;
+        if (const char* e = std::getenv("UDAPE_REWARP_BWD_PER_SM")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) per_sm = v; }
+        const int64_t npass = B * ((C + planes_per_pass - 1) / planes_per_pass);
+        int64_t grid = per_sm * static_cast<int64_t>(sm_count());
+        if (grid > npass) grid = npass;
+        UDAPE_REQUIRE(npass < (1ll << 31), UDAPE_ERR_SHAPE, "udape_rewarp_bwd: too many planes");
+        const size_t smem = 2 * static_cast<size_t>(push_pitch_bytes(acc_words, static_cast<int>(hw)));
         UDAPE_DISPATCH_FLOAT(dtype, T, {
-            constexpr int RING = sizeof(T) == 2 ? kWideRingHalf : kRwRing;
-            const size_t smem = RING * sizeof(uint32_t) * static_cast<size_t>(bw);
-            const int r2 = reserve_smem(rewarp_bwd_plan_kernel<T, RING>, smem, "udape_rewarp_bwd");
-            if (r2) return r2;
-            rewarp_bwd_plan_kernel<T, RING><<<static_cast<unsigned>(grid), kRwThreads, smem, st>>>(
-                a, static_cast<const T*>(grad_out), static_cast<T*>(grad_in), bw, inverse_plan);
+            if constexpr (sizeof(T) == 2) {
+                const int r2 = reserve_smem(rewarp_bwd_push2_kernel<T, 2>, smem, "udape_rewarp_bwd");
+                if (r2) return r2;
+                rewarp_bwd_push2_kernel<T, 2><<<static_cast<unsigned>(grid), kRwThreads, smem, st>>>(
+                    a, static_cast<const T*>(grad_out), static_cast<T*>(grad_in), acc_words, inverse_plan);
+            } else {
+                const int r2 = reserve_smem(rewarp_bwd_push_kernel<T, 2>, smem, "udape_rewarp_bwd");
+                if (r2) return r2;
+                rewarp_bwd_push_kernel<T, 2><<<static_cast<unsigned>(grid), kRwThreads, smem, st>>>(
+                    a, static_cast<const T*>(grad_out), static_cast<T*>(grad_in), acc_words, inverse_plan);
+            }
         });
         return check_launch("udape_rewarp_bwd");
     }
