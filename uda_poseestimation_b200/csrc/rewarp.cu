@@ -41,6 +41,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "pipeline.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -1129,49 +1130,67 @@ template <> struct Pair2<__nv_bfloat16> {
     }
 };
 
-template <typename T, int NPAIR>
-__global__ void __launch_bounds__(kRwThreads, 3)
+// The planes of a pass are contiguous in global memory: ONE 1-D TMA bulk copy (cp.async.bulk + mbarrier) brings the
+// next pass into a staging buffer while the current one is folded and read out.  (Prefetching into registers — 32
+// outstanding LDG per thread — did not overlap anything: the loads share the warp's few scoreboards with the fold's
+// own LDS / LDG, so the fold waited for HBM at its first dependent instruction; ncu: 44 % of the warp time in the
+// fold phase on long_scoreboard, and the same ~29 us at C5 for 256, 512 and 1024 threads per CTA.)
+// FULL: planes of exactly 4096 pixels (the 64 x 64 heatmaps) — every thread slot is live and the output addresses of
+// a pass with all of its planes are one base pointer plus compile-time offsets.
+// dynamic smem: NPAIR x (uint32 acc[acc_words] | uint32 tail[hw8] | 16 bytes) | T stage[2 * NPAIR][hw8] | mbarrier
+template <typename T, int NPAIR, bool FULL, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 rewarp_bwd_push2_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __restrict__ gin, int acc_words,
                         const uint16_t* __restrict__ plan) {
     static_assert(sizeof(T) == 2, "packed pairs of 2-byte elements");
     constexpr int NP = 2 * NPAIR;
-    constexpr int SLOTS = kRwPix / 2;
-    constexpr int QUADS = kRwPix / 4;
+    constexpr int PIX = kRwThreads * kRwPix / NT;   // pixels per thread and plane: 16 / 8 for 256 / 512 threads
+    constexpr int SLOTS = PIX / 2;
+    constexpr int QUADS = PIX / 4;
     extern __shared__ __align__(16) uint32_t rw_smem[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(rw_smem);
-    const int hw = a.H * a.W, hw8 = (hw + 7) & ~7, nwords = hw / 2, nquads = hw / 4;
+    const int hw = FULL ? kRwThreads * kRwPix : a.H * a.W;
+    const int hw8 = (hw + 7) & ~7, nwords = hw / 2, nquads = hw / 4;
     const int ppc = (a.C + NP - 1) / NP;                      // passes per sample
     const int64_t npass = static_cast<int64_t>(a.B) * ppc;
     const int pass0 = static_cast<int>(npass * blockIdx.x / gridDim.x), pass1 = static_cast<int>(npass * (blockIdx.x + 1) / gridDim.x);
     if (pass0 >= pass1) return;
     const int pitch = push_pitch_bytes(acc_words, hw);
     const uint32_t tail0 = static_cast<uint32_t>(acc_words) * 4u, dummy = tail0 + static_cast<uint32_t>(hw8) * 4u;
+    uint32_t* stage = reinterpret_cast<uint32_t*>(smem + NPAIR * pitch);                 // [NP][nwords]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + NPAIR * pitch + NP * hw8 * 2);
+    auto fetch = [&](int pass) {   // one thread: the planes of `pass` into the staging buffer
+        const int b = pass / ppc, c = (pass - b * ppc) * NP;
+        const uint32_t bytes = static_cast<uint32_t>(min(NP, a.C - c)) * static_cast<uint32_t>(hw) * 2u;
+        mbar_expect_tx(bar, bytes);
+        bulk_load(stage, gout + (static_cast<int64_t>(b) * a.C + c) * hw, bytes, bar);
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_init_fence();
+        fetch(pass0);
+    }
+    // the accumulator quads this thread reads out: row and 4 * column of quad t + NT * v (one division per thread)
     int ro_row[QUADS], ro_col[QUADS];
+    {
+        const int r0 = (4 * static_cast<int>(threadIdx.x)) / a.W, c0 = 4 * static_cast<int>(threadIdx.x) - r0 * a.W;
+        const bool even = (4 * NT) % a.W == 0;        // a quad step of NT is a whole number of rows
 #pragma unroll
-    for (int v = 0; v < QUADS; ++v) {
-        const int vi = v * kRwThreads + threadIdx.x;
-        ro_row[v] = vi < nquads ? (vi * 4) / a.W : -1;
-        ro_col[v] = (vi * 4 - ro_row[v] * a.W) * 4;
+        for (int v = 0; v < QUADS; ++v) {
+            const int vi = v * NT + threadIdx.x;
+            const int row = even ? r0 + v * ((4 * NT) / a.W) : (vi * 4) / a.W;
+            ro_row[v] = (FULL || vi < nquads) ? row : -1;
+            ro_col[v] = (even ? c0 : vi * 4 - row * a.W) * 4;
+        }
     }
 #pragma unroll
     for (int m = 0; m < NPAIR; ++m)
-        for (int i = threadIdx.x; i < acc_words / 4; i += kRwThreads) reinterpret_cast<uint4*>(smem + m * pitch)[i] = make_uint4(0u, 0u, 0u, 0u);
-    const uint32_t* g32 = reinterpret_cast<const uint32_t*>(gout);
-    uint32_t g[NP][SLOTS];
-    auto load = [&](int pass) {
-        const int b = pass / ppc, c = (pass - b * ppc) * NP;
-#pragma unroll
-        for (int n = 0; n < NP; ++n) {
-            const uint32_t* src = g32 + (static_cast<int64_t>(b) * a.C + c + n) * nwords + threadIdx.x;
-#pragma unroll
-            for (int sl = 0; sl < SLOTS; ++sl)
-                g[n][sl] = (c + n < a.C && sl * kRwThreads + static_cast<int>(threadIdx.x) < nwords) ? ldg_stream_u32(src + sl * kRwThreads) : 0u;
-        }
-    };
-    load(pass0);
-    uint32_t cw[SLOTS];   // the slots of this thread's pixels (word t + 256*slot: pixels 2w, 2w+1), 16 bits each
+        for (int i = threadIdx.x; i < acc_words / 4; i += NT) reinterpret_cast<uint4*>(smem + m * pitch)[i] = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t cw[SLOTS];   // the slots of this thread's pixels (word t + NT*slot: pixels 2w, 2w+1), 16 bits each
     int cur_b = -1, stride4 = 0, ngroups = 0;
     const uint2* g_group = nullptr;
+    uint2 e_first = make_uint2(0u, 1u);   // this thread's first group of the sample (kept across the sample's passes)
+    uint32_t parity = 0;
     __syncthreads();
     for (int pass = pass0; pass < pass1; ++pass) {
         const int b = pass / ppc, c = (pass - b * ppc) * NP;
@@ -1183,62 +1202,91 @@ rewarp_bwd_push2_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __res
             ngroups = P[1];
 #pragma unroll
             for (int m = 0; m < SLOTS; ++m) {
-                const int word = m * kRwThreads + threadIdx.x;
-                cw[m] = word < nwords ? __ldg(reinterpret_cast<const uint32_t*>(P + 8) + word) : (dummy | (dummy << 16));
+                const int word = m * NT + threadIdx.x;
+                cw[m] = (FULL || word < nwords) ? __ldg(reinterpret_cast<const uint32_t*>(P + 8) + word) : (dummy | (dummy << 16));
             }
+            if (static_cast<int>(threadIdx.x) < ngroups) e_first = __ldg(g_group + threadIdx.x);
         }
-        // push: pixel (2w + e) of planes (2m, 2m + 1) as one word into its slot
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        // push: pixel (2w + e) of planes (2m, 2m + 1) as one word into its slot.  (Planes beyond C hold whatever
+        // the buffer held before: they only ever reach the unused half of a pair.)
 #pragma unroll
         for (int sl = 0; sl < SLOTS; ++sl) {
-            const uint32_t o0 = cw[sl] & 0xffffu, o1 = cw[sl] >> 16;
+            const int word = sl * NT + threadIdx.x;
+            if (FULL || word < nwords) {
+                const uint32_t o0 = cw[sl] & 0xffffu, o1 = cw[sl] >> 16;
 #pragma unroll
-            for (int m = 0; m < NPAIR; ++m) {
-                *reinterpret_cast<uint32_t*>(smem + m * pitch + o0) = __byte_perm(g[2 * m][sl], g[2 * m + 1][sl], 0x5410);
-                *reinterpret_cast<uint32_t*>(smem + m * pitch + o1) = __byte_perm(g[2 * m][sl], g[2 * m + 1][sl], 0x7632);
+                for (int m = 0; m < NPAIR; ++m) {
+                    const uint32_t ga = stage[(2 * m) * nwords + word], gb = stage[(2 * m + 1) * nwords + word];
+                    *reinterpret_cast<uint32_t*>(smem + m * pitch + o0) = __byte_perm(ga, gb, 0x5410);
+                    *reinterpret_cast<uint32_t*>(smem + m * pitch + o1) = __byte_perm(ga, gb, 0x7632);
+                }
             }
         }
         __syncthreads();
-        if (pass + 1 < pass1) load(pass + 1);   // in flight while the groups are folded and the sums leave
-        // groups: fp32 sums in ascending p, one rounding, back into the source pixel's slot
-        for (int i = threadIdx.x; i < ngroups; i += kRwThreads) {
-            const uint2 e = __ldg(g_group + i);
+        if (threadIdx.x == 0 && pass + 1 < pass1) fetch(pass + 1);   // in flight while the groups are folded and the sums leave
+        // groups: fp32 sums in ascending p, one rounding, back into the source pixel's slot.  Every group has at
+        // least one tail entry; the groups with exactly one come first, so most warps never enter the loop.
+        // (A group entry is 8 bytes from L1 / L2: the next one is requested before the current one is folded.)
+        uint2 e = e_first;
+        for (int i = threadIdx.x; i < ngroups; i += NT) {
+            const uint2 nxt = i + NT < ngroups ? __ldg(g_group + i + NT) : e;
             const uint32_t q = e.x & 0xffffu;
             uint32_t t = tail0 + (e.x >> 16) * 4u;
             float s0[NPAIR], s1[NPAIR];
 #pragma unroll
             for (int m = 0; m < NPAIR; ++m) {
                 const uint32_t w = *reinterpret_cast<const uint32_t*>(smem + m * pitch + q);
-                s0[m] = Pair2<T>::lo(w); s1[m] = Pair2<T>::hi(w);
+                const uint32_t x = *reinterpret_cast<const uint32_t*>(smem + m * pitch + t);
+                s0[m] = Pair2<T>::lo(w) + Pair2<T>::lo(x); s1[m] = Pair2<T>::hi(w) + Pair2<T>::hi(x);
             }
 #pragma unroll 1
-            for (uint32_t j = e.y; j != 0u; --j, t += 4u) {
+            for (uint32_t j = e.y - 1u; j != 0u; --j) {
+                t += 4u;
 #pragma unroll
                 for (int m = 0; m < NPAIR; ++m) {
-                    const uint32_t w = *reinterpret_cast<const uint32_t*>(smem + m * pitch + t);
-                    s0[m] += Pair2<T>::lo(w); s1[m] += Pair2<T>::hi(w);
+                    const uint32_t x = *reinterpret_cast<const uint32_t*>(smem + m * pitch + t);
+                    s0[m] += Pair2<T>::lo(x); s1[m] += Pair2<T>::hi(x);
                 }
             }
 #pragma unroll
             for (int m = 0; m < NPAIR; ++m) *reinterpret_cast<uint32_t*>(smem + m * pitch + q) = Pair2<T>::pack(s0[m], s1[m]);
+            e = nxt;
         }
         __syncthreads();
         // read-out: four source pixels of a plane pair per 128-bit load, planes separated by PRMT, slots re-zeroed
+        uint2* o2 = reinterpret_cast<uint2*>(gin + (static_cast<int64_t>(b) * a.C + c) * hw) + threadIdx.x;
+        if (FULL && c + NP <= a.C) {
 #pragma unroll
-        for (int v = 0; v < QUADS; ++v) {
-            if (ro_row[v] >= 0) {
+            for (int v = 0; v < QUADS; ++v) {
                 const int ro = ro_row[v] * stride4 + ro_col[v];
-                const int vi = v * kRwThreads + threadIdx.x;
 #pragma unroll
                 for (int m = 0; m < NPAIR; ++m) {
-                    if (c + 2 * m < a.C) {
-                        uint4* sp = reinterpret_cast<uint4*>(smem + m * pitch + ro);
-                        uint4 w = *sp;
-                        *sp = make_uint4(0u, 0u, 0u, 0u);
-                        w.x = Pair2<T>::plus_zero(w.x); w.y = Pair2<T>::plus_zero(w.y); w.z = Pair2<T>::plus_zero(w.z); w.w = Pair2<T>::plus_zero(w.w);
-                        T* o = gin + (static_cast<int64_t>(b) * a.C + c + 2 * m) * hw;
-                        reinterpret_cast<uint2*>(o)[vi] = make_uint2(__byte_perm(w.x, w.y, 0x5410), __byte_perm(w.z, w.w, 0x5410));
-                        if (c + 2 * m + 1 < a.C)
-                            reinterpret_cast<uint2*>(o + hw)[vi] = make_uint2(__byte_perm(w.x, w.y, 0x7632), __byte_perm(w.z, w.w, 0x7632));
+                    uint4* sp = reinterpret_cast<uint4*>(smem + m * pitch + ro);
+                    uint4 w = *sp;
+                    *sp = make_uint4(0u, 0u, 0u, 0u);
+                    w.x = Pair2<T>::plus_zero(w.x); w.y = Pair2<T>::plus_zero(w.y); w.z = Pair2<T>::plus_zero(w.z); w.w = Pair2<T>::plus_zero(w.w);
+                    o2[(2 * m) * (NT * QUADS) + v * NT] = make_uint2(__byte_perm(w.x, w.y, 0x5410), __byte_perm(w.z, w.w, 0x5410));
+                    o2[(2 * m + 1) * (NT * QUADS) + v * NT] = make_uint2(__byte_perm(w.x, w.y, 0x7632), __byte_perm(w.z, w.w, 0x7632));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < QUADS; ++v) {
+                if (ro_row[v] >= 0) {
+                    const int ro = ro_row[v] * stride4 + ro_col[v];
+#pragma unroll
+                    for (int m = 0; m < NPAIR; ++m) {
+                        if (c + 2 * m < a.C) {
+                            uint4* sp = reinterpret_cast<uint4*>(smem + m * pitch + ro);
+                            uint4 w = *sp;
+                            *sp = make_uint4(0u, 0u, 0u, 0u);
+                            w.x = Pair2<T>::plus_zero(w.x); w.y = Pair2<T>::plus_zero(w.y); w.z = Pair2<T>::plus_zero(w.z); w.w = Pair2<T>::plus_zero(w.w);
+                            o2[static_cast<int64_t>(2 * m) * nquads + v * NT] = make_uint2(__byte_perm(w.x, w.y, 0x5410), __byte_perm(w.z, w.w, 0x5410));
+                            if (c + 2 * m + 1 < a.C)
+                                o2[static_cast<int64_t>(2 * m + 1) * nquads + v * NT] = make_uint2(__byte_perm(w.x, w.y, 0x7632), __byte_perm(w.z, w.w, 0x7632));
+                        }
                     }
                 }
             }
@@ -1627,27 +1675,37 @@ extern "C" int udape_rewarp_bwd(const void* grad_out, const float* theta, int st
         UDAPE_REQUIRE(acc_words != 0 && aligned16(grad_out) && aligned16(grad_in) && aligned16(inverse_plan),
                       UDAPE_ERR_ARG, "udape_rewarp_bwd: the inverse plan does not apply to this plane / alignment");
         // a pass = 4 planes as two packed pairs (2-byte types) or 2 planes (float32): 2 x (17 KB accumulators + 16 KB
-        // tail) of shared memory per CTA, three CTAs per SM; one wave of CTAs, every CTA an equal share of the passes
+        // tail) of shared memory per CTA (+ 32 KB of staged planes for the 2-byte types); one wave of CTAs, every CTA
+        // an equal share of the passes
         const int planes_per_pass = es == 2 ? 4 : 2;
-        int64_t per_sm = 3;
-        if (const char* e = std::getenv("UDAPE_REWARP_BWD_PER_SM")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) per_sm = v; }
+        int nt = 512;
+        if (const char* e = std::getenv("UDAPE_REWARP_BWD_NT")) { const int v = std::atoi(e); if (v == 256 || v == 512) nt = v; }
+        if (es != 2 || hw != kRwThreads * kRwPix) nt = 256;
+        int per_sm = es == 2 ? 2 : 3;
+        if (const char* e = std::getenv("UDAPE_REWARP_BWD_PER_SM")) { const int v = std::atoi(e); if (v >= 1 && v <= 3) per_sm = v; }
         const int64_t npass = B * ((C + planes_per_pass - 1) / planes_per_pass);
         int64_t grid = per_sm * static_cast<int64_t>(sm_count());
         if (grid > npass) grid = npass;
         UDAPE_REQUIRE(npass < (1ll << 31), UDAPE_ERR_SHAPE, "udape_rewarp_bwd: too many planes");
-        const size_t smem = 2 * static_cast<size_t>(push_pitch_bytes(acc_words, static_cast<int>(hw)));
+        const int64_t hw8 = (hw + 7) & ~7ll;
+        const size_t smem = 2 * static_cast<size_t>(push_pitch_bytes(acc_words, static_cast<int>(hw))) + (es == 2 ? 4 * hw8 * 2 + 16 : 0);
         UDAPE_DISPATCH_FLOAT(dtype, T, {
+            auto go = [&](auto kernel, int threads) -> int {
+                const int r2 = reserve_smem(kernel, smem, "udape_rewarp_bwd");
+                if (r2) return r2;
+                kernel<<<static_cast<unsigned>(grid), threads, smem, st>>>(a, static_cast<const T*>(grad_out), static_cast<T*>(grad_in),
+                                                                           acc_words, inverse_plan);
+                return UDAPE_OK;
+            };
+            int r2;
             if constexpr (sizeof(T) == 2) {
-                const int r2 = reserve_smem(rewarp_bwd_push2_kernel<T, 2>, smem, "udape_rewarp_bwd");
-                if (r2) return r2;
-                rewarp_bwd_push2_kernel<T, 2><<<static_cast<unsigned>(grid), kRwThreads, smem, st>>>(
-                    a, static_cast<const T*>(grad_out), static_cast<T*>(grad_in), acc_words, inverse_plan);
+                if (hw != kRwThreads * kRwPix) r2 = go(rewarp_bwd_push2_kernel<T, 2, false, 256, 2>, 256);
+                else if (nt == 512) r2 = go(rewarp_bwd_push2_kernel<T, 2, true, 512, 2>, 512);
+                else r2 = go(rewarp_bwd_push2_kernel<T, 2, true, 256, 2>, 256);
             } else {
-                const int r2 = reserve_smem(rewarp_bwd_push_kernel<T, 2>, smem, "udape_rewarp_bwd");
-                if (r2) return r2;
-                rewarp_bwd_push_kernel<T, 2><<<static_cast<unsigned>(grid), kRwThreads, smem, st>>>(
-                    a, static_cast<const T*>(grad_out), static_cast<T*>(grad_in), acc_words, inverse_plan);
+                r2 = go(rewarp_bwd_push_kernel<T, 2>, 256);
             }
+            if (r2) return r2;
         });
         return check_launch("udape_rewarp_bwd");
     }
