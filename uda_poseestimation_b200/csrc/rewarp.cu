@@ -817,6 +817,46 @@ __device__ __forceinline__ void build_map_compact(const float* __restrict__ s_th
     } else build_map_variant<2, -1>(s_theta, a.W, a.H, a.stages, a.half_mask, a.grid_dtype, map, none, code);
 }
 
+// the same builder with the stage table in registers (no LDS.64 of theta per stage and pixel)
+template <int HM, int GD, typename Code>
+__device__ __noinline__ void build_map_regs(const float* __restrict__ s_theta, int W, int H, int stages, int half_mask,
+                                            int grid_dtype, uint16_t* __restrict__ map, uint16_t none, Code code) {
+    const int hw = H * W;
+    const int nt = blockDim.x;
+    const int dj = nt / W, di = nt - dj * W;
+    const float Wf = static_cast<float>(W), Hf = static_cast<float>(H);
+    const float cx = 0.5f - 0.5f * Wf, cy = 0.5f - 0.5f * Hf;
+    const bool xy_exact = GD == UDAPE_F16 ? true : grid_xy_exact(W, H, grid_dtype);
+    float r[kRwMaxStages][6];
+#pragma unroll
+    for (int st = 0; st < kRwMaxStages; ++st)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) r[st][k] = st < stages ? s_theta[6 * st + k] : 0.0f;
+    int p = threadIdx.x;
+    int j0 = p / W, i0 = p - j0 * W;
+#pragma unroll 1
+    for (; p < hw; p += nt) {
+        float fi = static_cast<float>(i0), fj = static_cast<float>(j0);
+        bool ok = true;
+#pragma unroll
+        for (int st = 0; st < kRwMaxStages; ++st)
+            if (st < stages && ok)
+                ok = stage_source_f<HM, GD>(fi, fj, r[st], Wf, Hf, cx, cy, (half_mask >> st) & 1, grid_dtype, xy_exact);
+        map[p] = ok ? code(static_cast<int>(fi), static_cast<int>(fj)) : none;
+        i0 += di; j0 += dj;
+        if (i0 >= W) { i0 -= W; ++j0; }
+    }
+}
+template <typename Code>
+__device__ __forceinline__ void build_map_fast(const float* __restrict__ s_theta, const RewarpArgs& a, uint16_t* __restrict__ map,
+                                               uint16_t none, Code code) {
+    if (a.half_mask == 0) build_map_regs<0, -1>(s_theta, a.W, a.H, a.stages, a.half_mask, a.grid_dtype, map, none, code);
+    else if (a.half_mask == (1 << a.stages) - 1) {
+        if (a.grid_dtype == UDAPE_F16) build_map_regs<1, UDAPE_F16>(s_theta, a.W, a.H, a.stages, a.half_mask, a.grid_dtype, map, none, code);
+        else build_map_regs<1, UDAPE_BF16>(s_theta, a.W, a.H, a.stages, a.half_mask, a.grid_dtype, map, none, code);
+    } else build_map_regs<2, -1>(s_theta, a.W, a.H, a.stages, a.half_mask, a.grid_dtype, map, none, code);
+}
+
 // ---- the push plan: what the backward needs, computed once per batch and kept in global memory ----------------
 // The backward is a SCATTER  grad_in[src(p)] += grad_out[p].  It is made deterministic — and free of atomics,
 // sorting and per-pixel branches — by giving every output pixel p its own SLOT in shared memory:
@@ -869,7 +909,7 @@ rewarp_push_plan_kernel(const RewarpArgs a, uint16_t* __restrict__ plan, int acc
     float J[4];
     composed_jacobian(s_theta, a, J);
     const int stride = pick_stride(a.W, static_cast<float>(EPW) * J[0], static_cast<float>(EPW) * J[2], 0);
-    build_map_compact(s_theta, a, map, static_cast<uint16_t>(0xffffu), [=](int i, int j) {
+    build_map_fast(s_theta, a, map, static_cast<uint16_t>(0xffffu), [=](int i, int j) {
         return static_cast<uint16_t>((j * stride + i) * 4);
     });
     __syncthreads();
@@ -883,18 +923,22 @@ rewarp_push_plan_kernel(const RewarpArgs a, uint16_t* __restrict__ plan, int acc
         if (code[k] != 0xffffu) pending |= 1u << k;
         else code[k] = 0xffffffffu;
     }
-    for (uint32_t r = 0;; ++r) {
+    for (uint32_t r = 0;; ++r) {   // (after two or three rounds most threads have nothing pending and only meet the barriers)
         const uint32_t key_hi = (r + 1) << 16;
+        if (pending) {
 #pragma unroll
-        for (int k = 0; k < kPlanPix; ++k)
-            if (pending & (1u << k)) atomicMax(&owner[code[k] >> 2], key_hi | (0xffffu - static_cast<uint32_t>(k * kPlanThreads + threadIdx.x)));
+            for (int k = 0; k < kPlanPix; ++k)
+                if (pending & (1u << k)) atomicMax(&owner[code[k] >> 2], key_hi | (0xffffu - static_cast<uint32_t>(k * kPlanThreads + threadIdx.x)));
+        }
         __syncthreads();
+        if (pending) {
 #pragma unroll
-        for (int k = 0; k < kPlanPix; ++k)
-            if ((pending & (1u << k)) && owner[code[k] >> 2] == (key_hi | (0xffffu - static_cast<uint32_t>(k * kPlanThreads + threadIdx.x)))) {
-                code[k] |= r << 16;
-                pending &= ~(1u << k);
-            }
+            for (int k = 0; k < kPlanPix; ++k)
+                if ((pending & (1u << k)) && owner[code[k] >> 2] == (key_hi | (0xffffu - static_cast<uint32_t>(k * kPlanThreads + threadIdx.x)))) {
+                    code[k] |= r << 16;
+                    pending &= ~(1u << k);
+                }
+        }
         if (!__syncthreads_or(pending != 0)) break;   // also: this round's reads are over before the next round's atomics
     }
     // 2. groups (source pixels with >= 2 contributors): exclusive scans of (single-tail groups | longer groups << 16)
@@ -1207,6 +1251,7 @@ rewarp_bwd_push2_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __res
             }
             if (static_cast<int>(threadIdx.x) < ngroups) e_first = __ldg(g_group + threadIdx.x);
         }
+        const int live = (min(NP, a.C - c) + 1) / 2;   // plane pairs of this pass (the last pass of a sample may hold fewer)
         mbar_wait(bar, parity);
         parity ^= 1u;
         // push: pixel (2w + e) of planes (2m, 2m + 1) as one word into its slot.  (Planes beyond C hold whatever
@@ -1218,9 +1263,11 @@ rewarp_bwd_push2_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __res
                 const uint32_t o0 = cw[sl] & 0xffffu, o1 = cw[sl] >> 16;
 #pragma unroll
                 for (int m = 0; m < NPAIR; ++m) {
-                    const uint32_t ga = stage[(2 * m) * nwords + word], gb = stage[(2 * m + 1) * nwords + word];
-                    *reinterpret_cast<uint32_t*>(smem + m * pitch + o0) = __byte_perm(ga, gb, 0x5410);
-                    *reinterpret_cast<uint32_t*>(smem + m * pitch + o1) = __byte_perm(ga, gb, 0x7632);
+                    if (m < live) {
+                        const uint32_t ga = stage[(2 * m) * nwords + word], gb = stage[(2 * m + 1) * nwords + word];
+                        *reinterpret_cast<uint32_t*>(smem + m * pitch + o0) = __byte_perm(ga, gb, 0x5410);
+                        *reinterpret_cast<uint32_t*>(smem + m * pitch + o1) = __byte_perm(ga, gb, 0x7632);
+                    }
                 }
             }
         }
@@ -1237,21 +1284,26 @@ rewarp_bwd_push2_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __res
             float s0[NPAIR], s1[NPAIR];
 #pragma unroll
             for (int m = 0; m < NPAIR; ++m) {
-                const uint32_t w = *reinterpret_cast<const uint32_t*>(smem + m * pitch + q);
-                const uint32_t x = *reinterpret_cast<const uint32_t*>(smem + m * pitch + t);
-                s0[m] = Pair2<T>::lo(w) + Pair2<T>::lo(x); s1[m] = Pair2<T>::hi(w) + Pair2<T>::hi(x);
+                if (m < live) {
+                    const uint32_t w = *reinterpret_cast<const uint32_t*>(smem + m * pitch + q);
+                    const uint32_t x = *reinterpret_cast<const uint32_t*>(smem + m * pitch + t);
+                    s0[m] = Pair2<T>::lo(w) + Pair2<T>::lo(x); s1[m] = Pair2<T>::hi(w) + Pair2<T>::hi(x);
+                }
             }
 #pragma unroll 1
             for (uint32_t j = e.y - 1u; j != 0u; --j) {
                 t += 4u;
 #pragma unroll
                 for (int m = 0; m < NPAIR; ++m) {
-                    const uint32_t x = *reinterpret_cast<const uint32_t*>(smem + m * pitch + t);
-                    s0[m] += Pair2<T>::lo(x); s1[m] += Pair2<T>::hi(x);
+                    if (m < live) {
+                        const uint32_t x = *reinterpret_cast<const uint32_t*>(smem + m * pitch + t);
+                        s0[m] += Pair2<T>::lo(x); s1[m] += Pair2<T>::hi(x);
+                    }
                 }
             }
 #pragma unroll
-            for (int m = 0; m < NPAIR; ++m) *reinterpret_cast<uint32_t*>(smem + m * pitch + q) = Pair2<T>::pack(s0[m], s1[m]);
+            for (int m = 0; m < NPAIR; ++m)
+                if (m < live) *reinterpret_cast<uint32_t*>(smem + m * pitch + q) = Pair2<T>::pack(s0[m], s1[m]);
             e = nxt;
         }
         __syncthreads();
@@ -1375,6 +1427,114 @@ rewarp_wide_kernel(const RewarpArgs a, T* __restrict__ out, int buf_words) {
                 w32 = lo | (hi << 16);
             }
             if (sl * kWideThreads + static_cast<int>(threadIdx.x) < nwords) o32[sl * kWideThreads] = w32;
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// ---- second-generation wide forward (full 4096-pixel planes, single view) -------------------------------------
+// ncu on the first wide kernel at C5 (profiles/r02q): the fp16 gather was bound by shared-memory WAVEFRONTS, not
+// by HBM — 5.65 M per launch = 20 us of its 25: LDS.U16 gathers at 2.25 x their ideal (bank conflicts of the padded
+// rows), LDGSTS staging writes at 2.6 x, and three LDS.64 of theta per stage and pixel in the map builder; and it
+// paid one CTA barrier, one cp.async wait and a set of predicates / 64-bit address computations per PLANE.  Here:
+//   * rows are not padded but XOR-swizzled at 16-byte granularity (chunk ^ row): a plane is exactly H*W elements
+//     (+ one zero chunk that out-of-image pixels read).  (A word-granular skew staged with 4-byte cp.async was
+//     measured too: fp32 41.3 us, fp16 26.5 us at C5 against 31.5 / 24.1 — four times the copy instructions.)
+//   * an item of the ring is G planes (4 x 8 KB or 2 x 16 KB): one barrier and one wait per 32 KB;
+//   * the stage table lives in registers while the map is built;
+//   * every slot of every thread is live (H*W = 512 threads x 8 pixels): no predicates, addresses are one base
+//     pointer per plane plus compile-time offsets.
+constexpr int kW2Threads = 512;
+constexpr int kW2Pixels = 4096;
+
+// dynamic smem: RING stages x G planes x (H*W*sizeof(T) + 16 zero bytes) | uint16 map[4096]
+template <typename T, int G, int RING>
+__global__ void __launch_bounds__(kW2Threads, 2)
+rewarp_wide2_kernel(const RewarpArgs a, T* __restrict__ out) {
+    constexpr int ES = static_cast<int>(sizeof(T)), EPW = 4 / ES;
+    constexpr int PIX = kW2Pixels / kW2Threads;         // 8 pixels per thread and plane
+    constexpr int SLOTS = PIX / EPW;                     // words per thread and plane
+    constexpr int WORDS = kW2Pixels / EPW;               // 32-bit words of a plane
+    constexpr int CHUNKS = kW2Pixels * ES / 16;          // 16-byte chunks of a plane
+    constexpr int VEC = CHUNKS / kW2Threads;             // staging copies per thread and plane
+    constexpr int PITCH = kW2Pixels * ES + 16;           // a staged plane and its zero chunk
+    constexpr int STAGE = G * PITCH;
+    extern __shared__ __align__(16) uint32_t rw_smem[];
+    __shared__ float s_theta[kRwMaxStages * 6];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(rw_smem);
+    uint16_t* map = reinterpret_cast<uint16_t*>(smem + RING * STAGE);
+    const int b = blockIdx.x;
+    if (threadIdx.x < a.stages * 6)
+        s_theta[threadIdx.x] = a.view[0].theta[static_cast<int64_t>(b) * a.stages * 6 + threadIdx.x];
+    for (int i = threadIdx.x; i < RING * G * 4; i += kW2Threads)       // the zero chunk behind every staged plane
+        *reinterpret_cast<uint32_t*>(smem + (i >> 2) * PITCH + kW2Pixels * ES + (i & 3) * 4) = 0u;
+    // chunk c of a plane = row (c / cpr), chunk-in-row (c % cpr); staged at chunk-in-row ^ (row % 8)
+    const int cpr = a.W * ES / 16, cpr_log2 = 31 - __clz(cpr), swz = min(cpr, 8) - 1;
+    uint32_t so[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+        const int c = q * kW2Threads + threadIdx.x, row = c >> cpr_log2, cc = c & (cpr - 1);
+        so[q] = static_cast<uint32_t>(((row << cpr_log2) + (cc ^ (row & swz))) * 16);
+    }
+    const int nitems = (a.C + G - 1) / G;
+    const uint32_t smem0 = smem_u32(smem);
+    const uint4* in0 = reinterpret_cast<const uint4*>(static_cast<const T*>(a.view[0].in) + static_cast<int64_t>(b) * a.C * kW2Pixels) + threadIdx.x;
+    auto issue = [&](int it) {
+        const uint32_t dst = smem0 + (it % RING) * STAGE;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            if (it * G + g < a.C) {
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) cp_async16(dst + g * PITCH + so[q], in0 + static_cast<int64_t>(it * G + g) * CHUNKS + q * kW2Threads);
+            }
+        }
+    };
+#pragma unroll
+    for (int it = 0; it < RING - 1; ++it) {   // in flight while the map is computed
+        if (it < nitems) issue(it);
+        cp_async_commit();
+    }
+    __syncthreads();   // theta
+    {
+        const int W = a.W;
+        build_map_fast(s_theta, a, map, static_cast<uint16_t>(kW2Pixels * ES), [=](int i, int j) {
+            const int byte = i * ES, cc = byte >> 4;
+            return static_cast<uint16_t>((((j * W * ES) >> 4) + (cc ^ (j & swz))) * 16 + (byte & 15));
+        });
+    }
+    __syncthreads();
+    uint32_t idx[PIX / 2];   // the staged byte offsets of this thread's pixels (words t + 512*slot), two per register
+#pragma unroll
+    for (int k = 0; k < PIX; k += 2) {
+        const int p0 = ((k / EPW) * kW2Threads + threadIdx.x) * EPW + (k % EPW);
+        const int p1 = (((k + 1) / EPW) * kW2Threads + threadIdx.x) * EPW + ((k + 1) % EPW);
+        idx[k >> 1] = static_cast<uint32_t>(map[p0]) | (static_cast<uint32_t>(map[p1]) << 16);
+    }
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(out + static_cast<int64_t>(b) * a.C * kW2Pixels) + threadIdx.x;
+    for (int it = 0; it < nitems; ++it) {
+        cp_async_wait<RING - 2>();   // this thread's copies of item `it` have landed ...
+        __syncthreads();                // ... everybody's have, and everybody is done with item it-1
+        if (it + RING - 1 < nitems) issue(it + RING - 1);
+        cp_async_commit();
+        const uint8_t* base = smem + (it % RING) * STAGE;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            if (it * G + g < a.C) {
+                const uint8_t* bytes = base + g * PITCH;
+                uint32_t* o = o32 + static_cast<int64_t>(it * G + g) * WORDS;
+#pragma unroll
+                for (int sl = 0; sl < SLOTS; ++sl) {   // the values are moved, never converted
+                    uint32_t w32;
+                    if constexpr (EPW == 1) {
+                        w32 = *reinterpret_cast<const uint32_t*>(bytes + ((idx[sl >> 1] >> (16 * (sl & 1))) & 0xffffu));
+                    } else {
+                        const uint32_t lo = *reinterpret_cast<const uint16_t*>(bytes + (idx[sl] & 0xffffu));
+                        const uint32_t hi = *reinterpret_cast<const uint16_t*>(bytes + (idx[sl] >> 16));
+                        w32 = lo | (hi << 16);
+                    }
+                    o[sl * kW2Threads] = w32;
+                }
+            }
         }
     }
     cp_async_wait<0>();
@@ -1532,6 +1692,14 @@ static bool wide_route(int64_t B, int64_t hw) {
     return hw <= kWideThreads * kWidePix && (hw % 8) == 0 && B >= 1;
 }
 
+// the second-generation wide route: planes of exactly 4096 pixels whose rows are a power-of-two number of 16-byte chunks
+static bool wide2_route(int64_t H, int64_t W, int es) {
+    const char* e = std::getenv("UDAPE_REWARP_WIDE2");   // tests / tuning: "0" keeps the first wide kernel
+    if (e && e[0] == '0') return false;
+    const int64_t cpr = W * es / 16;   // 16-byte chunks per row: a power of two
+    return H * W == kW2Pixels && (W * es) % 16 == 0 && cpr >= 1 && (cpr & (cpr - 1)) == 0;
+}
+
 constexpr int kRwDeepRing = 6;   // single view, a CTA that owns >= 6 planes
 
 template <typename T>
@@ -1599,6 +1767,20 @@ extern "C" int udape_rewarp_fwd(const void* const* in, const float* const* theta
         }
         const int r3 = check_launch("udape_rewarp_fwd(plan)");
         if (r3 || !out) return r3;
+    }
+    // (batches that do not fill the GPU are latency-bound per CTA and stay with the per-plane ring: C2, 32 samples,
+    // fp16 10.7 us against 11.9 us; C5: 25.9 -> 24.1 us fp16, 33.5 -> 31.5 us fp32)
+    if (buf_words && views == 1 && wide_route(B, hw) && wide2_route(H, W, es) && B * C >= 2048) {
+        // second-generation wide route: full 4096-pixel planes, swizzled staging, G planes per barrier
+        UDAPE_DISPATCH_FLOAT(dtype, T, {
+            constexpr int G = sizeof(T) == 2 ? 4 : 2;
+            constexpr int RING = 3;
+            const size_t smem = static_cast<size_t>(RING) * G * (kW2Pixels * sizeof(T) + 16) + sizeof(uint16_t) * kW2Pixels;
+            const int r2 = reserve_smem(rewarp_wide2_kernel<T, G, RING>, smem, "udape_rewarp_fwd");
+            if (r2) return r2;
+            rewarp_wide2_kernel<T, G, RING><<<static_cast<unsigned>(B), kW2Threads, smem, st>>>(a, static_cast<T*>(out));
+        });
+        return check_launch("udape_rewarp_fwd");
     }
     if (buf_words && views == 1 && wide_route(B, hw)) {
         // wide route: one CTA of 512 threads per sample
