@@ -342,13 +342,20 @@ loss_step_kernel(const TS* __restrict__ y_s, const TT* __restrict__ label, const
     __shared__ float red[32];
     __shared__ float s_tab[kWinTabN * kWinTabN];
     const int hw = a.hw;
-    const bool sup = static_cast<int>(blockIdx.x) < a.planes_s;
+    // Supervised and consistency planes ALTERNATE over the grid (pairs first, the longer set's rest behind them): a
+    // consistency plane of the analytic route brings 8 KB into flight, a supervised one 24 KB, and a wave made of
+    // consistency planes only (the second half of a grid ordered by kind) left HBM idle — Little's law:
+    // 8 resident CTAs x 8 KB per SM at 2-4 us of loaded latency is 2.7 TB/s, which is what that half ran at.
+    const int npair = min(a.planes_s, a.planes_t);
+    const int bid = static_cast<int>(blockIdx.x);
+    const bool sup = bid < 2 * npair ? (bid & 1) == 0 : a.planes_s > a.planes_t;
+    const int64_t plane = bid < 2 * npair ? (bid >> 1) : bid - npair;
+    const int slot = sup ? static_cast<int>(plane) : a.planes_s + static_cast<int>(plane);   // partial[]: supervised planes first
     const float* tab = nullptr;
     if (!sup && tea == nullptr) {  // CTA-uniform: the window table of the analytic teacher map
         tab = build_window_table(s_tab, a.gw);
         __syncthreads();
     }
-    const int64_t plane = sup ? blockIdx.x : blockIdx.x - a.planes_s;
     const float g = a.grad_scale_dev ? __ldg(a.grad_scale_dev) : a.grad_scale;
     const TS* s;
     const TT* t;
@@ -426,7 +433,7 @@ loss_step_kernel(const TS* __restrict__ y_s, const TT* __restrict__ label, const
         }
     }
     acc = block_sum<kStepThreads>(acc, red);
-    if (threadIdx.x == 0) a.partial[blockIdx.x] = plane_scale * acc;
+    if (threadIdx.x == 0) a.partial[slot] = plane_scale * acc;
     if (last_block_done(a.ticket, gridDim.x)) {
         const float ss = a.planes_s ? cta_sum_array(a.partial, a.planes_s, red) : 0.0f;
         const float sc = a.planes_t ? cta_sum_array(a.partial + a.planes_s, a.planes_t, red) : 0.0f;
