@@ -41,7 +41,7 @@ from .optim import SGD, Adam, GradScaler
 from .stylize import StyleTransfer
 from .rewarp import affine_nearest, occlude_keypoints, student_recon, teacher_recon
 
-__version__ = "0.3.0"
+__version__ = "0.3.1"
 
 __all__ = [
     "UdapeError", "library_path", "load_library", "check_tickets",

@@ -32,10 +32,14 @@
 //   general route (rewarp_fwd_kernel): gathers straight from global memory; used for image-sized
 //     planes (occlusion, 3x256x256), ragged widths and the paste / pass-through options.
 //
-// Backward (student recon): grad_in[s] = sum of grad_out[p] over {p : src(p) = s}.  No float
-// atomics: the CTA inverts the composed map in shared memory (integer counting sort, lists sorted
-// by p) once per sample and every channel then sums its list in ascending p — deterministic.
-// The gradient plane is staged through the same padded shared-memory buffers.
+// Backward (student recon): grad_in[s] = sum of grad_out[p] over {p : src(p) = s}, float32 sums in ascending p,
+// one rounding; no float atomics anywhere.
+//   with a plan (what autograd and the step use): the forward side builds, once per batch, a PUSH PLAN — a
+//     shared-memory slot for every output pixel — and the backward is a branch-free scatter into those slots,
+//     one ordered fold per source pixel that has several contributors, and a read-out (rewarp_push_plan_kernel,
+//     rewarp_bwd_push2_kernel / rewarp_bwd_push_kernel below);
+//   without one: the CTA inverts the composed map in shared memory (integer counting sort, lists sorted by p)
+//     once per sample and every channel sums its lists, staged through the padded buffers (the fallback).
 #include <cooperative_groups.h>
 
 #include <cstdlib>
@@ -863,7 +867,7 @@ __device__ __forceinline__ void build_map_fast(const float* __restrict__ s_theta
 //   * the first contributor of a source pixel (rank 0, the smallest p) is stored straight into the padded fp32
 //     accumulator plane at the source pixel;
 //   * every later contributor (rank >= 1) is stored into a TAIL array ordered by (source pixel, rank);
-//   * pixels without a source are stored into a dummy word.
+//   * pixels without a source carry a marker offset and are not stored at all.
 // One barrier later the thread that owns a GROUP (a source pixel with two or more contributors) folds the group's
 // tail entries — contiguous, ascending p — into the accumulator:  ((v0 + v1) + v2) + ...  the same fp32 order, bit
 // for bit, as the list-based kernels below and as a sequential CPU scatter.  Source pixels without contributors
@@ -1103,8 +1107,10 @@ rewarp_bwd_push_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __rest
 #pragma unroll
         for (int k = 0; k < kRwPix; ++k) {
             const uint32_t off = (cw[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+            if (off != dummy) {   // pixels without a source push nothing (their slot offset is only a marker)
 #pragma unroll
-            for (int n = 0; n < NP; ++n) *reinterpret_cast<float*>(smem + n * pitch + off) = word_elem<T>(g[n][k / EPW], k % EPW);
+                for (int n = 0; n < NP; ++n) *reinterpret_cast<float*>(smem + n * pitch + off) = word_elem<T>(g[n][k / EPW], k % EPW);
+            }
         }
         __syncthreads();
         if (pass + 1 < pass1) load(pass + 1);   // in flight while the groups are folded and the sums leave
@@ -1265,8 +1271,9 @@ rewarp_bwd_push2_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __res
                 for (int m = 0; m < NPAIR; ++m) {
                     if (m < live) {
                         const uint32_t ga = stage[(2 * m) * nwords + word], gb = stage[(2 * m + 1) * nwords + word];
-                        *reinterpret_cast<uint32_t*>(smem + m * pitch + o0) = __byte_perm(ga, gb, 0x5410);
-                        *reinterpret_cast<uint32_t*>(smem + m * pitch + o1) = __byte_perm(ga, gb, 0x7632);
+                        // (pixels without a source push nothing: their slot offset is only a marker)
+                        if (o0 != dummy) *reinterpret_cast<uint32_t*>(smem + m * pitch + o0) = __byte_perm(ga, gb, 0x5410);
+                        if (o1 != dummy) *reinterpret_cast<uint32_t*>(smem + m * pitch + o1) = __byte_perm(ga, gb, 0x7632);
                     }
                 }
             }

@@ -136,9 +136,10 @@ def stage_table(stages, height: int, width: int, dtype: torch.dtype = torch.floa
     return table, half_mask, (_lib._DTYPE_CODE[ac] if ac is not None else _lib.F16)
 
 
-# The backward reads an inverse plan the forward (or build_inverse_plan, on another stream) wrote: the composed map
-# of every sample inverted once per batch.  UDAPE_REWARP_PLAN=0 makes the backward invert the map itself instead
-# (one launch less, but 85-120 us against 15-66 us at the trainers' / the microbench sizes on B200).
+# The backward reads an inverse plan the forward (or build_inverse_plan, on another stream) wrote: per sample a
+# shared-memory slot for every output pixel and the source pixels with several contributors, built once per batch.
+# UDAPE_REWARP_PLAN=0 makes the backward build and invert the map itself instead (one launch less, but 86-120 us
+# against 5.6-25 us at the trainers' / the microbench sizes on B200).
 USE_INVERSE_PLAN = os.environ.get("UDAPE_REWARP_PLAN", "1") == "1"
 
 
@@ -168,8 +169,8 @@ def _check_theta(y, theta):
 
 def inverse_plan_buffer(y: torch.Tensor) -> torch.Tensor | None:
     """Device buffer for the inverse plan of a re-warp of ``y`` ([B,C,H,W]) — what the forward saves for
-    the backward (the composed map of every sample, inverted once) — or None when the plan route does
-    not apply to this plane size (the backward then inverts the map itself)."""
+    the backward (a slot per output pixel + the source pixels with several contributors; opaque) — or None
+    when the plan route does not apply to this plane size (the backward then inverts the map itself)."""
     b, _, h, w = y.shape
     n = _lib.load().udape_rewarp_plan_elems(h, w, y.element_size())
     return torch.empty((b, n), dtype=torch.int16, device=y.device) if n > 0 else None
