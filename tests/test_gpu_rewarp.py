@@ -323,3 +323,52 @@ def test_rewarp_wide_route_equals_the_256_thread_kernels(dev, dt, monkeypatch):
         for route, (f, bw) in res.items():
             assert torch.equal(f, res["wide"][0]), (route, "forward", b, k, h, w)
             assert torch.equal(bw, res["wide"][1]), (route, "backward", b, k, h, w)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("c", [5, 8])
+def test_rewarp_backward_degenerate_maps(dev, dt, c):
+    """The push plan on maps it was not tuned for, against a sequential float32 scatter on the host (ascending
+    output pixel, one rounding): every output pixel onto ONE source pixel (a list of 4096 entries: 4095 tail
+    slots, one group), no output pixel inside the image (nothing is pushed), the identity (no group), a 2x zoom
+    (every source pixel four contributors) and an ordinary augmentation; an odd channel count leaves the last
+    pass of a sample partly empty.  Also: the plan route and the list route agree bit for bit."""
+    h = w = 64
+    hw = h * w
+    one = [[0.0, 0.0, 0.1], [0.0, 0.0, -0.2]]          # grid constant: every pixel reads the same source
+    none = [[0.0, 0.0, 5.0], [0.0, 0.0, 5.0]]          # grid outside [-1, 1]
+    ident = [[1.0 / 32, 0.0, 0.0], [0.0, 1.0 / 32, 0.0]]   # rows are theta / (0.5 * size), pixels in, grid out
+    zoom = [[0.5 / 32, 0.0, 0.0], [0.0, 0.5 / 32, 0.0]]
+    theta = torch.tensor([one, none, ident, zoom], dtype=torch.float32).reshape(4, 1, 6)
+    aug = S.aug_params(1, seed=404)
+    half = dt != torch.float32
+    extra = RW.stage_table(RW.recon_stages(aug, 4.0, 1), h, w, torch.float32, None)[0][:, :1]   # one ordinary stage
+    theta = torch.cat([theta, extra.reshape(1, 1, 6)], 0).to(dev)
+    b = theta.shape[0]
+    # the source index of every output pixel, from gathering an index image (float32, exact): 0 = no source
+    index_img = (torch.arange(hw, dtype=torch.float32) + 1).reshape(1, 1, h, w).expand(b, 1, h, w).contiguous().to(dev)
+    src = RW.gather(index_img, theta, 0, None).reshape(b, hw).long().cpu() - 1
+    assert (src[0] == src[0, 0]).all() and src[0, 0] >= 0 and (src[1] < 0).all()
+    assert torch.equal(src[2], torch.arange(hw)) and src[3].unique(return_counts=True)[1].max() == 4
+    g = (torch.randn(b, c, h, w, generator=torch.Generator().manual_seed(7)) * 2).to(dt)
+    g[:, 0, 0, :8] = -0.0                               # a lone -0.0 contributor must come out as +0.0
+    want = torch.zeros(b, c, hw, dtype=torch.float32)
+    gf = g.float().reshape(b, c, hw)
+    for i in range(b):
+        ok = src[i] >= 0
+        want[i].index_add_(1, src[i][ok], gf[i][:, ok])  # CPU index_add_: sequential, ascending output pixel
+    want = want.to(dt).reshape(b, c, h, w)
+    gd = g.to(dev)
+    x = torch.zeros(b, c, h, w, dtype=dt, device=dev)
+    plan = RW.build_inverse_plan(x, theta, 0, None)
+    assert plan is not None
+    got_plan = RW.gather_backward(gd, theta, 0, None, plan=plan)
+    got_list = RW.gather_backward(gd, theta, 0, None)
+    assert torch.equal(got_plan, got_list)
+    if not half:
+        assert torch.equal(got_plan.cpu(), want)
+    else:
+        # the sum of 4096 rounded-once values: same order, same float32 arithmetic -> same bits
+        assert torch.equal(got_plan.cpu().float(), want.float())
+    assert not torch.signbit(got_plan[2, 0, 0, :8]).any()
+    del half
