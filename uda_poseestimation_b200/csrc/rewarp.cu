@@ -70,6 +70,7 @@ struct RewarpArgs {
     int paste_after;        // the paste remap is applied after this many evaluated stages
     int B, C, H, W;
     int cpc;                // channels per CTA
+    int tile_log2;          // wide2 route, 2-byte planes: a warp's 32 output words form a tile 2^tile_log2 words wide (0: a row walk)
 };
 
 __device__ __forceinline__ float round_grid(float v, int grid_dtype) {
@@ -1030,6 +1031,18 @@ template <> __device__ __forceinline__ void store_quad<__nv_bfloat16>(__nv_bfloa
     reinterpret_cast<uint2*>(plane)[vi] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
 }
 
+// The passes of a launch, sample-major (ppc passes of NP planes per sample, the last one possibly shorter); a CTA
+// takes a contiguous run of equal length.  (Measured and dropped, profiles/r02ak: every sample's full passes first and
+// the short ones after, in runs of equal cost (fixed + planes) — a pass costs nearly the same whatever its plane
+// count, and a pass that changes the sample pays the plan's load latency on top: 25.4 - 46.8 us against 24.7 at C5.)
+struct PassOrder {
+    int ppc, np;
+    long long n_all;
+    __device__ __forceinline__ PassOrder(int B, int C, int NP) : ppc((C + NP - 1) / NP), np(NP), n_all(static_cast<long long>(B) * ((C + NP - 1) / NP)) {}
+    __device__ __forceinline__ int first(unsigned k, unsigned grid) const { return static_cast<int>(n_all * k / grid); }
+    __device__ __forceinline__ void at(int v, int& b, int& c) const { b = v / ppc; c = (v - b * ppc) * np; }
+};
+
 // backward from the push plan.  The work is cut into PASSES of NP gradient planes of one sample; the grid is one
 // wave of CTAs and CTA i owns a contiguous, equal share of the passes (a sample's passes may be split between
 // CTAs; a CTA reloads its per-sample state — 8 registers of slots — when its run crosses into the next sample).
@@ -1047,9 +1060,8 @@ rewarp_bwd_push_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __rest
     extern __shared__ __align__(16) uint32_t rw_smem[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(rw_smem);
     const int hw = a.H * a.W, hw8 = (hw + 7) & ~7, nwords = hw / EPW, nquads = hw / 4;
-    const int ppc = (a.C + NP - 1) / NP;                      // passes per sample
-    const int64_t npass = static_cast<int64_t>(a.B) * ppc;
-    const int pass0 = static_cast<int>(npass * blockIdx.x / gridDim.x), pass1 = static_cast<int>(npass * (blockIdx.x + 1) / gridDim.x);
+    const PassOrder order(a.B, a.C, NP);
+    const int pass0 = order.first(blockIdx.x, gridDim.x), pass1 = order.first(blockIdx.x + 1, gridDim.x);
     if (pass0 >= pass1) return;
     const int pitch = push_pitch_bytes(acc_words, hw);
     const uint32_t tail0 = static_cast<uint32_t>(acc_words) * 4u, dummy = tail0 + static_cast<uint32_t>(hw8) * 4u;
@@ -1067,7 +1079,8 @@ rewarp_bwd_push_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __rest
     const uint32_t* g32 = reinterpret_cast<const uint32_t*>(gout);
     uint32_t g[NP][SLOTS];
     auto load = [&](int pass) {
-        const int b = pass / ppc, c = (pass - b * ppc) * NP;
+        int b, c;
+        order.at(pass, b, c);
 #pragma unroll
         for (int n = 0; n < NP; ++n) {
             const uint32_t* src = g32 + (static_cast<int64_t>(b) * a.C + c + n) * nwords + threadIdx.x;
@@ -1082,7 +1095,8 @@ rewarp_bwd_push_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __rest
     const uint2* g_group = nullptr;
     __syncthreads();
     for (int pass = pass0; pass < pass1; ++pass) {
-        const int b = pass / ppc, c = (pass - b * ppc) * NP;
+        int b, c;
+        order.at(pass, b, c);
         const int np = min(NP, a.C - c);
         if (b != cur_b) {   // CTA-uniform: the per-sample state
             cur_b = b;
@@ -1201,16 +1215,16 @@ rewarp_bwd_push2_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __res
     uint8_t* smem = reinterpret_cast<uint8_t*>(rw_smem);
     const int hw = FULL ? kRwThreads * kRwPix : a.H * a.W;
     const int hw8 = (hw + 7) & ~7, nwords = hw / 2, nquads = hw / 4;
-    const int ppc = (a.C + NP - 1) / NP;                      // passes per sample
-    const int64_t npass = static_cast<int64_t>(a.B) * ppc;
-    const int pass0 = static_cast<int>(npass * blockIdx.x / gridDim.x), pass1 = static_cast<int>(npass * (blockIdx.x + 1) / gridDim.x);
+    const PassOrder order(a.B, a.C, NP);
+    const int pass0 = order.first(blockIdx.x, gridDim.x), pass1 = order.first(blockIdx.x + 1, gridDim.x);
     if (pass0 >= pass1) return;
     const int pitch = push_pitch_bytes(acc_words, hw);
     const uint32_t tail0 = static_cast<uint32_t>(acc_words) * 4u, dummy = tail0 + static_cast<uint32_t>(hw8) * 4u;
     uint32_t* stage = reinterpret_cast<uint32_t*>(smem + NPAIR * pitch);                 // [NP][nwords]
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + NPAIR * pitch + NP * hw8 * 2);
     auto fetch = [&](int pass) {   // one thread: the planes of `pass` into the staging buffer
-        const int b = pass / ppc, c = (pass - b * ppc) * NP;
+        int b, c;
+        order.at(pass, b, c);
         const uint32_t bytes = static_cast<uint32_t>(min(NP, a.C - c)) * static_cast<uint32_t>(hw) * 2u;
         mbar_expect_tx(bar, bytes);
         bulk_load(stage, gout + (static_cast<int64_t>(b) * a.C + c) * hw, bytes, bar);
@@ -1243,7 +1257,8 @@ rewarp_bwd_push2_kernel(const RewarpArgs a, const T* __restrict__ gout, T* __res
     uint32_t parity = 0;
     __syncthreads();
     for (int pass = pass0; pass < pass1; ++pass) {
-        const int b = pass / ppc, c = (pass - b * ppc) * NP;
+        int b, c;
+        order.at(pass, b, c);
         if (b != cur_b) {   // CTA-uniform: the per-sample state
             cur_b = b;
             const uint16_t* P = plan + static_cast<int64_t>(b) * plan_elems_for(hw);
@@ -1510,14 +1525,29 @@ rewarp_wide2_kernel(const RewarpArgs a, T* __restrict__ out) {
         });
     }
     __syncthreads();
-    uint32_t idx[PIX / 2];   // the staged byte offsets of this thread's pixels (words t + 512*slot), two per register
+    // Which output words a thread owns: word tw + 512 * slot.  tw = threadIdx.x makes the 32 lanes of a gather walk
+    // one output row, i.e. a LINE of the source plane: whatever the row layout, some rotation makes that line collide
+    // in the banks (ncu, C5 fp16: LDS.U16 at 2.4-2.8 wavefronts each, the kernel bound by them).  With tile_log2 = t
+    // the lanes cover a compact tile of 2^t words x 2^(5-t) rows instead, which maps to a compact patch of the source
+    // for every rotation: the XOR swizzle spreads the patch's rows over the chunk columns.  Measured at C5, fp16
+    // (profiles/r02ai): row walk 24.0 us, 16 x 4 px 21.0 us (t = 3, the default), 32 x 2 px 21.3, 8 x 8 px 26.4 (its
+    // stores fill half a 32-byte sector per row); other row keys of the swizzle (bit-reversed row) change nothing;
+    // fp32 planes keep the row walk (31.8 us against 33.1 / 47.2 tiled).
+    int tw = threadIdx.x;
+    if (a.tile_log2 > 0) {
+        const int tl = a.tile_log2, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        const int row_words = a.W / EPW, tpr_log2 = (31 - __clz(row_words)) - tl;    // tiles per row
+        const int th_log2 = 5 - tl;                                                  // rows of a tile
+        tw = ((((w >> tpr_log2) << th_log2) + (lane >> tl)) * row_words) + ((w & ((1 << tpr_log2) - 1)) << tl) + (lane & ((1 << tl) - 1));
+    }
+    uint32_t idx[PIX / 2];   // the staged byte offsets of this thread's pixels (words tw + 512*slot), two per register
 #pragma unroll
     for (int k = 0; k < PIX; k += 2) {
-        const int p0 = ((k / EPW) * kW2Threads + threadIdx.x) * EPW + (k % EPW);
-        const int p1 = (((k + 1) / EPW) * kW2Threads + threadIdx.x) * EPW + ((k + 1) % EPW);
+        const int p0 = ((k / EPW) * kW2Threads + tw) * EPW + (k % EPW);
+        const int p1 = (((k + 1) / EPW) * kW2Threads + tw) * EPW + ((k + 1) % EPW);
         idx[k >> 1] = static_cast<uint32_t>(map[p0]) | (static_cast<uint32_t>(map[p1]) << 16);
     }
-    uint32_t* o32 = reinterpret_cast<uint32_t*>(out + static_cast<int64_t>(b) * a.C * kW2Pixels) + threadIdx.x;
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(out + static_cast<int64_t>(b) * a.C * kW2Pixels) + tw;
     for (int it = 0; it < nitems; ++it) {
         cp_async_wait<RING - 2>();   // this thread's copies of item `it` have landed ...
         __syncthreads();                // ... everybody's have, and everybody is done with item it-1
@@ -1637,7 +1667,7 @@ static int fill_common(RewarpArgs& a, const char* name, int views, int stages, i
     UDAPE_REQUIRE(half_mask >= 0 && half_mask < (1 << stages), UDAPE_ERR_ARG, "%s: half_mask has bits beyond the stages", name);
     a.views = views; a.stages = stages; a.half_mask = half_mask; a.grid_dtype = grid_dtype;
     a.B = static_cast<int>(B); a.C = static_cast<int>(C); a.H = static_cast<int>(H); a.W = static_cast<int>(W);
-    a.paste = nullptr; a.active = nullptr; a.paste_after = 0;
+    a.paste = nullptr; a.active = nullptr; a.paste_after = 0; a.tile_log2 = 0;
     return UDAPE_OK;
 }
 
@@ -1705,6 +1735,19 @@ static bool wide2_route(int64_t H, int64_t W, int es) {
     if (e && e[0] == '0') return false;
     const int64_t cpr = W * es / 16;   // 16-byte chunks per row: a power of two
     return H * W == kW2Pixels && (W * es) % 16 == 0 && cpr >= 1 && (cpr & (cpr - 1)) == 0;
+}
+
+// the tile a warp's gather covers (see the kernel): 32 words must split into whole tile rows, and 16 warps x 32
+// words = 512 words must be whole rows of tiles
+static int wide2_tile_log2(int64_t W, int es) {
+    int tl = es == 2 ? 3 : 0;
+    if (const char* e = std::getenv("UDAPE_RW_TILE")) tl = std::atoi(e);   // tuning: 0 = row walk, 2 = 8x8 px, 3 = 16x4 px
+    const int64_t row_words = W * es / 4;
+    if (tl < 1 || tl > 4 || (row_words & (row_words - 1)) != 0 || (1 << tl) > row_words) return 0;
+    const int64_t tiles_per_row = row_words >> tl, rows_per_tile = 32 >> tl;
+    // a slot of 512 words = 512 / row_words rows must hold whole tile rows
+    if ((512 / row_words) % rows_per_tile != 0 || 512 % row_words != 0 || tiles_per_row > 16) return 0;
+    return tl;
 }
 
 constexpr int kRwDeepRing = 6;   // single view, a CTA that owns >= 6 planes
@@ -1785,6 +1828,7 @@ extern "C" int udape_rewarp_fwd(const void* const* in, const float* const* theta
             const size_t smem = static_cast<size_t>(RING) * G * (kW2Pixels * sizeof(T) + 16) + sizeof(uint16_t) * kW2Pixels;
             const int r2 = reserve_smem(rewarp_wide2_kernel<T, G, RING>, smem, "udape_rewarp_fwd");
             if (r2) return r2;
+            a.tile_log2 = wide2_tile_log2(W, es);
             rewarp_wide2_kernel<T, G, RING><<<static_cast<unsigned>(B), kW2Threads, smem, st>>>(a, static_cast<T*>(out));
         });
         return check_launch("udape_rewarp_fwd");
