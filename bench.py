@@ -157,11 +157,19 @@ class ClockSampler:
 # `--impl reference` arm) or on CUDA tensors (eager PyTorch on the same GPU: what each kernel replaces)
 # ------------------------------------------------------------------------------------------------
 def reference_step_factory(cfg: dict, seed: int, device="cpu", tail: bool = True):
-    """Returns (step_fn, batch): one reference-style step on seeded inputs, everything as train_human.py:347-444
+    """Returns (step_fn, batch, kind): one reference-style step on seeded inputs, everything as train_human.py:347-444
     (fp32 on the CPU, which has no fp16 autocast path; fp16 student maps on CUDA), `tail`: incl. GradScaler
-    unscale + Adam (:436-437) in front of the EMA (:438)."""
-    from oracle import reference_port as R  # test infrastructure, allowed here as the timed baseline
+    unscale + Adam (:436-437) in front of the EMA (:438).
 
+    kind "reference": the reference's OWN functions and objects (oracle/reference_live.py: imported from the
+    reference tree, or from the bytecode oracle/build_ref.py compiled from it into oracle/_ref/, which travels to
+    the GPU box) with the trainer's inline loops restated around them; kind "port": oracle/reference_port.py
+    alone, when neither is present."""
+    from oracle import reference_live as RL  # test infrastructure, allowed here as the timed baseline
+    from oracle import reference_port as RP
+
+    live = RL.available()
+    R = RL if live else RP
     dev = torch.device(device)
     on_gpu = dev.type == "cuda"
     host = make_host_inputs(cfg, seed, student_dtype=torch.float16 if on_gpu else torch.float32, pin=False)
@@ -175,8 +183,14 @@ def reference_step_factory(cfg: dict, seed: int, device="cpu", tail: bool = True
     student = S.parameter_list(shapes, seed + 6, device=dev)
     teacher = [x.clone() for x in student]
     grads = synthetic_grads(shapes, seed + 9, device=dev) if tail else None
-    m = [torch.zeros_like(x) for x in student] if tail else None
-    v = [torch.zeros_like(x) for x in student] if tail else None
+    trainer_tail = ema = None
+    if live:
+        # the reference's own objects: torch.optim.Adam + GradScaler + OldWeightEMA (train_human.py:139-141, :324)
+        trainer_tail = RL.TrainerTail(student, teacher, LR, 0.999, LOSS_SCALE, dev)
+        scaler, ema = trainer_tail.scaler, trainer_tail.ema
+    else:
+        m = [torch.zeros_like(x) for x in student] if tail else None
+        v = [torch.zeros_like(x) for x in student] if tail else None
     state = {"step": 0}
     rng = np.random.RandomState(seed)
 
@@ -193,22 +207,30 @@ def reference_step_factory(cfg: dict, seed: int, device="cpu", tail: bool = True
         with (torch.autocast("cuda", dtype=torch.float16) if on_gpu else contextlib.nullcontext()):     # :414
             y_t_recon = R.student_recon(y_t, host["aug_stu"], 4.0, autocast=not on_gpu)  # :417-423
             loss = R.joints_mse_loss(y_s, label, weight) + 1.0 * R.cons_loss(y_t_recon, rect, tea_mask=mask)
-        (loss * LOSS_SCALE).backward()
-        if tail:
-            _, state["step"] = R.student_teacher_step("adam", student, [g.clone() for g in grads], m, v, teacher,
-                                                      state["step"], LOSS_SCALE, 0.999, lr=LR)   # :436-438
+        if live:
+            scaler.scale(loss).backward()                                               # :435
+            if tail:
+                trainer_tail.step(grads)                                                # :436-441
+            else:
+                ema.step()                                                              # :438
+                scaler.update()
         else:
-            R.ema_step(teacher, student, 0.999)
+            (loss * LOSS_SCALE).backward()
+            if tail:
+                _, state["step"] = R.student_teacher_step("adam", student, [g.clone() for g in grads], m, v, teacher,
+                                                          state["step"], LOSS_SCALE, 0.999, lr=LR)   # :436-438
+            else:
+                R.ema_step(teacher, student, 0.999)
         acc, avg, cnt, pred = R.accuracy(y_s.detach().cpu().numpy(), label.cpu().numpy())   # :443-444
         return float(loss), avg, t1, t2, table
 
-    return step, b
+    return step, b, ("reference" if live else "port")
 
 
 def time_reference_path(cfg: dict, seed: int, steps: int, warmup: int, budget_s: float | None, device="cpu", tail: bool = True) -> dict:
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step, b = reference_step_factory(cfg, seed, device=device, tail=tail)
+    step, b, kind = reference_step_factory(cfg, seed, device=device, tail=tail)
     sync = torch.cuda.synchronize if device != "cpu" else (lambda: None)
     t0 = time.perf_counter()
     step()
@@ -227,12 +249,17 @@ def time_reference_path(cfg: dict, seed: int, steps: int, warmup: int, budget_s:
         sync()
         ts.append(time.perf_counter() - t0)
     mean, med = float(np.mean(ts)), float(np.median(ts))
+    from oracle import ref_loader
+    impl = ("the reference's own functions and objects (adain, rectify, JointsMSELoss, ConsLoss, accuracy, generate_target, "
+            f"OldWeightEMA, torch Adam + GradScaler; loaded from {'the reference tree' if ref_loader.kind() == 'source' else 'oracle/_ref bytecode compiled from the reference tree'}) "
+            "with the trainer's inline re-warp loops / masks restated around them (oracle/reference_live.py)"
+            if kind == "reference" else "oracle/reference_port.py (restated; reference files not present on this box)")
     what = (f"{n} full steps of {cfg['name']} (batch {b}, {cfg['joints']} keypoints) after {warmup} warm-up, incl. "
-            f"{'GradScaler unscale + Adam + ' if tail else ''}EMA over the PoseResNet-101 census; oracle/reference_port.py")
+            f"{'GradScaler unscale + Adam + ' if tail else ''}EMA over the PoseResNet-101 census; {impl}")
     if device == "cpu":
-        return dict(value=b / mean, unit=UNIT, cores=cores, kind="port", ms_per_step=mean * 1e3, steps=n,
+        return dict(value=b / mean, unit=UNIT, cores=cores, kind=kind, ms_per_step=mean * 1e3, steps=n,
                     sample=what + f", fp32, torch.set_num_threads({cores})")
-    return dict(value=b / med, unit=UNIT, ms_per_step=med * 1e3, steps=n,
+    return dict(value=b / med, unit=UNIT, ms_per_step=med * 1e3, steps=n, kind=kind,
                 sample=what + " as eager PyTorch on CUDA tensors of this GPU (fp16 student maps; its per-sample "
                               "tF.affine loops, CPU staging tensors, .item() syncs and the D2H for accuracy() included); median")
 

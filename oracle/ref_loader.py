@@ -1,17 +1,22 @@
-"""Loads the REAL reference functions by file path — TEST INFRASTRUCTURE ONLY.
+"""Loads the REAL reference functions — TEST INFRASTRUCTURE ONLY.
 
-``/root/reference`` exists only in the build container, never on the GPU box, so nothing in
-the ``-m gpu`` tests, ``smoke()`` or ``bench.py`` may depend on this module at run time.  It is
-used (a) by ``tests/golden/make_golden.py`` to generate the committed fixtures and (b) by
-``tests/test_oracle_vs_reference.py`` (skipped when the tree is absent) to pin
-``oracle/reference_port.py`` against the reference itself.
+Two sources, in this order:
 
-The reference's package ``__init__``s do not import under current torchvision / without
-``webcolors``, so each hot-path file is loaded on its own with
-``importlib.util.spec_from_file_location``.
+* the reference tree itself (``/root/reference``, build container only): each hot-path file is imported by path;
+* ``oracle/_ref/*.pyc`` — CPython bytecode compiled from those same files by ``oracle/build_ref.py`` (outputs only,
+  git-ignored, travels to the GPU box): what lets ``bench.py``'s CPU arm and ``tests/test_gpu_vs_reference.py`` run
+  the reference's own functions where the tree does not exist.
+
+Used by ``tests/golden/make_golden.py`` (fixtures), ``tests/test_oracle_vs_reference.py`` (pins
+``oracle/reference_port.py`` against the reference), ``oracle/reference_live.py`` (the reference-backed step of the
+CPU baseline) and the GPU parity tests.  Never imported by the product package.
+
+The reference's package ``__init__``s do not import under current torchvision / without ``webcolors``
+(SURVEY.md §4), so each hot-path file is loaded on its own.
 """
 from __future__ import annotations
 
+import importlib.machinery
 import importlib.util
 import os
 import sys
@@ -32,8 +37,32 @@ _FILES = {
 }
 
 
-def available() -> bool:
+BYTECODE_ROOT = Path(__file__).resolve().parent / "_ref"
+
+
+def source_available() -> bool:
     return all((REFERENCE_ROOT / f).is_file() for f in _FILES.values())
+
+
+def bytecode_available() -> bool:
+    """oracle/_ref holds bytecode of every hot-path file, compiled by THIS interpreter version."""
+    try:
+        import json
+
+        manifest = json.loads((BYTECODE_ROOT / "MANIFEST.json").read_text())
+    except (OSError, ValueError):
+        return False
+    return (manifest.get("magic") == importlib.util.MAGIC_NUMBER.hex()
+            and all((BYTECODE_ROOT / f"{n}.pyc").is_file() for n in _FILES))
+
+
+def available() -> bool:
+    return source_available() or bytecode_available()
+
+
+def kind() -> str | None:
+    """Where load() takes the reference from: "source" | "bytecode" | None."""
+    return "source" if source_available() else ("bytecode" if bytecode_available() else None)
 
 
 def load(name: str) -> types.ModuleType:
@@ -41,12 +70,21 @@ def load(name: str) -> types.ModuleType:
     mod_name = f"_udape_ref_{name}"
     if mod_name in sys.modules:
         return sys.modules[mod_name]
-    path = REFERENCE_ROOT / _FILES[name]
     if name == "adain_net":
         # adain/net.py does `from function import ...` (it is run with adain/ as the working directory)
         sys.modules.setdefault("function", load("function"))
-    spec = importlib.util.spec_from_file_location(mod_name, path)
+    if source_available():
+        spec = importlib.util.spec_from_file_location(mod_name, REFERENCE_ROOT / _FILES[name])
+    elif bytecode_available():
+        path = str(BYTECODE_ROOT / f"{name}.pyc")
+        spec = importlib.util.spec_from_loader(mod_name, importlib.machinery.SourcelessFileLoader(mod_name, path), origin=path)
+    else:
+        raise ImportError(f"reference file {_FILES[name]}: neither {REFERENCE_ROOT} nor {BYTECODE_ROOT} holds it")
     mod = importlib.util.module_from_spec(spec)
     sys.modules[mod_name] = mod
-    spec.loader.exec_module(mod)
+    try:
+        spec.loader.exec_module(mod)
+    except BaseException:
+        sys.modules.pop(mod_name, None)
+        raise
     return mod

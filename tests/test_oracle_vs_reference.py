@@ -4,6 +4,7 @@ golden fixtures, which were produced by the same functions.  The tree exists onl
 everywhere else (the GPU box) this module is skipped.  Equality is exact: the oracle calls the same
 torch / numpy primitives in the same order.
 """
+import os
 import types
 
 import numpy as np
@@ -142,3 +143,36 @@ def test_style_transfer_forward_only():
         ref = torch.maximum(torch.minimum(g_t.permute(0, 2, 3, 1), hi), lo).permute(0, 3, 1, 2)
     assert torch.equal(R.style_transfer(sn.vgg, sn.decoder, content, style, 0.6), g_t)
     assert torch.equal(R.style_transfer(sn.vgg, sn.decoder, content, style, 0.6, lo, hi), ref)
+
+
+def test_bytecode_of_the_reference_loads_without_the_tree():
+    """oracle/build_ref.py compiles the hot-path files into oracle/_ref/*.pyc (outputs only); a process that cannot
+    see /root/reference — the GPU box — imports the reference's functions from there and gets the reference's results."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    from oracle import build_ref
+
+    if not build_ref.build(verbose=False):
+        pytest.skip("no reference tree and no prebuilt bytecode")
+    root = Path(__file__).resolve().parents[1]
+    code = (
+        "import torch, numpy as np\n"
+        "from oracle import ref_loader as L, reference_live as RL, reference_port as R\n"
+        "from uda_poseestimation_b200 import synthetic as S\n"
+        "assert L.kind() == 'bytecode', L.kind()\n"
+        "assert L.load('utils').rectify.__code__.co_filename.startswith('<reference>/')\n"
+        "hm = S.heatmaps(3, 4, seed=3, peak=(0.3, 1.2))\n"
+        "assert torch.equal(RL.rectify(hm.clone(), 2), R.rectify(hm.clone(), 2))\n"
+        "c, s = S.vgg_features(2, seed=1, channels=8)\n"
+        "assert torch.equal(RL.adain_mix(c, s, 0.3), R.adain_mix(c, s, 0.3))\n"
+        "a, b = RL.accuracy(hm.numpy(), S.heatmaps(3, 4, seed=4).numpy()), R.accuracy(hm.numpy(), S.heatmaps(3, 4, seed=4).numpy())\n"
+        "assert a[1] == b[1] and a[2] == b[2] and np.array_equal(a[0], b[0])\n"
+        "j, v = S.keypoints(2, 5, seed=2)\n"
+        "assert np.array_equal(RL.generate_target(j[0], v[0], (64, 64), 2, (256, 256))[0], R.generate_target(j[0], v[0], (64, 64), 2, (256, 256))[0])\n"
+        "print('ok')\n"
+    )
+    env = dict(os.environ, UDAPE_REFERENCE_ROOT="/nonexistent-reference-root")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root, env=env)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]

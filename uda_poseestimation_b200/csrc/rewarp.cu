@@ -1034,7 +1034,9 @@ template <> __device__ __forceinline__ void store_quad<__nv_bfloat16>(__nv_bfloa
 // The passes of a launch, sample-major (ppc passes of NP planes per sample, the last one possibly shorter); a CTA
 // takes a contiguous run of equal length.  (Measured and dropped, profiles/r02ak: every sample's full passes first and
 // the short ones after, in runs of equal cost (fixed + planes) — a pass costs nearly the same whatever its plane
-// count, and a pass that changes the sample pays the plan's load latency on top: 25.4 - 46.8 us against 24.7 at C5.)
+// count: 25.4 - 46.8 us against 24.7 at C5.  Requesting the next sample's plan words one pass ahead changed
+// nothing either (24.5 us): what a pass costs is its ~3 k cycles of shared-memory wavefronts — scattered pushes,
+// 128-bit read-out — and its three barriers, not the plan's latency.)
 struct PassOrder {
     int ppc, np;
     long long n_all;
