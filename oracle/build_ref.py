@@ -2,7 +2,7 @@
 
 The reference is pure Python; what a C reference's ``gcc`` recipe is for a compiled one, ``py_compile`` is here: the
 eight hot-path files are compiled FROM THE SOURCES WHERE THEY LIE under ``/root/reference`` and only the outputs
-(``*.pyc`` code objects + a manifest) are written, into ``oracle/_ref/`` — git-ignored, so the history stays free of
+(``*.code`` files: marshalled code objects in the .pyc format — the snapshot sent to the GPU box skips ``*.pyc`` — + a manifest) are written, into ``oracle/_ref/`` — git-ignored, so the history stays free of
 reference code, but not gpurun-ignored, so the directory travels to the GPU box like the built ``.so``.  There
 ``oracle/ref_loader.py`` imports the bytecode (same image, same CPython 3.12 magic number), which lets
 
@@ -48,7 +48,7 @@ def build(verbose: bool = True) -> bool:
     for name, rel in ref_loader._FILES.items():
         src = root / rel
         digest = hashlib.sha256(src.read_bytes()).hexdigest()
-        out = OUT / f"{name}.pyc"
+        out = OUT / f"{name}.code"
         if files.get(name, {}).get("sha256") == digest and out.is_file():
             continue
         # dfile: the name tracebacks show (relative to the reference root); unchecked hash: valid without the source

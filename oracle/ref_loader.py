@@ -3,7 +3,7 @@
 Two sources, in this order:
 
 * the reference tree itself (``/root/reference``, build container only): each hot-path file is imported by path;
-* ``oracle/_ref/*.pyc`` — CPython bytecode compiled from those same files by ``oracle/build_ref.py`` (outputs only,
+* ``oracle/_ref/*.code`` (.pyc format) — CPython bytecode compiled from those same files by ``oracle/build_ref.py`` (outputs only,
   git-ignored, travels to the GPU box): what lets ``bench.py``'s CPU arm and ``tests/test_gpu_vs_reference.py`` run
   the reference's own functions where the tree does not exist.
 
@@ -53,7 +53,7 @@ def bytecode_available() -> bool:
     except (OSError, ValueError):
         return False
     return (manifest.get("magic") == importlib.util.MAGIC_NUMBER.hex()
-            and all((BYTECODE_ROOT / f"{n}.pyc").is_file() for n in _FILES))
+            and all((BYTECODE_ROOT / f"{n}.code").is_file() for n in _FILES))
 
 
 def available() -> bool:
@@ -76,7 +76,7 @@ def load(name: str) -> types.ModuleType:
     if source_available():
         spec = importlib.util.spec_from_file_location(mod_name, REFERENCE_ROOT / _FILES[name])
     elif bytecode_available():
-        path = str(BYTECODE_ROOT / f"{name}.pyc")
+        path = str(BYTECODE_ROOT / f"{name}.code")
         spec = importlib.util.spec_from_loader(mod_name, importlib.machinery.SourcelessFileLoader(mod_name, path), origin=path)
     else:
         raise ImportError(f"reference file {_FILES[name]}: neither {REFERENCE_ROOT} nor {BYTECODE_ROOT} holds it")

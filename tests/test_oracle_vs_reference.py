@@ -146,7 +146,7 @@ def test_style_transfer_forward_only():
 
 
 def test_bytecode_of_the_reference_loads_without_the_tree():
-    """oracle/build_ref.py compiles the hot-path files into oracle/_ref/*.pyc (outputs only); a process that cannot
+    """oracle/build_ref.py compiles the hot-path files into oracle/_ref/*.code (.pyc format, outputs only); a process that cannot
     see /root/reference — the GPU box — imports the reference's functions from there and gets the reference's results."""
     import subprocess
     import sys
