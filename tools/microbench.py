@@ -206,6 +206,13 @@ def main():
             return lambda: chk(lib.udape_decode(d["tea"].data_ptr(), _lib.F32, planes, 64, 64, None, None, None, d["maxv"].data_ptr(),
                                                 d["pos"].data_ptr(), 0.9, d["conf"].data_ptr(), float(sigma), d["rect"].data_ptr(), st()))
 
+        def mk_decsel(r):   # the step's teacher call: decode + conf_table + k-th value mask in one launch, no map written
+            d = B(r)
+            tk = _lib.ticket(dev)
+            return lambda: chk(lib.udape_decode_select(d["tea"].data_ptr(), _lib.F32, planes, 64, 64, None, d["preds"].data_ptr(), None,
+                                                       d["maxv"].data_ptr(), d["pos"].data_ptr(), 0.9, d["conf"].data_ptr(), float(sigma), None,
+                                                       planes // 2, None, d["thresh"].data_ptr(), d["tm"].data_ptr(), tk, st()))
+
         def mk_sel(r):
             d = B(r)
             return lambda: chk(lib.udape_mask_select(d["maxv"].data_ptr(), planes, planes // 2, None, d["thresh"].data_ptr(),
@@ -265,6 +272,7 @@ def main():
         bench("decode f32", shape, hm32 + 16 * planes, mk_dec32, "decode")
         bench("decode f16", shape, hm16 + 16 * planes, mk_dec16, "decode")
         bench("decode+conf+rectify f32", shape, 2 * hm32 + 32 * planes, mk_decrect, "decode")
+        bench("decode+conf+kth-select f32", shape, hm32 + 41 * planes, mk_decsel, "decode")
         # valid arg-max coordinates for the analytic loss step
         mk_dec32(0)()
         for r_ in list(bundles):

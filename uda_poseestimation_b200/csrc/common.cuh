@@ -319,10 +319,24 @@ __device__ __forceinline__ bool last_block_done(uint32_t* ticket, unsigned total
     __syncthreads();
     return is_last;
 }
-// fixed-order sum of n floats by one CTA (any block size)
-__device__ __forceinline__ float cta_sum_array(const volatile float* v, int64_t n, float* red) {
+// Fixed-order sum of n floats by one CTA (any block size): thread t adds v[t], v[t + T], ... in that order, then the
+// block tree.  The values were written by OTHER CTAs of the grid (published by the ticket's fences), so they are read
+// from L2 (ld.global.cg) — sixteen loads of a thread in flight at a time: as a volatile loop the tail of the LAST CTA
+// was a chain of dependent L2 round trips (42 per thread at C5, ~8 us of the fused loss step's 59) while every other
+// SM had already drained.  Same order of additions as before, same bits.
+// (not inlined: its sixteen load registers must not raise the register count of the streaming path around it)
+static __device__ __noinline__ float cta_sum_array(const float* v, int64_t n, float* red) {
+    constexpr int UN = 16;
+    const int64_t stride = blockDim.x;
     float s = 0.0f;
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
+    for (int64_t i = threadIdx.x; i < n; i += UN * stride) {
+        float x[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) x[u] = (i + u * stride < n) ? __ldcg(v + i + u * stride) : 0.0f;
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
+            if (i + u * stride < n) s += x[u];
+    }
     return block_sum_rt(s, red);
 }
 

@@ -132,20 +132,41 @@ struct SelectArgs {
     float* thresh_out;          // optional
     uint8_t* tm_out;            // optional
     uint32_t* ticket;           // decode launch only: zeroed, self-resetting; NULL = no select
+    int cache_elems;            // decode_kernel only: floats of dynamic shared memory the launch reserved for the select's values
 };
 
-__device__ __forceinline__ void select_body(const float* __restrict__ act, int n, const SelectArgs& sa) {
+__device__ __forceinline__ void select_body(const float* __restrict__ act, int n, const SelectArgs& sa,
+                                            float* __restrict__ cache = nullptr, int cache_elems = 0) {
     __shared__ unsigned int hist[256];
     __shared__ unsigned int s_prefix, s_mask, s_k;
     const int nthreads = blockDim.x;
     if (threadIdx.x == 0) { s_prefix = 0u; s_mask = 0u; s_k = static_cast<unsigned>(sa.kth); }
+    // The values are fetched from L2 ONCE — four loads of a thread in flight at a time — into shared memory
+    // (`cache`, when the caller has room for n floats) and the four passes and the mask read them there.  Re-read
+    // from L2 in every pass they were 5 x n/T dependent round trips in the LAST CTA of the decode launch — on the
+    // teacher chain of the step — while the rest of the GPU had drained.
+    const bool cached = cache != nullptr && n <= cache_elems;
+    if (cached) {
+        constexpr int UN = 4;
+        for (int i0 = threadIdx.x; i0 < n; i0 += UN * nthreads) {
+            float x[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) x[u] = (i0 + u * nthreads < n) ? __ldcg(act + i0 + u * nthreads) : 0.0f;
+#pragma unroll
+            for (int u = 0; u < UN; ++u)
+                if (i0 + u * nthreads < n) cache[i0 + u * nthreads] = x[u];
+        }
+    }
+    auto value = [&](int i) { return cached ? cache[i] : __ldcg(act + i); };   // (a thread only ever reads what it cached)
     for (int pass = 3; pass >= 0; --pass) {
         const int shift = pass * 8;
         for (int i = threadIdx.x; i < 256; i += nthreads) hist[i] = 0u;
         __syncthreads();
         const unsigned prefix = s_prefix, mask = s_mask;
+        // (Same-address shared-memory atomics are not what this pass waits for: aggregating the lanes of a warp per
+        // bin with match.any made the select 70 % slower — 8.8 -> 14.8 us at C5 — profiles/r02ao.)
         for (int i = threadIdx.x; i < n; i += nthreads) {
-            const uint32_t key = order_key(__ldcg(act + i));
+            const uint32_t key = order_key(value(i));
             if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
         }
         __syncthreads();
@@ -182,7 +203,7 @@ __device__ __forceinline__ void select_body(const float* __restrict__ act, int n
     if (threadIdx.x == 0 && sa.thresh_out) *sa.thresh_out = thresh;
     if (sa.tm_out) {
         for (int i = threadIdx.x; i < n; i += nthreads) {
-            const float v = __ldcg(act + i);
+            const float v = value(i);
             const float a = sa.tm_in ? sa.tm_in[i] * v : v;
             sa.tm_out[i] = (a > thresh) ? 1 : 0;
         }
@@ -190,14 +211,17 @@ __device__ __forceinline__ void select_body(const float* __restrict__ act, int n
 }
 
 constexpr int kSelThreads = 1024;
+constexpr int kSelCache = 8192;     // floats of static shared memory of the stand-alone kernel (B*K of every config)
 
 __global__ void __launch_bounds__(kSelThreads)
 mask_select_kernel(const float* __restrict__ act, int n, SelectArgs sa) {
-    select_body(act, n, sa);
+    __shared__ float s_cache[kSelCache];
+    select_body(act, n, sa, s_cache, kSelCache);
 }
 
+// (8 / 6 CTAs per SM: the select / flag tails are separate functions whose registers must not cost the scan its occupancy)
 template <typename T, bool VEC>
-__global__ void __launch_bounds__(kDecThreads)
+__global__ void __launch_bounds__(kDecThreads, 8)
 decode_kernel(const T* __restrict__ hm, int hw, int w, int h, int32_t* __restrict__ idx_out,
               float* __restrict__ preds, T* __restrict__ maxvals, float* __restrict__ maxvals_f32,
               int64_t* __restrict__ position, float occlude_thresh, uint8_t* __restrict__ conf_table,
@@ -251,8 +275,10 @@ decode_kernel(const T* __restrict__ hm, int hw, int w, int h, int32_t* __restric
     }
     }
     // train_human.py:427-430 in the same launch: the CTA that finishes last selects the k-th activation
-    if (sel.ticket != nullptr && last_block_done(sel.ticket, gridDim.x))
-        select_body(maxvals_f32, static_cast<int>(gridDim.x), sel);
+    if (sel.ticket != nullptr && last_block_done(sel.ticket, gridDim.x)) {
+        extern __shared__ __align__(16) float sel_cache[];
+        select_body(maxvals_f32, static_cast<int>(gridDim.x), sel, sel.cache_elems > 0 ? sel_cache : nullptr, sel.cache_elems);
+    }
 }
 
 // ---- TMA-staged warp-per-plane arg-max (pipeline.cuh) ---------------------------------------
@@ -377,8 +403,10 @@ decode_tma_kernel(const T* __restrict__ hm, int64_t planes, int hw, int w, int h
             }
         });
     }
+    // (the ring is idle by now — every consumer warp has passed the ticket's barrier: it caches the select's values)
     if (sel.ticket != nullptr && last_block_done(sel.ticket, gridDim.x))
-        select_body(maxvals_f32, static_cast<int>(planes), sel);
+        select_body(maxvals_f32, static_cast<int>(planes), sel, reinterpret_cast<float*>(smem),
+                    static_cast<int>(static_cast<size_t>(stages) * stage_bytes / sizeof(float)));
 }
 
 // ---- PCK -------------------------------------------------------------------------------------
@@ -410,16 +438,22 @@ __device__ __forceinline__ uint8_t pck_flags(uint32_t io, float vo, uint32_t it,
 }
 
 // last CTA: per-joint integer sums of the per-plane flags (exact, order-independent)
-__device__ __forceinline__ void pck_reduce_flags(const volatile uint8_t* flags, int64_t planes, int joints,
+__device__ __forceinline__ void pck_reduce_flags(const uint8_t* flags, int64_t planes, int joints,
                                                  int32_t* __restrict__ hits, int32_t* __restrict__ valid) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
     const int64_t batch = planes / joints;
+    constexpr int UN = 4;   // flags of other CTAs, from L2, four loads of a lane in flight (not a chain of round trips)
     for (int k = warp; k < joints; k += warps) {
         int nh = 0, nv = 0;
-        for (int64_t b = lane; b < batch; b += 32) {
-            const uint8_t f = flags[b * joints + k];
-            nv += f & 1;
-            nh += (f >> 1) & 1;
+        for (int64_t b = lane; b < batch; b += 32 * UN) {
+            uint32_t f[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) f[u] = (b + 32 * u < batch) ? __ldcg(flags + (b + 32 * u) * joints + k) : 0u;
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                nv += f[u] & 1;
+                nh += (f[u] >> 1) & 1;
+            }
         }
         nh = __reduce_add_sync(0xffffffffu, nh);
         nv = __reduce_add_sync(0xffffffffu, nv);
@@ -428,7 +462,7 @@ __device__ __forceinline__ void pck_reduce_flags(const volatile uint8_t* flags, 
 }
 
 template <typename TO, typename TT, bool VEC_O, bool VEC_T>
-__global__ void __launch_bounds__(kDecThreads)
+__global__ void __launch_bounds__(kDecThreads, 6)
 pck_kernel(const TO* __restrict__ output, const TT* __restrict__ target, int joints, int hw, int w,
            double norm_x, double norm_y, double thr, float* __restrict__ pred_out,
            float* __restrict__ tgt_out, int32_t* __restrict__ hits, int32_t* __restrict__ valid,
@@ -508,16 +542,22 @@ static int launch_decode(const void* hm, int64_t planes, int64_t h, int64_t w, i
             static_cast<const T*>(hm), planes, hw, static_cast<int>(w), static_cast<int>(h), idx, preds,
             static_cast<T*>(maxvals), maxvals_f32, position, occlude_thresh, conf_table, gw,
             static_cast<T*>(rect), pg.group, pg.stages, sel);
-    } else if (vec)
-        decode_kernel<T, true><<<grid, kDecThreads, 0, st>>>(
+        return check_launch("udape_decode");
+    }
+    // the fused select caches its B*K values in dynamic shared memory (every CTA reserves it, the last one uses it)
+    SelectArgs sel2 = sel;
+    const size_t sel_smem = (sel.ticket != nullptr && planes * sizeof(float) <= 32 * 1024) ? ((planes * sizeof(float) + 15) & ~size_t(15)) : 0;
+    sel2.cache_elems = static_cast<int>(sel_smem / sizeof(float));
+    if (vec)
+        decode_kernel<T, true><<<grid, kDecThreads, sel_smem, st>>>(
             static_cast<const T*>(hm), hw, static_cast<int>(w), static_cast<int>(h), idx, preds,
             static_cast<T*>(maxvals), maxvals_f32, position, occlude_thresh, conf_table, gw,
-            static_cast<T*>(rect), sel);
+            static_cast<T*>(rect), sel2);
     else
-        decode_kernel<T, false><<<grid, kDecThreads, 0, st>>>(
+        decode_kernel<T, false><<<grid, kDecThreads, sel_smem, st>>>(
             static_cast<const T*>(hm), hw, static_cast<int>(w), static_cast<int>(h), idx, preds,
             static_cast<T*>(maxvals), maxvals_f32, position, occlude_thresh, conf_table, gw,
-            static_cast<T*>(rect), sel);
+            static_cast<T*>(rect), sel2);
     return check_launch("udape_decode");
 }
 
@@ -601,7 +641,7 @@ extern "C" int udape_decode_select(const void* hm, int dtype, int64_t planes, in
     // torch.kthvalue raises for k outside [1, n]
     UDAPE_REQUIRE(kth >= 1 && kth <= planes, UDAPE_ERR_ARG, "udape_decode_select: kth=%lld outside [1,%lld]",
                   (long long)kth, (long long)planes);
-    const SelectArgs sel = {static_cast<int>(kth), tea_mask_in, thresh_out, tea_mask_out, ticket};
+    const SelectArgs sel = {static_cast<int>(kth), tea_mask_in, thresh_out, tea_mask_out, ticket, 0};
     return decode_entry(hm, dtype, planes, h, w, idx, preds, maxvals, maxvals_f32, position, occlude_thresh, conf_table,
                         sigma, rectified, sel, stream);
 }
@@ -614,7 +654,7 @@ extern "C" int udape_mask_select(const float* activates, int64_t n, int64_t kth,
     // torch.kthvalue raises for k outside [1, n]
     UDAPE_REQUIRE(kth >= 1 && kth <= n, UDAPE_ERR_ARG, "udape_mask_select: kth=%lld outside [1,%lld]",
                   (long long)kth, (long long)n);
-    const SelectArgs sa = {static_cast<int>(kth), tea_mask_in, thresh_out, tea_mask_out, nullptr};
+    const SelectArgs sa = {static_cast<int>(kth), tea_mask_in, thresh_out, tea_mask_out, nullptr, 0};
     mask_select_kernel<<<1, kSelThreads, 0, as_stream(stream)>>>(activates, static_cast<int>(n), sa);
     return check_launch("udape_mask_select");
 }
