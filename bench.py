@@ -20,7 +20,7 @@ One JSON line is printed by rank 0:
               buffered against the previous step) + D2H of losses / PCK counts / predictions, in the timed region
   roofline    the dominant kernel (student_step at N=1; the peer-memory gather+EMA at N>1) timed with CUDA
               events on its own launches, vs MEASURED_PEAKS.json; `nvlink` at N>1: bytes pulled over NVLink / time
-  cpu_baseline / eager_cuda_baseline   the oracle port of the reference's path on this box's host cores / the
+  cpu_baseline / eager_cuda_baseline   the reference's own functions (oracle/_ref bytecode; the restated port when absent) on this box's host cores / the
               same functions as eager PyTorch on CUDA tensors of the same GPU (incl. its host syncs and copies)
   multi_gpu_parity (N>1)  N-rank results == single-process results on the rank-ordered sum (tools/dp_parity.py)
 `--impl reference` times the CPU path alone (the reference is pure Python on torch/numpy and /root/reference
@@ -547,7 +547,7 @@ def run_b200_arm(args, cfg, rank, world, local):
             main.close()
             torch.cuda.empty_cache()
             r = time_reference_path(cfg, 1234, steps=5, warmup=2, budget_s=60.0, device=str(dev), tail=kind != "ema")
-            eager = {k_: r[k_] for k_ in ("value", "unit", "ms_per_step", "steps", "sample")}
+            eager = {k_: r[k_] for k_ in ("value", "unit", "ms_per_step", "steps", "kind", "sample")}
         except Exception as exc:
             eager = {"error": f"{type(exc).__name__}: {exc}"}
     line = {
