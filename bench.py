@@ -23,8 +23,10 @@ One JSON line is printed by rank 0:
   cpu_baseline / eager_cuda_baseline   the reference's own functions (oracle/_ref bytecode; the restated port when absent) on this box's host cores / the
               same functions as eager PyTorch on CUDA tensors of the same GPU (incl. its host syncs and copies)
   multi_gpu_parity (N>1)  N-rank results == single-process results on the rank-ordered sum (tools/dp_parity.py)
-`--impl reference` times the CPU path alone (the reference is pure Python on torch/numpy and /root/reference
-does not exist on the GPU box, so the pinned oracle port is what runs).
+`--impl reference` times the CPU path alone: the reference is pure Python on torch/numpy; /root/reference does not
+exist on the GPU box, but the bytecode oracle/build_ref.py compiled from its hot-path files (oracle/_ref/, outputs
+only) does, so what runs is the reference's own functions and objects with the trainer's inline loops restated
+around them (oracle/reference_live.py; `cpu_baseline.kind` says which: "reference", or "port" without the bytecode).
 """
 from __future__ import annotations
 

@@ -24,7 +24,11 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 
 import uda_poseestimation_b200 as U  # noqa: E402
-from oracle import reference_port as R  # noqa: E402
+from oracle import reference_live, reference_port  # noqa: E402
+
+# the reference's own functions where they can be loaded (tree, or oracle/_ref bytecode on the GPU box), else the port
+R = reference_live if reference_live.available() else reference_port
+EAGER = ("the reference's own functions (oracle/reference_live.py, " + str(reference_live.source()) + ")") if R is reference_live else "oracle/reference_port.py"
 from uda_poseestimation_b200 import synthetic as S  # noqa: E402
 
 
@@ -185,7 +189,7 @@ def main():
     out = Path(args.out)
     out.parent.mkdir(parents=True, exist_ok=True)
     meta = dict(gpu=torch.cuda.get_device_name(0), torch=torch.__version__, config=args.config,
-                how="wall time between device synchronisations, median; eager = oracle/reference_port.py on CUDA tensors")
+                how=f"wall time between device synchronisations, median; eager = {EAGER} on CUDA tensors")
     out.with_suffix(".json").write_text(json.dumps(dict(meta=meta, rows=rows), indent=1))
     lines = [f"# Reference eager op sequences vs the package's operators on one {meta['gpu']} ({args.config} sizes)", "",
              meta["how"] + ".", "", "| operator | reference site | shape | eager PyTorch (us) | this package (us) | speed-up | note |", "|---|---|---|---:|---:|---:|---|"]
