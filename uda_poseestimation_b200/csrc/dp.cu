@@ -54,7 +54,9 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
 // 128-bit load of data another GPU owns.  A plain (weak) load that does not allocate in L1: the data was complete
 // before this kernel started (the flag wait is an earlier kernel of the same stream, and L1 is invalidated at
 // kernel boundaries; peer addresses bypass the local L2), so no stale line can serve it.  (ld.relaxed.sys moved
-// the same bytes ~20 % slower: 583 GB/s vs the 770 GB/s a peer copy reaches.)
+// the same bytes ~20 % slower.  What 128-bit loads can pull at all, two GPUs pulling from each other at once, is
+// 621 GB/s whatever the grid / loads in flight — copy engines 718, cp.async.bulk 652, stores to the peer 671:
+// tools/probe/peer_probe.py, profiles/r02au_peer_probe_n2.json.)
 __device__ __forceinline__ uint4 ld_peer(const void* p) {
     uint4 r;
     asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
