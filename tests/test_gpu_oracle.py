@@ -575,6 +575,42 @@ def test_fused_losses_partial_and_odd_shapes(dev):
         assert_close_scaled(g2, s1.grad, 1e-5, f"cons-only grad {shape}")
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(256, 21, 64, 64), (32, 16, 64, 64), (3, 5, 24, 24), (2, 2, 8, 8)])   # square: the reference's rectify raises on others (utils.py:89,101-105)
+def test_fused_losses_pair_route_equals_plane_per_cta(dev, dtype, shape):
+    """The analytic fused step has two grids: a plane per CTA, and — the default from 16 x SMs plane pairs up (C5) —
+    one supervised + one consistency plane per CTA with the first loads of both issued up front.  Same per-thread
+    order of additions, same block trees, same partial slots: losses and gradients agree bit for bit; and against
+    the oracle at the usual bars."""
+    import os
+    b, k, h, w = shape
+    y_s = S.heatmaps(b, k, seed=30, h=h, w=w).to(dtype)
+    y_t = S.heatmaps(b, k, seed=31, h=h, w=w).to(dtype)
+    tea_raw = S.heatmaps(b, k, seed=32, peak=(0.3, 1.2), h=h, w=w)
+    label = S.heatmaps(b, k, seed=33, noise=0.0, h=h, w=w)
+    weight = (torch.rand(b, k, 1, generator=torch.Generator().manual_seed(34)) > 0.1).float()
+    tea_mask, _, _ = R.consistency_mask(tea_raw, 0.5)
+    d = U.decode(tea_raw.to(dev), want_preds=True)
+    args = (y_s.to(dev), label.to(dev), weight.to(dev), y_t.to(dev), None, tea_mask.to(dev))
+    outs = {}
+    for flag in ("0", "1"):
+        outs[flag] = _with_env("UDAPE_LOSS_PAIR", flag, lambda: U.fused_losses(*args, lambda_c=0.7, grad_scale=65536.0,
+                                                                              tea_preds=d["preds"], sigma=2))
+    for a, e in zip(outs["1"], outs["0"]):
+        assert torch.equal(a, e)
+    default = U.fused_losses(*args, lambda_c=0.7, grad_scale=65536.0, tea_preds=d["preds"], sigma=2)
+    for a, e in zip(default, outs["0"]):
+        assert torch.equal(a, e)
+    if b * k <= 1024:     # (the oracle's rectify loops over every plane on the host)
+        o1, o2 = y_s.float().clone().requires_grad_(True), y_t.float().clone().requires_grad_(True)
+        l_all = R.joints_mse_loss(o1, label, weight) + 0.7 * R.cons_loss(o2, R.rectify(tea_raw, 2), tea_mask=tea_mask)
+        (l_all * 65536.0).backward()
+        rtol = 1e-5 if dtype == torch.float32 else 1e-2
+        assert_close_scaled(outs["1"][0][0], l_all.detach(), 1e-5, "pair route loss_all")
+        assert_close_scaled(outs["1"][1].float(), o1.grad, rtol, "pair route grad y_s")
+        assert_close_scaled(outs["1"][2].float(), o2.grad, rtol, "pair route grad y_t_stu")
+
+
 # ---------------------------------------------------------------- TMA-staged vs register-staged paths --------
 def _with_env(name, value, fn):
     import os

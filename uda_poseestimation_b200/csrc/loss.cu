@@ -10,6 +10,8 @@
 // Reductions are deterministic: every CTA reduces its plane with a fixed shuffle/smem
 // tree and writes one partial; the last CTA to finish (ticket counter) sums the
 // partials in a fixed order.  No floating-point atomics anywhere.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "gauss.cuh"
 
@@ -260,22 +262,32 @@ cons_bwd_kernel(const TS* __restrict__ stu, const TT* __restrict__ tea,
 // student heatmap is read (128-bit vectors of the student dtype) and its gradient written; the
 // teacher value is zero for almost every vector and a shared-memory table lookup inside the
 // (6*sigma+1)^2 window around the decoded arg-max.  Returns the thread's sum of (s - t)^2.
-template <typename TS, typename TT, int THREADS>
+// The loads of a batch (kLossUnroll vectors of a thread), apart from their use: the pair kernel below issues the first
+// batch of BOTH of its planes before anything else.
+template <typename TS, int THREADS>
+__device__ __forceinline__ void cons_batch_load(Pack<TS, 16 / static_cast<int>(sizeof(TS))> (&gs_)[kLossUnroll],
+                                                const TS* __restrict__ s, int base, int ngrp) {
+    constexpr int G = 16 / static_cast<int>(sizeof(TS));
+#pragma unroll
+    for (int u = 0; u < kLossUnroll; ++u) {
+        const int gi = base + u * THREADS + threadIdx.x;
+        if (gi < ngrp) gs_[u].load(s + G * gi);
+    }
+}
+
+// PRE: `gs_` already holds the first batch (cons_batch_load(gs_, s, 0, ngrp) was issued by the caller).
+template <typename TS, typename TT, int THREADS, bool PRE = false>
 __device__ __forceinline__ float cons_plane_analytic(const TS* __restrict__ s, TS* __restrict__ gout, int hw, int w,
                                                      const RectGeom& geom, const GaussWindow& gw,
-                                                     const float* __restrict__ tab, float coef) {
+                                                     const float* __restrict__ tab, float coef,
+                                                     Pack<TS, 16 / static_cast<int>(sizeof(TS))> (&gs_)[kLossUnroll]) {
     constexpr int G = 16 / static_cast<int>(sizeof(TS));
     const int ngrp = hw / G;
     int y = (threadIdx.x * G) / w, x = threadIdx.x * G - y * w;  // one division, then incremental
     const int step_y = (THREADS * G) / w, step_x = THREADS * G - step_y * w;
     float acc = 0.0f;
     for (int base = 0; base < ngrp; base += kLossUnroll * THREADS) {
-        Pack<TS, G> gs_[kLossUnroll];
-#pragma unroll
-        for (int u = 0; u < kLossUnroll; ++u) {
-            const int gi = base + u * THREADS + threadIdx.x;
-            if (gi < ngrp) gs_[u].load(s + G * gi);
-        }
+        if (!PRE || base > 0) cons_batch_load<TS, THREADS>(gs_, s, base, ngrp);
 #pragma unroll
         for (int u = 0; u < kLossUnroll; ++u) {
             const int gi = base + u * THREADS + threadIdx.x;
@@ -385,7 +397,8 @@ loss_step_kernel(const TS* __restrict__ y_s, const TT* __restrict__ label, const
     }
     float acc = 0.0f;
     if (VEC && analytic) {
-        acc = cons_plane_analytic<TS, TT, kStepThreads>(s, gout, hw, a.w, geom, a.gw, tab, coef);
+        Pack<TS, 16 / static_cast<int>(sizeof(TS))> gs_[kLossUnroll];
+        acc = cons_plane_analytic<TS, TT, kStepThreads>(s, gout, hw, a.w, geom, a.gw, tab, coef, gs_);
     } else if (VEC) {
         constexpr int G = PairGroup<TS, TT>::G;
         const int ngrp = hw / G;
@@ -441,6 +454,100 @@ loss_step_kernel(const TS* __restrict__ y_s, const TT* __restrict__ label, const
             const float loss_s = a.planes_s ? ss / static_cast<float>(a.planes_s) : 0.0f;
             const float loss_c = a.planes_t ? sc / static_cast<float>(a.joints) /
                                      (static_cast<float>(a.planes_t / a.joints) * static_cast<float>(hw)) : 0.0f;
+            a.losses[0] = loss_s + a.lambda_c * loss_c;   // train_human.py:434
+            a.losses[1] = loss_s;
+            a.losses[2] = loss_c;
+        }
+    }
+}
+
+// ---- fused loss step, one supervised + one consistency plane per CTA ---------------------------------------------
+// The analytic route of the step (no teacher map) at equal plane counts: CTA i owns supervised plane i AND consistency
+// plane i.  The first batch of loads of both planes is issued before the window table is built and before any
+// per-plane scalar is looked at (160 bytes per thread in flight instead of 64 / 96), a CTA pays one table, one
+// launch slot and one ticket for 40 KB of traffic instead of one each for 16 KB and 32 KB, and the grid is half as
+// long.  Per-thread order of additions, block trees, partial slots and the last CTA's sums are those of
+// loss_step_kernel: the results are bit-identical.
+template <typename TS, typename TT>
+__global__ void __launch_bounds__(kStepThreads)
+loss_step_pair_kernel(const TS* __restrict__ y_s, const TT* __restrict__ label, const TS* __restrict__ y_t,
+                      TS* __restrict__ grad_s, TS* __restrict__ grad_t, const LossStepArgs a) {
+    __shared__ float red[32];
+    __shared__ float s_tab[kWinTabN * kWinTabN];
+    constexpr int T = kStepThreads, U = kLossUnroll;
+    constexpr int GC = 16 / static_cast<int>(sizeof(TS));
+    constexpr int GS = PairGroup<TS, TT>::G;
+    const int hw = a.hw, ngc = hw / GC, ngs = hw / GS;
+    const int64_t plane = blockIdx.x;
+    const TS* sc = y_t + plane * hw;
+    const TS* ss = y_s + plane * hw;
+    const TT* tl = label + plane * hw;
+    TS* gc = grad_t ? grad_t + plane * hw : nullptr;
+    TS* gs = grad_s ? grad_s + plane * hw : nullptr;
+    Pack<TS, GC> c_[U];
+    Pack<TS, GS> s_[U];
+    Pack<TT, GS> t_[U];
+    cons_batch_load<TS, T>(c_, sc, 0, ngc);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int gi = u * T + threadIdx.x;
+        if (gi < ngs) {
+            s_[u].load(ss + GS * gi);
+            t_[u].load(tl + GS * gi);
+        }
+    }
+    const float* tab = build_window_table(s_tab, a.gw);
+    const float g = a.grad_scale_dev ? __ldg(a.grad_scale_dev) : a.grad_scale;
+    const float wgt = load_plane_scalar(a.weight, a.w_dtype, plane);
+    const float m = load_plane_scalar(a.tea_mask, a.mask_dtype, plane);
+    const float coef_s = g * wgt / (static_cast<float>(a.planes_s) * static_cast<float>(hw));
+    const float coef_c = 2.0f * (g * a.lambda_c) * m * m / (static_cast<float>(a.joints) *
+                         (static_cast<float>(a.planes_t / a.joints) * static_cast<float>(hw)));
+    const RectGeom geom = rect_geometry(a.tea_preds[2 * plane], a.tea_preds[2 * plane + 1], a.h, a.w, a.gw);
+    __syncthreads();   // the table
+    float acc_c = cons_plane_analytic<TS, TT, T, true>(sc, gc, hw, a.w, geom, a.gw, tab, coef_c, c_);
+    float acc_s = 0.0f;
+    for (int base = 0; base < ngs; base += U * T) {
+        if (base > 0) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int gi = base + u * T + threadIdx.x;
+                if (gi < ngs) {
+                    s_[u].load(ss + GS * gi);
+                    t_[u].load(tl + GS * gi);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int gi = base + u * T + threadIdx.x;
+            if (gi < ngs) {
+                float fs[GS], ft[GS];
+                s_[u].get(fs);
+                t_[u].get(ft);
+                float tsum = 0.0f;
+#pragma unroll
+                for (int e = 0; e < GS; ++e) {
+                    const float d = fs[e] - ft[e];
+                    tsum = fmaf(d, d, tsum);
+                    fs[e] = coef_s * d;
+                }
+                acc_s += tsum;
+                if (gs) Pack<TS, GS>::store(gs + GS * gi, fs);
+            }
+        }
+    }
+    acc_s = block_sum<T>(acc_s, red);
+    if (threadIdx.x == 0) a.partial[plane] = (0.5f * wgt / static_cast<float>(hw)) * acc_s;
+    acc_c = block_sum<T>(acc_c, red);
+    if (threadIdx.x == 0) a.partial[a.planes_s + plane] = (m * m) * acc_c;
+    if (last_block_done(a.ticket, gridDim.x)) {
+        const float sum_s = cta_sum_array(a.partial, a.planes_s, red);
+        const float sum_c = cta_sum_array(a.partial + a.planes_s, a.planes_t, red);
+        if (threadIdx.x == 0) {
+            const float loss_s = sum_s / static_cast<float>(a.planes_s);
+            const float loss_c = sum_c / static_cast<float>(a.joints) /
+                                 (static_cast<float>(a.planes_t / a.joints) * static_cast<float>(hw));
             a.losses[0] = loss_s + a.lambda_c * loss_c;   // train_human.py:434
             a.losses[1] = loss_s;
             a.losses[2] = loss_c;
@@ -616,6 +723,17 @@ extern "C" int udape_loss_step(const void* y_s, const void* label, const void* w
     const unsigned grid = static_cast<unsigned>(planes_s + planes_t);
     const bool vec = (hw % 8) == 0 && aligned16(y_s) && aligned16(label) && aligned16(y_t_stu) && aligned16(tea) &&
                      aligned16(grad_y_s) && aligned16(grad_y_t_stu);
+    // one supervised + one consistency plane per CTA: the analytic route at equal plane counts (what the step runs)
+    // — for batches that fill the GPU: 56.0 -> 53.9 us at C5 (5376 pairs, 72 -> 75 % of the HBM roofline), but fewer and
+    // longer CTAs are slower when the grid is a wave or two (C4, 1152 pairs: 16.4 -> 17.6 us; C2: 10.2 -> 10.7 us)
+    bool pair = !tea && planes_s == planes_t && planes_s > 0;
+    if (const char* e = std::getenv("UDAPE_LOSS_PAIR")) {   // tests / tuning: force the route
+        pair = pair && e[0] == '1';
+    } else if (pair) {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+        pair = planes_s >= 16ll * sms;
+    }
     UDAPE_DISPATCH_FLOAT(stu_dtype, TS, UDAPE_DISPATCH_FLOAT(tgt_dtype, TT, {
         const TS* ys = static_cast<const TS*>(y_s);
         const TS* yt = static_cast<const TS*>(y_t_stu);
@@ -623,7 +741,8 @@ extern "C" int udape_loss_step(const void* y_s, const void* label, const void* w
         const TT* te = static_cast<const TT*>(tea);
         TS* g1 = static_cast<TS*>(grad_y_s);
         TS* g2 = static_cast<TS*>(grad_y_t_stu);
-        if (vec) loss_step_kernel<TS, TT, true><<<grid, kStepThreads, 0, st>>>(ys, lb, yt, te, g1, g2, a);
+        if (vec && pair) loss_step_pair_kernel<TS, TT><<<static_cast<unsigned>(planes_s), kStepThreads, 0, st>>>(ys, lb, yt, g1, g2, a);
+        else if (vec) loss_step_kernel<TS, TT, true><<<grid, kStepThreads, 0, st>>>(ys, lb, yt, te, g1, g2, a);
         else loss_step_kernel<TS, TT, false><<<grid, kStepThreads, 0, st>>>(ys, lb, yt, te, g1, g2, a);
     }));
     return check_launch("udape_loss_step");
