@@ -141,11 +141,13 @@ __device__ __forceinline__ void select_body(const float* __restrict__ act, int n
     __shared__ unsigned int s_prefix, s_mask, s_k;
     const int nthreads = blockDim.x;
     if (threadIdx.x == 0) { s_prefix = 0u; s_mask = 0u; s_k = static_cast<unsigned>(sa.kth); }
-    // The values are fetched from L2 ONCE — four loads of a thread in flight at a time — into shared memory
-    // (`cache`, when the caller has room for n floats) and the four passes and the mask read them there.  Re-read
-    // from L2 in every pass they were 5 x n/T dependent round trips in the LAST CTA of the decode launch — on the
-    // teacher chain of the step — while the rest of the GPU had drained.
+    // The values are fetched from L2 ONCE — four loads of a thread in flight at a time — and kept in shared memory
+    // (`cache`, when the caller has room for n words) as ORDERED KEYS; the four passes and the mask read them there.
+    // Re-read from L2 in every pass they were 5 x n/T dependent round trips in the LAST CTA of the decode launch —
+    // on the teacher chain of the step — while the rest of the GPU had drained.  (key_value(order_key(v)) is v but
+    // for -0.0 -> +0.0 and the NaN payload: neither changes `a > thresh`.)
     const bool cached = cache != nullptr && n <= cache_elems;
+    uint32_t* __restrict__ keys = reinterpret_cast<uint32_t*>(cache);
     if (cached) {
         constexpr int UN = 4;
         for (int i0 = threadIdx.x; i0 < n; i0 += UN * nthreads) {
@@ -154,10 +156,9 @@ __device__ __forceinline__ void select_body(const float* __restrict__ act, int n
             for (int u = 0; u < UN; ++u) x[u] = (i0 + u * nthreads < n) ? __ldcg(act + i0 + u * nthreads) : 0.0f;
 #pragma unroll
             for (int u = 0; u < UN; ++u)
-                if (i0 + u * nthreads < n) cache[i0 + u * nthreads] = x[u];
+                if (i0 + u * nthreads < n) keys[i0 + u * nthreads] = order_key(x[u]);   // (a thread only ever reads what it cached)
         }
     }
-    auto value = [&](int i) { return cached ? cache[i] : __ldcg(act + i); };   // (a thread only ever reads what it cached)
     for (int pass = 3; pass >= 0; --pass) {
         const int shift = pass * 8;
         for (int i = threadIdx.x; i < 256; i += nthreads) hist[i] = 0u;
@@ -165,9 +166,17 @@ __device__ __forceinline__ void select_body(const float* __restrict__ act, int n
         const unsigned prefix = s_prefix, mask = s_mask;
         // (Same-address shared-memory atomics are not what this pass waits for: aggregating the lanes of a warp per
         // bin with match.any made the select 70 % slower — 8.8 -> 14.8 us at C5 — profiles/r02ao.)
-        for (int i = threadIdx.x; i < n; i += nthreads) {
-            const uint32_t key = order_key(value(i));
-            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        if (cached) {
+#pragma unroll 2
+            for (int i = threadIdx.x; i < n; i += nthreads) {
+                const uint32_t key = keys[i];
+                if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+            }
+        } else {
+            for (int i = threadIdx.x; i < n; i += nthreads) {
+                const uint32_t key = order_key(__ldcg(act + i));
+                if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+            }
         }
         __syncthreads();
         if (threadIdx.x < 32) {
@@ -202,8 +211,9 @@ __device__ __forceinline__ void select_body(const float* __restrict__ act, int n
     const float thresh = key_value(s_prefix);
     if (threadIdx.x == 0 && sa.thresh_out) *sa.thresh_out = thresh;
     if (sa.tm_out) {
+#pragma unroll 2
         for (int i = threadIdx.x; i < n; i += nthreads) {
-            const float v = value(i);
+            const float v = cached ? key_value(keys[i]) : __ldcg(act + i);
             const float a = sa.tm_in ? sa.tm_in[i] * v : v;
             sa.tm_out[i] = (a > thresh) ? 1 : 0;
         }
