@@ -347,8 +347,10 @@ class Variant:
         hook = None
         if world > 1:
             hook = None if kind == "peer" else D.allreduce_counts   # the peer tail exchanges the counts itself
+        # (one teacher view + the fused loss step: re-warp, decode, conf_table and the k-th value mask of the teacher chain
+        # are ONE launch and the re-warped map is never written)
         self.step = HotPathStep(teacher, student, sigma=cfg["sigma"], fused=not args.unfused, tail=tail, counts_hook=hook,
-                                loss_scale=LOSS_SCALE)
+                                loss_scale=LOSS_SCALE, fuse_teacher_decode=not args.unfused)
         self.step.alpha_feed = feed
         self.graphs = []
         self.inputs = inputs
@@ -478,7 +480,8 @@ def run_b200_arm(args, cfg, rank, world, local):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- the dominant kernel on its own launches + NVLink figures --------------------------------
-    abytes = step_algorithmic_bytes(inputs[0], main.step.n_params, fused=main.step.fused, tail=main.tail)
+    abytes = step_algorithmic_bytes(inputs[0], main.step.n_params, fused=main.step.fused, tail=main.tail,
+                                    fuse_teacher_decode=main.step.fuse_teacher_decode)
     probe = probe_tail(main, world, dev, reps=max(5, min(args.steps, 20)))
 
     # ---- the other tails, same inputs ------------------------------------------------------------
@@ -490,7 +493,8 @@ def run_b200_arm(args, cfg, rank, world, local):
         try:
             v = build(alt)
             ms, _ = timed_loop(v, min(args.steps, 50), max(3, min(args.warmup, 5)), world, dev)
-            ab = step_algorithmic_bytes(inputs[0], v.step.n_params, fused=v.step.fused, tail=v.tail)
+            ab = step_algorithmic_bytes(inputs[0], v.step.n_params, fused=v.step.fused, tail=v.tail,
+                                            fuse_teacher_decode=v.step.fuse_teacher_decode)
             variants[alt] = {"ms_per_step": ms, "value": world * b / (ms / 1e3), "step_algorithmic_bytes": ab["total"]}
             if alt == "nccl":
                 variants[alt]["grad_allreduce"] = time_nccl_allreduce(v, world, dev)

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define UDAPE_VERSION 301 /* major*10000 + minor*100 + patch */
+#define UDAPE_VERSION 302 /* major*10000 + minor*100 + patch */
 
 #if defined(__GNUC__)
 #define UDAPE_API __attribute__((visibility("default")))
@@ -453,6 +453,21 @@ UDAPE_API int udape_rewarp_fwd(const void* const* in, const float* const* theta,
 /* uint16 elements per sample of the inverse plan for H x W planes of elem_bytes-sized elements;
  * 0 if the plan route does not apply (planes above 4096 pixels, rows that are not 16-byte multiples). */
 UDAPE_API int64_t udape_rewarp_plan_elems(int64_t H, int64_t W, int elem_bytes);
+/* udape_rewarp_fwd (one view, no paste) + udape_decode_select in ONE launch, for a re-warped map that is only ever
+ * decoded — the teacher chain of the step: train_human.py:359-372 (three tF.affine per sample) feeding :376-383
+ * (conf / position / conf_table) and :427-430 (activates, k-th value mask).  The re-warped map is never written:
+ * every plane is arg-maxed where it is gathered (same ordered keys, first output pixel wins ties, pixels that left
+ * the image count as 0), so the outputs equal udape_decode_select(udape_rewarp_fwd(in)) bit for bit while the stage
+ * moves B*C*H*W*E bytes instead of 3x that.  Outputs as udape_decode (maxvals_f32 required; idx / preds / position /
+ * conf_table optional).  kth = 0: no select (ticket may be NULL); kth in [1, B*C]: as udape_decode_select.
+ * Shapes: planes of exactly 4096 pixels, rows a power-of-two number of 16-byte chunks, C <= 64, `in` 16-byte aligned;
+ * otherwise UDAPE_ERR_SHAPE / UDAPE_ERR_ALIGN — call the two entries. */
+UDAPE_API int udape_rewarp_decode_select(const void* in, const float* theta, int stages, int half_mask, int grid_dtype,
+                               int64_t B, int64_t C, int64_t H, int64_t W, int dtype, int32_t* idx, float* preds,
+                               float* maxvals_f32, int64_t* position, float occlude_thresh, uint8_t* conf_table,
+                               int64_t kth, const float* tea_mask_in, float* thresh_out, uint8_t* tea_mask_out,
+                               uint32_t* ticket, void* stream);
+
 /* Gradient of the single-view re-warp w.r.t. its input: grad_in[s] = sum of grad_out[p] over
  * {p : source(p) = s}, float32 accumulation in ascending p, one rounding to `dtype` (deterministic:
  * integer counting / max-key rounds decide the order, no float atomics).  H*W <= 25600.

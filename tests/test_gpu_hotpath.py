@@ -68,7 +68,8 @@ def _oracle_step(host, a1, a2, teacher, student, scale=65536.0):
 
 
 def _check(out, ref):
-    assert torch.equal(out["y_t_tea_recon"].cpu(), ref["y_t_tea"])              # gathers: bit-exact
+    if out["y_t_tea_recon"] is not None:      # (None with fuse_teacher_decode: the map is decoded where it is gathered)
+        assert torch.equal(out["y_t_tea_recon"].cpu(), ref["y_t_tea"])          # gathers: bit-exact
     assert torch.equal(out["y_t_stu_recon"].cpu(), ref["y_t_stu_recon"].to(out["y_t_stu_recon"].dtype))
     assert_close_scaled(out["t_s2t"], ref["t_s2t"], 1e-5, "s2t")
     assert_close_scaled(out["t_t2s"], ref["t_t2s"], 1e-5, "t2s")
@@ -244,6 +245,46 @@ def test_step_at_c2_size_with_k2_views_graph(dev):
         _check(out, ref)
         for p, e in zip(teacher.parameters(), t_cpu):
             assert torch.equal(p.detach().cpu(), e)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_step_with_the_teacher_chain_in_one_launch(dev, graph):
+    """fuse_teacher_decode: teacher re-warp + decode + conf_table + k-th value mask as ONE launch (the re-warped map is
+    never written) at the BASELINE config's size with one teacher view — against the oracle, and bit for bit against the
+    step that materialises the map; eagerly (with the occlusion stage, which only needs conf_table / position) and as a
+    replayed graph."""
+    host, inp = _c2_inputs(dev, seed=47, k_views=1)
+    if not graph:
+        inp.x_t_stu, inp.aug_param_stu = host["x_t_stu"].to(dev), host["aug_stu"]
+    shapes = [(64, 3, 7, 7), (64,), (17,)]
+    outs = {}
+    for fuse in (False, True):
+        s_cpu, t_cpu = S.parameter_list(shapes, 1), S.parameter_list(shapes, 2)
+        student, teacher = Bag(s_cpu).to(dev), Bag(t_cpu).to(dev)
+        step = HotPathStep(teacher, student, sigma=2, rng=np.random.RandomState(78), fuse_teacher_decode=fuse)
+        R.ema_init(t_cpu, s_cpu)
+        if graph:
+            step.capture(inp, include_ema=True, warmup=1)
+            R.ema_step(t_cpu, s_cpu, 0.999)
+            out = step.replay()
+        else:
+            out = step.run(inp)
+        torch.cuda.synchronize()
+        assert (out["y_t_tea_recon"] is None) == fuse
+        outs[(fuse, 'kernels')] = step.kernels_per_step
+        outs[fuse] = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in out.items()}
+        ref = _oracle_c2(host, 0.3, 0.8, t_cpu, s_cpu, occlusion_seed=None if graph else 78)
+        _check(out, ref)
+        if not graph:
+            assert torch.equal(out["x_t_stu"].cpu(), ref["x_t_stu"])
+    for k in ("conf_table", "position", "tea_mask", "mask_thresh", "tea_preds", "loss_all", "loss_s", "loss_c", "grad_y_s",
+              "grad_y_t_stu", "pck_counts"):
+        assert torch.equal(outs[True][k], outs[False][k]), k
+    assert outs[(False, 'kernels')] - outs[(True, 'kernels')] == 1
+    by_two = step_algorithmic_bytes(inp, n_params=1000, fused=True)
+    by_one = step_algorithmic_bytes(inp, n_params=1000, fused=True, fuse_teacher_decode=True)
+    hm = inp.teacher_views[0].numel() * 4
+    assert by_two["total"] - by_one["total"] == 2 * hm      # the map's write and its re-read
 
 
 def test_ticket_words_are_zero_between_launches(dev):

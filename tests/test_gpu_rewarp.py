@@ -372,3 +372,52 @@ def test_rewarp_backward_degenerate_maps(dev, dt, c):
         assert torch.equal(got_plan.cpu().float(), want.float())
     assert not torch.signbit(got_plan[2, 0, 0, :8]).any()
     del half
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("b,c", [(32, 16), (3, 21), (150, 5), (1, 64)])
+def test_gather_decode_equals_gather_then_decode(dev, dt, b, c):
+    """udape_rewarp_decode_select: the planes are arg-maxed where they are gathered, the re-warped map is never written.
+    Every output of decode / decode_select on the materialised map — idx, preds, maxvals, position, conf_table, the k-th
+    value threshold and tea_mask — bit for bit, on ordinary augmentations and on planes built to tie (constant planes,
+    duplicated maxima, all-negative planes whose maximum is an out-of-image zero, NaN)."""
+    from uda_poseestimation_b200 import keypoint_detection as KD
+    y = S.heatmaps(b, c, seed=600 + b, peak=(0.3, 1.2))
+    y[0, 0] = 0.25                                   # constant: ties everywhere -> first output pixel with a source
+    y[0, 1 % c] = -1.0                               # all negative: the zeros of pixels that left the image win
+    if c > 2:
+        y[0, 2, 10, 11] = y[0, 2, 40, 41] = 3.0      # duplicated maximum
+    if c > 3:
+        y[0, 3, 5, 5] = float("nan")
+    y = y.to(dt).to(dev)
+    aug = S.aug_params(b, seed=610 + c)
+    half = dt != torch.float32
+    theta, half_mask, _ = RW.stage_table(RW.recon_stages(aug, 4.0, b), 64, 64, dt if half else torch.float32, dt if half else None)
+    theta = theta.to(dev)
+    grid = dt if half else None
+    assert RW.gather_decode_supported(y)
+    mid = RW.gather(y, theta, half_mask, grid)
+    kth = max(1, (b * c) // 2)
+    tm = (torch.rand(b, c, generator=torch.Generator().manual_seed(5)) > 0.2).float().to(dev)
+    want = KD.decode(mid, want_idx=True, want_preds=True, want_maxvals_f32=True, want_position=True, occlude_thresh=0.9,
+                     select_kth=kth, select_tea_mask=tm)
+    got = RW.gather_decode(y, theta, half_mask, grid, want_idx=True, want_preds=True, want_position=True, occlude_thresh=0.9,
+                           select_kth=kth, select_tea_mask=tm)
+    for k in ("idx", "preds", "position", "conf_table", "tea_mask"):
+        assert torch.equal(got[k], want[k]), k
+    for k in ("maxvals_f32", "mask_thresh"):         # NaN-aware equality of the bits
+        assert torch.equal(got[k].view(torch.int32), want[k].view(torch.int32)), k
+    # no select, nothing optional
+    lean = RW.gather_decode(y, theta, half_mask, grid, want_preds=False)
+    assert set(lean) == {"maxvals_f32"} and torch.equal(lean["maxvals_f32"].view(torch.int32), want["maxvals_f32"].view(torch.int32))
+
+
+def test_gather_decode_rejects_what_it_has_no_launch_for(dev):
+    y = torch.zeros(2, 3, 32, 32, device=dev)
+    theta = torch.zeros(2, 3, 6, device=dev)
+    assert not RW.gather_decode_supported(y)
+    with pytest.raises(ValueError, match="no fused launch"):
+        RW.gather_decode(y, theta)
+    import uda_poseestimation_b200 as U_
+    tt = U_.teacher_targets_rewarped(y, theta, 2, 0.5, occlude_thresh=0.9)       # falls back to two launches
+    assert tt["y_t_tea_recon"] is None and tt["tea_mask"].shape == (2, 3)

@@ -334,6 +334,14 @@ def main():
             return lambda: chk(lib.udape_rewarp_fwd(ia, ta, 1, 3, 0, _lib.F16, None, 0, None, b, k, 64, 64, _lib.F32,
                                                     d["rect"].data_ptr(), None, st()))
 
+        def mk_rwdec(r):   # the step's teacher chain in one launch: re-warp + decode + conf_table + k-th value mask, no map written
+            d = B(r)
+            tk = _lib.ticket(dev)
+            return lambda: chk(lib.udape_rewarp_decode_select(d["tea"].data_ptr(), t32.data_ptr(), 3, 0, _lib.F16, b, k, 64, 64, _lib.F32,
+                                                              None, d["preds"].data_ptr(), d["maxv"].data_ptr(), d["pos"].data_ptr(), 0.9,
+                                                              d["conf"].data_ptr(), planes // 2, None, d["thresh"].data_ptr(),
+                                                              d["tm"].data_ptr(), tk, st()))
+
         def mk_rw16(r):
             d = B(r)
             ia, ta = in_arr(d["stu16"]), in_arr(t16)
@@ -359,6 +367,7 @@ def main():
                                                     d["grad16"].data_ptr(), plan16.data_ptr(), st()))
 
         bench("rewarp_fwd f32 (teacher)", shape, 2 * hm32, mk_rw32, "rewarp")
+        bench("rewarp f32 + decode + kth-select (1 launch)", shape, hm32 + 41 * planes, mk_rwdec, "rewarp")
         bench("rewarp_fwd f16 (student)", shape, 2 * hm16, mk_rw16, "rewarp")
         bench("rewarp_fwd f16 + inv. plan", shape, 2 * hm16 + plan16.numel() * 2, mk_rw16p, "rewarp")
         bench("rewarp_bwd f16 (no plan)", shape, 2 * hm16, mk_rwb, "rewarp")

@@ -15,7 +15,7 @@ Reference name → module here
     lib/models/loss.py                         : JointsMSELoss, ConsLoss
     lib/models/ema.py                          : ModelEMA
     lib/datasets/util.py                       : generate_target, draw_labelmap_ori
-    train_human.py:376-383,427-430 (inline)    : confidence_mask, consistency_mask, teacher_targets
+    train_human.py:376-383,427-430 (inline)    : confidence_mask, consistency_mask, teacher_targets, teacher_targets_rewarped
     train_human.py:359-372,417-423 (inline)    : teacher_recon, student_recon (three tF.affine calls per
                                                  sample → one gather launch, with backward)
     train_human.py:385-412 (inline)            : occlude_keypoints;  affine_nearest = batched tF.affine
@@ -35,13 +35,13 @@ from .heatmap import (draw_labelmap_batched, draw_labelmap_ori, draw_labelmaps_m
 from .keypoint_detection import (accuracy, accuracy_from_counts, calc_dists, decode, dist_acc, get_max_preds,
                                  get_max_preds_torch, pck_counts)
 from .loss import ConsLoss, JointsMSELoss, cons_loss, fused_losses, joints_mse_loss
-from .mask import confidence_mask, consistency_mask, teacher_targets
+from .mask import confidence_mask, consistency_mask, teacher_targets, teacher_targets_rewarped
 from .dp import PeerGroup, ShardedStudentStep
 from .optim import SGD, Adam, GradScaler
 from .stylize import StyleTransfer
 from .rewarp import affine_nearest, occlude_keypoints, student_recon, teacher_recon
 
-__version__ = "0.3.1"
+__version__ = "0.3.2"
 
 __all__ = [
     "UdapeError", "library_path", "load_library", "check_tickets",
@@ -51,7 +51,7 @@ __all__ = [
     "JointsMSELoss", "ConsLoss", "joints_mse_loss", "cons_loss", "fused_losses",
     "generate_target", "generate_target_batched", "draw_labelmap_ori", "draw_labelmap_batched", "rectify",
     "generate_targets_multi", "draw_labelmaps_multi",
-    "confidence_mask", "consistency_mask", "teacher_targets",
+    "confidence_mask", "consistency_mask", "teacher_targets", "teacher_targets_rewarped",
     "OldWeightEMA", "ModelEMA", "MultiTensorPlan",
     "teacher_recon", "student_recon", "occlude_keypoints", "affine_nearest",
     "Adam", "SGD", "GradScaler", "StyleTransfer",

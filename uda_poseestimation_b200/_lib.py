@@ -139,6 +139,9 @@ PROTOTYPES = {
     "udape_rewarp_plan_elems": (c_int64, [c_int64, c_int64, c_int]),
     "udape_rewarp_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int,
                                  c_void_p, c_void_p, c_void_p]),
+    "udape_rewarp_decode_select": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int,
+                                           c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int64, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lock = threading.Lock()

@@ -46,6 +46,7 @@
 
 #include "common.cuh"
 #include "pipeline.cuh"
+#include "select.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -1472,9 +1473,35 @@ constexpr int kW2Threads = 512;
 constexpr int kW2Pixels = 4096;
 
 // dynamic smem: RING stages x G planes x (H*W*sizeof(T) + 16 zero bytes) | uint16 map[4096]
-template <typename T, int G, int RING>
+// DECODE: the gathered planes are not stored but arg-maxed where they are gathered (udape_rewarp_decode_select: the
+// teacher chain of the step only ever decodes its re-warped map, train_human.py:359-383, :427-430).  Every thread
+// keeps, per plane of an item, the best (ordered key, ~output pixel) of its eight pixels; warps leave their best in
+// a [planes][16] table and after the last item thread c folds row c and writes plane c's decode outputs; the CTA
+// that takes the last ticket runs the k-th value select over the batch.  Same keys, same tie rule (first output
+// pixel) and same zero for pixels that left the image as decoding the stored map: bit-identical outputs.
+struct RewarpDecodeOut {
+    int32_t* idx;            // [B*C] or NULL
+    float* preds;            // [B*C, 2] or NULL
+    float* maxvals_f32;      // [B*C]
+    int64_t* position;       // [B*C, 2] or NULL
+    uint8_t* conf_table;     // [B*C] or NULL
+    float occlude_thresh;
+    SelectArgs sel;          // ticket == NULL: no select
+};
+constexpr int kW2DecodeMaxC = 64;   // planes per sample of the decode route: its [C][16] table of warp maxima reuses the map's 8 KB
+
+template <typename T> __device__ __forceinline__ float word_value(uint32_t w32, int e);
+template <> __device__ __forceinline__ float word_value<float>(uint32_t w32, int) { return __uint_as_float(w32); }
+template <> __device__ __forceinline__ float word_value<__half>(uint32_t w32, int e) {
+    return __half2float(__ushort_as_half(static_cast<unsigned short>(e ? (w32 >> 16) : (w32 & 0xffffu))));
+}
+template <> __device__ __forceinline__ float word_value<__nv_bfloat16>(uint32_t w32, int e) {
+    return __uint_as_float(e ? (w32 & 0xffff0000u) : (w32 << 16));
+}
+
+template <typename T, int G, int RING, bool DECODE = false>
 __global__ void __launch_bounds__(kW2Threads, 2)
-rewarp_wide2_kernel(const RewarpArgs a, T* __restrict__ out) {
+rewarp_wide2_kernel(const RewarpArgs a, T* __restrict__ out, const RewarpDecodeOut dec = RewarpDecodeOut{}) {
     constexpr int ES = static_cast<int>(sizeof(T)), EPW = 4 / ES;
     constexpr int PIX = kW2Pixels / kW2Threads;         // 8 pixels per thread and plane
     constexpr int SLOTS = PIX / EPW;                     // words per thread and plane
@@ -1549,7 +1576,10 @@ rewarp_wide2_kernel(const RewarpArgs a, T* __restrict__ out) {
         const int p1 = (((k + 1) / EPW) * kW2Threads + tw) * EPW + ((k + 1) % EPW);
         idx[k >> 1] = static_cast<uint32_t>(map[p0]) | (static_cast<uint32_t>(map[p1]) << 16);
     }
-    uint32_t* o32 = reinterpret_cast<uint32_t*>(out + static_cast<int64_t>(b) * a.C * kW2Pixels) + tw;
+    uint32_t* o32 = DECODE ? nullptr : reinterpret_cast<uint32_t*>(out + static_cast<int64_t>(b) * a.C * kW2Pixels) + tw;
+    // (the [C][16] table of warp maxima takes the map's place: the map lives on in `idx` once the item loop starts, and
+    // the loop's first barrier separates its last read from the first write here; 64 planes x 16 warps x 8 bytes = 8 KB)
+    unsigned long long* s_best = reinterpret_cast<unsigned long long*>(map);
     for (int it = 0; it < nitems; ++it) {
         cp_async_wait<RING - 2>();   // this thread's copies of item `it` have landed ...
         __syncthreads();                // ... everybody's have, and everybody is done with item it-1
@@ -1560,7 +1590,8 @@ rewarp_wide2_kernel(const RewarpArgs a, T* __restrict__ out) {
         for (int g = 0; g < G; ++g) {
             if (it * G + g < a.C) {
                 const uint8_t* bytes = base + g * PITCH;
-                uint32_t* o = o32 + static_cast<int64_t>(it * G + g) * WORDS;
+                uint32_t* o = DECODE ? nullptr : o32 + static_cast<int64_t>(it * G + g) * WORDS;
+                float vals[DECODE ? PIX : 1];   // DECODE: this thread's eight gathered values, in ascending output pixel
 #pragma unroll
                 for (int sl = 0; sl < SLOTS; ++sl) {   // the values are moved, never converted
                     uint32_t w32;
@@ -1571,12 +1602,62 @@ rewarp_wide2_kernel(const RewarpArgs a, T* __restrict__ out) {
                         const uint32_t hi = *reinterpret_cast<const uint16_t*>(bytes + (idx[sl] >> 16));
                         w32 = lo | (hi << 16);
                     }
-                    o[sl * kW2Threads] = w32;
+                    if constexpr (DECODE) {
+#pragma unroll
+                        for (int e = 0; e < EPW; ++e) vals[sl * EPW + e] = word_value<T>(w32, e);
+                    } else {
+                        o[sl * kW2Threads] = w32;
+                    }
+                }
+                if constexpr (DECODE) {
+                    // one NaN-propagating max per pixel, then the FIRST pixel that equals it (floating == ties -0.0
+                    // with +0.0; a NaN maximum matches the first NaN) — the per-pixel 64-bit keys of the first version
+                    // doubled the kernel's instruction count (42.7 us at C5 against 31.8 for the plain gather)
+                    float m = vals[0];
+#pragma unroll
+                    for (int q = 1; q < PIX; ++q) m = fmax_nan(m, vals[q]);
+                    const bool m_nan = m != m;
+                    int first = PIX - 1;
+#pragma unroll
+                    for (int q = PIX - 2; q >= 0; --q) first = (vals[q] == m || (m_nan && vals[q] != vals[q])) ? q : first;
+                    const uint32_t p = static_cast<uint32_t>(((first / EPW) * kW2Threads + tw) * EPW + (first % EPW));   // its output pixel
+                    unsigned long long best = warp_max_u64(pack_arg(order_key(m), p));
+                    if ((threadIdx.x & 31) == 0) s_best[(it * G + g) * (kW2Threads / 32) + (threadIdx.x >> 5)] = best;
                 }
             }
         }
     }
     cp_async_wait<0>();
+    if constexpr (DECODE) {
+        __syncthreads();
+        if (static_cast<int>(threadIdx.x) < a.C) {
+            unsigned long long best = 0ull;
+#pragma unroll
+            for (int w = 0; w < kW2Threads / 32; ++w) {
+                const unsigned long long v = s_best[threadIdx.x * (kW2Threads / 32) + w];
+                best = v > best ? v : best;
+            }
+            // the outputs of decode_kernel (decode.cu), for plane b * C + c
+            const int64_t plane = static_cast<int64_t>(b) * a.C + threadIdx.x;
+            const uint32_t pidx = arg_idx(best);
+            const float mv = key_value(arg_key(best));
+            const int ix = static_cast<int>(pidx % static_cast<uint32_t>(a.W)), iy = static_cast<int>(pidx / static_cast<uint32_t>(a.W));
+            const bool positive = mv > 0.0f;   // false for NaN, like np.greater / torch.gt
+            if (dec.idx) dec.idx[plane] = static_cast<int32_t>(pidx);
+            if (dec.preds) {
+                dec.preds[2 * plane] = positive ? static_cast<float>(ix) : 0.0f;
+                dec.preds[2 * plane + 1] = positive ? static_cast<float>(iy) : 0.0f;
+            }
+            dec.maxvals_f32[plane] = mv;
+            if (dec.position) { dec.position[2 * plane] = ix; dec.position[2 * plane + 1] = iy; }
+            if (dec.conf_table) dec.conf_table[plane] = (mv >= dec.occlude_thresh) ? 1 : 0;
+        }
+        __syncthreads();   // every writer is done before thread 0 fences and takes the ticket (fence cumulativity, as in pck_tma_kernel)
+        // train_human.py:427-430 in the same launch: the CTA that finishes last selects the k-th activation; the
+        // staging ring is idle by now and caches the batch's values
+        if (dec.sel.ticket != nullptr && last_block_done(dec.sel.ticket, gridDim.x))
+            select_body(dec.maxvals_f32, a.B * a.C, dec.sel, reinterpret_cast<float*>(smem), RING * STAGE / 4);
+    }
 }
 
 // general route (any plane up to 25600 px): gradient gathered from global memory.
@@ -1882,6 +1963,50 @@ extern "C" int udape_rewarp_fwd(const void* const* in, const float* const* theta
 extern "C" int64_t udape_rewarp_plan_elems(int64_t H, int64_t W, int elem_bytes) {
     if (H <= 0 || W <= 0 || (elem_bytes != 2 && elem_bytes != 4)) return 0;
     return rank_route_words(H, W, elem_bytes) ? plan_elems_for(H * W) : 0;
+}
+
+extern "C" int udape_rewarp_decode_select(const void* in, const float* theta, int stages, int half_mask, int grid_dtype,
+                                          int64_t B, int64_t C, int64_t H, int64_t W, int dtype, int32_t* idx, float* preds,
+                                          float* maxvals_f32, int64_t* position, float occlude_thresh, uint8_t* conf_table,
+                                          int64_t kth, const float* tea_mask_in, float* thresh_out, uint8_t* tea_mask_out,
+                                          uint32_t* ticket, void* stream) {
+    RewarpArgs a = {};
+    UDAPE_REQUIRE(in && theta && maxvals_f32, UDAPE_ERR_NULL, "udape_rewarp_decode_select: NULL pointer (in, theta and maxvals_f32 are required)");
+    const int rc = fill_common(a, "udape_rewarp_decode_select", 1, stages, half_mask, grid_dtype, B, C, H, W, dtype);
+    if (rc) return rc;
+    const int es = dtype_size(dtype);
+    UDAPE_REQUIRE(aligned16(in) && aligned_to(theta, 4) && aligned_to(maxvals_f32, 4) && (!idx || aligned_to(idx, 4)) &&
+                      (!preds || aligned_to(preds, 4)) && (!position || aligned_to(position, 8)) &&
+                      (!ticket || aligned_to(ticket, 4)) && (!thresh_out || aligned_to(thresh_out, 4)) &&
+                      (!tea_mask_in || aligned_to(tea_mask_in, 4)),
+                  UDAPE_ERR_ALIGN, "udape_rewarp_decode_select: misaligned pointer (the planes need 16-byte alignment)");
+    // the fused route is the second-generation wide kernel: planes of exactly 4096 pixels, rows a power-of-two number of
+    // 16-byte chunks, at most kW2DecodeMaxC planes per sample.  Anything else: udape_rewarp_fwd + udape_decode_select.
+    const int64_t cpr = W * es / 16;
+    UDAPE_REQUIRE(H * W == kW2Pixels && (W * es) % 16 == 0 && cpr >= 1 && (cpr & (cpr - 1)) == 0 && C <= kW2DecodeMaxC,
+                  UDAPE_ERR_SHAPE, "udape_rewarp_decode_select: needs planes of 4096 pixels with power-of-two rows and C <= %d "
+                  "(got C=%lld H=%lld W=%lld): call udape_rewarp_fwd and udape_decode_select", kW2DecodeMaxC, (long long)C,
+                  (long long)H, (long long)W);
+    UDAPE_REQUIRE(kth >= 0 && kth <= B * C, UDAPE_ERR_ARG, "udape_rewarp_decode_select: kth=%lld outside [0,%lld] (0 = no select)",
+                  (long long)kth, (long long)(B * C));
+    UDAPE_REQUIRE(kth == 0 || ticket, UDAPE_ERR_NULL, "udape_rewarp_decode_select: the select needs a ticket");
+    a.view[0].in = in;
+    a.view[0].theta = theta;
+    RewarpDecodeOut dec = {};
+    dec.idx = idx; dec.preds = preds; dec.maxvals_f32 = maxvals_f32; dec.position = position; dec.conf_table = conf_table;
+    dec.occlude_thresh = occlude_thresh;
+    dec.sel = SelectArgs{static_cast<int>(kth), tea_mask_in, thresh_out, tea_mask_out, kth > 0 ? ticket : nullptr, 0};
+    cudaStream_t st = as_stream(stream);
+    UDAPE_DISPATCH_FLOAT(dtype, T, {
+        constexpr int G = sizeof(T) == 2 ? 4 : 2;
+        constexpr int RING = 3;
+        const size_t smem = static_cast<size_t>(RING) * G * (kW2Pixels * sizeof(T) + 16) + sizeof(uint16_t) * kW2Pixels;
+        const int r2 = reserve_smem(rewarp_wide2_kernel<T, G, RING, true>, smem, "udape_rewarp_decode_select");
+        if (r2) return r2;
+        a.tile_log2 = wide2_tile_log2(W, es);
+        rewarp_wide2_kernel<T, G, RING, true><<<static_cast<unsigned>(B), kW2Threads, smem, st>>>(a, nullptr, dec);
+    });
+    return check_launch("udape_rewarp_decode_select");
 }
 
 extern "C" int udape_rewarp_bwd(const void* grad_out, const float* theta, int stages, int half_mask, int grid_dtype,

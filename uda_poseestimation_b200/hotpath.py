@@ -31,7 +31,7 @@ from .adain import adain_mix, adain_mix_multi
 from .ema import OldWeightEMA
 from .keypoint_detection import _pck
 from .loss import cons_loss, fused_losses, joints_mse_loss
-from .mask import teacher_targets
+from .mask import teacher_targets, teacher_targets_rewarped
 
 __all__ = ["StepInputs", "HotPathStep", "step_algorithmic_bytes", "ScalarFeed", "ReplicatedTail", "PeerTail"]
 
@@ -185,12 +185,14 @@ class StepInputs:
         return list(self.y_t_tea) if isinstance(self.y_t_tea, (list, tuple)) else [self.y_t_tea]
 
 
-def step_algorithmic_bytes(inp: StepInputs, n_params: int, param_bytes: int = 4, fused: bool = True, tail=None) -> dict:
+def step_algorithmic_bytes(inp: StepInputs, n_params: int, param_bytes: int = 4, fused: bool = True, tail=None,
+                           fuse_teacher_decode: bool = False) -> dict:
     """Algorithmic HBM bytes of one step, per kernel family.
 
     ``fused=True`` is the default step (one loss launch, rectified teacher map evaluated on the fly);
     ``fused=False`` the operator-by-operator sequence (separate fwd/bwd launches, materialised map).
-    ``tail``: the ReplicatedTail / PeerTail of the step (its kernels replace the bare EMA pass)."""
+    ``tail``: the ReplicatedTail / PeerTail of the step (its kernels replace the bare EMA pass).
+    ``fuse_teacher_decode``: the teacher re-warp is arg-maxed where it is gathered (one read, no map written or re-read)."""
     ef = inp.feat_src.element_size()
     feat = inp.feat_src.numel() * ef
     tea0 = inp.teacher_views[0]
@@ -220,7 +222,11 @@ def step_algorithmic_bytes(inp: StepInputs, n_params: int, param_bytes: int = 4,
         out["cons_bwd"] = hm * (e_s + e_t) + hm * e_s
     if inp.theta_tea is not None:
         k_views = len(inp.teacher_views)
-        out["rewarp_teacher"] = (k_views + 1) * hm * e_t + 72 * k_views * tea0.shape[0]   # k reads + 1 write (+ the stage tables)
+        if fuse_teacher_decode and fused and k_views == 1:
+            out["rewarp_teacher+decode"] = hm * e_t + 72 * tea0.shape[0] + 40 * planes    # one read; the map is never written
+            del out["decode"]
+        else:
+            out["rewarp_teacher"] = (k_views + 1) * hm * e_t + 72 * k_views * tea0.shape[0]   # k reads + 1 write (+ the stage tables)
     if inp.theta_stu is not None:
         out["rewarp_student_fwd"] = 2 * hm * e_s + 72 * inp.y_t_stu.shape[0]
         out["rewarp_student_bwd"] = 2 * hm * e_s + 72 * inp.y_t_stu.shape[0]   # grad read + grad write
@@ -235,7 +241,8 @@ class HotPathStep:
                  occlude_thresh: float = 0.9, teacher_alpha: float = 0.999, lambda_c: float = 1.0,
                  loss_scale: float = 65536.0, parallel: bool = True, fused: bool = True,
                  ema_parallel: bool = True, counts_hook=None, tail=None, ema: OldWeightEMA | None = None,
-                 occlude_rate: float = 0.5, occlude_size: int = 10, image_size: int = 256, rng=None):
+                 occlude_rate: float = 0.5, occlude_size: int = 10, image_size: int = 256, rng=None,
+                 fuse_teacher_decode: bool = False):
         self.sigma, self.mask_ratio, self.occlude_thresh = sigma, mask_ratio, occlude_thresh
         self.lambda_c, self.loss_scale = lambda_c, loss_scale
         self.parallel, self.fused, self.ema_parallel = parallel, fused, ema_parallel
@@ -245,6 +252,9 @@ class HotPathStep:
         self.counts_hook = counts_hook
         self.occlude_rate, self.occlude_size, self.image_size = occlude_rate, occlude_size, image_size
         self.rng = rng          # np.random-like stream of the occlusion draws (None: numpy's global one, as the reference)
+        # one teacher view + the fused loss step: the re-warped teacher map is only ever decoded, so the teacher chain is ONE
+        # launch that arg-maxes the planes where it gathers them (rewarp.gather_decode) and out["y_t_tea_recon"] is None
+        self.fuse_teacher_decode = fuse_teacher_decode
         self._side = None
         # tail: what follows backward — None: the bare EMA (:438, the student update left to torch);
         # ReplicatedTail / PeerTail: gradient exchange + unscale + Adam | SGD + EMA (:436-438)
@@ -330,9 +340,12 @@ class HotPathStep:
                     self.ema.step()
                     self._mark("ema done")
         # teacher forward; student forward + inverse plan + backward
+        tea_one_launch = (self.fuse_teacher_decode and self.fused and inp.theta_tea is not None and len(inp.teacher_views) == 1
+                          and _rewarp.gather_decode_supported(inp.teacher_views[0]))
         self.rewarp_kernels = ((1 if inp.theta_tea is not None else 0)
                                + ((3 if _rewarp.USE_INVERSE_PLAN else 2) if inp.theta_stu is not None else 0)
-                               + (1 if inp.x_t_stu is not None else 0))
+                               + (1 if inp.x_t_stu is not None else 0)
+                               - (1 if tea_one_launch else 0))      # teacher re-warp + decode + select: one launch
         # the student's grids are built under autocast (:414): every stage samples on a half grid
         stu_half = inp.y_t_stu.dtype in (torch.float16, torch.bfloat16)
         stu_mask = (1 << inp.theta_stu.shape[1]) - 1 if (inp.theta_stu is not None and stu_half) else 0
@@ -365,7 +378,15 @@ class HotPathStep:
             with torch.no_grad():
                 views = inp.teacher_views
                 y_t_tea = views[0]
-                if inp.theta_tea is not None:
+                tt = None
+                if tea_one_launch:
+                    # :359-383 and :427-430 in one launch; the map itself is never written
+                    self._mark("tea gather start")
+                    tt = teacher_targets_rewarped(views[0], inp.theta_tea if torch.is_tensor(inp.theta_tea) else inp.theta_tea[0],
+                                                  self.sigma, self.mask_ratio, occlude_thresh=self.occlude_thresh)
+                    y_t_tea = None
+                    self._mark("tea gather done")
+                elif inp.theta_tea is not None:
                     # :359-372 — every teacher view warped back to the un-augmented frame, mean over the k views
                     self._mark("tea gather start")
                     if len(views) == 1:
@@ -376,8 +397,9 @@ class HotPathStep:
                 elif len(views) > 1:
                     raise ValueError("k teacher views need their re-warp tables (theta_tea: one per view)")
                 # train_human.py:376-383 and :427-430 — one decode pass + k-th value select
-                tt = teacher_targets(y_t_tea, self.sigma, self.mask_ratio, occlude_thresh=self.occlude_thresh,
-                                     materialise=not self.fused)
+                if tt is None:
+                    tt = teacher_targets(y_t_tea, self.sigma, self.mask_ratio, occlude_thresh=self.occlude_thresh,
+                                         materialise=not self.fused)
                 self._mark("decode+mask done")
                 x_t_stu_occ = None
                 if inp.x_t_stu is not None and not torch.cuda.is_current_stream_capturing():
@@ -385,7 +407,7 @@ class HotPathStep:
                     # student network runs on the result).  conf_table / position go to the host for the reference's
                     # np.random draws, so this stage exists in eager runs only; a captured step ends before it.
                     x_t_stu_occ = _rewarp.occlude_keypoints(inp.x_t_stu, tt["conf_table"], tt["position"], inp.aug_param_stu,
-                                                            self.image_size / y_t_tea.shape[-1], self.occlude_rate,
+                                                            self.image_size / views[0].shape[-1], self.occlude_rate,
                                                             self.occlude_size, self.image_size,
                                                             **({"rng": self.rng} if self.rng is not None else {}))
                 if recon_ready is not None:

@@ -25,7 +25,7 @@ import torch
 from . import _lib
 from .keypoint_detection import decode
 
-__all__ = ["confidence_mask", "consistency_mask", "teacher_targets"]
+__all__ = ["confidence_mask", "consistency_mask", "teacher_targets", "teacher_targets_rewarped"]
 
 
 def confidence_mask(hm: torch.Tensor, occlude_thresh: float):
@@ -84,6 +84,32 @@ def teacher_targets(hm: torch.Tensor, sigma, mask_ratio: float, occlude_thresh: 
     mask, thresh = r["tea_mask"], r["mask_thresh"]
     out = {"activates": act, "preds": r["preds"], "rectified": r.get("rectified"), "tea_mask": mask,
            "mask_thresh": thresh}
+    if occlude_thresh is not None:
+        out.update(conf=act, position=r["position"], conf_table=r["conf_table"])
+    return out
+
+
+def teacher_targets_rewarped(y_t_tea: torch.Tensor, theta: torch.Tensor, sigma, mask_ratio: float,
+                             occlude_thresh: float | None = None, tea_mask: torch.Tensor | None = None) -> dict:
+    """``teacher_targets(gather(y_t_tea, theta), ..., materialise=False)`` — the whole teacher chain of the step for ONE
+    teacher view (train_human.py:359-372, :376-383, :427-430) — in one launch where ``rewarp.gather_decode`` has one
+    (64 x 64 heatmaps), in two otherwise.  The re-warped teacher map is only ever decoded, so it is not written:
+    ``y_t_tea_recon`` is ``None`` in the result (``gather`` it when it is wanted).  Same keys as
+    :func:`teacher_targets` otherwise, ``rectified`` is ``None`` (``fused_losses(..., tea_preds=preds, sigma=sigma)``)."""
+    from . import rewarp as _rewarp
+
+    y = y_t_tea.detach()
+    if not _rewarp.gather_decode_supported(y.contiguous()):
+        out = teacher_targets(_rewarp.gather(y, theta), sigma, mask_ratio, occlude_thresh=occlude_thresh, tea_mask=tea_mask,
+                              materialise=False)
+        out["y_t_tea_recon"] = None
+        return out
+    kth = int(mask_ratio * y.shape[0] * y.shape[1])   # train_human.py:429
+    r = _rewarp.gather_decode(y, theta, want_preds=True, want_position=occlude_thresh is not None,
+                              occlude_thresh=occlude_thresh, select_kth=kth, select_tea_mask=tea_mask)
+    act = r["maxvals_f32"]
+    out = {"activates": act, "preds": r["preds"], "rectified": None, "tea_mask": r["tea_mask"],
+           "mask_thresh": r["mask_thresh"], "y_t_tea_recon": None}
     if occlude_thresh is not None:
         out.update(conf=act, position=r["position"], conf_table=r["conf_table"])
     return out

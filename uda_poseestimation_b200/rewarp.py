@@ -33,7 +33,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["inverse_affine_matrix", "recon_stages", "stage_table", "gather", "gather_views", "gather_backward", "inverse_plan_buffer", "student_recon", "teacher_recon",
+__all__ = ["inverse_affine_matrix", "recon_stages", "stage_table", "gather", "gather_views", "gather_decode", "gather_decode_supported", "gather_backward", "inverse_plan_buffer", "student_recon", "teacher_recon",
            "affine_nearest", "occlusion_plan", "occlude_keypoints"]
 
 
@@ -244,6 +244,70 @@ def gather(y: torch.Tensor, theta: torch.Tensor, half_mask: int = 0, grid_dtype:
     if y.requires_grad and torch.is_grad_enabled():
         return _Rewarp.apply(y, theta, half_mask, grid_code)
     return _launch_fwd([y], [theta], half_mask, grid_code, torch.empty_like(y), plan=plan)
+
+
+def gather_decode_supported(y: torch.Tensor) -> bool:
+    """Whether :func:`gather_decode` has a fused launch for ``y``: planes of exactly 4096 pixels whose rows are a
+    power-of-two number of 16-byte chunks, at most 64 planes per sample (``udape_rewarp_decode_select``)."""
+    if y.dim() != 4 or not y.is_cuda or y.dtype not in _lib._DTYPE_CODE:
+        return False
+    _, c, h, w = y.shape
+    row = w * y.element_size()
+    cpr = row // 16
+    return h * w == 4096 and row % 16 == 0 and cpr >= 1 and (cpr & (cpr - 1)) == 0 and c <= 64 and y.data_ptr() % 16 == 0
+
+
+def gather_decode(y: torch.Tensor, theta: torch.Tensor, half_mask: int = 0, grid_dtype: torch.dtype | None = None, *,
+                  want_idx: bool = False, want_preds: bool = True, want_position: bool = False,
+                  occlude_thresh: float | None = None, select_kth: int | None = None,
+                  select_tea_mask: torch.Tensor | None = None) -> dict:
+    """``decode(gather(y, theta))`` without the re-warped map: one launch (``udape_rewarp_decode_select``) that
+    arg-maxes every plane where it is gathered — the teacher chain of the step (train_human.py:359-372 feeding
+    :376-383 and :427-430), whose re-warped map is only ever decoded.  Bit-identical to the two calls.  Keys as
+    :func:`keypoint_detection.decode`: ``maxvals_f32`` float32[B,K] always, ``idx`` / ``preds`` / ``position`` /
+    ``conf_table`` on request, ``tea_mask`` + ``mask_thresh`` with ``select_kth`` (1-based rank, train_human.py:429).
+    Raises ``ValueError`` for shapes without a fused launch (see :func:`gather_decode_supported`)."""
+    dev = _lib.require_cuda(y, theta, select_tea_mask)
+    _check_theta(y, theta)
+    _lib.no_autograd("gather_decode", y)
+    y = y.detach().contiguous()
+    theta = theta.contiguous()
+    if not gather_decode_supported(y):
+        raise ValueError(f"gather_decode: no fused launch for planes {tuple(y.shape)} {y.dtype}; use gather() then decode()")
+    b, k, h, w = y.shape
+    planes = b * k
+    grid_code = _lib._DTYPE_CODE[grid_dtype] if grid_dtype is not None else _lib.F16
+    idx = torch.empty((b, k), dtype=torch.int32, device=dev) if want_idx else None
+    preds = torch.empty((b, k, 2), dtype=torch.float32, device=dev) if want_preds else None
+    mv32 = torch.empty((b, k), dtype=torch.float32, device=dev)
+    pos = torch.empty((b, k, 2), dtype=torch.int64, device=dev) if want_position else None
+    conf = torch.empty((b, k), dtype=torch.bool, device=dev) if occlude_thresh is not None else None
+    if occlude_thresh is not None and y.dtype != torch.float32:
+        occlude_thresh = float(torch.tensor(float(occlude_thresh), dtype=y.dtype))   # torch compares in the tensor's dtype
+    kth, tm_in, tea_mask, thresh = 0, None, None, None
+    if select_kth is not None:
+        if not (1 <= select_kth <= planes):
+            raise IndexError(f"kthvalue(): selected number k out of range for dimension 0 (k={select_kth}, n={planes})")
+        kth = int(select_kth)
+        if select_tea_mask is not None:
+            if select_tea_mask.numel() != planes:
+                raise ValueError("gather_decode: select_tea_mask must have one entry per (b, k)")
+            tm_in = select_tea_mask.detach().to(torch.float32).contiguous()
+        tea_mask = torch.empty((b, k), dtype=torch.bool, device=dev)
+        thresh = torch.empty((), dtype=torch.float32, device=dev)
+    with _lib.on_device(dev):
+        st = _lib.load().udape_rewarp_decode_select(
+            y.data_ptr(), theta.data_ptr(), theta.shape[1], int(half_mask), grid_code, b, k, h, w, _lib.float_code(y),
+            _lib.ptr(idx), _lib.ptr(preds), mv32.data_ptr(), _lib.ptr(pos),
+            float(occlude_thresh if occlude_thresh is not None else 0.0), _lib.ptr(conf), kth, _lib.ptr(tm_in),
+            _lib.ptr(thresh), _lib.ptr(tea_mask), _lib.ticket(dev) if kth else None, _lib.stream_ptr(dev))
+    _lib.check(st, "gather_decode")
+    out = {"maxvals_f32": mv32}
+    for name, t in (("idx", idx), ("preds", preds), ("position", pos), ("conf_table", conf), ("tea_mask", tea_mask),
+                    ("mask_thresh", thresh)):
+        if t is not None:
+            out[name] = t
+    return out
 
 
 def gather_views(views: Sequence[torch.Tensor], thetas: Sequence[torch.Tensor], half_mask: int = 0,
