@@ -51,7 +51,8 @@ __device__ __forceinline__ void select_body(const float* __restrict__ act, int n
         __syncthreads();
         const unsigned prefix = s_prefix, mask = s_mask;
         // (Same-address shared-memory atomics are not what this pass waits for: aggregating the lanes of a warp per
-        // bin with match.any made the select 70 % slower — 8.8 -> 14.8 us at C5 — profiles/r02ao.)
+        // bin made the select SLOWER both ways it was tried — with match.any 8.8 -> 14.8 us at C5 (profiles/r02ao), with
+        // two rounds of ballot + leader add 7.7 -> 13.0 us (profiles/r02bc).)
         if (cached) {
 #pragma unroll 2
             for (int i = threadIdx.x; i < n; i += nthreads) {
