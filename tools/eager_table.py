@@ -134,6 +134,18 @@ def main():
     row("teacher re-warp (3 x tF.affine)", "train_human.py:359-372", rshape + " f32", lambda: R.teacher_recon([tea_r], [aug_t], 4.0),
         lambda: U.teacher_recon([tea_r], [aug_t], 4.0), ref_reps=2, note="reference: per-sample loop, CPU staging tensor")
 
+    from uda_poseestimation_b200 import rewarp as RW
+    theta_t = RW.stage_table(RW.recon_stages(aug_t, 4.0, rb), 64, 64, torch.float32, None)[0].to(dev)
+
+    def ref_chain():     # :359-372 then :376-383 and :427-430 on the re-warped map
+        rec = R.teacher_recon([tea_r], [aug_t], 4.0)
+        R.confidence_mask(rec, 0.9)
+        R.consistency_mask(rec, 0.5)
+
+    row("teacher chain: re-warp -> conf / position / kth-mask", "train_human.py:359-383,427-430", rshape + " f32", ref_chain,
+        lambda: U.teacher_targets_rewarped(tea_r, theta_t, sigma, 0.5, occlude_thresh=0.9), ref_reps=2,
+        note="this package: ONE launch, the re-warped map is never written")
+
     def ref_stu():
         y = stu_r.detach().requires_grad_(True)
         with torch.autocast("cuda", dtype=torch.float16):
