@@ -297,3 +297,47 @@ def test_old_weight_ema_is_constructible_before_the_models_move_to_the_gpu():
     assert ema.target_params[0] is next(teacher.parameters())      # the live Parameter objects (they survive .cuda())
     with pytest.raises(RuntimeError, match="CUDA-only"):
         ema.step()                                                  # no CPU fallback for the operator itself
+
+
+def test_step_bytes_with_the_teacher_chain_in_one_launch():
+    """hotpath.step_algorithmic_bytes: with the teacher re-warp arg-maxed where it is gathered the step loses the map's
+    write and its re-read by the decode (2 x B*K*H*W*4 bytes); k > 1 views or the unfused losses keep both launches."""
+    from uda_poseestimation_b200.hotpath import StepInputs, step_algorithmic_bytes
+    b, k = 4, 3
+    hm32 = lambda: torch.zeros(b, k, 64, 64)
+    f = torch.zeros(2, 8, 32, 32)
+    one = torch.zeros(1)
+    inp = StepInputs(f, f, f, f, hm32().half(), hm32().half(), hm32(), hm32(), torch.ones(b, k, 1), one, one,
+                     theta_tea=torch.zeros(b, 3, 6), theta_stu=torch.zeros(b, 3, 6))
+    two = step_algorithmic_bytes(inp, 1000, fused=True)
+    fused = step_algorithmic_bytes(inp, 1000, fused=True, fuse_teacher_decode=True)
+    assert two["total"] - fused["total"] == 2 * b * k * 64 * 64 * 4
+    assert "decode" not in fused and "rewarp_teacher" not in fused and "rewarp_teacher+decode" in fused
+    assert step_algorithmic_bytes(inp, 1000, fused=False, fuse_teacher_decode=True) == step_algorithmic_bytes(inp, 1000, fused=False)
+    inp.y_t_tea, inp.theta_tea = [hm32(), hm32()], [torch.zeros(b, 3, 6)] * 2
+    assert step_algorithmic_bytes(inp, 1000, fuse_teacher_decode=True) == step_algorithmic_bytes(inp, 1000)
+
+
+def test_gather_decode_support_predicate_and_argument_errors():
+    """rewarp.gather_decode_supported is pure host logic; the fused entry point rejects what it has no launch for
+    through the C-ABI's error codes (no GPU needed: the checks run before any launch)."""
+    import ctypes
+    from uda_poseestimation_b200 import _lib, rewarp as RW
+    assert not RW.gather_decode_supported(torch.zeros(2, 3, 64, 64))            # CPU tensor
+    assert not RW.gather_decode_supported(torch.zeros(2, 3, 64))                 # not [B,C,H,W]
+    lib = _lib.load()
+    buf = (ctypes.c_float * 64)()
+    addr = (ctypes.addressof(buf) + 15) & ~15                                      # a 16-byte aligned (host) address: never dereferenced
+    args = dict(stages=3, half_mask=0, grid=_lib.F16, B=2, C=3, H=64, W=64, dtype=_lib.F32)
+    def call(**kw):
+        a = dict(args, **kw)
+        return lib.udape_rewarp_decode_select(addr, addr, a["stages"], a["half_mask"], a["grid"], a["B"], a["C"], a["H"], a["W"],
+                                              a["dtype"], None, None, addr, None, 0.9, None, a.get("kth", 0), None, None, None,
+                                              a.get("ticket"), None)
+    assert call(H=32, W=32) < 0                                                   # planes of 1024 pixels: UDAPE_ERR_SHAPE
+    assert call(C=65) < 0                                                         # more planes than the maxima table holds
+    assert call(kth=7) < 0 and call(kth=3, ticket=None) < 0                       # kth outside [0, B*C]; a select without a ticket
+    assert call(stages=5) < 0
+    msg = ctypes.create_string_buffer(256)
+    lib.udape_last_error(msg, 256)
+    assert b"stages" in msg.value
