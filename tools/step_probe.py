@@ -33,13 +33,16 @@ def main():
     student = B.ParamBag(S.parameter_list(shapes, 7, device=dev))
     teacher = B.ParamBag([torch.empty_like(p) for p in student.parameters()])
 
-    def timeline(title, **kw):
+    def timeline(title, models=None, **kw):
         inp = StepInputs(feat_src=d["feat_src"], feat_tgt_ori=d["feat_tgt_ori"], feat_tgt_tea=d["feat_tgt_tea"],
                          feat_src_ori=d["feat_src_ori"], y_s=d["y_s"], y_t_stu=d["y_t_stu"], y_t_tea=d["y_t_tea"],
                          label_s=label, weight_s=weight, alpha_s2t=alpha[0:1], alpha_t2s=alpha[1:2],
                          theta_tea=t_tea.to(dev), theta_stu=t_stu.to(dev))
-        step = HotPathStep(teacher, student, sigma=cfg["sigma"], **kw)
+        tea_m, stu_m = models if models is not None else (teacher, student)
+        step = HotPathStep(tea_m, stu_m, sigma=cfg["sigma"], **kw)
         step.marks = []
+        if kw.get("tail") is not None:
+            kw["tail"].mark = step._mark
         step.capture(inp, include_ema=True, warmup=2)
         acc = {}
         n = 20
@@ -53,9 +56,21 @@ def main():
         for name, ts in sorted(acc.items(), key=lambda kv: np.median(kv[1][3:])):
             print(f"   {name:<22}{np.median(ts[3:]):8.1f}")
 
+    def adam_tail():
+        # the bench's default step: grad check -> unscale + Adam + EMA on the tail stream (bench.Variant, kind "replicated")
+        from uda_poseestimation_b200.hotpath import ReplicatedTail
+        stu = B.ParamBag(S.parameter_list(shapes, 1234 + 6, device=dev))
+        tea = B.ParamBag([p.detach().clone() for p in stu.parameters()])
+        tail = ReplicatedTail(stu, U.OldWeightEMA(tea, stu, alpha=0.999), algo="adam", loss_scale=B.LOSS_SCALE, lr=B.LR)
+        for p, g in zip(stu.parameters(), B.synthetic_grads(shapes, 1234 + 9)):
+            p.grad.copy_(g.to(dev))
+        return dict(tail=tail, loss_scale=B.LOSS_SCALE), tea, stu
+
     if os.environ.get("PROBE_TIMELINE", "1") == "1":
         timeline("full step")
         timeline("EMA serial after the join", ema_parallel=False)
+        kw, tea2, stu2 = adam_tail()
+        timeline("Adam tail in the step (teacher chain as one launch)", models=(tea2, stu2), fuse_teacher_decode=True, **kw)
 
     def variant(name, ema=True, rewarp=True, skip=(), ema_parallel=True):
         inp = StepInputs(feat_src=d["feat_src"], feat_tgt_ori=d["feat_tgt_ori"], feat_tgt_tea=d["feat_tgt_tea"],

@@ -77,6 +77,7 @@ class ReplicatedTail:
         self.n_params = self.bucket.flat.numel()
         self.scale = torch.full((), float(loss_scale), dtype=torch.float32, device=self.bucket.flat.device)
         self.kernels = 2   # grad_check + student_step (the NCCL kernel is the library's, not counted)
+        self.mark = None   # profiling only: HotPathStep._mark of the step that records a timeline
 
     @property
     def found_inf(self):
@@ -89,6 +90,8 @@ class ReplicatedTail:
     def finish(self, counts=None):
         # (the PCK counts of this tail travel by ncclAllReduce from the PCK chain: HotPathStep.counts_hook)
         self.opt.grad_scale, self.opt.found_inf = self.scale, self.opt.check_grads()
+        if self.mark is not None:
+            self.mark("grad check done")      # profiling only (tools/step_probe.py)
         self.opt.step()
         self.ema._fused_pending = False   # tea_optimizer.step() is not called separately by the assembled step
 
@@ -301,7 +304,8 @@ class HotPathStep:
             on = os.environ.get("UDAPE_STEP_PRIORITY", "1") == "1"
             hi = int(os.environ.get("UDAPE_CHAIN_PRIORITY", "-2")) if on else 0
             ad = int(os.environ.get("UDAPE_ADAIN_PRIORITY", "-1")) if on else 0
-            self._side = (torch.cuda.Stream(dev, priority=hi), torch.cuda.Stream(dev, priority=hi), torch.cuda.Stream(dev),
+            tl = int(os.environ.get("UDAPE_TAIL_PRIORITY", "0")) if on else 0
+            self._side = (torch.cuda.Stream(dev, priority=hi), torch.cuda.Stream(dev, priority=hi), torch.cuda.Stream(dev, priority=tl),
                           torch.cuda.Stream(dev, priority=hi), torch.cuda.Stream(dev, priority=ad))
         return self._side
 
@@ -474,6 +478,7 @@ class HotPathStep:
                 # rank meets its peers in one order)
                 if pck_done is not None:
                     s_ema.wait_event(pck_done)
+                self._mark("tail start")
                 self.tail.finish(counts if pck_done is not None else None)
                 self._mark("ema done")
         if s_adain is not cur:
