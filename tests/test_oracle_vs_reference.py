@@ -176,3 +176,30 @@ def test_bytecode_of_the_reference_loads_without_the_tree():
     env = dict(os.environ, UDAPE_REFERENCE_ROOT="/nonexistent-reference-root")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root, env=env)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
+
+
+def test_reference_bytecode_manifest(tmp_path, monkeypatch):
+    """oracle/build_ref.py: a second build with unchanged sources recompiles nothing; bytecode of another interpreter
+    version (a different magic number in the manifest) is not used."""
+    import json
+
+    from oracle import build_ref
+
+    if not ref_loader.source_available():
+        pytest.skip("needs the reference tree to compile from")
+    monkeypatch.setattr(build_ref, "OUT", tmp_path)
+    monkeypatch.setattr(ref_loader, "BYTECODE_ROOT", tmp_path)
+    assert build_ref.build(verbose=False) and ref_loader.bytecode_available()
+    names = sorted(p.name for p in tmp_path.iterdir())
+    assert names == sorted(["MANIFEST.json"] + [f"{n}.code" for n in ref_loader._FILES])
+    for p in tmp_path.iterdir():       # outputs only: marshalled code objects, no source text of the reference
+        assert b"def calc_mean_std(feat" not in p.read_bytes()
+    stamps = {p.name: p.stat().st_mtime_ns for p in tmp_path.glob("*.code")}
+    assert build_ref.build(verbose=False)
+    assert stamps == {p.name: p.stat().st_mtime_ns for p in tmp_path.glob("*.code")}
+    manifest = json.loads((tmp_path / "MANIFEST.json").read_text())
+    assert set(manifest["files"]) == set(ref_loader._FILES) and all(len(v["sha256"]) == 64 for v in manifest["files"].values())
+    manifest["magic"] = "00000000"
+    (tmp_path / "MANIFEST.json").write_text(json.dumps(manifest))
+    assert not ref_loader.bytecode_available()
+    assert build_ref.build(verbose=False) and ref_loader.bytecode_available()      # rebuilt for this interpreter
